@@ -162,7 +162,7 @@ class Recorder:
             r = o_sel(self_, threshold, max_number_matches, near_miss)
             rec.cur["selected"] = [[int(k), float(v)] for k, v in self_.matches.items()]
             rec.cur["rng_after_select"] = rng_digest()
-            rec.cur["user_matches"] = dict(self_.user_matches)
+            rec.cur["user_matches"] = [[k, v] for k, v in self_.user_matches.items()]  # ordered
             rec.cur["ref_clip_id"] = self_.ref_clip_id
             return r
 
