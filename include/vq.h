@@ -1,0 +1,154 @@
+/*
+ * vq.h — C ABI of libvq_b200: the B200-native match-scoring path of Video Query.
+ *
+ * The reference (PARC-projects/video-query-algorithms) is pure Python and has no FFI; its seam
+ * for this path is method dispatch on Ticket / TargetClip / Hyperparameter driven by
+ * compute_matches (reference src/models/compute_matches.py:8).  Each entry point below replaces
+ * the arithmetic of one reference method; the Python host layer (video_query_algorithms_b200/)
+ * binds them with ctypes and keeps the reference's method names and semantics.
+ *
+ * Conventions
+ *   - every function returns 0 on success, < 0 on error; vq_last_error() gives the text
+ *     (thread-local).  No C++ exception crosses this boundary.
+ *   - all buffers are caller-allocated and caller-owned; HOST pointers unless the name says _dev.
+ *   - a store is an opaque handle that owns one HBM-resident shard: clip-major rows of
+ *     n_streams * stream_len fp32 (stream_len = n_splits * dim), 16-byte aligned.
+ *   - rows are identified by GLOBAL row number = first_global_row + local row; lists come back
+ *     in ascending row order (= database order, which the reference's seeded sampling needs,
+ *     ticket.py:326-333).
+ *   - calls on one store must be serialised by the caller (the broker runs one job at a time,
+ *     broker.py:90-92) but may come from any thread: the library sets the device per call.
+ *   - `stream` arguments are a cudaStream_t passed as void*; NULL = the store's own stream.
+ */
+#ifndef VQ_B200_H
+#define VQ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VQ_MAX_STREAMS 4
+#define VQ_MAX_TOPK 1024
+#define VQ_ABI_VERSION 1
+
+typedef struct vq_store vq_store;
+
+/* ---------------------------------------------------------------- errors / environment */
+const char *vq_last_error(void);
+int vq_abi_version(void);
+int vq_device_count(int *count_out);
+
+/* ---------------------------------------------------------------- feature store (A2)
+ * Replaces Ticket._get_candidate_features (ticket.py:358-382): instead of pulling every feature
+ * row over HTTP per job, rows live in HBM for the life of the broker process.               */
+int vq_store_create(vq_store **out, int device, int64_t n_rows, int n_streams, int n_splits,
+                    int dim, int64_t first_global_row);
+int vq_store_destroy(vq_store *s);
+int vq_store_describe(const vq_store *s, int64_t *n_rows, int *n_streams, int *n_splits, int *dim,
+                      int64_t *first_global_row, int *device);
+/* rows: [n_rows][n_streams][n_splits][dim] fp32, local row range.  Pinned memory is copied
+ * asynchronously on the store's stream; the call returns after the copy has completed.       */
+int vq_store_upload(vq_store *s, int64_t first_row, int64_t n_rows, const float *rows);
+int vq_store_download(vq_store *s, int64_t first_row, int64_t n_rows, float *rows_out);
+/* 1 / (number of splits the clip actually has) per (row, stream); NULL restores "all present".
+ * Missing (row, stream, split) slots must be uploaded as zeros (ticket.py:155-157).          */
+int vq_store_set_split_weights(vq_store *s, const float *inv_counts /* [n_rows][n_streams] */);
+/* VQSYN-1 counter-based generator (oracle/synth.py is the CPU twin), fills the whole shard.  */
+int vq_store_fill_synthetic(vq_store *s, uint64_t seed, const float *stream_means);
+/* device base pointer of the shard (for zero-copy consumers such as bench.py)               */
+int vq_store_device_ptr(vq_store *s, void **rows_dev);
+
+/* ---------------------------------------------------------------- single-query scan (A3-A7)
+ * compute_similarities (ticket.py:120-163) + compute_scores (:165-180) + the two candidate
+ * scans of select_clips_to_review (:325-327) + ranking (:266), one pass over the shard.     */
+typedef struct vq_scan_params {
+    double weights[VQ_MAX_STREAMS]; /* w_s in stream order (ticket.py:176)                   */
+    double threshold;               /* match set  = { score >= threshold }                   */
+    double lower_limit;             /* near set   = { lower_limit <= score < threshold }     */
+    double eps;                     /* tie band   = |score - threshold| < eps or |score - lower_limit| < eps */
+    int32_t topk;                   /* 0..VQ_MAX_TOPK best rows (score desc, row asc)         */
+    int32_t want_sims;              /* also keep per-stream similarities [n_rows][n_streams] */
+} vq_scan_params;
+
+typedef struct vq_scan_counts {
+    int64_t n_match, n_near, n_tie;
+    int32_t n_topk;
+    float scan_ms;                  /* device time of the fused scan kernel (K1), CUDA events */
+} vq_scan_counts;
+
+/* target: [n_streams][n_splits][dim] fp32 HOST.  Synchronous: copies the target in, runs the
+ * scan and its selection kernels, copies the counts out.  Lists stay on the device until
+ * fetched.                                                                                   */
+int vq_scan(vq_store *s, const float *target, const vq_scan_params *p, vq_scan_counts *out);
+/* Same work, enqueued only: target already on the device, nothing copied back, no sync.
+ * Used for device-side timing and for multi-GPU merges that read the results in place.      */
+int vq_scan_enqueue(vq_store *s, const float *target_dev, const vq_scan_params *p, void *stream);
+int vq_scan_wait(vq_store *s, void *stream, vq_scan_counts *out);
+
+int vq_fetch_matches(vq_store *s, int64_t cap, int64_t *rows_out, float *scores_out);
+int vq_fetch_near(vq_store *s, int64_t cap, int64_t *rows_out, float *scores_out);
+int vq_fetch_ties(vq_store *s, int64_t cap, int64_t *rows_out, float *scores_out);
+int vq_fetch_topk(vq_store *s, int32_t cap, int64_t *rows_out, float *scores_out);
+int vq_fetch_scores(vq_store *s, int64_t first_row, int64_t n_rows, float *scores_out);
+int vq_fetch_sims(vq_store *s, int64_t first_row, int64_t n_rows, float *sims_out);
+
+/* device views of the last scan's results (valid until the next scan on this store)         */
+typedef struct vq_scan_device_view {
+    const float *scores_dev;        /* [n_rows]                                               */
+    const float *sims_dev;          /* [n_rows][n_streams] or NULL                            */
+    const int64_t *counts_dev;      /* [4] = n_match, n_near, n_tie, n_topk                   */
+    const float *topk_scores_dev;   /* [VQ_MAX_TOPK], -inf padded                             */
+    const int64_t *topk_rows_dev;   /* [VQ_MAX_TOPK] GLOBAL rows, -1 padded                   */
+    const uint32_t *match_rows_dev; /* [n_match] LOCAL rows ascending                         */
+    const uint32_t *near_rows_dev;  /* [n_near]                                               */
+} vq_scan_device_view;
+int vq_scan_view(vq_store *s, vq_scan_device_view *out);
+
+/* Multi-GPU merge (the one collective of the path).  After a scan, each rank's payload
+ * [4 + 2*topk] int64 = counts | top-k global rows | top-k score bits sits at *payload_dev; ranks
+ * exchange it with one NCCL allgather and every rank merges the gathered buffer on its device:
+ * merged_dev gets the same layout with counts summed and the global top-k.                    */
+int vq_scan_payload(vq_store *s, const int64_t **payload_dev, int32_t *n_int64);
+int vq_merge_payloads_enqueue(int device, const int64_t *gathered_dev, int32_t n_lists, int32_t topk,
+                              int64_t *merged_dev, void *stream);
+
+/* per-launch device times of K1 recorded since the last call (ring of 1024), in ms           */
+int vq_scan_kernel_times(vq_store *s, int32_t cap, float *ms_out, int32_t *n_out);
+/* merge per-shard top-k lists (score desc, global row asc) — the host/rank-0 side of the
+ * NCCL allgather merge; lists: [n_lists][k] with -inf / -1 padding.                          */
+int vq_merge_topk(int32_t n_lists, int32_t k, const float *scores, const int64_t *rows,
+                  float *scores_out, int64_t *rows_out, int32_t *n_out);
+
+/* ---------------------------------------------------------------- labelled subset, fp64 (A6, A8)
+ * Similarities of a short list of rows against an fp64 target, fp64 accumulation
+ * (the inputs of Hyperparameter.optimize_weights, hyperparameter.py:57-65).                  */
+int vq_labelled_sims(vq_store *s, const double *target /* [S][P][dim] */, const int64_t *rows,
+                     int64_t n, double *sims_out /* [n][S] */);
+/* losses[r][iw][ith] for R replicate index sets over L labelled clips (hyperparameter.py:56-65);
+ * replicate r uses labelled indices rep_index[rep_offset[r] .. rep_offset[r+1]).             */
+int vq_loss_grid(int device, const double *sims /* [L][2] */, const uint8_t *labels, int64_t L,
+                 const double *weight_grid, int32_t n_w, const double *threshold_grid,
+                 int32_t n_th, double ballast, const int32_t *rep_offset, const int32_t *rep_index,
+                 int32_t R, double *losses_out);
+
+/* ---------------------------------------------------------------- target bootstrap, fp64 (A10)
+ * New target from user-labelled rows: TargetClip._bootstrap_valid_matches (target_clip.py:161-199)
+ * when n_invalid == 0, else _bootstrap_valid_plus_invalid (:201-261).  One (stream, split)
+ * problem per slot, all solved in one call.  Resampling stays with the caller (Python RNG).  */
+int vq_bootstrap_target(vq_store *s, const int64_t *valid_rows, int32_t n_valid,
+                        const int64_t *invalid_rows, int32_t n_invalid, double mu,
+                        double *target_out /* [S][P][dim] */);
+
+/* ---------------------------------------------------------------- batched queries (tcgen05)
+ * Q targets scored against the shard in one pass; per query: counts and top-k.               */
+int vq_scan_batch(vq_store *s, const float *targets /* [Q][S][P][dim] */, int32_t n_queries,
+                  const vq_scan_params *p, int64_t *counts_out /* [Q][2] match, near */,
+                  int64_t *topk_rows_out /* [Q][topk] */, float *topk_scores_out /* [Q][topk] */,
+                  float *kernel_ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQ_B200_H */

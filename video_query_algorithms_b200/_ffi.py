@@ -1,0 +1,103 @@
+"""ctypes binding of include/vq.h.  There is no CPU fallback: if the CUDA library is missing
+or a call fails, VQError is raised (the broker's `except` logs it, reference src/broker.py:88-89)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libvq_b200.so")
+MAX_STREAMS = 4
+MAX_TOPK = 1024
+
+
+class VQError(RuntimeError):
+    pass
+
+
+class ScanParams(C.Structure):
+    _fields_ = [("weights", C.c_double * MAX_STREAMS), ("threshold", C.c_double),
+                ("lower_limit", C.c_double), ("eps", C.c_double), ("topk", C.c_int32),
+                ("want_sims", C.c_int32)]
+
+
+class ScanCounts(C.Structure):
+    _fields_ = [("n_match", C.c_int64), ("n_near", C.c_int64), ("n_tie", C.c_int64),
+                ("n_topk", C.c_int32), ("scan_ms", C.c_float)]
+
+
+class ScanDeviceView(C.Structure):
+    _fields_ = [("scores_dev", C.c_void_p), ("sims_dev", C.c_void_p), ("counts_dev", C.c_void_p),
+                ("topk_scores_dev", C.c_void_p), ("topk_rows_dev", C.c_void_p),
+                ("match_rows_dev", C.c_void_p), ("near_rows_dev", C.c_void_p)]
+
+
+_P = C.POINTER
+_vp, _i32, _i64, _f32p, _f64p, _i64p = C.c_void_p, C.c_int32, C.c_int64, _P(C.c_float), _P(C.c_double), _P(C.c_int64)
+
+# name -> (restype, argtypes); every symbol include/vq.h declares
+PROTOTYPES = {
+    "vq_last_error": (C.c_char_p, []),
+    "vq_abi_version": (C.c_int, []),
+    "vq_device_count": (C.c_int, [_P(C.c_int)]),
+    "vq_store_create": (C.c_int, [_P(_vp), C.c_int, _i64, C.c_int, C.c_int, C.c_int, _i64]),
+    "vq_store_destroy": (C.c_int, [_vp]),
+    "vq_store_describe": (C.c_int, [_vp, _i64p, _P(C.c_int), _P(C.c_int), _P(C.c_int), _i64p, _P(C.c_int)]),
+    "vq_store_upload": (C.c_int, [_vp, _i64, _i64, _vp]),
+    "vq_store_download": (C.c_int, [_vp, _i64, _i64, _vp]),
+    "vq_store_set_split_weights": (C.c_int, [_vp, _vp]),
+    "vq_store_fill_synthetic": (C.c_int, [_vp, C.c_uint64, _vp]),
+    "vq_store_device_ptr": (C.c_int, [_vp, _P(_vp)]),
+    "vq_scan": (C.c_int, [_vp, _vp, _P(ScanParams), _P(ScanCounts)]),
+    "vq_scan_enqueue": (C.c_int, [_vp, _vp, _P(ScanParams), _vp]),
+    "vq_scan_wait": (C.c_int, [_vp, _vp, _P(ScanCounts)]),
+    "vq_fetch_matches": (C.c_int, [_vp, _i64, _vp, _vp]),
+    "vq_fetch_near": (C.c_int, [_vp, _i64, _vp, _vp]),
+    "vq_fetch_ties": (C.c_int, [_vp, _i64, _vp, _vp]),
+    "vq_fetch_topk": (C.c_int, [_vp, _i32, _vp, _vp]),
+    "vq_fetch_scores": (C.c_int, [_vp, _i64, _i64, _vp]),
+    "vq_fetch_sims": (C.c_int, [_vp, _i64, _i64, _vp]),
+    "vq_scan_view": (C.c_int, [_vp, _P(ScanDeviceView)]),
+    "vq_scan_payload": (C.c_int, [_vp, _P(_vp), _P(_i32)]),
+    "vq_merge_payloads_enqueue": (C.c_int, [C.c_int, _vp, _i32, _i32, _vp, _vp]),
+    "vq_scan_kernel_times": (C.c_int, [_vp, _i32, _vp, _P(_i32)]),
+    "vq_merge_topk": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _P(_i32)]),
+    "vq_labelled_sims": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
+    "vq_loss_grid": (C.c_int, [C.c_int, _vp, _vp, _i64, _vp, _i32, _vp, _i32, C.c_double, _vp, _vp, _i32, _vp]),
+    "vq_bootstrap_target": (C.c_int, [_vp, _vp, _i32, _vp, _i32, C.c_double, _vp]),
+    "vq_scan_batch": (C.c_int, [_vp, _vp, _i32, _P(ScanParams), _vp, _vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library; raises VQError if it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise VQError("libvq_b200.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(expected at %s)" % LIB_PATH)
+        try:
+            handle = C.CDLL(LIB_PATH)
+        except OSError as e:
+            raise VQError("cannot load %s: %s" % (LIB_PATH, e))
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().vq_last_error()
+        raise VQError("%s failed (%d): %s" % (what or "libvq_b200 call", rc, msg.decode() if msg else "?"))
+
+
+def ptr(a):
+    """void* of a C-contiguous numpy array (or None)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)

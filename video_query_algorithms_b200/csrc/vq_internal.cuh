@@ -1,0 +1,83 @@
+// Internal definitions shared by the translation units of libvq_b200 (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "vq.h"
+
+namespace vq {
+
+constexpr int kHistBins = 4096;         // score histogram for top-k pruning: [-1, 1) in 1/2048 steps
+constexpr int kChunkRows = 4096;        // rows per block in the selection kernels
+constexpr int kTimeRing = 1024;
+
+void set_error(const char *fmt, ...);
+
+#define VQ_CUDA(call)                                                                   \
+    do {                                                                                \
+        cudaError_t e__ = (call);                                                       \
+        if (e__ != cudaSuccess) {                                                       \
+            vq::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call,                  \
+                          cudaGetErrorString(e__));                                     \
+            return -2;                                                                  \
+        }                                                                               \
+    } while (0)
+
+#define VQ_REQUIRE(cond, ...)                                                           \
+    do {                                                                                \
+        if (!(cond)) {                                                                  \
+            vq::set_error(__VA_ARGS__);                                                 \
+            return -1;                                                                  \
+        }                                                                               \
+    } while (0)
+
+// Device-side copy of the scan parameters.
+struct ScanArgs {
+    float w[VQ_MAX_STREAMS];       // weights
+    float inv_den;                 // 1 / sum w^2
+    float inv_splits;              // 1 / n_splits when every slot is present
+    double th, lo, eps;
+    int topk;
+    int want_sims;
+};
+
+}  // namespace vq
+
+// The opaque store.  One shard of the clip-major feature database plus the scratch the
+// scan writes into.  Everything is allocated once at create time: a scan allocates nothing.
+struct vq_store {
+    int device = 0;
+    int64_t n_rows = 0, first_global_row = 0;
+    int n_streams = 0, n_splits = 0, dim = 0, stream_len = 0;   // stream_len = n_splits * dim
+    size_t row_floats = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+
+    float *rows = nullptr;           // [n_rows][n_streams][stream_len]
+    float *inv_counts = nullptr;     // [n_rows][n_streams] or null
+    float *target = nullptr;         // [n_streams][stream_len] fp32 staging for vq_scan
+    float *scores = nullptr;         // [n_rows]
+    float *sims = nullptr;           // [n_rows][n_streams] (allocated on first want_sims)
+    unsigned int *hist = nullptr;    // [kHistBins] + [1] block ticket + [1] cut bin
+    int64_t n_chunks = 0;
+    unsigned int *chunk_counts = nullptr;    // [3][n_chunks]
+    unsigned int *chunk_offsets = nullptr;   // [3][n_chunks]
+    int64_t *counts = nullptr;       // [4] n_match n_near n_tie n_topk   (device)
+    int64_t *counts_host = nullptr;  // pinned mirror
+    uint32_t *list_rows[3] = {nullptr, nullptr, nullptr};   // match / near / tie, capacity n_rows
+    float *list_scores[3] = {nullptr, nullptr, nullptr};
+    unsigned int *cand_count = nullptr;      // [1]
+    unsigned long long *cand_keys = nullptr; // [cand_cap] composite (score, ~row) keys
+    int64_t cand_cap = 0;
+    float *topk_scores = nullptr;    // [VQ_MAX_TOPK]
+    int64_t *topk_rows = nullptr;    // [VQ_MAX_TOPK]
+    int last_topk = 0;
+    int64_t *pack = nullptr;         // [4 + 2*VQ_MAX_TOPK] counts | top-k rows | top-k score bits (allgather payload)
+
+    cudaEvent_t ev_start[vq::kTimeRing], ev_stop[vq::kTimeRing];
+    bool ev_made = false;
+    int ev_head = 0, ev_count = 0;
+    void *pinned_stage = nullptr;    // small pinned buffer for targets / params
+};

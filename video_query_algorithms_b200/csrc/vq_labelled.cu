@@ -1,0 +1,408 @@
+// Labelled-subset path, all float64: the reference does every step on the user-labelled clips in
+// float64 and the small linear solves are ill-conditioned enough (cond up to ~1e4) that fp32
+// arithmetic breaks the 1e-5 bar.  Inputs are the fp32 store rows, widened.
+//
+//   K4  labelled_sims     fp64 similarities of a row list        (inputs of hyperparameter.py:57-65)
+//   K5  loss_grid         R replicates x 40 weights x 31 thresholds hinge loss (hyperparameter.py:56-65)
+//   K6  gram / solve / combine   new target from labelled rows   (target_clip.py:161-261)
+#include <vector>
+
+#include "vq_internal.cuh"
+
+namespace {
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// one warp per (labelled row, stream); per-split dots summed in split order, then / n_splits
+__global__ void labelled_sims_kernel(const float *__restrict__ rows, const double *__restrict__ target,
+                                     const long long *__restrict__ row_ids, const float *__restrict__ inv_counts,
+                                     long long n, int n_streams, int n_splits, int dim, double *sims) {
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= n * n_streams) return;
+    const long long i = w / n_streams;
+    const int s = (int)(w - i * n_streams);
+    const long long r = row_ids[i];
+    const size_t stream_len = (size_t)n_splits * dim;
+    const float *x = rows + ((size_t)r * n_streams + s) * stream_len;
+    const double *t = target + (size_t)s * stream_len;
+    double total = 0.0;
+    for (int p = 0; p < n_splits; ++p) {
+        double acc = 0.0;
+        for (int d = lane; d < dim; d += 32) acc = fma((double)x[p * dim + d], t[p * dim + d], acc);
+        total += warp_sum_d(acc);
+    }
+    if (lane == 0) {
+        const double cnt = inv_counts ? (double)__float2int_rn(1.0f / inv_counts[r * n_streams + s]) : (double)n_splits;
+        sims[i * n_streams + s] = total / cnt;
+    }
+}
+
+// score table [n_w][L]: 1 - sqrt(((1 - s0))^2 + (w (1 - s1))^2) / (1 + w^2)) in the reference's
+// operation order (ticket.py:174-180 with weights {1.0, w}); no FMA contraction.
+__global__ void score_table_kernel(const double *__restrict__ sims, long long L, const double *__restrict__ wgrid,
+                                   int n_w, double *table) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= L * n_w) return;
+    const int iw = (int)(i / L);
+    const long long l = i - (long long)iw * L;
+    const double w = wgrid[iw];
+    const double d0 = __dmul_rn(1.0, __dsub_rn(1.0, sims[2 * l]));
+    const double d1 = __dmul_rn(w, __dsub_rn(1.0, sims[2 * l + 1]));
+    const double ssum = __dadd_rn(__dadd_rn(0.0, __dmul_rn(d0, d0)), __dmul_rn(d1, d1));
+    const double den = __dadd_rn(__dadd_rn(0.0, 1.0), __dmul_rn(w, w));
+    table[i] = __dsub_rn(1.0, sqrt(__ddiv_rn(ssum, den)));
+}
+
+constexpr int kLossThreads = 128;
+constexpr int kMaxTh = 32;
+
+// one block per (replicate, weight): 31 running sums per thread, block tree reduction
+__global__ void __launch_bounds__(kLossThreads)
+loss_grid_kernel(const double *__restrict__ table, const unsigned char *__restrict__ labels, long long L,
+                 const double *__restrict__ thgrid, int n_th, int n_w, double ballast,
+                 const int *__restrict__ rep_offset, const int *__restrict__ rep_index, double *losses) {
+    __shared__ double th_s[kMaxTh];
+    __shared__ double red[kLossThreads / 32][kMaxTh];
+    const int r = blockIdx.x / n_w, iw = blockIdx.x - r * n_w;
+    if (threadIdx.x < n_th) th_s[threadIdx.x] = thgrid[threadIdx.x];
+    __syncthreads();
+    const int lo = rep_offset[r], hi = rep_offset[r + 1];
+    double acc[kMaxTh];
+#pragma unroll
+    for (int j = 0; j < kMaxTh; ++j) acc[j] = 0.0;
+    const double *row = table + (size_t)iw * L;
+    for (int q = lo + threadIdx.x; q < hi; q += kLossThreads) {
+        const int l = rep_index[q];
+        const double sc = row[l];
+        const double y = labels[l] ? 1.0 : 0.0;
+        const double wgt = 1.0 + y * ballast;
+#pragma unroll
+        for (int j = 0; j < kMaxTh; ++j) {
+            if (j < n_th) {
+                const double d = sc - th_s[j];
+                const double h = (d >= 0.0) ? 1.0 : 0.0;        // np.heaviside(d, 1)
+                acc[j] += (h - y) * d * wgt;
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < kMaxTh; ++j) {
+        const double v = warp_sum_d(acc[j]);
+        if (lane == 0) red[wid][j] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < n_th) {
+        double v = 0.0;
+        for (int w = 0; w < kLossThreads / 32; ++w) v += red[w][threadIdx.x];
+        const double n = (double)(hi - lo);
+        losses[((size_t)r * n_w + iw) * n_th + threadIdx.x] = (0.5 * th_s[threadIdx.x] + v) / n;
+    }
+}
+
+// ------------------------------------------------------------------ target bootstrap (K6)
+// Z = [valid rows; invalid rows] (n + m rows).  Gram matrices per (stream, split) slot:
+// G[slot][i][j] = z_i . z_j over that slot's `dim` floats.  One warp per (slot, i <= j).
+__global__ void gram_kernel(const float *__restrict__ rows, const long long *__restrict__ ids, int nz,
+                            int n_slots, int dim, size_t row_floats, double *G) {
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const long long pairs = (long long)nz * nz;
+    if (w >= pairs * n_slots) return;
+    const int slot = (int)(w / pairs);
+    const long long ij = w - (long long)slot * pairs;
+    const int i = (int)(ij / nz), j = (int)(ij - (long long)i * nz);
+    if (j < i) return;
+    const float *a = rows + (size_t)ids[i] * row_floats + (size_t)slot * dim;
+    const float *b = rows + (size_t)ids[j] * row_floats + (size_t)slot * dim;
+    double acc = 0.0;
+    for (int d = lane; d < dim; d += 32) acc = fma((double)a[d], (double)b[d], acc);
+    acc = warp_sum_d(acc);
+    if (lane == 0) {
+        G[((size_t)slot * nz + i) * nz + j] = acc;
+        G[((size_t)slot * nz + j) * nz + i] = acc;
+    }
+}
+
+// Block-cooperative LU with partial pivoting on A (n x n, row-major, in global scratch), applied
+// to nrhs right-hand sides B (n x nrhs, row-major).  On return B holds the solutions.
+__device__ void lu_solve(double *A, double *B, int n, int nrhs, int *piv_s) {
+    for (int k = 0; k < n; ++k) {
+        if (threadIdx.x == 0) {
+            int p = k;
+            double best = fabs(A[(size_t)k * n + k]);
+            for (int i = k + 1; i < n; ++i) {
+                const double v = fabs(A[(size_t)i * n + k]);
+                if (v > best) { best = v; p = i; }
+            }
+            *piv_s = p;
+        }
+        __syncthreads();
+        const int p = *piv_s;
+        if (p != k) {
+            for (int j = threadIdx.x; j < n; j += blockDim.x) {
+                const double t = A[(size_t)k * n + j];
+                A[(size_t)k * n + j] = A[(size_t)p * n + j];
+                A[(size_t)p * n + j] = t;
+            }
+            for (int j = threadIdx.x; j < nrhs; j += blockDim.x) {
+                const double t = B[(size_t)k * nrhs + j];
+                B[(size_t)k * nrhs + j] = B[(size_t)p * nrhs + j];
+                B[(size_t)p * nrhs + j] = t;
+            }
+        }
+        __syncthreads();
+        const double pivot = A[(size_t)k * n + k];
+        for (int i = k + 1 + threadIdx.x; i < n; i += blockDim.x) A[(size_t)i * n + k] /= pivot;
+        __syncthreads();
+        const int rem = n - k - 1;
+        for (long long e = threadIdx.x; e < (long long)rem * (rem + nrhs); e += blockDim.x) {
+            const int i = k + 1 + (int)(e / (rem + nrhs));
+            const int c = (int)(e % (rem + nrhs));
+            const double l = A[(size_t)i * n + k];
+            if (c < rem) A[(size_t)i * n + (k + 1 + c)] -= l * A[(size_t)k * n + (k + 1 + c)];
+            else B[(size_t)i * nrhs + (c - rem)] -= l * B[(size_t)k * nrhs + (c - rem)];
+        }
+        __syncthreads();
+    }
+    // back substitution, one column of B per thread
+    for (int j = threadIdx.x; j < nrhs; j += blockDim.x) {
+        for (int i = n - 1; i >= 0; --i) {
+            double v = B[(size_t)i * nrhs + j];
+            for (int c = i + 1; c < n; ++c) v -= A[(size_t)i * n + c] * B[(size_t)c * nrhs + j];
+            B[(size_t)i * nrhs + j] = v / A[(size_t)i * n + i];
+        }
+    }
+    __syncthreads();
+}
+
+// One block per slot.  Computes coefficient vectors a (n) and b (m) with
+//     w = X^T a + Y^T b
+// equal to the reference's w_final (target_clip.py:248-260), via the Woodbury identity so that only
+// (n+m)-sized Gram blocks are needed instead of the reference's dim x dim inverse:
+//     c = mu / tr(Gyy);  K = c (I + c Gyy)^-1;  B = Gxx - Gxy K Gyx;  beta = B^-1 1;
+//     gamma = 1 - K Gyy 1;  delta = B^-1 Gxy gamma;
+//     a = beta - c delta;   b = c gamma + c K Gyx delta - K Gyx beta.
+// With m = 0 (or mu = 0 => c = 0, K = 0) this is a = Gxx^-1 1, the valid-only rule (:194-198).
+// Scratch per slot (doubles): Bm[n*n] | R[n*2] | Ky[m*m] | Z[m*(n+1)] | tmp[n+m]
+__global__ void __launch_bounds__(256)
+bootstrap_solve_kernel(const double *__restrict__ G, int n, int m, double mu, double *scratch,
+                       size_t scratch_per_slot, double *coef) {
+    __shared__ int piv_s;
+    __shared__ double c_s;
+    const int slot = blockIdx.x;
+    const int nz = n + m;
+    const double *Gs = G + (size_t)slot * nz * nz;
+    double *Bm = scratch + (size_t)slot * scratch_per_slot;
+    double *R = Bm + (size_t)n * n;
+    double *Ky = R + (size_t)n * 2;
+    double *Z = Ky + (size_t)m * m;
+    double *co = coef + (size_t)slot * nz;
+#define GXX(i, j) Gs[(size_t)(i) * nz + (j)]
+#define GXY(i, j) Gs[(size_t)(i) * nz + n + (j)]
+#define GYY(i, j) Gs[(size_t)(n + (i)) * nz + n + (j)]
+    if (threadIdx.x == 0) {
+        double tr = 0.0;
+        for (int j = 0; j < m; ++j) tr += GYY(j, j);
+        c_s = (m > 0) ? mu / tr : 0.0;
+    }
+    __syncthreads();
+    const double c = c_s;
+    const bool use_y = (m > 0) && (c != 0.0);
+    if (use_y) {
+        // Z = (I + c Gyy)^-1 [ c Gyx | c Gyy 1 ]   -> Z[:, :n] = K Gyx, Z[:, n] = K Gyy 1
+        for (int e = threadIdx.x; e < m * m; e += blockDim.x) {
+            const int i = e / m, j = e % m;
+            Ky[e] = (i == j ? 1.0 : 0.0) + c * GYY(i, j);
+        }
+        for (int e = threadIdx.x; e < m * (n + 1); e += blockDim.x) {
+            const int i = e / (n + 1), j = e % (n + 1);
+            double v;
+            if (j < n) v = c * GXY(j, i);
+            else {
+                v = 0.0;
+                for (int q = 0; q < m; ++q) v += GYY(i, q);
+                v *= c;
+            }
+            Z[e] = v;
+        }
+        __syncthreads();
+        lu_solve(Ky, Z, m, n + 1, &piv_s);
+    }
+    // B = Gxx - Gxy (K Gyx);  R = [1 | Gxy gamma],  gamma = 1 - K Gyy 1
+    for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
+        const int i = e / n, j = e % n;
+        double v = GXX(i, j);
+        if (use_y)
+            for (int q = 0; q < m; ++q) v -= GXY(i, q) * Z[(size_t)q * (n + 1) + j];
+        Bm[e] = v;
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        R[2 * i] = 1.0;
+        double v = 0.0;
+        if (use_y)
+            for (int q = 0; q < m; ++q) v += GXY(i, q) * (1.0 - Z[(size_t)q * (n + 1) + n]);
+        R[2 * i + 1] = v;
+    }
+    __syncthreads();
+    lu_solve(Bm, R, n, 2, &piv_s);                 // R[:,0] = beta, R[:,1] = delta
+    for (int i = threadIdx.x; i < n; i += blockDim.x) co[i] = R[2 * i] - c * R[2 * i + 1];
+    for (int j = threadIdx.x; j < m; j += blockDim.x) {
+        double v = 0.0;
+        if (use_y) {
+            const double gamma = 1.0 - Z[(size_t)j * (n + 1) + n];
+            double kd = 0.0, kb = 0.0;               // (K Gyx delta)_j, (K Gyx beta)_j
+            for (int i = 0; i < n; ++i) {
+                const double z = Z[(size_t)j * (n + 1) + i];
+                kd += z * R[2 * i + 1];
+                kb += z * R[2 * i];
+            }
+            v = c * gamma + c * kd - kb;
+        }
+        co[n + j] = v;
+    }
+#undef GXX
+#undef GXY
+#undef GYY
+}
+
+// w[slot][d] = sum_i coef[slot][i] * z_i[slot][d]
+__global__ void combine_kernel(const float *__restrict__ rows, const long long *__restrict__ ids, int nz,
+                               int n_slots, int dim, size_t row_floats, const double *__restrict__ coef,
+                               double *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_slots * dim) return;
+    const int slot = i / dim, d = i - slot * dim;
+    double acc = 0.0;
+    for (int r = 0; r < nz; ++r)
+        acc = fma(coef[(size_t)slot * nz + r], (double)rows[(size_t)ids[r] * row_floats + (size_t)slot * dim + d], acc);
+    out[i] = acc;
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 8); }
+    template <class T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+int local_rows(const vq_store *s, const int64_t *rows, int64_t n, std::vector<long long> &out, const char *who) {
+    out.resize((size_t)n);
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t r = rows[i] - s->first_global_row;
+        VQ_REQUIRE(r >= 0 && r < s->n_rows, "%s: global row %lld is not in this shard [%lld, %lld)", who,
+                   (long long)rows[i], (long long)s->first_global_row,
+                   (long long)(s->first_global_row + s->n_rows));
+        out[(size_t)i] = r;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int vq_labelled_sims(vq_store *s, const double *target, const int64_t *rows, int64_t n,
+                                double *sims_out) {
+    VQ_REQUIRE(s && target && (rows || n == 0) && (sims_out || n == 0), "vq_labelled_sims: null argument");
+    if (n == 0) return 0;
+    std::vector<long long> loc;
+    if (int r = local_rows(s, rows, n, loc, "vq_labelled_sims")) return r;
+    VQ_CUDA(cudaSetDevice(s->device));
+    DevBuf d_t, d_ids, d_out;
+    VQ_CUDA(d_t.alloc(s->row_floats * sizeof(double)));
+    VQ_CUDA(d_ids.alloc((size_t)n * sizeof(long long)));
+    VQ_CUDA(d_out.alloc((size_t)n * s->n_streams * sizeof(double)));
+    VQ_CUDA(cudaMemcpyAsync(d_t.p, target, s->row_floats * sizeof(double), cudaMemcpyHostToDevice, s->stream));
+    VQ_CUDA(cudaMemcpyAsync(d_ids.p, loc.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, s->stream));
+    const long long warps = n * s->n_streams;
+    const int blocks = (int)((warps * 32 + 255) / 256);
+    labelled_sims_kernel<<<blocks, 256, 0, s->stream>>>(s->rows, d_t.as<double>(), d_ids.as<long long>(),
+                                                        s->inv_counts, n, s->n_streams, s->n_splits, s->dim,
+                                                        d_out.as<double>());
+    VQ_CUDA(cudaGetLastError());
+    VQ_CUDA(cudaMemcpyAsync(sims_out, d_out.p, (size_t)n * s->n_streams * sizeof(double), cudaMemcpyDeviceToHost,
+                            s->stream));
+    VQ_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+extern "C" int vq_loss_grid(int device, const double *sims, const uint8_t *labels, int64_t L,
+                            const double *weight_grid, int32_t n_w, const double *threshold_grid, int32_t n_th,
+                            double ballast, const int32_t *rep_offset, const int32_t *rep_index, int32_t R,
+                            double *losses_out) {
+    VQ_REQUIRE(sims && labels && weight_grid && threshold_grid && rep_offset && rep_index && losses_out,
+               "vq_loss_grid: null argument");
+    VQ_REQUIRE(L > 0 && n_w > 0 && R > 0 && n_th > 0 && n_th <= kMaxTh,
+               "vq_loss_grid: need L, R, n_w > 0 and 0 < n_th <= %d", kMaxTh);
+    for (int r = 0; r < R; ++r)
+        VQ_REQUIRE(rep_offset[r + 1] > rep_offset[r], "vq_loss_grid: replicate %d is empty", r);
+    const int64_t n_idx = rep_offset[R];
+    for (int64_t i = 0; i < n_idx; ++i)
+        VQ_REQUIRE(rep_index[i] >= 0 && rep_index[i] < L, "vq_loss_grid: replicate index out of range");
+    VQ_CUDA(cudaSetDevice(device));
+    DevBuf d_sims, d_lab, d_w, d_th, d_off, d_idx, d_tab, d_out;
+    VQ_CUDA(d_sims.alloc((size_t)L * 2 * sizeof(double)));
+    VQ_CUDA(d_lab.alloc((size_t)L));
+    VQ_CUDA(d_w.alloc((size_t)n_w * sizeof(double)));
+    VQ_CUDA(d_th.alloc((size_t)n_th * sizeof(double)));
+    VQ_CUDA(d_off.alloc((size_t)(R + 1) * sizeof(int)));
+    VQ_CUDA(d_idx.alloc((size_t)n_idx * sizeof(int)));
+    VQ_CUDA(d_tab.alloc((size_t)L * n_w * sizeof(double)));
+    VQ_CUDA(d_out.alloc((size_t)R * n_w * n_th * sizeof(double)));
+    VQ_CUDA(cudaMemcpy(d_sims.p, sims, (size_t)L * 2 * sizeof(double), cudaMemcpyHostToDevice));
+    VQ_CUDA(cudaMemcpy(d_lab.p, labels, (size_t)L, cudaMemcpyHostToDevice));
+    VQ_CUDA(cudaMemcpy(d_w.p, weight_grid, (size_t)n_w * sizeof(double), cudaMemcpyHostToDevice));
+    VQ_CUDA(cudaMemcpy(d_th.p, threshold_grid, (size_t)n_th * sizeof(double), cudaMemcpyHostToDevice));
+    VQ_CUDA(cudaMemcpy(d_off.p, rep_offset, (size_t)(R + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    VQ_CUDA(cudaMemcpy(d_idx.p, rep_index, (size_t)n_idx * sizeof(int), cudaMemcpyHostToDevice));
+    score_table_kernel<<<(unsigned int)((L * n_w + 255) / 256), 256>>>(d_sims.as<double>(), L, d_w.as<double>(),
+                                                                      n_w, d_tab.as<double>());
+    loss_grid_kernel<<<(unsigned int)(R * n_w), kLossThreads>>>(d_tab.as<double>(), d_lab.as<unsigned char>(), L,
+                                                               d_th.as<double>(), n_th, n_w, ballast,
+                                                               d_off.as<int>(), d_idx.as<int>(), d_out.as<double>());
+    VQ_CUDA(cudaGetLastError());
+    VQ_CUDA(cudaMemcpy(losses_out, d_out.p, (size_t)R * n_w * n_th * sizeof(double), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int vq_bootstrap_target(vq_store *s, const int64_t *valid_rows, int32_t n_valid,
+                                   const int64_t *invalid_rows, int32_t n_invalid, double mu, double *target_out) {
+    VQ_REQUIRE(s && valid_rows && target_out, "vq_bootstrap_target: null argument");
+    VQ_REQUIRE(n_valid >= 1 && n_invalid >= 0 && (n_invalid == 0 || invalid_rows),
+               "vq_bootstrap_target: need at least one valid row");
+    VQ_REQUIRE(n_valid <= s->dim, "vq_bootstrap_target: %d valid rows exceed the feature dimension %d (singular system)",
+               n_valid, s->dim);
+    const int n = n_valid, m = n_invalid, nz = n + m;
+    const int n_slots = s->n_streams * s->n_splits;
+    std::vector<long long> loc, loc2;
+    if (int r = local_rows(s, valid_rows, n, loc, "vq_bootstrap_target")) return r;
+    if (m) {
+        if (int r = local_rows(s, invalid_rows, m, loc2, "vq_bootstrap_target")) return r;
+        loc.insert(loc.end(), loc2.begin(), loc2.end());
+    }
+    VQ_CUDA(cudaSetDevice(s->device));
+    const size_t per_slot = (size_t)n * n + (size_t)n * 2 + (size_t)m * m + (size_t)m * (n + 1) + (size_t)nz + 8;
+    DevBuf d_ids, d_G, d_scr, d_coef, d_out;
+    VQ_CUDA(d_ids.alloc((size_t)nz * sizeof(long long)));
+    VQ_CUDA(d_G.alloc((size_t)n_slots * nz * nz * sizeof(double)));
+    VQ_CUDA(d_scr.alloc((size_t)n_slots * per_slot * sizeof(double)));
+    VQ_CUDA(d_coef.alloc((size_t)n_slots * nz * sizeof(double)));
+    VQ_CUDA(d_out.alloc((size_t)n_slots * s->dim * sizeof(double)));
+    VQ_CUDA(cudaMemcpyAsync(d_ids.p, loc.data(), (size_t)nz * sizeof(long long), cudaMemcpyHostToDevice, s->stream));
+    const long long warps = (long long)nz * nz * n_slots;
+    gram_kernel<<<(unsigned int)((warps * 32 + 255) / 256), 256, 0, s->stream>>>(
+        s->rows, d_ids.as<long long>(), nz, n_slots, s->dim, s->row_floats, d_G.as<double>());
+    bootstrap_solve_kernel<<<n_slots, 256, 0, s->stream>>>(d_G.as<double>(), n, m, mu, d_scr.as<double>(), per_slot,
+                                                           d_coef.as<double>());
+    combine_kernel<<<(n_slots * s->dim + 255) / 256, 256, 0, s->stream>>>(
+        s->rows, d_ids.as<long long>(), nz, n_slots, s->dim, s->row_floats, d_coef.as<double>(), d_out.as<double>());
+    VQ_CUDA(cudaGetLastError());
+    VQ_CUDA(cudaMemcpyAsync(target_out, d_out.p, (size_t)n_slots * s->dim * sizeof(double), cudaMemcpyDeviceToHost,
+                            s->stream));
+    VQ_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}

@@ -1,0 +1,784 @@
+// Single-query scan: the HBM-bound hot path.
+//
+//   K1  scan_rows_*      one pass over the shard: per-stream dot products against the target
+//                        (reference ticket.py:146-160), split mean, weighted fusion into the score
+//                        (ticket.py:173-180), score histogram for top-k pruning.  8192 B read per
+//                        clip (S=2, 1024-d), 4 B written.
+//   K2a select_count     per 4096-row chunk: match / near-miss / tie-band counts (ticket.py:325-327)
+//                        and top-k candidate collection (rows whose histogram bin can hold the k-th).
+//   K2b select_finish    block 0: exclusive scan of chunk counts; block 1: exact top-k of the
+//                        candidates (radix select on (score, row) keys + bitonic sort), ranking
+//                        rule of ticket.py:266 (score descending, database order among equals).
+//   K2c select_compact   order-preserving compaction of the three row lists.
+//
+// Summation order is fixed by the launch geometry, so results are deterministic run to run.
+#include <algorithm>
+#include <vector>
+
+#include "vq_internal.cuh"
+
+namespace {
+
+using vq::kChunkRows;
+using vq::kHistBins;
+using vq::ScanArgs;
+
+constexpr int kScanThreads = 128;   // 4 warps per block, one clip row per warp iteration
+
+__device__ __forceinline__ float4 ld_stream(const float4 *p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ int score_bin(float sc) {
+    // [-1, 1) in steps of 1/2048; monotone in sc; NaN -> 0
+    const int b = __float2int_rd((sc + 1.0f) * 2048.0f);
+    return min(max(b, 0), kHistBins - 1);
+}
+
+template <int S>
+__device__ __forceinline__ float fuse_score(const float (&sim)[S], const ScanArgs &a) {
+    float ssum = 0.f;
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+        const float d = a.w[s] * (1.0f - sim[s]);
+        ssum = fmaf(d, d, ssum);
+    }
+    return 1.0f - __fsqrt_rn(ssum * a.inv_den);
+}
+
+// Tail shared by both K1 variants: flush the block histogram, and let the last block to finish
+// turn the global histogram into the cut bin (largest bin b with count(bins >= b) >= k).
+__device__ void finish_histogram(unsigned int *hist_s, unsigned int *hist_g, int topk) {
+    __shared__ unsigned int is_last;
+    __shared__ unsigned int part[32];
+    __syncthreads();
+    for (int b = threadIdx.x; b < kHistBins; b += blockDim.x) {
+        const unsigned int c = hist_s[b];
+        if (c) atomicAdd(&hist_g[b], c);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(&hist_g[kHistBins], 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // suffix counts: thread t owns bins [t*per, (t+1)*per) from the TOP of the range
+    const int per = kHistBins / blockDim.x;          // blockDim divides 4096
+    const int top = kHistBins - 1 - threadIdx.x * per;
+    unsigned int mine = 0;
+    for (int j = 0; j < per; ++j) mine += ((volatile unsigned int *)hist_g)[top - j];
+    // inclusive scan of `mine` across threads (thread 0 = highest bins)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned int inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) part[wid] = inc;
+    __syncthreads();
+    unsigned int before = 0;
+    for (int w = 0; w < wid; ++w) before += part[w];
+    inc += before;
+    const unsigned int excl = inc - mine;
+    if (threadIdx.x == 0) hist_g[kHistBins + 1] = 0;   // default: everything is a candidate
+    __syncthreads();
+    if (topk > 0 && excl < (unsigned int)topk && inc >= (unsigned int)topk) {
+        unsigned int run = excl;
+        for (int j = 0; j < per; ++j) {
+            run += ((volatile unsigned int *)hist_g)[top - j];
+            if (run >= (unsigned int)topk) {
+                hist_g[kHistBins + 1] = (unsigned int)(top - j);
+                break;
+            }
+        }
+    }
+}
+
+// K1, specialised: S streams of V*128 floats, target held in registers.
+template <int S, int V>
+__global__ void __launch_bounds__(kScanThreads, 3)
+scan_rows_reg(const float4 *__restrict__ rows, const float4 *__restrict__ target,
+              const float *__restrict__ inv_counts, const ScanArgs a, const long long n_rows,
+              float *__restrict__ scores, float *__restrict__ sims, unsigned int *hist_g) {
+    __shared__ unsigned int hist_s[kHistBins];
+    for (int b = threadIdx.x; b < kHistBins; b += blockDim.x) hist_s[b] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (long long)blockIdx.x * (kScanThreads / 32) + (threadIdx.x >> 5);
+    const long long n_warps = (long long)gridDim.x * (kScanThreads / 32);
+    float4 t[S][V];
+#pragma unroll
+    for (int s = 0; s < S; ++s)
+#pragma unroll
+        for (int i = 0; i < V; ++i) t[s][i] = target[(s * V + i) * 32 + lane];
+
+    for (long long row = warp0; row < n_rows; row += n_warps) {
+        const float4 *p = rows + row * (long long)(S * V * 32) + lane;
+        float4 x[S][V];
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+#pragma unroll
+            for (int i = 0; i < V; ++i) x[s][i] = ld_stream(p + (s * V + i) * 32);
+        float sim[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int i = 0; i < V; ++i) {
+                a0 = fmaf(x[s][i].x, t[s][i].x, a0);
+                a1 = fmaf(x[s][i].y, t[s][i].y, a1);
+                a2 = fmaf(x[s][i].z, t[s][i].z, a2);
+                a3 = fmaf(x[s][i].w, t[s][i].w, a3);
+            }
+            const float d = warp_sum((a0 + a1) + (a2 + a3));
+            sim[s] = d * (inv_counts ? inv_counts[row * S + s] : a.inv_splits);
+        }
+        if (lane == 0) {
+            const float sc = fuse_score<S>(sim, a);
+            scores[row] = sc;
+            if (a.want_sims) {
+#pragma unroll
+                for (int s = 0; s < S; ++s) sims[row * S + s] = sim[s];
+            }
+            if (a.topk > 0 && sc == sc) atomicAdd(&hist_s[score_bin(sc)], 1u);
+        }
+    }
+    finish_histogram(hist_s, hist_g, a.topk);
+}
+
+// K1, generic: any stream count <= 4 and any stream length (multiple of 4 floats); the target
+// sits in shared memory.  Used for databases with several splits per stream (fixtures: 3 x 1024).
+template <int S>
+__global__ void __launch_bounds__(kScanThreads)
+scan_rows_smem(const float4 *__restrict__ rows, const float4 *__restrict__ target,
+               const float *__restrict__ inv_counts, const ScanArgs a, const long long n_rows,
+               const int len4, float *__restrict__ scores, float *__restrict__ sims,
+               unsigned int *hist_g) {
+    extern __shared__ float4 tgt_s[];                 // [S][len4]
+    __shared__ unsigned int hist_s[kHistBins];
+    for (int b = threadIdx.x; b < kHistBins; b += blockDim.x) hist_s[b] = 0;
+    for (int i = threadIdx.x; i < S * len4; i += blockDim.x) tgt_s[i] = target[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (long long)blockIdx.x * (kScanThreads / 32) + (threadIdx.x >> 5);
+    const long long n_warps = (long long)gridDim.x * (kScanThreads / 32);
+    constexpr int U = 8;
+    for (long long row = warp0; row < n_rows; row += n_warps) {
+        const float4 *p = rows + row * (long long)(S * len4);
+        float sim[S];
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            for (int base = 0; base < len4; base += 32 * U) {
+                float4 x[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int j = base + u * 32 + lane;
+                    x[u] = (j < len4) ? ld_stream(p + s * len4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int j = base + u * 32 + lane;
+                    if (j < len4) {
+                        const float4 tv = tgt_s[s * len4 + j];
+                        a0 = fmaf(x[u].x, tv.x, a0);
+                        a1 = fmaf(x[u].y, tv.y, a1);
+                        a2 = fmaf(x[u].z, tv.z, a2);
+                        a3 = fmaf(x[u].w, tv.w, a3);
+                    }
+                }
+            }
+            const float d = warp_sum((a0 + a1) + (a2 + a3));
+            sim[s] = d * (inv_counts ? inv_counts[row * S + s] : a.inv_splits);
+        }
+        if (lane == 0) {
+            const float sc = fuse_score<S>(sim, a);
+            scores[row] = sc;
+            if (a.want_sims) {
+#pragma unroll
+                for (int s = 0; s < S; ++s) sims[row * S + s] = sim[s];
+            }
+            if (a.topk > 0 && sc == sc) atomicAdd(&hist_s[score_bin(sc)], 1u);
+        }
+    }
+    finish_histogram(hist_s, hist_g, a.topk);
+}
+
+// ------------------------------------------------------------------------------ selection
+constexpr int kSelThreads = 256;
+constexpr int kRowsPerThread = kChunkRows / kSelThreads;   // 16 contiguous rows per thread
+
+__device__ __forceinline__ unsigned long long make_key(float sc, unsigned int row) {
+    unsigned int u = __float_as_uint(sc);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - row);
+}
+
+struct Flags {
+    bool m, nm, tie;
+};
+__device__ __forceinline__ Flags classify(float sc, const ScanArgs &a) {
+    const double d = (double)sc;
+    Flags f;
+    f.m = d >= a.th;
+    f.nm = (!f.m) && (d >= a.lo);
+    f.tie = (fabs(d - a.th) < a.eps) || (fabs(d - a.lo) < a.eps);
+    return f;
+}
+
+__device__ __forceinline__ void load_chunk_scores(const float *scores, long long n_rows, long long r0,
+                                                  float (&sc)[kRowsPerThread]) {
+    if (r0 + kRowsPerThread <= n_rows) {
+        const float4 *p = reinterpret_cast<const float4 *>(scores + r0);
+#pragma unroll
+        for (int q = 0; q < kRowsPerThread / 4; ++q) {
+            const float4 v = p[q];
+            sc[4 * q] = v.x; sc[4 * q + 1] = v.y; sc[4 * q + 2] = v.z; sc[4 * q + 3] = v.w;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kRowsPerThread; ++j)
+            sc[j] = (r0 + j < n_rows) ? scores[r0 + j] : __int_as_float(0x7fc00000);
+    }
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+select_count(const float *__restrict__ scores, const long long n_rows, const ScanArgs a,
+             const unsigned int *__restrict__ hist_g, unsigned int *chunk_counts, const long long n_chunks,
+             unsigned int *cand_count, unsigned long long *cand_keys, const long long cand_cap) {
+    __shared__ unsigned int red[3][kSelThreads / 32];
+    const long long chunk = blockIdx.x;
+    const long long r0 = chunk * kChunkRows + (long long)threadIdx.x * kRowsPerThread;
+    float sc[kRowsPerThread];
+    load_chunk_scores(scores, n_rows, r0, sc);
+    const int cut = (int)hist_g[kHistBins + 1];
+    unsigned int cm = 0, cn = 0, ct = 0, cc = 0;
+    unsigned int cmask = 0;
+#pragma unroll
+    for (int j = 0; j < kRowsPerThread; ++j) {
+        const Flags f = classify(sc[j], a);
+        cm += f.m; cn += f.nm; ct += f.tie;
+        if (a.topk > 0 && sc[j] == sc[j] && score_bin(sc[j]) >= cut) { cmask |= 1u << j; ++cc; }
+    }
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // top-k candidates: one atomic per warp
+    if (a.topk > 0) {
+        unsigned int inc = cc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        const unsigned int tot = __shfl_sync(0xffffffffu, inc, 31);
+        unsigned int base = 0;
+        if (lane == 31 && tot) base = atomicAdd(cand_count, tot);
+        base = __shfl_sync(0xffffffffu, base, 31);
+        unsigned int at = base + inc - cc;
+#pragma unroll
+        for (int j = 0; j < kRowsPerThread; ++j)
+            if (cmask & (1u << j)) {
+                if ((long long)at < cand_cap) cand_keys[at] = make_key(sc[j], (unsigned int)(r0 + j));
+                ++at;
+            }
+    }
+    unsigned int v0 = cm, v1 = cn, v2 = ct;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        v0 += __shfl_xor_sync(0xffffffffu, v0, o);
+        v1 += __shfl_xor_sync(0xffffffffu, v1, o);
+        v2 += __shfl_xor_sync(0xffffffffu, v2, o);
+    }
+    if (lane == 0) { red[0][wid] = v0; red[1][wid] = v1; red[2][wid] = v2; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        unsigned int t = 0;
+        for (int w = 0; w < kSelThreads / 32; ++w) t += red[threadIdx.x][w];
+        chunk_counts[threadIdx.x * n_chunks + chunk] = t;
+    }
+}
+
+constexpr int kFinThreads = 1024;
+
+__device__ unsigned int block_excl_scan_1024(unsigned int v, unsigned int *ws /*[33]*/, unsigned int *total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    __syncthreads();
+    if (lane == 31) ws[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned int w = ws[lane];
+        unsigned int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int u = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += u;
+        }
+        ws[lane] = winc - w;
+        if (lane == 31) ws[32] = winc;
+    }
+    __syncthreads();
+    *total = ws[32];
+    return inc - v + ws[wid];
+}
+
+__global__ void __launch_bounds__(kFinThreads)
+select_finish(const unsigned int *__restrict__ chunk_counts, unsigned int *chunk_offsets,
+              const long long n_chunks, long long *counts, unsigned int *hist_g,
+              unsigned int *cand_count, const unsigned long long *__restrict__ cand_keys,
+              const long long cand_cap, const int topk, const long long first_global_row,
+              float *topk_scores, long long *topk_rows) {
+    __shared__ unsigned int ws[33];
+    __shared__ unsigned int digit_hist[256];
+    __shared__ unsigned long long sel[VQ_MAX_TOPK];
+    __shared__ unsigned int sel_n;
+    __shared__ unsigned long long prefix_s;
+    __shared__ unsigned int remain_s;
+    if (blockIdx.x == 0) {
+        // exclusive scan of the three chunk-count arrays; also re-arm the histogram for the next scan
+        for (int which = 0; which < 3; ++which) {
+            unsigned long long carry = 0;
+            for (long long base = 0; base < n_chunks; base += kFinThreads) {
+                const long long i = base + threadIdx.x;
+                const unsigned int v = (i < n_chunks) ? chunk_counts[which * n_chunks + i] : 0u;
+                unsigned int total;
+                const unsigned int ex = block_excl_scan_1024(v, ws, &total);
+                if (i < n_chunks) chunk_offsets[which * n_chunks + i] = (unsigned int)carry + ex;
+                carry += total;
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) counts[which] = (long long)carry;
+        }
+        for (int b = threadIdx.x; b < kHistBins + 2; b += kFinThreads) hist_g[b] = 0;
+        return;
+    }
+    // ---- block 1: exact top-k over the candidate keys (all keys are distinct)
+    long long C = (long long)*cand_count;
+    if (C > cand_cap) C = cand_cap;
+    const int k = (int)min((long long)topk, C);
+    if (k > 0) {
+        // radix select, 8 bits at a time from the top: find the k-th largest key
+        unsigned long long prefix = 0, mask = 0;
+        unsigned int remain = (unsigned int)k;
+        for (int shift = 56; shift >= 0; shift -= 8) {
+            if (threadIdx.x < 256) digit_hist[threadIdx.x] = 0;
+            __syncthreads();
+            for (long long i = threadIdx.x; i < C; i += kFinThreads) {
+                const unsigned long long key = cand_keys[i];
+                if ((key & mask) == prefix) atomicAdd(&digit_hist[(unsigned int)(key >> shift) & 255u], 1u);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned int run = 0;
+                int d = 255;
+                for (; d > 0; --d) {
+                    if (run + digit_hist[d] >= remain) break;
+                    run += digit_hist[d];
+                }
+                prefix_s = prefix | ((unsigned long long)d << shift);
+                remain_s = remain - run;
+            }
+            __syncthreads();
+            prefix = prefix_s;
+            remain = remain_s;
+            mask |= 0xFFull << shift;
+            __syncthreads();
+        }
+        const unsigned long long kth = prefix;      // exact key of the k-th best
+        if (threadIdx.x == 0) sel_n = 0;
+        __syncthreads();
+        for (long long i = threadIdx.x; i < C; i += kFinThreads) {
+            const unsigned long long key = cand_keys[i];
+            if (key >= kth) {
+                const unsigned int at = atomicAdd(&sel_n, 1u);
+                if (at < VQ_MAX_TOPK) sel[at] = key;
+            }
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < VQ_MAX_TOPK; i += kFinThreads)
+        if (i >= k) sel[i] = 0ull;
+    __syncthreads();
+    // bitonic sort, descending, 1024 keys, one key per thread pair
+    for (int size = 2; size <= VQ_MAX_TOPK; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const int t = threadIdx.x;
+            if (t < VQ_MAX_TOPK / 2) {
+                const int lo = 2 * t - (t & (stride - 1));
+                const int hi = lo + stride;
+                const bool desc = ((lo & size) == 0);
+                const unsigned long long a = sel[lo], b = sel[hi];
+                if (desc ? (a < b) : (a > b)) { sel[lo] = b; sel[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < VQ_MAX_TOPK; i += kFinThreads) {
+        if (i < k) {
+            const unsigned long long key = sel[i];
+            unsigned int u = (unsigned int)(key >> 32);
+            u = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+            topk_scores[i] = __uint_as_float(u);
+            topk_rows[i] = first_global_row + (long long)(0xFFFFFFFFu - (unsigned int)(key & 0xFFFFFFFFull));
+        } else {
+            topk_scores[i] = __int_as_float(0xff800000);   // -inf
+            topk_rows[i] = -1;
+        }
+    }
+    if (threadIdx.x == 0) {
+        counts[3] = k;
+        *cand_count = 0;
+    }
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+select_compact(const float *__restrict__ scores, const long long n_rows, const ScanArgs a,
+               const unsigned int *__restrict__ chunk_offsets, const long long n_chunks,
+               unsigned int *rows_m, float *sc_m, unsigned int *rows_n, float *sc_n,
+               unsigned int *rows_t, float *sc_t, const long long *__restrict__ counts,
+               const float *__restrict__ topk_scores, const long long *__restrict__ topk_rows,
+               long long *pack) {
+    __shared__ unsigned int wsum[3][kSelThreads / 32];
+    if (blockIdx.x == 0) {
+        // allgather payload for the multi-GPU merge: counts | top-k rows | top-k score bits
+        const int k = a.topk;
+        if (threadIdx.x < 4) pack[threadIdx.x] = counts[threadIdx.x];
+        for (int i = threadIdx.x; i < k; i += kSelThreads) {
+            pack[4 + i] = topk_rows[i];
+            pack[4 + k + i] = (long long)__float_as_uint(topk_scores[i]);
+        }
+    }
+    const long long chunk = blockIdx.x;
+    const long long r0 = chunk * kChunkRows + (long long)threadIdx.x * kRowsPerThread;
+    float sc[kRowsPerThread];
+    load_chunk_scores(scores, n_rows, r0, sc);
+    unsigned int mm = 0, mn = 0, mt = 0;
+#pragma unroll
+    for (int j = 0; j < kRowsPerThread; ++j) {
+        const Flags f = classify(sc[j], a);
+        mm |= (unsigned int)f.m << j; mn |= (unsigned int)f.nm << j; mt |= (unsigned int)f.tie << j;
+    }
+    const unsigned int c[3] = {(unsigned int)__popc(mm), (unsigned int)__popc(mn), (unsigned int)__popc(mt)};
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    unsigned int inc[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        unsigned int v = c[q];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int u = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += u;
+        }
+        inc[q] = v;
+        if (lane == 31) wsum[q][wid] = v;
+    }
+    __syncthreads();
+    unsigned int *const out_rows[3] = {rows_m, rows_n, rows_t};
+    float *const out_sc[3] = {sc_m, sc_n, sc_t};
+    const unsigned int masks[3] = {mm, mn, mt};
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        unsigned int before = 0;
+        for (int w = 0; w < wid; ++w) before += wsum[q][w];
+        unsigned int at = chunk_offsets[q * n_chunks + chunk] + before + inc[q] - c[q];
+        if (c[q]) {
+#pragma unroll
+            for (int j = 0; j < kRowsPerThread; ++j)
+                if (masks[q] & (1u << j)) {
+                    out_rows[q][at] = (unsigned int)(r0 + j);
+                    out_sc[q][at] = sc[j];
+                    ++at;
+                }
+        }
+    }
+}
+
+// Multi-GPU merge (C1): `gathered` holds n_lists payloads of (4 + 2k) int64 as laid out above,
+// one per rank, after the NCCL allgather.  Counts are summed; the global top-k is found by exact
+// ranking of the n_lists * k candidates under (score descending, global row ascending).
+__global__ void __launch_bounds__(1024)
+merge_packed(const long long *__restrict__ gathered, const int n_lists, const int k, long long *out) {
+    const int per = 4 + 2 * k;
+    const int n = n_lists * k;
+    __shared__ unsigned int n_valid;
+    if (threadIdx.x == 0) n_valid = 0;
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        long long t = 0;
+        for (int l = 0; l < n_lists; ++l) t += gathered[(size_t)l * per + threadIdx.x];
+        out[threadIdx.x] = t;
+    }
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        out[4 + i] = -1;
+        out[4 + k + i] = (long long)0xff800000u;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int li = i / k, ii = i - li * k;
+        const long long row = gathered[(size_t)li * per + 4 + ii];
+        if (row < 0) continue;
+        const float sc = __uint_as_float((unsigned int)gathered[(size_t)li * per + 4 + k + ii]);
+        int rank = 0;
+        for (int j = 0; j < n; ++j) {
+            const int lj = j / k, jj = j - lj * k;
+            const long long r2 = gathered[(size_t)lj * per + 4 + jj];
+            if (r2 < 0) continue;
+            const float s2 = __uint_as_float((unsigned int)gathered[(size_t)lj * per + 4 + k + jj]);
+            rank += (s2 > sc) || (s2 == sc && r2 < row);
+        }
+        atomicAdd(&n_valid, 1u);
+        if (rank < k) {
+            out[4 + rank] = row;
+            out[4 + k + rank] = (long long)__float_as_uint(sc);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) out[3] = (long long)min((unsigned int)k, n_valid);
+}
+
+int fill_args(const vq_store *s, const vq_scan_params *p, ScanArgs *a) {
+    VQ_REQUIRE(p, "scan: null params");
+    VQ_REQUIRE(p->topk >= 0 && p->topk <= VQ_MAX_TOPK, "scan: topk %d outside 0..%d", p->topk, VQ_MAX_TOPK);
+    double den = 0.0;
+    for (int i = 0; i < VQ_MAX_STREAMS; ++i) {
+        a->w[i] = (i < s->n_streams) ? (float)p->weights[i] : 0.f;
+        if (i < s->n_streams) den += p->weights[i] * p->weights[i];
+    }
+    VQ_REQUIRE(den > 0.0, "scan: all stream weights are zero");
+    a->inv_den = (float)(1.0 / den);
+    a->inv_splits = (float)(1.0 / (double)s->n_splits);
+    a->th = p->threshold;
+    a->lo = p->lower_limit;
+    a->eps = p->eps;
+    a->topk = p->topk;
+    a->want_sims = p->want_sims;
+    return 0;
+}
+
+template <int S>
+void launch_smem(vq_store *s, const float *target_dev, const ScanArgs &a, int grid, cudaStream_t st) {
+    const int len4 = s->stream_len / 4;
+    const size_t smem = (size_t)S * len4 * sizeof(float4);
+    cudaFuncSetAttribute(scan_rows_smem<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    scan_rows_smem<S><<<grid, kScanThreads, smem, st>>>(
+        reinterpret_cast<const float4 *>(s->rows), reinterpret_cast<const float4 *>(target_dev),
+        s->inv_counts, a, s->n_rows, len4, s->scores, s->sims, s->hist);
+}
+
+}  // namespace
+
+extern "C" int vq_scan_enqueue(vq_store *s, const float *target_dev, const vq_scan_params *p, void *stream) {
+    VQ_REQUIRE(s && target_dev, "vq_scan_enqueue: null argument");
+    ScanArgs a;
+    if (int r = fill_args(s, p, &a)) return r;
+    VQ_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    if (a.want_sims && !s->sims)
+        VQ_CUDA(cudaMalloc((void **)&s->sims, (size_t)(s->n_rows > 0 ? s->n_rows : 1) * s->n_streams * sizeof(float)));
+    s->last_topk = a.topk;
+    const size_t smem_need = (size_t)s->n_streams * s->stream_len * sizeof(float);
+    VQ_REQUIRE(smem_need <= 200 * 1024, "scan: target of %zu bytes does not fit in shared memory", smem_need);
+    const int slot = s->ev_head;
+    s->ev_head = (s->ev_head + 1) % vq::kTimeRing;
+    if (s->ev_count < vq::kTimeRing) s->ev_count++;
+    VQ_CUDA(cudaEventRecord(s->ev_start[slot], st));
+    const int grid = s->sm_count * 3;
+    if (s->n_streams == 2 && s->stream_len == 1024) {
+        scan_rows_reg<2, 8><<<grid, kScanThreads, 0, st>>>(
+            reinterpret_cast<const float4 *>(s->rows), reinterpret_cast<const float4 *>(target_dev),
+            s->inv_counts, a, s->n_rows, s->scores, s->sims, s->hist);
+    } else {
+        switch (s->n_streams) {
+            case 1: launch_smem<1>(s, target_dev, a, grid, st); break;
+            case 2: launch_smem<2>(s, target_dev, a, grid, st); break;
+            case 3: launch_smem<3>(s, target_dev, a, grid, st); break;
+            default: launch_smem<4>(s, target_dev, a, grid, st); break;
+        }
+    }
+    VQ_CUDA(cudaEventRecord(s->ev_stop[slot], st));
+    const unsigned int sel_blocks = (unsigned int)(s->n_chunks > 0 ? s->n_chunks : 1);
+    const long long sel_chunks = (long long)sel_blocks;
+    select_count<<<sel_blocks, kSelThreads, 0, st>>>(s->scores, s->n_rows, a, s->hist, s->chunk_counts,
+                                                     sel_chunks, s->cand_count, s->cand_keys, s->cand_cap);
+    select_finish<<<2, kFinThreads, 0, st>>>(s->chunk_counts, s->chunk_offsets, sel_chunks,
+                                             (long long *)s->counts, s->hist, s->cand_count, s->cand_keys,
+                                             s->cand_cap, a.topk, s->first_global_row, s->topk_scores,
+                                             (long long *)s->topk_rows);
+    select_compact<<<sel_blocks, kSelThreads, 0, st>>>(
+        s->scores, s->n_rows, a, s->chunk_offsets, sel_chunks, s->list_rows[0], s->list_scores[0],
+        s->list_rows[1], s->list_scores[1], s->list_rows[2], s->list_scores[2], (const long long *)s->counts,
+        s->topk_scores, (const long long *)s->topk_rows, (long long *)s->pack);
+    VQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int vq_scan_wait(vq_store *s, void *stream, vq_scan_counts *out) {
+    VQ_REQUIRE(s, "vq_scan_wait: null store");
+    VQ_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    VQ_CUDA(cudaMemcpyAsync(s->counts_host, s->counts, 4 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    VQ_CUDA(cudaStreamSynchronize(st));
+    if (out) {
+        out->n_match = s->counts_host[0];
+        out->n_near = s->counts_host[1];
+        out->n_tie = s->counts_host[2];
+        out->n_topk = (int32_t)s->counts_host[3];
+        out->scan_ms = 0.f;
+        if (s->ev_count > 0) {
+            const int slot = (s->ev_head + vq::kTimeRing - 1) % vq::kTimeRing;
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, s->ev_start[slot], s->ev_stop[slot]) == cudaSuccess) out->scan_ms = ms;
+        }
+    }
+    return 0;
+}
+
+extern "C" int vq_scan(vq_store *s, const float *target, const vq_scan_params *p, vq_scan_counts *out) {
+    VQ_REQUIRE(s && target, "vq_scan: null argument");
+    VQ_CUDA(cudaSetDevice(s->device));
+    const size_t bytes = s->row_floats * sizeof(float);
+    memcpy(s->pinned_stage, target, bytes);
+    VQ_CUDA(cudaMemcpyAsync(s->target, s->pinned_stage, bytes, cudaMemcpyHostToDevice, s->stream));
+    if (int r = vq_scan_enqueue(s, s->target, p, s->stream)) return r;
+    return vq_scan_wait(s, s->stream, out);
+}
+
+static int fetch_list(vq_store *s, int which, int64_t cap, int64_t *rows_out, float *scores_out,
+                      const char *who) {
+    VQ_REQUIRE(s, "%s: null store", who);
+    VQ_CUDA(cudaSetDevice(s->device));
+    const int64_t n = s->counts_host[which];
+    VQ_REQUIRE(cap >= n, "%s: capacity %lld < %lld entries", who, (long long)cap, (long long)n);
+    if (n == 0) return 0;
+    if (rows_out) {
+        std::vector<uint32_t> tmp((size_t)n);
+        VQ_CUDA(cudaMemcpy(tmp.data(), s->list_rows[which], (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < n; ++i) rows_out[i] = s->first_global_row + (int64_t)tmp[(size_t)i];
+    }
+    if (scores_out)
+        VQ_CUDA(cudaMemcpy(scores_out, s->list_scores[which], (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int vq_fetch_matches(vq_store *s, int64_t cap, int64_t *rows_out, float *scores_out) {
+    return fetch_list(s, 0, cap, rows_out, scores_out, "vq_fetch_matches");
+}
+extern "C" int vq_fetch_near(vq_store *s, int64_t cap, int64_t *rows_out, float *scores_out) {
+    return fetch_list(s, 1, cap, rows_out, scores_out, "vq_fetch_near");
+}
+extern "C" int vq_fetch_ties(vq_store *s, int64_t cap, int64_t *rows_out, float *scores_out) {
+    return fetch_list(s, 2, cap, rows_out, scores_out, "vq_fetch_ties");
+}
+
+extern "C" int vq_fetch_topk(vq_store *s, int32_t cap, int64_t *rows_out, float *scores_out) {
+    VQ_REQUIRE(s, "vq_fetch_topk: null store");
+    VQ_CUDA(cudaSetDevice(s->device));
+    const int n = (int)s->counts_host[3];
+    VQ_REQUIRE(cap >= n, "vq_fetch_topk: capacity %d < %d entries", cap, n);
+    if (n == 0) return 0;
+    if (rows_out) VQ_CUDA(cudaMemcpy(rows_out, s->topk_rows, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    if (scores_out) VQ_CUDA(cudaMemcpy(scores_out, s->topk_scores, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int vq_fetch_scores(vq_store *s, int64_t first_row, int64_t n_rows, float *scores_out) {
+    VQ_REQUIRE(s && (scores_out || n_rows == 0), "vq_fetch_scores: null argument");
+    VQ_REQUIRE(first_row >= 0 && n_rows >= 0 && first_row + n_rows <= s->n_rows, "vq_fetch_scores: range outside shard");
+    VQ_CUDA(cudaSetDevice(s->device));
+    if (n_rows)
+        VQ_CUDA(cudaMemcpy(scores_out, s->scores + first_row, (size_t)n_rows * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int vq_fetch_sims(vq_store *s, int64_t first_row, int64_t n_rows, float *sims_out) {
+    VQ_REQUIRE(s && (sims_out || n_rows == 0), "vq_fetch_sims: null argument");
+    VQ_REQUIRE(s->sims, "vq_fetch_sims: the last scan did not keep similarities (want_sims = 0)");
+    VQ_REQUIRE(first_row >= 0 && n_rows >= 0 && first_row + n_rows <= s->n_rows, "vq_fetch_sims: range outside shard");
+    VQ_CUDA(cudaSetDevice(s->device));
+    if (n_rows)
+        VQ_CUDA(cudaMemcpy(sims_out, s->sims + (size_t)first_row * s->n_streams,
+                           (size_t)n_rows * s->n_streams * sizeof(float), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int vq_scan_view(vq_store *s, vq_scan_device_view *out) {
+    VQ_REQUIRE(s && out, "vq_scan_view: null argument");
+    out->scores_dev = s->scores;
+    out->sims_dev = s->sims;
+    out->counts_dev = s->counts;
+    out->topk_scores_dev = s->topk_scores;
+    out->topk_rows_dev = s->topk_rows;
+    out->match_rows_dev = s->list_rows[0];
+    out->near_rows_dev = s->list_rows[1];
+    return 0;
+}
+
+extern "C" int vq_scan_payload(vq_store *s, const int64_t **payload_dev, int32_t *n_int64) {
+    VQ_REQUIRE(s && payload_dev && n_int64, "vq_scan_payload: null argument");
+    *payload_dev = s->pack;
+    *n_int64 = 4 + 2 * s->last_topk;
+    return 0;
+}
+
+extern "C" int vq_merge_payloads_enqueue(int device, const int64_t *gathered_dev, int32_t n_lists, int32_t topk,
+                                         int64_t *merged_dev, void *stream) {
+    VQ_REQUIRE(gathered_dev && merged_dev && n_lists >= 1 && topk >= 0 && topk <= VQ_MAX_TOPK,
+               "vq_merge_payloads_enqueue: bad argument");
+    VQ_CUDA(cudaSetDevice(device));
+    merge_packed<<<1, 1024, 0, (cudaStream_t)stream>>>((const long long *)gathered_dev, n_lists, topk,
+                                                       (long long *)merged_dev);
+    VQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int vq_scan_kernel_times(vq_store *s, int32_t cap, float *ms_out, int32_t *n_out) {
+    VQ_REQUIRE(s && n_out, "vq_scan_kernel_times: null argument");
+    VQ_CUDA(cudaSetDevice(s->device));
+    int n = s->ev_count < cap ? s->ev_count : cap;
+    int got = 0;
+    for (int i = 0; i < n; ++i) {
+        const int slot = (s->ev_head + vq::kTimeRing - n + i) % vq::kTimeRing;
+        float ms = 0.f;
+        cudaError_t e = cudaEventElapsedTime(&ms, s->ev_start[slot], s->ev_stop[slot]);
+        if (e == cudaSuccess && ms_out) ms_out[got++] = ms;
+    }
+    cudaGetLastError();
+    *n_out = got;
+    s->ev_count = 0;
+    return 0;
+}
+
+extern "C" int vq_merge_topk(int32_t n_lists, int32_t k, const float *scores, const int64_t *rows,
+                             float *scores_out, int64_t *rows_out, int32_t *n_out) {
+    VQ_REQUIRE(n_lists >= 0 && k >= 0 && scores && rows && scores_out && rows_out && n_out,
+               "vq_merge_topk: bad argument");
+    std::vector<std::pair<float, int64_t>> all;
+    all.reserve((size_t)n_lists * k);
+    for (int64_t i = 0; i < (int64_t)n_lists * k; ++i)
+        if (rows[i] >= 0) all.emplace_back(scores[i], rows[i]);
+    std::sort(all.begin(), all.end(), [](const std::pair<float, int64_t> &x, const std::pair<float, int64_t> &y) {
+        return x.first > y.first || (x.first == y.first && x.second < y.second);
+    });
+    const int n = (int)std::min<size_t>(all.size(), (size_t)k);
+    for (int i = 0; i < n; ++i) {
+        scores_out[i] = all[(size_t)i].first;
+        rows_out[i] = all[(size_t)i].second;
+    }
+    *n_out = n;
+    return 0;
+}

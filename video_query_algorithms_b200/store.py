@@ -1,0 +1,423 @@
+"""HBM-resident feature store and its scan API (host side of include/vq.h).
+
+Replaces the per-job HTTP pull of `Ticket._get_candidate_features` (reference
+src/models/ticket.py:358-382): a search set's feature rows are laid out once, clip-major
+`[clip][stream][split][dim]` fp32, sharded by contiguous clip range over the GPUs of the box, and
+stay resident across broker ticks.  Row order is the order of first appearance of each clip id in
+the `search-sets/features` response — the insertion order of the reference's `scores` dict, which
+its seeded `random.sample` depends on (ticket.py:326-333).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import ScanCounts, ScanParams, VQError, check, lib, ptr
+
+
+@dataclass
+class ScanResult:
+    n_match: int
+    n_near: int
+    n_tie: int
+    n_topk: int
+    scan_ms: float                 # device time of the scan kernel, max over shards
+
+
+class Shard:
+    """One vq_store on one device holding global rows [first, first + n)."""
+
+    def __init__(self, device, n_rows, n_streams, n_splits, dim, first_global_row=0):
+        self.handle = C.c_void_p()
+        check(lib().vq_store_create(C.byref(self.handle), device, n_rows, n_streams, n_splits, dim,
+                                    first_global_row), "vq_store_create")
+        self.device, self.n_rows, self.first = device, n_rows, first_global_row
+        self.n_streams, self.n_splits, self.dim = n_streams, n_splits, dim
+
+    def close(self):
+        if self.handle:
+            lib().vq_store_destroy(self.handle)
+            self.handle = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def device_ptr(self):
+        p = C.c_void_p()
+        check(lib().vq_store_device_ptr(self.handle, C.byref(p)), "vq_store_device_ptr")
+        return p.value
+
+
+def make_params(weights, threshold, lower_limit, eps, topk=0, want_sims=False):
+    p = ScanParams()
+    for i, w in enumerate(weights):
+        p.weights[i] = float(w)
+    p.threshold, p.lower_limit, p.eps = float(threshold), float(lower_limit), float(eps)
+    p.topk, p.want_sims = int(topk), int(bool(want_sims))
+    return p
+
+
+class FeatureStore:
+    """A search set's features in HBM, as one shard per device."""
+
+    def __init__(self, n_rows, streams, splits, dim=1024, devices=None, clip_ids=None,
+                 first_global_row=0):
+        n_dev = C.c_int()
+        check(lib().vq_device_count(C.byref(n_dev)), "vq_device_count")
+        if n_dev.value < 1:
+            raise VQError("no CUDA device visible: the scoring path has no CPU fallback")
+        if devices is None:
+            devices = list(range(n_dev.value)) if n_rows >= 65536 * n_dev.value else [0]
+        self.streams = tuple(streams)
+        self.splits = [int(p) for p in splits]
+        self.dim, self.n_rows, self.first_global_row = int(dim), int(n_rows), int(first_global_row)
+        self.row_shape = (len(self.streams), len(self.splits), self.dim)
+        per = -(-self.n_rows // len(devices)) if self.n_rows else 0
+        self.shards = []
+        for i, dev in enumerate(devices):
+            lo = min(i * per, self.n_rows)
+            hi = min(lo + per, self.n_rows)
+            if hi > lo or i == 0:
+                self.shards.append(Shard(dev, hi - lo, len(self.streams), len(self.splits), self.dim,
+                                         self.first_global_row + lo))
+        self.clip_ids = None
+        self._row_of = None
+        self.present = None          # bool [N, S, P] when some clip lacks some split, else None
+        if clip_ids is not None:
+            self.set_clip_ids(clip_ids)
+        self.last = None
+
+    # ------------------------------------------------------------------ construction
+    def set_clip_ids(self, clip_ids):
+        self.clip_ids = np.asarray(clip_ids, dtype=np.int64)
+        assert self.clip_ids.shape == (self.n_rows,)
+        self._row_of = None
+
+    def _index(self):
+        if self._row_of is None:
+            self._row_of = {int(c): i for i, c in enumerate(self.clip_ids)}
+        return self._row_of
+
+    def row_of(self, clip_id):
+        return self._index()[int(clip_id)]
+
+    def has_clip(self, clip_id):
+        return clip_id is not None and int(clip_id) in self._index()
+
+    def rows_of(self, clip_ids):
+        return np.array([self.first_global_row + self.row_of(c) for c in clip_ids], dtype=np.int64)
+
+    def _shard_of(self, global_row):
+        for sh in self.shards:
+            if sh.first <= global_row < sh.first + sh.n_rows:
+                return sh
+        raise VQError("row %d is not in the store" % global_row)
+
+    def upload(self, first_row, rows):
+        """rows: float32 [n, S, P, dim] (or [n, S*P*dim]) for local rows first_row.. of the store."""
+        rows = np.ascontiguousarray(rows, dtype=np.float32).reshape(-1, int(np.prod(self.row_shape)))
+        g0 = self.first_global_row + first_row
+        for sh in self.shards:
+            lo, hi = max(g0, sh.first), min(g0 + rows.shape[0], sh.first + sh.n_rows)
+            if hi > lo:
+                part = rows[lo - g0:hi - g0]
+                check(lib().vq_store_upload(sh.handle, lo - sh.first, hi - lo, ptr(part)), "vq_store_upload")
+
+    def download(self, first_row, n_rows):
+        out = np.empty((n_rows,) + self.row_shape, np.float32)
+        g0 = self.first_global_row + first_row
+        for sh in self.shards:
+            lo, hi = max(g0, sh.first), min(g0 + n_rows, sh.first + sh.n_rows)
+            if hi > lo:
+                part = np.empty((hi - lo,) + self.row_shape, np.float32)
+                check(lib().vq_store_download(sh.handle, lo - sh.first, hi - lo, ptr(part)), "vq_store_download")
+                out[lo - g0:hi - g0] = part
+        return out
+
+    def set_present(self, present):
+        """present: bool [N, S, P]; slots that are False must have been uploaded as zeros."""
+        present = np.asarray(present, dtype=bool)
+        if present.all():
+            self.present = None
+            for sh in self.shards:
+                check(lib().vq_store_set_split_weights(sh.handle, None), "vq_store_set_split_weights")
+            return
+        self.present = present
+        self._apply_split_weights(present.sum(axis=2))
+
+    def _apply_split_weights(self, counts):
+        if (counts == 0).any():
+            raise VQError("a clip has no feature row at all for one stream; the reference raises KeyError "
+                          "for such a search set (ticket.py:177)")
+        inv = (1.0 / counts).astype(np.float32)
+        for sh in self.shards:
+            lo = sh.first - self.first_global_row
+            part = np.ascontiguousarray(inv[lo:lo + sh.n_rows])
+            check(lib().vq_store_set_split_weights(sh.handle, ptr(part)), "vq_store_set_split_weights")
+
+    def fill_synthetic(self, seed, means=None):
+        m = None if means is None else np.asarray(means, dtype=np.float32)
+        for sh in self.shards:
+            check(lib().vq_store_fill_synthetic(sh.handle, int(seed), ptr(m)), "vq_store_fill_synthetic")
+
+    @classmethod
+    def from_feature_rows(cls, feature_rows, streams, feature_name, devices=None):
+        """Build from the `search-sets/features` API response (list of feature dicts), applying the
+        reference's filters (ticket.py:374-381: stream in streams, name == feature_name)."""
+        streams = tuple(streams)
+        order, seen, splits = [], set(), set()
+        for tf in feature_rows:
+            if tf["dnn_stream_id"] in streams and tf["name"] == feature_name:
+                splits.add(int(tf["dnn_stream_split"]))
+                c = tf["video_clip_id"]
+                if c not in seen:
+                    seen.add(c)
+                    order.append(c)
+        splits = sorted(splits)
+        if not order:
+            raise VQError("search set has no '%s' features for streams %s" % (feature_name, streams))
+        dim = None
+        for tf in feature_rows:
+            if tf["dnn_stream_id"] in streams and tf["name"] == feature_name:
+                dim = len(tf["feature_vector"])
+                break
+        row = {c: i for i, c in enumerate(order)}
+        s_of = {s: i for i, s in enumerate(streams)}
+        p_of = {p: i for i, p in enumerate(splits)}
+        X = np.zeros((len(order), len(streams), len(splits), dim), np.float32)
+        present = np.zeros((len(order), len(streams), len(splits)), bool)
+        for tf in feature_rows:
+            if tf["dnn_stream_id"] in streams and tf["name"] == feature_name:
+                i, s, p = row[tf["video_clip_id"]], s_of[tf["dnn_stream_id"]], p_of[int(tf["dnn_stream_split"])]
+                X[i, s, p] = tf["feature_vector"]       # later duplicates overwrite, like the dict does
+                present[i, s, p] = True
+        st = cls(len(order), streams, splits, dim, devices=devices, clip_ids=order)
+        st.upload(0, X)
+        st.set_present(present)
+        return st
+
+    def close(self):
+        for sh in self.shards:
+            sh.close()
+        self.shards = []
+
+    # ------------------------------------------------------------------ target layout
+    def pack_target(self, target_features, dtype=np.float32):
+        """{stream: {split: vector}} -> [S, P, dim] in the store's slot order; splits the target
+        lacks are zero (they then contribute nothing, ticket.py:149-152)."""
+        T = np.zeros(self.row_shape, dtype)
+        have = np.zeros(self.row_shape[:2], bool)
+        for si, s in enumerate(self.streams):
+            for pi, p in enumerate(self.splits):
+                v = target_features.get(s, {}).get(p)
+                if v is not None:
+                    T[si, pi] = np.asarray(v, dtype=np.float64)
+                    have[si, pi] = True
+        return T, have
+
+    def _sync_split_weights_for_target(self, have):
+        """The reference averages over splits that BOTH the target and the clip have."""
+        if have.all() and self.present is None:
+            return
+        present = np.ones((self.n_rows,) + self.row_shape[:2], bool) if self.present is None else self.present
+        eff = present & have[None]
+        key = eff.tobytes() if eff.size < (1 << 22) else None
+        if getattr(self, "_eff_key", None) != key or key is None:
+            self._apply_split_weights(eff.sum(axis=2))
+            self._eff_key = key
+
+    # ------------------------------------------------------------------ scan
+    def scan(self, target_features, weights, threshold, lower_limit, eps, topk=0, want_sims=False):
+        """One fused pass: similarities, scores, match / near-miss / tie lists, top-k."""
+        T, have = self.pack_target(target_features, np.float32)
+        self._sync_split_weights_for_target(have)
+        w = [weights[s] for s in self.streams] if isinstance(weights, dict) else list(weights)
+        p = make_params(w, threshold, lower_limit, eps, topk, want_sims)
+        Tc = np.ascontiguousarray(T)
+        # enqueue on every shard first (each has its own stream), then wait: shards run concurrently
+        if len(self.shards) == 1:
+            c = ScanCounts()
+            check(lib().vq_scan(self.shards[0].handle, ptr(Tc), C.byref(p), C.byref(c)), "vq_scan")
+            counts = [c]
+        else:
+            counts = self._scan_multi(Tc, p)
+        self.last = ScanResult(sum(c.n_match for c in counts), sum(c.n_near for c in counts),
+                               sum(c.n_tie for c in counts), 0, max(c.scan_ms for c in counts))
+        self._last_counts = counts
+        self._last_topk = topk
+        return self.last
+
+    def _scan_multi(self, Tc, p):
+        import threading
+        counts = [ScanCounts() for _ in self.shards]
+        errs = []
+
+        def run(i):
+            try:
+                check(lib().vq_scan(self.shards[i].handle, ptr(Tc), C.byref(p), C.byref(counts[i])), "vq_scan")
+            except Exception as e:       # surfaced below
+                errs.append(e)
+
+        ts = [threading.Thread(target=run, args=(i,)) for i in range(len(self.shards))]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        if errs:
+            raise errs[0]
+        return counts
+
+    def _fetch_list(self, fn, attr):
+        rows, scores = [], []
+        for sh, c in zip(self.shards, self._last_counts):
+            n = getattr(c, attr)
+            r = np.empty(n, np.int64)
+            s = np.empty(n, np.float32)
+            check(fn(sh.handle, n, ptr(r), ptr(s)), attr)
+            rows.append(r)
+            scores.append(s)
+        return np.concatenate(rows), np.concatenate(scores)
+
+    def matches(self):
+        """(global rows ascending, fp32 scores) of {score >= threshold}."""
+        return self._fetch_list(lib().vq_fetch_matches, "n_match")
+
+    def near_misses(self):
+        return self._fetch_list(lib().vq_fetch_near, "n_near")
+
+    def ties(self):
+        return self._fetch_list(lib().vq_fetch_ties, "n_tie")
+
+    def topk(self):
+        k = self._last_topk
+        if k == 0:
+            return np.empty(0, np.int64), np.empty(0, np.float32)
+        n_l = len(self.shards)
+        sc = np.full((n_l, k), -np.inf, np.float32)
+        rw = np.full((n_l, k), -1, np.int64)
+        for i, (sh, c) in enumerate(zip(self.shards, self._last_counts)):
+            r = np.empty(c.n_topk, np.int64)
+            s = np.empty(c.n_topk, np.float32)
+            check(lib().vq_fetch_topk(sh.handle, c.n_topk, ptr(r), ptr(s)), "vq_fetch_topk")
+            sc[i, :c.n_topk], rw[i, :c.n_topk] = s, r
+        if n_l == 1:
+            n = self._last_counts[0].n_topk
+            return rw[0, :n].copy(), sc[0, :n].copy()
+        so, ro, n = np.empty(k, np.float32), np.empty(k, np.int64), C.c_int32()
+        check(lib().vq_merge_topk(n_l, k, ptr(sc), ptr(rw), ptr(so), ptr(ro), C.byref(n)), "vq_merge_topk")
+        return ro[:n.value], so[:n.value]
+
+    def scores(self):
+        out = np.empty(self.n_rows, np.float32)
+        for sh in self.shards:
+            lo = sh.first - self.first_global_row
+            part = np.empty(sh.n_rows, np.float32)
+            check(lib().vq_fetch_scores(sh.handle, 0, sh.n_rows, ptr(part)), "vq_fetch_scores")
+            out[lo:lo + sh.n_rows] = part
+        return out
+
+    def sims(self):
+        out = np.empty((self.n_rows, len(self.streams)), np.float32)
+        for sh in self.shards:
+            lo = sh.first - self.first_global_row
+            part = np.empty((sh.n_rows, len(self.streams)), np.float32)
+            check(lib().vq_fetch_sims(sh.handle, 0, sh.n_rows, ptr(part)), "vq_fetch_sims")
+            out[lo:lo + sh.n_rows] = part
+        return out
+
+    # ------------------------------------------------------------------ labelled subset (fp64)
+    def labelled_sims(self, target_features, global_rows):
+        """float64 [n, S] similarities of the given rows (any shard) against an fp64 target."""
+        T, have = self.pack_target(target_features, np.float64)
+        self._sync_split_weights_for_target(have)
+        rows = np.asarray(global_rows, dtype=np.int64)
+        out = np.empty((len(rows), len(self.streams)), np.float64)
+        Tc = np.ascontiguousarray(T)
+        for sh in self.shards:
+            sel = np.flatnonzero((rows >= sh.first) & (rows < sh.first + sh.n_rows))
+            if len(sel):
+                r = np.ascontiguousarray(rows[sel])
+                o = np.empty((len(sel), len(self.streams)), np.float64)
+                check(lib().vq_labelled_sims(sh.handle, ptr(Tc), ptr(r), len(sel), ptr(o)), "vq_labelled_sims")
+                out[sel] = o
+        return out
+
+    def bootstrap_target(self, valid_rows, invalid_rows, mu):
+        """float64 [S, P, dim]: new target from labelled rows (target_clip.py:161-261), solved on
+        the GPU that holds the rows.  Labelled rows spread over several shards are first gathered
+        onto the first shard's device through a scratch store."""
+        valid = np.ascontiguousarray(valid_rows, dtype=np.int64)
+        invalid = np.ascontiguousarray(invalid_rows if invalid_rows is not None else [], dtype=np.int64)
+        allr = np.concatenate([valid, invalid])
+        sh = self._shard_of(int(allr[0]))
+        if not all(sh.first <= r < sh.first + sh.n_rows for r in allr):
+            return self._bootstrap_gathered(valid, invalid, mu)
+        out = np.empty(self.row_shape, np.float64)
+        check(lib().vq_bootstrap_target(sh.handle, ptr(valid), len(valid), ptr(invalid) if len(invalid) else None,
+                                        len(invalid), float(mu), ptr(out)), "vq_bootstrap_target")
+        return out
+
+    def _bootstrap_gathered(self, valid, invalid, mu):
+        allr = np.concatenate([valid, invalid])
+        uniq = np.unique(allr)
+        feats = np.concatenate([self.download(int(r) - self.first_global_row, 1) for r in uniq])
+        tmp = FeatureStore(len(uniq), self.streams, self.splits, self.dim, devices=[self.shards[0].device])
+        try:
+            tmp.upload(0, feats)
+            pos = {int(r): i for i, r in enumerate(uniq)}
+            v = np.array([pos[int(r)] for r in valid], np.int64)
+            iv = np.array([pos[int(r)] for r in invalid], np.int64)
+            return tmp.bootstrap_target(v, iv, mu)
+        finally:
+            tmp.close()
+
+
+def loss_grid(sims, labels, weight_grid, threshold_grid, ballast, replicates=None, device=0):
+    """losses [R, n_w, n_th] (float64) on the GPU — hyperparameter.py:56-65 for R index sets.
+    replicates: list of index arrays into the L labelled clips; None = one replicate of all L."""
+    sims = np.ascontiguousarray(sims, dtype=np.float64)
+    L = sims.shape[0]
+    if sims.shape[1] != 2:
+        raise VQError("optimize_weights is defined for exactly two streams (hyperparameter.py:58)")
+    lab = np.ascontiguousarray(np.asarray(labels).astype(bool).astype(np.uint8))
+    if replicates is None:
+        replicates = [np.arange(L, dtype=np.int32)]
+    off = np.zeros(len(replicates) + 1, np.int32)
+    off[1:] = np.cumsum([len(r) for r in replicates])
+    idx = np.ascontiguousarray(np.concatenate([np.asarray(r, dtype=np.int32) for r in replicates]))
+    wg = np.ascontiguousarray(weight_grid, dtype=np.float64)
+    tg = np.ascontiguousarray(threshold_grid, dtype=np.float64)
+    out = np.empty((len(replicates), len(wg), len(tg)), np.float64)
+    check(lib().vq_loss_grid(device, ptr(sims), ptr(lab), L, ptr(wg), len(wg), ptr(tg), len(tg), float(ballast),
+                             ptr(off), ptr(idx), len(replicates), ptr(out)), "vq_loss_grid")
+    return out
+
+
+# One store per (api url, search set, streams, feature name); outlives broker ticks.
+_REGISTRY = {}
+
+
+def get_store(key, builder):
+    st = _REGISTRY.get(key)
+    if st is None:
+        st = builder()
+        _REGISTRY[key] = st
+    return st
+
+
+def register_store(key, store):
+    _REGISTRY[key] = store
+
+
+def invalidate(key=None):
+    """Drop a cached store (or all): call when load_db.py has added clips to the search set."""
+    for k in [key] if key is not None else list(_REGISTRY):
+        st = _REGISTRY.pop(k, None)
+        if st is not None:
+            st.close()

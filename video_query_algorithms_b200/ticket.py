@@ -1,0 +1,413 @@
+"""Job ticket: scoring and selection for one query update, backed by the HBM store.
+
+Mirror of reference `src/models/ticket.py`: same constructor, attributes and method names, same
+API actions.  What changes is where the arithmetic runs:
+  * `_get_candidate_features` returns the resident FeatureStore instead of a nested dict built
+    from a full HTTP download (ticket.py:358-382);
+  * `compute_similarities` / `compute_scores` only record the target and the weights; the work is
+    one fused GPU scan issued by `select_clips_to_review` (or by the first read of `.scores` /
+    `.similarities`, which are lazy read-only mappings over device results);
+  * the two candidate scans (ticket.py:326-327) come back as row lists in database order, and the
+    seeded sampling (:333, :341) runs on the host with Python's `random`, consuming it exactly as
+    the reference does.
+"""
+from __future__ import annotations
+
+import csv
+import json
+import logging
+import os
+import random
+from collections.abc import Mapping
+from datetime import datetime, timedelta
+from time import sleep
+
+import numpy as np
+
+from . import store as _store
+from ._ffi import VQError
+
+try:
+    from requests import ConnectionError
+except Exception:                           # pragma: no cover
+    ConnectionError = OSError
+
+
+def _default_client(api_url):
+    """coreapi client with token auth, as the reference builds it (ticket.py:36-37,
+    api/authenticate.py:6-24).  Only used when no client is injected."""
+    import coreapi
+    import requests
+    response = requests.post(os.path.join(api_url, 'api-token-auth/'),
+                             data={'username': os.environ['API_CLIENT_USERNAME'],
+                                   'password': os.environ['API_CLIENT_PASSWORD']})
+    auth = None
+    if response.status_code == requests.codes.ok:
+        auth = coreapi.auth.TokenAuthentication(scheme='Token', token=response.json()['token'])
+    else:
+        print("Authentication failed: ")
+    return coreapi.Client(auth=auth)
+
+
+class _ScoreView(Mapping):
+    """Read-only {video_clip_id: score} over the device score array, in database order."""
+
+    def __init__(self, ticket):
+        self._t = ticket
+        self._arr = None
+
+    def _scores(self):
+        if self._arr is None:
+            self._t._ensure_scan()
+            self._arr = self._t.feature_store().scores()
+        return self._arr
+
+    def __getitem__(self, clip):
+        st = self._t.feature_store()
+        if not st.has_clip(clip):
+            raise KeyError(clip)
+        return float(self._scores()[st.row_of(clip)])
+
+    def __contains__(self, clip):
+        return self._t.feature_store().has_clip(clip)
+
+    def __iter__(self):
+        return (int(c) for c in self._t.feature_store().clip_ids)
+
+    def __len__(self):
+        return self._t.feature_store().n_rows
+
+    def array(self):
+        return self._scores()
+
+
+class _SimilarityView(Mapping):
+    """Read-only {video_clip_id: {stream: [avg similarity, n_splits]}} (ticket.py:124)."""
+
+    def __init__(self, ticket):
+        self._t = ticket
+        self._arr = None
+
+    def _sims(self):
+        if self._arr is None:
+            self._t._ensure_scan(want_sims=True)
+            self._arr = self._t.feature_store().sims()
+        return self._arr
+
+    def __getitem__(self, clip):
+        st = self._t.feature_store()
+        if not st.has_clip(clip):
+            raise KeyError(clip)
+        r = st.row_of(clip)
+        have = self._t._target_have
+        out = {}
+        for si, s in enumerate(st.streams):
+            pres = have[si] if st.present is None else (st.present[r, si] & have[si])
+            out[s] = [float(self._sims()[r, si]), int(np.sum(pres))]
+        return out
+
+    def __iter__(self):
+        return (int(c) for c in self._t.feature_store().clip_ids)
+
+    def __len__(self):
+        return self._t.feature_store().n_rows
+
+    def array(self):
+        return self._sims()
+
+
+class Ticket:
+    def __init__(self, update_object, api_url, client=None, schema=None, store=None, devices=None):
+        """update_object: the job dict of `APIRepository.get_status()` (ticket.py:18-33).
+        client/schema: an injected coreapi-style client (tests, embedding); store: a pre-built
+        FeatureStore for the job's search set (otherwise built once from `search-sets/features`
+        and cached for later ticks)."""
+        self.api_url = api_url
+        self.client = client if client is not None else _default_client(api_url)
+        self.schema = schema if schema is not None else self.client.get(os.path.join(api_url, "docs"))
+        self.query_id = update_object["query_id"]
+        self.video_id = update_object["video_id"]
+        self.ref_clip = update_object["ref_clip"]
+        self.ref_clip_id = update_object["ref_clip_id"]
+        self.search_set = update_object["search_set"]
+        self.number_of_matches_to_review = update_object["number_of_matches_to_review"]
+        self.dynamic_target_adjustment = update_object["dynamic_target_adjustment"]
+        self.latest_query_result = update_object.get("latest_query_result")
+        if "matches" in update_object:
+            self.matches = update_object["matches"]
+        self.user_matches = update_object.get("user_matches", {})
+        self.target = None
+        self.similarities = {}
+        self.scores = {}
+        # --- B200 path state
+        self.devices = devices
+        self.features_from_store = False   # True: read clip features back from HBM, not the API
+        self._store = store
+        self._hp = None
+        self._weights = None
+        self._target_have = None
+        self._scanned = False
+        self._have_sims = False
+        self.topk = 0                    # optional ranked list size (BASELINE "top-100")
+        self.ranked = None               # (clip ids, scores) of the last scan's top-k
+        self.tie_band = []               # clip ids within COMPUTE_EPS of a set boundary
+        self.last_scan = None
+
+    # ------------------------------------------------------------------ API plumbing
+    def add_matches_to_database(self, new_result_id):
+        for video_clip, score in self.matches.items():
+            self.create_match(new_result_id, score, self.user_matches.get(str(video_clip)), video_clip)
+
+    def add_note(self, note):
+        result = self._request(["queries", "read"], {"id": self.query_id})
+        new_notes = result["notes"] + '\n\n' + note if result["notes"] else note
+        self._request(["queries", "partial_update"], {"id": self.query_id, "notes": new_notes})
+
+    def catch_errors(self, job_type):
+        """Fatal / recoverable query errors (ticket.py:80-110)."""
+        fatal, recoverable = [], []
+        if self.ref_clip_id is None:
+            fatal.append("*** Fatal Error: A video clip corresponding to the reference time does "
+                         "not exist in the database. ***")
+        if job_type != "new" and not self.matches:
+            fatal.append("*** Fatal Error: This is not a new query but there are 0 matches computed "
+                         "for the previous round. Cannot update without matches. Check database consistency "
+                         "for this query")
+        if job_type != "new" and self.dynamic_target_adjustment is True:
+            if not any(match["user_match"] is True for match in self.matches):
+                recoverable.append('*** Error: Dynamic target adjustment is True but there are no user matches '
+                                   'provided for the previous round. Changing dynamic target adjustment to False')
+                self.dynamic_target_adjustment = False
+        return "\n".join(fatal), "\n".join(recoverable)
+
+    def change_process_state(self, process_state, message=None):
+        result = self._request(["queries", "partial_update"], {"id": self.query_id, "process_state": process_state})
+        if message:
+            self.add_note(message)
+        return result["process_state"]
+
+    def create_match(self, qresult, score, user_match, video_clip):
+        self._request(["matches", "create"], {"query_result": qresult, "score": score,
+                                              "user_match": user_match, "video_clip": video_clip})
+
+    def create_query_result(self, nround, hyperparameters):
+        weights_values = [hyperparameters.weights[stream] for stream in hyperparameters.streams]
+        params = {"round": nround, "match_criterion": hyperparameters.threshold, "weights": weights_values,
+                  "query": self.query_id, "bootstrapped_target": json.dumps(self.target.target_features)}
+        return self._request(["query-results", "create"], params)["id"]
+
+    def _request(self, action, params):
+        while True:
+            try:
+                return self.client.action(self.schema, action, params=params)
+            except ConnectionError:
+                sleep(0.05)
+                logging.warning('Try API request again: action = {}, params = {}'.format(action, params))
+
+    def _post_file(self, action, params):
+        while True:
+            try:
+                return self.client.action(self.schema, action, params=params, encoding="multipart/form-data")
+            except ConnectionError:
+                sleep(0.05)
+                logging.warning('Try API file post by Ticket again: action = {}, params = {}'.format(action, params))
+
+    # ------------------------------------------------------------------ store
+    def feature_store(self, optional=False):
+        if self._store is None and not optional:
+            if self._hp is None:
+                raise VQError("ticket has no feature store yet: call attach_store / compute_similarities first")
+            self._get_candidate_features(None, self._hp)
+        return self._store
+
+    def _get_candidate_features(self, splits, hyperparameters):
+        """The resident store of this job's search set (built on first use from the same API action
+        the reference calls every job, ticket.py:363-365)."""
+        if self._store is not None:
+            return self._store
+        key = (self.api_url, self.search_set, tuple(hyperparameters.streams), hyperparameters.feature_name)
+
+        def build():
+            rows = self._request(["search-sets", "features"], {"id": self.search_set})
+            return _store.FeatureStore.from_feature_rows(rows, hyperparameters.streams,
+                                                         hyperparameters.feature_name, devices=self.devices)
+        self._store = _store.get_store(key, build)
+        return self._store
+
+    def attach_store(self, hyperparameters):
+        """Resolve the store before the target is built (TargetClip reads labelled rows from it)."""
+        self._hp = hyperparameters
+        return self._get_candidate_features(None, hyperparameters)
+
+    # ------------------------------------------------------------------ scoring (A3, A4)
+    def compute_similarities(self, hyperparameters):
+        """Bind target and store; similarities materialise on first read (ticket.py:120-163)."""
+        self._hp = hyperparameters
+        st = self._get_candidate_features(self.target.splits, hyperparameters)
+        _, self._target_have = st.pack_target(self.target.target_features)
+        self._scanned = self._have_sims = False
+        self.similarities = _SimilarityView(self)
+
+    def compute_scores(self, weights):
+        """Record the stream weights; scores materialise with the next scan (ticket.py:165-180)."""
+        self._weights = dict(weights)
+        self._scanned = self._have_sims = False
+        self.scores = _ScoreView(self)
+
+    def _eps(self):
+        return float(os.environ["COMPUTE_EPS"])
+
+    def _scan(self, threshold, lower_limit, want_sims=False):
+        st = self.feature_store()
+        weights = self._weights if self._weights is not None else (
+            self._hp.weights or self._hp.default_weights)
+        want_sims = want_sims or self._have_sims
+        self.last_scan = st.scan(self.target.target_features, [weights[s] for s in st.streams],
+                                 threshold, lower_limit, self._eps(), topk=self.topk, want_sims=want_sims)
+        self._scanned, self._have_sims = True, want_sims
+        if isinstance(self.scores, _ScoreView):
+            self.scores._arr = None
+        if isinstance(self.similarities, _SimilarityView):
+            self.similarities._arr = None
+        if self.topk:
+            rows, sc = st.topk()
+            self.ranked = (st.clip_ids[rows - st.first_global_row], sc)
+        return self.last_scan
+
+    def _ensure_scan(self, want_sims=False):
+        """Run the scan if `.scores` / `.similarities` are read before (or without) a selection."""
+        if not self._scanned or (want_sims and not self._have_sims):
+            th = self._hp.threshold if self._hp is not None else float("nan")
+            self._scan(th, float("nan"), want_sims=want_sims)
+
+    def lowest_scoring_user_match(self):
+        """(min(1, scores of user-confirmed clips), last such clip in database order) — ticket.py:301-309.
+        Uses the float64 labelled-subset path: no full scan is needed for a handful of clips."""
+        st = self.feature_store()
+        clips = [int(c) for c, v in self.user_matches.items() if v is True and st.has_clip(int(c))]
+        if not clips:
+            return 1, None
+        clips.sort(key=st.row_of)
+        sims = st.labelled_sims(self.target.target_features, st.rows_of(clips))
+        weights = self._weights if self._weights is not None else self._hp.weights
+        ssum, denom = np.zeros(len(clips)), 0.0
+        for si, s in enumerate(st.streams):
+            ssum = ssum + (weights[s] * (1 - sims[:, si])) ** 2
+            denom += weights[s] ** 2
+        sc = 1 - np.sqrt(ssum / denom)
+        return min(1, float(sc.min())), clips[-1]
+
+    # ------------------------------------------------------------------ selection (A5)
+    def select_clips_to_review(self, threshold=0.8, max_number_matches=20, near_miss=0.5):
+        """Matches and near misses for review (ticket.py:311-356): half from {score >= threshold},
+        the rest from {lower <= score < threshold} with the best near miss always kept; the reference
+        clip and previously confirmed clips are forced in.  Result: self.matches = {clip: score}."""
+        lower_limit = threshold - near_miss * (1 - threshold)
+        st = self.feature_store()
+        res = self._scan(threshold, lower_limit)
+        ids = st.clip_ids
+        m_rows, m_sc = st.matches()
+        n_rows, n_sc = st.near_misses()
+        t_rows, _ = st.ties()
+        self.tie_band = [int(ids[r - st.first_global_row]) for r in t_rows]
+        if self.tie_band:
+            logging.info("query %s: %d clip(s) within COMPUTE_EPS of a selection boundary: %s",
+                         self.query_id, len(self.tie_band), self.tie_band[:20])
+        mscores = int(min(max_number_matches / 2, res.n_match))
+        m_near_scores = int(min(max_number_matches - mscores, res.n_near))
+        # random.sample(population, k) draws depend only on (len(population), k): sampling the index
+        # range consumes the generator exactly like sampling the reference's dict items (:333).
+        picked = random.sample(range(res.n_match), mscores)
+        chosen = [(int(ids[m_rows[j] - st.first_global_row]), float(m_sc[j])) for j in picked]
+        near_best = {}
+        if m_near_scores > 0:
+            m_near_scores -= 1
+            jbest = int(np.argmax(n_sc))               # first maximum in database order (:338)
+            near_best = {int(ids[n_rows[jbest] - st.first_global_row]): float(n_sc[jbest])}
+            n_rows, n_sc = np.delete(n_rows, jbest), np.delete(n_sc, jbest)
+        picked = random.sample(range(len(n_rows)), m_near_scores)
+        chosen += [(int(ids[n_rows[j] - st.first_global_row]), float(n_sc[j])) for j in picked]
+        self.matches = dict(chosen)
+        self.matches.update(near_best)
+        forced = {}
+        if st.has_clip(self.ref_clip_id):
+            forced[self.ref_clip_id] = self._score_of(self.ref_clip_id)
+        if self.user_matches:
+            for clip, value in self.user_matches.items():
+                if value is True:
+                    forced[int(clip)] = self._score_of(int(clip))
+        self.matches.update(forced)
+
+    def _score_of(self, clip):
+        st = self.feature_store()
+        if not st.has_clip(clip):
+            raise KeyError(clip)
+        g = st.first_global_row + st.row_of(clip)
+        sh = st._shard_of(g)
+        out = np.empty(1, np.float32)
+        from ._ffi import check, lib, ptr
+        check(lib().vq_fetch_scores(sh.handle, g - sh.first, 1, ptr(out)), "vq_fetch_scores")
+        return float(out[0])
+
+    # ------------------------------------------------------------------ final report (A7)
+    def create_final_report(self, hyperparameters, query_result_id):
+        """CSV of every selected clip ranked by score, stable and descending (ticket.py:182-274)."""
+        query = self._request(["queries", "read"], {"id": self.query_id})
+        video = self._request(["videos", "read"], {"id": self.video_id})
+        query_result = self._request(["query-results", "read"], {"id": query_result_id})
+        search_set = self._request(["search-sets", "read"], {"id": query["search_set_to_query"]})
+        out_dir = '../final_reports/'
+        os.makedirs(out_dir, exist_ok=True)
+        path = os.path.join(out_dir, 'final_report_query_{}_{}.csv'.format(
+            query["name"], datetime.now().strftime('%m-%d-%Y_%Hh%Mm%Ss')))
+        hp = hyperparameters
+        header = [
+            ['Query:', query["name"], 'Query pk:', self.query_id],
+            ['Search Set queried:', search_set["name"], 'Search set pk:', search_set["id"]],
+            ['Reference Video:', video["name"], 'Video pk:', self.video_id],
+            ['Reference time:', query["reference_time"]],
+            ['number of reviews:', query_result["round"] - 1],
+            ['min score for a match:', query_result["match_criterion"]],
+            ["max matches to review:", query["max_matches_for_review"]],
+            ['streams:', str(hp.streams)],
+            ['stream weights:', str(query_result["weights"])],
+            ['Target bootstrapping:', query["use_dynamic_target_adjustment"]],
+            ['query notes:', query["notes"]],
+            ['Hyperparameters:'],
+            ['', 'default weights:', str(hp.default_weights)],
+            ['', 'default threshold:', str(hp.default_threshold)],
+            ['', 'near miss default:', str(hp.near_miss_default)],
+            ['', 'feature name:', str(hp.feature_name)],
+            ['', 'ballast:', str(hp.ballast)],
+            ['', 'mu:', str(hp.mu)],
+            ['', 'f_bootstrap:', str(hp.f_bootstrap)],
+            ['', 'f_memory:', str(hp.f_memory)],
+            ['', 'bootstrap type:', str(hp.bootstrap_type)],
+        ]
+        if hp.bootstrap_type == "bagging":
+            header.append(['', 'number of bags:', str(hp.nbags)])
+        header += [[''],
+                   ['List of all clips with scores greater than min(threshold, score of lowest scoring'
+                    ' user validated match)'],
+                   ['clip #', 'start time', 'match type', 'video pk', 'video clip id', 'score', 'duration', 'notes']]
+        rows = []
+        for video_clip_id, score in self.matches.items():
+            label = self.user_matches.get(str(video_clip_id))
+            if str(video_clip_id) in self.user_matches:
+                match_type = "user-identified match" if label is True else "user-identified non-match"
+            elif score >= query_result["match_criterion"]:
+                match_type = "inferred match"
+            else:
+                match_type = "inferred non-match"
+            clip = self._request(["video-clips", "read"], {"id": video_clip_id})
+            match = self._request(["matches", "list"], {"query_result": query_result_id, "video_clip": video_clip_id})
+            start = int(match["results"][0]["match_video_time_span"].split(",")[0])
+            rows.append([clip['clip'], str(timedelta(seconds=start)), match_type, clip['video'], video_clip_id,
+                         score, clip['duration'], clip['notes']])
+        rows.sort(key=lambda r: r[5], reverse=True)
+        with open(path, 'x', newline='') as f:
+            w = csv.writer(f)
+            w.writerows(header)
+            w.writerows(rows)
+        with open(path, 'r') as f:
+            self._post_file(["queries", "partial_update"], {"id": self.query_id, "final_report_file": f})
