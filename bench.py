@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""Benchmark of the match-scoring hot path (BASELINE.json configs[1], weak-scaled over N GPUs).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            this repo's CUDA path
+  python bench.py --impl reference [--gpus N] [--steps K] ...    the reference's CPU path (port)
+
+A step = one single-query pass of the hot path over every rank's resident shard of 1M synthetic
+clips (2 streams x 1024-d fp32 = 8192 B/clip, 8.19 GB per GPU > 126 MB L2, so no flush is needed):
+fused scan K1 (dots, fusion, score) + selection K2 (match / near-miss / tie lists in database
+order, exact top-100) and, for N > 1, one NCCL allgather of the per-rank payload + device merge.
+Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("COMPUTE_EPS", ".000003")          # reference Dockerfile:15
+os.environ.setdefault("RANDOM_SEED", "73459912436")
+
+STREAMS = ("rgb", "warped_optical_flow")
+DIM = 1024
+ROW_BYTES = len(STREAMS) * DIM * 4                       # algorithmic bytes per clip per scan
+WEIGHTS = (1.0, 1.5)                                     # broker.py:36-41
+THRESHOLD, NEAR_MISS, EPS, TOPK = 0.8, 0.35, 3e-6, 100
+DATA_SEED = 20261018
+REF_ROW = 18120                                          # VQSYN-1 row with alpha ~ 0.9: ~9 % of clips match
+METRIC = "clips scored/sec per query"
+KERNELS_PER_STEP = 4                                     # scan_rows, select_count, select_finish, select_compact
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--clips-per-gpu", type=int, default=1_000_000)
+    ap.add_argument("--no-cold", action="store_true", help="skip the cold end-to-end leg (8 GB upload per step)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    """Polls NVML for SM clock and throttle reasons while the timed region runs."""
+    REASONS = {0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+               0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.mask, self.stop_flag = index, [], 0, False
+        self.max_mhz, self.ok = None, False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:                            # pragma: no cover
+            self.err = repr(e)
+
+    def run(self):
+        while self.ok and not self.stop_flag:
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                self.mask |= self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            except Exception:
+                pass
+            time.sleep(0.002)
+
+    def result(self):
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": float(self.max_mhz),
+                "reasons": [n for b, n in self.REASONS.items() if self.mask & b], "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------ CPU arms
+def cpu_port_throughput(n_sample, steps=1, warmup=0):
+    """The reference as written, restated (oracle/loop_port.py): dicts of Python lists, one
+    np.dot(list, list) per (clip, stream, split), single thread (the reference is GIL-bound).
+    Payload construction is outside the timed region, like the HTTP fetch it stands for."""
+    from oracle import loop_port, scoring, synth
+    X = synth.rows(DATA_SEED, np.arange(n_sample)).astype(np.float64)[:, :, None, :]
+    ref = synth.rows(DATA_SEED, [REF_ROW]).astype(np.float64)[0][:, None, :]
+    T = scoring.scale_target(ref)
+    cand = loop_port.make_candidates(X, np.arange(n_sample), STREAMS, [1])
+    tf = loop_port.make_target(T, STREAMS, [1])
+    w = dict(zip(STREAMS, WEIGHTS))
+    for _ in range(warmup):
+        loop_port.scoring_step(tf, cand, w, THRESHOLD, NEAR_MISS)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        loop_port.scoring_step(tf, cand, w, THRESHOLD, NEAR_MISS)
+    dt = time.perf_counter() - t0
+    return n_sample * steps / dt, dt
+
+
+def cpu_vectorised_throughput(n_sample):
+    """'Fair CPU' row: float64 numpy restatement (BLAS, all host cores) on fp32-stored rows."""
+    from oracle import scoring, synth
+    X = synth.database(DATA_SEED, n_sample)[:, :, None, :]
+    T = scoring.scale_target(synth.rows(DATA_SEED, [REF_ROW]).astype(np.float64)[0][:, None, :])
+    t0 = time.perf_counter()
+    sims, _ = scoring.similarities(X, T)
+    sc = scoring.scores(sims, WEIGHTS)
+    scoring.classify(sc, THRESHOLD, NEAR_MISS)
+    scoring.topk_stable(sc, TOPK)
+    dt = time.perf_counter() - t0
+    return n_sample / dt, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    total = max(args.steps + args.warmup, 1)
+    n_sample = int(min(20000, max(200, 120.0 * 3500 / total)))
+    v, dt = cpu_port_throughput(n_sample, steps=args.steps, warmup=args.warmup)
+    sample = ("%d-clip slice of the workload per step (loop port of ticket.py:120-180,325-327; features "
+              "as Python lists already in memory, HTTP/payload construction excluded)" % n_sample)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "clips/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic (VQSYN-1)",
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": v, "unit": "clips/s", "cores": 1, "cores_available": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference is single-threaded Python (GIL-bound loops); it cannot use more host threads",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": "configs[1]: %d-clip synthetic DB per GPU, single-query scan + threshold/near-miss lists "
+                        "+ top-%d" % (args.clips_per_gpu, TOPK),
+            "clips_per_gpu": args.clips_per_gpu, "global_clips": args.clips_per_gpu * world, "streams": 2,
+            "dim": DIM, "bytes_per_clip": ROW_BYTES, "topk": TOPK, "threshold": THRESHOLD, "near_miss": NEAR_MISS,
+            "weights": list(WEIGHTS), "parallelism": "clip-range shards x%d" % world,
+            "l2": "input %.2f GB per GPU > 126 MB L2, no flush" % (args.clips_per_gpu * ROW_BYTES / 1e9)}
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    g.build()
+    import video_query_algorithms_b200 as vq
+    from video_query_algorithms_b200 import _ffi
+    from video_query_algorithms_b200.store import make_params
+    lib = _ffi.lib()
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.clips_per_gpu
+    st = vq.FeatureStore(n, STREAMS, [1], DIM, devices=[local_rank], first_global_row=rank * n)
+    st.fill_synthetic(DATA_SEED)
+    handle = st.shards[0].handle
+
+    # target = reference clip scaled by its squared norm (target_clip.py:311-313); the clip lives on rank 0
+    T = torch.zeros(2 * DIM, dtype=torch.float64, device=dev)
+    if rank == 0:
+        f = st.download(REF_ROW, 1)[0].astype(np.float64)            # [2, 1, 1024]
+        t = np.stack([vq.TargetClip._scale_feature(f[s, 0]) for s in range(2)])
+        T.copy_(torch.from_numpy(t.reshape(-1)))
+    if world > 1:
+        dist.broadcast(T, src=0)
+    T_host = T.cpu().numpy().reshape(2, 1, DIM)
+    target_dev = T.to(torch.float32).contiguous()
+    tdict = {s: {1: T_host[i, 0]} for i, s in enumerate(STREAMS)}
+    lower = THRESHOLD - NEAR_MISS * (1 - THRESHOLD)
+    params = make_params(WEIGHTS, THRESHOLD, lower, EPS, topk=TOPK)
+
+    stream = torch.cuda.Stream(device=dev)       # explicit stream: handle 0 would mean "the store's own stream"
+    torch.cuda.set_stream(stream)
+    sptr = C.c_void_p(stream.cuda_stream)
+    assert stream.cuda_stream != 0
+    pay_ptr, pay_n = C.c_void_p(), C.c_int32()
+    npay = 4 + 2 * TOPK
+    gathered = torch.zeros(world * npay, dtype=torch.int64, device=dev)
+    merged = torch.zeros(npay, dtype=torch.int64, device=dev)
+    payload_t = None
+
+    class _Arr:                                                       # zero-copy view of the library's payload
+        def __init__(self, p, nbytes):
+            self.__cuda_array_interface__ = {"shape": (nbytes // 8,), "typestr": "<i8", "data": (p, False), "version": 3}
+
+    def step():
+        nonlocal payload_t
+        _ffi.check(lib.vq_scan_enqueue(handle, C.c_void_p(target_dev.data_ptr()), C.byref(params), sptr), "vq_scan_enqueue")
+        if world > 1:
+            if payload_t is None:
+                _ffi.check(lib.vq_scan_payload(handle, C.byref(pay_ptr), C.byref(pay_n)), "vq_scan_payload")
+                payload_t = torch.as_tensor(_Arr(pay_ptr.value, pay_n.value * 8), device=dev)
+            dist.all_gather_into_tensor(gathered, payload_t)
+            _ffi.check(lib.vq_merge_payloads_enqueue(local_rank, C.c_void_p(gathered.data_ptr()), world, TOPK,
+                                                     C.c_void_p(merged.data_ptr()), sptr), "vq_merge_payloads_enqueue")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    tmp = np.empty(1024, np.float32)
+    cnt = C.c_int32()
+    lib.vq_scan_kernel_times(handle, 1024, _ffi.ptr(tmp), C.byref(cnt))        # drop warm-up timings
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    sampler.stop_flag = True
+    sampler.join()
+    ms_total = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
+    ms_total = float(ms_total.item())
+    ktimes = np.empty(1024, np.float32)
+    _ffi.check(lib.vq_scan_kernel_times(handle, 1024, _ffi.ptr(ktimes), C.byref(cnt)), "vq_scan_kernel_times")
+    k1_ms = float(np.mean(ktimes[:cnt.value])) if cnt.value else float("nan")
+    value = world * n * args.steps / (ms_total * 1e-3)
+
+    # counts of the last step (sanity: the work is real)
+    sc_counts = _ffi.ScanCounts()
+    _ffi.check(lib.vq_scan_wait(handle, sptr, C.byref(sc_counts)), "vq_scan_wait")
+
+    # ---- end to end through the public API, host buffers: target H2D, counts + lists + top-k D2H
+    e2e_steps = max(3, min(args.steps, 100))
+    for _ in range(2):
+        st.scan(tdict, WEIGHTS, THRESHOLD, lower, EPS, topk=TOPK)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res = st.scan(tdict, WEIGHTS, THRESHOLD, lower, EPS, topk=TOPK)
+        k_rows, k_sc = st.topk()
+        m_rows, m_sc = st.matches()
+        nm_rows, nm_sc = st.near_misses()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * n * e2e_steps / float(e2e_s.item())
+    h2d = ROW_BYTES + C.sizeof(_ffi.ScanParams)
+    d2h = 32 + TOPK * 12 + (res.n_match + res.n_near) * 8
+
+    # ---- cold end to end: the shard itself is uploaded from pinned host memory every step
+    cold = None
+    if world == 1 and not args.no_cold:
+        try:
+            pinned = torch.empty(n * 2 * DIM, dtype=torch.float32, pin_memory=True)
+            host = pinned.numpy()
+            _ffi.check(lib.vq_store_download(handle, 0, n, _ffi.ptr(host)), "vq_store_download")
+            st.upload(0, host)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            cold_steps = 3
+            for _ in range(cold_steps):
+                st.upload(0, host)
+                st.scan(tdict, WEIGHTS, THRESHOLD, lower, EPS, topk=TOPK)
+                st.topk(); st.matches(); st.near_misses()
+            dt = time.perf_counter() - t0
+            cold = {"value": n * cold_steps / dt, "unit": "clips/s", "h2d_bytes_per_step": n * ROW_BYTES + h2d,
+                    "d2h_bytes_per_step": d2h, "steps": cold_steps,
+                    "what": "feature DB re-uploaded from pinned host memory every step (the reference re-fetches "
+                            "it over HTTP every job); PCIe-bound"}
+            del pinned, host
+        except Exception as e:                            # pragma: no cover
+            cold = {"value": None, "error": repr(e)[:200]}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = n * ROW_BYTES / (k1_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
+                traffic = json.load(f).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        line = {
+            "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (VQSYN-1 counter-based generator, on device)",
+            "config": workload_config(args, world),
+            "hbm_gbs_whole_step": value * ROW_BYTES / 1e9,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "scan_rows_reg<2,8> (K1)", "kernel_ms": k1_ms,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650",
+                         "frac_of_nominal_8TBs": achieved / 8000.0,
+                         "algorithmic_bytes_per_launch": n * ROW_BYTES},
+            "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "steps": e2e_steps, "what": "FeatureStore.scan + topk + matches + near_misses through the C ABI with host "
+                    "buffers; the shard stays resident in HBM between queries (the store outlives broker ticks)"},
+            "e2e_cold": cold,
+            "gpu_launches": KERNELS_PER_STEP * args.steps + (args.steps if world > 1 else 0),
+            "clocks": sampler.result(),
+            "last_step_counts": {"n_match": int(sc_counts.n_match), "n_near": int(sc_counts.n_near),
+                                 "n_tie": int(sc_counts.n_tie), "n_topk": int(sc_counts.n_topk)},
+        }
+        if world == 1 and not args.no_cpu:
+            cores = len(os.sched_getaffinity(0))
+            v, dt = cpu_port_throughput(40000)
+            vv, vdt = cpu_vectorised_throughput(200000)
+            line["cpu_baseline"] = {
+                "value": v, "unit": "clips/s", "cores": 1, "cores_available": cores, "kind": "port",
+                "sample": "40000-clip slice of the workload, one pass (%.1f s): loop port of the reference's "
+                          "compute_similarities/compute_scores/candidate scans, Python lists in memory" % dt,
+                "vectorised_numpy_f64": {"value": vv, "unit": "clips/s", "cores": cores,
+                                         "sample": "200000-clip slice, one pass (%.1f s), BLAS on all cores" % vdt}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    st.close()
+
+
+if __name__ == "__main__":
+    main()

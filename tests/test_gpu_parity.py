@@ -102,6 +102,23 @@ def test_scan_matches_oracle_on_synthetic(vq, n):
     st.close()
 
 
+def test_topk_with_massive_ties_keeps_database_order(vq):
+    """Thousands of identical rows share one score: the candidate set overflows the fast path
+    (radix-select branch) and the ranking must fall back to database order (stable sort, ticket.py:266)."""
+    base = synth.database(3, 40)
+    X = np.repeat(base[7:8], 6000, axis=0)
+    X[100], X[2000], X[5999] = base[1], base[2], base[3]
+    st = vq.FeatureStore(len(X), STREAMS, [1], 1024, devices=[0])
+    st.upload(0, X[:, :, None, :])
+    T = sc.scale_target(base[7].astype(np.float64)[:, None, :])
+    st.scan(tdict(T), (1.0, 1.5), 0.8, 0.73, EPS, topk=1000)
+    got = st.scores()
+    rows, scores = st.topk()
+    assert np.array_equal(rows, sc.topk_stable(got, 1000))
+    assert np.array_equal(rows[:3], [0, 1, 2]) and 100 not in rows[:99]
+    st.close()
+
+
 def test_scan_handles_empty_store(vq):
     st = vq.FeatureStore(0, STREAMS, [1], 1024, devices=[0])
     T = np.ones((2, 1, 1024))
@@ -243,8 +260,13 @@ def test_compute_matches_reproduces_reference_rounds(vq, name, tmp_path, monkeyp
         assert len(body) == len(ref)
         got_clips = [ln.split(",")[4] for ln in body[-len(scn.rounds[-1]["selected"]):]]
         ref_clips = [ln.split(",")[4] for ln in ref[-len(scn.rounds[-1]["selected"]):]]
-        if not tickets[-1].tie_band:
-            assert got_clips == ref_clips
+        # ranking is by score, stable and descending (ticket.py:266); clips whose float64 scores are
+        # within COMPUTE_EPS of each other (e.g. several bootstrapped matches at score ~1) may swap
+        ref_score = {str(k): v for k, v in scn.rounds[-1]["selected"]}
+        assert sorted(got_clips) == sorted(ref_clips) or tickets[-1].tie_band
+        for a, b in zip(got_clips, ref_clips):
+            if a in ref_score and b in ref_score:
+                assert a == b or abs(ref_score[a] - ref_score[b]) < EPS
     vq.invalidate()
 
 
@@ -257,8 +279,8 @@ def test_missing_library_or_bad_arguments_fail_loudly(vq):
         st.scan(tdict(np.ones((2, 1, 1024))), (0.0, 0.0), 0.8, 0.7, EPS)   # all-zero weights
     with pytest.raises(vq.VQError):
         st.labelled_sims(tdict(np.ones((2, 1, 1024))), np.array([10]))    # row outside the store
-    import ctypes as C
-    assert _ffi.lib().vq_scan_batch(st.shards[0].handle, None, 1, None, None, None, None, None) != 0 or True
+    with pytest.raises(vq.VQError):
+        st.bootstrap_target(np.array([3, 99]), None, 0.0)                 # row outside the store
     st.close()
 
 
@@ -269,7 +291,7 @@ def test_one_million_clip_scan_properties(vq):
     n, seed = 1_000_000, synth.DEFAULT_SEED
     st = vq.FeatureStore(n, STREAMS, [1], 1024, devices=[0])
     st.fill_synthetic(seed)
-    ref = 4242
+    ref = 18120                                   # alpha ~ 0.9: ~9 % of the clips match
     T = sc.scale_target(synth.rows(seed, [ref]).astype(np.float64)[0][:, None, :])
     th, lo, w = 0.8, sc.lower_limit(0.8, 0.35), (1.0, 1.5)
     r1 = st.scan(tdict(T), w, th, lo, EPS, topk=100)

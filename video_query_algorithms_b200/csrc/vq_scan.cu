@@ -371,8 +371,13 @@ select_finish(const unsigned int *__restrict__ chunk_counts, unsigned int *chunk
     long long C = (long long)*cand_count;
     if (C > cand_cap) C = cand_cap;
     const int k = (int)min((long long)topk, C);
-    if (k > 0) {
-        // radix select, 8 bits at a time from the top: find the k-th largest key
+    int n_sel = 0;                                  // keys staged in sel[] for the final sort
+    if (C <= VQ_MAX_TOPK) {
+        // common case (candidates = k + one histogram bin): sort them all, no selection passes
+        for (int i = threadIdx.x; i < (int)C; i += kFinThreads) sel[i] = cand_keys[i];
+        n_sel = (int)C;
+    } else if (k > 0) {
+        // radix select, 8 bits at a time from the top: exact key of the k-th best
         unsigned long long prefix = 0, mask = 0;
         unsigned int remain = (unsigned int)k;
         for (int shift = 56; shift >= 0; shift -= 8) {
@@ -383,23 +388,37 @@ select_finish(const unsigned int *__restrict__ chunk_counts, unsigned int *chunk
                 if ((key & mask) == prefix) atomicAdd(&digit_hist[(unsigned int)(key >> shift) & 255u], 1u);
             }
             __syncthreads();
-            if (threadIdx.x == 0) {
-                unsigned int run = 0;
-                int d = 255;
-                for (; d > 0; --d) {
-                    if (run + digit_hist[d] >= remain) break;
-                    run += digit_hist[d];
+            if (threadIdx.x < 32) {
+                // lane l owns digits 255-8l .. 248-8l (descending); find the digit where the running
+                // count from the top reaches `remain`
+                const int lane = threadIdx.x;
+                unsigned int mine = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) mine += digit_hist[255 - 8 * lane - j];
+                unsigned int inc = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned int v = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += v;
                 }
-                prefix_s = prefix | ((unsigned long long)d << shift);
-                remain_s = remain - run;
+                const unsigned int excl = inc - mine;
+                if (excl < remain && inc >= remain) {
+                    unsigned int run = excl;
+                    int d = 255 - 8 * lane;
+                    for (int j = 0; j < 8; ++j, --d) {
+                        if (run + digit_hist[d] >= remain) break;
+                        run += digit_hist[d];
+                    }
+                    prefix_s = prefix | ((unsigned long long)d << shift);
+                    remain_s = remain - run;
+                }
             }
             __syncthreads();
             prefix = prefix_s;
             remain = remain_s;
             mask |= 0xFFull << shift;
-            __syncthreads();
         }
-        const unsigned long long kth = prefix;      // exact key of the k-th best
+        const unsigned long long kth = prefix;
         if (threadIdx.x == 0) sel_n = 0;
         __syncthreads();
         for (long long i = threadIdx.x; i < C; i += kFinThreads) {
@@ -410,15 +429,18 @@ select_finish(const unsigned int *__restrict__ chunk_counts, unsigned int *chunk
             }
         }
         __syncthreads();
+        n_sel = k;
     }
-    for (int i = threadIdx.x; i < VQ_MAX_TOPK; i += kFinThreads)
-        if (i >= k) sel[i] = 0ull;
+    int P = 2;
+    while (P < n_sel) P <<= 1;                       // sort size: next power of two, <= 1024
+    for (int i = threadIdx.x; i < P; i += kFinThreads)
+        if (i >= n_sel) sel[i] = 0ull;
     __syncthreads();
-    // bitonic sort, descending, 1024 keys, one key per thread pair
-    for (int size = 2; size <= VQ_MAX_TOPK; size <<= 1) {
+    // bitonic sort, descending, P keys
+    for (int size = 2; size <= P; size <<= 1) {
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
             const int t = threadIdx.x;
-            if (t < VQ_MAX_TOPK / 2) {
+            if (t < P / 2) {
                 const int lo = 2 * t - (t & (stride - 1));
                 const int hi = lo + stride;
                 const bool desc = ((lo & size) == 0);

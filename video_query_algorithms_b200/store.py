@@ -119,9 +119,15 @@ class FeatureStore:
                 return sh
         raise VQError("row %d is not in the store" % global_row)
 
+    def _check_range(self, first_row, n_rows, who):
+        if first_row < 0 or n_rows < 0 or first_row + n_rows > self.n_rows:
+            raise VQError("%s: rows [%d, %d) outside the store of %d rows" % (who, first_row, first_row + n_rows,
+                                                                              self.n_rows))
+
     def upload(self, first_row, rows):
         """rows: float32 [n, S, P, dim] (or [n, S*P*dim]) for local rows first_row.. of the store."""
         rows = np.ascontiguousarray(rows, dtype=np.float32).reshape(-1, int(np.prod(self.row_shape)))
+        self._check_range(first_row, rows.shape[0], "upload")
         g0 = self.first_global_row + first_row
         for sh in self.shards:
             lo, hi = max(g0, sh.first), min(g0 + rows.shape[0], sh.first + sh.n_rows)
@@ -130,6 +136,7 @@ class FeatureStore:
                 check(lib().vq_store_upload(sh.handle, lo - sh.first, hi - lo, ptr(part)), "vq_store_upload")
 
     def download(self, first_row, n_rows):
+        self._check_range(first_row, n_rows, "download")
         out = np.empty((n_rows,) + self.row_shape, np.float32)
         g0 = self.first_global_row + first_row
         for sh in self.shards:
@@ -339,6 +346,9 @@ class FeatureStore:
         rows = np.asarray(global_rows, dtype=np.int64)
         out = np.empty((len(rows), len(self.streams)), np.float64)
         Tc = np.ascontiguousarray(T)
+        lo_g, hi_g = self.first_global_row, self.first_global_row + self.n_rows
+        if len(rows) and (rows.min() < lo_g or rows.max() >= hi_g):
+            raise VQError("labelled_sims: rows outside the store [%d, %d)" % (lo_g, hi_g))
         for sh in self.shards:
             sel = np.flatnonzero((rows >= sh.first) & (rows < sh.first + sh.n_rows))
             if len(sel):
@@ -355,6 +365,9 @@ class FeatureStore:
         valid = np.ascontiguousarray(valid_rows, dtype=np.int64)
         invalid = np.ascontiguousarray(invalid_rows if invalid_rows is not None else [], dtype=np.int64)
         allr = np.concatenate([valid, invalid])
+        lo_g, hi_g = self.first_global_row, self.first_global_row + self.n_rows
+        if len(valid) == 0 or allr.min() < lo_g or allr.max() >= hi_g:
+            raise VQError("bootstrap_target: need >= 1 valid row and all rows inside the store [%d, %d)" % (lo_g, hi_g))
         sh = self._shard_of(int(allr[0]))
         if not all(sh.first <= r < sh.first + sh.n_rows for r in allr):
             return self._bootstrap_gathered(valid, invalid, mu)
