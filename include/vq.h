@@ -148,6 +148,10 @@ int vq_scan_batch(vq_store *s, const float *targets /* [Q][S][P][dim] */, int32_
                   int64_t *topk_rows_out /* [Q][topk] */, float *topk_scores_out /* [Q][topk] */,
                   float *kernel_ms_out);
 
+/* Test hook: the full [Q][n_rows] fp32 score matrix of the batched path (small shards only). */
+int vq_scan_batch_scores(vq_store *s, const float *targets, int32_t n_queries, const vq_scan_params *p,
+                         float *scores_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -172,6 +172,43 @@ def test_two_shards_merge_like_one(vq):
     two.close()
 
 
+# ---------------------------------------------------------------------------- batched queries (tcgen05)
+@pytest.mark.parametrize("n,nq", [(5003, 70), (300, 3), (20000, 300)])
+def test_batched_tensor_core_scan_matches_oracle(vq, n, nq):
+    """K3: Q targets in one pass (3xTF32 on tcgen05).  Scores within 1e-5 of float64; per-query counts and
+    top-k equal to the oracle's up to rows within COMPUTE_EPS of a boundary / of each other."""
+    seed = 77
+    X = synth.database(seed, n)
+    st = vq.FeatureStore(n, STREAMS, [1], 1024, devices=[0])
+    st.upload(0, X[:, :, None, :])
+    X64 = X.astype(np.float64)[:, :, None, :]
+    rng = np.random.default_rng(3)
+    refs = rng.choice(n, nq, replace=nq > n)
+    alphas = synth.alpha(np.arange(n), seed)
+    refs[0] = int(np.argmin(np.abs(alphas - 0.9)))
+    T = np.stack([sc.scale_target(X64[r]) for r in refs])            # [Q, 2, 1, 1024]
+    w, th, near = (1.0, 1.5), 0.8, 0.35
+    lo = sc.lower_limit(th, near)
+    k = min(50, n)
+    got = st.scan_batch(T.astype(np.float32), w, th, lo, debug_scores=True)
+    counts, rows, scores, ms = st.scan_batch(T.astype(np.float32), w, th, lo, topk=k)
+    assert got.shape == (nq, n) and counts.shape == (nq, 2) and rows.shape == (nq, k)
+    T32 = T.astype(np.float32).astype(np.float64)
+    for q in range(nq):
+        sims64, _ = sc.similarities(X64, T32[q])
+        s64 = sc.scores(sims64, w)
+        assert_scores_close(got[q], s64)
+        m64, nm64 = sc.classify(s64, th, near)
+        g = got[q].astype(np.float64)
+        assert counts[q, 0] == np.count_nonzero(g >= th) and counts[q, 1] == np.count_nonzero((g >= lo) & (g < th))
+        assert_sets_match(np.flatnonzero(g >= th), m64, s64, (th,))
+        assert np.array_equal(rows[q], sc.topk_stable(got[q], k))
+        assert np.array_equal(scores[q], got[q][rows[q]])
+        for a, b in zip(rows[q], sc.topk_stable(s64, k)):
+            assert a == b or abs(s64[a] - s64[b]) < EPS
+    st.close()
+
+
 # ---------------------------------------------------------------------------- labelled subset (fp64)
 def test_loss_grid_and_replicates_match_oracle(vq):
     rng = np.random.default_rng(1)

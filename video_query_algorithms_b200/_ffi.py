@@ -66,6 +66,7 @@ PROTOTYPES = {
     "vq_loss_grid": (C.c_int, [C.c_int, _vp, _vp, _i64, _vp, _i32, _vp, _i32, C.c_double, _vp, _vp, _i32, _vp]),
     "vq_bootstrap_target": (C.c_int, [_vp, _vp, _i32, _vp, _i32, C.c_double, _vp]),
     "vq_scan_batch": (C.c_int, [_vp, _vp, _i32, _P(ScanParams), _vp, _vp, _vp, _vp]),
+    "vq_scan_batch_scores": (C.c_int, [_vp, _vp, _i32, _P(ScanParams), _vp]),
 }
 
 _lib = None

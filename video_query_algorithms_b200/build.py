@@ -31,6 +31,7 @@ def build(force=False, verbose=False):
            *[os.path.join(CSRC, f) for f in SOURCES]]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
+    cmd[1:1] = os.environ.get("VQ_NVCC_EXTRA", "").split()
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)

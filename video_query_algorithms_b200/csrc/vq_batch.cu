@@ -1,11 +1,663 @@
-// Batched queries (placeholder until the tcgen05 kernel lands): fails loudly, never falls back.
+// K3 — batched queries on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a.
+//
+// Q targets are scored against every clip of the shard in ONE pass over HBM per 128 queries: per
+// stream the similarities are a dense contraction SIM_s[clip, query] = sum_d X[clip, s, d] * T[query, s, d]
+// (reference ticket.py:146-160 for Q tickets at once), then the per-(clip, query) score of
+// ticket.py:173-180 and the candidate tests of ticket.py:325-327 are applied in the epilogue.
+// No Q x N score matrix is ever written: per query the kernel keeps the match / near-miss counts
+// and a candidate list for the exact top-k (ranking rule of ticket.py:266).
+//
+// Precision (measured on B200, see profiles/): two effects rule out a plain TF32 GEMM for the 1e-5 bar.
+//  (1) TF32 operands carry 10 mantissa bits -> each product is computed as three MMAs ("3xTF32"):
+//          x*t ~= hi(x)*hi(t) + lo(x)*hi(t) + hi(x)*lo(t)
+//      with lo(x) = x - trunc_tf32(x) made on the fly by converter warps (shared -> shared) and hi(t), lo(t)
+//      precomputed once per call (round-to-nearest split).
+//  (2) the tensor core adds each MMA into its fp32 accumulator with truncation: 384 accumulations of
+//      non-negative terms gave a -1.6e-5 relative bias.  So accumulation is two-level: hi*hi products go
+//      to a partial accumulator that is drained every 4 K-blocks (16 MMAs) and summed in registers with
+//      round-to-nearest fp32 adds; the small lo terms use their own accumulator (their truncation is
+//      relative to a 2^-11 times smaller magnitude).
+//
+// CTA layout (512 threads, 1 CTA per SM, persistent over 128-clip tiles), streams processed one after
+// the other:
+//     warp 0       TMA producer: per K block of 32 floats, A tile [128 clips] + B_hi, B_lo tiles
+//                  [128 queries], 128-byte swizzle, 3-stage ring of 64 KB
+//     warp 1       MMA issuer: one elected thread, tcgen05.mma.kind::tf32 M128 N128 K8
+//     warp 2       TMEM allocator (512 columns: P_hi[0], P_hi[1], P_lo, parked stream term)
+//     warps 4-11   epilogue: drain partials (tcgen05.ld), running sums in registers, score, tests,
+//                  warp-ballot counts, top-k candidates
+//     warps 12-15  converter: lo(x) tiles for the A operand
+#include <cuda.h>
+#include <stdlib.h>
+
+#include <vector>
+
 #include "vq_internal.cuh"
+#include "vq_topk.cuh"
+
+namespace {
+
+#ifdef VQ_BATCH_PROFILE          // role cycle counters (development builds only)
+#define VQ_CLOCK() clock64()
+#else
+#define VQ_CLOCK() 0ll
+#endif
+
+#ifndef VQ_GROUP_KB
+#define VQ_GROUP_KB 4
+#endif
+
+constexpr int BM = 128;                  // clips per tile (UMMA M)
+constexpr int QT = 128;                  // queries per pass (UMMA N)
+constexpr int BK = 32;                   // floats per K block = one 128-byte swizzle row
+constexpr int UK = 8;                    // UMMA K for tf32
+constexpr int STAGES = 3;
+constexpr int GROUP_KB = VQ_GROUP_KB;    // K blocks per partial accumulator (4 hi*hi MMAs each)
+constexpr uint32_t A_BYTES = BM * BK * 4;        // 16 KB
+constexpr uint32_t B_BYTES = QT * BK * 4;        // 16 KB
+constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // A, A_lo, B_hi, B_lo = 64 KB
+constexpr uint32_t TX_BYTES = A_BYTES + 2 * B_BYTES;
+constexpr int BATCH_THREADS = 512;
+constexpr int N_BARS = 3 * STAGES + 6;
+constexpr size_t BATCH_SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * QT * 4 /*cut, gate*/ +
+                              8 * 64 * 2 * 4 /*per-warp counts*/;
+constexpr uint32_t COL_PHI0 = 0, COL_PHI1 = 128, COL_PLO = 256, COL_PARK = 384;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t a, int c) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(c));
+}
+__device__ __forceinline__ void mbar_expect(uint32_t a, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t a) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+    // K-major, 128-byte swizzle: 8-row atoms of 128 B, atoms 1024 B apart (SBO), LBO unused (1), version 1
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc),
+        "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+
+struct BatchArgs {
+    float w[VQ_MAX_STREAMS];
+    float inv_den, inv_splits;
+    float th_f, lo_f;              // smallest floats >= the double thresholds: (double)s >= th  <=>  s >= th_f
+    int n_queries;
+    int kb_per_stream;             // stream_len / 32
+    int n_streams;
+    long long row0, n_rows_total;  // chunk start (local rows) and shard size
+    int n_tiles;                   // tiles in this chunk
+    long long cand_cap;
+};
+
+// hi/lo split of the targets, round to nearest (cvt.rna): hi has a 10-bit mantissa, lo = t - hi exactly
+__global__ void split_targets(const float *__restrict__ t, float *hi, float *lo, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = t[i];
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+    const float hf = __uint_as_float(h);
+    hi[i] = hf;
+    lo[i] = x - hf;
+}
+
+__global__ void __launch_bounds__(BATCH_THREADS, 1)
+batch_scan(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
+           const __grid_constant__ CUtensorMap map_blo, const BatchArgs a, const float *__restrict__ inv_counts,
+           const float *__restrict__ cut_g, unsigned long long *counts_g /*[QT][2]*/, unsigned int *cand_cnt /*[QT]*/,
+           unsigned long long *cand_keys /*[QT][cap]*/, float *scores_dbg /*[Q][n_rows] or null*/,
+           long long *prof /*[grid][8] cycle counters or null*/) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES * STAGE_BYTES);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + N_BARS);
+    float *cut_s = reinterpret_cast<float *>(smem + (size_t)STAGES * STAGE_BYTES + 256);
+    float *gate_s = cut_s + QT;
+    unsigned int *cnt_s = reinterpret_cast<unsigned int *>(gate_s + QT);      // [8 warps][64 queries][2]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar_full = smem_u32(&bars[0]), bar_conv = smem_u32(&bars[STAGES]),
+                   bar_empty = smem_u32(&bars[2 * STAGES]), bar_part_full = smem_u32(&bars[3 * STAGES]),
+                   bar_part_empty = smem_u32(&bars[3 * STAGES + 2]), bar_lo_full = smem_u32(&bars[3 * STAGES + 4]),
+                   bar_lo_empty = smem_u32(&bars[3 * STAGES + 5]);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_conv + 8 * s, 4);       // one arrive per converter warp
+            mbar_init(bar_empty + 8 * s, 1);      // tcgen05.commit
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_part_full + 8 * b, 1);  // tcgen05.commit
+            mbar_init(bar_part_empty + 8 * b, 8); // one arrive per epilogue warp
+        }
+        mbar_init(bar_lo_full, 1);
+        mbar_init(bar_lo_empty, 8);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < QT; i += blockDim.x) {
+        const float c = cut_g[i];
+        cut_s[i] = c;
+        gate_s[i] = fminf(c, a.lo_f);
+    }
+    for (int i = threadIdx.x; i < 8 * 64 * 2; i += blockDim.x) cnt_s[i] = 0;
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const int kbps = a.kb_per_stream;
+    const int kb_total = kbps * a.n_streams;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int it = 0;
+            long long p_wait = 0;
+            const long long p_t0 = VQ_CLOCK();
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+                const int row = (int)(a.row0 + (long long)tile * BM);
+                for (int kb = 0; kb < kb_total; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    const long long t0 = VQ_CLOCK();
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                    p_wait += VQ_CLOCK() - t0;
+                    const uint32_t base = smem_u32(smem + (size_t)s * STAGE_BYTES);
+                    mbar_expect(bar_full + 8 * s, TX_BYTES);
+                    tma_load_2d(base, &map_a, kb * BK, row, bar_full + 8 * s);
+                    tma_load_2d(base + 2 * A_BYTES, &map_bhi, kb * BK, 0, bar_full + 8 * s);
+                    tma_load_2d(base + 2 * A_BYTES + B_BYTES, &map_blo, kb * BK, 0, bar_full + 8 * s);
+                }
+            }
+            if (prof) { prof[blockIdx.x * 8 + 0] = p_wait; prof[blockIdx.x * 8 + 1] = VQ_CLOCK() - p_t0; }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            // instruction descriptor: D = f32, A = B = tf32, both K-major, N = QT, M = 128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(QT >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            int it = 0, gcount = 0, lcount = 0;
+            long long w_acc = 0, w_data = 0;
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+                for (int st = 0; st < a.n_streams; ++st) {
+                    uint32_t d_hi = 0;
+                    for (int kb = 0; kb < kbps; ++kb, ++it) {
+                        const bool group_first = (kb % GROUP_KB) == 0;
+                        const bool group_last = (kb % GROUP_KB) == GROUP_KB - 1 || kb == kbps - 1;
+                        long long t0 = VQ_CLOCK();
+                        if (group_first) {
+                            const int b = gcount & 1;
+                            mbar_wait(bar_part_empty + 8 * b, ((gcount >> 1) & 1) ^ 1);   // partial drained
+                            d_hi = tmem_base + (b ? COL_PHI1 : COL_PHI0);
+                        }
+                        if (kb == 0) mbar_wait(bar_lo_empty, (lcount & 1) ^ 1);
+                        w_acc += VQ_CLOCK() - t0;
+                        const int s = it % STAGES;
+                        const uint32_t ph = (it / STAGES) & 1;
+                        t0 = VQ_CLOCK();
+                        mbar_wait(bar_full + 8 * s, ph);
+                        mbar_wait(bar_conv + 8 * s, ph);
+                        w_data += VQ_CLOCK() - t0;
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t base = smem_u32(smem + (size_t)s * STAGE_BYTES);
+                        const uint32_t d_lo = tmem_base + COL_PLO;
+                        // small terms first, into their own accumulator
+#pragma unroll
+                        for (int k = 0; k < BK / UK; ++k) {
+                            const uint32_t off = (uint32_t)(k * UK * 4);
+                            umma_tf32(d_lo, umma_desc(base + A_BYTES + off), umma_desc(base + 2 * A_BYTES + off), idesc,
+                                      (kb == 0 && k == 0) ? 0u : 1u);
+                            umma_tf32(d_lo, umma_desc(base + off), umma_desc(base + 2 * A_BYTES + B_BYTES + off), idesc, 1u);
+                        }
+#pragma unroll
+                        for (int k = 0; k < BK / UK; ++k) {
+                            const uint32_t off = (uint32_t)(k * UK * 4);
+                            umma_tf32(d_hi, umma_desc(base + off), umma_desc(base + 2 * A_BYTES + off), idesc,
+                                      (group_first && k == 0) ? 0u : 1u);
+                        }
+                        umma_commit(bar_empty + 8 * s);                  // stage reusable once these MMAs retire
+                        if (group_last) {
+                            umma_commit(bar_part_full + 8 * (gcount & 1));
+                            ++gcount;
+                        }
+                    }
+                    umma_commit(bar_lo_full);
+                    ++lcount;
+                }
+            }
+            if (prof) { prof[blockIdx.x * 8 + 2] = w_acc; prof[blockIdx.x * 8 + 3] = w_data; }
+        }
+    } else if (warp >= 12) {
+        // ------------------------------------------------------------------ converter: A_lo = x - trunc_tf32(x)
+        const int t = threadIdx.x - 384;                             // 0..127
+        int it = 0;
+        long long c_wait = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            for (int kb = 0; kb < kb_total; ++kb, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                const long long t0 = VQ_CLOCK();
+                mbar_wait(bar_full + 8 * s, ph);
+                c_wait += VQ_CLOCK() - t0;
+                const float4 *src = reinterpret_cast<const float4 *>(smem + (size_t)s * STAGE_BYTES);
+                float4 *dst = reinterpret_cast<float4 *>(smem + (size_t)s * STAGE_BYTES + A_BYTES);
+#pragma unroll
+                for (int j = 0; j < (int)(A_BYTES / 16 / 128); ++j) {
+                    const float4 x = src[j * 128 + t];
+                    float4 l;
+                    l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+                    l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+                    l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+                    l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+                    dst[j * 128 + t] = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (UMMA)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_conv + 8 * s);
+            }
+        }
+        if (prof && t == 0) prof[blockIdx.x * 8 + 4] = c_wait;
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------------ epilogue (8 warps)
+        const int ew = warp - 4;                  // 0..7
+        const int quarter = warp & 3;             // TMEM lanes 32*quarter .. +31 (hardware rule: warp id % 4)
+        const int half = ew >> 2;                 // which 64 of the 128 queries this warp handles
+        const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 64);
+        unsigned int *my_cnt = cnt_s + ew * 64 * 2;
+        int gcount = 0, lcount = 0;
+        long long e_wait = 0, e_busy = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            const long long row = a.row0 + (long long)tile * BM + quarter * 32 + lane;    // this thread's clip
+            const bool row_ok = row < a.n_rows_total;
+            for (int st = 0; st < a.n_streams; ++st) {
+                float run[64];
+#pragma unroll
+                for (int j = 0; j < 64; ++j) run[j] = 0.f;
+                const int n_groups = (kbps + GROUP_KB - 1) / GROUP_KB;
+                for (int g = 0; g < n_groups; ++g, ++gcount) {
+                    const int b = gcount & 1;
+                    const long long t0 = VQ_CLOCK();
+                    mbar_wait(bar_part_full + 8 * b, (gcount >> 1) & 1);
+                    const long long t1 = VQ_CLOCK();
+                    e_wait += t1 - t0;
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    uint32_t r0[32], r1[32];
+                    const uint32_t col = b ? COL_PHI1 : COL_PHI0;
+                    tmem_ld32(tlane + col, r0);
+                    tmem_ld32(tlane + col + 32, r1);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_part_empty + 8 * b);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        run[j] += __uint_as_float(r0[j]);
+                        run[32 + j] += __uint_as_float(r1[j]);
+                    }
+                    e_busy += VQ_CLOCK() - t1;
+                }
+                // small terms of this stream, then this stream's contribution to the score
+                {
+                    const long long t0 = VQ_CLOCK();
+                    mbar_wait(bar_lo_full, lcount & 1);
+                    const long long t1 = VQ_CLOCK();
+                    e_wait += t1 - t0;
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    uint32_t r0[32], r1[32];
+                    tmem_ld32(tlane + COL_PLO, r0);
+                    tmem_ld32(tlane + COL_PLO + 32, r1);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_lo_empty);
+                    ++lcount;
+                    const float ic = (inv_counts && row_ok) ? inv_counts[row * a.n_streams + st] : a.inv_splits;
+                    const float w = a.w[st];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float d0 = w * (1.0f - (run[j] + __uint_as_float(r0[j])) * ic);
+                        const float d1 = w * (1.0f - (run[32 + j] + __uint_as_float(r1[j])) * ic);
+                        run[j] = d0 * d0;
+                        run[32 + j] = d1 * d1;
+                    }
+                    if (st > 0) {                                    // add the terms of the earlier streams
+                        tmem_ld32(tlane + COL_PARK, r0);
+                        tmem_ld32(tlane + COL_PARK + 32, r1);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            run[j] += __uint_as_float(r0[j]);
+                            run[32 + j] += __uint_as_float(r1[j]);
+                        }
+                    }
+                    if (st + 1 < a.n_streams) {                      // park until the next stream is done
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            r0[j] = __float_as_uint(run[j]);
+                            r1[j] = __float_as_uint(run[32 + j]);
+                        }
+                        tmem_st32(tlane + COL_PARK, r0);
+                        tmem_st32(tlane + COL_PARK + 32, r1);
+                        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    }
+                    e_busy += VQ_CLOCK() - t1;
+                }
+                if (st + 1 < a.n_streams) continue;
+                // ---- scores of this thread's clip against this warp's 64 queries
+                const long long t1 = VQ_CLOCK();
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    unsigned int cm = 0, cn = 0;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int ql = c * 32 + j;                   // query within this warp's 64
+                        const int q = half * 64 + ql;
+                        const float sc = 1.0f - __fsqrt_rn(run[ql] * a.inv_den);
+                        const bool live = row_ok && (q < a.n_queries);
+                        if (scores_dbg && live) scores_dbg[(size_t)q * a.n_rows_total + row] = sc;
+                        if (__any_sync(0xffffffffu, live && sc >= gate_s[q])) {
+                            const bool m = live && (sc >= a.th_f);
+                            const bool nm = live && !m && (sc >= a.lo_f);
+                            const bool cand = live && (sc > cut_s[q]);
+                            const unsigned int bm = __ballot_sync(0xffffffffu, m);
+                            const unsigned int bn = __ballot_sync(0xffffffffu, nm);
+                            const unsigned int bc = __ballot_sync(0xffffffffu, cand);
+                            if (lane == j) { cm += __popc(bm); cn += __popc(bn); }
+                            if (bc) {
+                                const int leader = __ffs(bc) - 1;
+                                unsigned int base = 0;
+                                if (lane == leader) base = atomicAdd(&cand_cnt[q], (unsigned int)__popc(bc));
+                                base = __shfl_sync(0xffffffffu, base, leader);
+                                if (cand) {
+                                    const long long slot = (long long)base + __popc(bc & ((1u << lane) - 1u));
+                                    if (slot < a.cand_cap)
+                                        cand_keys[(size_t)q * a.cand_cap + slot] = vq::make_key(sc, (unsigned int)row);
+                                }
+                            }
+                        }
+                    }
+                    my_cnt[(c * 32 + lane) * 2] += cm;               // lane owns query c*32+lane of this warp
+                    my_cnt[(c * 32 + lane) * 2 + 1] += cn;
+                }
+                e_busy += VQ_CLOCK() - t1;
+            }
+        }
+        __syncwarp();
+        for (int ql = lane; ql < 64; ql += 32) {
+            const int q = half * 64 + ql;
+            if (my_cnt[ql * 2]) atomicAdd(&counts_g[2 * q], (unsigned long long)my_cnt[ql * 2]);
+            if (my_cnt[ql * 2 + 1]) atomicAdd(&counts_g[2 * q + 1], (unsigned long long)my_cnt[ql * 2 + 1]);
+        }
+        if (prof && threadIdx.x == 128) { prof[blockIdx.x * 8 + 5] = e_wait; prof[blockIdx.x * 8 + 6] = e_busy; }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+    }
+}
+
+// After each chunk: keep the k best candidates per query (sorted), raise the cut to the k-th score.
+__global__ void __launch_bounds__(1024)
+batch_compact(unsigned int *cand_cnt, unsigned long long *cand_keys, long long cand_cap, int topk, float *cut_g) {
+    __shared__ vq::TopkScratch tk;
+    const int q = blockIdx.x;
+    long long C = (long long)cand_cnt[q];
+    if (C > cand_cap) C = cand_cap;
+    unsigned long long *keys = cand_keys + (size_t)q * cand_cap;
+    const int k = vq::block_topk_1024(keys, C, topk, tk);
+    __syncthreads();
+    for (int i = threadIdx.x; i < k; i += blockDim.x) keys[i] = tk.sel[i];
+    if (threadIdx.x == 0) {
+        cand_cnt[q] = (unsigned int)k;
+        if (k == topk && k > 0) cut_g[q] = vq::key_score(tk.sel[k - 1]);
+    }
+}
+
+__global__ void batch_output(const unsigned int *cand_cnt, const unsigned long long *cand_keys, long long cand_cap,
+                             int topk, long long first_global_row, long long *rows_out, float *scores_out) {
+    const int q = blockIdx.x;
+    const int k = (int)cand_cnt[q];
+    for (int i = threadIdx.x; i < topk; i += blockDim.x) {
+        if (i < k) {
+            const unsigned long long key = cand_keys[(size_t)q * cand_cap + i];
+            rows_out[(size_t)q * topk + i] = first_global_row + (long long)vq::key_row(key);
+            scores_out[(size_t)q * topk + i] = vq::key_score(key);
+        } else {
+            rows_out[(size_t)q * topk + i] = -1;
+            scores_out[(size_t)q * topk + i] = __int_as_float(0xff800000);
+        }
+    }
+}
+
+__global__ void fill_f32(float *p, float v, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int encode_map(CUtensorMap *map, const float *base, uint64_t inner, uint64_t rows, uint32_t box_rows) {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        VQ_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr));
+        VQ_REQUIRE(p && qr == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available in this driver");
+        fn = (EncodeTiledFn)p;
+    }
+    const cuuint64_t dims[2] = {inner, rows};
+    const cuuint64_t strides[1] = {inner * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VQ_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d", (int)r);
+    return 0;
+}
+
+float float_ceil_of(double x) {
+    // smallest float f with (double)f >= x, so that for every float s: (double)s >= x  <=>  s >= f
+    float f = (float)x;
+    if ((double)f < x) f = nextafterf(f, INFINITY);
+    return f;
+}
+
+struct Dev {
+    void *p = nullptr;
+    ~Dev() { if (p) cudaFree(p); }
+    cudaError_t alloc(size_t b) { return cudaMalloc(&p, b ? b : 8); }
+    template <class T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+int run_batch(vq_store *s, const float *targets, int n_queries, const vq_scan_params *p, int64_t *counts_out,
+              int64_t *topk_rows_out, float *topk_scores_out, float *kernel_ms_out, float *scores_dbg_host) {
+    VQ_REQUIRE(s && targets && p, "vq_scan_batch: null argument");
+    VQ_REQUIRE(n_queries >= 1, "vq_scan_batch: need at least one query");
+    VQ_REQUIRE(s->stream_len % BK == 0, "vq_scan_batch: stream length %d is not a multiple of %d", s->stream_len, BK);
+    VQ_REQUIRE(p->topk >= 0 && p->topk <= VQ_MAX_TOPK, "vq_scan_batch: topk %d outside 0..%d", p->topk, VQ_MAX_TOPK);
+    VQ_REQUIRE(s->n_rows < (1ll << 31), "vq_scan_batch: shard too large for 32-bit TMA coordinates");
+    double den = 0.0;
+    for (int i = 0; i < s->n_streams; ++i) den += p->weights[i] * p->weights[i];
+    VQ_REQUIRE(den > 0.0, "vq_scan_batch: all stream weights are zero");
+    VQ_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = s->stream;
+    const size_t K = s->row_floats;                       // floats per row = S * stream_len
+    const int topk = p->topk;
+    const long long chunk_rows = (long long)s->sm_count * BM * 6;
+    const long long cap = chunk_rows + VQ_MAX_TOPK;
+    VQ_CUDA(cudaFuncSetAttribute(batch_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BATCH_SMEM));
+    Dev d_t, d_hi, d_lo, d_cut, d_counts, d_cnt, d_keys, d_rows, d_sc, d_dbg;
+    VQ_CUDA(d_t.alloc((size_t)QT * K * 4));
+    VQ_CUDA(d_hi.alloc((size_t)QT * K * 4));
+    VQ_CUDA(d_lo.alloc((size_t)QT * K * 4));
+    VQ_CUDA(d_cut.alloc(QT * 4));
+    VQ_CUDA(d_counts.alloc(QT * 2 * 8));
+    VQ_CUDA(d_cnt.alloc(QT * 4));
+    VQ_CUDA(d_keys.alloc((size_t)QT * cap * 8));
+    VQ_CUDA(d_rows.alloc((size_t)QT * (topk ? topk : 1) * 8));
+    VQ_CUDA(d_sc.alloc((size_t)QT * (topk ? topk : 1) * 4));
+    if (scores_dbg_host) VQ_CUDA(d_dbg.alloc((size_t)QT * s->n_rows * 4));
+    Dev d_prof;
+    const bool want_prof = getenv("VQ_BATCH_PROF") != nullptr;
+    if (want_prof) VQ_CUDA(d_prof.alloc((size_t)s->sm_count * 8 * 8));
+    cudaEvent_t e0, e1;
+    VQ_CUDA(cudaEventCreate(&e0));
+    VQ_CUDA(cudaEventCreate(&e1));
+    float total_ms = 0.f;
+    int rc = 0;
+    for (int q0 = 0; q0 < n_queries && rc == 0; q0 += QT) {
+        const int nq = (n_queries - q0 < QT) ? (n_queries - q0) : QT;
+        VQ_CUDA(cudaMemsetAsync(d_t.p, 0, (size_t)QT * K * 4, st));
+        VQ_CUDA(cudaMemcpyAsync(d_t.p, targets + (size_t)q0 * K, (size_t)nq * K * 4, cudaMemcpyHostToDevice, st));
+        split_targets<<<(unsigned)(((size_t)QT * K + 255) / 256), 256, 0, st>>>(d_t.as<float>(), d_hi.as<float>(),
+                                                                                d_lo.as<float>(), (long long)QT * K);
+        fill_f32<<<1, QT, 0, st>>>(d_cut.as<float>(), -INFINITY, QT);
+        VQ_CUDA(cudaMemsetAsync(d_counts.p, 0, QT * 2 * 8, st));
+        VQ_CUDA(cudaMemsetAsync(d_cnt.p, 0, QT * 4, st));
+        CUtensorMap map_a, map_bhi, map_blo;
+        if (s->n_rows > 0) {
+            if ((rc = encode_map(&map_a, s->rows, K, (uint64_t)s->n_rows, BM))) break;
+            if ((rc = encode_map(&map_bhi, d_hi.as<float>(), K, QT, QT))) break;
+            if ((rc = encode_map(&map_blo, d_lo.as<float>(), K, QT, QT))) break;
+        }
+        BatchArgs a;
+        for (int i = 0; i < VQ_MAX_STREAMS; ++i) a.w[i] = (i < s->n_streams) ? (float)p->weights[i] : 0.f;
+        a.inv_den = (float)(1.0 / den);
+        a.inv_splits = (float)(1.0 / (double)s->n_splits);
+        a.th_f = float_ceil_of(p->threshold);
+        a.lo_f = float_ceil_of(p->lower_limit);
+        a.n_queries = nq;
+        a.kb_per_stream = s->stream_len / BK;
+        a.n_streams = s->n_streams;
+        a.n_rows_total = s->n_rows;
+        a.cand_cap = cap;
+        VQ_CUDA(cudaEventRecord(e0, st));
+        for (long long r0 = 0; r0 < s->n_rows; r0 += chunk_rows) {
+            const long long nr = (s->n_rows - r0 < chunk_rows) ? (s->n_rows - r0) : chunk_rows;
+            a.row0 = r0;
+            a.n_tiles = (int)((nr + BM - 1) / BM);
+            const int grid = a.n_tiles < s->sm_count ? a.n_tiles : s->sm_count;
+            batch_scan<<<grid, BATCH_THREADS, BATCH_SMEM, st>>>(
+                map_a, map_bhi, map_blo, a, s->inv_counts, d_cut.as<float>(), d_counts.as<unsigned long long>(),
+                d_cnt.as<unsigned int>(), d_keys.as<unsigned long long>(),
+                scores_dbg_host ? d_dbg.as<float>() : nullptr, want_prof ? d_prof.as<long long>() : nullptr);
+            if (topk > 0)
+                batch_compact<<<QT, 1024, 0, st>>>(d_cnt.as<unsigned int>(), d_keys.as<unsigned long long>(), cap, topk,
+                                                   d_cut.as<float>());
+            else
+                VQ_CUDA(cudaMemsetAsync(d_cnt.p, 0, QT * 4, st));
+        }
+        VQ_CUDA(cudaEventRecord(e1, st));
+        if (want_prof) {
+            std::vector<long long> h((size_t)s->sm_count * 8);
+            VQ_CUDA(cudaMemcpyAsync(h.data(), d_prof.p, h.size() * 8, cudaMemcpyDeviceToHost, st));
+            VQ_CUDA(cudaStreamSynchronize(st));
+            static const char *names[7] = {"producer wait empty", "producer total", "mma wait acc_empty", "mma wait data",
+                                           "converter wait full", "epilogue wait acc_full", "epilogue busy"};
+            for (int c = 0; c < 7; ++c) fprintf(stderr, "[K3 prof, last chunk, CTA 0] %-24s %12lld cycles\n", names[c], h[c]);
+        }
+        if (topk > 0)
+            batch_output<<<QT, 128, 0, st>>>(d_cnt.as<unsigned int>(), d_keys.as<unsigned long long>(), cap, topk,
+                                             s->first_global_row, d_rows.as<long long>(), d_sc.as<float>());
+        VQ_CUDA(cudaGetLastError());
+        if (counts_out) {
+            std::vector<unsigned long long> h(QT * 2);
+            VQ_CUDA(cudaMemcpyAsync(h.data(), d_counts.p, QT * 2 * 8, cudaMemcpyDeviceToHost, st));
+            VQ_CUDA(cudaStreamSynchronize(st));
+            for (int q = 0; q < nq; ++q) {
+                counts_out[2 * (q0 + q)] = (int64_t)h[2 * q];
+                counts_out[2 * (q0 + q) + 1] = (int64_t)h[2 * q + 1];
+            }
+        }
+        if (topk > 0 && topk_rows_out)
+            VQ_CUDA(cudaMemcpyAsync(topk_rows_out + (size_t)q0 * topk, d_rows.p, (size_t)nq * topk * 8,
+                                    cudaMemcpyDeviceToHost, st));
+        if (topk > 0 && topk_scores_out)
+            VQ_CUDA(cudaMemcpyAsync(topk_scores_out + (size_t)q0 * topk, d_sc.p, (size_t)nq * topk * 4,
+                                    cudaMemcpyDeviceToHost, st));
+        if (scores_dbg_host)
+            VQ_CUDA(cudaMemcpyAsync(scores_dbg_host + (size_t)q0 * s->n_rows, d_dbg.p, (size_t)nq * s->n_rows * 4,
+                                    cudaMemcpyDeviceToHost, st));
+        VQ_CUDA(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) total_ms += ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (kernel_ms_out) *kernel_ms_out = total_ms;
+    return rc;
+}
+
+}  // namespace
 
 extern "C" int vq_scan_batch(vq_store *s, const float *targets, int32_t n_queries, const vq_scan_params *p,
                              int64_t *counts_out, int64_t *topk_rows_out, float *topk_scores_out,
                              float *kernel_ms_out) {
-    (void)s; (void)targets; (void)n_queries; (void)p; (void)counts_out; (void)topk_rows_out;
-    (void)topk_scores_out; (void)kernel_ms_out;
-    vq::set_error("vq_scan_batch: the batched tcgen05 kernel is not part of this build");
-    return -4;
+    return run_batch(s, targets, n_queries, p, counts_out, topk_rows_out, topk_scores_out, kernel_ms_out, nullptr);
+}
+
+extern "C" int vq_scan_batch_scores(vq_store *s, const float *targets, int32_t n_queries, const vq_scan_params *p,
+                                    float *scores_out) {
+    VQ_REQUIRE(scores_out, "vq_scan_batch_scores: null output");
+    VQ_REQUIRE(s && (long long)s->n_rows * 256 <= (1ll << 28), "vq_scan_batch_scores: debug dump limited to 1M rows x 256 queries");
+    vq_scan_params q = *p;
+    q.topk = 0;
+    return run_batch(s, targets, n_queries, &q, nullptr, nullptr, nullptr, nullptr, scores_out);
 }

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "vq_internal.cuh"
+#include "vq_topk.cuh"
 
 namespace {
 
@@ -219,11 +220,7 @@ scan_rows_smem(const float4 *__restrict__ rows, const float4 *__restrict__ targe
 constexpr int kSelThreads = 256;
 constexpr int kRowsPerThread = kChunkRows / kSelThreads;   // 16 contiguous rows per thread
 
-__device__ __forceinline__ unsigned long long make_key(float sc, unsigned int row) {
-    unsigned int u = __float_as_uint(sc);
-    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-    return ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - row);
-}
+using vq::make_key;
 
 struct Flags {
     bool m, nm, tie;
@@ -344,11 +341,7 @@ select_finish(const unsigned int *__restrict__ chunk_counts, unsigned int *chunk
               const long long cand_cap, const int topk, const long long first_global_row,
               float *topk_scores, long long *topk_rows) {
     __shared__ unsigned int ws[33];
-    __shared__ unsigned int digit_hist[256];
-    __shared__ unsigned long long sel[VQ_MAX_TOPK];
-    __shared__ unsigned int sel_n;
-    __shared__ unsigned long long prefix_s;
-    __shared__ unsigned int remain_s;
+    __shared__ vq::TopkScratch tk;
     if (blockIdx.x == 0) {
         // exclusive scan of the three chunk-count arrays; also re-arm the histogram for the next scan
         for (int which = 0; which < 3; ++which) {
@@ -370,93 +363,12 @@ select_finish(const unsigned int *__restrict__ chunk_counts, unsigned int *chunk
     // ---- block 1: exact top-k over the candidate keys (all keys are distinct)
     long long C = (long long)*cand_count;
     if (C > cand_cap) C = cand_cap;
-    const int k = (int)min((long long)topk, C);
-    int n_sel = 0;                                  // keys staged in sel[] for the final sort
-    if (C <= VQ_MAX_TOPK) {
-        // common case (candidates = k + one histogram bin): sort them all, no selection passes
-        for (int i = threadIdx.x; i < (int)C; i += kFinThreads) sel[i] = cand_keys[i];
-        n_sel = (int)C;
-    } else if (k > 0) {
-        // radix select, 8 bits at a time from the top: exact key of the k-th best
-        unsigned long long prefix = 0, mask = 0;
-        unsigned int remain = (unsigned int)k;
-        for (int shift = 56; shift >= 0; shift -= 8) {
-            if (threadIdx.x < 256) digit_hist[threadIdx.x] = 0;
-            __syncthreads();
-            for (long long i = threadIdx.x; i < C; i += kFinThreads) {
-                const unsigned long long key = cand_keys[i];
-                if ((key & mask) == prefix) atomicAdd(&digit_hist[(unsigned int)(key >> shift) & 255u], 1u);
-            }
-            __syncthreads();
-            if (threadIdx.x < 32) {
-                // lane l owns digits 255-8l .. 248-8l (descending); find the digit where the running
-                // count from the top reaches `remain`
-                const int lane = threadIdx.x;
-                unsigned int mine = 0;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) mine += digit_hist[255 - 8 * lane - j];
-                unsigned int inc = mine;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const unsigned int v = __shfl_up_sync(0xffffffffu, inc, o);
-                    if (lane >= o) inc += v;
-                }
-                const unsigned int excl = inc - mine;
-                if (excl < remain && inc >= remain) {
-                    unsigned int run = excl;
-                    int d = 255 - 8 * lane;
-                    for (int j = 0; j < 8; ++j, --d) {
-                        if (run + digit_hist[d] >= remain) break;
-                        run += digit_hist[d];
-                    }
-                    prefix_s = prefix | ((unsigned long long)d << shift);
-                    remain_s = remain - run;
-                }
-            }
-            __syncthreads();
-            prefix = prefix_s;
-            remain = remain_s;
-            mask |= 0xFFull << shift;
-        }
-        const unsigned long long kth = prefix;
-        if (threadIdx.x == 0) sel_n = 0;
-        __syncthreads();
-        for (long long i = threadIdx.x; i < C; i += kFinThreads) {
-            const unsigned long long key = cand_keys[i];
-            if (key >= kth) {
-                const unsigned int at = atomicAdd(&sel_n, 1u);
-                if (at < VQ_MAX_TOPK) sel[at] = key;
-            }
-        }
-        __syncthreads();
-        n_sel = k;
-    }
-    int P = 2;
-    while (P < n_sel) P <<= 1;                       // sort size: next power of two, <= 1024
-    for (int i = threadIdx.x; i < P; i += kFinThreads)
-        if (i >= n_sel) sel[i] = 0ull;
-    __syncthreads();
-    // bitonic sort, descending, P keys
-    for (int size = 2; size <= P; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            const int t = threadIdx.x;
-            if (t < P / 2) {
-                const int lo = 2 * t - (t & (stride - 1));
-                const int hi = lo + stride;
-                const bool desc = ((lo & size) == 0);
-                const unsigned long long a = sel[lo], b = sel[hi];
-                if (desc ? (a < b) : (a > b)) { sel[lo] = b; sel[hi] = a; }
-            }
-            __syncthreads();
-        }
-    }
+    const int k = vq::block_topk_1024(cand_keys, C, topk, tk);
     for (int i = threadIdx.x; i < VQ_MAX_TOPK; i += kFinThreads) {
         if (i < k) {
-            const unsigned long long key = sel[i];
-            unsigned int u = (unsigned int)(key >> 32);
-            u = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
-            topk_scores[i] = __uint_as_float(u);
-            topk_rows[i] = first_global_row + (long long)(0xFFFFFFFFu - (unsigned int)(key & 0xFFFFFFFFull));
+            const unsigned long long key = tk.sel[i];
+            topk_scores[i] = vq::key_score(key);
+            topk_rows[i] = first_global_row + (long long)vq::key_row(key);
         } else {
             topk_scores[i] = __int_as_float(0xff800000);   // -inf
             topk_rows[i] = -1;

@@ -338,6 +338,54 @@ class FeatureStore:
             out[lo:lo + sh.n_rows] = part
         return out
 
+    # ------------------------------------------------------------------ batched queries (tcgen05)
+    def scan_batch(self, targets, weights, threshold, lower_limit, topk=0, debug_scores=False):
+        """Score Q targets against the whole store in one pass per shard on the tensor cores.
+        targets: list of {stream: {split: vector}} or array [Q, S, P, dim].
+        Returns (counts [Q, 2] = matches, near misses; topk_rows [Q, k]; topk_scores [Q, k]; kernel ms)
+        or, with debug_scores, the fp32 score matrix [Q, n_rows] (single-shard stores only)."""
+        if isinstance(targets, np.ndarray):
+            T = np.ascontiguousarray(targets, dtype=np.float32).reshape((-1,) + self.row_shape)
+        else:
+            T = np.stack([self.pack_target(t, np.float32)[0] for t in targets])
+        Q = T.shape[0]
+        w = [weights[s] for s in self.streams] if isinstance(weights, dict) else list(weights)
+        p = make_params(w, threshold, lower_limit, 0.0, topk)
+        if debug_scores:
+            if len(self.shards) != 1:
+                raise VQError("scan_batch(debug_scores=True) needs a single-shard store")
+            out = np.empty((Q, self.n_rows), np.float32)
+            check(lib().vq_scan_batch_scores(self.shards[0].handle, ptr(T), Q, C.byref(p), ptr(out)),
+                  "vq_scan_batch_scores")
+            return out
+        counts = np.zeros((Q, 2), np.int64)
+        k = max(topk, 1)
+        rows_l, sc_l, ms = [], [], 0.0
+        for sh in self.shards:
+            c = np.zeros((Q, 2), np.int64)
+            r = np.full((Q, k), -1, np.int64)
+            s_ = np.full((Q, k), -np.inf, np.float32)
+            t_ms = C.c_float()
+            check(lib().vq_scan_batch(sh.handle, ptr(T), Q, C.byref(p), ptr(c), ptr(r), ptr(s_), C.byref(t_ms)),
+                  "vq_scan_batch")
+            counts += c
+            rows_l.append(r)
+            sc_l.append(s_)
+            ms = max(ms, t_ms.value)
+        if topk == 0:
+            return counts, np.empty((Q, 0), np.int64), np.empty((Q, 0), np.float32), ms
+        if len(self.shards) == 1:
+            return counts, rows_l[0], sc_l[0], ms
+        rows_o = np.full((Q, topk), -1, np.int64)
+        sc_o = np.full((Q, topk), -np.inf, np.float32)
+        n = C.c_int32()
+        for q in range(Q):
+            sc = np.ascontiguousarray(np.stack([s_[q] for s_ in sc_l]))
+            rw = np.ascontiguousarray(np.stack([r[q] for r in rows_l]))
+            check(lib().vq_merge_topk(len(self.shards), topk, ptr(sc), ptr(rw), ptr(sc_o[q]), ptr(rows_o[q]),
+                                      C.byref(n)), "vq_merge_topk")
+        return counts, rows_o, sc_o, ms
+
     # ------------------------------------------------------------------ labelled subset (fp64)
     def labelled_sims(self, target_features, global_rows):
         """float64 [n, S] similarities of the given rows (any shard) against an fp64 target."""
