@@ -198,26 +198,12 @@ def main():
     torch.cuda.set_stream(stream)
     sptr = C.c_void_p(stream.cuda_stream)
     assert stream.cuda_stream != 0
-    pay_ptr, pay_n = C.c_void_p(), C.c_int32()
-    npay = 4 + 2 * TOPK
-    gathered = torch.zeros(world * npay, dtype=torch.int64, device=dev)
-    merged = torch.zeros(npay, dtype=torch.int64, device=dev)
-    payload_t = None
-
-    class _Arr:                                                       # zero-copy view of the library's payload
-        def __init__(self, p, nbytes):
-            self.__cuda_array_interface__ = {"shape": (nbytes // 8,), "typestr": "<i8", "data": (p, False), "version": 3}
+    from video_query_algorithms_b200.sharded import RankScan
+    rank_scan = RankScan(handle, TOPK, local_rank, dist if world > 1 else None, torch)
 
     def step():
-        nonlocal payload_t
-        _ffi.check(lib.vq_scan_enqueue(handle, C.c_void_p(target_dev.data_ptr()), C.byref(params), sptr), "vq_scan_enqueue")
-        if world > 1:
-            if payload_t is None:
-                _ffi.check(lib.vq_scan_payload(handle, C.byref(pay_ptr), C.byref(pay_n)), "vq_scan_payload")
-                payload_t = torch.as_tensor(_Arr(pay_ptr.value, pay_n.value * 8), device=dev)
-            dist.all_gather_into_tensor(gathered, payload_t)
-            _ffi.check(lib.vq_merge_payloads_enqueue(local_rank, C.c_void_p(gathered.data_ptr()), world, TOPK,
-                                                     C.c_void_p(merged.data_ptr()), sptr), "vq_merge_payloads_enqueue")
+        # local fused scan + selection; for N > 1 one NCCL allgather of the 1.6 KB payload + device merge
+        rank_scan.enqueue(target_dev.data_ptr(), params, stream.cuda_stream)
 
     def barrier():
         torch.cuda.synchronize()
@@ -309,7 +295,9 @@ def main():
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+                tj = json.load(f)
+                # ncu figure is per launch of a 1M-clip scan; traffic scales with the clips per launch
+                traffic = int(tj["dram_bytes_per_launch"] * (n / 1_000_000))
         except Exception:
             pass
         line = {

@@ -1,0 +1,102 @@
+"""Multi-GPU scan, one process per GPU (torchrun): clip-range shards, no data-path collective except the
+merge of per-rank results.
+
+Each rank owns rows [rank * n_local, (rank + 1) * n_local) of the search set.  After its local scan a
+rank's payload is `[4 + 2k] int64` = n_match, n_near, n_tie, n_topk | top-k global rows | top-k score bits;
+ranks exchange payloads with ONE all_gather (NCCL over NVLink on GPUs, gloo in the CPU tests) and every
+rank merges the gathered buffer: counts are summed, the global top-k is the k best under
+(score descending, global row ascending) — the ranking rule of reference ticket.py:266.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import check, lib, ptr
+
+
+def pack_payload(counts, rows, scores, k):
+    """Host-side twin of what `select_compact` writes on the device (tests / CPU ranks)."""
+    out = np.empty(4 + 2 * k, np.int64)
+    out[:4] = counts
+    out[4:4 + k] = -1
+    out[4 + k:] = np.float32(-np.inf).view(np.uint32)
+    n = len(rows)
+    out[4:4 + n] = rows
+    out[4 + k:4 + k + n] = np.asarray(scores, np.float32).view(np.uint32).astype(np.int64)
+    return out
+
+
+def unpack_payload(payload, k):
+    counts = payload[:4].copy()
+    n = int(counts[3])
+    rows = payload[4:4 + n].copy()
+    scores = payload[4 + k:4 + k + n].astype(np.uint32).view(np.float32).copy()
+    return counts, rows, scores
+
+
+def merge_payloads_host(gathered, world, k):
+    """gathered: int64 [world, 4 + 2k] -> merged payload (host merge through the C ABI's vq_merge_topk)."""
+    g = np.ascontiguousarray(gathered, dtype=np.int64).reshape(world, 4 + 2 * k)
+    rows = np.ascontiguousarray(g[:, 4:4 + k])
+    scores = np.ascontiguousarray(g[:, 4 + k:].astype(np.uint32).view(np.float32))
+    so, ro, n = np.empty(k, np.float32), np.empty(k, np.int64), C.c_int32()
+    check(lib().vq_merge_topk(world, k, ptr(scores), ptr(rows), ptr(so), ptr(ro), C.byref(n)), "vq_merge_topk")
+    counts = g[:, :4].sum(axis=0)
+    counts[3] = n.value
+    return pack_payload(counts, ro[:n.value], so[:n.value], k)
+
+
+class RankScan:
+    """One rank's view: local shard handle + the exchange.  `dist` is torch.distributed (already
+    initialised); on CUDA the merge runs on the device on the caller's stream, otherwise on the host."""
+
+    def __init__(self, handle, k, device_index, dist=None, torch=None):
+        self.handle, self.k, self.device_index = handle, int(k), device_index
+        self.dist, self.torch = dist, torch
+        self.world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+        self.n_payload = 4 + 2 * self.k
+        self._payload_t = None
+        if torch is not None and device_index is not None:
+            dev = torch.device("cuda", device_index)
+            self.gathered = torch.zeros(self.world * self.n_payload, dtype=torch.int64, device=dev)
+            self.merged = torch.zeros(self.n_payload, dtype=torch.int64, device=dev)
+
+    def _payload_view(self):
+        """Zero-copy torch view of the payload the library wrote on the device."""
+        if self._payload_t is None:
+            p, n = C.c_void_p(), C.c_int32()
+            check(lib().vq_scan_payload(self.handle, C.byref(p), C.byref(n)), "vq_scan_payload")
+
+            class _Arr:
+                pass
+            a = _Arr()
+            a.__cuda_array_interface__ = {"shape": (n.value,), "typestr": "<i8", "data": (p.value, False), "version": 3}
+            self._payload_t = self.torch.as_tensor(a, device=self.torch.device("cuda", self.device_index))
+        return self._payload_t
+
+    def enqueue(self, target_dev_ptr, params, stream_ptr):
+        """Local scan + (world > 1) allgather + device merge, all enqueued on `stream_ptr`; no host sync."""
+        check(lib().vq_scan_enqueue(self.handle, C.c_void_p(target_dev_ptr), C.byref(params), C.c_void_p(stream_ptr)),
+              "vq_scan_enqueue")
+        if self.world > 1:
+            self.dist.all_gather_into_tensor(self.gathered, self._payload_view())
+            check(lib().vq_merge_payloads_enqueue(self.device_index, C.c_void_p(self.gathered.data_ptr()), self.world,
+                                                  self.k, C.c_void_p(self.merged.data_ptr()), C.c_void_p(stream_ptr)),
+                  "vq_merge_payloads_enqueue")
+
+    def result(self):
+        """(counts[4], global top-k rows, scores) after the stream has been synchronised."""
+        t = self.merged if self.world > 1 else self._payload_view()
+        return unpack_payload(t.cpu().numpy(), self.k)
+
+
+def exchange_host(payload, dist, torch, k):
+    """CPU ranks (gloo): allgather numpy payloads and merge on the host."""
+    world = dist.get_world_size()
+    mine = torch.from_numpy(np.ascontiguousarray(payload, dtype=np.int64))
+    gathered = torch.empty(world * mine.numel(), dtype=torch.int64)
+    dist.all_gather_into_tensor(gathered, mine)
+    return merge_payloads_host(gathered.numpy(), world, k)
