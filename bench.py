@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--clips-per-gpu", type=int, default=1_000_000)
     ap.add_argument("--no-cold", action="store_true", help="skip the cold end-to-end leg (8 GB upload per step)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: peer-memory push + fused merge kernel (default) or NCCL allgather + merge kernel")
     return ap.parse_args()
 
 
@@ -199,7 +201,7 @@ def main():
     sptr = C.c_void_p(stream.cuda_stream)
     assert stream.cuda_stream != 0
     from video_query_algorithms_b200.sharded import RankScan
-    rank_scan = RankScan(handle, TOPK, local_rank, dist if world > 1 else None, torch)
+    rank_scan = RankScan(handle, TOPK, local_rank, dist if world > 1 else None, torch, exchange=args.exchange)
 
     def step():
         # local fused scan + selection; for N > 1 one NCCL allgather of the 1.6 KB payload + device merge
@@ -240,6 +242,7 @@ def main():
     sc_counts = _ffi.ScanCounts()
     _ffi.check(lib.vq_scan_wait(handle, sptr, C.byref(sc_counts)), "vq_scan_wait")
 
+    g_counts, g_rows, g_scores = rank_scan.result()
     # ---- end to end through the public API, host buffers: target H2D, counts + lists + top-k D2H
     e2e_steps = max(3, min(args.steps, 100))
     for _ in range(2):
@@ -315,10 +318,14 @@ def main():
                     "steps": e2e_steps, "what": "FeatureStore.scan + topk + matches + near_misses through the C ABI with host "
                     "buffers; the shard stays resident in HBM between queries (the store outlives broker ticks)"},
             "e2e_cold": cold,
-            "gpu_launches": KERNELS_PER_STEP * args.steps + (args.steps if world > 1 else 0),
+            "gpu_launches": rank_scan.kernels_per_step() * args.steps,
+            "exchange": rank_scan.exchange,
             "clocks": sampler.result(),
             "last_step_counts": {"n_match": int(sc_counts.n_match), "n_near": int(sc_counts.n_near),
                                  "n_tie": int(sc_counts.n_tie), "n_topk": int(sc_counts.n_topk)},
+            "last_step_global": {"n_match": int(g_counts[0]), "n_near": int(g_counts[1]), "n_topk": int(g_counts[3]),
+                                 "top1_row": int(g_rows[0]) if len(g_rows) else None,
+                                 "top1_score": float(g_scores[0]) if len(g_scores) else None},
         }
         if world == 1 and not args.no_cpu:
             cores = len(os.sched_getaffinity(0))
@@ -331,6 +338,8 @@ def main():
                 "vectorised_numpy_f64": {"value": vv, "unit": "clips/s", "cores": cores,
                                          "sample": "200000-clip slice, one pass (%.1f s), BLAS on all cores" % vdt}}
         print(json.dumps(line), flush=True)
+    # global result of the last timed step (all ranks hold the same merged payload)
+    rank_scan.close()
     if world > 1:
         dist.destroy_process_group()
     st.close()

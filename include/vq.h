@@ -114,6 +114,18 @@ int vq_scan_payload(vq_store *s, const int64_t **payload_dev, int32_t *n_int64);
 int vq_merge_payloads_enqueue(int device, const int64_t *gathered_dev, int32_t n_lists, int32_t topk,
                               int64_t *merged_dev, void *stream);
 
+/* Peer-memory variant of the same exchange (one process per GPU, same node): every rank stores its payload
+ * into all peers' inboxes over NVLink (CUDA IPC mappings), then waits for the others and merges — one
+ * kernel behind the selection kernels, no NCCL call.  Setup: create, exchange the 64-byte local handles
+ * between ranks by any means (torch.distributed all_gather, MPI, files), connect.                    */
+typedef struct vq_exchange vq_exchange;
+int vq_exchange_create(vq_exchange **out, int device, int world, int rank);
+int vq_exchange_local_handle(vq_exchange *x, void *handle_out /* 64 bytes */);
+int vq_exchange_connect(vq_exchange *x, const void *all_handles /* [world][64] */);
+int vq_exchange_destroy(vq_exchange *x);
+int vq_scan_exchange_enqueue(vq_store *s, vq_exchange *x, void *stream);
+int vq_exchange_merged(vq_exchange *x, const int64_t **merged_dev /* [4 + 2*topk] */);
+
 /* per-launch device times of K1 recorded since the last call (ring of 1024), in ms           */
 int vq_scan_kernel_times(vq_store *s, int32_t cap, float *ms_out, int32_t *n_out);
 /* merge per-shard top-k lists (score desc, global row asc) — the host/rank-0 side of the

@@ -60,6 +60,12 @@ PROTOTYPES = {
     "vq_scan_view": (C.c_int, [_vp, _P(ScanDeviceView)]),
     "vq_scan_payload": (C.c_int, [_vp, _P(_vp), _P(_i32)]),
     "vq_merge_payloads_enqueue": (C.c_int, [C.c_int, _vp, _i32, _i32, _vp, _vp]),
+    "vq_exchange_create": (C.c_int, [_P(_vp), C.c_int, C.c_int, C.c_int]),
+    "vq_exchange_local_handle": (C.c_int, [_vp, _vp]),
+    "vq_exchange_connect": (C.c_int, [_vp, _vp]),
+    "vq_exchange_destroy": (C.c_int, [_vp]),
+    "vq_scan_exchange_enqueue": (C.c_int, [_vp, _vp, _vp]),
+    "vq_exchange_merged": (C.c_int, [_vp, _P(_vp)]),
     "vq_scan_kernel_times": (C.c_int, [_vp, _i32, _vp, _P(_i32)]),
     "vq_merge_topk": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _P(_i32)]),
     "vq_labelled_sims": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),

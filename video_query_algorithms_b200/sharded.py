@@ -49,43 +49,78 @@ def merge_payloads_host(gathered, world, k):
     return pack_payload(counts, ro[:n.value], so[:n.value], k)
 
 
+class _DevArray:
+    """Zero-copy __cuda_array_interface__ view of library-owned device memory."""
+
+    def __init__(self, ptr_value, n_int64):
+        self.__cuda_array_interface__ = {"shape": (n_int64,), "typestr": "<i8", "data": (ptr_value, False), "version": 3}
+
+
 class RankScan:
     """One rank's view: local shard handle + the exchange.  `dist` is torch.distributed (already
-    initialised); on CUDA the merge runs on the device on the caller's stream, otherwise on the host."""
+    initialised).  exchange = "p2p": payloads are stored straight into the peers' inboxes over NVLink and
+    merged by one kernel (vq_scan_exchange_enqueue, csrc/vq_exchange.cu); exchange = "nccl": one
+    all_gather_into_tensor + the merge kernel.  Everything is enqueued on the caller's stream."""
 
-    def __init__(self, handle, k, device_index, dist=None, torch=None):
+    def __init__(self, handle, k, device_index, dist=None, torch=None, exchange="p2p"):
         self.handle, self.k, self.device_index = handle, int(k), device_index
         self.dist, self.torch = dist, torch
         self.world = dist.get_world_size() if dist is not None and dist.is_initialized() else 1
+        self.rank = dist.get_rank() if self.world > 1 else 0
         self.n_payload = 4 + 2 * self.k
+        self.exchange = exchange if self.world > 1 else "none"
         self._payload_t = None
-        if torch is not None and device_index is not None:
-            dev = torch.device("cuda", device_index)
+        self._x = None
+        dev = torch.device("cuda", device_index)
+        if self.exchange == "nccl":
             self.gathered = torch.zeros(self.world * self.n_payload, dtype=torch.int64, device=dev)
             self.merged = torch.zeros(self.n_payload, dtype=torch.int64, device=dev)
+        elif self.exchange == "p2p":
+            self._x = C.c_void_p()
+            check(lib().vq_exchange_create(C.byref(self._x), device_index, self.world, self.rank), "vq_exchange_create")
+            mine = np.zeros(64, np.uint8)
+            check(lib().vq_exchange_local_handle(self._x, ptr(mine)), "vq_exchange_local_handle")
+            t_mine = torch.from_numpy(mine).to(dev)
+            t_all = torch.empty(self.world * 64, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(t_all, t_mine)             # setup only: 64-byte IPC handles
+            handles = np.ascontiguousarray(t_all.cpu().numpy())
+            check(lib().vq_exchange_connect(self._x, ptr(handles)), "vq_exchange_connect")
+            dist.barrier()
+            p = C.c_void_p()
+            check(lib().vq_exchange_merged(self._x, C.byref(p)), "vq_exchange_merged")
+            self.merged = torch.as_tensor(_DevArray(p.value, self.n_payload), device=dev)
+
+    def close(self):
+        if self._x is not None:
+            self.torch.cuda.synchronize()
+            if self.world > 1:
+                self.dist.barrier()                                  # nobody unmaps while a peer may still write
+            lib().vq_exchange_destroy(self._x)
+            self._x = None
 
     def _payload_view(self):
         """Zero-copy torch view of the payload the library wrote on the device."""
         if self._payload_t is None:
             p, n = C.c_void_p(), C.c_int32()
             check(lib().vq_scan_payload(self.handle, C.byref(p), C.byref(n)), "vq_scan_payload")
-
-            class _Arr:
-                pass
-            a = _Arr()
-            a.__cuda_array_interface__ = {"shape": (n.value,), "typestr": "<i8", "data": (p.value, False), "version": 3}
-            self._payload_t = self.torch.as_tensor(a, device=self.torch.device("cuda", self.device_index))
+            self._payload_t = self.torch.as_tensor(_DevArray(p.value, n.value),
+                                                   device=self.torch.device("cuda", self.device_index))
         return self._payload_t
 
     def enqueue(self, target_dev_ptr, params, stream_ptr):
-        """Local scan + (world > 1) allgather + device merge, all enqueued on `stream_ptr`; no host sync."""
+        """Local scan + (world > 1) exchange + merge, all enqueued on `stream_ptr`; no host sync."""
         check(lib().vq_scan_enqueue(self.handle, C.c_void_p(target_dev_ptr), C.byref(params), C.c_void_p(stream_ptr)),
               "vq_scan_enqueue")
-        if self.world > 1:
+        if self.exchange == "p2p":
+            check(lib().vq_scan_exchange_enqueue(self.handle, self._x, C.c_void_p(stream_ptr)), "vq_scan_exchange_enqueue")
+        elif self.exchange == "nccl":
             self.dist.all_gather_into_tensor(self.gathered, self._payload_view())
             check(lib().vq_merge_payloads_enqueue(self.device_index, C.c_void_p(self.gathered.data_ptr()), self.world,
                                                   self.k, C.c_void_p(self.merged.data_ptr()), C.c_void_p(stream_ptr)),
                   "vq_merge_payloads_enqueue")
+
+    def kernels_per_step(self):
+        return 4 + {"none": 0, "p2p": 1, "nccl": 1}[self.exchange]
 
     def result(self):
         """(counts[4], global top-k rows, scores) after the stream has been synchronised."""
