@@ -125,3 +125,43 @@ def test_sample_of_index_range_equals_sample_of_items():
         random.seed(99)
         b = [items[j] for j in random.sample(range(len(items)), k)]
         assert a == b and random.getstate() == sa
+
+
+# ---------------------------------------------------------------------------- ingest (host parsing)
+def _write_csv(path, video, stream, clips, feats):
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    with open(path, "w") as f:
+        f.write("video =%s, video url =../x/, CNN stream =%s, feature blob =global_pool, caffe model =/m.caffemodel\n"
+                % (video, stream))
+        for c, row in zip(clips, feats):
+            f.write(",".join([str(c)] + [repr(float(x)) for x in row]) + "\n")
+
+
+def test_feature_tree_parser_reads_the_load_db_layout(tmp_path):
+    from video_query_algorithms_b200 import ingest
+    rng = np.random.default_rng(0)
+    want = {}
+    for split in (1, 2):
+        for stream in ("rgb", "warped_optical_flow"):
+            feats = rng.random((5, 8))
+            want[(stream, split)] = feats
+            _write_csv(str(tmp_path / "vidA" / ("UCF101_split%d" % split) / (stream + "_global_pool_features.csv")),
+                       "vidA", stream, [1, 2, 3, 4, 5], feats)
+    tree = ingest.read_feature_tree(str(tmp_path))
+    assert list(tree) == ["vidA"] and list(tree["vidA"]["clip_numbers"]) == [1, 2, 3, 4, 5]
+    for (stream, split), feats in want.items():
+        assert np.array_equal(tree["vidA"]["features"][stream][split], feats)     # repr() round-trips float64
+
+
+def test_feature_tree_parser_on_reference_fixture_if_present():
+    src = "/root/reference/data/features/stock-video-clips_features"
+    if not os.path.isdir(src):
+        pytest.skip("reference data not present (GPU box)")
+    from video_query_algorithms_b200 import ingest
+    tree = ingest.read_feature_tree(src)
+    z = np.load(os.path.join(ROOT, "tests", "golden", "fixture_brooklyn.npz"))
+    v = tree["DowntownBrooklynDrive_480p"]
+    assert np.array_equal(v["clip_numbers"], z["clip_numbers"])
+    for si, s in enumerate(("rgb", "warped_optical_flow")):
+        for pi, p in enumerate(z["splits"]):
+            assert np.array_equal(v["features"][s][int(p)], z["X"][:, si, pi])
