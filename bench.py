@@ -142,7 +142,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference is single-threaded Python (GIL-bound loops); it cannot use more host threads",
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, world):
@@ -155,6 +155,15 @@ def workload_config(args, world):
 
 
 # ------------------------------------------------------------------------------------ GPU arm
+def emit(line):
+    """Exactly one JSON line on the real stdout (libraries such as NCCL print banners to fd 1)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)                      # everything else that writes to stdout goes to stderr
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -337,7 +346,7 @@ def main():
                           "compute_similarities/compute_scores/candidate scans, Python lists in memory" % dt,
                 "vectorised_numpy_f64": {"value": vv, "unit": "clips/s", "cores": cores,
                                          "sample": "200000-clip slice, one pass (%.1f s), BLAS on all cores" % vdt}}
-        print(json.dumps(line), flush=True)
+        emit(line)
     # global result of the last timed step (all ranks hold the same merged payload)
     rank_scan.close()
     if world > 1:
