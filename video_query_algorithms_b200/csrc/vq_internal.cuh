@@ -80,4 +80,11 @@ struct vq_store {
     bool ev_made = false;
     int ev_head = 0, ev_count = 0;
     void *pinned_stage = nullptr;    // small pinned buffer for targets / params
+    // pinned mirror of the last scan's lists + top-k (filled by vq_scan so that the fetch calls are plain memcpys)
+    uint32_t *h_rows[3] = {nullptr, nullptr, nullptr};
+    float *h_scores[3] = {nullptr, nullptr, nullptr};
+    int64_t h_cap[3] = {0, 0, 0};
+    int64_t *h_topk_rows = nullptr;
+    float *h_topk_scores = nullptr;
+    bool staged = false;
 };

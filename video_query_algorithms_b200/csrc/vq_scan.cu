@@ -12,6 +12,8 @@
 //   K2c select_compact   order-preserving compaction of the three row lists.
 //
 // Summation order is fixed by the launch geometry, so results are deterministic run to run.
+#include <string.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -525,6 +527,7 @@ extern "C" int vq_scan_enqueue(vq_store *s, const float *target_dev, const vq_sc
     if (a.want_sims && !s->sims)
         VQ_CUDA(cudaMalloc((void **)&s->sims, (size_t)(s->n_rows > 0 ? s->n_rows : 1) * s->n_streams * sizeof(float)));
     s->last_topk = a.topk;
+    s->staged = false;
     const size_t smem_need = (size_t)s->n_streams * s->stream_len * sizeof(float);
     VQ_REQUIRE(smem_need <= 200 * 1024, "scan: target of %zu bytes does not fit in shared memory", smem_need);
     const int slot = s->ev_head;
@@ -582,6 +585,44 @@ extern "C" int vq_scan_wait(vq_store *s, void *stream, vq_scan_counts *out) {
     return 0;
 }
 
+// Copy the ordered lists and the top-k of the scan that just completed into pinned host memory with one
+// batch of async copies and one synchronisation, so that the vq_fetch_* calls are host memcpys.
+static int stage_results(vq_store *s) {
+    const int64_t kMaxStage = 64ll << 20;                    // entries; larger lists are fetched on demand
+    for (int i = 0; i < 3; ++i) {
+        const int64_t n = s->counts_host[i];
+        if (n > kMaxStage) return 0;
+        if (n > s->h_cap[i]) {
+            if (s->h_rows[i]) cudaFreeHost(s->h_rows[i]);
+            if (s->h_scores[i]) cudaFreeHost(s->h_scores[i]);
+            s->h_rows[i] = nullptr;
+            s->h_scores[i] = nullptr;
+            const int64_t cap = n + n / 4 + 1024;
+            VQ_CUDA(cudaMallocHost((void **)&s->h_rows[i], (size_t)cap * sizeof(uint32_t)));
+            VQ_CUDA(cudaMallocHost((void **)&s->h_scores[i], (size_t)cap * sizeof(float)));
+            s->h_cap[i] = cap;
+        }
+    }
+    if (!s->h_topk_rows) {
+        VQ_CUDA(cudaMallocHost((void **)&s->h_topk_rows, VQ_MAX_TOPK * sizeof(int64_t)));
+        VQ_CUDA(cudaMallocHost((void **)&s->h_topk_scores, VQ_MAX_TOPK * sizeof(float)));
+    }
+    for (int i = 0; i < 3; ++i) {
+        const size_t n = (size_t)s->counts_host[i];
+        if (!n) continue;
+        VQ_CUDA(cudaMemcpyAsync(s->h_rows[i], s->list_rows[i], n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
+        VQ_CUDA(cudaMemcpyAsync(s->h_scores[i], s->list_scores[i], n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    }
+    const size_t k = (size_t)s->counts_host[3];
+    if (k) {
+        VQ_CUDA(cudaMemcpyAsync(s->h_topk_rows, s->topk_rows, k * sizeof(int64_t), cudaMemcpyDeviceToHost, s->stream));
+        VQ_CUDA(cudaMemcpyAsync(s->h_topk_scores, s->topk_scores, k * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+    }
+    VQ_CUDA(cudaStreamSynchronize(s->stream));
+    s->staged = true;
+    return 0;
+}
+
 extern "C" int vq_scan(vq_store *s, const float *target, const vq_scan_params *p, vq_scan_counts *out) {
     VQ_REQUIRE(s && target, "vq_scan: null argument");
     VQ_CUDA(cudaSetDevice(s->device));
@@ -589,7 +630,8 @@ extern "C" int vq_scan(vq_store *s, const float *target, const vq_scan_params *p
     memcpy(s->pinned_stage, target, bytes);
     VQ_CUDA(cudaMemcpyAsync(s->target, s->pinned_stage, bytes, cudaMemcpyHostToDevice, s->stream));
     if (int r = vq_scan_enqueue(s, s->target, p, s->stream)) return r;
-    return vq_scan_wait(s, s->stream, out);
+    if (int r = vq_scan_wait(s, s->stream, out)) return r;
+    return stage_results(s);
 }
 
 static int fetch_list(vq_store *s, int which, int64_t cap, int64_t *rows_out, float *scores_out,
@@ -599,6 +641,12 @@ static int fetch_list(vq_store *s, int which, int64_t cap, int64_t *rows_out, fl
     const int64_t n = s->counts_host[which];
     VQ_REQUIRE(cap >= n, "%s: capacity %lld < %lld entries", who, (long long)cap, (long long)n);
     if (n == 0) return 0;
+    if (s->staged) {
+        if (rows_out)
+            for (int64_t i = 0; i < n; ++i) rows_out[i] = s->first_global_row + (int64_t)s->h_rows[which][i];
+        if (scores_out) memcpy(scores_out, s->h_scores[which], (size_t)n * sizeof(float));
+        return 0;
+    }
     if (rows_out) {
         std::vector<uint32_t> tmp((size_t)n);
         VQ_CUDA(cudaMemcpy(tmp.data(), s->list_rows[which], (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
@@ -625,6 +673,11 @@ extern "C" int vq_fetch_topk(vq_store *s, int32_t cap, int64_t *rows_out, float 
     const int n = (int)s->counts_host[3];
     VQ_REQUIRE(cap >= n, "vq_fetch_topk: capacity %d < %d entries", cap, n);
     if (n == 0) return 0;
+    if (s->staged) {
+        if (rows_out) memcpy(rows_out, s->h_topk_rows, (size_t)n * sizeof(int64_t));
+        if (scores_out) memcpy(scores_out, s->h_topk_scores, (size_t)n * sizeof(float));
+        return 0;
+    }
     if (rows_out) VQ_CUDA(cudaMemcpy(rows_out, s->topk_rows, (size_t)n * sizeof(int64_t), cudaMemcpyDeviceToHost));
     if (scores_out) VQ_CUDA(cudaMemcpy(scores_out, s->topk_scores, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost));
     return 0;

@@ -56,6 +56,12 @@ static void store_free(vq_store *s) {
     cudaFree(s->topk_rows);
     cudaFree(s->pack);
     if (s->pinned_stage) cudaFreeHost(s->pinned_stage);
+    for (int i = 0; i < 3; ++i) {
+        if (s->h_rows[i]) cudaFreeHost(s->h_rows[i]);
+        if (s->h_scores[i]) cudaFreeHost(s->h_scores[i]);
+    }
+    if (s->h_topk_rows) cudaFreeHost(s->h_topk_rows);
+    if (s->h_topk_scores) cudaFreeHost(s->h_topk_scores);
     if (s->ev_made)
         for (int i = 0; i < vq::kTimeRing; ++i) {
             cudaEventDestroy(s->ev_start[i]);

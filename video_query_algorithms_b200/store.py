@@ -289,6 +289,8 @@ class FeatureStore:
             check(fn(sh.handle, n, ptr(r), ptr(s)), attr)
             rows.append(r)
             scores.append(s)
+        if len(rows) == 1:
+            return rows[0], scores[0]
         return np.concatenate(rows), np.concatenate(scores)
 
     def matches(self):
@@ -306,6 +308,11 @@ class FeatureStore:
         if k == 0:
             return np.empty(0, np.int64), np.empty(0, np.float32)
         n_l = len(self.shards)
+        if n_l == 1:
+            n = self._last_counts[0].n_topk
+            r, s = np.empty(n, np.int64), np.empty(n, np.float32)
+            check(lib().vq_fetch_topk(self.shards[0].handle, n, ptr(r), ptr(s)), "vq_fetch_topk")
+            return r, s
         sc = np.full((n_l, k), -np.inf, np.float32)
         rw = np.full((n_l, k), -1, np.int64)
         for i, (sh, c) in enumerate(zip(self.shards, self._last_counts)):
