@@ -290,6 +290,8 @@ def test_compute_matches_reproduces_reference_rounds(vq, name, tmp_path, monkeyp
             assert_scores_close(got_sc, np.array([v for _, v in r["selected"]]))
         assert len(t.ranked[0]) == min(10, len(want_scores))
         assert list(t.ranked[0]) == [int(scn.clip_ids[j]) for j in sc.topk_stable(t.scores.array(), len(t.ranked[0]))]
+    # the store is built once per search set and reused by later ticks (the reference re-downloads every job)
+    assert api.calls.count(("search-sets", "features")) == 1
     if scn.rounds[-1]["kind"] == "finalize":
         assert len(api.uploaded_reports) == 1
         body = api.uploaded_reports[0].splitlines()
@@ -304,6 +306,43 @@ def test_compute_matches_reproduces_reference_rounds(vq, name, tmp_path, monkeyp
         for a, b in zip(got_clips, ref_clips):
             if a in ref_score and b in ref_score:
                 assert a == b or abs(ref_score[a] - ref_score[b]) < EPS
+    vq.invalidate()
+
+
+def test_job_error_states_follow_the_reference(vq, tmp_path, monkeypatch):
+    """compute_matches.py:47-52,92-94: fatal query errors -> state 5 + note; recoverable -> note and go on;
+    an empty selection -> state 5 'No matches were found'."""
+    from fake_api import FakeRepository
+    scn = Scenario("A_brooklyn_bagging")
+    monkeypatch.chdir(tmp_path)
+    vq.invalidate()
+    factory = lambda api: (lambda job, url: vq.Ticket(job, url, client=api.client(), devices=[0]))
+    # (1) reference time outside the video: no ref clip
+    api, qid = scn.build_api()
+    api.queries[qid]["ref_clip_id"] = None
+    api.request(qid, "new")
+    vq.compute_matches(FakeRepository(api), vq.Hyperparameter(**scn.hp()), ticket_factory=factory(api))
+    assert api.queries[qid]["process_state"] == 5 and "Fatal Error" in api.queries[qid]["notes"]
+    # (2) revise with dynamic target adjustment but no confirmed match: note, fall back to the scaled ref clip
+    vq.invalidate()
+    api, qid = scn.build_api()
+    api.request(qid, "new")
+    random.seed(a=scn.seed)
+    vq.compute_matches(FakeRepository(api), vq.Hyperparameter(**scn.hp()), ticket_factory=factory(api))
+    api.label_latest_round(qid, lambda m: False)
+    api.request(qid, "revise")
+    vq.compute_matches(FakeRepository(api), vq.Hyperparameter(**scn.hp()), ticket_factory=factory(api))
+    assert api.queries[qid]["process_state"] == 4
+    assert "Changing dynamic target adjustment to False" in api.queries[qid]["notes"]
+    # (3) nothing selectable: ref clip outside the search set and an unreachable threshold
+    vq.invalidate()
+    api, qid = scn.build_api()
+    ss = api.queries[qid]["search_set_to_query"]
+    api.search_sets[ss]["clip_ids"] = [c for c in api.search_sets[ss]["clip_ids"] if c != api.queries[qid]["ref_clip_id"]]
+    api.request(qid, "new")
+    hp = dict(scn.hp(), default_threshold=5.0, near_miss_default=0.0)
+    vq.compute_matches(FakeRepository(api), vq.Hyperparameter(**hp), ticket_factory=factory(api))
+    assert api.queries[qid]["process_state"] == 5 and "No matches were found" in api.queries[qid]["notes"]
     vq.invalidate()
 
 

@@ -255,7 +255,8 @@ class FeatureStore:
         else:
             counts = self._scan_multi(Tc, p)
         self.last = ScanResult(sum(c.n_match for c in counts), sum(c.n_near for c in counts),
-                               sum(c.n_tie for c in counts), 0, max(c.scan_ms for c in counts))
+                               sum(c.n_tie for c in counts), min(int(topk), sum(c.n_topk for c in counts)),
+                               max(c.scan_ms for c in counts))
         self._last_counts = counts
         self._last_topk = topk
         return self.last
