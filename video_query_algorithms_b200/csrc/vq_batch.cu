@@ -18,15 +18,15 @@
 //      round-to-nearest fp32 adds; the small lo terms use their own accumulator (their truncation is
 //      relative to a 2^-11 times smaller magnitude).
 //
-// CTA layout (512 threads, 1 CTA per SM, persistent over 128-clip tiles), streams processed one after
+// CTA layout (384 threads, 1 CTA per SM, persistent over 128-clip tiles), streams processed one after
 // the other:
 //     warp 0       TMA producer: per K block of 32 floats, A tile [128 clips] + B_hi, B_lo tiles
 //                  [128 queries], 128-byte swizzle, 3-stage ring of 64 KB
 //     warp 1       MMA issuer: one elected thread, tcgen05.mma.kind::tf32 M128 N128 K8
-//     warp 2       TMEM allocator (512 columns: P_hi[0], P_hi[1], P_lo, parked stream term)
+//     warps 2-3    converter: lo(x) tiles for the A operand; warp 2 also allocates TMEM
+//                  (512 columns: P_hi[0], P_hi[1], P_lo, parked stream term)
 //     warps 4-11   epilogue: drain partials (tcgen05.ld), running sums in registers, score, tests,
 //                  warp-ballot counts, top-k candidates
-//     warps 12-15  converter: lo(x) tiles for the A operand
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -51,16 +51,27 @@ constexpr int BM = 128;                  // clips per tile (UMMA M)
 constexpr int QT = 128;                  // queries per pass (UMMA N)
 constexpr int BK = 32;                   // floats per K block = one 128-byte swizzle row
 constexpr int UK = 8;                    // UMMA K for tf32
-constexpr int STAGES = 3;
 constexpr int GROUP_KB = VQ_GROUP_KB;    // K blocks per partial accumulator (4 hi*hi MMAs each)
 constexpr uint32_t A_BYTES = BM * BK * 4;        // 16 KB
-constexpr uint32_t B_BYTES = QT * BK * 4;        // 16 KB
-constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // A, A_lo, B_hi, B_lo = 64 KB
-constexpr uint32_t TX_BYTES = A_BYTES + 2 * B_BYTES;
-constexpr int BATCH_THREADS = 512;
-constexpr int N_BARS = 3 * STAGES + 6;
-constexpr size_t BATCH_SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 2 * QT * 4 /*cut, gate*/ +
-                              8 * 64 * 2 * 4 /*per-warp counts*/;
+constexpr int BATCH_THREADS = 384;      // 12 warps -> up to 168 registers per thread (the epilogue keeps 64 sums)
+constexpr int CONV_THREADS = 64;        // converter = warps 2-3
+constexpr int PF_KB = 8;                         // K blocks per L2 prefetch box (8 x 128 B = 1 KB per clip row)
+constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address -> CTA 0 of the pair
+
+// kPair = false: one CTA per tile of 128 clips (cta_group::1).
+// kPair = true : a CTA pair (cluster of 2, cta_group::2) per tile of 256 clips: each CTA stages its own 128
+//                clips and HALF of the query tile; one thread of the leader CTA issues M256 MMAs for both.
+//                Halves the B bytes each SM has to fill and re-read per MMA (the kernel is shared-memory
+//                bandwidth bound, profiles/r1_k3_batched_notes.md).
+template <bool kPair>
+struct Cfg {
+    static constexpr int kStages = kPair ? 4 : 3;
+    static constexpr uint32_t kBBytes = (kPair ? QT / 2 : QT) * BK * 4;          // per CTA: 8 KB or 16 KB
+    static constexpr uint32_t kStageBytes = 2 * A_BYTES + 2 * kBBytes;           // A, A_lo, B_hi, B_lo
+    static constexpr int kBars = 4 * kStages + 6;                                // a_full, full, conv, empty + 6
+    static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ +
+                                    2 * QT * 4 /*cut, gate*/ + 8 * 64 * 2 * 4 /*per-warp counts*/;
+};
 constexpr uint32_t COL_PHI0 = 0, COL_PHI1 = 128, COL_PLO = 256, COL_PARK = 384;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -79,10 +90,46 @@ __device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
         "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(a), "r"(parity) : "memory");
 }
+// same, acquiring at cluster scope: for barriers that the peer CTA of a pair arrives on remotely
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t a, uint32_t parity) {
+    asm volatile(
+        "{\n.reg .pred p;\nWAIT_%=:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(a), "r"(parity) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
         ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t leader_bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(leader_bar) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc),
+        "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((unsigned short)3) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap *map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
 }
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
     // K-major, 128-byte swizzle: 8-row atoms of 128 B, atoms 1024 B apart (SBO), LBO unused (1), version 1
@@ -99,6 +146,26 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t
         "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc),
         "r"(accumulate) : "memory");
+}
+// Lean issue path: the MMA issuer is ONE thread, so every ALU instruction between two tcgen05.mma costs
+// a full dependent-issue latency.  Descriptors are therefore kept as a per-stage 32-bit low word (start
+// address >> 4 | LBO) that only needs "+2" per K step (32 bytes), with a constant high word
+// (SBO = 1024 B, descriptor version 1, SWIZZLE_128B).
+constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+template <bool kPair, bool kAcc>
+__device__ __forceinline__ void umma_issue(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
+    if constexpr (kPair) {
+        asm volatile(
+            "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %4, 0;\nmov.b64 da, {%1, %5};\nmov.b64 db, {%2, %5};\n"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %3, p;\n}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc),
+            "n"(kAcc ? 1 : 0), "r"(DESC_HI) : "memory");
+    } else {
+        asm volatile(
+            "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %4, 0;\nmov.b64 da, {%1, %5};\nmov.b64 db, {%2, %5};\n"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc),
+            "n"(kAcc ? 1 : 0), "r"(DESC_HI) : "memory");
+    }
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -126,6 +193,12 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         : "memory");
 }
 
+__device__ __forceinline__ float sqrt_approx(float x) {     // MUFU.SQRT: 1 instruction, <= 2 ulp
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 struct BatchArgs {
     float w[VQ_MAX_STREAMS];
     float inv_den, inv_splits;
@@ -150,37 +223,47 @@ __global__ void split_targets(const float *__restrict__ t, float *hi, float *lo,
     lo[i] = x - hf;
 }
 
+template <bool kPair>
 __global__ void __launch_bounds__(BATCH_THREADS, 1)
 batch_scan(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
-           const __grid_constant__ CUtensorMap map_blo, const BatchArgs a, const float *__restrict__ inv_counts,
+           const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_apf, const BatchArgs a, const float *__restrict__ inv_counts,
            const float *__restrict__ cut_g, unsigned long long *counts_g /*[QT][2]*/, unsigned int *cand_cnt /*[QT]*/,
            unsigned long long *cand_keys /*[QT][cap]*/, float *scores_dbg /*[Q][n_rows] or null*/,
            long long *prof /*[grid][8] cycle counters or null*/) {
+    using C_ = Cfg<kPair>;
+    constexpr int STAGES = C_::kStages;
+    constexpr uint32_t B_BYTES = C_::kBBytes, STAGE_BYTES = C_::kStageBytes;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES * STAGE_BYTES);
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + N_BARS);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + C_::kBars);
     float *cut_s = reinterpret_cast<float *>(smem + (size_t)STAGES * STAGE_BYTES + 256);
     float *gate_s = cut_s + QT;
     unsigned int *cnt_s = reinterpret_cast<unsigned int *>(gate_s + QT);      // [8 warps][64 queries][2]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t bar_full = smem_u32(&bars[0]), bar_conv = smem_u32(&bars[STAGES]),
-                   bar_empty = smem_u32(&bars[2 * STAGES]), bar_part_full = smem_u32(&bars[3 * STAGES]),
-                   bar_part_empty = smem_u32(&bars[3 * STAGES + 2]), bar_lo_full = smem_u32(&bars[3 * STAGES + 4]),
-                   bar_lo_empty = smem_u32(&bars[3 * STAGES + 5]);
+    const uint32_t cta_rank = kPair ? cluster_ctarank() : 0u;
+    const bool leader = cta_rank == 0;
+    // Barriers (identical offsets in both CTAs of a pair).  Waited on locally: a_full, empty, part_full, lo_full.
+    // Owned by the leader CTA (the peer arrives remotely): full, conv, part_empty, lo_empty.
+    const uint32_t bar_afull = smem_u32(&bars[0]), bar_full = smem_u32(&bars[STAGES]), bar_conv = smem_u32(&bars[2 * STAGES]),
+                   bar_empty = smem_u32(&bars[3 * STAGES]), bar_part_full = smem_u32(&bars[4 * STAGES]),
+                   bar_part_empty = smem_u32(&bars[4 * STAGES + 2]), bar_lo_full = smem_u32(&bars[4 * STAGES + 4]),
+                   bar_lo_empty = smem_u32(&bars[4 * STAGES + 5]);
+    const int n_cta = kPair ? 2 : 1;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_conv + 8 * s, 4);       // one arrive per converter warp
-            mbar_init(bar_empty + 8 * s, 1);      // tcgen05.commit
+            mbar_init(bar_afull + 8 * s, 1);          // pair mode: this CTA's A tile has landed
+            mbar_init(bar_full + 8 * s, n_cta);       // producer arrive(s); bytes of all CTAs' TMA loads
+            mbar_init(bar_conv + 8 * s, (CONV_THREADS / 32) * n_cta);   // one arrive per converter warp
+            mbar_init(bar_empty + 8 * s, 1);          // tcgen05.commit
         }
         for (int b = 0; b < 2; ++b) {
-            mbar_init(bar_part_full + 8 * b, 1);  // tcgen05.commit
-            mbar_init(bar_part_empty + 8 * b, 8); // one arrive per epilogue warp
+            mbar_init(bar_part_full + 8 * b, 1);          // tcgen05.commit
+            mbar_init(bar_part_empty + 8 * b, 8 * n_cta); // one arrive per epilogue warp
         }
         mbar_init(bar_lo_full, 1);
-        mbar_init(bar_lo_empty, 8);
+        mbar_init(bar_lo_empty, 8 * n_cta);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = threadIdx.x; i < QT; i += blockDim.x) {
@@ -190,15 +273,25 @@ batch_scan(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
     }
     for (int i = threadIdx.x; i < 8 * 64 * 2; i += blockDim.x) cnt_s[i] = 0;
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        if constexpr (kPair) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if constexpr (kPair) cluster_sync_all();          // peer barriers are initialised before any remote arrive
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     const int kbps = a.kb_per_stream;
     const int kb_total = kbps * a.n_streams;
+    // work distribution: a "unit" is a CTA (128 clips) or a CTA pair (256 clips)
+    const int unit = kPair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int n_units = kPair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int unit_rows = BM * n_cta;
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
@@ -206,8 +299,8 @@ batch_scan(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
             int it = 0;
             long long p_wait = 0;
             const long long p_t0 = VQ_CLOCK();
-            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-                const int row = (int)(a.row0 + (long long)tile * BM);
+            for (int tile = unit; tile < a.n_tiles; tile += n_units) {
+                const int row = (int)(a.row0 + (long long)tile * unit_rows + (long long)cta_rank * BM);
                 for (int kb = 0; kb < kb_total; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
@@ -215,22 +308,47 @@ batch_scan(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                     mbar_wait(bar_empty + 8 * s, ph ^ 1);
                     p_wait += VQ_CLOCK() - t0;
                     const uint32_t base = smem_u32(smem + (size_t)s * STAGE_BYTES);
-                    mbar_expect(bar_full + 8 * s, TX_BYTES);
-                    tma_load_2d(base, &map_a, kb * BK, row, bar_full + 8 * s);
-                    tma_load_2d(base + 2 * A_BYTES, &map_bhi, kb * BK, 0, bar_full + 8 * s);
-                    tma_load_2d(base + 2 * A_BYTES + B_BYTES, &map_blo, kb * BK, 0, bar_full + 8 * s);
+                    if constexpr (kPair) {
+                        // A: local barrier (the local converter waits on it).  B halves: the leader's barrier.
+                        mbar_expect(bar_afull + 8 * s, A_BYTES);
+                        tma_load_2d(base, &map_a, kb * BK, row, bar_afull + 8 * s);
+                        const uint32_t lbar = (bar_full + 8 * s) & PEER_MASK;
+                        if (leader) mbar_expect(bar_full + 8 * s, 4 * B_BYTES);      // 2 CTAs x (B_hi + B_lo halves)
+                        else mbar_arrive_cluster(lbar);
+                        tma_load_2d_pair(base + 2 * A_BYTES, &map_bhi, kb * BK, (int)cta_rank * (QT / 2), lbar);
+                        tma_load_2d_pair(base + 2 * A_BYTES + B_BYTES, &map_blo, kb * BK, (int)cta_rank * (QT / 2), lbar);
+                    } else {
+                        mbar_expect(bar_full + 8 * s, A_BYTES + 2 * B_BYTES);
+                        tma_load_2d(base, &map_a, kb * BK, row, bar_full + 8 * s);
+                        tma_load_2d(base + 2 * A_BYTES, &map_bhi, kb * BK, 0, bar_full + 8 * s);
+                        tma_load_2d(base + 2 * A_BYTES + B_BYTES, &map_blo, kb * BK, 0, bar_full + 8 * s);
+                    }
                 }
             }
-            if (prof) { prof[blockIdx.x * 8 + 0] = p_wait; prof[blockIdx.x * 8 + 1] = VQ_CLOCK() - p_t0; }
+            (void)p_wait; (void)p_t0;
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
-            // instruction descriptor: D = f32, A = B = tf32, both K-major, N = QT, M = 128
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(QT >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+        // The whole warp runs the loop and the barrier waits, so that addresses and loop state are warp-uniform
+        // (uniform registers feed UTCHMMA directly); one elected lane issues the MMAs and commits.
+        if (leader) {
+            uint32_t elected;
+            asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(elected));
+            // instruction descriptor: D = f32, A = B = tf32, both K-major, N = QT, M = 128 (256 for a CTA pair)
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(QT >> 3) << 17) |
+                                   ((uint32_t)((BM * n_cta) >> 4) << 24);
+            auto commit = [&](uint32_t bar) {
+                if constexpr (kPair) umma_commit_pair(bar);
+                else umma_commit(bar);
+            };
+            auto wait = [&](uint32_t bar, uint32_t parity) {
+                if constexpr (kPair) mbar_wait_cluster(bar, parity);
+                else mbar_wait(bar, parity);
+            };
             int it = 0, gcount = 0, lcount = 0;
-            long long w_acc = 0, w_data = 0;
-            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            long long w_acc = 0, w_data = 0, w_lo = 0, w_conv = 0;
+            const long long m_t0 = VQ_CLOCK();
+            for (int tile = unit; tile < a.n_tiles; tile += n_units) {
                 for (int st = 0; st < a.n_streams; ++st) {
                     uint32_t d_hi = 0;
                     for (int kb = 0; kb < kbps; ++kb, ++it) {
@@ -239,76 +357,89 @@ batch_scan(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                         long long t0 = VQ_CLOCK();
                         if (group_first) {
                             const int b = gcount & 1;
-                            mbar_wait(bar_part_empty + 8 * b, ((gcount >> 1) & 1) ^ 1);   // partial drained
+                            wait(bar_part_empty + 8 * b, ((gcount >> 1) & 1) ^ 1);        // partial drained
                             d_hi = tmem_base + (b ? COL_PHI1 : COL_PHI0);
                         }
-                        if (kb == 0) mbar_wait(bar_lo_empty, (lcount & 1) ^ 1);
-                        w_acc += VQ_CLOCK() - t0;
+                        long long t1 = VQ_CLOCK();
+                        w_acc += t1 - t0;
+                        if (kb == 0) wait(bar_lo_empty, (lcount & 1) ^ 1);
+                        t0 = VQ_CLOCK();
+                        w_lo += t0 - t1;
                         const int s = it % STAGES;
                         const uint32_t ph = (it / STAGES) & 1;
-                        t0 = VQ_CLOCK();
-                        mbar_wait(bar_full + 8 * s, ph);
-                        mbar_wait(bar_conv + 8 * s, ph);
-                        w_data += VQ_CLOCK() - t0;
+                        wait(bar_full + 8 * s, ph);
+                        t1 = VQ_CLOCK();
+                        w_data += t1 - t0;
+                        wait(bar_conv + 8 * s, ph);
+                        w_conv += VQ_CLOCK() - t1;
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint32_t base = smem_u32(smem + (size_t)s * STAGE_BYTES);
                         const uint32_t d_lo = tmem_base + COL_PLO;
+                        if (elected) {
+                        const uint32_t xa = desc_lo(base), xl = desc_lo(base + A_BYTES), th = desc_lo(base + 2 * A_BYTES),
+                                       tl = desc_lo(base + 2 * A_BYTES + B_BYTES);
                         // small terms first, into their own accumulator
+                        if (kb == 0) umma_issue<kPair, false>(d_lo, xl, th, idesc);
+                        else umma_issue<kPair, true>(d_lo, xl, th, idesc);
+                        umma_issue<kPair, true>(d_lo, xa, tl, idesc);
 #pragma unroll
-                        for (int k = 0; k < BK / UK; ++k) {
-                            const uint32_t off = (uint32_t)(k * UK * 4);
-                            umma_tf32(d_lo, umma_desc(base + A_BYTES + off), umma_desc(base + 2 * A_BYTES + off), idesc,
-                                      (kb == 0 && k == 0) ? 0u : 1u);
-                            umma_tf32(d_lo, umma_desc(base + off), umma_desc(base + 2 * A_BYTES + B_BYTES + off), idesc, 1u);
+                        for (int k = 1; k < BK / UK; ++k) {
+                            umma_issue<kPair, true>(d_lo, xl + 2 * k, th + 2 * k, idesc);
+                            umma_issue<kPair, true>(d_lo, xa + 2 * k, tl + 2 * k, idesc);
                         }
+                        if (group_first) umma_issue<kPair, false>(d_hi, xa, th, idesc);
+                        else umma_issue<kPair, true>(d_hi, xa, th, idesc);
 #pragma unroll
-                        for (int k = 0; k < BK / UK; ++k) {
-                            const uint32_t off = (uint32_t)(k * UK * 4);
-                            umma_tf32(d_hi, umma_desc(base + off), umma_desc(base + 2 * A_BYTES + off), idesc,
-                                      (group_first && k == 0) ? 0u : 1u);
+                        for (int k = 1; k < BK / UK; ++k) umma_issue<kPair, true>(d_hi, xa + 2 * k, th + 2 * k, idesc);
+                        commit(bar_empty + 8 * s);                       // stage reusable once these MMAs retire
+                        if (group_last) commit(bar_part_full + 8 * (gcount & 1));
                         }
-                        umma_commit(bar_empty + 8 * s);                  // stage reusable once these MMAs retire
-                        if (group_last) {
-                            umma_commit(bar_part_full + 8 * (gcount & 1));
-                            ++gcount;
-                        }
+                        __syncwarp();
+                        if (group_last) ++gcount;
                     }
-                    umma_commit(bar_lo_full);
+                    if (elected) commit(bar_lo_full);
+                    __syncwarp();
                     ++lcount;
                 }
             }
-            if (prof) { prof[blockIdx.x * 8 + 2] = w_acc; prof[blockIdx.x * 8 + 3] = w_data; }
+            if (prof && elected) {
+                prof[blockIdx.x * 8 + 2] = w_acc; prof[blockIdx.x * 8 + 3] = w_data;
+                prof[blockIdx.x * 8 + 7] = w_lo; prof[blockIdx.x * 8 + 1] = w_conv; prof[blockIdx.x * 8 + 0] = VQ_CLOCK() - m_t0;
+            }
         }
-    } else if (warp >= 12) {
+    } else if (warp == 2 || warp == 3) {
         // ------------------------------------------------------------------ converter: A_lo = x - trunc_tf32(x)
-        const int t = threadIdx.x - 384;                             // 0..127
+        const int t = threadIdx.x - 64;                              // 0..CONV_THREADS-1
         int it = 0;
         long long c_wait = 0;
-        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        for (int tile = unit; tile < a.n_tiles; tile += n_units) {
             for (int kb = 0; kb < kb_total; ++kb, ++it) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 const long long t0 = VQ_CLOCK();
-                mbar_wait(bar_full + 8 * s, ph);
+                mbar_wait((kPair ? bar_afull : bar_full) + 8 * s, ph);
                 c_wait += VQ_CLOCK() - t0;
                 const float4 *src = reinterpret_cast<const float4 *>(smem + (size_t)s * STAGE_BYTES);
                 float4 *dst = reinterpret_cast<float4 *>(smem + (size_t)s * STAGE_BYTES + A_BYTES);
 #pragma unroll
-                for (int j = 0; j < (int)(A_BYTES / 16 / 128); ++j) {
-                    const float4 x = src[j * 128 + t];
+                for (int j = 0; j < (int)(A_BYTES / 16 / CONV_THREADS); ++j) {
+                    const float4 x = src[j * CONV_THREADS + t];
                     float4 l;
                     l.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
                     l.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
                     l.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
                     l.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-                    dst[j * 128 + t] = l;
+                    dst[j * CONV_THREADS + t] = l;
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (UMMA)
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_conv + 8 * s);
+                if (lane == 0) {
+                    if constexpr (kPair) mbar_arrive_cluster((bar_conv + 8 * s) & PEER_MASK);
+                    else mbar_arrive(bar_conv + 8 * s);
+                }
             }
         }
-        if (prof && t == 0) prof[blockIdx.x * 8 + 4] = c_wait;
+        (void)c_wait;
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ epilogue (8 warps)
         const int ew = warp - 4;                  // 0..7
@@ -317,9 +448,9 @@ batch_scan(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
         const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 64);
         unsigned int *my_cnt = cnt_s + ew * 64 * 2;
         int gcount = 0, lcount = 0;
-        long long e_wait = 0, e_busy = 0;
-        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-            const long long row = a.row0 + (long long)tile * BM + quarter * 32 + lane;    // this thread's clip
+        long long e_wait = 0, e_busy = 0, e_score = 0;
+        for (int tile = unit; tile < a.n_tiles; tile += n_units) {
+            const long long row = a.row0 + (long long)tile * unit_rows + (long long)cta_rank * BM + quarter * 32 + lane;
             const bool row_ok = row < a.n_rows_total;
             for (int st = 0; st < a.n_streams; ++st) {
                 float run[64];
@@ -333,19 +464,22 @@ batch_scan(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                     const long long t1 = VQ_CLOCK();
                     e_wait += t1 - t0;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    uint32_t r0[32], r1[32];
+                    uint32_t r0[32];
                     const uint32_t col = b ? COL_PHI1 : COL_PHI0;
                     tmem_ld32(tlane + col, r0);
-                    tmem_ld32(tlane + col + 32, r1);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) run[j] += __uint_as_float(r0[j]);
+                    tmem_ld32(tlane + col + 32, r0);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_part_empty + 8 * b);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        run[j] += __uint_as_float(r0[j]);
-                        run[32 + j] += __uint_as_float(r1[j]);
+                    if (lane == 0) {
+                        if constexpr (kPair) mbar_arrive_cluster((bar_part_empty + 8 * b) & PEER_MASK);
+                        else mbar_arrive(bar_part_empty + 8 * b);
                     }
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) run[32 + j] += __uint_as_float(r0[j]);
                     e_busy += VQ_CLOCK() - t1;
                 }
                 // small terms of this stream, then this stream's contribution to the score
@@ -355,83 +489,97 @@ batch_scan(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
                     const long long t1 = VQ_CLOCK();
                     e_wait += t1 - t0;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    uint32_t r0[32], r1[32];
-                    tmem_ld32(tlane + COL_PLO, r0);
-                    tmem_ld32(tlane + COL_PLO + 32, r1);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_lo_empty);
-                    ++lcount;
                     const float ic = (inv_counts && row_ok) ? inv_counts[row * a.n_streams + st] : a.inv_splits;
                     const float w = a.w[st];
+                    uint32_t r0[32];
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float d0 = w * (1.0f - (run[j] + __uint_as_float(r0[j])) * ic);
-                        const float d1 = w * (1.0f - (run[32 + j] + __uint_as_float(r1[j])) * ic);
-                        run[j] = d0 * d0;
-                        run[32 + j] = d1 * d1;
-                    }
-                    if (st > 0) {                                    // add the terms of the earlier streams
-                        tmem_ld32(tlane + COL_PARK, r0);
-                        tmem_ld32(tlane + COL_PARK + 32, r1);
+                    for (int h = 0; h < 2; ++h) {                    // two halves of 32 queries: keeps registers low
+                        tmem_ld32(tlane + COL_PLO + 32 * h, r0);
                         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        if (h == 1) {                                // P_lo fully read: the next stream may overwrite it
+                            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                            __syncwarp();
+                            if (lane == 0) {
+                                if constexpr (kPair) mbar_arrive_cluster(bar_lo_empty & PEER_MASK);
+                                else mbar_arrive(bar_lo_empty);
+                            }
+                        }
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            run[j] += __uint_as_float(r0[j]);
-                            run[32 + j] += __uint_as_float(r1[j]);
+                            const float d = w * (1.0f - (run[32 * h + j] + __uint_as_float(r0[j])) * ic);
+                            run[32 * h + j] = d * d;
                         }
-                    }
-                    if (st + 1 < a.n_streams) {                      // park until the next stream is done
+                        if (st > 0) {                                // add the terms of the earlier streams
+                            tmem_ld32(tlane + COL_PARK + 32 * h, r0);
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            r0[j] = __float_as_uint(run[j]);
-                            r1[j] = __float_as_uint(run[32 + j]);
+                            for (int j = 0; j < 32; ++j) run[32 * h + j] += __uint_as_float(r0[j]);
                         }
-                        tmem_st32(tlane + COL_PARK, r0);
-                        tmem_st32(tlane + COL_PARK + 32, r1);
-                        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                        if (st + 1 < a.n_streams) {                  // park until the next stream is done
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) r0[j] = __float_as_uint(run[32 * h + j]);
+                            tmem_st32(tlane + COL_PARK + 32 * h, r0);
+                            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                        }
                     }
+                    ++lcount;
                     e_busy += VQ_CLOCK() - t1;
                 }
                 if (st + 1 < a.n_streams) continue;
-                // ---- scores of this thread's clip against this warp's 64 queries
+                // ---- scores of this thread's clip against this warp's 64 queries.
+                // Phase 1 (branch-free, pipelined): all 64 scores; bit ql of `hot` = this row passes query ql's gate
+                // (gate = min(near-miss limit, current top-k cut)).  Phase 2: one warp-wide OR.  Phase 3: only the
+                // queries some row of this warp is interesting for take the ballot / append path.
                 const long long t1 = VQ_CLOCK();
+                unsigned int hot_lo = 0, hot_hi = 0;
+#pragma unroll
+                for (int ql = 0; ql < 64; ++ql) {
+                    const int q = half * 64 + ql;
+                    const float sc = 1.0f - sqrt_approx(run[ql] * a.inv_den);
+                    run[ql] = sc;
+                    const bool live = row_ok && (q < a.n_queries);
+                    if (scores_dbg && live) scores_dbg[(size_t)q * a.n_rows_total + row] = sc;
+                    const unsigned int bit = (live && sc >= gate_s[q]) ? 1u : 0u;
+                    if (ql < 32) hot_lo |= bit << ql;
+                    else hot_hi |= bit << (ql - 32);
+                }
+                hot_lo = __reduce_or_sync(0xffffffffu, hot_lo);
+                hot_hi = __reduce_or_sync(0xffffffffu, hot_hi);
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
+                    const unsigned int hot = c ? hot_hi : hot_lo;
+                    if (hot == 0) continue;                          // warp-uniform
                     unsigned int cm = 0, cn = 0;
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
-                        const int ql = c * 32 + j;                   // query within this warp's 64
+                        if (!(hot & (1u << j))) continue;            // warp-uniform
+                        const int ql = c * 32 + j;
                         const int q = half * 64 + ql;
-                        const float sc = 1.0f - __fsqrt_rn(run[ql] * a.inv_den);
+                        const float sc = run[ql];
                         const bool live = row_ok && (q < a.n_queries);
-                        if (scores_dbg && live) scores_dbg[(size_t)q * a.n_rows_total + row] = sc;
-                        if (__any_sync(0xffffffffu, live && sc >= gate_s[q])) {
-                            const bool m = live && (sc >= a.th_f);
-                            const bool nm = live && !m && (sc >= a.lo_f);
-                            const bool cand = live && (sc > cut_s[q]);
-                            const unsigned int bm = __ballot_sync(0xffffffffu, m);
-                            const unsigned int bn = __ballot_sync(0xffffffffu, nm);
-                            const unsigned int bc = __ballot_sync(0xffffffffu, cand);
-                            if (lane == j) { cm += __popc(bm); cn += __popc(bn); }
-                            if (bc) {
-                                const int leader = __ffs(bc) - 1;
-                                unsigned int base = 0;
-                                if (lane == leader) base = atomicAdd(&cand_cnt[q], (unsigned int)__popc(bc));
-                                base = __shfl_sync(0xffffffffu, base, leader);
-                                if (cand) {
-                                    const long long slot = (long long)base + __popc(bc & ((1u << lane) - 1u));
-                                    if (slot < a.cand_cap)
-                                        cand_keys[(size_t)q * a.cand_cap + slot] = vq::make_key(sc, (unsigned int)row);
-                                }
+                        const bool m = live && (sc >= a.th_f);
+                        const bool nm = live && !m && (sc >= a.lo_f);
+                        const bool cand = live && (sc > cut_s[q]);
+                        const unsigned int bm = __ballot_sync(0xffffffffu, m);
+                        const unsigned int bn = __ballot_sync(0xffffffffu, nm);
+                        const unsigned int bc = __ballot_sync(0xffffffffu, cand);
+                        if (lane == j) { cm += __popc(bm); cn += __popc(bn); }
+                        if (bc) {
+                            const int leader_lane = __ffs(bc) - 1;
+                            unsigned int base = 0;
+                            if (lane == leader_lane) base = atomicAdd(&cand_cnt[q], (unsigned int)__popc(bc));
+                            base = __shfl_sync(0xffffffffu, base, leader_lane);
+                            if (cand) {
+                                const long long slot = (long long)base + __popc(bc & ((1u << lane) - 1u));
+                                if (slot < a.cand_cap)
+                                    cand_keys[(size_t)q * a.cand_cap + slot] = vq::make_key(sc, (unsigned int)row);
                             }
                         }
                     }
                     my_cnt[(c * 32 + lane) * 2] += cm;               // lane owns query c*32+lane of this warp
                     my_cnt[(c * 32 + lane) * 2 + 1] += cn;
                 }
-                e_busy += VQ_CLOCK() - t1;
+                e_score += VQ_CLOCK() - t1;
             }
         }
         __syncwarp();
@@ -440,13 +588,15 @@ batch_scan(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CU
             if (my_cnt[ql * 2]) atomicAdd(&counts_g[2 * q], (unsigned long long)my_cnt[ql * 2]);
             if (my_cnt[ql * 2 + 1]) atomicAdd(&counts_g[2 * q + 1], (unsigned long long)my_cnt[ql * 2 + 1]);
         }
-        if (prof && threadIdx.x == 128) { prof[blockIdx.x * 8 + 5] = e_wait; prof[blockIdx.x * 8 + 6] = e_busy; }
+        if (prof && threadIdx.x == 128) { prof[blockIdx.x * 8 + 5] = e_wait; prof[blockIdx.x * 8 + 6] = e_busy; prof[blockIdx.x * 8 + 4] = e_score; }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if constexpr (kPair) cluster_sync_all();          // the peer may still be reading / being written
     if (warp == 2) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+        if constexpr (kPair) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
     }
 }
 
@@ -492,7 +642,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int encode_map(CUtensorMap *map, const float *base, uint64_t inner, uint64_t rows, uint32_t box_rows) {
+int encode_map(CUtensorMap *map, const float *base, uint64_t inner, uint64_t rows, uint32_t box_rows,
+               uint32_t box_inner = BK, bool swizzle = true) {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
         void *p = nullptr;
@@ -503,10 +654,11 @@ int encode_map(CUtensorMap *map, const float *base, uint64_t inner, uint64_t row
     }
     const cuuint64_t dims[2] = {inner, rows};
     const cuuint64_t strides[1] = {inner * sizeof(float)};
-    const cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+    const cuuint32_t box[2] = {box_inner, box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     VQ_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d", (int)r);
     return 0;
@@ -542,7 +694,11 @@ int run_batch(vq_store *s, const float *targets, int n_queries, const vq_scan_pa
     const int topk = p->topk;
     const long long chunk_rows = (long long)s->sm_count * BM * 6;
     const long long cap = chunk_rows + VQ_MAX_TOPK;
-    VQ_CUDA(cudaFuncSetAttribute(batch_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BATCH_SMEM));
+    // One CTA per 128-clip tile by default.  VQ_BATCH_PAIR=1 selects the CTA-pair variant (cta_group::2, M = 256):
+    // correct and parity-tested, but measured 25-35 % slower on B200 (profiles/r1_k3_batched_notes.md).
+    const bool pair = getenv("VQ_BATCH_PAIR") && atoi(getenv("VQ_BATCH_PAIR")) == 1 && s->sm_count >= 2;
+    VQ_CUDA(cudaFuncSetAttribute(batch_scan<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<false>::kSmem));
+    VQ_CUDA(cudaFuncSetAttribute(batch_scan<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg<true>::kSmem));
     Dev d_t, d_hi, d_lo, d_cut, d_counts, d_cnt, d_keys, d_rows, d_sc, d_dbg;
     VQ_CUDA(d_t.alloc((size_t)QT * K * 4));
     VQ_CUDA(d_hi.alloc((size_t)QT * K * 4));
@@ -571,11 +727,12 @@ int run_batch(vq_store *s, const float *targets, int n_queries, const vq_scan_pa
         fill_f32<<<1, QT, 0, st>>>(d_cut.as<float>(), -INFINITY, QT);
         VQ_CUDA(cudaMemsetAsync(d_counts.p, 0, QT * 2 * 8, st));
         VQ_CUDA(cudaMemsetAsync(d_cnt.p, 0, QT * 4, st));
-        CUtensorMap map_a, map_bhi, map_blo;
+        CUtensorMap map_a, map_bhi, map_blo, map_apf;
         if (s->n_rows > 0) {
             if ((rc = encode_map(&map_a, s->rows, K, (uint64_t)s->n_rows, BM))) break;
-            if ((rc = encode_map(&map_bhi, d_hi.as<float>(), K, QT, QT))) break;
-            if ((rc = encode_map(&map_blo, d_lo.as<float>(), K, QT, QT))) break;
+            if ((rc = encode_map(&map_apf, s->rows, K, (uint64_t)s->n_rows, BM, PF_KB * BK, false))) break;
+            if ((rc = encode_map(&map_bhi, d_hi.as<float>(), K, QT, pair ? QT / 2 : QT))) break;
+            if ((rc = encode_map(&map_blo, d_lo.as<float>(), K, QT, pair ? QT / 2 : QT))) break;
         }
         BatchArgs a;
         for (int i = 0; i < VQ_MAX_STREAMS; ++i) a.w[i] = (i < s->n_streams) ? (float)p->weights[i] : 0.f;
@@ -592,12 +749,33 @@ int run_batch(vq_store *s, const float *targets, int n_queries, const vq_scan_pa
         for (long long r0 = 0; r0 < s->n_rows; r0 += chunk_rows) {
             const long long nr = (s->n_rows - r0 < chunk_rows) ? (s->n_rows - r0) : chunk_rows;
             a.row0 = r0;
-            a.n_tiles = (int)((nr + BM - 1) / BM);
-            const int grid = a.n_tiles < s->sm_count ? a.n_tiles : s->sm_count;
-            batch_scan<<<grid, BATCH_THREADS, BATCH_SMEM, st>>>(
-                map_a, map_bhi, map_blo, a, s->inv_counts, d_cut.as<float>(), d_counts.as<unsigned long long>(),
-                d_cnt.as<unsigned int>(), d_keys.as<unsigned long long>(),
-                scores_dbg_host ? d_dbg.as<float>() : nullptr, want_prof ? d_prof.as<long long>() : nullptr);
+            const int unit_rows = pair ? 2 * BM : BM;
+            a.n_tiles = (int)((nr + unit_rows - 1) / unit_rows);
+            const int max_units = pair ? s->sm_count / 2 : s->sm_count;
+            const int units = a.n_tiles < max_units ? a.n_tiles : max_units;
+            float *dbg = scores_dbg_host ? d_dbg.as<float>() : nullptr;
+            long long *prof = want_prof ? d_prof.as<long long>() : nullptr;
+            if (pair) {
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(2 * units);
+                cfg.blockDim = dim3(BATCH_THREADS);
+                cfg.dynamicSmemBytes = Cfg<true>::kSmem;
+                cfg.stream = st;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeClusterDimension;
+                attr[0].val.clusterDim.x = 2;
+                attr[0].val.clusterDim.y = 1;
+                attr[0].val.clusterDim.z = 1;
+                cfg.attrs = attr;
+                cfg.numAttrs = 1;
+                VQ_CUDA(cudaLaunchKernelEx(&cfg, batch_scan<true>, map_a, map_bhi, map_blo, map_apf, a, (const float *)s->inv_counts,
+                                           (const float *)d_cut.as<float>(), d_counts.as<unsigned long long>(),
+                                           d_cnt.as<unsigned int>(), d_keys.as<unsigned long long>(), dbg, prof));
+            } else {
+                batch_scan<false><<<units, BATCH_THREADS, Cfg<false>::kSmem, st>>>(
+                    map_a, map_bhi, map_blo, map_apf, a, s->inv_counts, d_cut.as<float>(), d_counts.as<unsigned long long>(),
+                    d_cnt.as<unsigned int>(), d_keys.as<unsigned long long>(), dbg, prof);
+            }
             if (topk > 0)
                 batch_compact<<<QT, 1024, 0, st>>>(d_cnt.as<unsigned int>(), d_keys.as<unsigned long long>(), cap, topk,
                                                    d_cut.as<float>());
@@ -609,9 +787,9 @@ int run_batch(vq_store *s, const float *targets, int n_queries, const vq_scan_pa
             std::vector<long long> h((size_t)s->sm_count * 8);
             VQ_CUDA(cudaMemcpyAsync(h.data(), d_prof.p, h.size() * 8, cudaMemcpyDeviceToHost, st));
             VQ_CUDA(cudaStreamSynchronize(st));
-            static const char *names[7] = {"producer wait empty", "producer total", "mma wait acc_empty", "mma wait data",
-                                           "converter wait full", "epilogue wait acc_full", "epilogue busy"};
-            for (int c = 0; c < 7; ++c) fprintf(stderr, "[K3 prof, last chunk, CTA 0] %-24s %12lld cycles\n", names[c], h[c]);
+            static const char *names[8] = {"mma thread total", "mma wait conv", "mma wait part_empty", "mma wait full",
+                                           "epilogue scoring", "epilogue wait", "epilogue drains+finals", "mma wait lo_empty"};
+            for (int c = 0; c < 8; ++c) fprintf(stderr, "[K3 prof, last chunk, CTA 0] %-24s %12lld cycles\n", names[c], h[c]);
         }
         if (topk > 0)
             batch_output<<<QT, 128, 0, st>>>(d_cnt.as<unsigned int>(), d_keys.as<unsigned long long>(), cap, topk,
