@@ -176,7 +176,7 @@ scan_rows_smem(const float4 *__restrict__ rows, const float4 *__restrict__ targe
     const int lane = threadIdx.x & 31;
     const long long warp0 = (long long)blockIdx.x * (kScanThreads / 32) + (threadIdx.x >> 5);
     const long long n_warps = (long long)gridDim.x * (kScanThreads / 32);
-    constexpr int U = 8;
+    constexpr int U = 8;                               // 8 x 128-bit loads in flight per lane per chunk
     for (long long row = warp0; row < n_rows; row += n_warps) {
         const float4 *p = rows + row * (long long)(S * len4);
         float sim[S];
@@ -185,20 +185,33 @@ scan_rows_smem(const float4 *__restrict__ rows, const float4 *__restrict__ targe
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
             for (int base = 0; base < len4; base += 32 * U) {
                 float4 x[U];
+                if (base + 32 * U <= len4) {                 // full chunk: U unconditional loads back to back
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int j = base + u * 32 + lane;
-                    x[u] = (j < len4) ? ld_stream(p + s * len4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
+                    for (int u = 0; u < U; ++u) x[u] = ld_stream(p + s * len4 + base + u * 32 + lane);
 #pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int j = base + u * 32 + lane;
-                    if (j < len4) {
-                        const float4 tv = tgt_s[s * len4 + j];
+                    for (int u = 0; u < U; ++u) {
+                        const float4 tv = tgt_s[s * len4 + base + u * 32 + lane];
                         a0 = fmaf(x[u].x, tv.x, a0);
                         a1 = fmaf(x[u].y, tv.y, a1);
                         a2 = fmaf(x[u].z, tv.z, a2);
                         a3 = fmaf(x[u].w, tv.w, a3);
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int j = base + u * 32 + lane;
+                        x[u] = (j < len4) ? ld_stream(p + s * len4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int j = base + u * 32 + lane;
+                        if (j < len4) {
+                            const float4 tv = tgt_s[s * len4 + j];
+                            a0 = fmaf(x[u].x, tv.x, a0);
+                            a1 = fmaf(x[u].y, tv.y, a1);
+                            a2 = fmaf(x[u].z, tv.z, a2);
+                            a3 = fmaf(x[u].w, tv.w, a3);
+                        }
                     }
                 }
             }
@@ -511,6 +524,9 @@ void launch_smem(vq_store *s, const float *target_dev, const ScanArgs &a, int gr
     const int len4 = s->stream_len / 4;
     const size_t smem = (size_t)S * len4 * sizeof(float4);
     cudaFuncSetAttribute(scan_rows_smem<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 0;                                    // persistent grid: every resident block slot of every SM
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_rows_smem<S>, kScanThreads, smem) == cudaSuccess && per_sm > 0)
+        grid = s->sm_count * per_sm;
     scan_rows_smem<S><<<grid, kScanThreads, smem, st>>>(
         reinterpret_cast<const float4 *>(s->rows), reinterpret_cast<const float4 *>(target_dev),
         s->inv_counts, a, s->n_rows, len4, s->scores, s->sims, s->hist);
