@@ -6,7 +6,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libvq_b200.so")
+# VQ_B200_LIB: development override (e.g. a build with role cycle counters); the default is the in-tree build
+LIB_PATH = os.environ.get("VQ_B200_LIB") or os.path.join(HERE, "lib", "libvq_b200.so")
 MAX_STREAMS = 4
 MAX_TOPK = 1024
 

@@ -29,11 +29,13 @@
 //                  warp-ballot counts, top-k candidates
 #include <cuda.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <vector>
 
 #include "vq_internal.cuh"
 #include "vq_topk.cuh"
+#include "vq_tc.cuh"
 
 namespace {
 
@@ -56,7 +58,6 @@ constexpr uint32_t A_BYTES = BM * BK * 4;        // 16 KB
 constexpr int BATCH_THREADS = 384;      // 12 warps -> up to 168 registers per thread (the epilogue keeps 64 sums)
 constexpr int CONV_THREADS = 64;        // converter = warps 2-3
 constexpr int PF_KB = 8;                         // K blocks per L2 prefetch box (8 x 128 B = 1 KB per clip row)
-constexpr uint32_t PEER_MASK = 0xFEFFFFFFu;      // clears the CTA-rank bit of a shared::cluster address -> CTA 0 of the pair
 
 // kPair = false: one CTA per tile of 128 clips (cta_group::1).
 // kPair = true : a CTA pair (cluster of 2, cta_group::2) per tile of 256 clips: each CTA stages its own 128
@@ -74,130 +75,7 @@ struct Cfg {
 };
 constexpr uint32_t COL_PHI0 = 0, COL_PHI1 = 128, COL_PLO = 256, COL_PARK = 384;
 
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t a, int c) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(c));
-}
-__device__ __forceinline__ void mbar_expect(uint32_t a, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t a) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
-    asm volatile(
-        "{\n.reg .pred p;\nWAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(a), "r"(parity) : "memory");
-}
-// same, acquiring at cluster scope: for barriers that the peer CTA of a pair arrives on remotely
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t a, uint32_t parity) {
-    asm volatile(
-        "{\n.reg .pred p;\nWAIT_%=:\n"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(a), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t leader_bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
-        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(leader_bar) : "memory");
-}
-__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc),
-        "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"((unsigned short)3) : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap *map, int c0, int c1) {
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-    // K-major, 128-byte swizzle: 8-row atoms of 128 B, atoms 1024 B apart (SBO), LBO unused (1), version 1
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-    d |= (uint64_t)1 << 16;
-    d |= (uint64_t)(1024 >> 4) << 32;
-    d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
-    return d;
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc),
-        "r"(accumulate) : "memory");
-}
-// Lean issue path: the MMA issuer is ONE thread, so every ALU instruction between two tcgen05.mma costs
-// a full dependent-issue latency.  Descriptors are therefore kept as a per-stage 32-bit low word (start
-// address >> 4 | LBO) that only needs "+2" per K step (32 bytes), with a constant high word
-// (SBO = 1024 B, descriptor version 1, SWIZZLE_128B).
-constexpr uint32_t DESC_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
-__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
-template <bool kPair, bool kAcc>
-__device__ __forceinline__ void umma_issue(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
-    if constexpr (kPair) {
-        asm volatile(
-            "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %4, 0;\nmov.b64 da, {%1, %5};\nmov.b64 db, {%2, %5};\n"
-            "tcgen05.mma.cta_group::2.kind::tf32 [%0], da, db, %3, p;\n}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc),
-            "n"(kAcc ? 1 : 0), "r"(DESC_HI) : "memory");
-    } else {
-        asm volatile(
-            "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %4, 0;\nmov.b64 da, {%1, %5};\nmov.b64 db, {%2, %5};\n"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %3, p;\n}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc),
-            "n"(kAcc ? 1 : 0), "r"(DESC_HI) : "memory");
-    }
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
-        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
-        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
-        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
-          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
-          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
-        : "memory");
-}
-
-__device__ __forceinline__ float sqrt_approx(float x) {     // MUFU.SQRT: 1 instruction, <= 2 ulp
-    float y;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
+using namespace vqtc;
 
 struct BatchArgs {
     float w[VQ_MAX_STREAMS];
@@ -208,8 +86,11 @@ struct BatchArgs {
     int n_streams;
     long long row0, n_rows_total;  // chunk start (local rows) and shard size
     int n_tiles;                   // tiles in this chunk
+    int n_mma;                     // bf16 kernel: queries of this pass rounded up to 16 (the UMMA N)
     long long cand_cap;
 };
+
+#include "vq_batch_bf16.cuh"
 
 // hi/lo split of the targets, round to nearest (cvt.rna): hi has a 10-bit mantissa, lo = t - hi exactly
 __global__ void split_targets(const float *__restrict__ t, float *hi, float *lo, long long n) {
@@ -642,8 +523,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int encode_map(CUtensorMap *map, const float *base, uint64_t inner, uint64_t rows, uint32_t box_rows,
-               uint32_t box_inner = BK, bool swizzle = true) {
+int encode_map_ex(CUtensorMap *map, const void *base, CUtensorMapDataType dtype, size_t elem_bytes, uint64_t inner,
+                  uint64_t rows, uint32_t box_rows, uint32_t box_inner, CUtensorMapSwizzle swizzle) {
     static EncodeTiledFn fn = nullptr;
     if (!fn) {
         void *p = nullptr;
@@ -653,15 +534,19 @@ int encode_map(CUtensorMap *map, const float *base, uint64_t inner, uint64_t row
         fn = (EncodeTiledFn)p;
     }
     const cuuint64_t dims[2] = {inner, rows};
-    const cuuint64_t strides[1] = {inner * sizeof(float)};
+    const cuuint64_t strides[1] = {inner * elem_bytes};
     const cuuint32_t box[2] = {box_inner, box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
-                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUresult r = fn(map, dtype, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     VQ_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code %d", (int)r);
     return 0;
+}
+
+int encode_map(CUtensorMap *map, const float *base, uint64_t inner, uint64_t rows, uint32_t box_rows,
+               uint32_t box_inner = BK, bool swizzle = true) {
+    return encode_map_ex(map, base, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, sizeof(float), inner, rows, box_rows, box_inner,
+                         swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
 float float_ceil_of(double x) {
@@ -823,12 +708,144 @@ int run_batch(vq_store *s, const float *targets, int n_queries, const vq_scan_pa
     return rc;
 }
 
+
+// Default batched path: bf16x2 kernel (vq_batch_bf16.cuh), 256 queries per pass over the shard.
+int run_batch_bf16(vq_store *s, const float *targets, int n_queries, const vq_scan_params *p, int64_t *counts_out,
+                   int64_t *topk_rows_out, float *topk_scores_out, float *kernel_ms_out, float *scores_dbg_host) {
+    VQ_REQUIRE(s && targets && p, "vq_scan_batch: null argument");
+    VQ_REQUIRE(n_queries >= 1, "vq_scan_batch: need at least one query");
+    VQ_REQUIRE(s->stream_len % bf::BK == 0, "vq_scan_batch: stream length %d is not a multiple of %d", s->stream_len, bf::BK);
+    VQ_REQUIRE(p->topk >= 0 && p->topk <= VQ_MAX_TOPK, "vq_scan_batch: topk %d outside 0..%d", p->topk, VQ_MAX_TOPK);
+    VQ_REQUIRE(s->n_rows < (1ll << 31), "vq_scan_batch: shard too large for 32-bit TMA coordinates");
+    double den = 0.0;
+    for (int i = 0; i < s->n_streams; ++i) den += p->weights[i] * p->weights[i];
+    VQ_REQUIRE(den > 0.0, "vq_scan_batch: all stream weights are zero");
+    VQ_CUDA(cudaSetDevice(s->device));
+    cudaStream_t st = s->stream;
+    constexpr int QN = bf::QN;
+    const size_t K = s->row_floats;                       // floats per row = S * stream_len
+    const int topk = p->topk;
+    // chunk schedule: a short first launch (1 tile per CTA) seeds the per-query top-k cuts, so that only the first
+    // 19k clips are all candidates; then 8 tiles per CTA per launch
+    const long long first_rows = (long long)s->sm_count * bf::BM;
+    const long long chunk_rows = (long long)s->sm_count * bf::BM * 8;
+    const long long cap = chunk_rows + VQ_MAX_TOPK;
+    VQ_CUDA(cudaFuncSetAttribute(bf::batch_scan_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf::SMEM));
+    Dev d_t, d_t1, d_t2, d_cut, d_counts, d_cnt, d_keys, d_rows, d_sc, d_dbg, d_park, d_prof;
+    VQ_CUDA(d_t.alloc((size_t)QN * K * 4));
+    VQ_CUDA(d_t1.alloc((size_t)QN * K * 2));
+    VQ_CUDA(d_t2.alloc((size_t)QN * K * 2));
+    VQ_CUDA(d_cut.alloc(QN * 4));
+    VQ_CUDA(d_counts.alloc(QN * 2 * 8));
+    VQ_CUDA(d_cnt.alloc(QN * 4));
+    VQ_CUDA(d_keys.alloc((size_t)QN * cap * 8));
+    VQ_CUDA(d_rows.alloc((size_t)QN * (topk ? topk : 1) * 8));
+    VQ_CUDA(d_sc.alloc((size_t)QN * (topk ? topk : 1) * 4));
+    VQ_CUDA(d_park.alloc((size_t)s->sm_count * bf::PARK_FLOATS_PER_CTA * 4));
+    if (scores_dbg_host) VQ_CUDA(d_dbg.alloc((size_t)QN * s->n_rows * 4));
+    const bool want_prof = getenv("VQ_BATCH_PROF") != nullptr;
+    if (want_prof) VQ_CUDA(d_prof.alloc((size_t)s->sm_count * 8 * 8));
+    cudaEvent_t e0, e1;
+    VQ_CUDA(cudaEventCreate(&e0));
+    VQ_CUDA(cudaEventCreate(&e1));
+    float total_ms = 0.f;
+    int rc = 0;
+    for (int q0 = 0; q0 < n_queries && rc == 0; q0 += QN) {
+        const int nq = (n_queries - q0 < QN) ? (n_queries - q0) : QN;
+        VQ_CUDA(cudaMemsetAsync(d_t.p, 0, (size_t)QN * K * 4, st));
+        VQ_CUDA(cudaMemcpyAsync(d_t.p, targets + (size_t)q0 * K, (size_t)nq * K * 4, cudaMemcpyHostToDevice, st));
+        bf::split_targets_bf16<<<(unsigned)(((size_t)QN * K + 255) / 256), 256, 0, st>>>(
+            d_t.as<float>(), d_t1.as<unsigned short>(), d_t2.as<unsigned short>(), (long long)QN * K);
+        fill_f32<<<1, QN, 0, st>>>(d_cut.as<float>(), topk > 0 ? -INFINITY : INFINITY, QN);   // no top-k: nothing is a candidate
+        VQ_CUDA(cudaMemsetAsync(d_counts.p, 0, QN * 2 * 8, st));
+        VQ_CUDA(cudaMemsetAsync(d_cnt.p, 0, QN * 4, st));
+        CUtensorMap map_a, map_t1, map_t2;
+        if (s->n_rows > 0) {
+            if ((rc = encode_map(&map_a, s->rows, K, (uint64_t)s->n_rows, bf::BM))) break;
+            if ((rc = encode_map_ex(&map_t1, d_t1.p, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, QN, QN, bf::BK, CU_TENSOR_MAP_SWIZZLE_64B))) break;
+            if ((rc = encode_map_ex(&map_t2, d_t2.p, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, QN, QN, bf::BK, CU_TENSOR_MAP_SWIZZLE_64B))) break;
+        }
+        BatchArgs a;
+        for (int i = 0; i < VQ_MAX_STREAMS; ++i) a.w[i] = (i < s->n_streams) ? (float)p->weights[i] : 0.f;
+        a.inv_den = (float)(1.0 / den);
+        a.inv_splits = (float)(1.0 / (double)s->n_splits);
+        a.th_f = float_ceil_of(p->threshold);
+        a.lo_f = float_ceil_of(p->lower_limit);
+        a.n_queries = nq;
+        a.n_mma = ((nq + 15) / 16) * 16;
+        a.kb_per_stream = s->stream_len / bf::BK;
+        a.n_streams = s->n_streams;
+        a.n_rows_total = s->n_rows;
+        a.cand_cap = cap;
+        VQ_CUDA(cudaEventRecord(e0, st));
+        for (long long r0 = 0, step = first_rows; r0 < s->n_rows; r0 += step, step = chunk_rows) {
+            const long long nr = (s->n_rows - r0 < step) ? (s->n_rows - r0) : step;
+            a.row0 = r0;
+            a.n_tiles = (int)((nr + bf::BM - 1) / bf::BM);
+            const int units = a.n_tiles < s->sm_count ? a.n_tiles : s->sm_count;
+            bf::batch_scan_bf16<<<units, bf::THREADS, bf::SMEM, st>>>(
+                map_a, map_t1, map_t2, a, s->inv_counts, d_cut.as<float>(), d_counts.as<unsigned long long>(),
+                d_cnt.as<unsigned int>(), d_keys.as<unsigned long long>(), d_park.as<float>(),
+                scores_dbg_host ? d_dbg.as<float>() : nullptr, want_prof ? d_prof.as<long long>() : nullptr);
+            if (topk > 0)
+                batch_compact<<<QN, 1024, 0, st>>>(d_cnt.as<unsigned int>(), d_keys.as<unsigned long long>(), cap, topk,
+                                                   d_cut.as<float>());
+            else
+                VQ_CUDA(cudaMemsetAsync(d_cnt.p, 0, QN * 4, st));
+        }
+        VQ_CUDA(cudaEventRecord(e1, st));
+        if (want_prof) {
+            std::vector<long long> h((size_t)s->sm_count * 8);
+            VQ_CUDA(cudaMemcpyAsync(h.data(), d_prof.p, h.size() * 8, cudaMemcpyDeviceToHost, st));
+            VQ_CUDA(cudaStreamSynchronize(st));
+            static const char *names[8] = {"mma thread total", "mma wait conv", "mma wait part_empty", "mma wait full",
+                                           "epilogue scoring", "epilogue wait", "epilogue drains+finals", "converter wait full"};
+            for (int c = 0; c < 8; ++c) fprintf(stderr, "[K3 bf16 prof, last chunk, CTA 0] %-24s %12lld cycles\n", names[c], h[c]);
+        }
+        if (topk > 0)
+            batch_output<<<QN, 128, 0, st>>>(d_cnt.as<unsigned int>(), d_keys.as<unsigned long long>(), cap, topk,
+                                             s->first_global_row, d_rows.as<long long>(), d_sc.as<float>());
+        VQ_CUDA(cudaGetLastError());
+        if (counts_out) {
+            std::vector<unsigned long long> h(QN * 2);
+            VQ_CUDA(cudaMemcpyAsync(h.data(), d_counts.p, QN * 2 * 8, cudaMemcpyDeviceToHost, st));
+            VQ_CUDA(cudaStreamSynchronize(st));
+            for (int q = 0; q < nq; ++q) {
+                counts_out[2 * (q0 + q)] = (int64_t)h[2 * q];
+                counts_out[2 * (q0 + q) + 1] = (int64_t)h[2 * q + 1];
+            }
+        }
+        if (topk > 0 && topk_rows_out)
+            VQ_CUDA(cudaMemcpyAsync(topk_rows_out + (size_t)q0 * topk, d_rows.p, (size_t)nq * topk * 8,
+                                    cudaMemcpyDeviceToHost, st));
+        if (topk > 0 && topk_scores_out)
+            VQ_CUDA(cudaMemcpyAsync(topk_scores_out + (size_t)q0 * topk, d_sc.p, (size_t)nq * topk * 4,
+                                    cudaMemcpyDeviceToHost, st));
+        if (scores_dbg_host)
+            VQ_CUDA(cudaMemcpyAsync(scores_dbg_host + (size_t)q0 * s->n_rows, d_dbg.p, (size_t)nq * s->n_rows * 4,
+                                    cudaMemcpyDeviceToHost, st));
+        VQ_CUDA(cudaStreamSynchronize(st));
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) total_ms += ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (kernel_ms_out) *kernel_ms_out = total_ms;
+    return rc;
+}
+
+bool use_tf32_path() {
+    const char *e = getenv("VQ_BATCH_IMPL");
+    return e && strcmp(e, "tf32") == 0;
+}
+
 }  // namespace
 
 extern "C" int vq_scan_batch(vq_store *s, const float *targets, int32_t n_queries, const vq_scan_params *p,
                              int64_t *counts_out, int64_t *topk_rows_out, float *topk_scores_out,
                              float *kernel_ms_out) {
-    return run_batch(s, targets, n_queries, p, counts_out, topk_rows_out, topk_scores_out, kernel_ms_out, nullptr);
+    if (use_tf32_path()) return run_batch(s, targets, n_queries, p, counts_out, topk_rows_out, topk_scores_out, kernel_ms_out, nullptr);
+    return run_batch_bf16(s, targets, n_queries, p, counts_out, topk_rows_out, topk_scores_out, kernel_ms_out, nullptr);
 }
 
 extern "C" int vq_scan_batch_scores(vq_store *s, const float *targets, int32_t n_queries, const vq_scan_params *p,
@@ -837,5 +854,6 @@ extern "C" int vq_scan_batch_scores(vq_store *s, const float *targets, int32_t n
     VQ_REQUIRE(s && (long long)s->n_rows * 256 <= (1ll << 28), "vq_scan_batch_scores: debug dump limited to 1M rows x 256 queries");
     vq_scan_params q = *p;
     q.topk = 0;
-    return run_batch(s, targets, n_queries, &q, nullptr, nullptr, nullptr, nullptr, scores_out);
+    if (use_tf32_path()) return run_batch(s, targets, n_queries, &q, nullptr, nullptr, nullptr, nullptr, scores_out);
+    return run_batch_bf16(s, targets, n_queries, &q, nullptr, nullptr, nullptr, nullptr, scores_out);
 }

@@ -1,0 +1,471 @@
+// K3 (v4) — batched queries on tcgen05 with a two-term bf16 split ("bf16x2"), sm_100a.
+//
+// Included by vq_batch.cu inside its anonymous namespace.  Same contract as the 3xTF32 kernel it
+// replaces as the default (reference ticket.py:146-180, 325-327 for Q tickets at once), different
+// arithmetic and tiling:
+//
+//   x = x1 + x2 (+ r_x),  t = t1 + t2 (+ r_t)      x1 = bf16_rn(x), x2 = bf16_rn(x - x1), same for t
+//   x*t ~= x1*t1 + x2*t1 + x1*t2                   |dropped terms| <= 3 * 2^-18 |x*t|, signs random
+//
+// Three kind::f16 MMAs (M128 N256 K16, bf16 in, fp32 accumulate) per 16 dims instead of six
+// kind::tf32 MMAs (M128 N128 K8) per 16 dims and 128 queries: half the tensor-pipe cycles per
+// (clip, query), operands half as wide in shared memory, and all 256 queries of a pass share ONE
+// read + conversion of the clip tile (the 3xTF32 kernel streams the shard once per 128 queries).
+//
+// TMEM (512 columns) holds exactly two partial accumulators of 256 columns: the MMA warp fills one
+// while the epilogue drains the other into 128 running sums per thread (two-level accumulation: the
+// tensor core truncates on every accumulate, so a partial takes at most GROUP_KB * 6 = 24 MMAs).
+// The stream-0 term (w0 (1 - sim0))^2 is parked in an L2-resident scratch (128 KB per CTA, coalesced)
+// until stream 1 is done — neither TMEM nor registers have room for it.
+//
+// Warp roles (384 threads, 1 CTA per SM, persistent over 128-clip tiles); warpgroup 0 gives registers
+// to the epilogue warpgroups with setmaxnreg:
+//     warp 0       TMA producer: fp32 clip tile (128B swizzle) + t1, t2 query tiles (bf16, 64B swizzle)
+//     warp 1       MMA issuer (one elected lane)
+//     warps 2-3    converter: fp32 tile -> x1, x2 bf16 tiles in the 64B-swizzled K-major layout
+//     warps 4-11   epilogue
+#pragma once
+
+namespace bf {
+
+constexpr int BM = 128;                  // clips per tile (UMMA M)
+constexpr int QN = 256;                  // queries per pass (max UMMA N)
+constexpr int BK = 32;                   // dims per K block: 128 B of fp32, 64 B of bf16
+constexpr int UK = 16;                   // UMMA K for bf16
+#ifndef VQ_BF_GROUP_KB
+#define VQ_BF_GROUP_KB 4
+#endif
+constexpr int GROUP_KB = VQ_BF_GROUP_KB; // K blocks per partial accumulator
+constexpr int STAGES = 3;
+constexpr uint32_t A32_BYTES = BM * BK * 4;      // 16 KB
+constexpr uint32_t X_BYTES = BM * BK * 2;        //  8 KB
+constexpr uint32_t T_BYTES = QN * BK * 2;        // 16 KB
+constexpr uint32_t OFF_X1 = A32_BYTES, OFF_X2 = OFF_X1 + X_BYTES, OFF_T1 = OFF_X2 + X_BYTES, OFF_T2 = OFF_T1 + T_BYTES;
+constexpr uint32_t STAGE_BYTES = OFF_T2 + T_BYTES;   // 64 KB
+constexpr int THREADS = 384;
+constexpr int CONV_WARPS = 2;
+constexpr int EPI_WARPS = 8;
+constexpr int N_BARS = 3 * STAGES + 4;
+constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers + tmem slot*/ +
+                        QN * 4 /*cut*/ + EPI_WARPS * 128 * 2 * 4 /*per-warp counts*/;
+constexpr size_t PARK_FLOATS_PER_CTA = (size_t)QN * BM;
+// shared-memory descriptor high word: SBO = 512 B (8 rows of 64 B), descriptor version 1, SWIZZLE_64B
+constexpr uint32_t DESC_HI64 = (512u >> 4) | (1u << 14) | (4u << 29);
+
+template <bool kAcc>
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
+    asm volatile(
+        "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %4, 0;\nmov.b64 da, {%1, %5};\nmov.b64 db, {%2, %5};\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc),
+        "n"(kAcc ? 1 : 0), "r"(DESC_HI64) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float hi, float lo) {     // {bf16_rn(hi), bf16_rn(lo)}: lo in bits 0-15
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+// 8 floats -> 8 bf16 leading parts (p) and 8 bf16 residual parts (q); x - float(x1) is exact in fp32
+__device__ __forceinline__ void split8(const float4 &u, const float4 &v, uint4 &p, uint4 &q) {
+#define VQ_SPLIT2(f0, f1, P, Q)                                                                  \
+    {                                                                                            \
+        P = pack_bf16x2(f1, f0);                                                                 \
+        const float h0 = __uint_as_float(P << 16), h1 = __uint_as_float(P & 0xFFFF0000u);        \
+        Q = pack_bf16x2(f1 - h1, f0 - h0);                                                       \
+    }
+    VQ_SPLIT2(u.x, u.y, p.x, q.x)
+    VQ_SPLIT2(u.z, u.w, p.y, q.y)
+    VQ_SPLIT2(v.x, v.y, p.z, q.z)
+    VQ_SPLIT2(v.z, v.w, p.w, q.w)
+#undef VQ_SPLIT2
+}
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4 &v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// 32 x 32 bit-matrix transpose across a warp: lane r holds row r (bit c = column c) -> lane c holds column c
+// (bit r = row r).  Five block-swap steps; used to turn "my row passes query j" masks into per-query counts.
+__device__ __forceinline__ unsigned int transpose32(unsigned int x, int lane) {
+    unsigned int m = 0x0000FFFFu;
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        const unsigned int y = __shfl_xor_sync(0xffffffffu, x, j);
+        x = (lane & j) ? ((x & ~m) | ((y >> j) & m)) : ((x & m) | ((y << j) & ~m));
+        m ^= m << (j >> 1);
+    }
+    return x;
+}
+
+// End of a stream for one epilogue thread (one clip row, 128 queries): term = (w (1 - sim))^2, plus the terms of
+// the earlier streams from the park; the last stream leaves the sum in `run`, the others park it.
+template <bool kFirst, bool kLast>
+__device__ __forceinline__ void stream_final(float (&run)[128], float *park, float w, float ic, int nch) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        if (c < nch) {
+            float old[32];
+            if constexpr (!kFirst) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) old[j] = __ldcg(park + (size_t)(32 * c + j) * BM);
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float dd = w * (1.0f - run[32 * c + j] * ic);
+                float v = dd * dd;
+                if constexpr (!kFirst) v += old[j];
+                if constexpr (kLast) run[32 * c + j] = v;
+                else __stcg(park + (size_t)(32 * c + j) * BM, v);
+            }
+        }
+    }
+}
+
+// run[base + j] for a warp-uniform runtime j in 0..31 without local memory: 31 selects
+__device__ __forceinline__ float select32(const float (&run)[128], int base, int j) {
+    float v16[16], v8[8], v4[4], v2[2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v16[i] = (j & 16) ? run[base + 16 + i] : run[base + i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v8[i] = (j & 8) ? v16[8 + i] : v16[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v4[i] = (j & 4) ? v8[4 + i] : v8[i];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) v2[i] = (j & 2) ? v4[2 + i] : v4[i];
+    return (j & 1) ? v2[1] : v2[0];
+}
+
+// targets fp32 [n] -> t1, t2 bf16 (round to nearest both times)
+__global__ void split_targets_bf16(const float *__restrict__ t, unsigned short *t1, unsigned short *t2, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = t[i];
+    const uint32_t p = pack_bf16x2(0.f, x);
+    const float h = __uint_as_float(p << 16);
+    const uint32_t q = pack_bf16x2(0.f, x - h);
+    t1[i] = (unsigned short)(p & 0xFFFFu);
+    t2[i] = (unsigned short)(q & 0xFFFFu);
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_t1,
+                const __grid_constant__ CUtensorMap map_t2, const BatchArgs a, const float *__restrict__ inv_counts,
+                const float *__restrict__ cut_g, unsigned long long *counts_g /*[QN][2]*/, unsigned int *cand_cnt /*[QN]*/,
+                unsigned long long *cand_keys /*[QN][cap]*/, float *park_g /*[grid][QN][BM]*/,
+                float *scores_dbg /*[Q][n_rows] or null*/, long long *prof /*[grid][8] or null*/) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES * STAGE_BYTES);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + N_BARS);
+    float *cut_s = reinterpret_cast<float *>(smem + (size_t)STAGES * STAGE_BYTES + 256);
+    unsigned int *cnt_s = reinterpret_cast<unsigned int *>(cut_s + QN);      // [8 warps][128 queries][2]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t bar_full = smem_u32(&bars[0]), bar_conv = smem_u32(&bars[STAGES]), bar_empty = smem_u32(&bars[2 * STAGES]),
+                   bar_part_full = smem_u32(&bars[3 * STAGES]), bar_part_empty = smem_u32(&bars[3 * STAGES + 2]);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);            // producer's expect_tx arrive + TMA bytes
+            mbar_init(bar_conv + 8 * s, CONV_WARPS);   // one arrive per converter warp
+            mbar_init(bar_empty + 8 * s, 1);           // tcgen05.commit
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_part_full + 8 * b, 1);           // tcgen05.commit
+            mbar_init(bar_part_empty + 8 * b, EPI_WARPS);  // one arrive per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < QN; i += blockDim.x) {
+        cut_s[i] = cut_g[i];
+    }
+    for (int i = threadIdx.x; i < EPI_WARPS * 128 * 2; i += blockDim.x) cnt_s[i] = 0;
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const int kbps = a.kb_per_stream;
+    const int kb_total = kbps * a.n_streams;
+    const int n_mma = a.n_mma;                      // queries rounded up to 16: the N of every MMA
+
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+        if (warp == 0) {
+            // ------------------------------------------------------------------ TMA producer
+            if (lane == 0) {
+                int it = 0;
+                for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+                    const int row = (int)(a.row0 + (long long)tile * BM);
+                    for (int kb = 0; kb < kb_total; ++kb, ++it) {
+                        const int s = it % STAGES;
+                        const uint32_t ph = (it / STAGES) & 1;
+                        mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                        const uint32_t base = smem_u32(smem + (size_t)s * STAGE_BYTES);
+                        mbar_expect(bar_full + 8 * s, A32_BYTES + 2 * T_BYTES);
+                        tma_load_2d(base, &map_a, kb * BK, row, bar_full + 8 * s);
+                        tma_load_2d(base + OFF_T1, &map_t1, kb * BK, 0, bar_full + 8 * s);
+                        tma_load_2d(base + OFF_T2, &map_t2, kb * BK, 0, bar_full + 8 * s);
+                    }
+                }
+            }
+        } else if (warp == 1) {
+            // ------------------------------------------------------------------ MMA issuer
+            uint32_t elected;
+            asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(elected));
+            // instruction descriptor: D = f32, A = B = bf16, both K-major, N = n_mma, M = 128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            int it = 0, gcount = 0;
+            long long w_acc = 0, w_data = 0, w_conv = 0;
+            const long long m_t0 = VQ_CLOCK();
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+                for (int st = 0; st < a.n_streams; ++st) {
+                    uint32_t d = 0;
+                    for (int kb = 0; kb < kbps; ++kb, ++it) {
+                        const bool group_first = (kb % GROUP_KB) == 0;
+                        const bool group_last = (kb % GROUP_KB) == GROUP_KB - 1 || kb == kbps - 1;
+                        long long t0 = VQ_CLOCK();
+                        if (group_first) {
+                            const int b = gcount & 1;
+                            mbar_wait(bar_part_empty + 8 * b, ((gcount >> 1) & 1) ^ 1);       // partial drained
+                            d = tmem_base + (uint32_t)(b * QN);
+                        }
+                        long long t1 = VQ_CLOCK();
+                        w_acc += t1 - t0;
+                        const int s = it % STAGES;
+                        const uint32_t ph = (it / STAGES) & 1;
+                        mbar_wait(bar_full + 8 * s, ph);
+                        t0 = VQ_CLOCK();
+                        w_data += t0 - t1;
+                        mbar_wait(bar_conv + 8 * s, ph);
+                        w_conv += VQ_CLOCK() - t0;
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t base = smem_u32(smem + (size_t)s * STAGE_BYTES);
+                        if (elected) {
+                            const uint32_t x1 = desc_lo(base + OFF_X1), x2 = desc_lo(base + OFF_X2), t1d = desc_lo(base + OFF_T1),
+                                           t2d = desc_lo(base + OFF_T2);
+                            if (group_first) umma_bf16<false>(d, x1, t1d, idesc);
+                            else umma_bf16<true>(d, x1, t1d, idesc);
+                            umma_bf16<true>(d, x2, t1d, idesc);
+                            umma_bf16<true>(d, x1, t2d, idesc);
+#pragma unroll
+                            for (int k = 1; k < BK / UK; ++k) {                  // +32 B per K step inside the 64 B row
+                                umma_bf16<true>(d, x1 + 2 * k, t1d + 2 * k, idesc);
+                                umma_bf16<true>(d, x2 + 2 * k, t1d + 2 * k, idesc);
+                                umma_bf16<true>(d, x1 + 2 * k, t2d + 2 * k, idesc);
+                            }
+                            umma_commit(bar_empty + 8 * s);                       // stage reusable once these MMAs retire
+                            if (group_last) umma_commit(bar_part_full + 8 * (gcount & 1));
+                        }
+                        __syncwarp();
+                        if (group_last) ++gcount;
+                    }
+                }
+            }
+            if (prof && elected) {
+                prof[blockIdx.x * 8 + 0] = VQ_CLOCK() - m_t0; prof[blockIdx.x * 8 + 1] = w_conv;
+                prof[blockIdx.x * 8 + 2] = w_acc; prof[blockIdx.x * 8 + 3] = w_data;
+            }
+        } else {
+            // ------------------------------------------------------------------ converter (warps 2-3)
+            // Work item = (row r, 8 consecutive dims c8): two 16 B chunks of the fp32 row -> one 16 B chunk of x1 and of x2.
+            // 8 consecutive threads take rows (2p, 2p+1) x c8 = 0..3, which makes every quarter-warp phase of the
+            // 128-bit loads and stores hit 8 distinct 16 B bank groups under both swizzles.
+            const int t = threadIdx.x - 64;                              // 0..63
+            const int rsub = (t >> 3) * 2 + ((t & 7) >> 2);              // 0..15
+            const int c8 = t & 3;
+            const uint32_t src_off0 = (uint32_t)rsub * 128u + (uint32_t)(((2 * c8) ^ (rsub & 7)) * 16);
+            const uint32_t src_off1 = (uint32_t)rsub * 128u + (uint32_t)(((2 * c8 + 1) ^ (rsub & 7)) * 16);
+            const uint32_t dst_off = (uint32_t)rsub * 64u + (uint32_t)((c8 ^ ((rsub >> 1) & 3)) * 16);
+            int it = 0;
+            long long c_wait = 0;
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+                for (int kb = 0; kb < kb_total; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    const long long t0 = VQ_CLOCK();
+                    mbar_wait(bar_full + 8 * s, ph);
+                    c_wait += VQ_CLOCK() - t0;
+                    const uint32_t sbase = smem_base + (uint32_t)s * STAGE_BYTES;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {                      // two batches of 4 items: 8 loads in flight
+                        float4 u[4], v[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            u[j] = lds128(sbase + src_off0 + (uint32_t)((h * 4 + j) * 16 * 128));
+                            v[j] = lds128(sbase + src_off1 + (uint32_t)((h * 4 + j) * 16 * 128));
+                        }
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            uint4 p, q;
+                            split8(u[j], v[j], p, q);
+                            sts128(sbase + OFF_X1 + dst_off + (uint32_t)((h * 4 + j) * 16 * 64), p);
+                            sts128(sbase + OFF_X2 + dst_off + (uint32_t)((h * 4 + j) * 16 * 64), q);
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (UMMA)
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_conv + 8 * s);
+                }
+            }
+            if (prof && t == 0) prof[blockIdx.x * 8 + 7] = c_wait;
+        }
+    } else {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+        // ------------------------------------------------------------------ epilogue (8 warps)
+        const int ew = warp - 4;                  // 0..7
+        const int quarter = warp & 3;             // TMEM lanes 32*quarter .. +31 (hardware rule: warp id % 4)
+        const int half = ew >> 2;                 // which 128 of the 256 queries this warp handles
+        const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 128);
+        // 32-query chunks of this warp's half that hold live MMA columns (warp-uniform)
+        const int nch = max(0, min(4, (n_mma - half * 128 + 31) / 32));
+        unsigned int *my_cnt = cnt_s + ew * 128 * 2;
+        float *park = park_g + (size_t)blockIdx.x * PARK_FLOATS_PER_CTA + (size_t)(half * 128) * BM + quarter * 32 + lane;
+        int gcount = 0;
+        long long e_wait = 0, e_busy = 0, e_score = 0;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            const long long row = a.row0 + (long long)tile * BM + quarter * 32 + lane;
+            const bool row_ok = row < a.n_rows_total;
+            for (int st = 0; st < a.n_streams; ++st) {
+                float run[128];
+#pragma unroll
+                for (int j = 0; j < 128; ++j) run[j] = 0.f;
+                const int n_groups = (kbps + GROUP_KB - 1) / GROUP_KB;
+                for (int g = 0; g < n_groups; ++g, ++gcount) {
+                    const int b = gcount & 1;
+                    const long long t0 = VQ_CLOCK();
+                    mbar_wait(bar_part_full + 8 * b, (gcount >> 1) & 1);
+                    const long long t1 = VQ_CLOCK();
+                    e_wait += t1 - t0;
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t col = tlane + (uint32_t)(b * QN);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t r0[32];
+                        if (c < nch) {
+                            tmem_ld32(col + 32 * c, r0);
+                            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        }
+                        if (c == 3) {                                    // partial fully read: the MMA warp may refill it
+                            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(bar_part_empty + 8 * b);
+                        }
+                        if (c < nch) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) run[32 * c + j] += __uint_as_float(r0[j]);
+                        }
+                    }
+                    e_busy += VQ_CLOCK() - t1;
+                }
+                // this stream's contribution (w (1 - sim))^2; earlier streams' terms come back from the park
+                {
+                    const long long t1 = VQ_CLOCK();
+                    const float ic = (inv_counts && row_ok) ? inv_counts[row * a.n_streams + st] : a.inv_splits;
+                    const float w = st == 0 ? a.w[0] : (st == 1 ? a.w[1] : (st == 2 ? a.w[2] : a.w[3]));   // no dynamic indexing: keeps `a` in the constant bank
+                    const bool first = st == 0, last = st + 1 == a.n_streams;
+                    if (first) {
+                        if (last) stream_final<true, true>(run, park, w, ic, nch);
+                        else stream_final<true, false>(run, park, w, ic, nch);
+                    } else {
+                        if (last) stream_final<false, true>(run, park, w, ic, nch);
+                        else stream_final<false, false>(run, park, w, ic, nch);
+                    }
+                    e_busy += VQ_CLOCK() - t1;
+                }
+                if (st + 1 < a.n_streams) continue;
+                // ---- scores of this thread's clip against this warp's 128 queries.
+                // Phase 1 (branch-free): all scores; per 32-query chunk three bit masks of this row: score >= threshold,
+                // >= near-miss limit, > current top-k cut.  Phase 2: per-query counts by transposing the masks across
+                // the warp (lane j ends up with the 32 rows' bits of query j).  Phase 3: candidate appends, only for
+                // the (rare, after the first chunk) queries some row of this warp beats the cut of.
+                const long long t1 = VQ_CLOCK();
+                unsigned int m_th[4], m_nm[4], m_cd[4];
+                const unsigned int rowmask = row_ok ? 0xffffffffu : 0u;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    m_th[c] = m_nm[c] = m_cd[c] = 0u;
+                    if (c < nch) {
+                        unsigned int bt = 0, bl = 0, bc = 0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int ql = 32 * c + j;
+                            const float sc = 1.0f - sqrt_approx(run[ql] * a.inv_den);
+                            run[ql] = sc;
+                            bt |= (sc >= a.th_f ? 1u : 0u) << j;
+                            bl |= (sc >= a.lo_f ? 1u : 0u) << j;
+                            bc |= (sc > cut_s[half * 128 + ql] ? 1u : 0u) << j;
+                        }
+                        const int nlive = a.n_queries - (half * 128 + 32 * c);          // live queries of this chunk
+                        const unsigned int lm = rowmask & (nlive >= 32 ? 0xffffffffu : (nlive <= 0 ? 0u : ((1u << nlive) - 1u)));
+                        m_th[c] = bt & lm;
+                        m_nm[c] = bl & ~bt & lm;
+                        m_cd[c] = bc & lm;
+                    }
+                }
+                if (scores_dbg && row_ok) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (c < nch) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) {
+                                const int q = half * 128 + 32 * c + j;
+                                if (q < a.n_queries) scores_dbg[(size_t)q * a.n_rows_total + row] = run[32 * c + j];
+                            }
+                        }
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (c < nch) {                                   // lane owns query c*32+lane of this warp's half
+                        my_cnt[(c * 32 + lane) * 2] += __popc(transpose32(m_th[c], lane));
+                        my_cnt[(c * 32 + lane) * 2 + 1] += __popc(transpose32(m_nm[c], lane));
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    unsigned int h = __reduce_or_sync(0xffffffffu, m_cd[c]);
+                    // rare after the seeding chunk: a real loop over the hot queries (compact code, the score comes out
+                    // of the register file through a select tree on the warp-uniform index)
+                    while (h) {
+                        const int j = __ffs(h) - 1;
+                        h &= h - 1;
+                        const float sc = select32(run, 32 * c, j);
+                        const int q = half * 128 + c * 32 + j;
+                        const bool cand = (m_cd[c] >> j) & 1u;
+                        const unsigned int bc = __ballot_sync(0xffffffffu, cand);
+                        const int leader_lane = __ffs(bc) - 1;
+                        unsigned int base = 0;
+                        if (lane == leader_lane) base = atomicAdd(&cand_cnt[q], (unsigned int)__popc(bc));
+                        base = __shfl_sync(0xffffffffu, base, leader_lane);
+                        if (cand) {
+                            const long long slot = (long long)base + __popc(bc & ((1u << lane) - 1u));
+                            if (slot < a.cand_cap) cand_keys[(size_t)q * a.cand_cap + slot] = vq::make_key(sc, (unsigned int)row);
+                        }
+                    }
+                }
+                e_score += VQ_CLOCK() - t1;
+            }
+        }
+        __syncwarp();
+        for (int ql = lane; ql < 128; ql += 32) {
+            const int q = half * 128 + ql;
+            if (my_cnt[ql * 2]) atomicAdd(&counts_g[2 * q], (unsigned long long)my_cnt[ql * 2]);
+            if (my_cnt[ql * 2 + 1]) atomicAdd(&counts_g[2 * q + 1], (unsigned long long)my_cnt[ql * 2 + 1]);
+        }
+        if (prof && threadIdx.x == 128) { prof[blockIdx.x * 8 + 5] = e_wait; prof[blockIdx.x * 8 + 6] = e_busy; prof[blockIdx.x * 8 + 4] = e_score; }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+    }
+}
+
+}  // namespace bf
