@@ -85,6 +85,7 @@ struct BatchArgs {
     int kb_per_stream;             // stream_len / 32
     int n_streams;
     long long row0, n_rows_total;  // chunk start (local rows) and shard size
+    long long row_end;             // bf16 kernel: first row past this launch's chunk
     int n_tiles;                   // tiles in this chunk
     int n_mma;                     // bf16 kernel: queries of this pass rounded up to 16 (the UMMA N)
     long long cand_cap;
@@ -730,7 +731,13 @@ int run_batch_bf16(vq_store *s, const float *targets, int n_queries, const vq_sc
     const long long first_rows = (long long)s->sm_count * bf::BM;
     const long long chunk_rows = (long long)s->sm_count * bf::BM * 8;
     const long long cap = chunk_rows + VQ_MAX_TOPK;
-    VQ_CUDA(cudaFuncSetAttribute(bf::batch_scan_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf::SMEM));
+    // CTAs per cluster sharing the query tiles by TMA multicast (VQ_BATCH_CLUSTER = 1, 2 or 4; default 2)
+    int kc = getenv("VQ_BATCH_CLUSTER") ? atoi(getenv("VQ_BATCH_CLUSTER")) : 2;
+    if (kc != 1 && kc != 2 && kc != 4) kc = 2;
+    if (s->sm_count < kc) kc = 1;
+    VQ_CUDA(cudaFuncSetAttribute(bf::batch_scan_bf16<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf::SMEM));
+    VQ_CUDA(cudaFuncSetAttribute(bf::batch_scan_bf16<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf::SMEM));
+    VQ_CUDA(cudaFuncSetAttribute(bf::batch_scan_bf16<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf::SMEM));
     Dev d_t, d_t1, d_t2, d_cut, d_counts, d_cnt, d_keys, d_rows, d_sc, d_dbg, d_park, d_prof;
     VQ_CUDA(d_t.alloc((size_t)QN * K * 4));
     VQ_CUDA(d_t1.alloc((size_t)QN * K * 2));
@@ -744,7 +751,7 @@ int run_batch_bf16(vq_store *s, const float *targets, int n_queries, const vq_sc
     VQ_CUDA(d_park.alloc((size_t)s->sm_count * bf::PARK_FLOATS_PER_CTA * 4));
     if (scores_dbg_host) VQ_CUDA(d_dbg.alloc((size_t)QN * s->n_rows * 4));
     const bool want_prof = getenv("VQ_BATCH_PROF") != nullptr;
-    if (want_prof) VQ_CUDA(d_prof.alloc((size_t)s->sm_count * 8 * 8));
+    if (want_prof) VQ_CUDA(d_prof.alloc((size_t)s->sm_count * 16 * 8));
     cudaEvent_t e0, e1;
     VQ_CUDA(cudaEventCreate(&e0));
     VQ_CUDA(cudaEventCreate(&e1));
@@ -762,8 +769,8 @@ int run_batch_bf16(vq_store *s, const float *targets, int n_queries, const vq_sc
         CUtensorMap map_a, map_t1, map_t2;
         if (s->n_rows > 0) {
             if ((rc = encode_map(&map_a, s->rows, K, (uint64_t)s->n_rows, bf::BM))) break;
-            if ((rc = encode_map_ex(&map_t1, d_t1.p, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, QN, QN, bf::BK, CU_TENSOR_MAP_SWIZZLE_64B))) break;
-            if ((rc = encode_map_ex(&map_t2, d_t2.p, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, QN, QN, bf::BK, CU_TENSOR_MAP_SWIZZLE_64B))) break;
+            if ((rc = encode_map_ex(&map_t1, d_t1.p, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, QN, QN / kc, bf::BK, CU_TENSOR_MAP_SWIZZLE_64B))) break;
+            if ((rc = encode_map_ex(&map_t2, d_t2.p, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, QN, QN / kc, bf::BK, CU_TENSOR_MAP_SWIZZLE_64B))) break;
         }
         BatchArgs a;
         for (int i = 0; i < VQ_MAX_STREAMS; ++i) a.w[i] = (i < s->n_streams) ? (float)p->weights[i] : 0.f;
@@ -782,11 +789,28 @@ int run_batch_bf16(vq_store *s, const float *targets, int n_queries, const vq_sc
             const long long nr = (s->n_rows - r0 < step) ? (s->n_rows - r0) : step;
             a.row0 = r0;
             a.n_tiles = (int)((nr + bf::BM - 1) / bf::BM);
-            const int units = a.n_tiles < s->sm_count ? a.n_tiles : s->sm_count;
-            bf::batch_scan_bf16<<<units, bf::THREADS, bf::SMEM, st>>>(
-                map_a, map_t1, map_t2, a, s->inv_counts, d_cut.as<float>(), d_counts.as<unsigned long long>(),
-                d_cnt.as<unsigned int>(), d_keys.as<unsigned long long>(), d_park.as<float>(),
-                scores_dbg_host ? d_dbg.as<float>() : nullptr, want_prof ? d_prof.as<long long>() : nullptr);
+            a.row_end = r0 + nr;
+            const int n_unit_tiles = (a.n_tiles + kc - 1) / kc;
+            const int max_units = s->sm_count / kc;
+            const int units = n_unit_tiles < max_units ? n_unit_tiles : max_units;
+            float *dbg = scores_dbg_host ? d_dbg.as<float>() : nullptr;
+            long long *prof = want_prof ? d_prof.as<long long>() : nullptr;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(units * kc);
+            cfg.blockDim = dim3(bf::THREADS);
+            cfg.dynamicSmemBytes = bf::SMEM;
+            cfg.stream = st;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = kc;
+            attr[0].val.clusterDim.y = 1;
+            attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
+            auto kern = kc == 1 ? bf::batch_scan_bf16<1> : (kc == 2 ? bf::batch_scan_bf16<2> : bf::batch_scan_bf16<4>);
+            VQ_CUDA(cudaLaunchKernelEx(&cfg, kern, map_a, map_t1, map_t2, a, (const float *)s->inv_counts,
+                                       (const float *)d_cut.as<float>(), d_counts.as<unsigned long long>(),
+                                       d_cnt.as<unsigned int>(), d_keys.as<unsigned long long>(), d_park.as<float>(), dbg, prof));
             if (topk > 0)
                 batch_compact<<<QN, 1024, 0, st>>>(d_cnt.as<unsigned int>(), d_keys.as<unsigned long long>(), cap, topk,
                                                    d_cut.as<float>());
@@ -795,12 +819,13 @@ int run_batch_bf16(vq_store *s, const float *targets, int n_queries, const vq_sc
         }
         VQ_CUDA(cudaEventRecord(e1, st));
         if (want_prof) {
-            std::vector<long long> h((size_t)s->sm_count * 8);
+            std::vector<long long> h((size_t)s->sm_count * 16);
             VQ_CUDA(cudaMemcpyAsync(h.data(), d_prof.p, h.size() * 8, cudaMemcpyDeviceToHost, st));
             VQ_CUDA(cudaStreamSynchronize(st));
-            static const char *names[8] = {"mma thread total", "mma wait conv", "mma wait part_empty", "mma wait full",
-                                           "epilogue scoring", "epilogue wait", "epilogue drains+finals", "converter wait full"};
-            for (int c = 0; c < 8; ++c) fprintf(stderr, "[K3 bf16 prof, last chunk, CTA 0] %-24s %12lld cycles\n", names[c], h[c]);
+            static const char *names[12] = {"mma thread total", "mma wait x_full", "mma wait part_empty", "mma wait t_full",
+                                            "converter wait xt_empty", "epilogue wait part_full", "epilogue drains", "converter wait a_full",
+                                            "epilogue finals (park st)", "epilogue finals (park ld)", "epilogue scoring", "tiles"};
+            for (int c = 0; c < 12; ++c) fprintf(stderr, "[K3 bf16 prof, last chunk, CTA 0] %-28s %12lld\n", names[c], h[c]);
         }
         if (topk > 0)
             batch_output<<<QN, 128, 0, st>>>(d_cnt.as<unsigned int>(), d_keys.as<unsigned long long>(), cap, topk,

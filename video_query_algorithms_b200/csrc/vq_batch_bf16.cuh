@@ -36,18 +36,21 @@ constexpr int UK = 16;                   // UMMA K for bf16
 #define VQ_BF_GROUP_KB 4
 #endif
 constexpr int GROUP_KB = VQ_BF_GROUP_KB; // K blocks per partial accumulator
-constexpr int STAGES = 3;
+constexpr int NA = 4;                            // fp32 clip-tile ring, released by the converters as soon as they have read it
+constexpr int NX = 3;                            // operand ring (x1, x2 from the converters; t1, t2 by TMA), released by the MMA commits
 constexpr uint32_t A32_BYTES = BM * BK * 4;      // 16 KB
 constexpr uint32_t X_BYTES = BM * BK * 2;        //  8 KB
 constexpr uint32_t T_BYTES = QN * BK * 2;        // 16 KB
-constexpr uint32_t OFF_X1 = A32_BYTES, OFF_X2 = OFF_X1 + X_BYTES, OFF_T1 = OFF_X2 + X_BYTES, OFF_T2 = OFF_T1 + T_BYTES;
-constexpr uint32_t STAGE_BYTES = OFF_T2 + T_BYTES;   // 64 KB
-constexpr int THREADS = 384;
-constexpr int CONV_WARPS = 2;
+constexpr uint32_t OFF_X1 = 0, OFF_X2 = X_BYTES, OFF_T1 = 2 * X_BYTES, OFF_T2 = OFF_T1 + T_BYTES;   // inside an operand stage
+constexpr uint32_t XT_BYTES = OFF_T2 + T_BYTES;  // 48 KB
+constexpr uint32_t RING_XT = NA * A32_BYTES;     // operand ring starts after the fp32 ring
+constexpr uint32_t RING_END = RING_XT + NX * XT_BYTES;   // 208 KB
+constexpr int THREADS = 512;
+constexpr int CONV_WARPS = 4;
 constexpr int EPI_WARPS = 8;
-constexpr int N_BARS = 3 * STAGES + 4;
-constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers + tmem slot*/ +
-                        QN * 4 /*cut*/ + EPI_WARPS * 128 * 2 * 4 /*per-warp counts*/;
+constexpr int N_BARS = 2 * NA + 3 * NX + 4;
+constexpr size_t SMEM = (size_t)RING_END + 1024 /*align*/ + 256 /*barriers + tmem slot*/ + QN * 4 /*cut*/ +
+                        EPI_WARPS * 128 * 2 * 4 /*per-warp counts*/;
 constexpr size_t PARK_FLOATS_PER_CTA = (size_t)QN * BM;
 // shared-memory descriptor high word: SBO = 512 B (8 rows of 64 B), descriptor version 1, SWIZZLE_64B
 constexpr uint32_t DESC_HI64 = (512u >> 4) | (1u << 14) | (4u << 29);
@@ -58,6 +61,15 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint32_t a_lo, uint32
         "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %4, 0;\nmov.b64 da, {%1, %5};\nmov.b64 db, {%2, %5};\n"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc),
         "n"(kAcc ? 1 : 0), "r"(DESC_HI64) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar, uint32_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar), "h"((unsigned short)cta_mask) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint32_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((unsigned short)cta_mask) : "memory");
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float hi, float lo) {     // {bf16_rn(hi), bf16_rn(lo)}: lo in bits 0-15
     uint32_t d;
@@ -150,6 +162,11 @@ __global__ void split_targets_bf16(const float *__restrict__ t, unsigned short *
     t2[i] = (unsigned short)(q & 0xFFFFu);
 }
 
+// kC = CTAs per cluster.  kC > 1: the CTAs of a cluster walk their tiles in lockstep and share the query tiles:
+// each CTA fetches 1/kC of the rows of t1 / t2 and TMA-multicasts them into every CTA of the cluster, which
+// divides the L2 -> SM traffic for the (re-streamed, L2-resident) query operand by kC.  A stage of the operand
+// ring is reused only after the MMA warps of ALL CTAs of the cluster have committed it (multicast commit).
+template <int kC>
 __global__ void __launch_bounds__(THREADS, 1)
 batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_t1,
                 const __grid_constant__ CUtensorMap map_t2, const BatchArgs a, const float *__restrict__ inv_counts,
@@ -158,20 +175,25 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 float *scores_dbg /*[Q][n_rows] or null*/, long long *prof /*[grid][8] or null*/) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)STAGES * STAGE_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + RING_END);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + N_BARS);
-    float *cut_s = reinterpret_cast<float *>(smem + (size_t)STAGES * STAGE_BYTES + 256);
+    float *cut_s = reinterpret_cast<float *>(smem + RING_END + 256);
     unsigned int *cnt_s = reinterpret_cast<unsigned int *>(cut_s + QN);      // [8 warps][128 queries][2]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = smem_u32(smem);
-    const uint32_t bar_full = smem_u32(&bars[0]), bar_conv = smem_u32(&bars[STAGES]), bar_empty = smem_u32(&bars[2 * STAGES]),
-                   bar_part_full = smem_u32(&bars[3 * STAGES]), bar_part_empty = smem_u32(&bars[3 * STAGES + 2]);
+    const uint32_t bar_afull = smem_u32(&bars[0]), bar_aempty = smem_u32(&bars[NA]), bar_tfull = smem_u32(&bars[2 * NA]),
+                   bar_xfull = smem_u32(&bars[2 * NA + NX]), bar_xtempty = smem_u32(&bars[2 * NA + 2 * NX]),
+                   bar_part_full = smem_u32(&bars[2 * NA + 3 * NX]), bar_part_empty = smem_u32(&bars[2 * NA + 3 * NX + 2]);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(bar_full + 8 * s, 1);            // producer's expect_tx arrive + TMA bytes
-            mbar_init(bar_conv + 8 * s, CONV_WARPS);   // one arrive per converter warp
-            mbar_init(bar_empty + 8 * s, 1);           // tcgen05.commit
+        for (int s = 0; s < NA; ++s) {
+            mbar_init(bar_afull + 8 * s, 1);            // producer's expect_tx arrive + TMA bytes of the fp32 tile
+            mbar_init(bar_aempty + 8 * s, CONV_WARPS);  // one arrive per converter warp
+        }
+        for (int s = 0; s < NX; ++s) {
+            mbar_init(bar_tfull + 8 * s, 1);            // expect_tx arrive + TMA bytes of t1, t2
+            mbar_init(bar_xfull + 8 * s, CONV_WARPS);   // x1, x2 written
+            mbar_init(bar_xtempty + 8 * s, kC);         // tcgen05.commit of every CTA of the cluster
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(bar_part_full + 8 * b, 1);           // tcgen05.commit
@@ -179,9 +201,7 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < QN; i += blockDim.x) {
-        cut_s[i] = cut_g[i];
-    }
+    for (int i = threadIdx.x; i < QN; i += blockDim.x) cut_s[i] = cut_g[i];
     for (int i = threadIdx.x; i < EPI_WARPS * 128 * 2; i += blockDim.x) cnt_s[i] = 0;
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_slot)));
@@ -189,29 +209,51 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if constexpr (kC > 1) cluster_sync_all();         // peer barriers are initialised before any remote signal
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    // work unit = kC consecutive tiles, one per CTA of the cluster; every CTA of a cluster runs the same number of
+    // units (rows past the end of the shard are zero-filled by TMA and masked in the epilogue)
+    const int cta_rank = kC > 1 ? (int)cluster_ctarank() : 0;
+    const int unit0 = (int)blockIdx.x / kC, n_units = (int)gridDim.x / kC;
     const int kbps = a.kb_per_stream;
     const int kb_total = kbps * a.n_streams;
     const int n_mma = a.n_mma;                      // queries rounded up to 16: the N of every MMA
 
-    if (warp < 4) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+    if (warp < 8) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         if (warp == 0) {
-            // ------------------------------------------------------------------ TMA producer
+            // ------------------------------------------------------------------ TMA producer, clip tiles (fp32)
             if (lane == 0) {
                 int it = 0;
-                for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-                    const int row = (int)(a.row0 + (long long)tile * BM);
+                for (int unit = unit0; unit * kC < a.n_tiles; unit += n_units) {
+                    const int row = (int)(a.row0 + (long long)(unit * kC + cta_rank) * BM);
                     for (int kb = 0; kb < kb_total; ++kb, ++it) {
-                        const int s = it % STAGES;
-                        const uint32_t ph = (it / STAGES) & 1;
-                        mbar_wait(bar_empty + 8 * s, ph ^ 1);
-                        const uint32_t base = smem_u32(smem + (size_t)s * STAGE_BYTES);
-                        mbar_expect(bar_full + 8 * s, A32_BYTES + 2 * T_BYTES);
-                        tma_load_2d(base, &map_a, kb * BK, row, bar_full + 8 * s);
-                        tma_load_2d(base + OFF_T1, &map_t1, kb * BK, 0, bar_full + 8 * s);
-                        tma_load_2d(base + OFF_T2, &map_t2, kb * BK, 0, bar_full + 8 * s);
+                        const int s = it % NA;
+                        mbar_wait(bar_aempty + 8 * s, ((it / NA) & 1) ^ 1);
+                        mbar_expect(bar_afull + 8 * s, A32_BYTES);
+                        tma_load_2d(smem_base + (uint32_t)s * A32_BYTES, &map_a, kb * BK, row, bar_afull + 8 * s);
+                    }
+                }
+            }
+        } else if (warp == 2) {
+            // ------------------------------------------------------------------ TMA producer, query tiles (t1, t2)
+            if (lane == 0) {
+                int it = 0;
+                for (int unit = unit0; unit * kC < a.n_tiles; unit += n_units) {
+                    for (int kb = 0; kb < kb_total; ++kb, ++it) {
+                        const int s = it % NX;
+                        mbar_wait(bar_xtempty + 8 * s, ((it / NX) & 1) ^ 1);
+                        const uint32_t base = smem_base + RING_XT + (uint32_t)s * XT_BYTES;
+                        mbar_expect(bar_tfull + 8 * s, 2 * T_BYTES);     // bytes of all kC slices land here
+                        if constexpr (kC > 1) {
+                            constexpr uint32_t SLICE = T_BYTES / kC;      // this CTA's rows of the tile, sent to every CTA
+                            tma_load_2d_mc(base + OFF_T1 + cta_rank * SLICE, &map_t1, kb * BK, cta_rank * (QN / kC), bar_tfull + 8 * s, (1u << kC) - 1u);
+                            tma_load_2d_mc(base + OFF_T2 + cta_rank * SLICE, &map_t2, kb * BK, cta_rank * (QN / kC), bar_tfull + 8 * s, (1u << kC) - 1u);
+                        } else {
+                            tma_load_2d(base + OFF_T1, &map_t1, kb * BK, 0, bar_tfull + 8 * s);
+                            tma_load_2d(base + OFF_T2, &map_t2, kb * BK, 0, bar_tfull + 8 * s);
+                        }
                     }
                 }
             }
@@ -224,7 +266,7 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             int it = 0, gcount = 0;
             long long w_acc = 0, w_data = 0, w_conv = 0;
             const long long m_t0 = VQ_CLOCK();
-            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            for (int unit = unit0; unit * kC < a.n_tiles; unit += n_units) {
                 for (int st = 0; st < a.n_streams; ++st) {
                     uint32_t d = 0;
                     for (int kb = 0; kb < kbps; ++kb, ++it) {
@@ -238,15 +280,15 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         }
                         long long t1 = VQ_CLOCK();
                         w_acc += t1 - t0;
-                        const int s = it % STAGES;
-                        const uint32_t ph = (it / STAGES) & 1;
-                        mbar_wait(bar_full + 8 * s, ph);
+                        const int s = it % NX;
+                        const uint32_t ph = (it / NX) & 1;
+                        mbar_wait(bar_tfull + 8 * s, ph);
                         t0 = VQ_CLOCK();
                         w_data += t0 - t1;
-                        mbar_wait(bar_conv + 8 * s, ph);
+                        mbar_wait(bar_xfull + 8 * s, ph);
                         w_conv += VQ_CLOCK() - t0;
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t base = smem_u32(smem + (size_t)s * STAGE_BYTES);
+                        const uint32_t base = smem_base + RING_XT + (uint32_t)s * XT_BYTES;
                         if (elected) {
                             const uint32_t x1 = desc_lo(base + OFF_X1), x2 = desc_lo(base + OFF_X2), t1d = desc_lo(base + OFF_T1),
                                            t2d = desc_lo(base + OFF_T2);
@@ -260,7 +302,8 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                                 umma_bf16<true>(d, x2 + 2 * k, t1d + 2 * k, idesc);
                                 umma_bf16<true>(d, x1 + 2 * k, t2d + 2 * k, idesc);
                             }
-                            umma_commit(bar_empty + 8 * s);                       // stage reusable once these MMAs retire
+                            if constexpr (kC > 1) umma_commit_mc(bar_xtempty + 8 * s, (1u << kC) - 1u);   // ... in every CTA of the cluster
+                            else umma_commit(bar_xtempty + 8 * s);                // stage reusable once these MMAs retire
                             if (group_last) umma_commit(bar_part_full + 8 * (gcount & 1));
                         }
                         __syncwarp();
@@ -269,57 +312,60 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 }
             }
             if (prof && elected) {
-                prof[blockIdx.x * 8 + 0] = VQ_CLOCK() - m_t0; prof[blockIdx.x * 8 + 1] = w_conv;
-                prof[blockIdx.x * 8 + 2] = w_acc; prof[blockIdx.x * 8 + 3] = w_data;
+                prof[blockIdx.x * 16 + 0] = VQ_CLOCK() - m_t0; prof[blockIdx.x * 16 + 1] = w_conv;
+                prof[blockIdx.x * 16 + 2] = w_acc; prof[blockIdx.x * 16 + 3] = w_data;
             }
-        } else {
-            // ------------------------------------------------------------------ converter (warps 2-3)
+        } else if (warp >= 4) {
+            // ------------------------------------------------------------------ converter (warps 4-7, one per SM sub-partition)
             // Work item = (row r, 8 consecutive dims c8): two 16 B chunks of the fp32 row -> one 16 B chunk of x1 and of x2.
             // 8 consecutive threads take rows (2p, 2p+1) x c8 = 0..3, which makes every quarter-warp phase of the
             // 128-bit loads and stores hit 8 distinct 16 B bank groups under both swizzles.
-            const int t = threadIdx.x - 64;                              // 0..63
-            const int rsub = (t >> 3) * 2 + ((t & 7) >> 2);              // 0..15
+            const int t = threadIdx.x - 128;                             // 0..127
+            const int rsub = (t >> 3) * 2 + ((t & 7) >> 2);              // 0..31
             const int c8 = t & 3;
             const uint32_t src_off0 = (uint32_t)rsub * 128u + (uint32_t)(((2 * c8) ^ (rsub & 7)) * 16);
             const uint32_t src_off1 = (uint32_t)rsub * 128u + (uint32_t)(((2 * c8 + 1) ^ (rsub & 7)) * 16);
             const uint32_t dst_off = (uint32_t)rsub * 64u + (uint32_t)((c8 ^ ((rsub >> 1) & 3)) * 16);
             int it = 0;
-            long long c_wait = 0;
-            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            long long c_wait = 0, c_wait2 = 0;
+            for (int unit = unit0; unit * kC < a.n_tiles; unit += n_units) {
                 for (int kb = 0; kb < kb_total; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
-                    const long long t0 = VQ_CLOCK();
-                    mbar_wait(bar_full + 8 * s, ph);
-                    c_wait += VQ_CLOCK() - t0;
-                    const uint32_t sbase = smem_base + (uint32_t)s * STAGE_BYTES;
+                    const int sa = it % NA, sx = it % NX;
+                    long long t0 = VQ_CLOCK();
+                    mbar_wait(bar_afull + 8 * sa, (it / NA) & 1);
+                    long long t1 = VQ_CLOCK();
+                    c_wait += t1 - t0;
+                    mbar_wait(bar_xtempty + 8 * sx, ((it / NX) & 1) ^ 1);
+                    c_wait2 += VQ_CLOCK() - t1;
+                    const uint32_t src = smem_base + (uint32_t)sa * A32_BYTES;
+                    const uint32_t dst = smem_base + RING_XT + (uint32_t)sx * XT_BYTES + dst_off;
+                    float4 u[4], v[4];
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {                      // two batches of 4 items: 8 loads in flight
-                        float4 u[4], v[4];
+                    for (int j = 0; j < 4; ++j) {                        // 4 items per thread, 8 loads in flight
+                        u[j] = lds128(src + src_off0 + (uint32_t)(j * 32 * 128));
+                        v[j] = lds128(src + src_off1 + (uint32_t)(j * 32 * 128));
+                    }
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            u[j] = lds128(sbase + src_off0 + (uint32_t)((h * 4 + j) * 16 * 128));
-                            v[j] = lds128(sbase + src_off1 + (uint32_t)((h * 4 + j) * 16 * 128));
-                        }
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            uint4 p, q;
-                            split8(u[j], v[j], p, q);
-                            sts128(sbase + OFF_X1 + dst_off + (uint32_t)((h * 4 + j) * 16 * 64), p);
-                            sts128(sbase + OFF_X2 + dst_off + (uint32_t)((h * 4 + j) * 16 * 64), q);
-                        }
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 p, q;
+                        split8(u[j], v[j], p, q);
+                        sts128(dst + OFF_X1 + (uint32_t)(j * 32 * 64), p);
+                        sts128(dst + OFF_X2 + (uint32_t)(j * 32 * 64), q);
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (UMMA)
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_conv + 8 * s);
+                    if (lane == 0) {
+                        mbar_arrive(bar_xfull + 8 * sx);
+                        mbar_arrive(bar_aempty + 8 * sa);
+                    }
                 }
             }
-            if (prof && t == 0) prof[blockIdx.x * 8 + 7] = c_wait;
+            if (prof && t == 0) { prof[blockIdx.x * 16 + 7] = c_wait; prof[blockIdx.x * 16 + 4] = c_wait2; }
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
         // ------------------------------------------------------------------ epilogue (8 warps)
-        const int ew = warp - 4;                  // 0..7
+        const int ew = warp - 8;                  // 0..7
         const int quarter = warp & 3;             // TMEM lanes 32*quarter .. +31 (hardware rule: warp id % 4)
         const int half = ew >> 2;                 // which 128 of the 256 queries this warp handles
         const uint32_t tlane = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(half * 128);
@@ -328,10 +374,10 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         unsigned int *my_cnt = cnt_s + ew * 128 * 2;
         float *park = park_g + (size_t)blockIdx.x * PARK_FLOATS_PER_CTA + (size_t)(half * 128) * BM + quarter * 32 + lane;
         int gcount = 0;
-        long long e_wait = 0, e_busy = 0, e_score = 0;
-        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-            const long long row = a.row0 + (long long)tile * BM + quarter * 32 + lane;
-            const bool row_ok = row < a.n_rows_total;
+        long long e_wait = 0, e_busy = 0, e_score = 0, e_fin0 = 0, e_fin1 = 0, e_tiles = 0;
+        for (int unit = unit0; unit * kC < a.n_tiles; unit += n_units) {
+            const long long row = a.row0 + (long long)(unit * kC + cta_rank) * BM + quarter * 32 + lane;
+            const bool row_ok = row < a.row_end;
             for (int st = 0; st < a.n_streams; ++st) {
                 float run[128];
 #pragma unroll
@@ -377,9 +423,11 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         if (last) stream_final<false, true>(run, park, w, ic, nch);
                         else stream_final<false, false>(run, park, w, ic, nch);
                     }
-                    e_busy += VQ_CLOCK() - t1;
+                    if (last) e_fin1 += VQ_CLOCK() - t1;
+                    else e_fin0 += VQ_CLOCK() - t1;
                 }
                 if (st + 1 < a.n_streams) continue;
+                ++e_tiles;
                 // ---- scores of this thread's clip against this warp's 128 queries.
                 // Phase 1 (branch-free): all scores; per 32-query chunk three bit masks of this row: score >= threshold,
                 // >= near-miss limit, > current top-k cut.  Phase 2: per-query counts by transposing the masks across
@@ -458,10 +506,14 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             if (my_cnt[ql * 2]) atomicAdd(&counts_g[2 * q], (unsigned long long)my_cnt[ql * 2]);
             if (my_cnt[ql * 2 + 1]) atomicAdd(&counts_g[2 * q + 1], (unsigned long long)my_cnt[ql * 2 + 1]);
         }
-        if (prof && threadIdx.x == 128) { prof[blockIdx.x * 8 + 5] = e_wait; prof[blockIdx.x * 8 + 6] = e_busy; prof[blockIdx.x * 8 + 4] = e_score; }
+        if (prof && threadIdx.x == 256) {
+            prof[blockIdx.x * 16 + 5] = e_wait; prof[blockIdx.x * 16 + 6] = e_busy; prof[blockIdx.x * 16 + 8] = e_fin0;
+            prof[blockIdx.x * 16 + 9] = e_fin1; prof[blockIdx.x * 16 + 10] = e_score; prof[blockIdx.x * 16 + 11] = e_tiles;
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if constexpr (kC > 1) cluster_sync_all();         // no CTA leaves while a peer may still write into it or signal it
     if (warp == 2) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
