@@ -1,29 +1,31 @@
-// K3 (v4) — batched queries on tcgen05 with a two-term bf16 split ("bf16x2"), sm_100a.
+// K3 — batched queries on tcgen05 with a two-term bf16 split ("bf16x2"), sm_100a: the kernel.
+// Included by vq_batch.cu inside its anonymous namespace (reference ticket.py:146-180, 325-327 for Q tickets at once).
 //
-// Included by vq_batch.cu inside its anonymous namespace.  Same contract as the 3xTF32 kernel it
-// replaces as the default (reference ticket.py:146-180, 325-327 for Q tickets at once), different
-// arithmetic and tiling:
+// Arithmetic.  fp32 operands are split into two bf16 terms, round to nearest both times:
+//     x = x1 + x2 (+ r_x),  t = t1 + t2 (+ r_t)       x1 = bf16(x), x2 = bf16(x - x1), same for t
+//     x*t ~= x1*t1 + x2*t1 + x1*t2                    |dropped| <= 3 * 2^-18 |x*t| per product, signs random
+// i.e. three kind::f16 MMAs (M128 N256 K16, bf16 in, fp32 accumulate) per 16 dims.  Measured against float64
+// (profiles/): score error mean -5.3e-7, max 1.0e-6 — the same as the 3xTF32 kernel of v1-v3 at half its tensor-pipe
+// cycles and half its operand bytes.  The tensor core truncates on every accumulate into TMEM, so accumulation is
+// two-level: a partial accumulator takes GROUP_KB * 6 = 24 MMAs, then the epilogue drains it into fp32 running
+// sums in registers (round-to-nearest adds).
 //
-//   x = x1 + x2 (+ r_x),  t = t1 + t2 (+ r_t)      x1 = bf16_rn(x), x2 = bf16_rn(x - x1), same for t
-//   x*t ~= x1*t1 + x2*t1 + x1*t2                   |dropped terms| <= 3 * 2^-18 |x*t|, signs random
+// Tiling.  One CTA per SM, persistent over 128-clip tiles; all 256 queries of a pass share ONE read and ONE
+// conversion of the clip tile.  Per K block of 32 dims:
+//     TMA  -> fp32 clip tile [128 x 32] (128B swizzle, ring of 3)         -> converter warps -> x1, x2 bf16 tiles
+//     TMA  -> t1, t2 bf16 query tiles [256 x 32] (64B swizzle, ring of 3)    [128 x 32] (64B swizzle, ring of 4)
+//     6 x tcgen05.mma into the partial accumulator
+// TMEM (512 columns): columns 0-255 the partial accumulator, columns 256-511 the "park": the earlier streams'
+// terms (w_s (1 - sim_s))^2 of every (clip, query) wait there until the last stream is done — registers hold
+// the 128 running sums per thread and have no room for them.
 //
-// Three kind::f16 MMAs (M128 N256 K16, bf16 in, fp32 accumulate) per 16 dims instead of six
-// kind::tf32 MMAs (M128 N128 K8) per 16 dims and 128 queries: half the tensor-pipe cycles per
-// (clip, query), operands half as wide in shared memory, and all 256 queries of a pass share ONE
-// read + conversion of the clip tile (the 3xTF32 kernel streams the shard once per 128 queries).
-//
-// TMEM (512 columns) holds exactly two partial accumulators of 256 columns: the MMA warp fills one
-// while the epilogue drains the other into 128 running sums per thread (two-level accumulation: the
-// tensor core truncates on every accumulate, so a partial takes at most GROUP_KB * 6 = 24 MMAs).
-// The stream-0 term (w0 (1 - sim0))^2 is parked in an L2-resident scratch (128 KB per CTA, coalesced)
-// until stream 1 is done — neither TMEM nor registers have room for it.
-//
-// Warp roles (384 threads, 1 CTA per SM, persistent over 128-clip tiles); warpgroup 0 gives registers
-// to the epilogue warpgroups with setmaxnreg:
-//     warp 0       TMA producer: fp32 clip tile (128B swizzle) + t1, t2 query tiles (bf16, 64B swizzle)
-//     warp 1       MMA issuer (one elected lane)
-//     warps 2-3    converter: fp32 tile -> x1, x2 bf16 tiles in the 64B-swizzled K-major layout
-//     warps 4-11   epilogue
+// Warps (512 threads; setmaxnreg moves registers from warpgroups 0-1 to the epilogue warpgroups 2-3):
+//     warp 0       TMA producer, clip tiles            warp 2       TMEM allocation, TMA producer for t1 / t2
+//     warp 1       MMA issuer (one elected lane)       warp 3       idle
+//     warps 4-7    converters, one per SM sub-partition; the loads of K block i+1 are issued before block i is
+//                  converted and stored
+//     warps 8-15   epilogue: drains, running sums, scores, per-query counts (bit-mask transpose), top-k candidates
+// Development history and the measurements behind these choices: profiles/r1_k3_batched_notes.md.
 #pragma once
 
 namespace bf {
@@ -36,22 +38,21 @@ constexpr int UK = 16;                   // UMMA K for bf16
 #define VQ_BF_GROUP_KB 4
 #endif
 constexpr int GROUP_KB = VQ_BF_GROUP_KB; // K blocks per partial accumulator
-constexpr int NA = 4;                            // fp32 clip-tile ring, released by the converters as soon as they have read it
-constexpr int NX = 3;                            // operand ring (x1, x2 from the converters; t1, t2 by TMA), released by the MMA commits
+constexpr int NA = 3;                            // fp32 clip-tile ring: TMA -> converters (released as soon as they have read it)
+constexpr int NXR = 4;                           // x1 / x2 ring: converters -> MMA (released by the MMA commits)
+constexpr int NT = 3;                            // t1 / t2 ring: TMA -> MMA (released by the MMA commits)
 constexpr uint32_t A32_BYTES = BM * BK * 4;      // 16 KB
 constexpr uint32_t X_BYTES = BM * BK * 2;        //  8 KB
 constexpr uint32_t T_BYTES = QN * BK * 2;        // 16 KB
-constexpr uint32_t OFF_X1 = 0, OFF_X2 = X_BYTES, OFF_T1 = 2 * X_BYTES, OFF_T2 = OFF_T1 + T_BYTES;   // inside an operand stage
-constexpr uint32_t XT_BYTES = OFF_T2 + T_BYTES;  // 48 KB
-constexpr uint32_t RING_XT = NA * A32_BYTES;     // operand ring starts after the fp32 ring
-constexpr uint32_t RING_END = RING_XT + NX * XT_BYTES;   // 208 KB
+constexpr uint32_t RING_X = NA * A32_BYTES;                  // x1 at +0, x2 at +X_BYTES of a stage
+constexpr uint32_t RING_T = RING_X + NXR * 2 * X_BYTES;      // t1 at +0, t2 at +T_BYTES of a stage
+constexpr uint32_t RING_END = RING_T + NT * 2 * T_BYTES;     // 48 + 64 + 96 = 208 KB
 constexpr int THREADS = 512;
 constexpr int CONV_WARPS = 4;
 constexpr int EPI_WARPS = 8;
-constexpr int N_BARS = 2 * NA + 3 * NX + 4;
+constexpr int N_BARS = 2 * NA + 2 * NXR + 2 * NT + 2;
 constexpr size_t SMEM = (size_t)RING_END + 1024 /*align*/ + 256 /*barriers + tmem slot*/ + QN * 4 /*cut*/ +
                         EPI_WARPS * 128 * 2 * 4 /*per-warp counts*/;
-constexpr size_t PARK_FLOATS_PER_CTA = (size_t)QN * BM;
 // shared-memory descriptor high word: SBO = 512 B (8 rows of 64 B), descriptor version 1, SWIZZLE_64B
 constexpr uint32_t DESC_HI64 = (512u >> 4) | (1u << 14) | (4u << 29);
 
@@ -61,15 +62,6 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint32_t a_lo, uint32
         "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %4, 0;\nmov.b64 da, {%1, %5};\nmov.b64 db, {%2, %5};\n"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc),
         "n"(kAcc ? 1 : 0), "r"(DESC_HI64) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar, uint32_t cta_mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;"
-        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar), "h"((unsigned short)cta_mask) : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint32_t cta_mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"((unsigned short)cta_mask) : "memory");
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float hi, float lo) {     // {bf16_rn(hi), bf16_rn(lo)}: lo in bits 0-15
     uint32_t d;
@@ -115,25 +107,27 @@ __device__ __forceinline__ unsigned int transpose32(unsigned int x, int lane) {
 // End of a stream for one epilogue thread (one clip row, 128 queries): term = (w (1 - sim))^2, plus the terms of
 // the earlier streams from the park; the last stream leaves the sum in `run`, the others park it.
 template <bool kFirst, bool kLast>
-__device__ __forceinline__ void stream_final(float (&run)[128], float *park, float w, float ic, int nch) {
+__device__ __forceinline__ void stream_final(float (&run)[128], uint32_t tpark, float w, float ic, int nch) {
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        if (c < nch) {
-            float old[32];
+    for (int c = 0; c < 8; ++c) {                    // 16 queries at a time: small TMEM transfer buffers
+        if (c < 2 * nch) {
+            uint32_t old[16];
             if constexpr (!kFirst) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) old[j] = __ldcg(park + (size_t)(32 * c + j) * BM);
+                tmem_ld16(tpark + 16 * c, old);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             }
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float dd = w * (1.0f - run[32 * c + j] * ic);
+            for (int j = 0; j < 16; ++j) {
+                const float dd = w * (1.0f - run[16 * c + j] * ic);
                 float v = dd * dd;
-                if constexpr (!kFirst) v += old[j];
-                if constexpr (kLast) run[32 * c + j] = v;
-                else __stcg(park + (size_t)(32 * c + j) * BM, v);
+                if constexpr (!kFirst) v += __uint_as_float(old[j]);
+                if constexpr (kLast) run[16 * c + j] = v;
+                else old[j] = __float_as_uint(v);
             }
+            if constexpr (!kLast) tmem_st16(tpark + 16 * c, old);
         }
     }
+    if constexpr (!kLast) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
 // run[base + j] for a warp-uniform runtime j in 0..31 without local memory: 31 selects
@@ -162,17 +156,11 @@ __global__ void split_targets_bf16(const float *__restrict__ t, unsigned short *
     t2[i] = (unsigned short)(q & 0xFFFFu);
 }
 
-// kC = CTAs per cluster.  kC > 1: the CTAs of a cluster walk their tiles in lockstep and share the query tiles:
-// each CTA fetches 1/kC of the rows of t1 / t2 and TMA-multicasts them into every CTA of the cluster, which
-// divides the L2 -> SM traffic for the (re-streamed, L2-resident) query operand by kC.  A stage of the operand
-// ring is reused only after the MMA warps of ALL CTAs of the cluster have committed it (multicast commit).
-template <int kC>
 __global__ void __launch_bounds__(THREADS, 1)
 batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_t1,
                 const __grid_constant__ CUtensorMap map_t2, const BatchArgs a, const float *__restrict__ inv_counts,
                 const float *__restrict__ cut_g, unsigned long long *counts_g /*[QN][2]*/, unsigned int *cand_cnt /*[QN]*/,
-                unsigned long long *cand_keys /*[QN][cap]*/, float *park_g /*[grid][QN][BM]*/,
-                float *scores_dbg /*[Q][n_rows] or null*/, long long *prof /*[grid][8] or null*/) {
+                unsigned long long *cand_keys /*[QN][cap]*/,  float *scores_dbg /*[Q][n_rows] or null*/, long long *prof /*[grid][8] or null*/) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + RING_END);
@@ -181,24 +169,26 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     unsigned int *cnt_s = reinterpret_cast<unsigned int *>(cut_s + QN);      // [8 warps][128 queries][2]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = smem_u32(smem);
-    const uint32_t bar_afull = smem_u32(&bars[0]), bar_aempty = smem_u32(&bars[NA]), bar_tfull = smem_u32(&bars[2 * NA]),
-                   bar_xfull = smem_u32(&bars[2 * NA + NX]), bar_xtempty = smem_u32(&bars[2 * NA + 2 * NX]),
-                   bar_part_full = smem_u32(&bars[2 * NA + 3 * NX]), bar_part_empty = smem_u32(&bars[2 * NA + 3 * NX + 2]);
+    const uint32_t bar_afull = smem_u32(&bars[0]), bar_aempty = smem_u32(&bars[NA]), bar_xfull = smem_u32(&bars[2 * NA]),
+                   bar_xempty = smem_u32(&bars[2 * NA + NXR]), bar_tfull = smem_u32(&bars[2 * NA + 2 * NXR]),
+                   bar_tempty = smem_u32(&bars[2 * NA + 2 * NXR + NT]), bar_part_full = smem_u32(&bars[2 * NA + 2 * NXR + 2 * NT]),
+                   bar_part_empty = smem_u32(&bars[2 * NA + 2 * NXR + 2 * NT + 1]);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NA; ++s) {
             mbar_init(bar_afull + 8 * s, 1);            // producer's expect_tx arrive + TMA bytes of the fp32 tile
             mbar_init(bar_aempty + 8 * s, CONV_WARPS);  // one arrive per converter warp
         }
-        for (int s = 0; s < NX; ++s) {
-            mbar_init(bar_tfull + 8 * s, 1);            // expect_tx arrive + TMA bytes of t1, t2
+        for (int s = 0; s < NXR; ++s) {
             mbar_init(bar_xfull + 8 * s, CONV_WARPS);   // x1, x2 written
-            mbar_init(bar_xtempty + 8 * s, kC);         // tcgen05.commit of every CTA of the cluster
+            mbar_init(bar_xempty + 8 * s, 1);           // tcgen05.commit
         }
-        for (int b = 0; b < 2; ++b) {
-            mbar_init(bar_part_full + 8 * b, 1);           // tcgen05.commit
-            mbar_init(bar_part_empty + 8 * b, EPI_WARPS);  // one arrive per epilogue warp
+        for (int s = 0; s < NT; ++s) {
+            mbar_init(bar_tfull + 8 * s, 1);            // expect_tx arrive + TMA bytes of t1, t2
+            mbar_init(bar_tempty + 8 * s, 1);           // tcgen05.commit
         }
+        mbar_init(bar_part_full, 1);                    // tcgen05.commit
+        mbar_init(bar_part_empty, EPI_WARPS);           // one arrive per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = threadIdx.x; i < QN; i += blockDim.x) cut_s[i] = cut_g[i];
@@ -209,25 +199,23 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if constexpr (kC > 1) cluster_sync_all();         // peer barriers are initialised before any remote signal
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
-    // work unit = kC consecutive tiles, one per CTA of the cluster; every CTA of a cluster runs the same number of
-    // units (rows past the end of the shard are zero-filled by TMA and masked in the epilogue)
-    const int cta_rank = kC > 1 ? (int)cluster_ctarank() : 0;
-    const int unit0 = (int)blockIdx.x / kC, n_units = (int)gridDim.x / kC;
     const int kbps = a.kb_per_stream;
     const int kb_total = kbps * a.n_streams;
     const int n_mma = a.n_mma;                      // queries rounded up to 16: the N of every MMA
+    // this CTA's K blocks in issue order: tiles blockIdx.x, +gridDim.x, ...; kb_total blocks each
+    const int my_tiles = (a.n_tiles > (int)blockIdx.x) ? (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int n_it = my_tiles * kb_total;
 
-    if (warp < 8) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+    if (warp < 4) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         if (warp == 0) {
             // ------------------------------------------------------------------ TMA producer, clip tiles (fp32)
             if (lane == 0) {
                 int it = 0;
-                for (int unit = unit0; unit * kC < a.n_tiles; unit += n_units) {
-                    const int row = (int)(a.row0 + (long long)(unit * kC + cta_rank) * BM);
+                for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+                    const int row = (int)(a.row0 + (long long)tile * BM);
                     for (int kb = 0; kb < kb_total; ++kb, ++it) {
                         const int s = it % NA;
                         mbar_wait(bar_aempty + 8 * s, ((it / NA) & 1) ^ 1);
@@ -239,22 +227,14 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         } else if (warp == 2) {
             // ------------------------------------------------------------------ TMA producer, query tiles (t1, t2)
             if (lane == 0) {
-                int it = 0;
-                for (int unit = unit0; unit * kC < a.n_tiles; unit += n_units) {
-                    for (int kb = 0; kb < kb_total; ++kb, ++it) {
-                        const int s = it % NX;
-                        mbar_wait(bar_xtempty + 8 * s, ((it / NX) & 1) ^ 1);
-                        const uint32_t base = smem_base + RING_XT + (uint32_t)s * XT_BYTES;
-                        mbar_expect(bar_tfull + 8 * s, 2 * T_BYTES);     // bytes of all kC slices land here
-                        if constexpr (kC > 1) {
-                            constexpr uint32_t SLICE = T_BYTES / kC;      // this CTA's rows of the tile, sent to every CTA
-                            tma_load_2d_mc(base + OFF_T1 + cta_rank * SLICE, &map_t1, kb * BK, cta_rank * (QN / kC), bar_tfull + 8 * s, (1u << kC) - 1u);
-                            tma_load_2d_mc(base + OFF_T2 + cta_rank * SLICE, &map_t2, kb * BK, cta_rank * (QN / kC), bar_tfull + 8 * s, (1u << kC) - 1u);
-                        } else {
-                            tma_load_2d(base + OFF_T1, &map_t1, kb * BK, 0, bar_tfull + 8 * s);
-                            tma_load_2d(base + OFF_T2, &map_t2, kb * BK, 0, bar_tfull + 8 * s);
-                        }
-                    }
+                for (int it = 0; it < n_it; ++it) {
+                    const int s = it % NT;
+                    mbar_wait(bar_tempty + 8 * s, ((it / NT) & 1) ^ 1);
+                    const uint32_t base = smem_base + RING_T + (uint32_t)s * 2 * T_BYTES;
+                    const int kb = it % kb_total;
+                    mbar_expect(bar_tfull + 8 * s, 2 * T_BYTES);
+                    tma_load_2d(base, &map_t1, kb * BK, 0, bar_tfull + 8 * s);
+                    tma_load_2d(base + T_BYTES, &map_t2, kb * BK, 0, bar_tfull + 8 * s);
                 }
             }
         } else if (warp == 1) {
@@ -266,7 +246,9 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             int it = 0, gcount = 0;
             long long w_acc = 0, w_data = 0, w_conv = 0;
             const long long m_t0 = VQ_CLOCK();
-            for (int unit = unit0; unit * kC < a.n_tiles; unit += n_units) {
+            unsigned long long g_t0 = 0;
+            if (prof) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_t0));
+            for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
                 for (int st = 0; st < a.n_streams; ++st) {
                     uint32_t d = 0;
                     for (int kb = 0; kb < kbps; ++kb, ++it) {
@@ -274,24 +256,22 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         const bool group_last = (kb % GROUP_KB) == GROUP_KB - 1 || kb == kbps - 1;
                         long long t0 = VQ_CLOCK();
                         if (group_first) {
-                            const int b = gcount & 1;
-                            mbar_wait(bar_part_empty + 8 * b, ((gcount >> 1) & 1) ^ 1);       // partial drained
-                            d = tmem_base + (uint32_t)(b * QN);
+                            mbar_wait(bar_part_empty, (gcount & 1) ^ 1);              // partial drained
+                            d = tmem_base;
                         }
                         long long t1 = VQ_CLOCK();
                         w_acc += t1 - t0;
-                        const int s = it % NX;
-                        const uint32_t ph = (it / NX) & 1;
-                        mbar_wait(bar_tfull + 8 * s, ph);
+                        const int sx = it % NXR, stg = it % NT;
+                        mbar_wait(bar_tfull + 8 * stg, (it / NT) & 1);
                         t0 = VQ_CLOCK();
                         w_data += t0 - t1;
-                        mbar_wait(bar_xfull + 8 * s, ph);
+                        mbar_wait(bar_xfull + 8 * sx, (it / NXR) & 1);
                         w_conv += VQ_CLOCK() - t0;
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t base = smem_base + RING_XT + (uint32_t)s * XT_BYTES;
+                        const uint32_t xbase = smem_base + RING_X + (uint32_t)sx * 2 * X_BYTES;
+                        const uint32_t tbase = smem_base + RING_T + (uint32_t)stg * 2 * T_BYTES;
                         if (elected) {
-                            const uint32_t x1 = desc_lo(base + OFF_X1), x2 = desc_lo(base + OFF_X2), t1d = desc_lo(base + OFF_T1),
-                                           t2d = desc_lo(base + OFF_T2);
+                            const uint32_t x1 = desc_lo(xbase), x2 = desc_lo(xbase + X_BYTES), t1d = desc_lo(tbase), t2d = desc_lo(tbase + T_BYTES);
                             if (group_first) umma_bf16<false>(d, x1, t1d, idesc);
                             else umma_bf16<true>(d, x1, t1d, idesc);
                             umma_bf16<true>(d, x2, t1d, idesc);
@@ -302,9 +282,9 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                                 umma_bf16<true>(d, x2 + 2 * k, t1d + 2 * k, idesc);
                                 umma_bf16<true>(d, x1 + 2 * k, t2d + 2 * k, idesc);
                             }
-                            if constexpr (kC > 1) umma_commit_mc(bar_xtempty + 8 * s, (1u << kC) - 1u);   // ... in every CTA of the cluster
-                            else umma_commit(bar_xtempty + 8 * s);                // stage reusable once these MMAs retire
-                            if (group_last) umma_commit(bar_part_full + 8 * (gcount & 1));
+                            umma_commit(bar_xempty + 8 * sx);                     // both operand stages are reusable once these MMAs retire
+                            umma_commit(bar_tempty + 8 * stg);
+                            if (group_last) umma_commit(bar_part_full);
                         }
                         __syncwarp();
                         if (group_last) ++gcount;
@@ -314,54 +294,64 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             if (prof && elected) {
                 prof[blockIdx.x * 16 + 0] = VQ_CLOCK() - m_t0; prof[blockIdx.x * 16 + 1] = w_conv;
                 prof[blockIdx.x * 16 + 2] = w_acc; prof[blockIdx.x * 16 + 3] = w_data;
+                unsigned long long g_t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g_t1));
+                prof[blockIdx.x * 16 + 12] = (long long)(g_t1 - g_t0);
             }
-        } else if (warp >= 4) {
-            // ------------------------------------------------------------------ converter (warps 4-7, one per SM sub-partition)
-            // Work item = (row r, 8 consecutive dims c8): two 16 B chunks of the fp32 row -> one 16 B chunk of x1 and of x2.
-            // 8 consecutive threads take rows (2p, 2p+1) x c8 = 0..3, which makes every quarter-warp phase of the
-            // 128-bit loads and stores hit 8 distinct 16 B bank groups under both swizzles.
-            const int t = threadIdx.x - 128;                             // 0..127
-            const int rsub = (t >> 3) * 2 + ((t & 7) >> 2);              // 0..31
-            const int c8 = t & 3;
-            const uint32_t src_off0 = (uint32_t)rsub * 128u + (uint32_t)(((2 * c8) ^ (rsub & 7)) * 16);
-            const uint32_t src_off1 = (uint32_t)rsub * 128u + (uint32_t)(((2 * c8 + 1) ^ (rsub & 7)) * 16);
-            const uint32_t dst_off = (uint32_t)rsub * 64u + (uint32_t)((c8 ^ ((rsub >> 1) & 3)) * 16);
-            int it = 0;
-            long long c_wait = 0, c_wait2 = 0;
-            for (int unit = unit0; unit * kC < a.n_tiles; unit += n_units) {
-                for (int kb = 0; kb < kb_total; ++kb, ++it) {
-                    const int sa = it % NA, sx = it % NX;
-                    long long t0 = VQ_CLOCK();
-                    mbar_wait(bar_afull + 8 * sa, (it / NA) & 1);
-                    long long t1 = VQ_CLOCK();
-                    c_wait += t1 - t0;
-                    mbar_wait(bar_xtempty + 8 * sx, ((it / NX) & 1) ^ 1);
-                    c_wait2 += VQ_CLOCK() - t1;
-                    const uint32_t src = smem_base + (uint32_t)sa * A32_BYTES;
-                    const uint32_t dst = smem_base + RING_XT + (uint32_t)sx * XT_BYTES + dst_off;
-                    float4 u[4], v[4];
+        }
+    } else if (warp < 8) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+        // ---------------------------------------------------------------------- converter (warps 4-7, one per SM sub-partition)
+        // Work item = (row r, 8 consecutive dims c8): two 16 B chunks of the fp32 row -> one 16 B chunk of x1 and of x2.
+        // 8 consecutive threads take rows (2p, 2p+1) x c8 = 0..3, which makes every quarter-warp phase of the
+        // 128-bit loads and stores hit 8 distinct 16 B bank groups under both swizzles.  The loads of K block i+1
+        // are issued before block i is converted (software pipeline: shared-memory latency off the critical path).
+        const int t = threadIdx.x - 128;                             // 0..127
+        const int rsub = (t >> 3) * 2 + ((t & 7) >> 2);              // 0..31
+        const int c8 = t & 3;
+        const uint32_t src_off0 = (uint32_t)rsub * 128u + (uint32_t)(((2 * c8) ^ (rsub & 7)) * 16);
+        const uint32_t src_off1 = (uint32_t)rsub * 128u + (uint32_t)(((2 * c8 + 1) ^ (rsub & 7)) * 16);
+        const uint32_t dst_off = (uint32_t)rsub * 64u + (uint32_t)((c8 ^ ((rsub >> 1) & 3)) * 16);
+        long long c_wait = 0, c_wait2 = 0;
+        float4 u[4], v[4];
+        auto load_block = [&](int it) {
+            const int sa = it % NA;
+            const long long t0 = VQ_CLOCK();
+            mbar_wait(bar_afull + 8 * sa, (it / NA) & 1);
+            c_wait += VQ_CLOCK() - t0;
+            const uint32_t src = smem_base + (uint32_t)sa * A32_BYTES;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {                        // 4 items per thread, 8 loads in flight
-                        u[j] = lds128(src + src_off0 + (uint32_t)(j * 32 * 128));
-                        v[j] = lds128(src + src_off1 + (uint32_t)(j * 32 * 128));
-                    }
+            for (int j = 0; j < 4; ++j) {                            // 4 items per thread, 8 loads in flight
+                u[j] = lds128(src + src_off0 + (uint32_t)(j * 32 * 128));
+                v[j] = lds128(src + src_off1 + (uint32_t)(j * 32 * 128));
+            }
+        };
+        if (n_it > 0) load_block(0);
+        for (int it = 0; it < n_it; ++it) {
+            const int sa = it % NA, sx = it % NXR;
+            uint4 p[4], q[4];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 p, q;
-                        split8(u[j], v[j], p, q);
-                        sts128(dst + OFF_X1 + (uint32_t)(j * 32 * 64), p);
-                        sts128(dst + OFF_X2 + (uint32_t)(j * 32 * 64), q);
-                    }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (UMMA)
-                    __syncwarp();
-                    if (lane == 0) {
-                        mbar_arrive(bar_xfull + 8 * sx);
-                        mbar_arrive(bar_aempty + 8 * sa);
-                    }
+            for (int j = 0; j < 4; ++j) split8(u[j], v[j], p[j], q[j]);
+            // the fp32 stage is free as soon as its values sit in registers (the loads above have returned: split8 used them)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_aempty + 8 * sa);
+            if (it + 1 < n_it) load_block(it + 1);                   // next block's loads fly while this one is stored
+            const long long t1 = VQ_CLOCK();
+            mbar_wait(bar_xempty + 8 * sx, ((it / NXR) & 1) ^ 1);
+            c_wait2 += VQ_CLOCK() - t1;
+            const uint32_t dst = smem_base + RING_X + (uint32_t)sx * 2 * X_BYTES + dst_off;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                {
+                    sts128(dst + (uint32_t)(j * 32 * 64), p[j]);
+                    sts128(dst + X_BYTES + (uint32_t)(j * 32 * 64), q[j]);
                 }
             }
-            if (prof && t == 0) { prof[blockIdx.x * 16 + 7] = c_wait; prof[blockIdx.x * 16 + 4] = c_wait2; }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (UMMA)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_xfull + 8 * sx);
         }
+        if (prof && t == 0) { prof[blockIdx.x * 16 + 7] = c_wait; prof[blockIdx.x * 16 + 4] = c_wait2; }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
         // ------------------------------------------------------------------ epilogue (8 warps)
@@ -372,11 +362,10 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         // 32-query chunks of this warp's half that hold live MMA columns (warp-uniform)
         const int nch = max(0, min(4, (n_mma - half * 128 + 31) / 32));
         unsigned int *my_cnt = cnt_s + ew * 128 * 2;
-        float *park = park_g + (size_t)blockIdx.x * PARK_FLOATS_PER_CTA + (size_t)(half * 128) * BM + quarter * 32 + lane;
         int gcount = 0;
         long long e_wait = 0, e_busy = 0, e_score = 0, e_fin0 = 0, e_fin1 = 0, e_tiles = 0;
-        for (int unit = unit0; unit * kC < a.n_tiles; unit += n_units) {
-            const long long row = a.row0 + (long long)(unit * kC + cta_rank) * BM + quarter * 32 + lane;
+        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+            const long long row = a.row0 + (long long)tile * BM + quarter * 32 + lane;
             const bool row_ok = row < a.row_end;
             for (int st = 0; st < a.n_streams; ++st) {
                 float run[128];
@@ -384,13 +373,12 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 for (int j = 0; j < 128; ++j) run[j] = 0.f;
                 const int n_groups = (kbps + GROUP_KB - 1) / GROUP_KB;
                 for (int g = 0; g < n_groups; ++g, ++gcount) {
-                    const int b = gcount & 1;
                     const long long t0 = VQ_CLOCK();
-                    mbar_wait(bar_part_full + 8 * b, (gcount >> 1) & 1);
+                    mbar_wait(bar_part_full, gcount & 1);
                     const long long t1 = VQ_CLOCK();
                     e_wait += t1 - t0;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t col = tlane + (uint32_t)(b * QN);
+                    const uint32_t col = tlane;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         uint32_t r0[32];
@@ -401,7 +389,7 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         if (c == 3) {                                    // partial fully read: the MMA warp may refill it
                             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                             __syncwarp();
-                            if (lane == 0) mbar_arrive(bar_part_empty + 8 * b);
+                            if (lane == 0) mbar_arrive(bar_part_empty);
                         }
                         if (c < nch) {
 #pragma unroll
@@ -416,12 +404,13 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     const float ic = (inv_counts && row_ok) ? inv_counts[row * a.n_streams + st] : a.inv_splits;
                     const float w = st == 0 ? a.w[0] : (st == 1 ? a.w[1] : (st == 2 ? a.w[2] : a.w[3]));   // no dynamic indexing: keeps `a` in the constant bank
                     const bool first = st == 0, last = st + 1 == a.n_streams;
+                    const uint32_t tpark = tlane + (uint32_t)QN;
                     if (first) {
-                        if (last) stream_final<true, true>(run, park, w, ic, nch);
-                        else stream_final<true, false>(run, park, w, ic, nch);
+                        if (last) stream_final<true, true>(run, tpark, w, ic, nch);
+                        else stream_final<true, false>(run, tpark, w, ic, nch);
                     } else {
-                        if (last) stream_final<false, true>(run, park, w, ic, nch);
-                        else stream_final<false, false>(run, park, w, ic, nch);
+                        if (last) stream_final<false, true>(run, tpark, w, ic, nch);
+                        else stream_final<false, false>(run, tpark, w, ic, nch);
                     }
                     if (last) e_fin1 += VQ_CLOCK() - t1;
                     else e_fin0 += VQ_CLOCK() - t1;
@@ -513,7 +502,6 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if constexpr (kC > 1) cluster_sync_all();         // no CTA leaves while a peer may still write into it or signal it
     if (warp == 2) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
