@@ -216,8 +216,9 @@ def test_two_shards_merge_like_one(vq):
 # ---------------------------------------------------------------------------- batched queries (tcgen05)
 @pytest.mark.parametrize("n,nq", [(5003, 70), (300, 3), (20000, 300)])
 def test_batched_tensor_core_scan_matches_oracle(vq, n, nq):
-    """K3: Q targets in one pass (3xTF32 on tcgen05).  Scores within 1e-5 of float64; per-query counts and
-    top-k equal to the oracle's up to rows within COMPUTE_EPS of a boundary / of each other."""
+    """K3: Q targets in one pass (bf16x2 split on tcgen05, 256 queries per pass; 300 queries = two passes, 3 and 70
+    queries = MMAs narrower than 256).  Scores within 1e-5 of float64; per-query counts and top-k equal to the
+    oracle's up to rows within COMPUTE_EPS of a boundary / of each other."""
     seed = 77
     X = synth.database(seed, n)
     st = vq.FeatureStore(n, STREAMS, [1], 1024, devices=[0])
@@ -247,6 +248,28 @@ def test_batched_tensor_core_scan_matches_oracle(vq, n, nq):
         assert np.array_equal(scores[q], got[q][rows[q]])
         for a, b in zip(rows[q], sc.topk_stable(s64, k)):
             assert a == b or abs(s64[a] - s64[b]) < EPS
+    st.close()
+
+
+def test_batched_scan_counts_only_and_ragged_tail(vq):
+    """K3 without a top-k (no candidate lists at all) on a shard whose size is not a multiple of the 128-clip
+    tile, spanning the short seeding launch and a full one: counts equal the single-query scan's counts."""
+    n, seed = 148 * 128 + 4 * 128 + 77, 5
+    X = synth.database(seed, n)
+    st = vq.FeatureStore(n, STREAMS, [1], 1024, devices=[0])
+    st.upload(0, X[:, :, None, :])
+    X64 = X.astype(np.float64)[:, :, None, :]
+    refs = [3, n // 2, n - 1]
+    T = np.stack([sc.scale_target(X64[r]) for r in refs])
+    w, th, lo = (1.0, 1.5), 0.8, sc.lower_limit(0.8, 0.35)
+    counts, rows, scores, _ = st.scan_batch(T.astype(np.float32), w, th, lo, topk=0)
+    assert rows.shape == (3, 0) and scores.shape == (3, 0)
+    got = st.scan_batch(T.astype(np.float32), w, th, lo, debug_scores=True)
+    for q in range(3):
+        g = got[q].astype(np.float64)
+        assert counts[q, 0] == np.count_nonzero(g >= th) and counts[q, 1] == np.count_nonzero((g >= lo) & (g < th))
+        sims64, _ = sc.similarities(X64, T[q].astype(np.float32).astype(np.float64))
+        assert_scores_close(got[q], sc.scores(sims64, w))
     st.close()
 
 
