@@ -261,15 +261,15 @@ def main():
     for _ in range(e2e_steps):
         res = st.scan(tdict, WEIGHTS, THRESHOLD, lower, EPS, topk=TOPK)
         k_rows, k_sc = st.topk()
-        m_rows, m_sc = st.matches()
-        nm_rows, nm_sc = st.near_misses()
+        m_rows, m_sc = st.matches(copy=False)          # as Ticket.select_clips_to_review reads them: views of the
+        nm_rows, nm_sc = st.near_misses(copy=False)    # pinned host mirror the scan's publish kernel wrote
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = world * n * e2e_steps / float(e2e_s.item())
     h2d = ROW_BYTES + C.sizeof(_ffi.ScanParams)
-    d2h = 32 + TOPK * 12 + (res.n_match + res.n_near) * 8
+    d2h = 40 + TOPK * 12 + (res.n_match + res.n_near + res.n_tie) * 12
 
     # ---- cold end to end: the shard itself is uploaded from pinned host memory every step
     cold = None
@@ -324,8 +324,10 @@ def main():
                          "frac_of_nominal_8TBs": achieved / 8000.0,
                          "algorithmic_bytes_per_launch": n * ROW_BYTES},
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": e2e_steps, "what": "FeatureStore.scan + topk + matches + near_misses through the C ABI with host "
-                    "buffers; the shard stays resident in HBM between queries (the store outlives broker ticks)"},
+                    "steps": e2e_steps, "what": "FeatureStore.scan + topk + matches + near_misses through the C ABI: target from a "
+                    "host buffer, counts / top-k / ordered lists (int64 rows + fp32 scores) published into pinned host "
+                    "memory inside the call; the shard stays resident in HBM between queries (the store outlives "
+                    "broker ticks)"},
             "e2e_cold": cold,
             "gpu_launches": rank_scan.kernels_per_step() * args.steps,
             "exchange": rank_scan.exchange,

@@ -79,8 +79,9 @@ typedef struct vq_scan_counts {
 } vq_scan_counts;
 
 /* target: [n_streams][n_splits][dim] fp32 HOST.  Synchronous: copies the target in, runs the
- * scan and its selection kernels, copies the counts out.  Lists stay on the device until
- * fetched.                                                                                   */
+ * scan and its selection kernels, and publishes counts, top-k and the three ordered lists into
+ * a pinned host mirror owned by the library (one stream synchronisation).  vq_fetch_* copy
+ * from that mirror into caller buffers; vq_scan_host_list hands out read-only views of it.   */
 int vq_scan(vq_store *s, const float *target, const vq_scan_params *p, vq_scan_counts *out);
 /* Same work, enqueued only: target already on the device, nothing copied back, no sync.
  * Used for device-side timing and for multi-GPU merges that read the results in place.      */
@@ -91,6 +92,10 @@ int vq_fetch_matches(vq_store *s, int64_t cap, int64_t *rows_out, float *scores_
 int vq_fetch_near(vq_store *s, int64_t cap, int64_t *rows_out, float *scores_out);
 int vq_fetch_ties(vq_store *s, int64_t cap, int64_t *rows_out, float *scores_out);
 int vq_fetch_topk(vq_store *s, int32_t cap, int64_t *rows_out, float *scores_out);
+/* Read-only view of the host mirror filled by the last vq_scan on this store: which = 0 matches,
+ * 1 near misses, 2 tie band, 3 top-k; rows are GLOBAL, lists in database order (top-k ranked).
+ * Valid until the next scan on this store; the caller must not free or write it.             */
+int vq_scan_host_list(vq_store *s, int32_t which, const int64_t **rows, const float **scores, int64_t *n);
 int vq_fetch_scores(vq_store *s, int64_t first_row, int64_t n_rows, float *scores_out);
 int vq_fetch_sims(vq_store *s, int64_t first_row, int64_t n_rows, float *sims_out);
 

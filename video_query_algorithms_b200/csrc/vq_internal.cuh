@@ -80,11 +80,13 @@ struct vq_store {
     bool ev_made = false;
     int ev_head = 0, ev_count = 0;
     void *pinned_stage = nullptr;    // small pinned buffer for targets / params
-    // pinned mirror of the last scan's lists + top-k (filled by vq_scan so that the fetch calls are plain memcpys)
-    uint32_t *h_rows[3] = {nullptr, nullptr, nullptr};
+    // pinned, device-mapped mirror of the last scan's lists + top-k: vq_scan's publish kernel writes it over PCIe,
+    // so one stream synchronisation ends the call; the fetch calls are host memcpys, vq_scan_host_list hands out views
+    int64_t *h_rows[3] = {nullptr, nullptr, nullptr};        // GLOBAL rows (written by the publish kernel)
     float *h_scores[3] = {nullptr, nullptr, nullptr};
     int64_t h_cap[3] = {0, 0, 0};
     int64_t *h_topk_rows = nullptr;
     float *h_topk_scores = nullptr;
+    int64_t *h_result = nullptr;     // pinned [8]: n_match n_near n_tie n_topk overflow
     bool staged = false;
 };

@@ -500,6 +500,48 @@ merge_packed(const long long *__restrict__ gathered, const int n_lists, const in
     if (threadIdx.x == 0) out[3] = (long long)min((unsigned int)k, n_valid);
 }
 
+// Host-facing tail of vq_scan: copies the counts, the top-k and the three ordered lists (rows as GLOBAL int64) into
+// pinned, device-mapped host memory with coalesced stores, so that the call needs ONE stream synchronisation and
+// no host-side conversion.  Lists longer than the mirror's capacity set the overflow flag (the host grows the
+// mirror and publishes again).
+struct PublishArgs {
+    const long long *counts;             // device [4]
+    const unsigned int *rows[3];
+    const float *scores[3];
+    long long *h_rows[3];
+    float *h_scores[3];
+    long long cap[3];
+    const long long *topk_rows;
+    const float *topk_scores;
+    long long *h_topk_rows;
+    float *h_topk_scores;
+    long long *h_result;                 // [8]
+    long long first_global_row;
+};
+
+__global__ void __launch_bounds__(256)
+publish_results(const PublishArgs a) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nth = (long long)gridDim.x * blockDim.x;
+    long long overflow = 0;
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        long long n = a.counts[q];
+        if (n > a.cap[q]) { overflow = 1; n = a.cap[q]; }
+        for (long long i = tid; i < n; i += nth) {
+            a.h_rows[q][i] = a.first_global_row + (long long)a.rows[q][i];
+            a.h_scores[q][i] = a.scores[q][i];
+        }
+    }
+    const long long k = a.counts[3];
+    for (long long i = tid; i < k; i += nth) {
+        a.h_topk_rows[i] = a.topk_rows[i];
+        a.h_topk_scores[i] = a.topk_scores[i];
+    }
+    if (tid < 4) a.h_result[tid] = a.counts[tid];
+    if (tid == 4) a.h_result[4] = overflow;
+}
+
 int fill_args(const vq_store *s, const vq_scan_params *p, ScanArgs *a) {
     VQ_REQUIRE(p, "scan: null params");
     VQ_REQUIRE(p->topk >= 0 && p->topk <= VQ_MAX_TOPK, "scan: topk %d outside 0..%d", p->topk, VQ_MAX_TOPK);
@@ -601,41 +643,45 @@ extern "C" int vq_scan_wait(vq_store *s, void *stream, vq_scan_counts *out) {
     return 0;
 }
 
-// Copy the ordered lists and the top-k of the scan that just completed into pinned host memory with one
-// batch of async copies and one synchronisation, so that the vq_fetch_* calls are host memcpys.
-static int stage_results(vq_store *s) {
-    const int64_t kMaxStage = 64ll << 20;                    // entries; larger lists are fetched on demand
-    for (int i = 0; i < 3; ++i) {
-        const int64_t n = s->counts_host[i];
-        if (n > kMaxStage) return 0;
-        if (n > s->h_cap[i]) {
-            if (s->h_rows[i]) cudaFreeHost(s->h_rows[i]);
-            if (s->h_scores[i]) cudaFreeHost(s->h_scores[i]);
-            s->h_rows[i] = nullptr;
-            s->h_scores[i] = nullptr;
-            const int64_t cap = n + n / 4 + 1024;
-            VQ_CUDA(cudaMallocHost((void **)&s->h_rows[i], (size_t)cap * sizeof(uint32_t)));
-            VQ_CUDA(cudaMallocHost((void **)&s->h_scores[i], (size_t)cap * sizeof(float)));
-            s->h_cap[i] = cap;
-        }
-    }
+static int grow_mirror(vq_store *s, int which, int64_t need) {
+    if (need <= s->h_cap[which]) return 0;
+    if (s->h_rows[which]) cudaFreeHost(s->h_rows[which]);
+    if (s->h_scores[which]) cudaFreeHost(s->h_scores[which]);
+    s->h_rows[which] = nullptr;
+    s->h_scores[which] = nullptr;
+    s->h_cap[which] = 0;
+    int64_t cap = need + need / 4 + 1024;
+    if (cap > s->n_rows) cap = s->n_rows > 0 ? s->n_rows : 1;
+    VQ_CUDA(cudaMallocHost((void **)&s->h_rows[which], (size_t)cap * sizeof(int64_t)));
+    VQ_CUDA(cudaMallocHost((void **)&s->h_scores[which], (size_t)cap * sizeof(float)));
+    s->h_cap[which] = cap;
+    return 0;
+}
+
+static int publish(vq_store *s) {
     if (!s->h_topk_rows) {
         VQ_CUDA(cudaMallocHost((void **)&s->h_topk_rows, VQ_MAX_TOPK * sizeof(int64_t)));
         VQ_CUDA(cudaMallocHost((void **)&s->h_topk_scores, VQ_MAX_TOPK * sizeof(float)));
+        VQ_CUDA(cudaMallocHost((void **)&s->h_result, 8 * sizeof(int64_t)));
     }
+    PublishArgs a;
+    a.counts = (const long long *)s->counts;
     for (int i = 0; i < 3; ++i) {
-        const size_t n = (size_t)s->counts_host[i];
-        if (!n) continue;
-        VQ_CUDA(cudaMemcpyAsync(s->h_rows[i], s->list_rows[i], n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->stream));
-        VQ_CUDA(cudaMemcpyAsync(s->h_scores[i], s->list_scores[i], n * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+        a.rows[i] = s->list_rows[i];
+        a.scores[i] = s->list_scores[i];
+        a.h_rows[i] = (long long *)s->h_rows[i];
+        a.h_scores[i] = s->h_scores[i];
+        a.cap[i] = s->h_cap[i];
     }
-    const size_t k = (size_t)s->counts_host[3];
-    if (k) {
-        VQ_CUDA(cudaMemcpyAsync(s->h_topk_rows, s->topk_rows, k * sizeof(int64_t), cudaMemcpyDeviceToHost, s->stream));
-        VQ_CUDA(cudaMemcpyAsync(s->h_topk_scores, s->topk_scores, k * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
-    }
+    a.topk_rows = (const long long *)s->topk_rows;
+    a.topk_scores = s->topk_scores;
+    a.h_topk_rows = (long long *)s->h_topk_rows;
+    a.h_topk_scores = s->h_topk_scores;
+    a.h_result = (long long *)s->h_result;
+    a.first_global_row = s->first_global_row;
+    publish_results<<<s->sm_count, 256, 0, s->stream>>>(a);
+    VQ_CUDA(cudaGetLastError());
     VQ_CUDA(cudaStreamSynchronize(s->stream));
-    s->staged = true;
     return 0;
 }
 
@@ -646,8 +692,42 @@ extern "C" int vq_scan(vq_store *s, const float *target, const vq_scan_params *p
     memcpy(s->pinned_stage, target, bytes);
     VQ_CUDA(cudaMemcpyAsync(s->target, s->pinned_stage, bytes, cudaMemcpyHostToDevice, s->stream));
     if (int r = vq_scan_enqueue(s, s->target, p, s->stream)) return r;
-    if (int r = vq_scan_wait(s, s->stream, out)) return r;
-    return stage_results(s);
+    // the mirror starts at 1/8 of the shard per list (at least 64k entries) and grows on demand
+    const int64_t first_cap = s->n_rows / 8 > 65536 ? s->n_rows / 8 : 65536;
+    for (int i = 0; i < 3; ++i)
+        if (s->h_cap[i] == 0)
+            if (int r = grow_mirror(s, i, first_cap)) return r;
+    if (int r = publish(s)) return r;
+    if (s->h_result[4]) {                                  // a list outgrew its mirror: grow, publish again
+        for (int i = 0; i < 3; ++i)
+            if (int r = grow_mirror(s, i, s->h_result[i])) return r;
+        if (int r = publish(s)) return r;
+    }
+    for (int i = 0; i < 4; ++i) s->counts_host[i] = s->h_result[i];
+    s->staged = true;
+    if (out) {
+        out->n_match = s->counts_host[0];
+        out->n_near = s->counts_host[1];
+        out->n_tie = s->counts_host[2];
+        out->n_topk = (int32_t)s->counts_host[3];
+        out->scan_ms = 0.f;
+        if (s->ev_count > 0) {
+            const int slot = (s->ev_head + vq::kTimeRing - 1) % vq::kTimeRing;
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, s->ev_start[slot], s->ev_stop[slot]) == cudaSuccess) out->scan_ms = ms;
+        }
+    }
+    return 0;
+}
+
+extern "C" int vq_scan_host_list(vq_store *s, int32_t which, const int64_t **rows, const float **scores, int64_t *n) {
+    VQ_REQUIRE(s && rows && scores && n, "vq_scan_host_list: null argument");
+    VQ_REQUIRE(which >= 0 && which <= 3, "vq_scan_host_list: list %d outside 0..3 (matches, near misses, ties, top-k)", which);
+    VQ_REQUIRE(s->staged, "vq_scan_host_list: the last scan on this store was not a vq_scan (no host mirror)");
+    *n = s->counts_host[which];
+    *rows = which == 3 ? s->h_topk_rows : s->h_rows[which];
+    *scores = which == 3 ? s->h_topk_scores : s->h_scores[which];
+    return 0;
 }
 
 static int fetch_list(vq_store *s, int which, int64_t cap, int64_t *rows_out, float *scores_out,
@@ -658,8 +738,7 @@ static int fetch_list(vq_store *s, int which, int64_t cap, int64_t *rows_out, fl
     VQ_REQUIRE(cap >= n, "%s: capacity %lld < %lld entries", who, (long long)cap, (long long)n);
     if (n == 0) return 0;
     if (s->staged) {
-        if (rows_out)
-            for (int64_t i = 0; i < n; ++i) rows_out[i] = s->first_global_row + (int64_t)s->h_rows[which][i];
+        if (rows_out) memcpy(rows_out, s->h_rows[which], (size_t)n * sizeof(int64_t));
         if (scores_out) memcpy(scores_out, s->h_scores[which], (size_t)n * sizeof(float));
         return 0;
     }

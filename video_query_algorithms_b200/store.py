@@ -281,28 +281,44 @@ class FeatureStore:
             raise errs[0]
         return counts
 
-    def _fetch_list(self, fn, attr):
+    def _host_view(self, shard, which):
+        """Read-only numpy views of the library's pinned host mirror (valid until the next scan)."""
+        rp, sp, n = C.c_void_p(), C.c_void_p(), C.c_int64()
+        check(lib().vq_scan_host_list(shard.handle, which, C.byref(rp), C.byref(sp), C.byref(n)), "vq_scan_host_list")
+        if n.value == 0:
+            return np.empty(0, np.int64), np.empty(0, np.float32)
+        r = np.ctypeslib.as_array(C.cast(rp, C.POINTER(C.c_int64)), shape=(n.value,))
+        s = np.ctypeslib.as_array(C.cast(sp, C.POINTER(C.c_float)), shape=(n.value,))
+        r.flags.writeable = False
+        s.flags.writeable = False
+        return r, s
+
+    def _fetch_list(self, fn, attr, which, copy):
         rows, scores = [], []
         for sh, c in zip(self.shards, self._last_counts):
-            n = getattr(c, attr)
-            r = np.empty(n, np.int64)
-            s = np.empty(n, np.float32)
-            check(fn(sh.handle, n, ptr(r), ptr(s)), attr)
+            if not copy:
+                r, s = self._host_view(sh, which)
+            else:
+                n = getattr(c, attr)
+                r = np.empty(n, np.int64)
+                s = np.empty(n, np.float32)
+                check(fn(sh.handle, n, ptr(r), ptr(s)), attr)
             rows.append(r)
             scores.append(s)
         if len(rows) == 1:
             return rows[0], scores[0]
         return np.concatenate(rows), np.concatenate(scores)
 
-    def matches(self):
-        """(global rows ascending, fp32 scores) of {score >= threshold}."""
-        return self._fetch_list(lib().vq_fetch_matches, "n_match")
+    def matches(self, copy=True):
+        """(global rows ascending, fp32 scores) of {score >= threshold}.  copy=False returns read-only views of
+        the pinned host mirror the scan published into: no copy, valid until the next scan on this store."""
+        return self._fetch_list(lib().vq_fetch_matches, "n_match", 0, copy)
 
-    def near_misses(self):
-        return self._fetch_list(lib().vq_fetch_near, "n_near")
+    def near_misses(self, copy=True):
+        return self._fetch_list(lib().vq_fetch_near, "n_near", 1, copy)
 
-    def ties(self):
-        return self._fetch_list(lib().vq_fetch_ties, "n_tie")
+    def ties(self, copy=True):
+        return self._fetch_list(lib().vq_fetch_ties, "n_tie", 2, copy)
 
     def topk(self):
         k = self._last_topk

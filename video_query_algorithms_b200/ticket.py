@@ -306,9 +306,9 @@ class Ticket:
         st = self.feature_store()
         res = self._scan(threshold, lower_limit)
         ids = st.clip_ids
-        m_rows, m_sc = st.matches()
-        n_rows, n_sc = st.near_misses()
-        t_rows, _ = st.ties()
+        m_rows, m_sc = st.matches(copy=False)         # views of the scan's host mirror: consumed before the next scan
+        n_rows, n_sc = st.near_misses(copy=False)
+        t_rows, _ = st.ties(copy=False)
         self.tie_band = [int(ids[r - st.first_global_row]) for r in t_rows]
         if self.tie_band:
             logging.info("query %s: %d clip(s) within COMPUTE_EPS of a selection boundary: %s",
