@@ -12,6 +12,7 @@
 //   K2c select_compact   order-preserving compaction of the three row lists.
 //
 // Summation order is fixed by the launch geometry, so results are deterministic run to run.
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -160,73 +161,74 @@ scan_rows_reg(const float4 *__restrict__ rows, const float4 *__restrict__ target
     finish_histogram(hist_s, hist_g, a.topk);
 }
 
-// K1, generic: any stream count <= 4 and any stream length (multiple of 4 floats); the target
-// sits in shared memory.  Used for databases with several splits per stream (fixtures: 3 x 1024).
-template <int S>
+// K1, generic: any stream count <= 4 and any stream length (multiple of 4 floats); the target sits in shared
+// memory.  Used for databases with several splits per stream (fixtures: 3 x 1024 floats per stream).
+// A warp walks its rows as one linear sequence of chunks of 32 x U float4 (stream after stream, row after row);
+// the 128-bit loads of chunk k+1 are issued before chunk k is consumed (register double buffer), so U loads per
+// lane are always in flight whatever the row shape.  Score terms are accumulated in stream order, like fuse_score.
+template <int U>
 __global__ void __launch_bounds__(kScanThreads)
-scan_rows_smem(const float4 *__restrict__ rows, const float4 *__restrict__ target,
-               const float *__restrict__ inv_counts, const ScanArgs a, const long long n_rows,
-               const int len4, float *__restrict__ scores, float *__restrict__ sims,
-               unsigned int *hist_g) {
+scan_rows_generic(const float4 *__restrict__ rows, const float4 *__restrict__ target,
+                  const float *__restrict__ inv_counts, const ScanArgs a, const long long n_rows, const int n_streams,
+                  const int len4, float *__restrict__ scores, float *__restrict__ sims, unsigned int *hist_g) {
     extern __shared__ float4 tgt_s[];                 // [S][len4]
     __shared__ unsigned int hist_s[kHistBins];
     for (int b = threadIdx.x; b < kHistBins; b += blockDim.x) hist_s[b] = 0;
-    for (int i = threadIdx.x; i < S * len4; i += blockDim.x) tgt_s[i] = target[i];
+    for (int i = threadIdx.x; i < n_streams * len4; i += blockDim.x) tgt_s[i] = target[i];
     __syncthreads();
     const int lane = threadIdx.x & 31;
     const long long warp0 = (long long)blockIdx.x * (kScanThreads / 32) + (threadIdx.x >> 5);
     const long long n_warps = (long long)gridDim.x * (kScanThreads / 32);
-    constexpr int U = 8;                               // 8 x 128-bit loads in flight per lane per chunk
-    for (long long row = warp0; row < n_rows; row += n_warps) {
-        const float4 *p = rows + row * (long long)(S * len4);
-        float sim[S];
+    const int cps = (len4 + 32 * U - 1) / (32 * U);   // chunks per stream
+    const long long row_f4 = (long long)n_streams * len4;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+    float4 xn[U];
+    long long row = warp0;
+    int st = 0, ck = 0;                               // stream and chunk-in-stream of the chunk held in xn
+    auto load = [&](long long r, int s_, int c_) {
+        const float4 *p = rows + r * row_f4 + (long long)s_ * len4 + c_ * (32 * U) + lane;
+        const int j0 = c_ * (32 * U) + lane;
 #pragma unroll
-        for (int s = 0; s < S; ++s) {
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-            for (int base = 0; base < len4; base += 32 * U) {
-                float4 x[U];
-                if (base + 32 * U <= len4) {                 // full chunk: U unconditional loads back to back
+        for (int u = 0; u < U; ++u) xn[u] = (r < n_rows && j0 + u * 32 < len4) ? ld_stream(p + u * 32) : zero4;
+    };
+    if (row < n_rows) load(row, 0, 0);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, ssum = 0.f;
+    while (row < n_rows) {
+        float4 x[U];
 #pragma unroll
-                    for (int u = 0; u < U; ++u) x[u] = ld_stream(p + s * len4 + base + u * 32 + lane);
+        for (int u = 0; u < U; ++u) x[u] = xn[u];
+        // position of the next chunk, and its loads
+        long long nrow = row;
+        int nst = st, nck = ck + 1;
+        if (nck == cps) { nck = 0; if (++nst == n_streams) { nst = 0; nrow += n_warps; } }
+        load(nrow, nst, nck);
+        const int j0 = ck * (32 * U) + lane;
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const float4 tv = tgt_s[s * len4 + base + u * 32 + lane];
-                        a0 = fmaf(x[u].x, tv.x, a0);
-                        a1 = fmaf(x[u].y, tv.y, a1);
-                        a2 = fmaf(x[u].z, tv.z, a2);
-                        a3 = fmaf(x[u].w, tv.w, a3);
-                    }
-                } else {
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const int j = base + u * 32 + lane;
-                        x[u] = (j < len4) ? ld_stream(p + s * len4 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const int j = base + u * 32 + lane;
-                        if (j < len4) {
-                            const float4 tv = tgt_s[s * len4 + j];
-                            a0 = fmaf(x[u].x, tv.x, a0);
-                            a1 = fmaf(x[u].y, tv.y, a1);
-                            a2 = fmaf(x[u].z, tv.z, a2);
-                            a3 = fmaf(x[u].w, tv.w, a3);
-                        }
-                    }
+        for (int u = 0; u < U; ++u) {
+            const int j = j0 + u * 32;
+            const float4 tv = (j < len4) ? tgt_s[st * len4 + j] : zero4;
+            a0 = fmaf(x[u].x, tv.x, a0);
+            a1 = fmaf(x[u].y, tv.y, a1);
+            a2 = fmaf(x[u].z, tv.z, a2);
+            a3 = fmaf(x[u].w, tv.w, a3);
+        }
+        if (ck == cps - 1) {                          // end of a stream: similarity, score term
+            const float d = warp_sum((a0 + a1) + (a2 + a3)) * (inv_counts ? inv_counts[row * n_streams + st] : a.inv_splits);
+            a0 = a1 = a2 = a3 = 0.f;
+            const float e = a.w[st] * (1.0f - d);
+            ssum = fmaf(e, e, ssum);
+            if (a.want_sims && lane == 0) sims[row * n_streams + st] = d;
+            if (st == n_streams - 1) {                // end of the row
+                if (lane == 0) {
+                    const float sc = 1.0f - __fsqrt_rn(ssum * a.inv_den);
+                    scores[row] = sc;
+                    if (a.topk > 0 && sc == sc) atomicAdd(&hist_s[score_bin(sc)], 1u);
                 }
+                ssum = 0.f;
             }
-            const float d = warp_sum((a0 + a1) + (a2 + a3));
-            sim[s] = d * (inv_counts ? inv_counts[row * S + s] : a.inv_splits);
         }
-        if (lane == 0) {
-            const float sc = fuse_score<S>(sim, a);
-            scores[row] = sc;
-            if (a.want_sims) {
-#pragma unroll
-                for (int s = 0; s < S; ++s) sims[row * S + s] = sim[s];
-            }
-            if (a.topk > 0 && sc == sc) atomicAdd(&hist_s[score_bin(sc)], 1u);
-        }
+        row = nrow; st = nst; ck = nck;
     }
     finish_histogram(hist_s, hist_g, a.topk);
 }
@@ -561,17 +563,28 @@ int fill_args(const vq_store *s, const vq_scan_params *p, ScanArgs *a) {
     return 0;
 }
 
-template <int S>
-void launch_smem(vq_store *s, const float *target_dev, const ScanArgs &a, int grid, cudaStream_t st) {
+template <int U>
+void launch_generic_u(vq_store *s, const float *target_dev, const ScanArgs &a, int grid, cudaStream_t st) {
     const int len4 = s->stream_len / 4;
-    const size_t smem = (size_t)S * len4 * sizeof(float4);
-    cudaFuncSetAttribute(scan_rows_smem<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const size_t smem = (size_t)s->n_streams * len4 * sizeof(float4);
+    cudaFuncSetAttribute(scan_rows_generic<U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int per_sm = 0;                                    // persistent grid: every resident block slot of every SM
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_rows_smem<S>, kScanThreads, smem) == cudaSuccess && per_sm > 0)
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scan_rows_generic<U>, kScanThreads, smem) == cudaSuccess && per_sm > 0)
         grid = s->sm_count * per_sm;
-    scan_rows_smem<S><<<grid, kScanThreads, smem, st>>>(
+    scan_rows_generic<U><<<grid, kScanThreads, smem, st>>>(
         reinterpret_cast<const float4 *>(s->rows), reinterpret_cast<const float4 *>(target_dev),
-        s->inv_counts, a, s->n_rows, len4, s->scores, s->sims, s->hist);
+        s->inv_counts, a, s->n_rows, s->n_streams, len4, s->scores, s->sims, s->hist);
+}
+
+void launch_generic(vq_store *s, const float *target_dev, const ScanArgs &a, int grid, cudaStream_t st) {
+    const int len4 = s->stream_len / 4;
+    const char *force = getenv("VQ_SCAN_U");           // development override
+    // measured on 3 x 1024-float streams (B200): U = 8 / 12 / 16 -> 6.22 / 6.11 / 6.86 TB/s (a partial last chunk costs less
+    // than fewer loads in flight); short streams keep 8
+    const int u = force ? atoi(force) : (len4 >= 512 ? 16 : 8);
+    if (u == 12) launch_generic_u<12>(s, target_dev, a, grid, st);
+    else if (u == 16) launch_generic_u<16>(s, target_dev, a, grid, st);
+    else launch_generic_u<8>(s, target_dev, a, grid, st);
 }
 
 }  // namespace
@@ -598,12 +611,7 @@ extern "C" int vq_scan_enqueue(vq_store *s, const float *target_dev, const vq_sc
             reinterpret_cast<const float4 *>(s->rows), reinterpret_cast<const float4 *>(target_dev),
             s->inv_counts, a, s->n_rows, s->scores, s->sims, s->hist);
     } else {
-        switch (s->n_streams) {
-            case 1: launch_smem<1>(s, target_dev, a, grid, st); break;
-            case 2: launch_smem<2>(s, target_dev, a, grid, st); break;
-            case 3: launch_smem<3>(s, target_dev, a, grid, st); break;
-            default: launch_smem<4>(s, target_dev, a, grid, st); break;
-        }
+        launch_generic(s, target_dev, a, grid, st);
     }
     VQ_CUDA(cudaEventRecord(s->ev_stop[slot], st));
     const unsigned int sel_blocks = (unsigned int)(s->n_chunks > 0 ? s->n_chunks : 1);
