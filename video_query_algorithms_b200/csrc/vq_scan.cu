@@ -606,7 +606,7 @@ extern "C" int vq_scan_enqueue(vq_store *s, const float *target_dev, const vq_sc
     if (s->ev_count < vq::kTimeRing) s->ev_count++;
     VQ_CUDA(cudaEventRecord(s->ev_start[slot], st));
     const int grid = s->sm_count * 3;
-    if (s->n_streams == 2 && s->stream_len == 1024) {
+    if (s->n_streams == 2 && s->stream_len == 1024 && !getenv("VQ_SCAN_GENERIC")) {
         scan_rows_reg<2, 8><<<grid, kScanThreads, 0, st>>>(
             reinterpret_cast<const float4 *>(s->rows), reinterpret_cast<const float4 *>(target_dev),
             s->inv_counts, a, s->n_rows, s->scores, s->sims, s->hist);
