@@ -147,7 +147,7 @@ int run_batch_bf16(vq_store *s, const float *targets, int n_queries, const vq_sc
     const long long chunk_rows = (long long)s->sm_count * bf::BM * 16;
     const long long cap = chunk_rows + VQ_MAX_TOPK;
     VQ_CUDA(cudaFuncSetAttribute(bf::batch_scan_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf::SMEM));
-    Dev d_t, d_t1, d_t2, d_cut, d_counts, d_cnt, d_keys, d_rows, d_sc, d_dbg, d_prof;
+    Dev d_t, d_t1, d_t2, d_cut, d_counts, d_cnt, d_keys, d_rows, d_sc, d_dbg, d_prof, d_park;
     VQ_CUDA(d_t.alloc((size_t)QN * K * 4));
     VQ_CUDA(d_t1.alloc((size_t)QN * K * 2));
     VQ_CUDA(d_t2.alloc((size_t)QN * K * 2));
@@ -158,6 +158,7 @@ int run_batch_bf16(vq_store *s, const float *targets, int n_queries, const vq_sc
     VQ_CUDA(d_rows.alloc((size_t)QN * (topk ? topk : 1) * 8));
     VQ_CUDA(d_sc.alloc((size_t)QN * (topk ? topk : 1) * 4));
     if (scores_dbg_host) VQ_CUDA(d_dbg.alloc((size_t)QN * s->n_rows * 4));
+    VQ_CUDA(d_park.alloc((size_t)s->sm_count * QN * bf::BM * 4));
     const bool want_prof = getenv("VQ_BATCH_PROF") != nullptr;
     if (want_prof) VQ_CUDA(d_prof.alloc((size_t)s->sm_count * 16 * 8));
     cudaEvent_t e0, e1;
@@ -201,7 +202,7 @@ int run_batch_bf16(vq_store *s, const float *targets, int n_queries, const vq_sc
             const int units = a.n_tiles < s->sm_count ? a.n_tiles : s->sm_count;
             bf::batch_scan_bf16<<<units, bf::THREADS, bf::SMEM, st>>>(
                 map_a, map_t1, map_t2, a, s->inv_counts, d_cut.as<float>(), d_counts.as<unsigned long long>(),
-                d_cnt.as<unsigned int>(), d_keys.as<unsigned long long>(),
+                d_cnt.as<unsigned int>(), d_keys.as<unsigned long long>(), d_park.as<float>(),
                 scores_dbg_host ? d_dbg.as<float>() : nullptr, want_prof ? d_prof.as<long long>() : nullptr);
             if (topk > 0)
                 batch_compact<<<QN, 1024, 0, st>>>(d_cnt.as<unsigned int>(), d_keys.as<unsigned long long>(), cap, topk,

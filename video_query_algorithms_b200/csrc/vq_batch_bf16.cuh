@@ -15,9 +15,11 @@
 //     TMA  -> fp32 clip tile [128 x 32] (128B swizzle, ring of 3)         -> converter warps -> x1, x2 bf16 tiles
 //     TMA  -> t1, t2 bf16 query tiles [256 x 32] (64B swizzle, ring of 3)    [128 x 32] (64B swizzle, ring of 4)
 //     6 x tcgen05.mma into the partial accumulator
-// TMEM (512 columns): columns 0-255 the partial accumulator, columns 256-511 the "park": the earlier streams'
-// terms (w_s (1 - sim_s))^2 of every (clip, query) wait there until the last stream is done — registers hold
-// the 128 running sums per thread and have no room for them.
+// TMEM (512 columns) holds two partial accumulators of 256 columns: the MMA warp fills one while the epilogue drains
+// the other.  The earlier streams' terms (w_s (1 - sim_s))^2 of every (clip, query) are parked in an L2-resident
+// scratch (128 KB per CTA, float4 per thread, evict-last) until the last stream is done — registers hold the 128
+// running sums per thread and TMEM the accumulators; neither has room.  Clip tiles are loaded evict-first, query
+// tiles evict-last, so the 3 TB/s clip stream does not push the park and the query operand out of L2.
 //
 // Warps (512 threads; setmaxnreg moves registers from warpgroups 0-1 to the epilogue warpgroups 2-3):
 //     warp 0       TMA producer, clip tiles            warp 2       TMEM allocation, TMA producer for t1 / t2
@@ -50,7 +52,7 @@ constexpr uint32_t RING_END = RING_T + NT * 2 * T_BYTES;     // 48 + 64 + 96 = 2
 constexpr int THREADS = 512;
 constexpr int CONV_WARPS = 4;
 constexpr int EPI_WARPS = 8;
-constexpr int N_BARS = 2 * NA + 2 * NXR + 2 * NT + 2;
+constexpr int N_BARS = 2 * NA + 2 * NXR + 2 * NT + 4;
 constexpr size_t SMEM = (size_t)RING_END + 1024 /*align*/ + 256 /*barriers + tmem slot*/ + QN * 4 /*cut*/ +
                         EPI_WARPS * 128 * 2 * 4 /*per-warp counts*/;
 // shared-memory descriptor high word: SBO = 512 B (8 rows of 64 B), descriptor version 1, SWIZZLE_64B
@@ -62,6 +64,31 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint32_t a_lo, uint32
         "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %4, 0;\nmov.b64 da, {%1, %5};\nmov.b64 db, {%2, %5};\n"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, p;\n}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc),
         "n"(kAcc ? 1 : 0), "r"(DESC_HI64) : "memory");
+}
+// L2 residency control.  The clip tiles are a read-once stream (evict-first); the query tiles and the park are
+// re-read every tile (evict-last), otherwise the 3 TB/s clip stream pushes them out of L2 between two uses.
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_load_2d_hint(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+        ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar), "l"(pol) : "memory");
+}
+__device__ __forceinline__ float4 ld_park(const float4 *p, uint64_t pol) {
+    float4 v;
+    asm volatile("ld.global.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+__device__ __forceinline__ void st_park(float4 *p, const float4 &v, uint64_t pol) {
+    asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float hi, float lo) {     // {bf16_rn(hi), bf16_rn(lo)}: lo in bits 0-15
     uint32_t d;
@@ -106,28 +133,36 @@ __device__ __forceinline__ unsigned int transpose32(unsigned int x, int lane) {
 
 // End of a stream for one epilogue thread (one clip row, 128 queries): term = (w (1 - sim))^2, plus the terms of
 // the earlier streams from the park; the last stream leaves the sum in `run`, the others park it.
+// The park lives in global memory, L2-resident (evict-last): per CTA [64 query groups of 4][128 rows] float4, so a warp
+// moves 512 contiguous bytes per instruction.
 template <bool kFirst, bool kLast>
-__device__ __forceinline__ void stream_final(float (&run)[128], uint32_t tpark, float w, float ic, int nch) {
+__device__ __forceinline__ void stream_final(float (&run)[128], float4 *park, uint64_t pol, float w, float ic, int nch) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {                    // 16 queries at a time: small TMEM transfer buffers
-        if (c < 2 * nch) {
-            uint32_t old[16];
+    for (int c = 0; c < 4; ++c) {
+        if (c < nch) {
+            float4 old[8];
             if constexpr (!kFirst) {
-                tmem_ld16(tpark + 16 * c, old);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int g = 0; g < 8; ++g) old[g] = ld_park(park + (size_t)(8 * c + g) * BM, pol);
             }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const float dd = w * (1.0f - run[16 * c + j] * ic);
-                float v = dd * dd;
-                if constexpr (!kFirst) v += __uint_as_float(old[j]);
-                if constexpr (kLast) run[16 * c + j] = v;
-                else old[j] = __float_as_uint(v);
+            for (int g = 0; g < 8; ++g) {
+                float v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const float dd = w * (1.0f - run[32 * c + 4 * g + e] * ic);
+                    v[e] = dd * dd;
+                }
+                if constexpr (!kFirst) { v[0] += old[g].x; v[1] += old[g].y; v[2] += old[g].z; v[3] += old[g].w; }
+                if constexpr (kLast) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) run[32 * c + 4 * g + e] = v[e];
+                } else {
+                    st_park(park + (size_t)(8 * c + g) * BM, make_float4(v[0], v[1], v[2], v[3]), pol);
+                }
             }
-            if constexpr (!kLast) tmem_st16(tpark + 16 * c, old);
         }
     }
-    if constexpr (!kLast) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
 // run[base + j] for a warp-uniform runtime j in 0..31 without local memory: 31 selects
@@ -160,7 +195,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_t1,
                 const __grid_constant__ CUtensorMap map_t2, const BatchArgs a, const float *__restrict__ inv_counts,
                 const float *__restrict__ cut_g, unsigned long long *counts_g /*[QN][2]*/, unsigned int *cand_cnt /*[QN]*/,
-                unsigned long long *cand_keys /*[QN][cap]*/,  float *scores_dbg /*[Q][n_rows] or null*/, long long *prof /*[grid][8] or null*/) {
+                unsigned long long *cand_keys /*[QN][cap]*/, float *park_g /*[grid][QN][BM], L2 park only*/, float *scores_dbg /*[Q][n_rows] or null*/, long long *prof /*[grid][8] or null*/) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + RING_END);
@@ -172,7 +207,7 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const uint32_t bar_afull = smem_u32(&bars[0]), bar_aempty = smem_u32(&bars[NA]), bar_xfull = smem_u32(&bars[2 * NA]),
                    bar_xempty = smem_u32(&bars[2 * NA + NXR]), bar_tfull = smem_u32(&bars[2 * NA + 2 * NXR]),
                    bar_tempty = smem_u32(&bars[2 * NA + 2 * NXR + NT]), bar_part_full = smem_u32(&bars[2 * NA + 2 * NXR + 2 * NT]),
-                   bar_part_empty = smem_u32(&bars[2 * NA + 2 * NXR + 2 * NT + 1]);
+                   bar_part_empty = smem_u32(&bars[2 * NA + 2 * NXR + 2 * NT + 2]);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NA; ++s) {
@@ -187,8 +222,10 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             mbar_init(bar_tfull + 8 * s, 1);            // expect_tx arrive + TMA bytes of t1, t2
             mbar_init(bar_tempty + 8 * s, 1);           // tcgen05.commit
         }
-        mbar_init(bar_part_full, 1);                    // tcgen05.commit
-        mbar_init(bar_part_empty, EPI_WARPS);           // one arrive per epilogue warp
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_part_full + 8 * b, 1);           // tcgen05.commit
+            mbar_init(bar_part_empty + 8 * b, EPI_WARPS);  // one arrive per epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     for (int i = threadIdx.x; i < QN; i += blockDim.x) cut_s[i] = cut_g[i];
@@ -204,6 +241,7 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int kbps = a.kb_per_stream;
     const int kb_total = kbps * a.n_streams;
     const int n_mma = a.n_mma;                      // queries rounded up to 16: the N of every MMA
+    constexpr int NPART = 2;                        // partial accumulators: TMEM columns 0-255 and 256-511
     // this CTA's K blocks in issue order: tiles blockIdx.x, +gridDim.x, ...; kb_total blocks each
     const int my_tiles = (a.n_tiles > (int)blockIdx.x) ? (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int n_it = my_tiles * kb_total;
@@ -214,27 +252,29 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             // ------------------------------------------------------------------ TMA producer, clip tiles (fp32)
             if (lane == 0) {
                 int it = 0;
+                const uint64_t pol = policy_evict_first();
                 for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
                     const int row = (int)(a.row0 + (long long)tile * BM);
                     for (int kb = 0; kb < kb_total; ++kb, ++it) {
                         const int s = it % NA;
                         mbar_wait(bar_aempty + 8 * s, ((it / NA) & 1) ^ 1);
                         mbar_expect(bar_afull + 8 * s, A32_BYTES);
-                        tma_load_2d(smem_base + (uint32_t)s * A32_BYTES, &map_a, kb * BK, row, bar_afull + 8 * s);
+                        tma_load_2d_hint(smem_base + (uint32_t)s * A32_BYTES, &map_a, kb * BK, row, bar_afull + 8 * s, pol);
                     }
                 }
             }
         } else if (warp == 2) {
             // ------------------------------------------------------------------ TMA producer, query tiles (t1, t2)
             if (lane == 0) {
+                const uint64_t pol = policy_evict_last();
                 for (int it = 0; it < n_it; ++it) {
                     const int s = it % NT;
                     mbar_wait(bar_tempty + 8 * s, ((it / NT) & 1) ^ 1);
                     const uint32_t base = smem_base + RING_T + (uint32_t)s * 2 * T_BYTES;
                     const int kb = it % kb_total;
                     mbar_expect(bar_tfull + 8 * s, 2 * T_BYTES);
-                    tma_load_2d(base, &map_t1, kb * BK, 0, bar_tfull + 8 * s);
-                    tma_load_2d(base + T_BYTES, &map_t2, kb * BK, 0, bar_tfull + 8 * s);
+                    tma_load_2d_hint(base, &map_t1, kb * BK, 0, bar_tfull + 8 * s, pol);
+                    tma_load_2d_hint(base + T_BYTES, &map_t2, kb * BK, 0, bar_tfull + 8 * s, pol);
                 }
             }
         } else if (warp == 1) {
@@ -256,8 +296,9 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         const bool group_last = (kb % GROUP_KB) == GROUP_KB - 1 || kb == kbps - 1;
                         long long t0 = VQ_CLOCK();
                         if (group_first) {
-                            mbar_wait(bar_part_empty, (gcount & 1) ^ 1);              // partial drained
-                            d = tmem_base;
+                            const int b = gcount % NPART;
+                            mbar_wait(bar_part_empty + 8 * b, ((gcount / NPART) & 1) ^ 1);    // partial drained
+                            d = tmem_base + (uint32_t)(b * QN);
                         }
                         long long t1 = VQ_CLOCK();
                         w_acc += t1 - t0;
@@ -284,7 +325,7 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                             }
                             umma_commit(bar_xempty + 8 * sx);                     // both operand stages are reusable once these MMAs retire
                             umma_commit(bar_tempty + 8 * stg);
-                            if (group_last) umma_commit(bar_part_full);
+                            if (group_last) umma_commit(bar_part_full + 8 * (gcount % NPART));
                         }
                         __syncwarp();
                         if (group_last) ++gcount;
@@ -362,6 +403,8 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         // 32-query chunks of this warp's half that hold live MMA columns (warp-uniform)
         const int nch = max(0, min(4, (n_mma - half * 128 + 31) / 32));
         unsigned int *my_cnt = cnt_s + ew * 128 * 2;
+        float4 *park = reinterpret_cast<float4 *>(park_g) + (size_t)blockIdx.x * (QN / 4) * BM + (size_t)(half * 32) * BM + quarter * 32 + lane;
+        const uint64_t pol_park = policy_evict_last();
         int gcount = 0;
         long long e_wait = 0, e_busy = 0, e_score = 0, e_fin0 = 0, e_fin1 = 0, e_tiles = 0;
         for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
@@ -374,11 +417,12 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 const int n_groups = (kbps + GROUP_KB - 1) / GROUP_KB;
                 for (int g = 0; g < n_groups; ++g, ++gcount) {
                     const long long t0 = VQ_CLOCK();
-                    mbar_wait(bar_part_full, gcount & 1);
+                    const int b = gcount % NPART;
+                    mbar_wait(bar_part_full + 8 * b, (gcount / NPART) & 1);
                     const long long t1 = VQ_CLOCK();
                     e_wait += t1 - t0;
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t col = tlane;
+                    const uint32_t col = tlane + (uint32_t)(b * QN);
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
                         uint32_t r0[32];
@@ -389,7 +433,7 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         if (c == 3) {                                    // partial fully read: the MMA warp may refill it
                             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                             __syncwarp();
-                            if (lane == 0) mbar_arrive(bar_part_empty);
+                            if (lane == 0) mbar_arrive(bar_part_empty + 8 * b);
                         }
                         if (c < nch) {
 #pragma unroll
@@ -404,13 +448,12 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     const float ic = (inv_counts && row_ok) ? inv_counts[row * a.n_streams + st] : a.inv_splits;
                     const float w = st == 0 ? a.w[0] : (st == 1 ? a.w[1] : (st == 2 ? a.w[2] : a.w[3]));   // no dynamic indexing: keeps `a` in the constant bank
                     const bool first = st == 0, last = st + 1 == a.n_streams;
-                    const uint32_t tpark = tlane + (uint32_t)QN;
                     if (first) {
-                        if (last) stream_final<true, true>(run, tpark, w, ic, nch);
-                        else stream_final<true, false>(run, tpark, w, ic, nch);
+                        if (last) stream_final<true, true>(run, park, pol_park, w, ic, nch);
+                        else stream_final<true, false>(run, park, pol_park, w, ic, nch);
                     } else {
-                        if (last) stream_final<false, true>(run, tpark, w, ic, nch);
-                        else stream_final<false, false>(run, tpark, w, ic, nch);
+                        if (last) stream_final<false, true>(run, park, pol_park, w, ic, nch);
+                        else stream_final<false, false>(run, park, pol_park, w, ic, nch);
                     }
                     if (last) e_fin1 += VQ_CLOCK() - t1;
                     else e_fin0 += VQ_CLOCK() - t1;
