@@ -38,10 +38,13 @@ def batched(n=10_000_000, Q=256):
     rows = REF + np.arange(Q) * 37
     X = synth.rows(SEED, rows).astype(np.float64)[:, :, None, :]
     T = np.stack([sc.scale_target(x) for x in X]).astype(np.float32)
-    best = None
-    for _ in range(3):
+    best, best_call = None, None
+    for _ in range(4):
+        t0 = time.perf_counter()
         counts, r, s, ms = st.scan_batch(T, (1.0, 1.5), 0.8, 0.73, topk=100)
+        call = (time.perf_counter() - t0) * 1e3
         best = ms if best is None else min(best, ms)
+        best_call = call if best_call is None else min(best_call, call)
     # spot check query 0 against float64 on regenerated rows: its top-10 and a sample
     chk = np.unique(np.concatenate([r[0][:10], np.arange(0, n, max(n // 2000, 1))]))
     Xc = synth.rows(SEED, chk).astype(np.float64)[:, :, None, :]
@@ -52,7 +55,7 @@ def batched(n=10_000_000, Q=256):
     pk = peaks()
     bf16_peak, bf16_sustained = pk.get("bf16_tflops", 1590.0), pk.get("bf16_tflops_sustained", 1400.0)
     out = {"config": "configs[3]: batched %d-query scoring vs %d clips as tcgen05 GEMM + fused top-k" % (Q, n),
-           "kernel_ms": best, "clips_x_queries_per_s": n * Q / best * 1e3,
+           "kernel_ms": best, "call_ms_host_buffers_in_and_out": best_call, "clips_x_queries_per_s": n * Q / best * 1e3,
            "algorithmic_tflops": flops / best / 1e9, "executed_tflops_bf16x2": 3 * flops / best / 1e9,
            "executed_vs_measured_bf16_burst": 3 * flops / best / 1e9 / bf16_peak,
            "executed_vs_measured_bf16_sustained": 3 * flops / best / 1e9 / bf16_sustained,

@@ -125,6 +125,43 @@ struct Dev {
     template <class T> T *as() { return reinterpret_cast<T *>(p); }
 };
 
+// Scratch of the batched path, owned by the store: allocated on the first batched scan, reused by every later one.
+struct BatchScratch {
+    Dev t, t1, t2, cut, counts, cnt, keys, rows, sc, park;
+    void *pinned_t = nullptr;            // pinned staging for one pass of targets
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ~BatchScratch() {
+        if (pinned_t) cudaFreeHost(pinned_t);
+        if (e0) cudaEventDestroy(e0);
+        if (e1) cudaEventDestroy(e1);
+    }
+};
+void free_batch_scratch(void *p) { delete static_cast<BatchScratch *>(p); }
+
+int get_batch_scratch(vq_store *s, size_t K, long long cap, BatchScratch **out) {
+    constexpr int QN = bf::QN;
+    if (!s->batch_scratch) {
+        BatchScratch *b = new BatchScratch();
+        s->batch_scratch = b;
+        s->batch_scratch_free = free_batch_scratch;
+        VQ_CUDA(b->t.alloc((size_t)QN * K * 4));
+        VQ_CUDA(b->t1.alloc((size_t)QN * K * 2));
+        VQ_CUDA(b->t2.alloc((size_t)QN * K * 2));
+        VQ_CUDA(b->cut.alloc(QN * 4));
+        VQ_CUDA(b->counts.alloc(QN * 2 * 8));
+        VQ_CUDA(b->cnt.alloc(QN * 4));
+        VQ_CUDA(b->keys.alloc((size_t)QN * cap * 8));
+        VQ_CUDA(b->rows.alloc((size_t)QN * VQ_MAX_TOPK * 8));
+        VQ_CUDA(b->sc.alloc((size_t)QN * VQ_MAX_TOPK * 4));
+        VQ_CUDA(b->park.alloc((size_t)s->sm_count * QN * bf::BM * 4));
+        VQ_CUDA(cudaMallocHost(&b->pinned_t, (size_t)QN * K * 4));
+        VQ_CUDA(cudaEventCreate(&b->e0));
+        VQ_CUDA(cudaEventCreate(&b->e1));
+    }
+    *out = static_cast<BatchScratch *>(s->batch_scratch);
+    return 0;
+}
+
 // The batched path: bf16x2 kernel (vq_batch_bf16.cuh), 256 queries per pass over the shard.
 int run_batch_bf16(vq_store *s, const float *targets, int n_queries, const vq_scan_params *p, int64_t *counts_out,
                    int64_t *topk_rows_out, float *topk_scores_out, float *kernel_ms_out, float *scores_dbg_host) {
@@ -147,29 +184,22 @@ int run_batch_bf16(vq_store *s, const float *targets, int n_queries, const vq_sc
     const long long chunk_rows = (long long)s->sm_count * bf::BM * 16;
     const long long cap = chunk_rows + VQ_MAX_TOPK;
     VQ_CUDA(cudaFuncSetAttribute(bf::batch_scan_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf::SMEM));
-    Dev d_t, d_t1, d_t2, d_cut, d_counts, d_cnt, d_keys, d_rows, d_sc, d_dbg, d_prof, d_park;
-    VQ_CUDA(d_t.alloc((size_t)QN * K * 4));
-    VQ_CUDA(d_t1.alloc((size_t)QN * K * 2));
-    VQ_CUDA(d_t2.alloc((size_t)QN * K * 2));
-    VQ_CUDA(d_cut.alloc(QN * 4));
-    VQ_CUDA(d_counts.alloc(QN * 2 * 8));
-    VQ_CUDA(d_cnt.alloc(QN * 4));
-    VQ_CUDA(d_keys.alloc((size_t)QN * cap * 8));
-    VQ_CUDA(d_rows.alloc((size_t)QN * (topk ? topk : 1) * 8));
-    VQ_CUDA(d_sc.alloc((size_t)QN * (topk ? topk : 1) * 4));
+    BatchScratch *bs = nullptr;
+    if (int r = get_batch_scratch(s, K, cap, &bs)) return r;
+    Dev &d_t = bs->t, &d_t1 = bs->t1, &d_t2 = bs->t2, &d_cut = bs->cut, &d_counts = bs->counts, &d_cnt = bs->cnt,
+        &d_keys = bs->keys, &d_rows = bs->rows, &d_sc = bs->sc, &d_park = bs->park;
+    Dev d_dbg, d_prof;
     if (scores_dbg_host) VQ_CUDA(d_dbg.alloc((size_t)QN * s->n_rows * 4));
-    VQ_CUDA(d_park.alloc((size_t)s->sm_count * QN * bf::BM * 4));
     const bool want_prof = getenv("VQ_BATCH_PROF") != nullptr;
     if (want_prof) VQ_CUDA(d_prof.alloc((size_t)s->sm_count * 16 * 8));
-    cudaEvent_t e0, e1;
-    VQ_CUDA(cudaEventCreate(&e0));
-    VQ_CUDA(cudaEventCreate(&e1));
+    cudaEvent_t e0 = bs->e0, e1 = bs->e1;
     float total_ms = 0.f;
     int rc = 0;
     for (int q0 = 0; q0 < n_queries && rc == 0; q0 += QN) {
         const int nq = (n_queries - q0 < QN) ? (n_queries - q0) : QN;
-        VQ_CUDA(cudaMemsetAsync(d_t.p, 0, (size_t)QN * K * 4, st));
-        VQ_CUDA(cudaMemcpyAsync(d_t.p, targets + (size_t)q0 * K, (size_t)nq * K * 4, cudaMemcpyHostToDevice, st));
+        if (nq < QN) VQ_CUDA(cudaMemsetAsync(d_t.p, 0, (size_t)QN * K * 4, st));
+        memcpy(bs->pinned_t, targets + (size_t)q0 * K, (size_t)nq * K * 4);       // caller memory may be pageable
+        VQ_CUDA(cudaMemcpyAsync(d_t.p, bs->pinned_t, (size_t)nq * K * 4, cudaMemcpyHostToDevice, st));
         bf::split_targets_bf16<<<(unsigned)(((size_t)QN * K + 255) / 256), 256, 0, st>>>(
             d_t.as<float>(), d_t1.as<unsigned short>(), d_t2.as<unsigned short>(), (long long)QN * K);
         fill_f32<<<1, QN, 0, st>>>(d_cut.as<float>(), topk > 0 ? -INFINITY : INFINITY, QN);   // no top-k: nothing is a candidate
@@ -246,8 +276,6 @@ int run_batch_bf16(vq_store *s, const float *targets, int n_queries, const vq_sc
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) total_ms += ms;
     }
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     if (kernel_ms_out) *kernel_ms_out = total_ms;
     return rc;
 }

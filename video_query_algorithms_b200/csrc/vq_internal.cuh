@@ -89,4 +89,7 @@ struct vq_store {
     float *h_topk_scores = nullptr;
     int64_t *h_result = nullptr;     // pinned [8]: n_match n_near n_tie n_topk overflow
     bool staged = false;
+    // scratch of the batched path (vq_batch.cu), allocated on its first call and kept: a batched scan allocates nothing
+    void *batch_scratch = nullptr;
+    void (*batch_scratch_free)(void *) = nullptr;
 };

@@ -60,6 +60,8 @@ static void store_free(vq_store *s) {
         if (s->h_rows[i]) cudaFreeHost(s->h_rows[i]);
         if (s->h_scores[i]) cudaFreeHost(s->h_scores[i]);
     }
+    if (s->batch_scratch && s->batch_scratch_free) s->batch_scratch_free(s->batch_scratch);
+    s->batch_scratch = nullptr;
     if (s->h_result) cudaFreeHost(s->h_result);
     if (s->h_topk_rows) cudaFreeHost(s->h_topk_rows);
     if (s->h_topk_scores) cudaFreeHost(s->h_topk_scores);
