@@ -46,6 +46,11 @@ int vq_device_count(int *count_out);
 int vq_store_create(vq_store **out, int device, int64_t n_rows, int n_streams, int n_splits,
                     int dim, int64_t first_global_row);
 int vq_store_destroy(vq_store *s);
+/* Incremental growth (load_db.py adds clips to a search set, reference load_db.py:10-28): append n_new rows after the
+ * last row of the shard; the buffers grow geometrically (vq_store_reserve pre-sizes them).  Per-row split weights set
+ * with vq_store_set_split_weights are dropped by an append and must be set again for the grown shard.              */
+int vq_store_reserve(vq_store *s, int64_t capacity);
+int vq_store_append(vq_store *s, int64_t n_new, const float *rows /* [n_new][n_streams][n_splits][dim] host */);
 int vq_store_describe(const vq_store *s, int64_t *n_rows, int *n_streams, int *n_splits, int *dim,
                       int64_t *first_global_row, int *device);
 /* rows: [n_rows][n_streams][n_splits][dim] fp32, local row range.  Pinned memory is copied

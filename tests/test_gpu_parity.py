@@ -213,6 +213,63 @@ def test_two_shards_merge_like_one(vq):
     two.close()
 
 
+def test_append_grows_the_store_like_a_rebuild(vq):
+    """Incremental growth (load_db.py adds clips): a store filled by three appends (two of them re-allocating)
+    scans, ranks and batch-scans exactly like a store built in one upload; split weights follow."""
+    rng = np.random.default_rng(12)
+    n0, adds, S, P, dim = 700, (1, 900, 5000), 2, 2, 256
+    n = n0 + sum(adds)
+    X = (rng.random((n, S, P, dim)) * rng.random((n, 1, 1, 1)) * 2).astype(np.float32)
+    present = rng.random((n, S, P)) > 0.15
+    present[:, :, 0] = True                                   # every clip keeps at least one split per stream
+    X[~present] = 0
+    ids = np.arange(n) * 3 + 11
+    full = vq.FeatureStore(n, ("a", "b"), [1, 2], dim, devices=[0], clip_ids=ids)
+    full.upload(0, X)
+    full.set_present(present)
+    grown = vq.FeatureStore(n0, ("a", "b"), [1, 2], dim, devices=[0], clip_ids=ids[:n0])
+    grown.upload(0, X[:n0])
+    grown.set_present(present[:n0])
+    at = n0
+    for k in adds:
+        grown.append(X[at:at + k], clip_ids=ids[at:at + k], present=present[at:at + k])
+        at += k
+    assert grown.n_rows == n and grown.row_of(ids[-1]) == n - 1
+    with pytest.raises(vq.VQError):
+        grown.append(X[:1], clip_ids=ids[:1])                  # id already present
+    ref = int(np.flatnonzero(present.all(axis=(1, 2)))[0])          # a reference clip with every split
+    T = sc.scale_target(X[ref].astype(np.float64))
+    td = {s: {p: T[si, pi] for pi, p in enumerate([1, 2])} for si, s in enumerate(("a", "b"))}
+    ra = full.scan(td, (1.0, 1.5), 0.6, 0.5, EPS, topk=40)
+    rb = grown.scan(td, (1.0, 1.5), 0.6, 0.5, EPS, topk=40)
+    assert (ra.n_match, ra.n_near, ra.n_tie) == (rb.n_match, rb.n_near, rb.n_tie)
+    assert np.array_equal(full.scores(), grown.scores())
+    for f in ("matches", "near_misses", "topk"):
+        a, b = getattr(full, f)(), getattr(grown, f)()
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    assert np.array_equal(full.download(0, n), grown.download(0, n))
+    T32 = T[None].astype(np.float32)
+    assert np.array_equal(full.scan_batch(T32, (1.0, 1.5), 0.6, 0.5, debug_scores=True),
+                          grown.scan_batch(T32, (1.0, 1.5), 0.6, 0.5, debug_scores=True))
+    full.close()
+    grown.close()
+    # the same through the API-response path: a store built from the first clips + append_feature_rows(all rows)
+    def feats(clips):
+        return [{"dnn_stream_id": s, "dnn_stream_split": p, "name": "global_pool", "video_clip_id": int(ids[c]),
+                 "feature_vector": X[c, si, pi].tolist()}
+                for c in clips for si, s in enumerate(("a", "b")) for pi, p in enumerate([1, 2]) if present[c, si, pi]]
+    some, more = list(range(40)), list(range(25, 90))
+    one = vq.FeatureStore.from_feature_rows(feats(list(range(90))), ("a", "b"), "global_pool", devices=[0])
+    two = vq.FeatureStore.from_feature_rows(feats(some), ("a", "b"), "global_pool", devices=[0])
+    assert two.append_feature_rows(feats(more), "global_pool") == 50 and two.n_rows == 90
+    assert np.array_equal(one.clip_ids, two.clip_ids) and np.array_equal(one.download(0, 90), two.download(0, 90))
+    one.scan(td, (1.0, 1.5), 0.6, 0.5, EPS, topk=10)
+    two.scan(td, (1.0, 1.5), 0.6, 0.5, EPS, topk=10)
+    assert np.array_equal(one.scores(), two.scores())
+    one.close()
+    two.close()
+
+
 # ---------------------------------------------------------------------------- batched queries (tcgen05)
 @pytest.mark.parametrize("n,nq", [(5003, 70), (300, 3), (20000, 300)])
 def test_batched_tensor_core_scan_matches_oracle(vq, n, nq):

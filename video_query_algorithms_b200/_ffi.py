@@ -43,6 +43,8 @@ PROTOTYPES = {
     "vq_device_count": (C.c_int, [_P(C.c_int)]),
     "vq_store_create": (C.c_int, [_P(_vp), C.c_int, _i64, C.c_int, C.c_int, C.c_int, _i64]),
     "vq_store_destroy": (C.c_int, [_vp]),
+    "vq_store_reserve": (C.c_int, [_vp, _i64]),
+    "vq_store_append": (C.c_int, [_vp, _i64, _vp]),
     "vq_store_describe": (C.c_int, [_vp, _i64p, _P(C.c_int), _P(C.c_int), _P(C.c_int), _i64p, _P(C.c_int)]),
     "vq_store_upload": (C.c_int, [_vp, _i64, _i64, _vp]),
     "vq_store_download": (C.c_int, [_vp, _i64, _i64, _vp]),

@@ -50,6 +50,7 @@ struct ScanArgs {
 struct vq_store {
     int device = 0;
     int64_t n_rows = 0, first_global_row = 0;
+    int64_t capacity = 0;            // rows the buffers are allocated for (>= n_rows; grows with vq_store_append)
     int n_streams = 0, n_splits = 0, dim = 0, stream_len = 0;   // stream_len = n_splits * dim
     size_t row_floats = 0;
     int sm_count = 0;

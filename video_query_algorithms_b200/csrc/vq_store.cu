@@ -74,6 +74,34 @@ static void store_free(vq_store *s) {
     delete s;
 }
 
+// Everything sized by the row capacity: the rows themselves and the per-row scratch of the scan.  Called at create
+// time and by vq_store_reserve (which moves the rows over and swaps the scratch).
+static int alloc_row_buffers(vq_store *s, int64_t capacity) {
+    const size_t nr = (size_t)capacity;
+    const size_t nc = (size_t)((capacity + vq::kChunkRows - 1) / vq::kChunkRows);
+#define VQ_ALLOC(ptr, bytes)                                                              \
+    do {                                                                                  \
+        cudaError_t e2 = cudaMalloc((void **)&(ptr), (bytes));                            \
+        if (e2 != cudaSuccess) {                                                          \
+            vq::set_error("vq_store: cudaMalloc(%zu bytes) for %s -> %s", (size_t)(bytes), #ptr, cudaGetErrorString(e2)); \
+            return -3;                                                                    \
+        }                                                                                 \
+    } while (0)
+    VQ_ALLOC(s->rows, nr * s->row_floats * sizeof(float));
+    VQ_ALLOC(s->scores, nr * sizeof(float));
+    VQ_ALLOC(s->chunk_counts, 3 * nc * sizeof(unsigned int));
+    VQ_ALLOC(s->chunk_offsets, 3 * nc * sizeof(unsigned int));
+    for (int i = 0; i < 3; ++i) {
+        VQ_ALLOC(s->list_rows[i], nr * sizeof(uint32_t));
+        VQ_ALLOC(s->list_scores[i], nr * sizeof(float));
+    }
+    VQ_ALLOC(s->cand_keys, nr * sizeof(unsigned long long));
+#undef VQ_ALLOC
+    s->cand_cap = (int64_t)nr;
+    s->capacity = capacity;
+    return 0;
+}
+
 extern "C" int vq_store_create(vq_store **out, int device, int64_t n_rows, int n_streams,
                                int n_splits, int dim, int64_t first_global_row) {
     VQ_REQUIRE(out, "vq_store_create: null output");
@@ -100,9 +128,15 @@ extern "C" int vq_store_create(vq_store **out, int device, int64_t n_rows, int n
     cudaDeviceProp prop;
     cudaError_t e = cudaGetDeviceProperties(&prop, device);
     s->sm_count = (e == cudaSuccess) ? prop.multiProcessorCount : 148;
-    const size_t nr = (size_t)(n_rows > 0 ? n_rows : 1);
-    const size_t nc = (size_t)(s->n_chunks > 0 ? s->n_chunks : 1);
-    s->cand_cap = (int64_t)nr;
+    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        vq::set_error("vq_store_create: cudaStreamCreate failed");
+        store_free(s);
+        return -2;
+    }
+    if (int r = alloc_row_buffers(s, n_rows > 0 ? n_rows : 1)) {
+        store_free(s);
+        return r;
+    }
 #define VQ_ALLOC(ptr, bytes)                                                              \
     do {                                                                                  \
         cudaError_t e2 = cudaMalloc((void **)&(ptr), (bytes));                            \
@@ -113,24 +147,10 @@ extern "C" int vq_store_create(vq_store **out, int device, int64_t n_rows, int n
             return -3;                                                                    \
         }                                                                                 \
     } while (0)
-    if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) {
-        vq::set_error("vq_store_create: cudaStreamCreate failed");
-        store_free(s);
-        return -2;
-    }
-    VQ_ALLOC(s->rows, nr * s->row_floats * sizeof(float));
     VQ_ALLOC(s->target, s->row_floats * sizeof(float));
-    VQ_ALLOC(s->scores, nr * sizeof(float));
     VQ_ALLOC(s->hist, (vq::kHistBins + 8) * sizeof(unsigned int));
-    VQ_ALLOC(s->chunk_counts, 3 * nc * sizeof(unsigned int));
-    VQ_ALLOC(s->chunk_offsets, 3 * nc * sizeof(unsigned int));
     VQ_ALLOC(s->counts, 4 * sizeof(int64_t));
-    for (int i = 0; i < 3; ++i) {
-        VQ_ALLOC(s->list_rows[i], nr * sizeof(uint32_t));
-        VQ_ALLOC(s->list_scores[i], nr * sizeof(float));
-    }
     VQ_ALLOC(s->cand_count, 4 * sizeof(unsigned int));
-    VQ_ALLOC(s->cand_keys, (size_t)s->cand_cap * sizeof(unsigned long long));
     VQ_ALLOC(s->topk_scores, VQ_MAX_TOPK * sizeof(float));
     VQ_ALLOC(s->topk_rows, VQ_MAX_TOPK * sizeof(int64_t));
     VQ_ALLOC(s->pack, (4 + 2 * VQ_MAX_TOPK) * sizeof(int64_t));
@@ -157,6 +177,56 @@ extern "C" int vq_store_create(vq_store **out, int device, int64_t n_rows, int n
 extern "C" int vq_store_destroy(vq_store *s) {
     store_free(s);
     return 0;
+}
+
+extern "C" int vq_store_reserve(vq_store *s, int64_t capacity) {
+    VQ_REQUIRE(s, "vq_store_reserve: null store");
+    VQ_REQUIRE(capacity < (int64_t)0xFFFFFFF0u, "vq_store_reserve: capacity %lld out of range", (long long)capacity);
+    if (capacity <= s->capacity) return 0;
+    VQ_CUDA(cudaSetDevice(s->device));
+    VQ_CUDA(cudaStreamSynchronize(s->stream));
+    // keep the old buffers until the new ones exist: a failed reservation leaves the store as it was
+    vq_store old = *s;
+    s->rows = nullptr; s->scores = nullptr; s->chunk_counts = nullptr; s->chunk_offsets = nullptr; s->cand_keys = nullptr;
+    for (int i = 0; i < 3; ++i) { s->list_rows[i] = nullptr; s->list_scores[i] = nullptr; }
+    if (int r = alloc_row_buffers(s, capacity)) {
+        cudaFree(s->rows); cudaFree(s->scores); cudaFree(s->chunk_counts); cudaFree(s->chunk_offsets); cudaFree(s->cand_keys);
+        for (int i = 0; i < 3; ++i) { cudaFree(s->list_rows[i]); cudaFree(s->list_scores[i]); }
+        s->rows = old.rows; s->scores = old.scores; s->chunk_counts = old.chunk_counts; s->chunk_offsets = old.chunk_offsets;
+        s->cand_keys = old.cand_keys; s->cand_cap = old.cand_cap; s->capacity = old.capacity;
+        for (int i = 0; i < 3; ++i) { s->list_rows[i] = old.list_rows[i]; s->list_scores[i] = old.list_scores[i]; }
+        return r;
+    }
+    if (s->n_rows > 0)
+        VQ_CUDA(cudaMemcpyAsync(s->rows, old.rows, (size_t)s->n_rows * s->row_floats * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+    VQ_CUDA(cudaStreamSynchronize(s->stream));
+    cudaFree(old.rows); cudaFree(old.scores); cudaFree(old.chunk_counts); cudaFree(old.chunk_offsets); cudaFree(old.cand_keys);
+    for (int i = 0; i < 3; ++i) { cudaFree(old.list_rows[i]); cudaFree(old.list_scores[i]); }
+    if (s->sims) { cudaFree(s->sims); s->sims = nullptr; }      // re-allocated by the next want_sims scan
+    s->staged = false;
+    return 0;
+}
+
+extern "C" int vq_store_append(vq_store *s, int64_t n_new, const float *rows) {
+    VQ_REQUIRE(s, "vq_store_append: null store");
+    VQ_REQUIRE(n_new >= 0 && (rows || n_new == 0), "vq_store_append: bad argument");
+    if (n_new == 0) return 0;
+    const int64_t need = s->n_rows + n_new;
+    if (need > s->capacity) {                           // grow geometrically: amortised O(1) copies per appended row
+        int64_t cap = s->capacity + s->capacity / 2;
+        if (cap < need) cap = need;
+        if (int r = vq_store_reserve(s, cap)) return r;
+    }
+    const int64_t first = s->n_rows;
+    s->n_rows = need;
+    s->n_chunks = (s->n_rows + vq::kChunkRows - 1) / vq::kChunkRows;
+    if (s->inv_counts) {                                // per-row split weights no longer cover the shard: the caller sets them again
+        cudaFree(s->inv_counts);
+        s->inv_counts = nullptr;
+    }
+    if (s->sims) { cudaFree(s->sims); s->sims = nullptr; }
+    s->staged = false;
+    return vq_store_upload(s, first, n_new, rows);
 }
 
 extern "C" int vq_store_describe(const vq_store *s, int64_t *n_rows, int *n_streams, int *n_splits,

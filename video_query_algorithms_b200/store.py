@@ -168,6 +168,66 @@ class FeatureStore:
             part = np.ascontiguousarray(inv[lo:lo + sh.n_rows])
             check(lib().vq_store_set_split_weights(sh.handle, ptr(part)), "vq_store_set_split_weights")
 
+    # ------------------------------------------------------------------ incremental growth
+    def append(self, rows, clip_ids=None, present=None):
+        """Append clips after the last row (load_db.py adds clips to a search set, reference load_db.py:10-28).
+        rows: float32 [n, S, P, dim]; clip_ids: their ids (required when the store has an id table);
+        present: bool [n, S, P] when some new clip lacks some split.  The last shard grows (geometric
+        reallocation inside the library), everything resident stays resident."""
+        rows = np.ascontiguousarray(rows, dtype=np.float32).reshape(-1, int(np.prod(self.row_shape)))
+        n_new = rows.shape[0]
+        if n_new == 0:
+            return
+        if self.clip_ids is not None:
+            if clip_ids is None or len(clip_ids) != n_new:
+                raise VQError("append: the store has a clip-id table; pass the %d new clip ids" % n_new)
+            new_ids = np.asarray(clip_ids, dtype=np.int64)
+            known = self._index()
+            dup = [int(c) for c in new_ids if int(c) in known]
+            if dup or len(set(new_ids.tolist())) != n_new:
+                raise VQError("append: clip ids already in the store or repeated: %s" % (dup[:5] or "repeated ids"))
+        sh = self.shards[-1]
+        check(lib().vq_store_append(sh.handle, n_new, ptr(rows)), "vq_store_append")
+        sh.n_rows += n_new
+        self.n_rows += n_new
+        if self.clip_ids is not None:
+            self.clip_ids = np.concatenate([self.clip_ids, new_ids])
+            self._row_of = None
+        if self.present is not None or present is not None:
+            old = self.present if self.present is not None else np.ones((self.n_rows - n_new,) + self.row_shape[:2], bool)
+            new = np.ones((n_new,) + self.row_shape[:2], bool) if present is None else np.asarray(present, dtype=bool)
+            self._eff_key = None
+            self.set_present(np.concatenate([old, new]))
+        self.last = None
+
+    def append_feature_rows(self, feature_rows, feature_name):
+        """Append the clips of a `search-sets/features`-style response that the store does not hold yet (same
+        filters and first-appearance order as from_feature_rows); returns the number of clips added."""
+        s_of = {s: i for i, s in enumerate(self.streams)}
+        p_of = {p: i for i, p in enumerate(self.splits)}
+        order, seen = [], set()
+        for tf in feature_rows:
+            if tf["dnn_stream_id"] in s_of and tf["name"] == feature_name:
+                c = tf["video_clip_id"]
+                if c not in seen and not self.has_clip(c):
+                    seen.add(c)
+                    order.append(c)
+        if not order:
+            return 0
+        row = {c: i for i, c in enumerate(order)}
+        X = np.zeros((len(order),) + self.row_shape, np.float32)
+        present = np.zeros((len(order),) + self.row_shape[:2], bool)
+        for tf in feature_rows:
+            if tf["dnn_stream_id"] in s_of and tf["name"] == feature_name and tf["video_clip_id"] in row:
+                p = int(tf["dnn_stream_split"])
+                if p not in p_of:
+                    raise VQError("append_feature_rows: split %d is not one of the store's splits %s" % (p, self.splits))
+                i, si, pi = row[tf["video_clip_id"]], s_of[tf["dnn_stream_id"]], p_of[p]
+                X[i, si, pi] = tf["feature_vector"]
+                present[i, si, pi] = True
+        self.append(X, clip_ids=order, present=present)
+        return len(order)
+
     def fill_synthetic(self, seed, means=None):
         m = None if means is None else np.asarray(means, dtype=np.float32)
         for sh in self.shards:
