@@ -101,6 +101,9 @@ int vq_fetch_topk(vq_store *s, int32_t cap, int64_t *rows_out, float *scores_out
  * 1 near misses, 2 tie band, 3 top-k; rows are GLOBAL, lists in database order (top-k ranked).
  * Valid until the next scan on this store; the caller must not free or write it.             */
 int vq_scan_host_list(vq_store *s, int32_t which, const int64_t **rows, const float **scores, int64_t *n);
+/* Full ranking of a list of the last scan (which = 0 matches, 1 near misses), sorted on the device: score descending,
+ * database order among equal scores (the report order of ticket.py:266).                                         */
+int vq_fetch_ranked(vq_store *s, int32_t which, int64_t cap, int64_t *rows_out, float *scores_out);
 int vq_fetch_scores(vq_store *s, int64_t first_row, int64_t n_rows, float *scores_out);
 int vq_fetch_sims(vq_store *s, int64_t first_row, int64_t n_rows, float *sims_out);
 

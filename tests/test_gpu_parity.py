@@ -120,6 +120,31 @@ def test_topk_with_massive_ties_keeps_database_order(vq):
     st.close()
 
 
+@pytest.mark.parametrize("n", [3000, 70001])
+def test_full_ranking_of_the_match_list(vq, n):
+    """Finalize-round ranking on the device (vq_fetch_ranked): the whole match / near-miss list by score descending,
+    database order among equal scores — with heavy ties (scores quantised by construction) and list lengths that
+    are not powers of two, below and above one 2048-key sort tile."""
+    rng = np.random.default_rng(n)
+    base = synth.database(21, 64)                              # 64 distinct clips, each repeated many times -> ties
+    pick = rng.integers(0, 64, n)
+    X = base[pick][:, :, None, :]
+    st = vq.FeatureStore(n, STREAMS, [1], 1024, devices=[0])
+    st.upload(0, X)
+    T = sc.scale_target(base[7].astype(np.float64)[:, None, :])
+    res = st.scan(tdict(T), (1.0, 1.5), 0.62, 0.55, EPS, topk=10)
+    assert max(res.n_match, res.n_near) > 4 * 2048 or n < 5000     # several sort tiles and global steps
+    got = st.scores()
+    for which, (rows, sc_) in (("matches", st.matches()), ("near_misses", st.near_misses())):
+        r, s_ = st.ranked(which)
+        order = np.lexsort((rows, -sc_.astype(np.float64)))    # score descending, row ascending
+        assert np.array_equal(r, rows[order]) and np.array_equal(s_, sc_[order])
+        assert np.array_equal(s_, got[r])
+    m2 = st.matches(copy=False)                                # the database-order mirror is untouched by the ranking
+    assert np.array_equal(m2[0], np.flatnonzero(got.astype(np.float64) >= 0.62))
+    st.close()
+
+
 def test_scan_handles_empty_store(vq):
     st = vq.FeatureStore(0, STREAMS, [1], 1024, devices=[0])
     T = np.ones((2, 1, 1024))

@@ -59,6 +59,7 @@ PROTOTYPES = {
     "vq_fetch_ties": (C.c_int, [_vp, _i64, _vp, _vp]),
     "vq_fetch_topk": (C.c_int, [_vp, _i32, _vp, _vp]),
     "vq_scan_host_list": (C.c_int, [_vp, _i32, _P(_vp), _P(_vp), _i64p]),
+    "vq_fetch_ranked": (C.c_int, [_vp, _i32, _i64, _vp, _vp]),
     "vq_fetch_scores": (C.c_int, [_vp, _i64, _i64, _vp]),
     "vq_fetch_sims": (C.c_int, [_vp, _i64, _i64, _vp]),
     "vq_scan_view": (C.c_int, [_vp, _P(ScanDeviceView)]),

@@ -89,6 +89,9 @@ struct vq_store {
     int64_t *h_topk_rows = nullptr;
     float *h_topk_scores = nullptr;
     int64_t *h_result = nullptr;     // pinned [8]: n_match n_near n_tie n_topk overflow
+    int64_t *h_rank_rows = nullptr;  // pinned staging of vq_fetch_ranked
+    float *h_rank_scores = nullptr;
+    int64_t h_rank_cap = 0;
     bool staged = false;
     // scratch of the batched path (vq_batch.cu), allocated on its first call and kept: a batched scan allocates nothing
     void *batch_scratch = nullptr;

@@ -786,6 +786,131 @@ extern "C" int vq_fetch_topk(vq_store *s, int32_t cap, int64_t *rows_out, float 
     return 0;
 }
 
+// ------------------------------------------------------------------------------ full ranking of a list
+// GPU-side ranking for the finalize round (ticket.py:266: the report lists every selected clip by score, descending):
+// bitonic sort of the list's 64-bit (score, ~row) keys — the same keys as the top-k, so equal scores keep database
+// order.  All compare-exchanges run in one direction (mirror step + xor steps), so a list whose length is not a
+// power of two needs no padding: a missing partner is the smallest key and never moves.  Steps with partner distance
+// < 2048 are fused in shared memory (one 2048-key tile per block); the cand_keys scratch of the scan holds the keys.
+namespace {
+
+constexpr int kSortTile = 2048;
+
+__device__ __forceinline__ void cmpx(unsigned long long &a, unsigned long long &b) {
+    if (a < b) { const unsigned long long t = a; a = b; b = t; }
+}
+
+__global__ void rank_make_keys(const unsigned int *__restrict__ rows, const float *__restrict__ scores, long long n,
+                               unsigned long long *keys) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = vq::make_key(scores[i], rows[i]);
+}
+
+// tile-local steps: full = every size 2..2048 from scratch; otherwise the tail (strides 1024..1) of one larger size
+__global__ void __launch_bounds__(kSortTile / 2)
+rank_sort_tile(unsigned long long *keys, long long n, bool full) {
+    __shared__ unsigned long long t[kSortTile];
+    const long long base = (long long)blockIdx.x * kSortTile;
+    for (int i = threadIdx.x; i < kSortTile; i += blockDim.x) t[i] = (base + i < n) ? keys[base + i] : 0ull;
+    __syncthreads();
+    const int tid = threadIdx.x;
+    if (full) {
+        for (int size = 2; size <= kSortTile; size <<= 1) {
+            {   // mirror step: i <-> i ^ (size - 1) inside each block of `size`
+                const int blk = tid / (size / 2), off = tid % (size / 2);
+                const int i = blk * size + off, j = blk * size + size - 1 - off;
+                cmpx(t[i], t[j]);
+                __syncthreads();
+            }
+            for (int stride = size / 4; stride > 0; stride >>= 1) {
+                const int i = 2 * tid - (tid & (stride - 1));
+                cmpx(t[i], t[i + stride]);
+                __syncthreads();
+            }
+        }
+    } else {
+        for (int stride = kSortTile / 2; stride > 0; stride >>= 1) {
+            const int i = 2 * tid - (tid & (stride - 1));
+            cmpx(t[i], t[i + stride]);
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < kSortTile; i += blockDim.x)
+        if (base + i < n) keys[base + i] = t[i];
+}
+
+// one global step: mirror (j = i ^ (size - 1)) or xor (j = i ^ stride); pair index p enumerates the lower partners
+__global__ void rank_sort_step(unsigned long long *keys, long long n, long long size, long long stride, bool mirror) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long i, j;
+    if (mirror) {
+        const long long blk = p / (size / 2), off = p % (size / 2);
+        i = blk * size + off;
+        j = blk * size + size - 1 - off;
+    } else {
+        i = 2 * p - (p & (stride - 1));
+        j = i + stride;
+    }
+    if (j < n) {                                        // a partner past the end is the smallest key: nothing moves
+        unsigned long long a = keys[i], b = keys[j];
+        if (a < b) { keys[i] = b; keys[j] = a; }
+    }
+}
+
+__global__ void rank_unpack(const unsigned long long *__restrict__ keys, long long n, long long first_global_row,
+                            long long *rows_out, float *scores_out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        rows_out[i] = first_global_row + (long long)vq::key_row(keys[i]);
+        scores_out[i] = vq::key_score(keys[i]);
+    }
+}
+
+}  // namespace
+
+extern "C" int vq_fetch_ranked(vq_store *s, int32_t which, int64_t cap, int64_t *rows_out, float *scores_out) {
+    VQ_REQUIRE(s && rows_out && scores_out, "vq_fetch_ranked: null argument");
+    VQ_REQUIRE(which == 0 || which == 1, "vq_fetch_ranked: list %d (0 = matches, 1 = near misses)", which);
+    VQ_CUDA(cudaSetDevice(s->device));
+    const int64_t n = s->counts_host[which];
+    VQ_REQUIRE(cap >= n, "vq_fetch_ranked: capacity %lld < %lld entries", (long long)cap, (long long)n);
+    if (n == 0) return 0;
+    VQ_REQUIRE(n <= s->cand_cap, "vq_fetch_ranked: list longer than the key scratch");
+    cudaStream_t st = s->stream;
+    unsigned long long *keys = s->cand_keys;           // free between scans (the top-k pass has consumed it)
+    const unsigned int nb = (unsigned int)((n + 255) / 256);
+    rank_make_keys<<<nb, 256, 0, st>>>(s->list_rows[which], s->list_scores[which], n, keys);
+    const unsigned int tiles = (unsigned int)((n + kSortTile - 1) / kSortTile);
+    rank_sort_tile<<<tiles, kSortTile / 2, 0, st>>>(keys, n, true);
+    long long P = kSortTile;
+    while (P < n) P <<= 1;
+    for (long long size = 2 * kSortTile; size <= P; size <<= 1) {
+        const unsigned int pairs_blocks = (unsigned int)((P / 2 + 255) / 256);
+        rank_sort_step<<<pairs_blocks, 256, 0, st>>>(keys, n, size, 0, true);
+        for (long long stride = size / 4; stride >= kSortTile; stride >>= 1)
+            rank_sort_step<<<pairs_blocks, 256, 0, st>>>(keys, n, size, stride, false);
+        rank_sort_tile<<<tiles, kSortTile / 2, 0, st>>>(keys, n, false);
+    }
+    // unpack into device-visible pinned staging (its own: the scan's host mirror keeps the database-order lists)
+    if (n > s->h_rank_cap) {
+        if (s->h_rank_rows) cudaFreeHost(s->h_rank_rows);
+        if (s->h_rank_scores) cudaFreeHost(s->h_rank_scores);
+        s->h_rank_rows = nullptr;
+        s->h_rank_scores = nullptr;
+        s->h_rank_cap = 0;
+        const int64_t c = n + n / 4 + 1024;
+        VQ_CUDA(cudaMallocHost((void **)&s->h_rank_rows, (size_t)c * sizeof(int64_t)));
+        VQ_CUDA(cudaMallocHost((void **)&s->h_rank_scores, (size_t)c * sizeof(float)));
+        s->h_rank_cap = c;
+    }
+    rank_unpack<<<nb, 256, 0, st>>>(keys, n, s->first_global_row, (long long *)s->h_rank_rows, s->h_rank_scores);
+    VQ_CUDA(cudaGetLastError());
+    VQ_CUDA(cudaStreamSynchronize(st));
+    memcpy(rows_out, s->h_rank_rows, (size_t)n * sizeof(int64_t));
+    memcpy(scores_out, s->h_rank_scores, (size_t)n * sizeof(float));
+    return 0;
+}
+
 extern "C" int vq_fetch_scores(vq_store *s, int64_t first_row, int64_t n_rows, float *scores_out) {
     VQ_REQUIRE(s && (scores_out || n_rows == 0), "vq_fetch_scores: null argument");
     VQ_REQUIRE(first_row >= 0 && n_rows >= 0 && first_row + n_rows <= s->n_rows, "vq_fetch_scores: range outside shard");

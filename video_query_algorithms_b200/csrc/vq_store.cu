@@ -63,6 +63,8 @@ static void store_free(vq_store *s) {
     if (s->batch_scratch && s->batch_scratch_free) s->batch_scratch_free(s->batch_scratch);
     s->batch_scratch = nullptr;
     if (s->h_result) cudaFreeHost(s->h_result);
+    if (s->h_rank_rows) cudaFreeHost(s->h_rank_rows);
+    if (s->h_rank_scores) cudaFreeHost(s->h_rank_scores);
     if (s->h_topk_rows) cudaFreeHost(s->h_topk_rows);
     if (s->h_topk_scores) cudaFreeHost(s->h_topk_scores);
     if (s->ev_made)

@@ -380,6 +380,24 @@ class FeatureStore:
     def ties(self, copy=True):
         return self._fetch_list(lib().vq_fetch_ties, "n_tie", 2, copy)
 
+    def ranked(self, which="matches"):
+        """The whole match (or near-miss) list of the last scan ranked on the device: score descending, database
+        order among equal scores (report order, ticket.py:266).  Shards are ranked separately and merged here."""
+        idx = {"matches": 0, "near_misses": 1}[which]
+        attr = ("n_match", "n_near")[idx]
+        rows, scores = [], []
+        for sh, c in zip(self.shards, self._last_counts):
+            n = getattr(c, attr)
+            r, s = np.empty(n, np.int64), np.empty(n, np.float32)
+            check(lib().vq_fetch_ranked(sh.handle, idx, n, ptr(r), ptr(s)), "vq_fetch_ranked")
+            rows.append(r)
+            scores.append(s)
+        if len(rows) == 1:
+            return rows[0], scores[0]
+        r, s = np.concatenate(rows), np.concatenate(scores)
+        order = np.lexsort((r, -s.astype(np.float64)))
+        return r[order], s[order]
+
     def topk(self):
         k = self._last_topk
         if k == 0:

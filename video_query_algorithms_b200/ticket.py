@@ -338,6 +338,15 @@ class Ticket:
                     forced[int(clip)] = self._score_of(int(clip))
         self.matches.update(forced)
 
+    def ranked_selection(self, which="matches"):
+        """[(clip id, score)] of the last selection's whole match (or near-miss) set in report order — score descending,
+        database order among equal scores (ticket.py:266) — ranked on the device: the finalize round returns every clip
+        above min(threshold, lowest user match), which is far too many to sort as Python tuples."""
+        st = self.feature_store()
+        rows, sc = st.ranked(which)
+        ids = st.clip_ids[rows - st.first_global_row]
+        return list(zip(ids.tolist(), sc.tolist()))
+
     def _score_of(self, clip):
         st = self.feature_store()
         if not st.has_clip(clip):
