@@ -145,6 +145,46 @@ def test_full_ranking_of_the_match_list(vq, n):
     st.close()
 
 
+def test_nan_rows_maximum_topk_and_topk_beyond_the_store(vq):
+    """Edge cases: a clip whose features hold a NaN has a NaN score and belongs to no list, exactly like the
+    reference (every comparison with NaN is False, ticket.py:326-327) and does not disturb its neighbours;
+    top-k at the ABI maximum (1024) and larger than the store."""
+    n = 2600
+    X = synth.database(31, n)
+    bad = [0, 77, 1299, n - 1]
+    X[bad, 1, 5] = np.nan
+    st = vq.FeatureStore(n, STREAMS, [1], 1024, devices=[0])
+    st.upload(0, X[:, :, None, :])
+    X64 = X.astype(np.float64)[:, :, None, :]
+    T = sc.scale_target(X64[10])
+    th, lo = 0.7, 0.6
+    res = st.scan(tdict(T), (1.0, 1.5), th, lo, EPS, topk=1024)
+    got = st.scores()
+    sims64, _ = sc.similarities(X64, T)
+    s64 = sc.scores(sims64, (1.0, 1.5))
+    assert np.isnan(got[bad]).all() and np.isnan(s64[bad]).all()
+    ok = np.setdiff1d(np.arange(n), bad)
+    assert_scores_close(got[ok], s64[ok])
+    assert not np.intersect1d(st.matches()[0], bad).size and not np.intersect1d(st.near_misses()[0], bad).size
+    assert res.n_match == np.count_nonzero(got[ok].astype(np.float64) >= th)
+    rows, scs = st.topk()
+    assert len(rows) == 1024 and not np.intersect1d(rows, bad).size
+    want = ok[sc.topk_stable(got[ok], 1024)]
+    assert np.array_equal(rows, want)
+    gb = st.scan_batch(T[None].astype(np.float32), (1.0, 1.5), th, lo, debug_scores=True)[0]
+    assert np.isnan(gb[bad]).all()
+    cb = st.scan_batch(T[None].astype(np.float32), (1.0, 1.5), th, lo, topk=5)[0]
+    assert cb[0, 0] == np.count_nonzero(gb[ok].astype(np.float64) >= th)
+    small = vq.FeatureStore(7, STREAMS, [1], 1024, devices=[0])
+    small.upload(0, X[100:107, :, None, :])
+    r = small.scan(tdict(T), (1.0, 1.5), th, lo, EPS, topk=100)      # k larger than the store: all rows, ranked
+    assert r.n_topk == 7 and np.array_equal(small.topk()[0], sc.topk_stable(small.scores(), 7))
+    with pytest.raises(vq.VQError):
+        small.scan(tdict(T), (1.0, 1.5), th, lo, EPS, topk=1025)
+    st.close()
+    small.close()
+
+
 def test_scan_handles_empty_store(vq):
     st = vq.FeatureStore(0, STREAMS, [1], 1024, devices=[0])
     T = np.ones((2, 1, 1024))

@@ -13,8 +13,15 @@ X = synth.database(5, n).astype(np.float64)[:, :, None, :]
 T = sc.scale_target(X[11])
 td = {s: {1: T[i, 0]} for i, s in enumerate(S)}
 r = st.scan(td, (1.0, 1.5), 0.8, 0.73, 3e-6, topk=64, want_sims=True)
-print("scan", r, len(st.matches()[0]), len(st.topk()[0]), st.sims().shape)
-c, rows, scores, ms = st.scan_batch(np.stack([T, sc.scale_target(X[12]), sc.scale_target(X[13])]).astype(np.float32), (1.0, 1.5), 0.8, 0.73, topk=20)
+print("scan", r, len(st.matches()[0]), len(st.matches(copy=False)[0]), len(st.topk()[0]), st.sims().shape)
+print("ranked", st.ranked("matches")[0][:3], st.ranked("near_misses")[1][:3])
+st.append(synth.database(6, 3000)[:, :, None, :])
+r = st.scan(td, (1.0, 1.5), 0.8, 0.73, 3e-6, topk=64)
+print("after append", st.n_rows, r, st.ranked("near_misses")[0].shape)
+Tq = np.stack([T, sc.scale_target(X[12]), sc.scale_target(X[13])]).astype(np.float32)
+c, rows, scores, ms = st.scan_batch(Tq, (1.0, 1.5), 0.8, 0.73, topk=20)
+c2 = st.scan_batch(np.concatenate([Tq] * 60), (1.0, 1.5), 0.8, 0.73, topk=0)[0]
+print("batch 180 queries, no top-k", c2[:3].tolist(), c2[177:].tolist())
 print("batch", c.tolist(), rows[:, 0])
 print("labelled", st.labelled_sims(td, np.arange(0, n, 500)).shape)
 print("bootstrap", st.bootstrap_target(np.array([3, 9, 10, 40]), np.array([0, 20]), 0.3).shape)
