@@ -138,25 +138,33 @@ struct BatchScratch {
 };
 void free_batch_scratch(void *p) { delete static_cast<BatchScratch *>(p); }
 
-int get_batch_scratch(vq_store *s, size_t K, long long cap, BatchScratch **out) {
+int alloc_batch_scratch(const vq_store *s, size_t K, long long cap, BatchScratch *b) {
     constexpr int QN = bf::QN;
+    VQ_CUDA(b->t.alloc((size_t)QN * K * 4));
+    VQ_CUDA(b->t1.alloc((size_t)QN * K * 2));
+    VQ_CUDA(b->t2.alloc((size_t)QN * K * 2));
+    VQ_CUDA(b->cut.alloc(QN * 4));
+    VQ_CUDA(b->counts.alloc(QN * 2 * 8));
+    VQ_CUDA(b->cnt.alloc(QN * 4));
+    VQ_CUDA(b->keys.alloc((size_t)QN * cap * 8));
+    VQ_CUDA(b->rows.alloc((size_t)QN * VQ_MAX_TOPK * 8));
+    VQ_CUDA(b->sc.alloc((size_t)QN * VQ_MAX_TOPK * 4));
+    VQ_CUDA(b->park.alloc((size_t)s->sm_count * QN * bf::BM * 4));
+    VQ_CUDA(cudaMallocHost(&b->pinned_t, (size_t)QN * K * 4));
+    VQ_CUDA(cudaEventCreate(&b->e0));
+    VQ_CUDA(cudaEventCreate(&b->e1));
+    return 0;
+}
+
+int get_batch_scratch(vq_store *s, size_t K, long long cap, BatchScratch **out) {
     if (!s->batch_scratch) {
         BatchScratch *b = new BatchScratch();
+        if (int r = alloc_batch_scratch(s, K, cap, b)) {   // all or nothing: a half-built scratch is never kept
+            delete b;
+            return r;
+        }
         s->batch_scratch = b;
         s->batch_scratch_free = free_batch_scratch;
-        VQ_CUDA(b->t.alloc((size_t)QN * K * 4));
-        VQ_CUDA(b->t1.alloc((size_t)QN * K * 2));
-        VQ_CUDA(b->t2.alloc((size_t)QN * K * 2));
-        VQ_CUDA(b->cut.alloc(QN * 4));
-        VQ_CUDA(b->counts.alloc(QN * 2 * 8));
-        VQ_CUDA(b->cnt.alloc(QN * 4));
-        VQ_CUDA(b->keys.alloc((size_t)QN * cap * 8));
-        VQ_CUDA(b->rows.alloc((size_t)QN * VQ_MAX_TOPK * 8));
-        VQ_CUDA(b->sc.alloc((size_t)QN * VQ_MAX_TOPK * 4));
-        VQ_CUDA(b->park.alloc((size_t)s->sm_count * QN * bf::BM * 4));
-        VQ_CUDA(cudaMallocHost(&b->pinned_t, (size_t)QN * K * 4));
-        VQ_CUDA(cudaEventCreate(&b->e0));
-        VQ_CUDA(cudaEventCreate(&b->e1));
     }
     *out = static_cast<BatchScratch *>(s->batch_scratch);
     return 0;
