@@ -271,6 +271,27 @@ def main():
     h2d = ROW_BYTES + C.sizeof(_ffi.ScanParams)
     d2h = 40 + TOPK * 12 + (res.n_match + res.n_near + res.n_tie) * 12
 
+    # ---- the review round's call (Ticket.select_clips_to_review): lists stay on the device, the host draws 20 list
+    # positions with the reference's RNG and gathers just those entries + the best near miss
+    import random as _random
+    _random.seed(a=os.environ["RANDOM_SEED"])
+    for _ in range(2):
+        st.scan(tdict, WEIGHTS, THRESHOLD, lower, EPS, topk=TOPK, lists=False)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        r2 = st.scan(tdict, WEIGHTS, THRESHOLD, lower, EPS, topk=TOPK, lists=False)
+        st.topk()
+        st.ties(copy=False)
+        st.gather("matches", _random.sample(range(r2.n_match), min(10, r2.n_match)))
+        nb = st.near_best()
+        st.gather("near_misses", _random.sample(range(max(r2.n_near - 1, 0)), min(9, max(r2.n_near - 1, 0))))
+    barrier()
+    sel_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(sel_s, op=dist.ReduceOp.MAX)
+    e2e_select_value = world * n * e2e_steps / float(sel_s.item())
+
     # ---- cold end to end: the shard itself is uploaded from pinned host memory every step
     cold = None
     if world == 1 and not args.no_cold:
@@ -328,6 +349,11 @@ def main():
                     "host buffer, counts / top-k / ordered lists (int64 rows + fp32 scores) published into pinned host "
                     "memory inside the call; the shard stays resident in HBM between queries (the store outlives "
                     "broker ticks)"},
+            "e2e_select": {"value": e2e_select_value, "unit": "clips/s", "h2d_bytes_per_step": int(h2d + 19 * 8),
+                           "d2h_bytes_per_step": int(64 + TOPK * 12 + res.n_tie * 12 + 19 * 12), "steps": e2e_steps,
+                           "what": "the review round as Ticket.select_clips_to_review runs it: FeatureStore.scan(lists=False) "
+                                   "+ topk + tie band + gather of 10 sampled matches and 9 sampled near misses + best near miss; "
+                                   "the match / near-miss lists stay on the device"},
             "e2e_cold": cold,
             "gpu_launches": rank_scan.kernels_per_step() * args.steps,
             "exchange": rank_scan.exchange,

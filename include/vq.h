@@ -88,6 +88,14 @@ typedef struct vq_scan_counts {
  * a pinned host mirror owned by the library (one stream synchronisation).  vq_fetch_* copy
  * from that mirror into caller buffers; vq_scan_host_list hands out read-only views of it.   */
 int vq_scan(vq_store *s, const float *target, const vq_scan_params *p, vq_scan_counts *out);
+/* The selection round's variant (ticket.py:311-356 samples a few dozen clips out of lists that can hold millions):
+ * same scan, but only the counts, the top-k, the tie band and the BEST near miss (highest score, first in database
+ * order, ticket.py:335-340; row -1 when there is none) cross PCIe; the caller draws list positions itself and fetches
+ * exactly those with vq_gather_list (positions index the ordered match / near-miss / tie lists of this scan).        */
+int vq_scan_select(vq_store *s, const float *target, const vq_scan_params *p, vq_scan_counts *out,
+                   int64_t *near_best_pos, int64_t *near_best_row, float *near_best_score);
+int vq_gather_list(vq_store *s, int32_t which, int64_t n_idx, const int64_t *positions, int64_t *rows_out,
+                   float *scores_out);
 /* Same work, enqueued only: target already on the device, nothing copied back, no sync.
  * Used for device-side timing and for multi-GPU merges that read the results in place.      */
 int vq_scan_enqueue(vq_store *s, const float *target_dev, const vq_scan_params *p, void *stream);

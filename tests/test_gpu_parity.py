@@ -185,6 +185,43 @@ def test_nan_rows_maximum_topk_and_topk_beyond_the_store(vq):
     small.close()
 
 
+def test_selection_scan_gathers_what_the_full_lists_hold(vq):
+    """vq_scan_select / vq_gather_list (the review round's path: lists stay on the device) against the full-list
+    scan: same counts, tie band and top-k; gathered entries equal the list entries at those positions; the best near
+    miss is the first maximum of the near-miss list in database order — also across two shards."""
+    n = 30011
+    X = synth.database(17, n)
+    X[5000] = X[77]                                               # a duplicated clip: equal scores, two positions
+    for devices in ([0], [0, 0]):
+        st = vq.FeatureStore(n, STREAMS, [1], 1024, devices=devices)
+        st.upload(0, X[:, :, None, :])
+        ref = int(np.argmin(np.abs(synth.alpha(np.arange(n), 17) - 0.9)))      # a clip with many matches and near misses
+        T = sc.scale_target(X[ref].astype(np.float64)[:, None, :])
+        full = st.scan(tdict(T), (1.0, 1.5), 0.8, 0.73, EPS, topk=50)
+        assert full.n_match > 100 and full.n_near > 100
+        m, nm, ti, tk = st.matches(), st.near_misses(), st.ties(), st.topk()
+        lite = st.scan(tdict(T), (1.0, 1.5), 0.8, 0.73, EPS, topk=50, lists=False)
+        assert (full.n_match, full.n_near, full.n_tie, full.n_topk) == (lite.n_match, lite.n_near, lite.n_tie, lite.n_topk)
+        assert np.array_equal(st.ties(copy=False)[0], ti[0]) and np.array_equal(st.topk()[0], tk[0])
+        rng = np.random.default_rng(0)
+        for name, (rows, scs) in (("matches", m), ("near_misses", nm)):
+            pos = rng.choice(len(rows), size=min(40, len(rows)), replace=False)
+            r, s = st.gather(name, pos)
+            assert np.array_equal(r, rows[pos]) and np.array_equal(s, scs[pos])
+            with pytest.raises(vq.VQError):
+                st.gather(name, [len(rows)])
+        jbest = int(np.argmax(nm[1]))
+        assert st.near_best() == (jbest, int(nm[0][jbest]), float(nm[1][jbest]))
+        assert np.array_equal(st.matches()[0], m[0])              # whole lists remain fetchable (device copy path)
+        # a near-miss band that contains the duplicated pair as its maximum: the first one in database order wins
+        sc77 = float(st.scores()[77])
+        th_up = float(np.nextafter(np.float32(sc77), np.float32(2.0)))          # the band's maximum is exactly sc77
+        st.scan(tdict(T), (1.0, 1.5), th_up, sc77 - 0.05, EPS, lists=False)
+        pos_b, row_b, s_b = st.near_best()
+        assert row_b == 77 and s_b == sc77
+        st.close()
+
+
 def test_scan_handles_empty_store(vq):
     st = vq.FeatureStore(0, STREAMS, [1], 1024, devices=[0])
     T = np.ones((2, 1, 1024))

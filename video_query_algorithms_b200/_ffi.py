@@ -52,6 +52,8 @@ PROTOTYPES = {
     "vq_store_fill_synthetic": (C.c_int, [_vp, C.c_uint64, _vp]),
     "vq_store_device_ptr": (C.c_int, [_vp, _P(_vp)]),
     "vq_scan": (C.c_int, [_vp, _vp, _P(ScanParams), _P(ScanCounts)]),
+    "vq_scan_select": (C.c_int, [_vp, _vp, _P(ScanParams), _P(ScanCounts), _i64p, _i64p, _f32p]),
+    "vq_gather_list": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _vp]),
     "vq_scan_enqueue": (C.c_int, [_vp, _vp, _P(ScanParams), _vp]),
     "vq_scan_wait": (C.c_int, [_vp, _vp, _P(ScanCounts)]),
     "vq_fetch_matches": (C.c_int, [_vp, _i64, _vp, _vp]),

@@ -61,7 +61,7 @@ struct vq_store {
     float *target = nullptr;         // [n_streams][stream_len] fp32 staging for vq_scan
     float *scores = nullptr;         // [n_rows]
     float *sims = nullptr;           // [n_rows][n_streams] (allocated on first want_sims)
-    unsigned int *hist = nullptr;    // [kHistBins] + [1] block ticket + [1] cut bin
+    unsigned int *hist = nullptr;    // [kHistBins] + [1] block ticket + [1] cut bin + u64 best near-miss key + u64 its list position
     int64_t n_chunks = 0;
     unsigned int *chunk_counts = nullptr;    // [3][n_chunks]
     unsigned int *chunk_offsets = nullptr;   // [3][n_chunks]
@@ -92,7 +92,9 @@ struct vq_store {
     int64_t *h_rank_rows = nullptr;  // pinned staging of vq_fetch_ranked
     float *h_rank_scores = nullptr;
     int64_t h_rank_cap = 0;
-    bool staged = false;
+    bool staged = false;             // the mirror holds all three lists + top-k of the last scan (vq_scan)
+    bool staged_ties = false;        // ... at least the tie band + top-k (vq_scan, vq_scan_select)
+    void *h_gather = nullptr;        // pinned staging of vq_gather_list
     // scratch of the batched path (vq_batch.cu), allocated on its first call and kept: a batched scan allocates nothing
     void *batch_scratch = nullptr;
     void (*batch_scratch_free)(void *) = nullptr;

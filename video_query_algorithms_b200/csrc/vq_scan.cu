@@ -76,6 +76,7 @@ __device__ void finish_histogram(unsigned int *hist_s, unsigned int *hist_g, int
     __syncthreads();
     if (!is_last) return;
     __threadfence();
+    if (threadIdx.x < 4) hist_g[kHistBins + 2 + threadIdx.x] = 0;   // best near-miss key / list position of this scan (K2a, K2c)
     // suffix counts: thread t owns bins [t*per, (t+1)*per) from the TOP of the range
     const int per = kHistBins / blockDim.x;          // blockDim divides 4096
     const int top = kHistBins - 1 - threadIdx.x * per;
@@ -270,7 +271,8 @@ __device__ __forceinline__ void load_chunk_scores(const float *scores, long long
 __global__ void __launch_bounds__(kSelThreads)
 select_count(const float *__restrict__ scores, const long long n_rows, const ScanArgs a,
              const unsigned int *__restrict__ hist_g, unsigned int *chunk_counts, const long long n_chunks,
-             unsigned int *cand_count, unsigned long long *cand_keys, const long long cand_cap) {
+             unsigned int *cand_count, unsigned long long *cand_keys, const long long cand_cap,
+             unsigned long long *near_best_key) {
     __shared__ unsigned int red[3][kSelThreads / 32];
     const long long chunk = blockIdx.x;
     const long long r0 = chunk * kChunkRows + (long long)threadIdx.x * kRowsPerThread;
@@ -279,13 +281,27 @@ select_count(const float *__restrict__ scores, const long long n_rows, const Sca
     const int cut = (int)hist_g[kHistBins + 1];
     unsigned int cm = 0, cn = 0, ct = 0, cc = 0;
     unsigned int cmask = 0;
+    unsigned long long best_nm = 0ull;                 // best near miss of this thread: max score, then lowest row
 #pragma unroll
     for (int j = 0; j < kRowsPerThread; ++j) {
         const Flags f = classify(sc[j], a);
         cm += f.m; cn += f.nm; ct += f.tie;
+        if (f.nm) {
+            const unsigned long long k = make_key(sc[j], (unsigned int)(r0 + j));
+            best_nm = k > best_nm ? k : best_nm;
+        }
         if (a.topk > 0 && sc[j] == sc[j] && score_bin(sc[j]) >= cut) { cmask |= 1u << j; ++cc; }
     }
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    // the best near miss of the shard (ticket.py:335-340 holds it out of the sampling): one atomicMax per warp that has one
+    if (__any_sync(0xffffffffu, best_nm != 0ull)) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long other = __shfl_xor_sync(0xffffffffu, best_nm, o);
+            best_nm = other > best_nm ? other : best_nm;
+        }
+        if (lane == 0) atomicMax(near_best_key, best_nm);
+    }
     // top-k candidates: one atomic per warp
     if (a.topk > 0) {
         unsigned int inc = cc;
@@ -403,7 +419,7 @@ select_compact(const float *__restrict__ scores, const long long n_rows, const S
                unsigned int *rows_m, float *sc_m, unsigned int *rows_n, float *sc_n,
                unsigned int *rows_t, float *sc_t, const long long *__restrict__ counts,
                const float *__restrict__ topk_scores, const long long *__restrict__ topk_rows,
-               long long *pack) {
+               long long *pack, const unsigned long long *__restrict__ near_best_key, long long *near_best_pos) {
     __shared__ unsigned int wsum[3][kSelThreads / 32];
     if (blockIdx.x == 0) {
         // allgather payload for the multi-GPU merge: counts | top-k rows | top-k score bits
@@ -448,11 +464,13 @@ select_compact(const float *__restrict__ scores, const long long n_rows, const S
         for (int w = 0; w < wid; ++w) before += wsum[q][w];
         unsigned int at = chunk_offsets[q * n_chunks + chunk] + before + inc[q] - c[q];
         if (c[q]) {
+            const unsigned int best_row = (q == 1) ? vq::key_row(*near_best_key) : 0xFFFFFFFFu;
 #pragma unroll
             for (int j = 0; j < kRowsPerThread; ++j)
                 if (masks[q] & (1u << j)) {
                     out_rows[q][at] = (unsigned int)(r0 + j);
                     out_sc[q][at] = sc[j];
+                    if (q == 1 && (unsigned int)(r0 + j) == best_row) *near_best_pos = (long long)at;
                     ++at;
                 }
         }
@@ -517,8 +535,11 @@ struct PublishArgs {
     const float *topk_scores;
     long long *h_topk_rows;
     float *h_topk_scores;
-    long long *h_result;                 // [8]
+    long long *h_result;                 // [8]: counts[4], overflow, best near miss: global row, score bits, list position
     long long first_global_row;
+    const unsigned long long *near_best_key;
+    const long long *near_best_pos;
+    int lists;                           // 1: all three lists; 0: only the tie band (the caller gathers what it samples)
 };
 
 __global__ void __launch_bounds__(256)
@@ -528,6 +549,7 @@ publish_results(const PublishArgs a) {
     long long overflow = 0;
 #pragma unroll
     for (int q = 0; q < 3; ++q) {
+        if (!a.lists && q < 2) continue;
         long long n = a.counts[q];
         if (n > a.cap[q]) { overflow = 1; n = a.cap[q]; }
         for (long long i = tid; i < n; i += nth) {
@@ -542,6 +564,12 @@ publish_results(const PublishArgs a) {
     }
     if (tid < 4) a.h_result[tid] = a.counts[tid];
     if (tid == 4) a.h_result[4] = overflow;
+    if (tid == 5) {
+        const unsigned long long k = *a.near_best_key;
+        a.h_result[5] = k ? a.first_global_row + (long long)vq::key_row(k) : -1;
+        a.h_result[6] = (long long)__float_as_uint(vq::key_score(k));
+        a.h_result[7] = k ? *a.near_best_pos : -1;
+    }
 }
 
 int fill_args(const vq_store *s, const vq_scan_params *p, ScanArgs *a) {
@@ -599,6 +627,7 @@ extern "C" int vq_scan_enqueue(vq_store *s, const float *target_dev, const vq_sc
         VQ_CUDA(cudaMalloc((void **)&s->sims, (size_t)(s->n_rows > 0 ? s->n_rows : 1) * s->n_streams * sizeof(float)));
     s->last_topk = a.topk;
     s->staged = false;
+    s->staged_ties = false;
     const size_t smem_need = (size_t)s->n_streams * s->stream_len * sizeof(float);
     VQ_REQUIRE(smem_need <= 200 * 1024, "scan: target of %zu bytes does not fit in shared memory", smem_need);
     const int slot = s->ev_head;
@@ -617,7 +646,8 @@ extern "C" int vq_scan_enqueue(vq_store *s, const float *target_dev, const vq_sc
     const unsigned int sel_blocks = (unsigned int)(s->n_chunks > 0 ? s->n_chunks : 1);
     const long long sel_chunks = (long long)sel_blocks;
     select_count<<<sel_blocks, kSelThreads, 0, st>>>(s->scores, s->n_rows, a, s->hist, s->chunk_counts,
-                                                     sel_chunks, s->cand_count, s->cand_keys, s->cand_cap);
+                                                     sel_chunks, s->cand_count, s->cand_keys, s->cand_cap,
+                                                     reinterpret_cast<unsigned long long *>(s->hist + kHistBins + 2));
     select_finish<<<2, kFinThreads, 0, st>>>(s->chunk_counts, s->chunk_offsets, sel_chunks,
                                              (long long *)s->counts, s->hist, s->cand_count, s->cand_keys,
                                              s->cand_cap, a.topk, s->first_global_row, s->topk_scores,
@@ -625,7 +655,8 @@ extern "C" int vq_scan_enqueue(vq_store *s, const float *target_dev, const vq_sc
     select_compact<<<sel_blocks, kSelThreads, 0, st>>>(
         s->scores, s->n_rows, a, s->chunk_offsets, sel_chunks, s->list_rows[0], s->list_scores[0],
         s->list_rows[1], s->list_scores[1], s->list_rows[2], s->list_scores[2], (const long long *)s->counts,
-        s->topk_scores, (const long long *)s->topk_rows, (long long *)s->pack);
+        s->topk_scores, (const long long *)s->topk_rows, (long long *)s->pack,
+        reinterpret_cast<const unsigned long long *>(s->hist + kHistBins + 2), reinterpret_cast<long long *>(s->hist + kHistBins + 4));
     VQ_CUDA(cudaGetLastError());
     return 0;
 }
@@ -666,7 +697,7 @@ static int grow_mirror(vq_store *s, int which, int64_t need) {
     return 0;
 }
 
-static int publish(vq_store *s) {
+static int publish(vq_store *s, int lists) {
     if (!s->h_topk_rows) {
         VQ_CUDA(cudaMallocHost((void **)&s->h_topk_rows, VQ_MAX_TOPK * sizeof(int64_t)));
         VQ_CUDA(cudaMallocHost((void **)&s->h_topk_scores, VQ_MAX_TOPK * sizeof(float)));
@@ -687,14 +718,17 @@ static int publish(vq_store *s) {
     a.h_topk_scores = s->h_topk_scores;
     a.h_result = (long long *)s->h_result;
     a.first_global_row = s->first_global_row;
-    publish_results<<<s->sm_count, 256, 0, s->stream>>>(a);
+    a.near_best_key = reinterpret_cast<const unsigned long long *>(s->hist + kHistBins + 2);
+    a.near_best_pos = reinterpret_cast<const long long *>(s->hist + kHistBins + 4);
+    a.lists = lists;
+    publish_results<<<lists ? s->sm_count : 8, 256, 0, s->stream>>>(a);
     VQ_CUDA(cudaGetLastError());
     VQ_CUDA(cudaStreamSynchronize(s->stream));
     return 0;
 }
 
-extern "C" int vq_scan(vq_store *s, const float *target, const vq_scan_params *p, vq_scan_counts *out) {
-    VQ_REQUIRE(s && target, "vq_scan: null argument");
+static int scan_host(vq_store *s, const float *target, const vq_scan_params *p, vq_scan_counts *out, int lists, const char *who) {
+    VQ_REQUIRE(s && target, "%s: null argument", who);
     VQ_CUDA(cudaSetDevice(s->device));
     const size_t bytes = s->row_floats * sizeof(float);
     memcpy(s->pinned_stage, target, bytes);
@@ -702,17 +736,18 @@ extern "C" int vq_scan(vq_store *s, const float *target, const vq_scan_params *p
     if (int r = vq_scan_enqueue(s, s->target, p, s->stream)) return r;
     // the mirror starts at 1/8 of the shard per list (at least 64k entries) and grows on demand
     const int64_t first_cap = s->n_rows / 8 > 65536 ? s->n_rows / 8 : 65536;
-    for (int i = 0; i < 3; ++i)
+    for (int i = lists ? 0 : 2; i < 3; ++i)
         if (s->h_cap[i] == 0)
-            if (int r = grow_mirror(s, i, first_cap)) return r;
-    if (int r = publish(s)) return r;
+            if (int r = grow_mirror(s, i, lists ? first_cap : 65536)) return r;
+    if (int r = publish(s, lists)) return r;
     if (s->h_result[4]) {                                  // a list outgrew its mirror: grow, publish again
-        for (int i = 0; i < 3; ++i)
+        for (int i = lists ? 0 : 2; i < 3; ++i)
             if (int r = grow_mirror(s, i, s->h_result[i])) return r;
-        if (int r = publish(s)) return r;
+        if (int r = publish(s, lists)) return r;
     }
     for (int i = 0; i < 4; ++i) s->counts_host[i] = s->h_result[i];
-    s->staged = true;
+    s->staged = lists != 0;
+    s->staged_ties = true;
     if (out) {
         out->n_match = s->counts_host[0];
         out->n_near = s->counts_host[1];
@@ -728,10 +763,66 @@ extern "C" int vq_scan(vq_store *s, const float *target, const vq_scan_params *p
     return 0;
 }
 
+extern "C" int vq_scan(vq_store *s, const float *target, const vq_scan_params *p, vq_scan_counts *out) {
+    return scan_host(s, target, p, out, 1, "vq_scan");
+}
+
+extern "C" int vq_scan_select(vq_store *s, const float *target, const vq_scan_params *p, vq_scan_counts *out,
+                              int64_t *near_best_pos, int64_t *near_best_row, float *near_best_score) {
+    if (int r = scan_host(s, target, p, out, 0, "vq_scan_select")) return r;
+    if (near_best_pos) *near_best_pos = s->h_result[7];
+    if (near_best_row) *near_best_row = s->h_result[5];
+    if (near_best_score) {
+        const uint32_t bits = (uint32_t)s->h_result[6];
+        memcpy(near_best_score, &bits, sizeof(float));
+    }
+    return 0;
+}
+
+namespace {
+__global__ void gather_list(const unsigned int *__restrict__ rows, const float *__restrict__ scores, long long n_list,
+                            const long long *__restrict__ pos, int n, long long first_global_row, long long *rows_out,
+                            float *scores_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long p = pos[i];
+    const bool ok = p >= 0 && p < n_list;
+    rows_out[i] = ok ? first_global_row + (long long)rows[p] : -1;
+    scores_out[i] = ok ? scores[p] : __int_as_float(0x7fc00000);
+}
+}  // namespace
+
+extern "C" int vq_gather_list(vq_store *s, int32_t which, int64_t n_idx, const int64_t *positions, int64_t *rows_out,
+                              float *scores_out) {
+    VQ_REQUIRE(s && (n_idx == 0 || (positions && rows_out && scores_out)), "vq_gather_list: null argument");
+    VQ_REQUIRE(which >= 0 && which <= 2, "vq_gather_list: list %d outside 0..2 (matches, near misses, ties)", which);
+    VQ_CUDA(cudaSetDevice(s->device));
+    const int64_t n_list = s->counts_host[which];
+    for (int64_t i = 0; i < n_idx; ++i)
+        VQ_REQUIRE(positions[i] >= 0 && positions[i] < n_list, "vq_gather_list: position %lld outside the list of %lld entries",
+                   (long long)positions[i], (long long)n_list);
+    constexpr int kStep = 4096;                         // entries per round trip; the staging is pinned and device-mapped
+    if (!s->h_gather) VQ_CUDA(cudaMallocHost((void **)&s->h_gather, (size_t)kStep * (8 + 8 + 4)));
+    long long *h_pos = (long long *)s->h_gather, *h_rows = h_pos + kStep;
+    float *h_sc = (float *)(h_rows + kStep);
+    for (int64_t base = 0; base < n_idx; base += kStep) {
+        const int n = (int)(n_idx - base < kStep ? n_idx - base : kStep);
+        memcpy(h_pos, positions + base, (size_t)n * sizeof(int64_t));
+        gather_list<<<(n + 255) / 256, 256, 0, s->stream>>>(s->list_rows[which], s->list_scores[which], n_list, h_pos, n,
+                                                            s->first_global_row, h_rows, h_sc);
+        VQ_CUDA(cudaGetLastError());
+        VQ_CUDA(cudaStreamSynchronize(s->stream));
+        memcpy(rows_out + base, h_rows, (size_t)n * sizeof(int64_t));
+        memcpy(scores_out + base, h_sc, (size_t)n * sizeof(float));
+    }
+    return 0;
+}
+
 extern "C" int vq_scan_host_list(vq_store *s, int32_t which, const int64_t **rows, const float **scores, int64_t *n) {
     VQ_REQUIRE(s && rows && scores && n, "vq_scan_host_list: null argument");
     VQ_REQUIRE(which >= 0 && which <= 3, "vq_scan_host_list: list %d outside 0..3 (matches, near misses, ties, top-k)", which);
-    VQ_REQUIRE(s->staged, "vq_scan_host_list: the last scan on this store was not a vq_scan (no host mirror)");
+    VQ_REQUIRE(s->staged || (which == 2 && s->staged_ties) || (which == 3 && s->staged_ties),
+               "vq_scan_host_list: the last scan on this store did not publish this list to the host mirror");
     *n = s->counts_host[which];
     *rows = which == 3 ? s->h_topk_rows : s->h_rows[which];
     *scores = which == 3 ? s->h_topk_scores : s->h_scores[which];
@@ -745,7 +836,7 @@ static int fetch_list(vq_store *s, int which, int64_t cap, int64_t *rows_out, fl
     const int64_t n = s->counts_host[which];
     VQ_REQUIRE(cap >= n, "%s: capacity %lld < %lld entries", who, (long long)cap, (long long)n);
     if (n == 0) return 0;
-    if (s->staged) {
+    if (s->staged || (which == 2 && s->staged_ties)) {
         if (rows_out) memcpy(rows_out, s->h_rows[which], (size_t)n * sizeof(int64_t));
         if (scores_out) memcpy(scores_out, s->h_scores[which], (size_t)n * sizeof(float));
         return 0;
@@ -776,7 +867,7 @@ extern "C" int vq_fetch_topk(vq_store *s, int32_t cap, int64_t *rows_out, float 
     const int n = (int)s->counts_host[3];
     VQ_REQUIRE(cap >= n, "vq_fetch_topk: capacity %d < %d entries", cap, n);
     if (n == 0) return 0;
-    if (s->staged) {
+    if (s->staged || s->staged_ties) {
         if (rows_out) memcpy(rows_out, s->h_topk_rows, (size_t)n * sizeof(int64_t));
         if (scores_out) memcpy(scores_out, s->h_topk_scores, (size_t)n * sizeof(float));
         return 0;

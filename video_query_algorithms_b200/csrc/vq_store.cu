@@ -63,6 +63,7 @@ static void store_free(vq_store *s) {
     if (s->batch_scratch && s->batch_scratch_free) s->batch_scratch_free(s->batch_scratch);
     s->batch_scratch = nullptr;
     if (s->h_result) cudaFreeHost(s->h_result);
+    if (s->h_gather) cudaFreeHost(s->h_gather);
     if (s->h_rank_rows) cudaFreeHost(s->h_rank_rows);
     if (s->h_rank_scores) cudaFreeHost(s->h_rank_scores);
     if (s->h_topk_rows) cudaFreeHost(s->h_topk_rows);
@@ -151,7 +152,7 @@ extern "C" int vq_store_create(vq_store **out, int device, int64_t n_rows, int n
     } while (0)
     VQ_ALLOC(s->target, s->row_floats * sizeof(float));
     VQ_ALLOC(s->hist, (vq::kHistBins + 8) * sizeof(unsigned int));
-    VQ_ALLOC(s->counts, 4 * sizeof(int64_t));
+    VQ_ALLOC(s->counts, 8 * sizeof(int64_t));
     VQ_ALLOC(s->cand_count, 4 * sizeof(unsigned int));
     VQ_ALLOC(s->topk_scores, VQ_MAX_TOPK * sizeof(float));
     VQ_ALLOC(s->topk_rows, VQ_MAX_TOPK * sizeof(int64_t));
@@ -168,7 +169,7 @@ extern "C" int vq_store_create(vq_store **out, int device, int64_t n_rows, int n
         cudaEventCreate(&s->ev_stop[i]);
     }
     s->ev_made = true;
-    cudaMemsetAsync(s->counts, 0, 4 * sizeof(int64_t), s->stream);
+    cudaMemsetAsync(s->counts, 0, 8 * sizeof(int64_t), s->stream);
     cudaMemsetAsync(s->hist, 0, (vq::kHistBins + 8) * sizeof(unsigned int), s->stream);
     cudaMemsetAsync(s->cand_count, 0, 4 * sizeof(unsigned int), s->stream);
     VQ_CUDA(cudaStreamSynchronize(s->stream));

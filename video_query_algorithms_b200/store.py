@@ -300,20 +300,24 @@ class FeatureStore:
             self._eff_key = key
 
     # ------------------------------------------------------------------ scan
-    def scan(self, target_features, weights, threshold, lower_limit, eps, topk=0, want_sims=False):
-        """One fused pass: similarities, scores, match / near-miss / tie lists, top-k."""
+    def scan(self, target_features, weights, threshold, lower_limit, eps, topk=0, want_sims=False, lists=True):
+        """One fused pass: similarities, scores, match / near-miss / tie lists, top-k.
+        lists=False is the selection round's variant: the match and near-miss lists stay on the device (only counts,
+        top-k, tie band and the best near miss come back); fetch sampled entries with gather()."""
         T, have = self.pack_target(target_features, np.float32)
         self._sync_split_weights_for_target(have)
         w = [weights[s] for s in self.streams] if isinstance(weights, dict) else list(weights)
         p = make_params(w, threshold, lower_limit, eps, topk, want_sims)
         Tc = np.ascontiguousarray(T)
         # enqueue on every shard first (each has its own stream), then wait: shards run concurrently
+        self._near_best = [None] * len(self.shards)
         if len(self.shards) == 1:
             c = ScanCounts()
-            check(lib().vq_scan(self.shards[0].handle, ptr(Tc), C.byref(p), C.byref(c)), "vq_scan")
+            self._scan_shard(0, Tc, p, c, lists)
             counts = [c]
         else:
-            counts = self._scan_multi(Tc, p)
+            counts = self._scan_multi(Tc, p, lists)
+        self._lists_on_host = bool(lists)
         self.last = ScanResult(sum(c.n_match for c in counts), sum(c.n_near for c in counts),
                                sum(c.n_tie for c in counts), min(int(topk), sum(c.n_topk for c in counts)),
                                max(c.scan_ms for c in counts))
@@ -321,14 +325,23 @@ class FeatureStore:
         self._last_topk = topk
         return self.last
 
-    def _scan_multi(self, Tc, p):
+    def _scan_shard(self, i, Tc, p, c, lists):
+        if lists:
+            check(lib().vq_scan(self.shards[i].handle, ptr(Tc), C.byref(p), C.byref(c)), "vq_scan")
+        else:
+            pos, row, sc = C.c_int64(), C.c_int64(), C.c_float()
+            check(lib().vq_scan_select(self.shards[i].handle, ptr(Tc), C.byref(p), C.byref(c), C.byref(pos), C.byref(row),
+                                       C.byref(sc)), "vq_scan_select")
+            self._near_best[i] = (pos.value, row.value, sc.value)
+
+    def _scan_multi(self, Tc, p, lists=True):
         import threading
         counts = [ScanCounts() for _ in self.shards]
         errs = []
 
         def run(i):
             try:
-                check(lib().vq_scan(self.shards[i].handle, ptr(Tc), C.byref(p), C.byref(counts[i])), "vq_scan")
+                self._scan_shard(i, Tc, p, counts[i], lists)
             except Exception as e:       # surfaced below
                 errs.append(e)
 
@@ -353,8 +366,40 @@ class FeatureStore:
         s.flags.writeable = False
         return r, s
 
+    def near_best(self):
+        """(position in the near-miss list, global row, score) of the best near miss of a lists=False scan — highest
+        score, first in database order (the clip ticket.py:335-340 holds out of the sampling); None if there is none."""
+        best, base = None, 0
+        for nb, c in zip(self._near_best, self._last_counts):
+            if nb is not None and nb[1] >= 0 and (best is None or nb[2] > best[2]):     # ties: the earlier shard wins
+                best = (base + nb[0], nb[1], nb[2])
+            base += c.n_near
+        return best
+
+    def gather(self, which, positions):
+        """Entries of the ordered match / near-miss / tie list of the last scan at the given list positions:
+        (global rows, fp32 scores).  One small round trip instead of the whole list."""
+        idx = {"matches": 0, "near_misses": 1, "ties": 2}[which]
+        attr = ("n_match", "n_near", "n_tie")[idx]
+        pos = np.asarray(positions, dtype=np.int64).reshape(-1)
+        rows, scores = np.empty(len(pos), np.int64), np.empty(len(pos), np.float32)
+        base = 0
+        for sh, c in zip(self.shards, self._last_counts):
+            n = getattr(c, attr)
+            sel = np.flatnonzero((pos >= base) & (pos < base + n))
+            if len(sel):
+                local = np.ascontiguousarray(pos[sel] - base)
+                r, s = np.empty(len(sel), np.int64), np.empty(len(sel), np.float32)
+                check(lib().vq_gather_list(sh.handle, idx, len(sel), ptr(local), ptr(r), ptr(s)), "vq_gather_list")
+                rows[sel], scores[sel] = r, s
+            base += n
+        if len(pos) and (pos.min() < 0 or pos.max() >= base):
+            raise VQError("gather: position outside the %s list of %d entries" % (which, base))
+        return rows, scores
+
     def _fetch_list(self, fn, attr, which, copy):
         rows, scores = [], []
+        copy = copy or not (self._lists_on_host or which == 2)      # after a lists=False scan only the tie band is mirrored
         for sh, c in zip(self.shards, self._last_counts):
             if not copy:
                 r, s = self._host_view(sh, which)

@@ -257,13 +257,13 @@ class Ticket:
     def _eps(self):
         return float(os.environ["COMPUTE_EPS"])
 
-    def _scan(self, threshold, lower_limit, want_sims=False):
+    def _scan(self, threshold, lower_limit, want_sims=False, lists=True):
         st = self.feature_store()
         weights = self._weights if self._weights is not None else (
             self._hp.weights or self._hp.default_weights)
         want_sims = want_sims or self._have_sims
         self.last_scan = st.scan(self.target.target_features, [weights[s] for s in st.streams],
-                                 threshold, lower_limit, self._eps(), topk=self.topk, want_sims=want_sims)
+                                 threshold, lower_limit, self._eps(), topk=self.topk, want_sims=want_sims, lists=lists)
         self._scanned, self._have_sims = True, want_sims
         if isinstance(self.scores, _ScoreView):
             self.scores._arr = None
@@ -304,10 +304,11 @@ class Ticket:
         clip and previously confirmed clips are forced in.  Result: self.matches = {clip: score}."""
         lower_limit = threshold - near_miss * (1 - threshold)
         st = self.feature_store()
-        res = self._scan(threshold, lower_limit)
+        # A review round samples a few dozen clips: the lists stay on the device and only the sampled entries are
+        # fetched.  The finalize round (max = inf) returns every clip above the criterion: whole lists come back.
+        sampled = max_number_matches != float("inf")
+        res = self._scan(threshold, lower_limit, lists=not sampled)
         ids = st.clip_ids
-        m_rows, m_sc = st.matches(copy=False)         # views of the scan's host mirror: consumed before the next scan
-        n_rows, n_sc = st.near_misses(copy=False)
         t_rows, _ = st.ties(copy=False)
         self.tie_band = [int(ids[r - st.first_global_row]) for r in t_rows]
         if self.tie_band:
@@ -318,15 +319,34 @@ class Ticket:
         # random.sample(population, k) draws depend only on (len(population), k): sampling the index
         # range consumes the generator exactly like sampling the reference's dict items (:333).
         picked = random.sample(range(res.n_match), mscores)
-        chosen = [(int(ids[m_rows[j] - st.first_global_row]), float(m_sc[j])) for j in picked]
+        if sampled:
+            m_rows, m_sc = st.gather("matches", picked)
+            chosen = [(int(ids[r - st.first_global_row]), float(s)) for r, s in zip(m_rows, m_sc)]
+        else:
+            m_rows, m_sc = st.matches(copy=False)         # views of the scan's host mirror: consumed before the next scan
+            chosen = [(int(ids[m_rows[j] - st.first_global_row]), float(m_sc[j])) for j in picked]
         near_best = {}
+        n_left = res.n_near
+        jbest = None
         if m_near_scores > 0:
             m_near_scores -= 1
-            jbest = int(np.argmax(n_sc))               # first maximum in database order (:338)
-            near_best = {int(ids[n_rows[jbest] - st.first_global_row]): float(n_sc[jbest])}
-            n_rows, n_sc = np.delete(n_rows, jbest), np.delete(n_sc, jbest)
-        picked = random.sample(range(len(n_rows)), m_near_scores)
-        chosen += [(int(ids[n_rows[j] - st.first_global_row]), float(n_sc[j])) for j in picked]
+            n_left -= 1
+            if sampled:
+                jbest, brow, bsc = st.near_best()          # first maximum in database order (:338), found on the device
+                near_best = {int(ids[brow - st.first_global_row]): float(bsc)}
+            else:
+                n_rows, n_sc = st.near_misses(copy=False)
+                jbest = int(np.argmax(n_sc))
+                near_best = {int(ids[n_rows[jbest] - st.first_global_row]): float(n_sc[jbest])}
+        picked = random.sample(range(n_left), m_near_scores)
+        # positions in the list with the best near miss deleted (:340) -> positions in the full list
+        pos = [j if jbest is None or j < jbest else j + 1 for j in picked]
+        if sampled:
+            n_rows_p, n_sc_p = st.gather("near_misses", pos)
+            chosen += [(int(ids[r - st.first_global_row]), float(s)) for r, s in zip(n_rows_p, n_sc_p)]
+        else:
+            n_rows, n_sc = st.near_misses(copy=False)
+            chosen += [(int(ids[n_rows[j] - st.first_global_row]), float(n_sc[j])) for j in pos]
         self.matches = dict(chosen)
         self.matches.update(near_best)
         forced = {}
