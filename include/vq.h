@@ -145,6 +145,11 @@ int vq_exchange_local_handle(vq_exchange *x, void *handle_out /* 64 bytes */);
 int vq_exchange_connect(vq_exchange *x, const void *all_handles /* [world][64] */);
 int vq_exchange_destroy(vq_exchange *x);
 int vq_scan_exchange_enqueue(vq_store *s, vq_exchange *x, void *stream);
+/* A stream of queries: push this step's payload, merge the PREVIOUS step's (no rank waits for the slowest rank of the
+ * current step); vq_exchange_flush_enqueue merges the last pushed step.  vq_exchange_merged then holds step i-1 after
+ * the i-th lagged call and the last step after the flush.                                                          */
+int vq_scan_exchange_enqueue_lagged(vq_store *s, vq_exchange *x, void *stream);
+int vq_exchange_flush_enqueue(vq_exchange *x, void *stream);
 int vq_exchange_merged(vq_exchange *x, const int64_t **merged_dev /* [4 + 2*topk] */);
 
 /* per-launch device times of K1 recorded since the last call (ring of 1024), in ms           */

@@ -34,10 +34,12 @@ def main():
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
     results = {}
-    for mode in ("p2p", "nccl"):
+    for mode in ("p2p", "p2p-lagged", "nccl"):
         rs = RankScan(st.shards[0].handle, k, local, dist, torch, exchange=mode)
-        for _ in range(5):                                   # several steps: exercises the two inbox slots
-            rs.enqueue(target.data_ptr(), params, stream.cuda_stream)
+        for i in range(7):                                   # several steps: exercises all four inbox slots;
+            params = make_params((1.0, 1.5), 0.75 + 0.01 * i, 0.73, 3e-6, topk=k)   # every step has its own threshold, so a
+            rs.enqueue(target.data_ptr(), params, stream.cuda_stream)               # merge of the wrong step shows
+        rs.flush(stream.cuda_stream)                         # lagged mode: merge the last step
         torch.cuda.synchronize()
         dist.barrier()
         results[mode] = rs.result()
@@ -46,7 +48,7 @@ def main():
     if rank == 0:
         full = vq.FeatureStore(n_local * world, S, [1], 1024, devices=[local])
         full.fill_synthetic(seed)
-        res = full.scan({s: {1: T[i, 0]} for i, s in enumerate(S)}, (1.0, 1.5), 0.8, 0.73, 3e-6, topk=k)
+        res = full.scan({s: {1: T[i, 0]} for i, s in enumerate(S)}, (1.0, 1.5), 0.75 + 0.01 * 6, 0.73, 3e-6, topk=k)
         rows, scores = full.topk()
         for mode, (counts, g_rows, g_scores) in results.items():
             same = (counts[0] == res.n_match and counts[1] == res.n_near and counts[2] == res.n_tie and

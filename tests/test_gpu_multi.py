@@ -21,4 +21,4 @@ def test_sharded_scan_equals_single_gpu_scan():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0
-    assert "exchange p2p" in r.stdout and "exchange nccl" in r.stdout
+    assert "exchange p2p:" in r.stdout and "exchange p2p-lagged:" in r.stdout and "exchange nccl:" in r.stdout

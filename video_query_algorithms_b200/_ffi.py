@@ -72,6 +72,8 @@ PROTOTYPES = {
     "vq_exchange_connect": (C.c_int, [_vp, _vp]),
     "vq_exchange_destroy": (C.c_int, [_vp]),
     "vq_scan_exchange_enqueue": (C.c_int, [_vp, _vp, _vp]),
+    "vq_scan_exchange_enqueue_lagged": (C.c_int, [_vp, _vp, _vp]),
+    "vq_exchange_flush_enqueue": (C.c_int, [_vp, _vp]),
     "vq_exchange_merged": (C.c_int, [_vp, _P(_vp)]),
     "vq_scan_kernel_times": (C.c_int, [_vp, _i32, _vp, _P(_i32)]),
     "vq_merge_topk": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _P(_i32)]),

@@ -4,27 +4,36 @@
 // k = 100).  Instead of an NCCL allgather followed by a merge kernel, each rank runs ONE single-block
 // kernel right behind its selection kernels: it stores its payload straight into every peer's inbox over
 // NVLink (peer pointers obtained through CUDA IPC), publishes a sequence flag with system-scope release
-// semantics, waits for the flags of all peers in its own inbox and merges.  Two inbox slots (sequence
-// parity) are enough: a rank cannot get two steps ahead, because finishing step i+1 needs every peer's
-// step-(i+1) payload, which a peer only sends after it has consumed step i.
+// semantics, waits for the flags of all peers in its own inbox and merges.
+// Two modes.  In-step: kernel i pushes payload i and merges step i (a rank cannot get two steps ahead, because
+// finishing step i+1 needs every peer's step-(i+1) payload).  Lagged (a stream of queries): kernel i pushes payload i
+// and merges step i-1, whose payloads the peers pushed a whole scan ago — no rank ever waits for the slowest rank of
+// the current step, ranks may drift by one step, and a flush kernel merges the last step.  Four inbox slots
+// (sequence mod 4) make the lagged mode safe: push i overwrites the slot of step i-4, which a peer reads in its
+// kernel i-3; before kernel i starts, this rank's kernel i-1 has seen every peer's flag i-2, i.e. every peer has
+// entered its kernel i-2 and therefore finished its kernel i-3.
 #include <string.h>
 
 #include "vq_internal.cuh"
 
 struct vq_exchange {
     int device = 0, world = 1, rank = 0;
-    long long *inbox = nullptr;                 // [2][world][kSlot] payloads, then [2][world] flags; IPC-exported
+    long long *inbox = nullptr;                 // [kSlots][world][kSlot] payloads, then [kSlots][world] flags; IPC-exported
     long long *peer_inbox[64] = {nullptr};      // mapped inboxes of all ranks (own = inbox)
     long long **peer_table_dev = nullptr;       // device copy of peer_inbox
     long long *merged = nullptr;                // [kSlot]
     long long *scratch = nullptr;               // [world][kSlot] private copy of the gathered payloads
     unsigned long long seq = 0;
     bool connected = false;
+    bool unmerged = false;                      // lagged mode: the last pushed step has not been merged yet
+    int topk = 0;
+    cudaStream_t stream = nullptr;
 };
 
 namespace {
 constexpr int kSlot = 4 + 2 * VQ_MAX_TOPK;      // int64 per payload slot
-__host__ __device__ inline size_t flags_offset(int world) { return (size_t)2 * world * kSlot; }
+constexpr int kSlots = 4;                       // inbox slots (sequence number mod 4)
+__host__ __device__ inline size_t flags_offset(int world) { return (size_t)kSlots * world * kSlot; }
 
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -42,28 +51,32 @@ __device__ __forceinline__ long long ld_volatile(const long long *p) {
 
 __global__ void __launch_bounds__(1024)
 exchange_push_merge(const long long *__restrict__ payload, long long *const *__restrict__ peers, const int world,
-                    const int rank, const int k, const unsigned long long seq, long long *merged,
-                    long long *scratch) {
+                    const int rank, const int k, const unsigned long long push_seq /* 0: nothing to push */,
+                    const unsigned long long merge_seq /* 0: nothing to merge */, long long *merged, long long *scratch) {
     const int n_pay = 4 + 2 * k;
-    const int slot = (int)(seq & 1ull);
-    // 1. push my payload into slot [slot][rank] of every inbox (own included)
-    for (int i = threadIdx.x; i < n_pay * world; i += blockDim.x) {
-        const int r = i / n_pay, j = i - r * n_pay;
-        peers[r][((size_t)slot * world + rank) * kSlot + j] = payload[j];
+    if (push_seq) {
+        // 1. push my payload into slot [push_seq mod 4][rank] of every inbox (own included)
+        const int slot = (int)(push_seq % kSlots);
+        for (int i = threadIdx.x; i < n_pay * world; i += blockDim.x) {
+            const int r = i / n_pay, j = i - r * n_pay;
+            peers[r][((size_t)slot * world + rank) * kSlot + j] = payload[j];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < world) {
+            unsigned long long *flag =
+                reinterpret_cast<unsigned long long *>(peers[threadIdx.x] + flags_offset(world)) + (size_t)slot * world + rank;
+            st_release_sys(flag, push_seq);
+        }
     }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < world) {
-        unsigned long long *flag =
-            reinterpret_cast<unsigned long long *>(peers[threadIdx.x] + flags_offset(world)) + (size_t)slot * world + rank;
-        st_release_sys(flag, seq);
-    }
-    // 2. wait until every rank's payload for this sequence number has landed in my inbox
+    if (!merge_seq) return;
+    // 2. wait until every rank's payload for the sequence number to merge has landed in my inbox
+    const int slot = (int)(merge_seq % kSlots);
     long long *mine = peers[rank];
     if (threadIdx.x < world) {
         const unsigned long long *flag =
             reinterpret_cast<const unsigned long long *>(mine + flags_offset(world)) + (size_t)slot * world + threadIdx.x;
-        while (ld_acquire_sys(flag) != seq) __nanosleep(64);
+        while (ld_acquire_sys(flag) != merge_seq) __nanosleep(64);
     }
     __syncthreads();
     // 3. private copy of the gathered payloads (peer-written memory is read once, bypassing L1), then merge:
@@ -122,7 +135,7 @@ extern "C" int vq_exchange_create(vq_exchange **out, int device, int world, int 
     x->device = device;
     x->world = world;
     x->rank = rank;
-    const size_t bytes = (flags_offset(world) + (size_t)2 * world) * sizeof(long long);
+    const size_t bytes = (flags_offset(world) + (size_t)kSlots * world) * sizeof(long long);
     if (cudaMalloc((void **)&x->inbox, bytes) != cudaSuccess || cudaMalloc((void **)&x->merged, kSlot * 8) != cudaSuccess ||
         cudaMalloc((void **)&x->scratch, (size_t)world * kSlot * 8) != cudaSuccess ||
         cudaMalloc((void **)&x->peer_table_dev, 64 * sizeof(long long *)) != cudaSuccess) {
@@ -177,19 +190,41 @@ extern "C" int vq_exchange_destroy(vq_exchange *x) {
     return 0;
 }
 
-extern "C" int vq_scan_exchange_enqueue(vq_store *s, vq_exchange *x, void *stream) {
-    VQ_REQUIRE(s && x, "vq_scan_exchange_enqueue: null argument");
-    VQ_REQUIRE(x->connected || x->world == 1, "vq_scan_exchange_enqueue: exchange is not connected");
-    VQ_REQUIRE(s->device == x->device, "vq_scan_exchange_enqueue: store and exchange live on different devices");
+static int exchange_enqueue(vq_store *s, vq_exchange *x, void *stream, bool lagged, const char *who) {
+    VQ_REQUIRE(s && x, "%s: null argument", who);
+    VQ_REQUIRE(x->connected || x->world == 1, "%s: exchange is not connected", who);
+    VQ_REQUIRE(s->device == x->device, "%s: store and exchange live on different devices", who);
     VQ_CUDA(cudaSetDevice(x->device));
     if (x->world == 1 && !x->connected) {
         VQ_CUDA(cudaMemcpy(x->peer_table_dev, x->peer_inbox, 64 * sizeof(long long *), cudaMemcpyHostToDevice));
         x->connected = true;
     }
     x->seq += 1;
-    exchange_push_merge<<<1, 1024, 0, stream ? (cudaStream_t)stream : s->stream>>>(
-        (const long long *)s->pack, x->peer_table_dev, x->world, x->rank, s->last_topk, x->seq, x->merged, x->scratch);
+    x->topk = s->last_topk;
+    x->stream = stream ? (cudaStream_t)stream : s->stream;
+    exchange_push_merge<<<1, 1024, 0, x->stream>>>((const long long *)s->pack, x->peer_table_dev, x->world, x->rank, x->topk,
+                                                   x->seq, lagged ? x->seq - 1 : x->seq, x->merged, x->scratch);
     VQ_CUDA(cudaGetLastError());
+    x->unmerged = lagged;
+    return 0;
+}
+
+extern "C" int vq_scan_exchange_enqueue(vq_store *s, vq_exchange *x, void *stream) {
+    return exchange_enqueue(s, x, stream, false, "vq_scan_exchange_enqueue");
+}
+
+extern "C" int vq_scan_exchange_enqueue_lagged(vq_store *s, vq_exchange *x, void *stream) {
+    return exchange_enqueue(s, x, stream, true, "vq_scan_exchange_enqueue_lagged");
+}
+
+extern "C" int vq_exchange_flush_enqueue(vq_exchange *x, void *stream) {
+    VQ_REQUIRE(x, "vq_exchange_flush_enqueue: null exchange");
+    if (!x->unmerged || x->seq == 0) return 0;
+    VQ_CUDA(cudaSetDevice(x->device));
+    exchange_push_merge<<<1, 1024, 0, stream ? (cudaStream_t)stream : x->stream>>>(
+        nullptr, x->peer_table_dev, x->world, x->rank, x->topk, 0ull, x->seq, x->merged, x->scratch);
+    VQ_CUDA(cudaGetLastError());
+    x->unmerged = false;
     return 0;
 }
 

@@ -59,8 +59,10 @@ class _DevArray:
 class RankScan:
     """One rank's view: local shard handle + the exchange.  `dist` is torch.distributed (already
     initialised).  exchange = "p2p": payloads are stored straight into the peers' inboxes over NVLink and
-    merged by one kernel (vq_scan_exchange_enqueue, csrc/vq_exchange.cu); exchange = "nccl": one
-    all_gather_into_tensor + the merge kernel.  Everything is enqueued on the caller's stream."""
+    merged by one kernel (vq_scan_exchange_enqueue, csrc/vq_exchange.cu); exchange = "p2p-lagged": the same kernel
+    pushes step i and merges step i-1 (a stream of queries: ranks never wait for the slowest rank of the current
+    step; call flush() after the last step); exchange = "nccl": one all_gather_into_tensor + the merge kernel.
+    Everything is enqueued on the caller's stream."""
 
     def __init__(self, handle, k, device_index, dist=None, torch=None, exchange="p2p"):
         self.handle, self.k, self.device_index = handle, int(k), device_index
@@ -75,7 +77,7 @@ class RankScan:
         if self.exchange == "nccl":
             self.gathered = torch.zeros(self.world * self.n_payload, dtype=torch.int64, device=dev)
             self.merged = torch.zeros(self.n_payload, dtype=torch.int64, device=dev)
-        elif self.exchange == "p2p":
+        elif self.exchange in ("p2p", "p2p-lagged"):
             self._x = C.c_void_p()
             check(lib().vq_exchange_create(C.byref(self._x), device_index, self.world, self.rank), "vq_exchange_create")
             mine = np.zeros(64, np.uint8)
@@ -113,14 +115,22 @@ class RankScan:
               "vq_scan_enqueue")
         if self.exchange == "p2p":
             check(lib().vq_scan_exchange_enqueue(self.handle, self._x, C.c_void_p(stream_ptr)), "vq_scan_exchange_enqueue")
+        elif self.exchange == "p2p-lagged":
+            check(lib().vq_scan_exchange_enqueue_lagged(self.handle, self._x, C.c_void_p(stream_ptr)),
+                  "vq_scan_exchange_enqueue_lagged")
         elif self.exchange == "nccl":
             self.dist.all_gather_into_tensor(self.gathered, self._payload_view())
             check(lib().vq_merge_payloads_enqueue(self.device_index, C.c_void_p(self.gathered.data_ptr()), self.world,
                                                   self.k, C.c_void_p(self.merged.data_ptr()), C.c_void_p(stream_ptr)),
                   "vq_merge_payloads_enqueue")
 
+    def flush(self, stream_ptr):
+        """Lagged exchange: merge the last pushed step (enqueued; no host sync).  No-op for the other modes."""
+        if self.exchange == "p2p-lagged":
+            check(lib().vq_exchange_flush_enqueue(self._x, C.c_void_p(stream_ptr)), "vq_exchange_flush_enqueue")
+
     def kernels_per_step(self):
-        return 4 + {"none": 0, "p2p": 1, "nccl": 1}[self.exchange]
+        return 4 + {"none": 0, "p2p": 1, "p2p-lagged": 1, "nccl": 1}[self.exchange]
 
     def result(self):
         """(counts[4], global top-k rows, scores) after the stream has been synchronised."""
