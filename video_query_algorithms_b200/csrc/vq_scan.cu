@@ -10,6 +10,11 @@
 //                        candidates (radix select on (score, row) keys + bitonic sort), ranking
 //                        rule of ticket.py:266 (score descending, database order among equals).
 //   K2c select_compact   order-preserving compaction of the three row lists.
+//   publish_results      host-facing tail of vq_scan / vq_scan_select: counts, top-k and lists into a pinned,
+//                        device-mapped host mirror (one synchronisation per query, zero-copy views).
+//   gather_list          vq_gather_list: the entries at caller-drawn list positions (review rounds sample a few dozen
+//                        clips, ticket.py:333,341; the best near miss of ticket.py:335-340 is tracked by K2a / K2c).
+//   K7  rank_sort_*      vq_fetch_ranked: the whole match / near-miss list in report order (ticket.py:266).
 //
 // Summation order is fixed by the launch geometry, so results are deterministic run to run.
 #include <stdlib.h>
