@@ -191,7 +191,8 @@ int run_batch_bf16(vq_store *s, const float *targets, int n_queries, const vq_sc
     const long long first_rows = (long long)s->sm_count * bf::BM;
     const long long chunk_rows = (long long)s->sm_count * bf::BM * 16;
     const long long cap = chunk_rows + VQ_MAX_TOPK;
-    VQ_CUDA(cudaFuncSetAttribute(bf::batch_scan_bf16, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf::SMEM));
+    VQ_CUDA(cudaFuncSetAttribute(bf::batch_scan_bf16<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf::Ring<256>::SMEM));
+    VQ_CUDA(cudaFuncSetAttribute(bf::batch_scan_bf16<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf::Ring<128>::SMEM));
     BatchScratch *bs = nullptr;
     if (int r = get_batch_scratch(s, K, cap, &bs)) return r;
     Dev &d_t = bs->t, &d_t1 = bs->t1, &d_t2 = bs->t2, &d_cut = bs->cut, &d_counts = bs->counts, &d_cnt = bs->cnt,
@@ -216,8 +217,11 @@ int run_batch_bf16(vq_store *s, const float *targets, int n_queries, const vq_sc
         CUtensorMap map_a, map_t1, map_t2;
         if (s->n_rows > 0) {
             if ((rc = encode_map(&map_a, s->rows, K, (uint64_t)s->n_rows, bf::BM))) break;
-            if ((rc = encode_map_ex(&map_t1, d_t1.p, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, QN, QN, bf::BK, CU_TENSOR_MAP_SWIZZLE_64B))) break;
-            if ((rc = encode_map_ex(&map_t2, d_t2.p, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, QN, QN, bf::BK, CU_TENSOR_MAP_SWIZZLE_64B))) break;
+            // only the query rows in use are fetched per K block (the kernel is bound by the L2 -> SM fill rate)
+            const int n_mma_q = ((nq + 15) / 16) * 16;
+            const uint32_t t_rows = n_mma_q > 128 ? 256u : (n_mma_q > 64 ? 128u : 64u);
+            if ((rc = encode_map_ex(&map_t1, d_t1.p, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, QN, t_rows, bf::BK, CU_TENSOR_MAP_SWIZZLE_64B))) break;
+            if ((rc = encode_map_ex(&map_t2, d_t2.p, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, K, QN, t_rows, bf::BK, CU_TENSOR_MAP_SWIZZLE_64B))) break;
         }
         BatchArgs a;
         for (int i = 0; i < VQ_MAX_STREAMS; ++i) a.w[i] = (i < s->n_streams) ? (float)p->weights[i] : 0.f;
@@ -238,7 +242,7 @@ int run_batch_bf16(vq_store *s, const float *targets, int n_queries, const vq_sc
             a.n_tiles = (int)((nr + bf::BM - 1) / bf::BM);
             a.row_end = r0 + nr;
             const int units = a.n_tiles < s->sm_count ? a.n_tiles : s->sm_count;
-            bf::batch_scan_bf16<<<units, bf::THREADS, bf::SMEM, st>>>(
+            (a.n_mma > 128 ? bf::batch_scan_bf16<256> : bf::batch_scan_bf16<128>)<<<units, bf::THREADS, a.n_mma > 128 ? bf::Ring<256>::SMEM : bf::Ring<128>::SMEM, st>>>(
                 map_a, map_t1, map_t2, a, s->inv_counts, d_cut.as<float>(), d_counts.as<unsigned long long>(),
                 d_cnt.as<unsigned int>(), d_keys.as<unsigned long long>(), d_park.as<float>(),
                 scores_dbg_host ? d_dbg.as<float>() : nullptr, want_prof ? d_prof.as<long long>() : nullptr);

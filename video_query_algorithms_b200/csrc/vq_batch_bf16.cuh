@@ -40,21 +40,27 @@ constexpr int UK = 16;                   // UMMA K for bf16
 #define VQ_BF_GROUP_KB 4
 #endif
 constexpr int GROUP_KB = VQ_BF_GROUP_KB; // K blocks per partial accumulator
-constexpr int NA = 3;                            // fp32 clip-tile ring: TMA -> converters (released as soon as they have read it)
-constexpr int NXR = 4;                           // x1 / x2 ring: converters -> MMA (released by the MMA commits)
-constexpr int NT = 3;                            // t1 / t2 ring: TMA -> MMA (released by the MMA commits)
 constexpr uint32_t A32_BYTES = BM * BK * 4;      // 16 KB
 constexpr uint32_t X_BYTES = BM * BK * 2;        //  8 KB
-constexpr uint32_t T_BYTES = QN * BK * 2;        // 16 KB
-constexpr uint32_t RING_X = NA * A32_BYTES;                  // x1 at +0, x2 at +X_BYTES of a stage
-constexpr uint32_t RING_T = RING_X + NXR * 2 * X_BYTES;      // t1 at +0, t2 at +T_BYTES of a stage
-constexpr uint32_t RING_END = RING_T + NT * 2 * T_BYTES;     // 48 + 64 + 96 = 208 KB
 constexpr int THREADS = 512;
 constexpr int CONV_WARPS = 4;
 constexpr int EPI_WARPS = 8;
-constexpr int N_BARS = 2 * NA + 2 * NXR + 2 * NT + 4;
-constexpr size_t SMEM = (size_t)RING_END + 1024 /*align*/ + 256 /*barriers + tmem slot*/ + QN * 4 /*cut*/ +
-                        EPI_WARPS * 128 * 2 * 4 /*per-warp counts*/;
+// Shared-memory rings, by query tier QT (rows of a t1 / t2 tile: 256, or 128 for batches of <= 128 queries).  With
+// 128-row query tiles the t ring is half as large and the fp32 ring twice as deep: small batches are bound by the
+// bytes in flight towards HBM (3 stages x 16 KB per SM against ~1.5 us of latency is only ~3.5 TB/s chip-wide).
+template <int QT>
+struct Ring {
+    static constexpr int NA = QT > 128 ? 3 : 6;      // fp32 clip-tile ring: TMA -> converters (released as soon as they have read it)
+    static constexpr int NXR = 4;                    // x1 / x2 ring: converters -> MMA (released by the MMA commits)
+    static constexpr int NT = 3;                     // t1 / t2 ring: TMA -> MMA (released by the MMA commits)
+    static constexpr uint32_t T_BYTES = QT * BK * 2; // 16 KB / 8 KB per t1 (or t2) tile
+    static constexpr uint32_t RING_X = NA * A32_BYTES;                  // x1 at +0, x2 at +X_BYTES of a stage
+    static constexpr uint32_t RING_T = RING_X + NXR * 2 * X_BYTES;      // t1 at +0, t2 at +T_BYTES of a stage
+    static constexpr uint32_t RING_END = RING_T + NT * 2 * T_BYTES;     // 48 + 64 + 96 = 208 KB / 96 + 64 + 48 = 208 KB
+    static constexpr int N_BARS = 2 * NA + 2 * NXR + 2 * NT + 4;
+    static constexpr size_t SMEM = (size_t)RING_END + 1024 /*align*/ + 256 /*barriers + tmem slot*/ + QN * 4 /*cut*/ +
+                                   EPI_WARPS * 128 * 2 * 4 /*per-warp counts*/;
+};
 // shared-memory descriptor high word: SBO = 512 B (8 rows of 64 B), descriptor version 1, SWIZZLE_64B
 constexpr uint32_t DESC_HI64 = (512u >> 4) | (1u << 14) | (4u << 29);
 
@@ -191,11 +197,72 @@ __global__ void split_targets_bf16(const float *__restrict__ t, unsigned short *
     t2[i] = (unsigned short)(q & 0xFFFFu);
 }
 
+// Converter role: fp32 clip tile -> x1, x2 bf16 tiles, for a group of 32 * ITEMS ... threads.
+// Work item = (row r, 8 consecutive dims c8): two 16 B chunks of the fp32 row -> one 16 B chunk of x1 and of x2.
+// 8 consecutive threads take rows (2p, 2p+1) x c8 = 0..3, which makes every quarter-warp phase of the 128-bit loads
+// and stores hit 8 distinct 16 B bank groups under both swizzles.  The loads of K block i+1 are issued before block i
+// is converted (software pipeline: shared-memory latency off the critical path).  ITEMS = items per thread and K
+// block: 4 for the four dedicated converter warps (t = 0..127), 2 when the four epilogue warps of an unused query
+// half join them (t = 0..255; batches of <= 128 queries are conversion-bound, not MMA-bound).
+template <int ITEMS, int QT>
+__device__ __forceinline__ void convert_blocks(const int t, const int lane, const int n_it, const uint32_t smem_base,
+                                               const uint32_t bar_afull, const uint32_t bar_aempty, const uint32_t bar_xfull,
+                                               const uint32_t bar_xempty, long long &c_wait, long long &c_wait2) {
+    constexpr int ROWS_PER_PASS = BM / ITEMS;                        // 32 or 64
+    constexpr int NA = Ring<QT>::NA, NXR = Ring<QT>::NXR;
+    constexpr uint32_t RING_X = Ring<QT>::RING_X;
+    const int rsub = (t >> 3) * 2 + ((t & 7) >> 2);                  // 0 .. ROWS_PER_PASS-1
+    const int c8 = t & 3;
+    const uint32_t src_off0 = (uint32_t)rsub * 128u + (uint32_t)(((2 * c8) ^ (rsub & 7)) * 16);
+    const uint32_t src_off1 = (uint32_t)rsub * 128u + (uint32_t)(((2 * c8 + 1) ^ (rsub & 7)) * 16);
+    const uint32_t dst_off = (uint32_t)rsub * 64u + (uint32_t)((c8 ^ ((rsub >> 1) & 3)) * 16);
+    float4 u[ITEMS], v[ITEMS];
+    auto load_block = [&](int it) {
+        const int sa = it % NA;
+        const long long t0 = VQ_CLOCK();
+        mbar_wait(bar_afull + 8 * sa, (it / NA) & 1);
+        c_wait += VQ_CLOCK() - t0;
+        const uint32_t src = smem_base + (uint32_t)sa * A32_BYTES;
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            u[j] = lds128(src + src_off0 + (uint32_t)(j * ROWS_PER_PASS * 128));
+            v[j] = lds128(src + src_off1 + (uint32_t)(j * ROWS_PER_PASS * 128));
+        }
+    };
+    if (n_it > 0) load_block(0);
+    for (int it = 0; it < n_it; ++it) {
+        const int sa = it % NA, sx = it % NXR;
+        uint4 p[ITEMS], q[ITEMS];
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) split8(u[j], v[j], p[j], q[j]);
+        // the fp32 stage is free as soon as its values sit in registers (the loads above have returned: split8 used them)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_aempty + 8 * sa);
+        if (it + 1 < n_it) load_block(it + 1);                       // next block's loads fly while this one is stored
+        const long long t1 = VQ_CLOCK();
+        mbar_wait(bar_xempty + 8 * sx, ((it / NXR) & 1) ^ 1);
+        c_wait2 += VQ_CLOCK() - t1;
+        const uint32_t dst = smem_base + RING_X + (uint32_t)sx * 2 * X_BYTES + dst_off;
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            sts128(dst + (uint32_t)(j * ROWS_PER_PASS * 64), p[j]);
+            sts128(dst + X_BYTES + (uint32_t)(j * ROWS_PER_PASS * 64), q[j]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (UMMA)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_xfull + 8 * sx);
+    }
+}
+
+template <int QT>
 __global__ void __launch_bounds__(THREADS, 1)
 batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_t1,
                 const __grid_constant__ CUtensorMap map_t2, const BatchArgs a, const float *__restrict__ inv_counts,
                 const float *__restrict__ cut_g, unsigned long long *counts_g /*[QN][2]*/, unsigned int *cand_cnt /*[QN]*/,
                 unsigned long long *cand_keys /*[QN][cap]*/, float *park_g /*[grid][QN][BM], L2 park only*/, float *scores_dbg /*[Q][n_rows] or null*/, long long *prof /*[grid][8] or null*/) {
+    using R = Ring<QT>;
+    constexpr int NA = R::NA, NXR = R::NXR, NT = R::NT, N_BARS = R::N_BARS;
+    constexpr uint32_t T_BYTES = R::T_BYTES, RING_X = R::RING_X, RING_T = R::RING_T, RING_END = R::RING_END;
     extern __shared__ unsigned char smem_raw[];
     unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + RING_END);
@@ -212,10 +279,10 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     if (threadIdx.x == 0) {
         for (int s = 0; s < NA; ++s) {
             mbar_init(bar_afull + 8 * s, 1);            // producer's expect_tx arrive + TMA bytes of the fp32 tile
-            mbar_init(bar_aempty + 8 * s, CONV_WARPS);  // one arrive per converter warp
+            mbar_init(bar_aempty + 8 * s, a.n_mma > 128 ? CONV_WARPS : 2 * CONV_WARPS);  // one arrive per converting warp
         }
         for (int s = 0; s < NXR; ++s) {
-            mbar_init(bar_xfull + 8 * s, CONV_WARPS);   // x1, x2 written
+            mbar_init(bar_xfull + 8 * s, a.n_mma > 128 ? CONV_WARPS : 2 * CONV_WARPS);   // x1, x2 written
             mbar_init(bar_xempty + 8 * s, 1);           // tcgen05.commit
         }
         for (int s = 0; s < NT; ++s) {
@@ -224,7 +291,7 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(bar_part_full + 8 * b, 1);           // tcgen05.commit
-            mbar_init(bar_part_empty + 8 * b, EPI_WARPS);  // one arrive per epilogue warp
+            mbar_init(bar_part_empty + 8 * b, a.n_mma > 128 ? EPI_WARPS : EPI_WARPS / 2);  // one arrive per draining epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -242,6 +309,9 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     const int kb_total = kbps * a.n_streams;
     const int n_mma = a.n_mma;                      // queries rounded up to 16: the N of every MMA
     constexpr int NPART = 2;                        // partial accumulators: TMEM columns 0-255 and 256-511
+    // batches of <= 128 queries leave the epilogue warps of the upper query half without work: they convert instead
+    const int conv_warps = n_mma > 128 ? CONV_WARPS : 2 * CONV_WARPS;
+    const uint32_t t_rows = n_mma > 128 ? 256u : (n_mma > 64 ? 128u : 64u);   // query rows fetched per t1 / t2 tile (host: same rule)
     // this CTA's K blocks in issue order: tiles blockIdx.x, +gridDim.x, ...; kb_total blocks each
     const int my_tiles = (a.n_tiles > (int)blockIdx.x) ? (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
     const int n_it = my_tiles * kb_total;
@@ -253,6 +323,8 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             if (lane == 0) {
                 int it = 0;
                 const uint64_t pol = policy_evict_first();
+                // (an L2 prefetch of the clip tiles 8-16 K blocks ahead was measured 4-6 % SLOWER: the kernel is bound by the
+                // L2 -> SM fill rate, ~6.3 KB/clk chip-wide, and prefetches only add L2 traffic)
                 for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
                     const int row = (int)(a.row0 + (long long)tile * BM);
                     for (int kb = 0; kb < kb_total; ++kb, ++it) {
@@ -272,7 +344,7 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                     mbar_wait(bar_tempty + 8 * s, ((it / NT) & 1) ^ 1);
                     const uint32_t base = smem_base + RING_T + (uint32_t)s * 2 * T_BYTES;
                     const int kb = it % kb_total;
-                    mbar_expect(bar_tfull + 8 * s, 2 * T_BYTES);
+                    mbar_expect(bar_tfull + 8 * s, 2 * t_rows * BK * 2);      // the tensor maps' box holds t_rows query rows
                     tma_load_2d_hint(base, &map_t1, kb * BK, 0, bar_tfull + 8 * s, pol);
                     tma_load_2d_hint(base + T_BYTES, &map_t2, kb * BK, 0, bar_tfull + 8 * s, pol);
                 }
@@ -343,59 +415,19 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     } else if (warp < 8) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
         // ---------------------------------------------------------------------- converter (warps 4-7, one per SM sub-partition)
-        // Work item = (row r, 8 consecutive dims c8): two 16 B chunks of the fp32 row -> one 16 B chunk of x1 and of x2.
-        // 8 consecutive threads take rows (2p, 2p+1) x c8 = 0..3, which makes every quarter-warp phase of the
-        // 128-bit loads and stores hit 8 distinct 16 B bank groups under both swizzles.  The loads of K block i+1
-        // are issued before block i is converted (software pipeline: shared-memory latency off the critical path).
-        const int t = threadIdx.x - 128;                             // 0..127
-        const int rsub = (t >> 3) * 2 + ((t & 7) >> 2);              // 0..31
-        const int c8 = t & 3;
-        const uint32_t src_off0 = (uint32_t)rsub * 128u + (uint32_t)(((2 * c8) ^ (rsub & 7)) * 16);
-        const uint32_t src_off1 = (uint32_t)rsub * 128u + (uint32_t)(((2 * c8 + 1) ^ (rsub & 7)) * 16);
-        const uint32_t dst_off = (uint32_t)rsub * 64u + (uint32_t)((c8 ^ ((rsub >> 1) & 3)) * 16);
         long long c_wait = 0, c_wait2 = 0;
-        float4 u[4], v[4];
-        auto load_block = [&](int it) {
-            const int sa = it % NA;
-            const long long t0 = VQ_CLOCK();
-            mbar_wait(bar_afull + 8 * sa, (it / NA) & 1);
-            c_wait += VQ_CLOCK() - t0;
-            const uint32_t src = smem_base + (uint32_t)sa * A32_BYTES;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {                            // 4 items per thread, 8 loads in flight
-                u[j] = lds128(src + src_off0 + (uint32_t)(j * 32 * 128));
-                v[j] = lds128(src + src_off1 + (uint32_t)(j * 32 * 128));
-            }
-        };
-        if (n_it > 0) load_block(0);
-        for (int it = 0; it < n_it; ++it) {
-            const int sa = it % NA, sx = it % NXR;
-            uint4 p[4], q[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) split8(u[j], v[j], p[j], q[j]);
-            // the fp32 stage is free as soon as its values sit in registers (the loads above have returned: split8 used them)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_aempty + 8 * sa);
-            if (it + 1 < n_it) load_block(it + 1);                   // next block's loads fly while this one is stored
-            const long long t1 = VQ_CLOCK();
-            mbar_wait(bar_xempty + 8 * sx, ((it / NXR) & 1) ^ 1);
-            c_wait2 += VQ_CLOCK() - t1;
-            const uint32_t dst = smem_base + RING_X + (uint32_t)sx * 2 * X_BYTES + dst_off;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                {
-                    sts128(dst + (uint32_t)(j * 32 * 64), p[j]);
-                    sts128(dst + X_BYTES + (uint32_t)(j * 32 * 64), q[j]);
-                }
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (UMMA)
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_xfull + 8 * sx);
-        }
+        const int t = threadIdx.x - 128;                             // 0..127
+        if (conv_warps == 2 * CONV_WARPS) convert_blocks<2, QT>(t, lane, n_it, smem_base, bar_afull, bar_aempty, bar_xfull, bar_xempty, c_wait, c_wait2);
+        else convert_blocks<4, QT>(t, lane, n_it, smem_base, bar_afull, bar_aempty, bar_xfull, bar_xempty, c_wait, c_wait2);
         if (prof && t == 0) { prof[blockIdx.x * 16 + 7] = c_wait; prof[blockIdx.x * 16 + 4] = c_wait2; }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
         // ------------------------------------------------------------------ epilogue (8 warps)
+        if (warp >= 12 && conv_warps == 2 * CONV_WARPS) {
+            // no queries in the upper half: these four warps are converter threads 128..255
+            long long cw = 0, cw2 = 0;
+            convert_blocks<2, QT>(threadIdx.x - 384 + 128, lane, n_it, smem_base, bar_afull, bar_aempty, bar_xfull, bar_xempty, cw, cw2);
+        }
         const int ew = warp - 8;                  // 0..7
         const int quarter = warp & 3;             // TMEM lanes 32*quarter .. +31 (hardware rule: warp id % 4)
         const int half = ew >> 2;                 // which 128 of the 256 queries this warp handles
@@ -407,7 +439,8 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         const uint64_t pol_park = policy_evict_last();
         int gcount = 0;
         long long e_wait = 0, e_busy = 0, e_score = 0, e_fin0 = 0, e_fin1 = 0, e_tiles = 0;
-        for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const bool drains = !(warp >= 12 && conv_warps == 2 * CONV_WARPS);     // the converting warps take no part in the epilogue
+        for (int tile = blockIdx.x; tile < a.n_tiles && drains; tile += gridDim.x) {
             const long long row = a.row0 + (long long)tile * BM + quarter * 32 + lane;
             const bool row_ok = row < a.row_end;
             for (int st = 0; st < a.n_streams; ++st) {
