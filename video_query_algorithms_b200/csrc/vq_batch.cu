@@ -202,6 +202,14 @@ int run_batch_bf16(vq_store *s, const float *targets, int n_queries, const vq_sc
     const bool want_prof = getenv("VQ_BATCH_PROF") != nullptr;
     if (want_prof) VQ_CUDA(d_prof.alloc((size_t)s->sm_count * 16 * 8));
     cudaEvent_t e0 = bs->e0, e1 = bs->e1;
+#ifdef VQ_BATCH_WATCHDOG          // development build (vq_tc.cuh): stuck barrier waits trap and are reported here
+    static unsigned long long *wd_host = nullptr;
+    if (!wd_host) {
+        VQ_CUDA(cudaMallocHost((void **)&wd_host, 256 * 16 * 2 * 8));
+        VQ_CUDA(cudaMemcpyToSymbol(vqtc::vq_watchdog_host, &wd_host, sizeof(wd_host)));
+    }
+    memset(wd_host, 0, 256 * 16 * 2 * 8);
+#endif
     float total_ms = 0.f;
     int rc = 0;
     for (int q0 = 0; q0 < n_queries && rc == 0; q0 += QN) {
@@ -253,6 +261,19 @@ int run_batch_bf16(vq_store *s, const float *targets, int n_queries, const vq_sc
                 VQ_CUDA(cudaMemsetAsync(d_cnt.p, 0, QN * 4, st));
         }
         VQ_CUDA(cudaEventRecord(e1, st));
+#ifdef VQ_BATCH_WATCHDOG
+        if (cudaStreamSynchronize(st) != cudaSuccess) {
+            for (int b = 0; b < 256; ++b)
+                for (int w = 0; w < 16; ++w) {
+                    const unsigned long long v = wd_host[(size_t)(b * 16 + w) * 2];
+                    if (v & 1ull)
+                        fprintf(stderr, "[K3 watchdog] block %d warp %d stuck on barrier 0x%llx (index %llu) parity %llu\n", b, w, v >> 32,
+                                ((v >> 32) & 0x3ffull) >> 3, (v >> 1) & 1ull);
+                }
+            vq::set_error("vq_scan_batch: watchdog trap (a barrier wait lasted more than 3e9 cycles)");
+            return -2;
+        }
+#endif
         if (want_prof) {
             std::vector<long long> h((size_t)s->sm_count * 16);
             VQ_CUDA(cudaMemcpyAsync(h.data(), d_prof.p, h.size() * 8, cudaMemcpyDeviceToHost, st));

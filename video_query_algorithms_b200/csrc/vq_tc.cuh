@@ -15,12 +15,37 @@ __device__ __forceinline__ void mbar_expect(uint32_t a, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t a) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
 }
+#ifdef VQ_BATCH_WATCHDOG
+// Development build: a wait that lasts longer than ~2 s records (block, warp, barrier address, parity) in mapped host
+// memory and traps, so that a protocol bug shows up as an error with a location instead of a hung GPU.
+__device__ unsigned long long *vq_watchdog_host = nullptr;
+__device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
+    const long long t0 = clock64();
+    while (true) {
+        uint32_t ok;
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+        if (ok) return;
+        if (clock64() - t0 > 3000000000ll) {
+            if ((threadIdx.x & 31) == 0 && vq_watchdog_host) {
+                unsigned long long *w = vq_watchdog_host + (size_t)(blockIdx.x * 16 + (threadIdx.x >> 5)) * 2;
+                w[0] = ((unsigned long long)a << 32) | (parity << 1) | 1ull;
+                w[1] = (unsigned long long)clock64();
+                __threadfence_system();
+            }
+            __nanosleep(100000000);
+            __trap();
+        }
+    }
+}
+#else
 __device__ __forceinline__ void mbar_wait(uint32_t a, uint32_t parity) {
     asm volatile(
         "{\n.reg .pred p;\nWAIT_%=:\n"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
         "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}" ::"r"(a), "r"(parity) : "memory");
 }
+#endif
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
