@@ -1,7 +1,7 @@
 """Development probe for K3: throughput and error of the batched tensor-core scan."""
 import sys, os, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 os.environ.setdefault("COMPUTE_EPS", ".000003")
 import video_query_algorithms_b200 as vq
 from oracle import synth, scoring as sc

@@ -1,8 +1,8 @@
 """BASELINE.json configs 4 and 5 on one B200 (config 2 = bench.py, config 3 per-GPU shard = bench.py
 --clips-per-gpu 12500000).  Prints one JSON object per config; results are copied into profiles/.
 
-  python tools/run_configs.py batched  [n_clips] [n_queries]
-  python tools/run_configs.py bootstrap [n_clips] [n_labelled] [n_replicates]
+  python tests/probes/run_configs.py batched  [n_clips] [n_queries]
+  python tests/probes/run_configs.py bootstrap [n_clips] [n_labelled] [n_replicates]
 """
 import json
 import os
@@ -12,7 +12,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 os.environ.setdefault("COMPUTE_EPS", ".000003")
 os.environ.setdefault("RANDOM_SEED", "73459912436")
