@@ -59,6 +59,11 @@ def test_product_package_never_imports_the_oracle_or_reference():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "/root/reference" not in text, f
+    # the oracle is test infrastructure: besides tests/, only smoke() and bench.py's CPU legs use it
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        if f.endswith((".py", ".sh")):
+            text = open(os.path.join(ROOT, "tools", f)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
 
 
 def test_sass_is_sm100a_only(built_lib):
