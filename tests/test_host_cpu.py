@@ -119,6 +119,39 @@ def test_random_fraction_consumes_rng_like_oracle():
     assert [sorted(r) for r in reps] == [sorted(ob.random_fraction(50, 1, True, random)) for _ in range(3)]
 
 
+def test_vectorised_choices_reproduce_pythons_stream_exactly():
+    """_rng.choices_range draws `random.choices(range(n), k=k)` through numpy's MT19937 from the caller's own
+    generator state: same indices, same generator state afterwards (so every later draw is unchanged), for the
+    `random` module and for Random instances, with a pending gauss value preserved."""
+    from video_query_algorithms_b200._rng import choices_range, set_order, _cpython_set_table_size
+    for n, k, r in ((5000, 5000, 3), (1, 1, 1), (7, 3, 5), (41, 41, 1), (100000, 10, 2), (3, 1000, 1)):
+        random.seed("73459912436")
+        a = [random.choices(range(n), k=k) for _ in range(r)]
+        sa, nxt = random.getstate(), random.random()
+        random.seed("73459912436")
+        b = choices_range(random, n, k, repeats=r)
+        assert np.array_equal(np.asarray(a).reshape(b.shape), b) and random.getstate() == sa and random.random() == nxt
+    r1, r2 = random.Random(5), random.Random(5)
+    r1.gauss(0, 1), r2.gauss(0, 1)                                   # leaves gauss_next set
+    assert r1.choices(range(50), k=50) == choices_range(r2, 50, 50).tolist() and r1.getstate() == r2.getstate()
+    # list(set(draws)) without building the set when its order is known; the real set otherwise
+    rng = np.random.default_rng(0)
+    fallbacks = 0
+    for n in (1, 2, 5, 8, 9, 31, 33, 100, 1000, 5000, 20000, 70000, 300000):
+        for k in (1, 3, n // 3 + 1, n, 2 * n):
+            d = rng.integers(0, n, size=k)
+            fallbacks += n > _cpython_set_table_size(len(set(d.tolist())))
+            assert set_order(d, n).tolist() == list(set(d.tolist())), (n, k)
+    assert fallbacks > 5                                             # both branches were exercised
+    from video_query_algorithms_b200 import resample_labelled
+    random.seed(7)
+    reps = resample_labelled(300, 40, random)
+    s1 = random.getstate()
+    random.seed(7)
+    ref = [list(set(random.choices(range(300), k=300))) for _ in range(40)]
+    assert all(list(a) == b for a, b in zip(reps, ref)) and s1 == random.getstate()
+
+
 def test_sample_of_index_range_equals_sample_of_items():
     """select_clips_to_review samples index ranges; the reference samples dict items (ticket.py:333).
     Python's random.sample consumes the generator identically for equal (n, k)."""

@@ -13,6 +13,8 @@ import os
 
 import numpy as np
 
+from ._rng import choices_range, set_order
+
 from . import store as _store
 
 
@@ -137,8 +139,6 @@ class Hyperparameter:
 def resample_labelled(n_labelled, n_replicates, rng):
     """Replicate index sets exactly as the reference's bagging draws them: `random.choices(range(n), k=n)`
     then `list(set(...))` (target_clip.py:297-309 with fraction 1, replacement True)."""
-    out = []
-    for _ in range(n_replicates):
-        draws = rng.choices(range(n_labelled), k=max(round(n_labelled * 1), 1))
-        out.append(np.array(list(set(draws)), dtype=np.int32))
-    return out
+    draws = choices_range(rng, n_labelled, max(round(n_labelled * 1), 1), repeats=n_replicates)   # same stream as the
+    draws = draws.reshape(n_replicates, -1)                                                        # reference's choices calls
+    return [set_order(d, n_labelled).astype(np.int32) for d in draws]                            # the reference's set order

@@ -14,6 +14,8 @@ from time import sleep
 
 import numpy as np
 
+from ._rng import choices_range
+
 try:                                        # requests is only needed to recognise its ConnectionError
     from requests import ConnectionError
 except Exception:                           # pragma: no cover
@@ -176,7 +178,7 @@ class TargetClip:
         if replacement is False:
             picks = random.sample(range(n), t)
         else:
-            picks = random.choices(range(n), k=t)
+            picks = choices_range(random, n, t).tolist()          # same stream as random.choices, vectorised
         picks = list(set(picks))
         return np.asarray([flist[m] for m in picks], dtype=np.int64)
 
