@@ -7,6 +7,10 @@
 //   K6  gram / solve / combine   new target from labelled rows   (target_clip.py:161-261)
 #include <vector>
 
+#include <chrono>
+#include <mutex>
+#include <stdlib.h>
+
 #include "vq_internal.cuh"
 
 namespace {
@@ -330,6 +334,13 @@ extern "C" int vq_labelled_sims(vq_store *s, const double *target, const int64_t
     return 0;
 }
 
+namespace {
+struct ArenaView {
+    char *p;
+    template <class T> T *as() { return reinterpret_cast<T *>(p); }
+};
+}  // namespace
+
 extern "C" int vq_loss_grid(int device, const double *sims, const uint8_t *labels, int64_t L,
                             const double *weight_grid, int32_t n_w, const double *threshold_grid, int32_t n_th,
                             double ballast, const int32_t *rep_offset, const int32_t *rep_index, int32_t R,
@@ -344,28 +355,53 @@ extern "C" int vq_loss_grid(int device, const double *sims, const uint8_t *label
     for (int64_t i = 0; i < n_idx; ++i)
         VQ_REQUIRE(rep_index[i] >= 0 && rep_index[i] < L, "vq_loss_grid: replicate index out of range");
     VQ_CUDA(cudaSetDevice(device));
-    DevBuf d_sims, d_lab, d_w, d_th, d_off, d_idx, d_tab, d_out;
-    VQ_CUDA(d_sims.alloc((size_t)L * 2 * sizeof(double)));
-    VQ_CUDA(d_lab.alloc((size_t)L));
-    VQ_CUDA(d_w.alloc((size_t)n_w * sizeof(double)));
-    VQ_CUDA(d_th.alloc((size_t)n_th * sizeof(double)));
-    VQ_CUDA(d_off.alloc((size_t)(R + 1) * sizeof(int)));
-    VQ_CUDA(d_idx.alloc((size_t)n_idx * sizeof(int)));
-    VQ_CUDA(d_tab.alloc((size_t)L * n_w * sizeof(double)));
-    VQ_CUDA(d_out.alloc((size_t)R * n_w * n_th * sizeof(double)));
+    const bool timing = getenv("VQ_TIMING") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [&](std::chrono::steady_clock::time_point t) { return std::chrono::duration<double, std::milli>(now() - t).count(); };
+    auto t_start = now();
+    // One grow-only arena per device, kept for the life of the process: with a multi-gigabyte store resident, every
+    // cudaMalloc / cudaFree costs ~2 ms, which was most of this call (8 of each per call before).
+    struct Arena { char *p = nullptr; size_t cap = 0; };
+    static Arena arenas[64];
+    static std::mutex arena_mutex;
+    std::lock_guard<std::mutex> lock(arena_mutex);
+    VQ_REQUIRE(device >= 0 && device < 64, "vq_loss_grid: device %d", device);
+    const size_t sizes[8] = {(size_t)L * 2 * sizeof(double), (size_t)L, (size_t)n_w * sizeof(double), (size_t)n_th * sizeof(double),
+                             (size_t)(R + 1) * sizeof(int), (size_t)n_idx * sizeof(int), (size_t)L * n_w * sizeof(double),
+                             (size_t)R * n_w * n_th * sizeof(double)};
+    size_t offs[8], total = 0;
+    for (int i = 0; i < 8; ++i) { offs[i] = total; total += (sizes[i] + 255) & ~(size_t)255; }
+    Arena &ar = arenas[device];
+    if (total > ar.cap) {
+        if (ar.p) cudaFree(ar.p);
+        ar.p = nullptr;
+        ar.cap = 0;
+        const size_t want = total + total / 2;
+        VQ_CUDA(cudaMalloc((void **)&ar.p, want));
+        ar.cap = want;
+    }
+    ArenaView d_sims{ar.p + offs[0]}, d_lab{ar.p + offs[1]}, d_w{ar.p + offs[2]}, d_th{ar.p + offs[3]}, d_off{ar.p + offs[4]},
+        d_idx{ar.p + offs[5]}, d_tab{ar.p + offs[6]}, d_out{ar.p + offs[7]};
+    if (timing) fprintf(stderr, "[vq_loss_grid] alloc %.2f ms\n", ms_since(t_start));
+    t_start = now();
     VQ_CUDA(cudaMemcpy(d_sims.p, sims, (size_t)L * 2 * sizeof(double), cudaMemcpyHostToDevice));
     VQ_CUDA(cudaMemcpy(d_lab.p, labels, (size_t)L, cudaMemcpyHostToDevice));
     VQ_CUDA(cudaMemcpy(d_w.p, weight_grid, (size_t)n_w * sizeof(double), cudaMemcpyHostToDevice));
     VQ_CUDA(cudaMemcpy(d_th.p, threshold_grid, (size_t)n_th * sizeof(double), cudaMemcpyHostToDevice));
     VQ_CUDA(cudaMemcpy(d_off.p, rep_offset, (size_t)(R + 1) * sizeof(int), cudaMemcpyHostToDevice));
     VQ_CUDA(cudaMemcpy(d_idx.p, rep_index, (size_t)n_idx * sizeof(int), cudaMemcpyHostToDevice));
+    if (timing) fprintf(stderr, "[vq_loss_grid] h2d %.2f ms\n", ms_since(t_start));
+    t_start = now();
     score_table_kernel<<<(unsigned int)((L * n_w + 255) / 256), 256>>>(d_sims.as<double>(), L, d_w.as<double>(),
                                                                       n_w, d_tab.as<double>());
     loss_grid_kernel<<<(unsigned int)(R * n_w), kLossThreads>>>(d_tab.as<double>(), d_lab.as<unsigned char>(), L,
                                                                d_th.as<double>(), n_th, n_w, ballast,
                                                                d_off.as<int>(), d_idx.as<int>(), d_out.as<double>());
     VQ_CUDA(cudaGetLastError());
+    if (timing) { cudaDeviceSynchronize(); fprintf(stderr, "[vq_loss_grid] kernels %.2f ms\n", ms_since(t_start)); }
+    t_start = now();
     VQ_CUDA(cudaMemcpy(losses_out, d_out.p, (size_t)R * n_w * n_th * sizeof(double), cudaMemcpyDeviceToHost));
+    if (timing) fprintf(stderr, "[vq_loss_grid] d2h %.2f ms\n", ms_since(t_start));
     return 0;
 }
 

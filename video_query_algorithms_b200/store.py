@@ -88,6 +88,7 @@ class FeatureStore:
                                          self.first_global_row + lo))
         self.clip_ids = None
         self._row_of = None
+        self._row_memo = {}
         self.present = None          # bool [N, S, P] when some clip lacks some split, else None
         if clip_ids is not None:
             self.set_clip_ids(clip_ids)
@@ -98,20 +99,56 @@ class FeatureStore:
         self.clip_ids = np.asarray(clip_ids, dtype=np.int64)
         assert self.clip_ids.shape == (self.n_rows,)
         self._row_of = None
+        self._row_memo = {}
 
     def _index(self):
+        """(sorted clip ids, their local rows): the id -> row table as two arrays, looked up by binary search.  A search
+        set of a million clips makes a Python dict a 100 ms, 100 MB affair; an id table that is already ascending (the
+        usual case: ids are issued in insertion order) needs no work at all."""
         if self._row_of is None:
-            self._row_of = {int(c): i for i, c in enumerate(self.clip_ids)}
+            ids = self.clip_ids
+            if ids.size < 2 or bool(np.all(ids[1:] > ids[:-1])):
+                self._row_of = (ids, None)
+            else:
+                order = np.argsort(ids, kind="stable")
+                self._row_of = (ids[order], order)
         return self._row_of
 
+    def _lookup(self, clip_ids):
+        """local rows of the given ids (-1 where the store does not hold the id); vectorised."""
+        sorted_ids, order = self._index()
+        q = np.asarray(clip_ids, dtype=np.int64).reshape(-1)
+        pos = np.searchsorted(sorted_ids, q)
+        pos_c = np.minimum(pos, max(len(sorted_ids) - 1, 0))
+        hit = (len(sorted_ids) > 0) & (sorted_ids[pos_c] == q) if len(sorted_ids) else np.zeros(len(q), bool)
+        rows = pos_c if order is None else order[pos_c]
+        return np.where(hit, rows, -1)
+
+    def _row_or_minus1(self, clip_id):
+        """scalar lookup, memoised (labelled clips are looked up again and again across rounds)"""
+        memo = self.__dict__.setdefault("_row_memo", {})
+        c = int(clip_id)
+        r = memo.get(c)
+        if r is None:
+            r = int(self._lookup([c])[0])
+            if len(memo) < 1_000_000:
+                memo[c] = r
+        return r
+
     def row_of(self, clip_id):
-        return self._index()[int(clip_id)]
+        r = self._row_or_minus1(clip_id)
+        if r < 0:
+            raise KeyError(clip_id)
+        return r
 
     def has_clip(self, clip_id):
-        return clip_id is not None and int(clip_id) in self._index()
+        return clip_id is not None and self._row_or_minus1(clip_id) >= 0
 
     def rows_of(self, clip_ids):
-        return np.array([self.first_global_row + self.row_of(c) for c in clip_ids], dtype=np.int64)
+        rows = self._lookup(clip_ids)
+        if (rows < 0).any():
+            raise KeyError(int(np.asarray(clip_ids).reshape(-1)[int(np.argmax(rows < 0))]))
+        return (self.first_global_row + rows).astype(np.int64)
 
     def _shard_of(self, global_row):
         for sh in self.shards:
@@ -182,8 +219,7 @@ class FeatureStore:
             if clip_ids is None or len(clip_ids) != n_new:
                 raise VQError("append: the store has a clip-id table; pass the %d new clip ids" % n_new)
             new_ids = np.asarray(clip_ids, dtype=np.int64)
-            known = self._index()
-            dup = [int(c) for c in new_ids if int(c) in known]
+            dup = [int(c) for c in new_ids[self._lookup(new_ids) >= 0]]
             if dup or len(set(new_ids.tolist())) != n_new:
                 raise VQError("append: clip ids already in the store or repeated: %s" % (dup[:5] or "repeated ids"))
         sh = self.shards[-1]
@@ -193,6 +229,7 @@ class FeatureStore:
         if self.clip_ids is not None:
             self.clip_ids = np.concatenate([self.clip_ids, new_ids])
             self._row_of = None
+            self._row_memo = {}
         if self.present is not None or present is not None:
             old = self.present if self.present is not None else np.ones((self.n_rows - n_new,) + self.row_shape[:2], bool)
             new = np.ones((n_new,) + self.row_shape[:2], bool) if present is None else np.asarray(present, dtype=bool)
@@ -209,9 +246,12 @@ class FeatureStore:
         for tf in feature_rows:
             if tf["dnn_stream_id"] in s_of and tf["name"] == feature_name:
                 c = tf["video_clip_id"]
-                if c not in seen and not self.has_clip(c):
+                if c not in seen:
                     seen.add(c)
                     order.append(c)
+        if order:                                                   # one vectorised lookup: keep the ids the store lacks
+            held = self._lookup(order) >= 0
+            order = [c for c, h in zip(order, held) if not h]
         if not order:
             return 0
         row = {c: i for i, c in enumerate(order)}
