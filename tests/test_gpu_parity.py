@@ -311,6 +311,11 @@ def test_two_shards_merge_like_one(vq):
         ra, sa = getattr(one, f)()
         rb, sb = getattr(two, f)()
         assert np.array_equal(ra, rb) and np.array_equal(sa, sb)
+    # batched path: the shards are scanned concurrently (one thread each) and the per-query top-k merged on the host
+    Tq = np.stack([sc.scale_target(X[r].astype(np.float64)) for r in (5, 4600, 8999)]).astype(np.float32)
+    ca, ra, sa, _ = one.scan_batch(Tq, (1.0, 1.5), 0.8, 0.73, topk=25)
+    cb, rb, sb, _ = two.scan_batch(Tq, (1.0, 1.5), 0.8, 0.73, topk=25)
+    assert np.array_equal(ca, cb) and np.array_equal(ra, rb) and np.array_equal(sa, sb)
     one.close()
     two.close()
 

@@ -547,18 +547,34 @@ class FeatureStore:
             return out
         counts = np.zeros((Q, 2), np.int64)
         k = max(topk, 1)
-        rows_l, sc_l, ms = [], [], 0.0
-        for sh in self.shards:
-            c = np.zeros((Q, 2), np.int64)
-            r = np.full((Q, k), -1, np.int64)
-            s_ = np.full((Q, k), -np.inf, np.float32)
-            t_ms = C.c_float()
-            check(lib().vq_scan_batch(sh.handle, ptr(T), Q, C.byref(p), ptr(c), ptr(r), ptr(s_), C.byref(t_ms)),
-                  "vq_scan_batch")
+        n_sh = len(self.shards)
+        c_l = [np.zeros((Q, 2), np.int64) for _ in range(n_sh)]
+        rows_l = [np.full((Q, k), -1, np.int64) for _ in range(n_sh)]
+        sc_l = [np.full((Q, k), -np.inf, np.float32) for _ in range(n_sh)]
+        ms_l = [C.c_float() for _ in range(n_sh)]
+        errs = []
+
+        def run(i):                                   # one call per shard; ctypes releases the GIL, devices run concurrently
+            try:
+                check(lib().vq_scan_batch(self.shards[i].handle, ptr(T), Q, C.byref(p), ptr(c_l[i]), ptr(rows_l[i]),
+                                          ptr(sc_l[i]), C.byref(ms_l[i])), "vq_scan_batch")
+            except Exception as e:                    # surfaced below
+                errs.append(e)
+
+        if n_sh == 1:
+            run(0)
+        else:
+            import threading
+            ts = [threading.Thread(target=run, args=(i,)) for i in range(n_sh)]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
+        if errs:
+            raise errs[0]
+        for c in c_l:
             counts += c
-            rows_l.append(r)
-            sc_l.append(s_)
-            ms = max(ms, t_ms.value)
+        ms = max(m.value for m in ms_l)
         if topk == 0:
             return counts, np.empty((Q, 0), np.int64), np.empty((Q, 0), np.float32), ms
         if len(self.shards) == 1:
