@@ -18,6 +18,7 @@ import hashlib
 import json
 import os
 import random
+import time
 import sys
 import tempfile
 import types
@@ -172,6 +173,9 @@ class Recorder:
 
 
 def save_scenario(name, rounds, meta):
+    if os.environ.get("VQ_GOLDEN_TIMING_ONLY"):
+        print("timings after", name, json.dumps(TIMINGS[-len(rounds):]))
+        return
     arrays, js = {}, {"meta": meta, "rounds": []}
     for i, r in enumerate(rounds):
         streams = meta["streams"]
@@ -192,6 +196,9 @@ def save_scenario(name, rounds, meta):
         json.dump(js, f, indent=1, sort_keys=True)
 
 
+TIMINGS = []           # wall time of every reference compute_matches call (VQ_GOLDEN_TIMING_ONLY=1: print, write nothing)
+
+
 def run_rounds(api, repo_cls, hp_kwargs, plan, rec, qid):
     """plan: list of (kind, label_rule or None applied BEFORE that round)."""
     from models.compute_matches import compute_matches
@@ -204,7 +211,10 @@ def run_rounds(api, repo_cls, hp_kwargs, plan, rec, qid):
         repo = repo_cls("http://fake/")
         hp = Hyperparameter(**hp_kwargs)
         random.seed(a=os.environ["RANDOM_SEED"])       # reference src/broker.py:83-84
+        t0 = time.perf_counter()
         compute_matches(repo, hp)
+        TIMINGS.append({"query": qid, "kind": kind, "reference_compute_matches_s": time.perf_counter() - t0,
+                        "n_clips": len(getattr(api, "clip_ids", [])) or None})
         q = api.queries[qid]
         rec.cur.update({"kind": kind, "weights": [float(hp.weights[s]) for s in hp.streams],
                         "threshold": float(hp.threshold), "process_state": q["process_state"],
