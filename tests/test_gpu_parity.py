@@ -377,6 +377,59 @@ def test_append_grows_the_store_like_a_rebuild(vq):
     two.close()
 
 
+def test_exchange_kernel_in_step_lagged_and_flush_on_one_rank(vq):
+    """The peer-memory exchange kernel with world = 1 (its own inbox is the only peer), so that the in-step / lagged /
+    flush logic and the four inbox slots are exercised on a single-GPU box too: in-step merges step i, lagged
+    leaves step i-1 in the merged buffer until the flush.  (The multi-rank run is tests/test_gpu_multi.py.)"""
+    import ctypes as C
+    import torch
+    from video_query_algorithms_b200 import _ffi
+    from video_query_algorithms_b200.store import make_params
+    from video_query_algorithms_b200.sharded import unpack_payload
+    lib = _ffi.lib()
+    n, k = 20000, 32
+    st = vq.FeatureStore(n, STREAMS, [1], 1024, devices=[0], first_global_row=1000)
+    st.fill_synthetic(99)
+    ref = synth.pick_reference_row(99, n)
+    T = sc.scale_target(synth.rows(99, [ref]).astype(np.float64)[0][:, None, :])
+    target = torch.from_numpy(T.astype(np.float32).reshape(-1)).to("cuda:0")
+    h = st.shards[0].handle
+    stream = torch.cuda.Stream()
+    x = C.c_void_p()
+    _ffi.check(lib.vq_exchange_create(C.byref(x), 0, 1, 0), "vq_exchange_create")
+    mp = C.c_void_p()
+    _ffi.check(lib.vq_exchange_merged(x, C.byref(mp)), "vq_exchange_merged")
+
+    from video_query_algorithms_b200.sharded import _DevArray
+    merged_t = torch.as_tensor(_DevArray(mp.value, 4 + 2 * k), device=torch.device("cuda", 0))   # zero-copy view, as RankScan does
+
+    def merged():
+        torch.cuda.synchronize()
+        return unpack_payload(merged_t.cpu().numpy(), k)
+
+    def expected(th):
+        res = st.scan(tdict(T), (1.0, 1.5), th, 0.73, EPS, topk=k)
+        return (res.n_match, res.n_near, res.n_tie), st.topk()
+
+    ths = [0.76 + 0.01 * i for i in range(6)]                  # six steps: every inbox slot is reused at least once
+    want = [expected(th) for th in ths]
+    for lagged in (False, True):
+        for i, th in enumerate(ths):
+            p = make_params((1.0, 1.5), th, 0.73, EPS, topk=k)
+            _ffi.check(lib.vq_scan_enqueue(h, C.c_void_p(target.data_ptr()), C.byref(p), C.c_void_p(stream.cuda_stream)), "enqueue")
+            fn = lib.vq_scan_exchange_enqueue_lagged if lagged else lib.vq_scan_exchange_enqueue
+            _ffi.check(fn(h, x, C.c_void_p(stream.cuda_stream)), "exchange")
+            counts, rows, scores = merged()
+            j = i - 1 if lagged else i                           # lagged: the previous step's result
+            if j >= 0 and not (lagged and i == 0):
+                assert tuple(counts[:3]) == want[j][0] and np.array_equal(rows, want[j][1][0]) and np.array_equal(scores, want[j][1][1])
+        _ffi.check(lib.vq_exchange_flush_enqueue(x, C.c_void_p(stream.cuda_stream)), "flush")
+        counts, rows, scores = merged()
+        assert tuple(counts[:3]) == want[-1][0] and np.array_equal(rows, want[-1][1][0]) and np.array_equal(scores, want[-1][1][1])
+    _ffi.check(lib.vq_exchange_destroy(x), "vq_exchange_destroy")
+    st.close()
+
+
 # ---------------------------------------------------------------------------- batched queries (tcgen05)
 @pytest.mark.parametrize("n,nq", [(5003, 70), (300, 3), (20000, 300)])
 def test_batched_tensor_core_scan_matches_oracle(vq, n, nq):
