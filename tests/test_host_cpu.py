@@ -41,6 +41,22 @@ def test_library_exports_every_declared_symbol(built_lib):
     assert built_lib.lib().vq_abi_version() == 1
 
 
+def test_header_is_plain_c(tmp_path):
+    """include/vq.h is the boundary a non-Python host binds: it must compile as C99 on its own (no C++, no CUDA, no torch
+    types), and the minimal use shown in INTEGRATION.md must type-check against it."""
+    src = tmp_path / "use_vq.c"
+    src.write_text('#include "vq.h"\n'
+                   'int use(vq_store *s, const float *target, long long *rows, float *scores) {\n'
+                   '    vq_scan_params p = {{1.0, 1.5}, 0.8, 0.73, 3e-6, 100, 0};\n'
+                   '    vq_scan_counts c;\n'
+                   '    if (vq_scan(s, target, &p, &c)) return 1;\n'
+                   '    return vq_fetch_matches(s, c.n_match, (int64_t *)rows, scores);\n'
+                   '}\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
+                        str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
 def test_no_gpu_means_loud_failure_not_fallback(built_lib):
     import video_query_algorithms_b200 as vq
     n = ctypes.c_int()
