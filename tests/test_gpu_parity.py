@@ -222,6 +222,28 @@ def test_selection_scan_gathers_what_the_full_lists_hold(vq):
         st.close()
 
 
+def test_lists_larger_than_the_host_mirror_grow_it(vq):
+    """The pinned host mirror starts at max(n/8, 65536) entries per list; a scan whose lists are longer sets the
+    overflow flag, the mirror grows and the lists are published again: whole-store match list, then a whole-store
+    near-miss list, then a normal scan, all equal to what the scores say."""
+    n = 200_000
+    st = vq.FeatureStore(n, STREAMS, [1], 1024, devices=[0], first_global_row=7)
+    st.fill_synthetic(4)
+    ref = synth.pick_reference_row(4, n)
+    T = sc.scale_target(synth.rows(4, [ref]).astype(np.float64)[0][:, None, :])
+    for th, lo in ((-5.0, -6.0), (5.0, -5.0), (0.8, 0.73)):
+        res = st.scan(tdict(T), (1.0, 1.5), th, lo, EPS, topk=10)
+        got = st.scores().astype(np.float64)
+        want_m = np.flatnonzero(got >= th) + 7
+        want_n = np.flatnonzero((got >= lo) & (got < th)) + 7
+        for copy in (False, True):
+            m, nm = st.matches(copy=copy), st.near_misses(copy=copy)
+            assert res.n_match == len(want_m) and np.array_equal(m[0], want_m) and np.array_equal(m[1], got[want_m - 7].astype(np.float32))
+            assert res.n_near == len(want_n) and np.array_equal(nm[0], want_n)
+    assert res.n_match < 65536 < n                                  # the first two scans overflowed the initial mirror
+    st.close()
+
+
 def test_scan_handles_empty_store(vq):
     st = vq.FeatureStore(0, STREAMS, [1], 1024, devices=[0])
     T = np.ones((2, 1, 1024))
