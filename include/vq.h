@@ -158,6 +158,10 @@ int vq_scan_kernel_times(vq_store *s, int32_t cap, float *ms_out, int32_t *n_out
  * NCCL allgather merge; lists: [n_lists][k] with -inf / -1 padding.                          */
 int vq_merge_topk(int32_t n_lists, int32_t k, const float *scores, const int64_t *rows,
                   float *scores_out, int64_t *rows_out, int32_t *n_out);
+/* the same for Q queries at once (per-shard / per-rank results of vq_scan_batch): lists
+ * [n_lists][n_queries][k] -> [n_queries][k] (padded with -inf / -1), n_out [n_queries].      */
+int vq_merge_topk_batch(int32_t n_lists, int32_t n_queries, int32_t k, const float *scores,
+                        const int64_t *rows, float *scores_out, int64_t *rows_out, int32_t *n_out);
 
 /* ---------------------------------------------------------------- labelled subset, fp64 (A6, A8)
  * Similarities of a short list of rows against an fp64 target, fp64 accumulation

@@ -44,10 +44,39 @@ def main():
         dist.barrier()
         results[mode] = rs.result()
         rs.close()
+    # the other exchanges of SURVEY §8(e) through RankStore: ordered lists, batched per-query top-k, labelled sims
+    from video_query_algorithms_b200.sharded import RankStore
+    rstore = RankStore(st, dist, torch, dev)
+    tf = {s: {1: T[i, 0]} for i, s in enumerate(S)}
+    r_counts, r_lists, (r_trows, r_tsc) = rstore.scan(tf, (1.0, 1.5), 0.81, 0.73, 3e-6, topk=k)
+    nq = 24
+    Tq = np.stack([sc.scale_target(synth.rows(seed, [100 + 977 * q]).astype(np.float64)[0][:, None, :]) for q in range(nq)])
+    Tq = Tq.astype(np.float32)
+    b_counts, b_rows, b_sc, _ = rstore.scan_batch(Tq, (1.0, 1.5), 0.81, 0.73, topk=17)
+    z_counts, z_rows, _, _ = rstore.scan_batch(Tq, (1.0, 1.5), 0.81, 0.73, topk=0)
+    labelled = np.arange(7, n_local * world, 997, dtype=np.int64)
+    l_sims = rstore.labelled_sims(tf, labelled)
     ok = True
     if rank == 0:
         full = vq.FeatureStore(n_local * world, S, [1], 1024, devices=[local])
         full.fill_synthetic(seed)
+        res = full.scan(tf, (1.0, 1.5), 0.81, 0.73, 3e-6, topk=k)
+        f_lists = [full.matches(), full.near_misses(), full.ties()]
+        f_trows, f_tsc = full.topk()
+        same = (list(r_counts) == [res.n_match, res.n_near, res.n_tie] and np.array_equal(r_trows, f_trows) and
+                np.array_equal(r_tsc, f_tsc) and
+                all(np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) for a, b in zip(r_lists, f_lists)))
+        print("rank store scan (lists of %d / %d / %d entries): equal to single-GPU scan: %s"
+              % (len(r_lists[0][0]), len(r_lists[1][0]), len(r_lists[2][0]), same))
+        ok = ok and same and len(r_lists[0][0]) > 0
+        fc, fr, fs, _ = full.scan_batch(Tq, (1.0, 1.5), 0.81, 0.73, topk=17)
+        same = (np.array_equal(fc, b_counts) and np.array_equal(fr, b_rows) and np.array_equal(fs, b_sc) and
+                np.array_equal(z_counts, fc) and z_rows.shape == (nq, 0))
+        print("rank store batched scan (%d queries, top-17): equal to single-GPU batched scan: %s" % (nq, same))
+        ok = ok and same
+        same = np.array_equal(full.labelled_sims(tf, labelled), l_sims)
+        print("rank store labelled sims (%d rows over %d ranks): equal: %s" % (len(labelled), world, same))
+        ok = ok and same
         res = full.scan({s: {1: T[i, 0]} for i, s in enumerate(S)}, (1.0, 1.5), 0.75 + 0.01 * 6, 0.73, 3e-6, topk=k)
         rows, scores = full.topk()
         for mode, (counts, g_rows, g_scores) in results.items():

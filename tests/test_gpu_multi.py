@@ -22,3 +22,4 @@ def test_sharded_scan_equals_single_gpu_scan():
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0
     assert "exchange p2p:" in r.stdout and "exchange p2p-lagged:" in r.stdout and "exchange nccl:" in r.stdout
+    assert "rank store scan" in r.stdout and "rank store batched scan" in r.stdout and "rank store labelled sims" in r.stdout

@@ -77,6 +77,7 @@ PROTOTYPES = {
     "vq_exchange_merged": (C.c_int, [_vp, _P(_vp)]),
     "vq_scan_kernel_times": (C.c_int, [_vp, _i32, _vp, _P(_i32)]),
     "vq_merge_topk": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _P(_i32)]),
+    "vq_merge_topk_batch": (C.c_int, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "vq_labelled_sims": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "vq_loss_grid": (C.c_int, [C.c_int, _vp, _vp, _i64, _vp, _i32, _vp, _i32, C.c_double, _vp, _vp, _i32, _vp]),
     "vq_bootstrap_target": (C.c_int, [_vp, _vp, _i32, _vp, _i32, C.c_double, _vp]),

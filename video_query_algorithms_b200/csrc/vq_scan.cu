@@ -1093,3 +1093,30 @@ extern "C" int vq_merge_topk(int32_t n_lists, int32_t k, const float *scores, co
     *n_out = n;
     return 0;
 }
+
+// Q queries at once (the batched path's per-shard / per-rank results): lists [n_lists][n_queries][k].
+extern "C" int vq_merge_topk_batch(int32_t n_lists, int32_t n_queries, int32_t k, const float *scores, const int64_t *rows,
+                                   float *scores_out, int64_t *rows_out, int32_t *n_out) {
+    VQ_REQUIRE(n_lists >= 0 && n_queries >= 0 && k >= 0 && scores && rows && scores_out && rows_out && n_out,
+               "vq_merge_topk_batch: bad argument");
+    std::vector<std::pair<float, int64_t>> all;
+    all.reserve((size_t)n_lists * k);
+    for (int q = 0; q < n_queries; ++q) {
+        all.clear();
+        for (int l = 0; l < n_lists; ++l) {
+            const size_t base = ((size_t)l * n_queries + q) * k;
+            for (int i = 0; i < k; ++i)
+                if (rows[base + i] >= 0) all.emplace_back(scores[base + i], rows[base + i]);
+        }
+        std::sort(all.begin(), all.end(), [](const std::pair<float, int64_t> &x, const std::pair<float, int64_t> &y) {
+            return x.first > y.first || (x.first == y.first && x.second < y.second);
+        });
+        const int n = (int)std::min<size_t>(all.size(), (size_t)k);
+        for (int i = 0; i < k; ++i) {
+            scores_out[(size_t)q * k + i] = i < n ? all[(size_t)i].first : -INFINITY;
+            rows_out[(size_t)q * k + i] = i < n ? all[(size_t)i].second : -1;
+        }
+        n_out[q] = n;
+    }
+    return 0;
+}

@@ -145,3 +145,110 @@ def exchange_host(payload, dist, torch, k):
     gathered = torch.empty(world * mine.numel(), dtype=torch.int64)
     dist.all_gather_into_tensor(gathered, mine)
     return merge_payloads_host(gathered.numpy(), world, k)
+
+
+# ---------------------------------------------------------------------------------------------------
+# The other exchanges of SURVEY.md §8(e): variable-length ordered lists, per-query top-k of the batched
+# path, labelled similarities for the weight update.  All three are small next to the scan they follow
+# (KBs to a few MB), so they are plain collectives on whatever backend `dist` runs (NCCL over NVLink with
+# one rank per GPU, gloo in the CPU tests); `device` = the rank's torch.device for NCCL, None for gloo.
+
+def _t(a, torch, device):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    return t.to(device) if device is not None else t
+
+
+def all_gather_np(a, dist, torch, device=None):
+    """numpy [..] on every rank -> numpy [world, ..] on every rank (same shape on all ranks)."""
+    world = dist.get_world_size()
+    mine = _t(a, torch, device).reshape(-1)
+    out = torch.empty(world * mine.numel(), dtype=mine.dtype, device=mine.device)
+    dist.all_gather_into_tensor(out, mine)
+    return out.cpu().numpy().reshape((world,) + tuple(np.shape(a)))
+
+
+def gather_lists(rows, scores, dist, torch, device=None):
+    """One rank's ordered match (or near-miss / tie) list -> the search set's list on every rank.
+    Ranks own ascending clip ranges, so concatenating in rank order keeps database order — the order of the
+    reference's `scores` dict that its seeded sampling walks (ticket.py:326-341).  Lengths differ per rank:
+    counts are gathered first, then the lists padded to the longest one."""
+    rows = np.asarray(rows, np.int64)
+    scores = np.asarray(scores, np.float32)
+    counts = all_gather_np(np.array([len(rows)], np.int64), dist, torch, device)[:, 0]
+    cap = int(counts.max())
+    if cap == 0:
+        return np.empty(0, np.int64), np.empty(0, np.float32)
+    pad = np.zeros((cap, 2), np.int64)
+    pad[:len(rows), 0] = rows
+    pad[:len(rows), 1] = scores.view(np.uint32)
+    g = all_gather_np(pad, dist, torch, device)
+    out_r = np.concatenate([g[r, :counts[r], 0] for r in range(len(counts))])
+    out_s = np.concatenate([g[r, :counts[r], 1] for r in range(len(counts))]).astype(np.uint32).view(np.float32)
+    return out_r, out_s
+
+
+def gather_batch(counts, topk_rows, topk_scores, dist, torch, device=None):
+    """Per-rank results of the batched path (counts [Q, 2], top-k global rows / scores [Q, k]) -> the search
+    set's: counts summed, per-query top-k merged with the ranking rule (vq_merge_topk_batch).  One allgather of
+    Q * (2 + 2k) int64 per rank (413 KB at Q = 256, k = 100)."""
+    from .store import merge_topk_batch
+    counts = np.asarray(counts, np.int64)
+    Q, k = topk_rows.shape
+    pay = np.empty((Q, 2 + 2 * k), np.int64)
+    pay[:, :2] = counts
+    pay[:, 2:2 + k] = topk_rows
+    pay[:, 2 + k:] = np.ascontiguousarray(topk_scores, dtype=np.float32).view(np.uint32)
+    g = all_gather_np(pay, dist, torch, device)
+    total = g[:, :, :2].sum(axis=0)
+    if k == 0:
+        return total, np.empty((Q, 0), np.int64), np.empty((Q, 0), np.float32)
+    rows_o, sc_o = merge_topk_batch(g[:, :, 2:2 + k], g[:, :, 2 + k:].astype(np.uint32).view(np.float32))
+    return total, rows_o, sc_o
+
+
+def gather_sims(partial, dist, torch, device=None):
+    """Labelled similarities for the weight update (hyperparameter.py:45-65): every rank holds float64 [L, S] with
+    the rows it owns filled in and zeros elsewhere; one all_reduce(SUM) of 8*L*S bytes gives every rank the full
+    table (x + 0 is exact, so the values are the owners' bit for bit)."""
+    t = _t(np.asarray(partial, np.float64), torch, device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return t.cpu().numpy()
+
+
+class RankStore:
+    """One rank's shard of a search set as a FeatureStore (`first_global_row` = the start of its clip range) plus
+    the collectives that turn per-rank results into the search set's.  Every rank calls every method (they are
+    collectives) and every rank gets the same result."""
+
+    def __init__(self, store, dist, torch, device=None):
+        self.store, self.dist, self.torch, self.device = store, dist, torch, device
+        self.world = dist.get_world_size()
+        self.lo = store.first_global_row
+        self.hi = store.first_global_row + store.n_rows
+
+    def scan(self, target_features, weights, threshold, lower_limit, eps, topk=0):
+        """Full single-query result with host buffers: counts [match, near, tie], ordered global match /
+        near-miss / tie lists and the merged top-k."""
+        res = self.store.scan(target_features, weights, threshold, lower_limit, eps, topk=topk)
+        k = int(topk)
+        rows, scores = self.store.topk() if k else (np.empty(0, np.int64), np.empty(0, np.float32))
+        payload = pack_payload([res.n_match, res.n_near, res.n_tie, len(rows)], rows, scores, k)
+        merged = merge_payloads_host(all_gather_np(payload, self.dist, self.torch, self.device), self.world, k)
+        counts, t_rows, t_scores = unpack_payload(merged, k)
+        lists = [gather_lists(*fn(copy=False), self.dist, self.torch, self.device)
+                 for fn in (self.store.matches, self.store.near_misses, self.store.ties)]
+        return counts[:3], lists, (t_rows, t_scores)
+
+    def scan_batch(self, targets, weights, threshold, lower_limit, topk=0):
+        c, r, s, ms = self.store.scan_batch(targets, weights, threshold, lower_limit, topk=topk)
+        if topk == 0:
+            r, s = np.empty((len(c), 0), np.int64), np.empty((len(c), 0), np.float32)
+        return gather_batch(c, r, s, self.dist, self.torch, self.device) + (ms,)
+
+    def labelled_sims(self, target_features, global_rows):
+        rows = np.asarray(global_rows, np.int64)
+        out = np.zeros((len(rows), len(self.store.streams)), np.float64)
+        own = np.flatnonzero((rows >= self.lo) & (rows < self.hi))
+        if len(own):
+            out[own] = self.store.labelled_sims(target_features, rows[own])
+        return gather_sims(out, self.dist, self.torch, self.device)

@@ -579,14 +579,7 @@ class FeatureStore:
             return counts, np.empty((Q, 0), np.int64), np.empty((Q, 0), np.float32), ms
         if len(self.shards) == 1:
             return counts, rows_l[0], sc_l[0], ms
-        rows_o = np.full((Q, topk), -1, np.int64)
-        sc_o = np.full((Q, topk), -np.inf, np.float32)
-        n = C.c_int32()
-        for q in range(Q):
-            sc = np.ascontiguousarray(np.stack([s_[q] for s_ in sc_l]))
-            rw = np.ascontiguousarray(np.stack([r[q] for r in rows_l]))
-            check(lib().vq_merge_topk(len(self.shards), topk, ptr(sc), ptr(rw), ptr(sc_o[q]), ptr(rows_o[q]),
-                                      C.byref(n)), "vq_merge_topk")
+        rows_o, sc_o = merge_topk_batch(np.stack(rows_l), np.stack(sc_l))
         return counts, rows_o, sc_o, ms
 
     # ------------------------------------------------------------------ labelled subset (fp64)
@@ -640,6 +633,18 @@ class FeatureStore:
             return tmp.bootstrap_target(v, iv, mu)
         finally:
             tmp.close()
+
+
+def merge_topk_batch(rows, scores):
+    """rows int64 / scores fp32 [n_lists, Q, k] (padding -1 / -inf) -> the k best per query under
+    (score descending, global row ascending), the ranking rule of reference ticket.py:266."""
+    rows = np.ascontiguousarray(rows, dtype=np.int64)
+    scores = np.ascontiguousarray(scores, dtype=np.float32)
+    n_lists, Q, k = rows.shape
+    rows_o, sc_o, n = np.empty((Q, k), np.int64), np.empty((Q, k), np.float32), np.empty(Q, np.int32)
+    check(lib().vq_merge_topk_batch(n_lists, Q, k, ptr(scores), ptr(rows), ptr(sc_o), ptr(rows_o), ptr(n)),
+          "vq_merge_topk_batch")
+    return rows_o, sc_o
 
 
 def loss_grid(sims, labels, weight_grid, threshold_grid, ballast, replicates=None, device=0):
