@@ -663,12 +663,19 @@ def test_missing_library_or_bad_arguments_fail_loudly(vq):
     st.close()
 
 
-# ---------------------------------------------------------------------------- full size (BASELINE config 2)
-def test_one_million_clip_scan_properties(vq):
-    """1M clips (8.19 GB) generated on the device: determinism, list invariants, and a float64 CPU
-    check of every selected/tie row plus a seeded sample of the rest (rows regenerated on the CPU)."""
-    n, seed = 1_000_000, synth.DEFAULT_SEED
-    st = vq.FeatureStore(n, STREAMS, [1], 1024, devices=[0])
+# ---------------------------------------------------------------------------- full size (BASELINE configs 2 and 3)
+@pytest.mark.parametrize("n, first", [(1_000_000, 0), (12_500_000, 87_500_000)],
+                         ids=["config2-1M", "config3-last-shard-of-100M"])
+def test_full_size_scan_properties(vq, n, first):
+    """1M clips (8.19 GB, config 2) and the last 12.5M-clip shard of the 100M-clip DB (102.4 GB, global rows
+    87.5M..100M, config 3) generated on the device: determinism, list invariants, and a float64 CPU check of
+    every top-k / tie row plus a seeded sample of the matches, near misses and the rest (rows regenerated on
+    the CPU from the counter-based generator)."""
+    import torch
+    if n * 8192 * 1.05 > torch.cuda.get_device_properties(0).total_memory:
+        pytest.skip("device memory too small for %d clips" % n)
+    seed = synth.DEFAULT_SEED
+    st = vq.FeatureStore(n, STREAMS, [1], 1024, devices=[0], first_global_row=first)
     st.fill_synthetic(seed)
     ref = 18120                                   # alpha ~ 0.9: ~9 % of the clips match
     T = sc.scale_target(synth.rows(seed, [ref]).astype(np.float64)[0][:, None, :])
@@ -680,18 +687,22 @@ def test_one_million_clip_scan_properties(vq):
     assert np.array_equal(s1, st.scores()) and (r1.n_match, r1.n_near) == (r2.n_match, r2.n_near)
     assert np.array_equal(m1[0], st.matches()[0]) and np.array_equal(k1[0], st.topk()[0])
     g = s1.astype(np.float64)
-    assert np.array_equal(m1[0], np.flatnonzero(g >= th))
-    assert np.array_equal(n1[0], np.flatnonzero((g >= lo) & (g < th)))
-    assert np.array_equal(k1[0], sc.topk_stable(s1, 100))
-    assert s1[ref] == pytest.approx(1.0, abs=1e-6) and k1[0][0] == ref
+    assert np.array_equal(m1[0], first + np.flatnonzero(g >= th))
+    assert np.array_equal(n1[0], first + np.flatnonzero((g >= lo) & (g < th)))
+    assert np.array_equal(m1[1], s1[m1[0] - first]) and np.array_equal(n1[1], s1[n1[0] - first])
+    top = sc.topk_stable(s1, 100)
+    assert np.array_equal(k1[0], first + top) and np.array_equal(k1[1], s1[top])
+    assert r1.n_match == len(m1[0]) > n // 50 and r1.n_near == len(n1[0]) > n // 100
+    if first <= ref < first + n:
+        assert s1[ref - first] == pytest.approx(1.0, abs=1e-6) and k1[0][0] == ref
     rng = np.random.default_rng(0)
     t_rows = st.ties()[0]
     check = np.unique(np.concatenate([k1[0], t_rows, rng.choice(m1[0], 300), rng.choice(n1[0], 300),
-                                      rng.integers(0, n, 1500)]))
+                                      first + rng.integers(0, n, 1500), [first, first + n - 1]]))
     X = synth.rows(seed, check).astype(np.float64)[:, :, None, :]
     sims64, _ = sc.similarities(X, T)
     s64 = sc.scores(sims64, w)
-    assert_scores_close(s1[check], s64)
+    assert_scores_close(s1[check - first], s64)
     in_m = np.isin(check, m1[0])
     in_n = np.isin(check, n1[0])
     for j, r in enumerate(check):
