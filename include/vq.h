@@ -194,6 +194,16 @@ int vq_scan_batch(vq_store *s, const float *targets /* [Q][S][P][dim] */, int32_
 int vq_scan_batch_scores(vq_store *s, const float *targets, int32_t n_queries, const vq_scan_params *p,
                          float *scores_out);
 
+/* ---------------------------------------------------------------- feature-CSV ingest (host code)
+ * The files the TSN extractor writes and load_db.py loads (src/api/api_load_records.py:41-58:
+ * csv.reader + float() per cell): header line of 5 `key =value` fields, then `clip_no, f0 .. f{dim-1}`
+ * per row.  vq_csv_shape returns the number of data rows, the feature length and the header line;
+ * vq_csv_read parses the rows with n_threads threads (0 = all cores) into caller-owned arrays —
+ * correctly rounded doubles, identical to Python's float().  Malformed rows are an error.       */
+int vq_csv_shape(const char *path, int64_t *n_rows_out, int32_t *dim_out, char *header_out, int32_t header_cap);
+int vq_csv_read(const char *path, int32_t n_threads, int64_t cap_rows, int32_t dim,
+                int64_t *clip_numbers_out /* [n] */, double *features_out /* [n][dim] */, int64_t *n_rows_out);
+
 #ifdef __cplusplus
 }
 #endif

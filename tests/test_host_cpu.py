@@ -207,6 +207,75 @@ def test_feature_tree_parser_reads_the_load_db_layout(tmp_path):
         assert np.array_equal(tree["vidA"]["features"][stream][split], feats)     # repr() round-trips float64
 
 
+def _python_csv(path):
+    """The reference's own loop (api_load_records.py:45-58): csv.reader + int() / float() per cell."""
+    import csv
+    with open(path, "r") as f:
+        reader = csv.reader(f)
+        header = next(reader)
+        clips, rows = [], []
+        for row in reader:
+            if row:
+                clips.append(int(row[0]))
+                rows.append([float(x) for x in row[1:]])
+    return header, np.array(clips, np.int64), np.array(rows, np.float64).reshape(len(clips), -1)
+
+
+def test_native_csv_reader_equals_csv_reader_plus_float(tmp_path):
+    """vq_csv_read against Python's csv + float(): hard-to-round decimals, exponents, signs, blanks, CRLF,
+    missing final newline, values outside the double range; any thread count gives the same arrays."""
+    import time
+    from video_query_algorithms_b200 import ingest
+    rng = np.random.default_rng(3)
+    n, dim = 257, 1024
+    vals = rng.random((n, dim)) * 10.0 ** rng.integers(-12, 6, (n, dim))
+    cells = [[repr(float(x)) for x in row] for row in vals]
+    tricky = ["0.1", "1e-05", "+2.5", "-0.0", "5e-324", "1.7976931348623157e308", "2.2250738585072014e-308",
+              "9007199254740993", "0.30000000000000004", "1E3", " 4.25", "7 ", "1e999", "-1e999", "1e-999", "123456789012345678901234567890",
+              "8.41692461872845e-05", "0.000001", "3.", ".5"]
+    cells[0][:len(tricky)] = tricky
+    path = tmp_path / "rgb_global_pool_features.csv"
+    with open(path, "w", newline="") as f:
+        f.write("video =vidA, video url =../x/, CNN stream =rgb, feature blob =global_pool, caffe model =/m/a=b.caffemodel\r\n")
+        for i, row in enumerate(cells):
+            f.write(",".join([str(i + 1)] + row) + ("\r\n" if i % 2 else "\n"))
+            if i == 100:
+                f.write("\n")                                            # an empty line is skipped by both
+        f.write(",".join(["9999"] + cells[1]))                            # last row without a newline
+    t0 = time.perf_counter()
+    header, clips, want = _python_csv(path)
+    t_py = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    rec = ingest.read_feature_csv(str(path))
+    t_native = time.perf_counter() - t0
+    assert rec["video"] == "vidA" and rec["stream"] == "rgb" and rec["feature_name"] == "global_pool"
+    assert rec["weights_uri"] == header[4].split("=")[-1] == "b.caffemodel"
+    assert np.array_equal(rec["clip_numbers"], clips) and clips[-1] == 9999 and len(clips) == n + 1
+    assert rec["features"].shape == want.shape == (n + 1, dim)
+    assert np.array_equal(rec["features"].view(np.uint64), want.view(np.uint64))      # bit for bit, signed zeros included
+    one = ingest.read_feature_csv(str(path), n_threads=1)
+    assert np.array_equal(one["features"].view(np.uint64), want.view(np.uint64))
+    assert t_native < t_py, (t_native, t_py)
+
+
+def test_native_csv_reader_rejects_malformed_files(tmp_path):
+    import video_query_algorithms_b200 as vq
+    from video_query_algorithms_b200 import ingest
+    head = "video =v, video url =u, CNN stream =rgb, feature blob =global_pool, caffe model =m\n"
+    for name, body in (("ragged", "1,0.5,0.25\n2,0.5\n"), ("text", "1,0.5,abc\n"), ("clip", "x,0.5,0.25\n"),
+                       ("junk", "1,0.5,0.25x\n")):
+        p = tmp_path / (name + ".csv")
+        p.write_text(head + body)
+        with pytest.raises(vq.VQError):
+            ingest.read_feature_csv(str(p))
+    with pytest.raises(vq.VQError):
+        ingest.read_feature_csv(str(tmp_path / "missing.csv"))
+    p = tmp_path / "empty.csv"
+    p.write_text(head)
+    rec = ingest.read_feature_csv(str(p))
+    assert rec["features"].shape[0] == 0 and len(rec["clip_numbers"]) == 0
+
+
 def test_feature_tree_parser_on_reference_fixture_if_present():
     src = "/root/reference/data/features/stock-video-clips_features"
     if not os.path.isdir(src):

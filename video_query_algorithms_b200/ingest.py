@@ -19,20 +19,22 @@ import numpy as np
 from .store import FeatureStore
 
 
-def read_feature_csv(path):
-    """-> dict(video, stream, feature_name, weights_uri, clip_numbers [n], features float64 [n, dim])."""
-    with open(path, "r", newline="") as f:
-        reader = csv.reader(f)
-        header = next(reader)
-        field = lambda i: header[i].split("=")[-1]
-        clips, rows = [], []
-        for row in reader:
-            if not row:
-                continue
-            clips.append(int(row[0]))
-            rows.append([float(x) for x in row[1:]])
+def read_feature_csv(path, n_threads=0):
+    """-> dict(video, stream, feature_name, weights_uri, clip_numbers [n], features float64 [n, dim]).
+    Parsed by the library (vq_csv_read: all cores, same doubles as float()); a malformed file raises VQError."""
+    import ctypes as C
+    from ._ffi import check, lib, ptr
+    bpath = os.fsencode(path)
+    n, dim, hdr = C.c_int64(), C.c_int32(), C.create_string_buffer(1 << 16)
+    check(lib().vq_csv_shape(bpath, C.byref(n), C.byref(dim), hdr, len(hdr)), "vq_csv_shape")
+    clips = np.empty(n.value, np.int64)
+    feats = np.empty((n.value, dim.value), np.float64)
+    got = C.c_int64()
+    check(lib().vq_csv_read(bpath, int(n_threads), n.value, dim.value, ptr(clips), ptr(feats), C.byref(got)), "vq_csv_read")
+    header = next(csv.reader([hdr.value.decode()]))
+    field = lambda i: header[i].split("=")[-1]
     return {"video": field(0), "stream": field(2), "feature_name": field(3), "weights_uri": field(4),
-            "clip_numbers": np.asarray(clips, dtype=np.int64), "features": np.asarray(rows, dtype=np.float64)}
+            "clip_numbers": clips, "features": feats}
 
 
 def read_feature_tree(src_dir):
