@@ -9,6 +9,7 @@ its seeded `random.sample` depends on (ticket.py:326-333).
 """
 from __future__ import annotations
 
+import array
 import ctypes as C
 from dataclasses import dataclass
 
@@ -61,6 +62,12 @@ def make_params(weights, threshold, lower_limit, eps, topk=0, want_sims=False):
     p.threshold, p.lower_limit, p.eps = float(threshold), float(lower_limit), float(eps)
     p.topk, p.want_sims = int(topk), int(bool(want_sims))
     return p
+
+
+def _as_doubles(v):
+    """A feature vector as the API delivers it (list of Python floats) in a form numpy copies without per-element
+    dispatch: array('d') unboxes a list ~1.7x faster than assigning the list to an ndarray row (13 vs 23 us per 1024)."""
+    return array.array("d", v) if isinstance(v, list) else v
 
 
 class FeatureStore:
@@ -263,7 +270,7 @@ class FeatureStore:
                 if p not in p_of:
                     raise VQError("append_feature_rows: split %d is not one of the store's splits %s" % (p, self.splits))
                 i, si, pi = row[tf["video_clip_id"]], s_of[tf["dnn_stream_id"]], p_of[p]
-                X[i, si, pi] = tf["feature_vector"]
+                X[i, si, pi] = _as_doubles(tf["feature_vector"])
                 present[i, si, pi] = True
         self.append(X, clip_ids=order, present=present)
         return len(order)
@@ -302,7 +309,7 @@ class FeatureStore:
         for tf in feature_rows:
             if tf["dnn_stream_id"] in streams and tf["name"] == feature_name:
                 i, s, p = row[tf["video_clip_id"]], s_of[tf["dnn_stream_id"]], p_of[int(tf["dnn_stream_split"])]
-                X[i, s, p] = tf["feature_vector"]       # later duplicates overwrite, like the dict does
+                X[i, s, p] = _as_doubles(tf["feature_vector"])       # later duplicates overwrite, like the dict does
                 present[i, s, p] = True
         st = cls(len(order), streams, splits, dim, devices=devices, clip_ids=order)
         st.upload(0, X)
