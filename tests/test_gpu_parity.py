@@ -663,6 +663,52 @@ def test_missing_library_or_bad_arguments_fail_loudly(vq):
     st.close()
 
 
+def test_calls_from_a_new_thread_every_tick(vq):
+    """The broker runs every tick on a fresh thread (reference src/broker.py:90-92, threading.Timer): a store built
+    on one thread must serve scans, list fetches, the fp64 labelled path and batched queries from any other."""
+    import threading
+    n, seed = 30_000, 11
+    st = vq.FeatureStore(n, STREAMS, [1], 1024, devices=[0])
+    st.fill_synthetic(seed)
+    T = sc.scale_target(synth.rows(seed, [123]).astype(np.float64)[0][:, None, :])
+    lo = sc.lower_limit(0.8, 0.35)
+    lab = np.arange(5, n, 701, dtype=np.int64)
+
+    def tick(out):
+        try:
+            r = st.scan(tdict(T), (1.0, 1.5), 0.8, lo, EPS, topk=50)
+            out["scan"] = (r.n_match, r.n_near, r.n_tie, st.matches()[0].copy(), st.near_misses()[0].copy(), st.topk()[0].copy(),
+                           st.scores().copy())
+            out["lab"] = st.labelled_sims(tdict(T), lab)
+            c, rows, scs, _ = st.scan_batch(np.stack([T, T]).astype(np.float32), (1.0, 1.5), 0.8, lo, topk=5)
+            out["batch"] = (c.copy(), rows.copy(), scs.copy())
+            out["grid"] = vq.loss_grid(out["lab"], (out["lab"][:, 0] > 0.9).astype(np.uint8), np.arange(0.5, 2.5, 0.05),
+                                       np.arange(0.5, 1.1, 0.02), 0.1)
+        except Exception as e:                     # surfaced on the main thread
+            out["error"] = e
+
+    results = []
+    for _ in range(3):                              # three ticks, three threads, one store
+        out = {}
+        th = threading.Thread(target=tick, args=(out,))
+        th.start()
+        th.join()
+        assert "error" not in out, out.get("error")
+        results.append(out)
+    main = {}
+    tick(main)
+    assert "error" not in main, main.get("error")
+    for out in results:
+        assert out["scan"][:3] == main["scan"][:3]
+        for a, b in zip(out["scan"][3:], main["scan"][3:]):
+            assert np.array_equal(a, b)
+        assert np.array_equal(out["lab"], main["lab"]) and np.array_equal(out["grid"], main["grid"])
+        for a, b in zip(out["batch"], main["batch"]):
+            assert np.array_equal(a, b)
+    assert main["scan"][0] > 0 and main["batch"][0][0, 0] == main["batch"][0][1, 0]
+    st.close()
+
+
 # ---------------------------------------------------------------------------- full size (BASELINE configs 2 and 3)
 @pytest.mark.parametrize("n, first", [(1_000_000, 0), (12_500_000, 87_500_000)],
                          ids=["config2-1M", "config3-last-shard-of-100M"])

@@ -181,6 +181,43 @@ def test_sample_of_index_range_equals_sample_of_items():
         assert a == b and random.getstate() == sa
 
 
+def test_batched_topk_merge_ranked_lists_unranked_lists_and_padding(built_lib):
+    """vq_merge_topk_batch (per-query merge of per-shard / per-rank top-k lists): ranked input takes the k-way merge,
+    unranked input the sort; both must give (score descending, global row ascending) with -1 / -inf padding."""
+    from video_query_algorithms_b200.store import merge_topk_batch
+    rng = np.random.default_rng(0)
+    L, Q, k = 5, 33, 40
+    sc_ = rng.random((L, Q, k)).astype(np.float32)
+    sc_[:, :, ::3] = np.float32(0.5)                                      # ties inside and across lists
+    rows = rng.permutation(L * Q * k).reshape(L, Q, k).astype(np.int64)
+    for l in range(L):
+        for q in range(Q):
+            o = np.lexsort((rows[l, q], -sc_[l, q]))
+            sc_[l, q], rows[l, q] = sc_[l, q][o], rows[l, q][o]
+    rows[3, :, 25:], sc_[3, :, 25:] = -1, -np.inf                         # a short list
+    rows[4], sc_[4] = -1, -np.inf                                         # an empty shard
+
+    def want(q, rr, ss):
+        a_s, a_r = ss[:, q].reshape(-1), rr[:, q].reshape(-1)
+        m = a_r >= 0
+        o = np.lexsort((a_r[m], -a_s[m]))[:k]
+        return a_r[m][o], a_s[m][o]
+
+    r, s_ = merge_topk_batch(rows, sc_)
+    for q in range(Q):
+        wr, ws = want(q, rows, sc_)
+        assert np.array_equal(r[q], wr) and np.array_equal(s_[q], ws)
+    shuffled_r, shuffled_s = rows.copy(), sc_.copy()
+    for l in range(3):
+        p_ = rng.permutation(k)
+        shuffled_r[l], shuffled_s[l] = rows[l][:, p_], sc_[l][:, p_]
+    r2, s2 = merge_topk_batch(shuffled_r, shuffled_s)
+    assert np.array_equal(r2, r) and np.array_equal(s2, s_)
+    few_r, few_s = rows[3:, :, :], sc_[3:, :, :]                          # fewer than k valid entries in total
+    r3, s3 = merge_topk_batch(few_r, few_s)
+    assert np.array_equal(r3[:, :25], rows[3, :, :25]) and np.all(r3[:, 25:] == -1) and np.all(np.isneginf(s3[:, 25:]))
+
+
 # ---------------------------------------------------------------------------- ingest (host parsing)
 def _write_csv(path, video, stream, clips, feats):
     os.makedirs(os.path.dirname(path), exist_ok=True)

@@ -1095,26 +1095,65 @@ extern "C" int vq_merge_topk(int32_t n_lists, int32_t k, const float *scores, co
 }
 
 // Q queries at once (the batched path's per-shard / per-rank results): lists [n_lists][n_queries][k].
+// Each list arrives ranked (that is how batch_output and select_finish write them), so the k best are taken by a
+// k-way merge of the list heads, O(k * n_lists) per query; a list that is not ranked falls back to a full sort.
 extern "C" int vq_merge_topk_batch(int32_t n_lists, int32_t n_queries, int32_t k, const float *scores, const int64_t *rows,
                                    float *scores_out, int64_t *rows_out, int32_t *n_out) {
     VQ_REQUIRE(n_lists >= 0 && n_queries >= 0 && k >= 0 && scores && rows && scores_out && rows_out && n_out,
                "vq_merge_topk_batch: bad argument");
+    auto before = [](float sa, int64_t ra, float sb, int64_t rb) { return sa > sb || (sa == sb && ra < rb); };
     std::vector<std::pair<float, int64_t>> all;
-    all.reserve((size_t)n_lists * k);
+    std::vector<int> head((size_t)n_lists), len((size_t)n_lists);
     for (int q = 0; q < n_queries; ++q) {
-        all.clear();
+        bool ranked = true;
         for (int l = 0; l < n_lists; ++l) {
             const size_t base = ((size_t)l * n_queries + q) * k;
-            for (int i = 0; i < k; ++i)
-                if (rows[base + i] >= 0) all.emplace_back(scores[base + i], rows[base + i]);
+            int n = 0;
+            while (n < k && rows[base + n] >= 0) ++n;                 // valid entries come first, padding after
+            for (int i = n; i < k && ranked; ++i) ranked = rows[base + i] < 0;
+            for (int i = 1; i < n && ranked; ++i)
+                ranked = !before(scores[base + i], rows[base + i], scores[base + i - 1], rows[base + i - 1]);
+            len[(size_t)l] = n;
+            head[(size_t)l] = 0;
         }
-        std::sort(all.begin(), all.end(), [](const std::pair<float, int64_t> &x, const std::pair<float, int64_t> &y) {
-            return x.first > y.first || (x.first == y.first && x.second < y.second);
-        });
-        const int n = (int)std::min<size_t>(all.size(), (size_t)k);
-        for (int i = 0; i < k; ++i) {
-            scores_out[(size_t)q * k + i] = i < n ? all[(size_t)i].first : -INFINITY;
-            rows_out[(size_t)q * k + i] = i < n ? all[(size_t)i].second : -1;
+        int n = 0;
+        if (ranked) {
+            for (; n < k; ++n) {
+                int best = -1;
+                for (int l = 0; l < n_lists; ++l) {
+                    if (head[(size_t)l] >= len[(size_t)l]) continue;
+                    const size_t i = ((size_t)l * n_queries + q) * k + head[(size_t)l];
+                    if (best < 0) {
+                        best = l;
+                        continue;
+                    }
+                    const size_t j = ((size_t)best * n_queries + q) * k + head[(size_t)best];
+                    if (before(scores[i], rows[i], scores[j], rows[j])) best = l;
+                }
+                if (best < 0) break;
+                const size_t j = ((size_t)best * n_queries + q) * k + head[(size_t)best]++;
+                scores_out[(size_t)q * k + n] = scores[j];
+                rows_out[(size_t)q * k + n] = rows[j];
+            }
+        } else {
+            all.clear();
+            for (int l = 0; l < n_lists; ++l) {
+                const size_t base = ((size_t)l * n_queries + q) * k;
+                for (int i = 0; i < k; ++i)
+                    if (rows[base + i] >= 0) all.emplace_back(scores[base + i], rows[base + i]);
+            }
+            std::sort(all.begin(), all.end(), [&](const std::pair<float, int64_t> &x, const std::pair<float, int64_t> &y) {
+                return before(x.first, x.second, y.first, y.second);
+            });
+            n = (int)std::min<size_t>(all.size(), (size_t)k);
+            for (int i = 0; i < n; ++i) {
+                scores_out[(size_t)q * k + i] = all[(size_t)i].first;
+                rows_out[(size_t)q * k + i] = all[(size_t)i].second;
+            }
+        }
+        for (int i = n; i < k; ++i) {
+            scores_out[(size_t)q * k + i] = -INFINITY;
+            rows_out[(size_t)q * k + i] = -1;
         }
         n_out[q] = n;
     }
