@@ -257,39 +257,83 @@ def main():
 
     g_counts, g_rows, g_scores = rank_scan.result()
     # ---- end to end through the public API, host buffers: target H2D, counts + lists + top-k D2H
+    # N > 1: through RankStore, whose methods are collectives — every rank ends each step holding the SEARCH SET's result
+    # (counts, merged top-k, the ordered lists of all ranks concatenated in database order), not just its shard's
     e2e_steps = max(3, min(args.steps, 100))
-    for _ in range(2):
-        st.scan(tdict, WEIGHTS, THRESHOLD, lower, EPS, topk=TOPK)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    rstore = None
+    if world > 1:
+        from video_query_algorithms_b200.sharded import RankStore
+        rstore = RankStore(st, dist, torch, dev)
+
+    def e2e_step():
+        if rstore is not None:
+            g_cnt, g_lists, g_top = rstore.scan(tdict, WEIGHTS, THRESHOLD, lower, EPS, topk=TOPK)
+            return st.last, int(g_cnt[0]) + int(g_cnt[1]) + int(g_cnt[2])
         res = st.scan(tdict, WEIGHTS, THRESHOLD, lower, EPS, topk=TOPK)
         k_rows, k_sc = st.topk()
         m_rows, m_sc = st.matches(copy=False)          # as Ticket.select_clips_to_review reads them: views of the
         nm_rows, nm_sc = st.near_misses(copy=False)    # pinned host mirror the scan's publish kernel wrote
+        return res, res.n_match + res.n_near + res.n_tie
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        res, n_listed = e2e_step()
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = world * n * e2e_steps / float(e2e_s.item())
     h2d = ROW_BYTES + C.sizeof(_ffi.ScanParams)
-    d2h = 40 + TOPK * 12 + (res.n_match + res.n_near + res.n_tie) * 12
+    d2h = 40 + TOPK * 12 + (res.n_match + res.n_near + res.n_tie) * 12      # this rank's shard -> its host
+    e2e_what = ("FeatureStore.scan + topk + matches + near_misses through the C ABI: target from a "
+                "host buffer, counts / top-k / ordered lists (int64 rows + fp32 scores) published into pinned host "
+                "memory inside the call; the shard stays resident in HBM between queries (the store outlives "
+                "broker ticks)")
+    sel_what = ("the review round as Ticket.select_clips_to_review runs it: FeatureStore.scan(lists=False) "
+                "+ topk + tie band + gather of 10 sampled matches and 9 sampled near misses + best near miss; "
+                "the match / near-miss lists stay on the device")
+    if world > 1:
+        e2e_what = ("RankStore.scan on every rank (one process per GPU): the local FeatureStore.scan as above, then the "
+                    "two collectives that give EVERY rank the search set's result — an allgather of one summary record per "
+                    "rank (counts, top-k, tie band; merged on the host) and an allgather of the ordered match / near-miss "
+                    "lists packed as (local row, score) = 8 B per entry (%d entries in all, padded to the longest rank's); "
+                    "h2d / d2h bytes are this rank's shard-to-host traffic, the collectives' staging copies come on top"
+                    % n_listed)
+        sel_what = ("RankStore.scan_select + gather_many on every rank: lists stay on each rank's device; two collectives — "
+                    "an allgather of one summary record per rank (counts, top-k, tie band, best near miss) and one "
+                    "all_reduce of 16 B per position that fetches the 19 sampled entries from the ranks that own them")
 
     # ---- the review round's call (Ticket.select_clips_to_review): lists stay on the device, the host draws 20 list
     # positions with the reference's RNG and gathers just those entries + the best near miss
     import random as _random
     _random.seed(a=os.environ["RANDOM_SEED"])
+    def select_step():
+        if rstore is not None:                         # same seed on every rank -> same positions on every rank
+            cnt, top, ties, nb = rstore.scan_select(tdict, WEIGHTS, THRESHOLD, lower, EPS, topk=TOPK)
+            n_m, n_nm = int(cnt[0]), int(cnt[1])
+        else:
+            r2 = st.scan(tdict, WEIGHTS, THRESHOLD, lower, EPS, topk=TOPK, lists=False)
+            st.topk()
+            st.ties(copy=False)
+            nb = st.near_best()
+            n_m, n_nm = r2.n_match, r2.n_near
+        pos_m = _random.sample(range(n_m), min(10, n_m))
+        pos_n = _random.sample(range(max(n_nm - 1, 0)), min(9, max(n_nm - 1, 0)))
+        if rstore is not None:
+            rstore.gather_many([("matches", pos_m), ("near_misses", pos_n)])
+        else:
+            st.gather("matches", pos_m)
+            st.gather("near_misses", pos_n)
+
     for _ in range(2):
-        st.scan(tdict, WEIGHTS, THRESHOLD, lower, EPS, topk=TOPK, lists=False)
+        select_step()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        r2 = st.scan(tdict, WEIGHTS, THRESHOLD, lower, EPS, topk=TOPK, lists=False)
-        st.topk()
-        st.ties(copy=False)
-        st.gather("matches", _random.sample(range(r2.n_match), min(10, r2.n_match)))
-        nb = st.near_best()
-        st.gather("near_misses", _random.sample(range(max(r2.n_near - 1, 0)), min(9, max(r2.n_near - 1, 0))))
+        select_step()
     barrier()
     sel_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
@@ -349,15 +393,10 @@ def main():
                          "frac_of_nominal_8TBs": achieved / 8000.0,
                          "algorithmic_bytes_per_launch": n * ROW_BYTES},
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": e2e_steps, "what": "FeatureStore.scan + topk + matches + near_misses through the C ABI: target from a "
-                    "host buffer, counts / top-k / ordered lists (int64 rows + fp32 scores) published into pinned host "
-                    "memory inside the call; the shard stays resident in HBM between queries (the store outlives "
-                    "broker ticks)"},
+                    "steps": e2e_steps, "what": e2e_what},
             "e2e_select": {"value": e2e_select_value, "unit": "clips/s", "h2d_bytes_per_step": int(h2d + 19 * 8),
                            "d2h_bytes_per_step": int(64 + TOPK * 12 + res.n_tie * 12 + 19 * 12), "steps": e2e_steps,
-                           "what": "the review round as Ticket.select_clips_to_review runs it: FeatureStore.scan(lists=False) "
-                                   "+ topk + tie band + gather of 10 sampled matches and 9 sampled near misses + best near miss; "
-                                   "the match / near-miss lists stay on the device"},
+                           "what": sel_what},
             "e2e_cold": cold,
             "gpu_launches": rank_scan.kernels_per_step() * args.steps,
             "exchange": rank_scan.exchange,

@@ -49,6 +49,14 @@ def main():
     rstore = RankStore(st, dist, torch, dev)
     tf = {s: {1: T[i, 0]} for i, s in enumerate(S)}
     r_counts, r_lists, (r_trows, r_tsc) = rstore.scan(tf, (1.0, 1.5), 0.81, 0.73, 3e-6, topk=k)
+    # review round: lists stay on the ranks; counts / top-k / tie band / best near miss / sampled positions cross
+    s_counts, (s_trows, s_tsc), s_ties, s_best = rstore.scan_select(tf, (1.0, 1.5), 0.81, 0.73, 3e-6, topk=k)
+    rng = np.random.default_rng(5)                           # same positions on every rank
+    pos_m = rng.integers(0, int(s_counts[0]), 25)
+    pos_n = np.concatenate([rng.integers(0, int(s_counts[1]), 25), [0, int(s_counts[1]) - 1]])
+    s_m, s_n, s_e = rstore.gather_many([("matches", pos_m), ("near_misses", pos_n), ("ties", [])])
+    s_m1 = rstore.gather("matches", pos_m[:3])
+    assert np.array_equal(s_m1[0], s_m[0][:3]) and np.array_equal(s_m1[1], s_m[1][:3])
     nq = 24
     Tq = np.stack([sc.scale_target(synth.rows(seed, [100 + 977 * q]).astype(np.float64)[0][:, None, :]) for q in range(nq)])
     Tq = Tq.astype(np.float32)
@@ -69,6 +77,16 @@ def main():
         print("rank store scan (lists of %d / %d / %d entries): equal to single-GPU scan: %s"
               % (len(r_lists[0][0]), len(r_lists[1][0]), len(r_lists[2][0]), same))
         ok = ok and same and len(r_lists[0][0]) > 0
+        nm_rows, nm_sc = f_lists[1]
+        j = int(np.argmax(nm_sc))                            # first maximum in database order (ticket.py:335-340)
+        same = (list(s_counts) == [res.n_match, res.n_near, res.n_tie] and np.array_equal(s_trows, f_trows) and
+                np.array_equal(s_tsc, f_tsc) and np.array_equal(s_ties[0], f_lists[2][0]) and
+                np.array_equal(s_ties[1], f_lists[2][1]) and s_best == (j, int(nm_rows[j]), float(nm_sc[j])) and
+                np.array_equal(s_m[0], f_lists[0][0][pos_m]) and np.array_equal(s_m[1], f_lists[0][1][pos_m]) and
+                np.array_equal(s_n[0], nm_rows[pos_n]) and np.array_equal(s_n[1], nm_sc[pos_n]) and len(s_e[0]) == 0)
+        print("rank store selection scan (best near miss at list position %d, %d + %d sampled positions): equal to "
+              "single-GPU scan: %s" % (s_best[0], len(pos_m), len(pos_n), same))
+        ok = ok and same
         fc, fr, fs, _ = full.scan_batch(Tq, (1.0, 1.5), 0.81, 0.73, topk=17)
         same = (np.array_equal(fc, b_counts) and np.array_equal(fr, b_rows) and np.array_equal(fs, b_sc) and
                 np.array_equal(z_counts, fc) and z_rows.shape == (nq, 0))

@@ -107,12 +107,42 @@ def _rank_collectives(rank, world, port, n_total, k, nq, out_dir):
         t_sc[q, :len(top)] = score[top]
         if q == 0:
             score0, sims0 = score, sims
-    # lists: rank 1 has an impossible threshold -> empty list on that rank
+    # single-query summary + packed lists: rank 1 has an impossible threshold -> empty match list on that rank; the
+    # tie band is faked from rows whose score is exactly 0.5 (more than TIE_CAP entries on each rank -> list gather)
     th = 0.8 if rank == 0 else 2.0
     m, _ = sc.classify(score0.astype(np.float64), th, 0.35)
-    g_rows, g_sc = sharded.gather_lists(first + m, score0[m], dist, torch)
-    e_rows, e_sc = sharded.gather_lists(np.empty(0, np.int64), np.empty(0, np.float32), dist, torch)
-    assert len(e_rows) == 0 and len(e_sc) == 0
+    _, nm = sc.classify(score0.astype(np.float64), 0.51, 0.35)   # ties at 0.5 top the near-miss band: the first one wins
+    ties = np.flatnonzero(score0 == np.float32(0.5))
+    assert len(ties) > sharded.TIE_CAP
+    lb = None
+    if len(nm):
+        j = int(np.argmax(score0[nm]))                       # first maximum in list order
+        lb = (j, first + int(nm[j]), float(score0[nm[j]]))
+    top0 = sc.topk_stable(score0, k)
+    rec = sharded.summary_record(first, [len(m), len(nm), len(ties)], first + top0, score0[top0], k, lb,
+                                 (first + ties, score0[ties]))
+    sm = sharded.exchange_summary(rec, k, dist, torch)
+    assert sm.ties is None
+    mine = [(first + m, score0[m]), (first + nm, score0[nm]), (first + ties, score0[ties])]
+    (g_rows, g_sc), (n_rows, n_sc), (tie_rows, tie_sc) = sharded.gather_lists_packed(mine, [0, 1, 2], sm, dist, torch)
+    # a short tie band rides in the summary record itself; k = 0 and no near miss at all
+    rec2 = sharded.summary_record(first, [0, 0, 2], [], [], 0, None, (first + ties[:2], score0[ties[:2]]))
+    sm2 = sharded.exchange_summary(rec2, 0, dist, torch)
+    assert sm2.near_best is None and len(sm2.topk[0]) == 0 and list(sm2.total) == [0, 0, 2 * world]
+    assert sharded.gather_lists_packed([((), ())], [0], sm2, dist, torch)[0][0].shape == (0,)
+    # sampled positions of two lists with one collective: last, first, first of rank 1, repeats
+    n_near = sm.counts[:, 1]
+    pos = np.array([int(n_near.sum()) - 1, 0, int(n_near[0]), 3, 3], np.int64)
+    pos_m = np.array([len(g_rows) - 1, 0], np.int64)
+    local = {0: (first + m, score0[m]), 1: (first + nm, score0[nm])}
+    (p_rows, p_sc), (pm_rows, pm_sc), (e_rows, _) = sharded.gather_positions_multi(
+        [(1, pos), (0, pos_m), (2, [])], sm, lambda c, loc: (local[c][0][loc], local[c][1][loc]), dist, torch)
+    assert len(e_rows) == 0
+    try:
+        sharded.gather_positions_multi([(1, [int(n_near.sum())])], sm, None, dist, torch)
+        raise AssertionError("position beyond the list accepted")
+    except sharded._ffi.VQError:
+        pass
     b_counts, b_rows, b_sc = sharded.gather_batch(counts, t_rows, t_sc, dist, torch)
     z_counts, z_rows, _ = sharded.gather_batch(counts, t_rows[:, :0], t_sc[:, :0], dist, torch)
     assert np.array_equal(z_counts, b_counts) and z_rows.shape == (nq, 0)
@@ -121,7 +151,10 @@ def _rank_collectives(rank, world, port, n_total, k, nq, out_dir):
     own = np.flatnonzero((labelled >= first) & (labelled < first + n_local))
     part[own] = sims0[labelled[own] - first]
     full = sharded.gather_sims(part, dist, torch)
-    np.savez(os.path.join(out_dir, "coll_%d.npz" % rank), g_rows=g_rows, g_sc=g_sc, b_counts=b_counts, b_rows=b_rows,
+    np.savez(os.path.join(out_dir, "coll_%d.npz" % rank), g_rows=g_rows, g_sc=g_sc, p_rows=p_rows, p_sc=p_sc, pos=pos,
+             best=np.array(sm.near_best[:2], np.int64), best_sc=np.float32(sm.near_best[2]), n_rows=n_rows, n_sc=n_sc,
+             t_rows=tie_rows, t_sc=tie_sc, pm_rows=pm_rows, pm_sc=pm_sc, s_top=sm.topk[0], s_top_sc=sm.topk[1],
+             s_total=sm.total, sm2_ties=sm2.ties[0], b_counts=b_counts, b_rows=b_rows,
              b_sc=b_sc, sims_full=full, labelled=labelled, score0=score0, sims0=sims0, counts=counts)
     dist.destroy_process_group()
 
@@ -136,12 +169,30 @@ def test_two_rank_lists_batch_topk_and_labelled_sims(tmp_path):
     world, n_total, k, nq, port = 2, 400, 12, 5, _free_port()
     mp.spawn(_rank_collectives, args=(world, port, n_total, k, nq, str(tmp_path)), nprocs=world, join=True)
     out = [np.load(tmp_path / ("coll_%d.npz" % r)) for r in range(world)]
-    for key in ("g_rows", "g_sc", "b_counts", "b_rows", "b_sc", "sims_full"):
+    for key in ("g_rows", "g_sc", "b_counts", "b_rows", "b_sc", "sims_full", "p_rows", "p_sc", "best", "best_sc",
+                "n_rows", "n_sc", "t_rows", "t_sc", "pm_rows", "pm_sc", "s_top", "s_top_sc", "s_total", "sm2_ties"):
         assert np.array_equal(out[0][key], out[1][key]), key            # every rank holds the same result
     # lists: rank 0's matches (rank 1 contributed none), in database order
     score0 = out[0]["score0"]
     m, _ = sc.classify(score0.astype(np.float64), 0.8, 0.35)
     assert np.array_equal(out[0]["g_rows"], m) and np.array_equal(out[0]["g_sc"], score0[m])
+    # near-miss / tie lists, merged top-k, sampled positions and the best near miss against the search set in one piece
+    score_all = np.concatenate([out[r]["score0"] for r in range(world)])
+    _, nm = sc.classify(score_all.astype(np.float64), 0.51, 0.35)
+    ties = np.flatnonzero(score_all == np.float32(0.5))
+    o = out[0]
+    assert np.array_equal(o["n_rows"], nm) and np.array_equal(o["n_sc"], score_all[nm])
+    assert np.array_equal(o["t_rows"], ties) and np.array_equal(o["t_sc"], score_all[ties])
+    assert list(o["s_total"]) == [len(m), len(nm), len(ties)]
+    top = sc.topk_stable(score_all, k)
+    assert np.array_equal(o["s_top"], top) and np.array_equal(o["s_top_sc"], score_all[top])
+    assert np.array_equal(o["p_rows"], nm[o["pos"]]) and np.array_equal(o["p_sc"], score_all[nm[o["pos"]]])
+    assert list(o["pm_rows"]) == [m[-1], m[0]] and list(o["pm_sc"]) == [score_all[m[-1]], score_all[m[0]]]
+    j = int(np.argmax(score_all[nm]))
+    assert list(o["best"]) == [j, nm[j]] and o["best_sc"] == score_all[nm[j]]
+    assert score_all[nm[j]] == np.float32(0.5) and nm[j] == 0             # the tie on both ranks: first in database order
+    n_local = n_total // world
+    assert list(o["sm2_ties"]) == [0, 5, n_local, n_local + 5]
     # batch: against the whole search set scored in one piece
     X = synth.database(5, n_total).astype(np.float64)[:, :, None, :]
     refs = synth.rows(5, list(range(3, 3 + nq))).astype(np.float64)[:, :, None, :]

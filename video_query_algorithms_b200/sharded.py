@@ -167,24 +167,30 @@ def all_gather_np(a, dist, torch, device=None):
     return out.cpu().numpy().reshape((world,) + tuple(np.shape(a)))
 
 
-def gather_lists(rows, scores, dist, torch, device=None):
-    """One rank's ordered match (or near-miss / tie) list -> the search set's list on every rank.
-    Ranks own ascending clip ranges, so concatenating in rank order keeps database order — the order of the
-    reference's `scores` dict that its seeded sampling walks (ticket.py:326-341).  Lengths differ per rank:
-    counts are gathered first, then the lists padded to the longest one."""
-    rows = np.asarray(rows, np.int64)
-    scores = np.asarray(scores, np.float32)
-    counts = all_gather_np(np.array([len(rows)], np.int64), dist, torch, device)[:, 0]
-    cap = int(counts.max())
-    if cap == 0:
-        return np.empty(0, np.int64), np.empty(0, np.float32)
-    pad = np.zeros((cap, 2), np.int64)
-    pad[:len(rows), 0] = rows
-    pad[:len(rows), 1] = scores.view(np.uint32)
-    g = all_gather_np(pad, dist, torch, device)
-    out_r = np.concatenate([g[r, :counts[r], 0] for r in range(len(counts))])
-    out_s = np.concatenate([g[r, :counts[r], 1] for r in range(len(counts))]).astype(np.uint32).view(np.float32)
-    return out_r, out_s
+_STAGE = {}
+
+
+def _staged_all_gather_i32(buf, dist, torch, device):
+    """all_gather of a large int32 buffer through pinned staging tensors kept per device (pageable copies run at a
+    fraction of the PCIe rate and a 100M-clip job gathers tens of MB per query).  Returns a [world, n] int32 view of
+    the pinned result, valid until the next call on this device: the caller copies what it keeps."""
+    if device is None:
+        return all_gather_np(buf, dist, torch, None)
+    world, n = dist.get_world_size(), buf.size
+    st = _STAGE.get(str(device))
+    if st is None or st[0] < n:
+        cap = max(1 << 16, 1 << int(n - 1).bit_length())
+        st = (cap, torch.empty(cap, dtype=torch.int32, pin_memory=True),
+              torch.empty(world * cap, dtype=torch.int32, pin_memory=True),
+              torch.empty(cap, dtype=torch.int32, device=device), torch.empty(world * cap, dtype=torch.int32, device=device))
+        _STAGE[str(device)] = st
+    _, h_in, h_out, d_in, d_out = st
+    h_in.numpy()[:n] = buf
+    d_in[:n].copy_(h_in[:n], non_blocking=True)
+    dist.all_gather_into_tensor(d_out[:world * n], d_in[:n])
+    h_out[:world * n].copy_(d_out[:world * n], non_blocking=True)
+    torch.cuda.current_stream(device).synchronize()
+    return h_out.numpy()[:world * n].reshape(world, n)
 
 
 def gather_batch(counts, topk_rows, topk_scores, dist, torch, device=None):
@@ -215,29 +221,198 @@ def gather_sims(partial, dist, torch, device=None):
     return t.cpu().numpy()
 
 
+TIE_CAP = 32          # tie-band entries per rank that ride in the summary record (the band is 2 * COMPUTE_EPS wide)
+_F32_NINF_BITS = int(np.array([-np.inf], np.float32).view(np.uint32)[0])
+
+
+def _bits(scores):
+    return np.ascontiguousarray(scores, dtype=np.float32).view(np.uint32).astype(np.int64)
+
+
+def _floats(bits):
+    return np.ascontiguousarray(bits).astype(np.uint32).view(np.float32)
+
+
+class RankSummary:
+    """What ONE all_gather of a fixed-size record per rank gives every rank: each rank's first global row and list
+    lengths (so list positions map to their owners without further traffic), the merged top-k, each rank's best
+    near miss and — when every rank's tie band fits TIE_CAP entries — the tie band."""
+
+    def __init__(self, first_rows, counts, topk, near_best, ties):
+        self.first_rows, self.counts, self.topk, self.near_best, self.ties = first_rows, counts, topk, near_best, ties
+
+    @property
+    def total(self):
+        return self.counts.sum(axis=0)
+
+
+def summary_record(first_row, counts3, topk_rows, topk_scores, k, near_best=None, ties=None):
+    """int64 [5 + 2k + 3 + 2*TIE_CAP]: first row | n_match n_near n_tie n_topk | top-k rows | top-k score bits |
+    best near miss (position in this rank's near-miss list, global row, score bits; row -1 = none) | tie rows | tie bits."""
+    rec = np.empty(5 + 2 * k + 3 + 2 * TIE_CAP, np.int64)
+    rec[0] = first_row
+    rec[1:5] = pack_payload(list(counts3) + [len(topk_rows)], topk_rows, topk_scores, k)[:4]
+    rec[5:5 + 2 * k] = pack_payload([0, 0, 0, 0], topk_rows, topk_scores, k)[4:]
+    o = 5 + 2 * k
+    rec[o:o + 3] = (-1, -1, 0)
+    if near_best is not None and near_best[1] >= 0:
+        rec[o:o + 3] = near_best[0], near_best[1], _bits([near_best[2]])[0]
+    o += 3
+    rec[o:o + TIE_CAP] = -1
+    rec[o + TIE_CAP:] = _F32_NINF_BITS
+    if ties is not None and len(ties[0]) <= TIE_CAP:
+        rec[o:o + len(ties[0])] = ties[0]
+        rec[o + TIE_CAP:o + TIE_CAP + len(ties[0])] = _bits(ties[1])
+    return rec
+
+
+def exchange_summary(rec, k, dist, torch, device=None):
+    """all_gather of summary_record -> RankSummary (identical on every rank)."""
+    g = all_gather_np(rec, dist, torch, device)
+    world = g.shape[0]
+    counts = g[:, 1:4].copy()
+    pay = np.concatenate([g[:, 1:5], g[:, 5:5 + 2 * k]], axis=1)
+    _, t_rows, t_scores = unpack_payload(merge_payloads_host(pay, world, k), k) if k else \
+        (None, np.empty(0, np.int64), np.empty(0, np.float32))
+    o = 5 + 2 * k
+    best, base = None, 0
+    for r in range(world):                                   # highest score; equal scores: the lower rank = the earlier rows
+        if g[r, o + 1] >= 0:
+            sc = float(_floats(g[r, o + 2:o + 3])[0])
+            if best is None or sc > best[2]:
+                best = (base + int(g[r, o]), int(g[r, o + 1]), sc)
+        base += int(counts[r, 1])
+    o += 3
+    ties = None
+    if int(counts[:, 2].max(initial=0)) <= TIE_CAP:
+        ties = (np.concatenate([g[r, o:o + counts[r, 2]] for r in range(world)]),
+                _floats(np.concatenate([g[r, o + TIE_CAP:o + TIE_CAP + counts[r, 2]] for r in range(world)])))
+    return RankSummary(g[:, 0].copy(), counts, (t_rows, t_scores), best, ties)
+
+
+def gather_lists_packed(lists, which, summary, dist, torch, device=None):
+    """Several ordered lists of this rank -> the search set's, with ONE all_gather: the lists (columns `which` of the
+    summary's counts) go back to back into one buffer of two planes — int64 global rows, then fp32 scores, 12 bytes
+    per entry — padded to the longest rank's total.  Planes, not pairs, and no re-basing of the rows: every copy on
+    either side is a plain contiguous memcpy (numpy's casting loops run at ~1.5 ns per entry, slower than the wire)."""
+    rank = dist.get_rank()
+    counts = summary.counts[:, which]
+    cap = int(counts.sum(axis=1).max(initial=0))
+    if cap == 0:
+        return [(np.empty(0, np.int64), np.empty(0, np.float32)) for _ in which]
+    buf = np.zeros(3 * cap, np.int32)                         # collectives carry int32 on every backend
+    b_rows, b_scores = buf[:2 * cap].view(np.int64), buf[2 * cap:].view(np.float32)
+    o = 0
+    for (rows, scores), n in zip(lists, counts[rank]):
+        assert len(rows) == n
+        b_rows[o:o + n] = rows
+        b_scores[o:o + n] = scores
+        o += n
+    g = _staged_all_gather_i32(buf, dist, torch, device)
+    out = []
+    starts = np.concatenate([np.zeros((len(counts), 1), np.int64), np.cumsum(counts, axis=1)], axis=1)
+    for j in range(len(which)):
+        n_j = counts[:, j]
+        rows = np.empty(int(n_j.sum()), np.int64)
+        scores = np.empty(len(rows), np.float32)
+        o = 0
+        for r in range(len(counts)):
+            a, n = int(starts[r, j]), int(n_j[r])
+            rows[o:o + n] = g[r, :2 * cap].view(np.int64)[a:a + n]
+            scores[o:o + n] = g[r, 2 * cap:].view(np.float32)[a:a + n]
+            o += n
+        out.append((rows, scores))
+    return out
+
+
+def gather_positions_multi(requests, summary, local_gather, dist, torch, device=None):
+    """requests: [(list column in the summary's counts, positions in the search set's list)], the same on every
+    rank.  Each rank fetches the entries its own lists hold with `local_gather(column, local positions) -> (global
+    rows, fp32 scores)`; ONE all_reduce of 16 bytes per position gives every rank all of them (x + 0: exact)."""
+    rank = dist.get_rank()
+    reqs = [(c, np.asarray(p, np.int64).reshape(-1)) for c, p in requests]
+    out = np.zeros((sum(len(p) for _, p in reqs), 2), np.int64)
+    o = 0
+    for c, pos in reqs:
+        n_list = summary.counts[:, c]
+        if len(pos) and (pos.min() < 0 or pos.max() >= int(n_list.sum())):
+            raise _ffi.VQError("gather: position outside the list of %d entries" % int(n_list.sum()))
+        base = int(n_list[:rank].sum())
+        sel = np.flatnonzero((pos >= base) & (pos < base + int(n_list[rank])))
+        if len(sel):
+            r, sc = local_gather(c, np.ascontiguousarray(pos[sel] - base))
+            out[o + sel, 0] = r
+            out[o + sel, 1] = _bits(sc)
+        o += len(pos)
+    if len(out):
+        t = _t(out, torch, device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        out = t.cpu().numpy()
+    res, o = [], 0
+    for _, pos in reqs:
+        res.append((out[o:o + len(pos), 0].copy(), _floats(out[o:o + len(pos), 1])))
+        o += len(pos)
+    return res
+
+
 class RankStore:
     """One rank's shard of a search set as a FeatureStore (`first_global_row` = the start of its clip range) plus
     the collectives that turn per-rank results into the search set's.  Every rank calls every method (they are
-    collectives) and every rank gets the same result."""
+    collectives) and every rank gets the same result.  A single-query call costs two collectives: one fixed-size
+    summary record per rank (RankSummary), then either the packed lists (scan) or the sampled entries (gather)."""
+
+    _COL = {"matches": 0, "near_misses": 1, "ties": 2}
 
     def __init__(self, store, dist, torch, device=None):
         self.store, self.dist, self.torch, self.device = store, dist, torch, device
         self.world = dist.get_world_size()
         self.lo = store.first_global_row
         self.hi = store.first_global_row + store.n_rows
+        self.summary = None
+
+    def _summarise(self, res, k, near_best=None):
+        rows, scores = self.store.topk() if k else (np.empty(0, np.int64), np.empty(0, np.float32))
+        ties = self.store.ties(copy=False)
+        rec = summary_record(self.lo, [res.n_match, res.n_near, res.n_tie], rows, scores, k, near_best, ties)
+        self.summary = exchange_summary(rec, k, self.dist, self.torch, self.device)
+        return ties
 
     def scan(self, target_features, weights, threshold, lower_limit, eps, topk=0):
         """Full single-query result with host buffers: counts [match, near, tie], ordered global match /
         near-miss / tie lists and the merged top-k."""
         res = self.store.scan(target_features, weights, threshold, lower_limit, eps, topk=topk)
-        k = int(topk)
-        rows, scores = self.store.topk() if k else (np.empty(0, np.int64), np.empty(0, np.float32))
-        payload = pack_payload([res.n_match, res.n_near, res.n_tie, len(rows)], rows, scores, k)
-        merged = merge_payloads_host(all_gather_np(payload, self.dist, self.torch, self.device), self.world, k)
-        counts, t_rows, t_scores = unpack_payload(merged, k)
-        lists = [gather_lists(*fn(copy=False), self.dist, self.torch, self.device)
-                 for fn in (self.store.matches, self.store.near_misses, self.store.ties)]
-        return counts[:3], lists, (t_rows, t_scores)
+        ties = self._summarise(res, int(topk))
+        sm = self.summary
+        mine = [self.store.matches(copy=False), self.store.near_misses(copy=False)]
+        if sm.ties is not None:
+            lists = gather_lists_packed(mine, [0, 1], sm, self.dist, self.torch, self.device) + [sm.ties]
+        else:
+            lists = gather_lists_packed(mine + [ties], [0, 1, 2], sm, self.dist, self.torch, self.device)
+        return sm.total, lists, sm.topk
+
+    def scan_select(self, target_features, weights, threshold, lower_limit, eps, topk=0):
+        """The review round's variant (ticket.py:311-356 samples a few dozen clips): every rank's match / near-miss
+        lists stay on its device; what crosses ranks is one summary record per rank (counts, top-k, tie band, best
+        near miss).  Returns (counts [match, near, tie], (top-k rows, scores), tie list, best near miss
+        (position in the search set's near-miss list, global row, score) or None); fetch sampled list entries with
+        gather() / gather_many()."""
+        res = self.store.scan(target_features, weights, threshold, lower_limit, eps, topk=topk, lists=False)
+        ties = self._summarise(res, int(topk), self.store.near_best())
+        sm = self.summary
+        tie_list = sm.ties if sm.ties is not None else \
+            gather_lists_packed([ties], [2], sm, self.dist, self.torch, self.device)[0]
+        return sm.total, sm.topk, tie_list, sm.near_best
+
+    def gather_many(self, requests):
+        """[(which, positions)] -> [(global rows, fp32 scores)]: entries of the search set's ordered match / near-miss /
+        tie lists of the last scan at the given positions (the same on every rank), one collective for all requests."""
+        names = {v: n for n, v in self._COL.items()}
+        return gather_positions_multi([(self._COL[w], p) for w, p in requests], self.summary,
+                                      lambda c, local: self.store.gather(names[c], local),
+                                      self.dist, self.torch, self.device)
+
+    def gather(self, which, positions):
+        return self.gather_many([(which, positions)])[0]
 
     def scan_batch(self, targets, weights, threshold, lower_limit, topk=0):
         c, r, s, ms = self.store.scan_batch(targets, weights, threshold, lower_limit, topk=topk)
