@@ -296,15 +296,17 @@ def main():
                 "+ topk + tie band + gather of 10 sampled matches and 9 sampled near misses + best near miss; "
                 "the match / near-miss lists stay on the device")
     if world > 1:
+        small_how = ("through the shared-memory host mailbox, vq_hostx_allgather" if rstore.mailbox is not None
+                     else "NCCL collectives staged through the devices")
         e2e_what = ("RankStore.scan on every rank (one process per GPU): the local FeatureStore.scan as above, then the "
-                    "two collectives that give EVERY rank the search set's result — an allgather of one summary record per "
-                    "rank (counts, top-k, tie band; merged on the host) and an allgather of the ordered match / near-miss "
+                    "two exchanges that give EVERY rank the search set's result — an all-gather of one summary record per "
+                    "rank (counts, top-k, tie band; %s; merged on the host) and an NCCL allgather of the ordered match / near-miss "
                     "lists packed as (local row, score) = 8 B per entry (%d entries in all, padded to the longest rank's); "
                     "h2d / d2h bytes are this rank's shard-to-host traffic, the collectives' staging copies come on top"
-                    % n_listed)
-        sel_what = ("RankStore.scan_select + gather_many on every rank: lists stay on each rank's device; two collectives — "
-                    "an allgather of one summary record per rank (counts, top-k, tie band, best near miss) and one "
-                    "all_reduce of 16 B per position that fetches the 19 sampled entries from the ranks that own them")
+                    % (small_how, n_listed))
+        sel_what = ("RankStore.scan_select + gather_many on every rank: lists stay on each rank's device; two exchanges (%s) — "
+                    "one summary record per rank (counts, top-k, tie band, best near miss) and 16 B per position to fetch "
+                    "the 19 sampled entries from the ranks that own them" % small_how)
 
     # ---- the review round's call (Ticket.select_clips_to_review): lists stay on the device, the host draws 20 list
     # positions with the reference's RNG and gathers just those entries + the best near miss
@@ -419,6 +421,8 @@ def main():
                                          "sample": "200000-clip slice, one pass (%.1f s), BLAS on all cores" % vdt}}
         emit(line)
     # global result of the last timed step (all ranks hold the same merged payload)
+    if rstore is not None:
+        rstore.close()
     rank_scan.close()
     if world > 1:
         dist.destroy_process_group()

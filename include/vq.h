@@ -152,6 +152,19 @@ int vq_scan_exchange_enqueue_lagged(vq_store *s, vq_exchange *x, void *stream);
 int vq_exchange_flush_enqueue(vq_exchange *x, void *stream);
 int vq_exchange_merged(vq_exchange *x, const int64_t **merged_dev /* [4 + 2*topk] */);
 
+/* Host mailbox: all-gather of small records (up to slot_bytes each) between the rank processes of ONE box through a
+ * POSIX shared-memory segment — the host-side twin of the exchange above, for what the host needs from its peers per
+ * query: counts, top-k, tie band, best near miss, sampled list entries (a few KB; a collective library would stage
+ * them through the devices with two stream synchronisations).  `name` ("/vq-<unique per job>") is created by rank 0
+ * and opened by the others — the caller puts a barrier between the two — and can be unlinked as soon as all ranks are
+ * attached.  vq_hostx_allgather is a collective: every rank makes the same calls with the same nbytes; all_out is
+ * [world][nbytes]; it fails (instead of hanging) when a peer has not arrived within timeout_s (<= 0: 60 s).           */
+typedef struct vq_hostx vq_hostx;
+int vq_hostx_create(vq_hostx **out, const char *name, int world, int rank, int64_t slot_bytes);
+int vq_hostx_unlink(vq_hostx *x);
+int vq_hostx_allgather(vq_hostx *x, const void *mine, int64_t nbytes, void *all_out, double timeout_s);
+int vq_hostx_destroy(vq_hostx *x);
+
 /* per-launch device times of K1 recorded since the last call (ring of 1024), in ms           */
 int vq_scan_kernel_times(vq_store *s, int32_t cap, float *ms_out, int32_t *n_out);
 /* merge per-shard top-k lists (score desc, global row asc) — the host/rank-0 side of the

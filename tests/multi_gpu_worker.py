@@ -103,6 +103,17 @@ def main():
             print("exchange %s: counts %s  equal to single-GPU scan: %s" % (mode, counts.tolist(), same))
             ok = ok and same
         full.close()
+    # the same selection scan with the small exchanges on NCCL instead of the host mailbox
+    rstore2 = RankStore(st, dist, torch, dev, host_mailbox=False)
+    n_counts, n_top, n_ties, n_best = rstore2.scan_select(tf, (1.0, 1.5), 0.81, 0.73, 3e-6, topk=k)
+    n_m, n_n = rstore2.gather_many([("matches", pos_m), ("near_misses", pos_n)])
+    same = (rstore.mailbox is not None and np.array_equal(n_counts, s_counts) and np.array_equal(n_top[0], s_trows) and
+            n_best == s_best and np.array_equal(n_m[0], s_m[0]) and np.array_equal(n_n[1], s_n[1]) and
+            np.array_equal(n_ties[0], s_ties[0]))
+    if rank == 0:
+        print("host mailbox and NCCL small exchanges agree: %s" % same)
+    ok = ok and same
+    rstore.close()
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, src=0)
     st.close()

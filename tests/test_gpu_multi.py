@@ -23,4 +23,4 @@ def test_sharded_scan_equals_single_gpu_scan():
     assert r.returncode == 0
     assert "exchange p2p:" in r.stdout and "exchange p2p-lagged:" in r.stdout and "exchange nccl:" in r.stdout
     assert "rank store scan" in r.stdout and "rank store batched scan" in r.stdout and "rank store labelled sims" in r.stdout
-    assert "rank store selection scan" in r.stdout
+    assert "rank store selection scan" in r.stdout and "host mailbox and NCCL small exchanges agree: True" in r.stdout

@@ -325,3 +325,57 @@ def test_feature_tree_parser_on_reference_fixture_if_present():
     for si, s in enumerate(("rgb", "warped_optical_flow")):
         for pi, p in enumerate(z["splits"]):
             assert np.array_equal(v["features"][s][int(p)], z["X"][:, si, pi])
+
+
+def test_host_mailbox_allgather_between_threads_and_its_failure_modes(built_lib):
+    """vq_hostx_* (csrc/vq_hostx.cu), the shared-memory all-gather of the rank-level path: three 'ranks' (threads with
+    their own handles on one segment; ctypes drops the GIL) make 3000 calls of changing sizes and check every peer's
+    record each time; a peer that never arrives is a timeout error, not a hang; oversized records, a second creation
+    of the same name and attaching to a missing segment are refused."""
+    import threading
+    lib, VQError = built_lib.lib(), built_lib.VQError
+    name = ("/vq-test-%d" % os.getpid()).encode()
+    world, slot = 3, 4096
+    hs = [ctypes.c_void_p() for _ in range(world)]
+    for r in range(world):
+        built_lib.check(lib.vq_hostx_create(ctypes.byref(hs[r]), name, world, r, slot), "vq_hostx_create")
+    dup = ctypes.c_void_p()
+    assert lib.vq_hostx_create(ctypes.byref(dup), name, world, 0, slot) != 0          # the name exists
+    assert b"shm_open" in lib.vq_last_error()
+    assert lib.vq_hostx_create(ctypes.byref(dup), name, world, 1, slot * 2) != 0      # ranks disagree on the slot size
+    built_lib.check(lib.vq_hostx_unlink(hs[0]), "vq_hostx_unlink")
+    assert not os.path.exists("/dev/shm" + name.decode())
+    assert lib.vq_hostx_create(ctypes.byref(dup), name, world, 1, slot) != 0          # nothing to attach to any more
+    errs = []
+
+    def rank_main(r):
+        try:
+            rng = np.random.default_rng(1234)                                          # same sizes on every rank
+            for c in range(3000):
+                n = int(rng.integers(0, slot // 8 + 1))
+                mine = np.arange(n, dtype=np.int64) * (r + 1) + c
+                out = np.empty((world, n), np.int64)
+                built_lib.check(lib.vq_hostx_allgather(hs[r], built_lib.ptr(mine), mine.nbytes, built_lib.ptr(out), 30.0),
+                                "vq_hostx_allgather")
+                for q in range(world):
+                    if not np.array_equal(out[q], np.arange(n, dtype=np.int64) * (q + 1) + c):
+                        raise AssertionError("call %d: rank %d read a wrong record of rank %d" % (c, r, q))
+        except Exception as e:
+            errs.append(e)
+
+    ts = [threading.Thread(target=rank_main, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs
+    big = np.zeros(slot // 8 + 16, np.int64)
+    out = np.empty((world, len(big)), np.int64)
+    assert lib.vq_hostx_allgather(hs[0], built_lib.ptr(big), big.nbytes, built_lib.ptr(out), 1.0) == -1
+    one = np.zeros(1, np.int64)
+    assert lib.vq_hostx_allgather(hs[0], built_lib.ptr(one), 8, built_lib.ptr(out), 0.2) == -3   # the peers never call
+    assert b"waited" in lib.vq_last_error()
+    with pytest.raises(VQError):
+        built_lib.check(-3, "vq_hostx_allgather")
+    for h in hs:
+        lib.vq_hostx_destroy(h)

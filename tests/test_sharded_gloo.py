@@ -123,6 +123,16 @@ def _rank_collectives(rank, world, port, n_total, k, nq, out_dir):
                                  (first + ties, score0[ties]))
     sm = sharded.exchange_summary(rec, k, dist, torch)
     assert sm.ties is None
+    # the same exchange through the shared-memory mailbox (both ranks run on this host) gives the same summary
+    mb = sharded.HostMailbox.try_create(dist)
+    assert mb is not None
+    sm_mb = sharded.exchange_summary(rec, k, dist, torch, mailbox=mb)
+    assert np.array_equal(sm_mb.counts, sm.counts) and np.array_equal(sm_mb.first_rows, sm.first_rows)
+    assert np.array_equal(sm_mb.topk[0], sm.topk[0]) and np.array_equal(sm_mb.topk[1], sm.topk[1])
+    assert sm_mb.near_best == sm.near_best and sm_mb.ties is None
+    tiny = sharded.HostMailbox(dist, slot_bytes=64)          # records that do not fit the slots use `dist`
+    assert not tiny.fits(rec) and sharded.exchange_summary(rec, k, dist, torch, mailbox=tiny).near_best == sm.near_best
+    tiny.close()
     mine = [(first + m, score0[m]), (first + nm, score0[nm]), (first + ties, score0[ties])]
     (g_rows, g_sc), (n_rows, n_sc), (tie_rows, tie_sc) = sharded.gather_lists_packed(mine, [0, 1, 2], sm, dist, torch)
     # a short tie band rides in the summary record itself; k = 0 and no near miss at all
@@ -138,6 +148,10 @@ def _rank_collectives(rank, world, port, n_total, k, nq, out_dir):
     (p_rows, p_sc), (pm_rows, pm_sc), (e_rows, _) = sharded.gather_positions_multi(
         [(1, pos), (0, pos_m), (2, [])], sm, lambda c, loc: (local[c][0][loc], local[c][1][loc]), dist, torch)
     assert len(e_rows) == 0
+    (q_rows, q_sc), (qm_rows, qm_sc), _ = sharded.gather_positions_multi(
+        [(1, pos), (0, pos_m), (2, [])], sm, lambda c, loc: (local[c][0][loc], local[c][1][loc]), dist, torch, mailbox=mb)
+    assert np.array_equal(q_rows, p_rows) and np.array_equal(q_sc, p_sc) and np.array_equal(qm_rows, pm_rows)
+    mb.close()
     try:
         sharded.gather_positions_multi([(1, [int(n_near.sum())])], sm, None, dist, torch)
         raise AssertionError("position beyond the list accepted")

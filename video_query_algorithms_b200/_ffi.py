@@ -75,6 +75,10 @@ PROTOTYPES = {
     "vq_scan_exchange_enqueue_lagged": (C.c_int, [_vp, _vp, _vp]),
     "vq_exchange_flush_enqueue": (C.c_int, [_vp, _vp]),
     "vq_exchange_merged": (C.c_int, [_vp, _P(_vp)]),
+    "vq_hostx_create": (C.c_int, [_P(_vp), C.c_char_p, C.c_int, C.c_int, _i64]),
+    "vq_hostx_unlink": (C.c_int, [_vp]),
+    "vq_hostx_allgather": (C.c_int, [_vp, _vp, _i64, _vp, C.c_double]),
+    "vq_hostx_destroy": (C.c_int, [_vp]),
     "vq_scan_kernel_times": (C.c_int, [_vp, _i32, _vp, _P(_i32)]),
     "vq_merge_topk": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _P(_i32)]),
     "vq_merge_topk_batch": (C.c_int, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),

@@ -167,6 +167,73 @@ def all_gather_np(a, dist, torch, device=None):
     return out.cpu().numpy().reshape((world,) + tuple(np.shape(a)))
 
 
+class HostMailbox:
+    """All-gather of small host records between the rank processes of one box through shared memory
+    (vq_hostx_*, csrc/vq_hostx.cu): no device hop, no stream synchronisation.  Setup is a collective on `dist`
+    (a unique segment name from rank 0, create / attach around a barrier, unlink once everybody is attached)."""
+
+    def __init__(self, dist, slot_bytes=1 << 16, timeout_s=60.0):
+        import os
+        import secrets
+        self.world, self.rank = dist.get_world_size(), dist.get_rank()
+        self.slot_bytes, self.timeout_s = int(slot_bytes), float(timeout_s)
+        name = ["/vq-%d-%s" % (os.getpid(), secrets.token_hex(6))] if self.rank == 0 else [None]
+        dist.broadcast_object_list(name, src=0)
+        self._x = C.c_void_p()
+        err = None
+        for turn in (0, 1):                                  # rank 0 creates, barrier, the others attach, barrier
+            if (self.rank == 0) == (turn == 0):
+                try:
+                    check(lib().vq_hostx_create(C.byref(self._x), name[0].encode(), self.world, self.rank,
+                                                self.slot_bytes), "vq_hostx_create")
+                except _ffi.VQError as e:
+                    err, self._x = e, C.c_void_p()
+            dist.barrier()
+        flags = [None] * self.world
+        dist.all_gather_object(flags, err is None)
+        if self._x:
+            lib().vq_hostx_unlink(self._x)
+        if not all(flags):                                   # e.g. ranks in different containers: nobody uses it
+            self.close()
+            raise _ffi.VQError("host mailbox unavailable on ranks %s: %s"
+                               % ([r for r, f in enumerate(flags) if not f], err or "see those ranks"))
+
+    @classmethod
+    def try_create(cls, dist, **kw):
+        """A mailbox when every rank of `dist` runs on this host and can attach, else None (callers then use the
+        collectives of `dist`).  Every rank gets the same answer."""
+        import socket
+        hosts = [None] * dist.get_world_size()
+        dist.all_gather_object(hosts, socket.gethostname())
+        if len(set(hosts)) != 1:
+            return None
+        try:
+            return cls(dist, **kw)
+        except _ffi.VQError:
+            return None
+
+    def fits(self, a):
+        return a.nbytes <= self.slot_bytes
+
+    def all_gather(self, a):
+        """numpy [..] on every rank -> numpy [world, ..] on every rank (same shape and dtype on all ranks)."""
+        a = np.ascontiguousarray(a)
+        out = np.empty((self.world,) + a.shape, a.dtype)
+        check(lib().vq_hostx_allgather(self._x, ptr(a), a.nbytes, ptr(out), self.timeout_s), "vq_hostx_allgather")
+        return out
+
+    def close(self):
+        if self._x:
+            lib().vq_hostx_destroy(self._x)
+            self._x = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 _STAGE = {}
 
 
@@ -266,9 +333,10 @@ def summary_record(first_row, counts3, topk_rows, topk_scores, k, near_best=None
     return rec
 
 
-def exchange_summary(rec, k, dist, torch, device=None):
-    """all_gather of summary_record -> RankSummary (identical on every rank)."""
-    g = all_gather_np(rec, dist, torch, device)
+def exchange_summary(rec, k, dist, torch, device=None, mailbox=None):
+    """all_gather of summary_record -> RankSummary (identical on every rank); through the host mailbox when there
+    is one and the record fits its slots, else a collective of `dist`."""
+    g = mailbox.all_gather(rec) if mailbox is not None and mailbox.fits(rec) else all_gather_np(rec, dist, torch, device)
     world = g.shape[0]
     counts = g[:, 1:4].copy()
     pay = np.concatenate([g[:, 1:5], g[:, 5:5 + 2 * k]], axis=1)
@@ -325,10 +393,11 @@ def gather_lists_packed(lists, which, summary, dist, torch, device=None):
     return out
 
 
-def gather_positions_multi(requests, summary, local_gather, dist, torch, device=None):
+def gather_positions_multi(requests, summary, local_gather, dist, torch, device=None, mailbox=None):
     """requests: [(list column in the summary's counts, positions in the search set's list)], the same on every
     rank.  Each rank fetches the entries its own lists hold with `local_gather(column, local positions) -> (global
-    rows, fp32 scores)`; ONE all_reduce of 16 bytes per position gives every rank all of them (x + 0: exact)."""
+    rows, fp32 scores)`; ONE exchange of 16 bytes per position — an all-gather through the host mailbox summed here, or
+    an all_reduce of `dist` — gives every rank all of them (x + 0 on integers: exact)."""
     rank = dist.get_rank()
     reqs = [(c, np.asarray(p, np.int64).reshape(-1)) for c, p in requests]
     out = np.zeros((sum(len(p) for _, p in reqs), 2), np.int64)
@@ -344,7 +413,9 @@ def gather_positions_multi(requests, summary, local_gather, dist, torch, device=
             out[o + sel, 0] = r
             out[o + sel, 1] = _bits(sc)
         o += len(pos)
-    if len(out):
+    if len(out) and mailbox is not None and mailbox.fits(out):
+        out = mailbox.all_gather(out).sum(axis=0)
+    elif len(out):
         t = _t(out, torch, device)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         out = t.cpu().numpy()
@@ -358,23 +429,31 @@ def gather_positions_multi(requests, summary, local_gather, dist, torch, device=
 class RankStore:
     """One rank's shard of a search set as a FeatureStore (`first_global_row` = the start of its clip range) plus
     the collectives that turn per-rank results into the search set's.  Every rank calls every method (they are
-    collectives) and every rank gets the same result.  A single-query call costs two collectives: one fixed-size
-    summary record per rank (RankSummary), then either the packed lists (scan) or the sampled entries (gather)."""
+    collectives) and every rank gets the same result.  A single-query call costs two exchanges: one fixed-size
+    summary record per rank (RankSummary), then either the packed lists (scan) or the sampled entries (gather).
+    The small ones go through the host mailbox when all ranks share a box, the lists through `dist`."""
 
     _COL = {"matches": 0, "near_misses": 1, "ties": 2}
 
-    def __init__(self, store, dist, torch, device=None):
+    def __init__(self, store, dist, torch, device=None, host_mailbox=True):
         self.store, self.dist, self.torch, self.device = store, dist, torch, device
         self.world = dist.get_world_size()
         self.lo = store.first_global_row
         self.hi = store.first_global_row + store.n_rows
         self.summary = None
+        # ranks of one box exchange their small per-query records through shared memory (collective setup)
+        self.mailbox = HostMailbox.try_create(dist) if host_mailbox else None
+
+    def close(self):
+        if self.mailbox is not None:
+            self.mailbox.close()
+            self.mailbox = None
 
     def _summarise(self, res, k, near_best=None):
         rows, scores = self.store.topk() if k else (np.empty(0, np.int64), np.empty(0, np.float32))
         ties = self.store.ties(copy=False)
         rec = summary_record(self.lo, [res.n_match, res.n_near, res.n_tie], rows, scores, k, near_best, ties)
-        self.summary = exchange_summary(rec, k, self.dist, self.torch, self.device)
+        self.summary = exchange_summary(rec, k, self.dist, self.torch, self.device, self.mailbox)
         return ties
 
     def scan(self, target_features, weights, threshold, lower_limit, eps, topk=0):
@@ -409,7 +488,7 @@ class RankStore:
         names = {v: n for n, v in self._COL.items()}
         return gather_positions_multi([(self._COL[w], p) for w, p in requests], self.summary,
                                       lambda c, local: self.store.gather(names[c], local),
-                                      self.dist, self.torch, self.device)
+                                      self.dist, self.torch, self.device, self.mailbox)
 
     def gather(self, which, positions):
         return self.gather_many([(which, positions)])[0]
