@@ -113,6 +113,7 @@ def _rank_collectives(rank, world, port, n_total, k, nq, out_dir):
     m, _ = sc.classify(score0.astype(np.float64), th, 0.35)
     _, nm = sc.classify(score0.astype(np.float64), 0.51, 0.35)   # ties at 0.5 top the near-miss band: the first one wins
     ties = np.flatnonzero(score0 == np.float32(0.5))
+    sharded.TIE_CAP = 16                                     # (512 in production; every rank uses the same value)
     assert len(ties) > sharded.TIE_CAP
     lb = None
     if len(nm):

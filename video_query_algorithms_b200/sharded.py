@@ -288,7 +288,7 @@ def gather_sims(partial, dist, torch, device=None):
     return t.cpu().numpy()
 
 
-TIE_CAP = 32          # tie-band entries per rank that ride in the summary record (the band is 2 * COMPUTE_EPS wide)
+TIE_CAP = 512         # tie-band entries per rank that ride in the summary record (the band is 2 * COMPUTE_EPS wide: ~10 per 1M clips)
 _F32_NINF_BITS = int(np.array([-np.inf], np.float32).view(np.uint32)[0])
 
 
