@@ -44,14 +44,24 @@ def parse():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--clips-per-gpu", type=int, default=1_000_000)
+    ap.add_argument("--workload", default="config2", choices=["config2", "config4", "config5"],
+                    help="config2 (default, the metric's configuration): single-query scan of 1M clips per GPU; config4: "
+                         "256-query batch against 10M clips per GPU on the tensor cores; config5: 1000 bootstrap replicates "
+                         "of the weight update over 5000 labelled clips of a 1M-clip DB")
+    ap.add_argument("--clips-per-gpu", type=int, default=None, help="default 1M (config2, config5) / 10M (config4)")
+    ap.add_argument("--queries", type=int, default=256, help="config4: queries per batch")
+    ap.add_argument("--labelled", type=int, default=5000, help="config5: labelled clips")
+    ap.add_argument("--replicates", type=int, default=1000, help="config5: bootstrap replicates per step")
     ap.add_argument("--no-cold", action="store_true", help="skip the cold end-to-end leg (8 GB upload per step)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--exchange", default="p2p-lagged", choices=["p2p-lagged", "p2p", "nccl"],
                     help="N > 1: peer-memory push + fused merge kernel, merging the previous step's payloads while this "
                          "step's are in flight (default; the last step is flushed inside the timed region), the same "
                          "merging in-step, or NCCL allgather + merge kernel")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.clips_per_gpu is None:
+        a.clips_per_gpu = 10_000_000 if a.workload == "config4" else 1_000_000
+    return a
 
 
 # ------------------------------------------------------------------------------------ clocks
@@ -173,6 +183,10 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         return run_reference(args, rank, world)
+    if args.workload == "config4":
+        return run_batched(args, rank, world, local_rank)
+    if args.workload == "config5":
+        return run_bootstrap(args, rank, world, local_rank)
 
     import torch
     import torch.distributed as dist
@@ -426,6 +440,205 @@ def main():
     rank_scan.close()
     if world > 1:
         dist.destroy_process_group()
+    st.close()
+
+
+# ------------------------------------------------------------------------------------ the other GPU configs
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)
+    except Exception:
+        return {}
+
+
+def _setup(local_rank, world):
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__ as g
+    g.build()
+    import video_query_algorithms_b200 as vq
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    return torch, dist, vq, dev
+
+
+def run_batched(args, rank, world, local_rank):
+    """BASELINE configs[3]: Q targets against every rank's resident shard in one pass on the tensor cores (K3), per-query
+    counts + top-k; N > 1: weak scaling, per-query top-k merged across ranks (RankStore.scan_batch).  A step = one
+    scan_batch call with host buffers in and out; `value` uses the device time of its kernels (CUDA events on the
+    library's stream, max over ranks), `e2e` the wall time of the call between barriers."""
+    torch, dist, vq, dev = _setup(local_rank, world)
+    n, Q = args.clips_per_gpu, args.queries
+    st = vq.FeatureStore(n, STREAMS, [1], DIM, devices=[local_rank], first_global_row=rank * n)
+    st.fill_synthetic(DATA_SEED)
+    T = torch.zeros(Q * 2 * DIM, dtype=torch.float32, device=dev)
+    if rank == 0:                                            # the query clips live in rank 0's shard
+        t = np.empty((Q, 2, 1, DIM), np.float32)
+        for q in range(Q):
+            f = st.download(REF_ROW + 37 * q, 1)[0].astype(np.float64)
+            t[q, :, 0] = [vq.TargetClip._scale_feature(f[s_, 0]) for s_ in range(2)]
+        T.copy_(torch.from_numpy(t.reshape(-1)))
+    if world > 1:
+        dist.broadcast(T, src=0)
+    targets = T.cpu().numpy().reshape(Q, 2, 1, DIM)
+    lower = THRESHOLD - NEAR_MISS * (1 - THRESHOLD)
+    rstore = None
+    if world > 1:
+        from video_query_algorithms_b200.sharded import RankStore
+        rstore = RankStore(st, dist, torch, dev)
+    call = (rstore or st).scan_batch
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(max(args.warmup, 3)):
+        call(targets, WEIGHTS, THRESHOLD, lower, topk=TOPK)
+    steps = args.steps if args.steps != 300 else 20          # the default K is config2's; a step here is ~30 ms
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    k_ms = []
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        counts, rows, scores, ms = call(targets, WEIGHTS, THRESHOLD, lower, topk=TOPK)
+        k_ms.append(ms)
+    barrier()
+    wall = time.perf_counter() - t0
+    sampler.stop_flag = True
+    sampler.join()
+    tt = torch.tensor(k_ms + [wall], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    tt = tt.tolist()
+    k_ms, wall = tt[:-1], tt[-1]
+    if rank == 0:
+        ms_step = float(np.mean(k_ms))
+        pairs = float(world) * n * Q
+        flops = 2.0 * pairs * 2 * DIM                        # algorithmic: 2 * Q * N * S * D
+        pk = _peaks()
+        peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1590.0)))
+        achieved = flops / world / (ms_step * 1e-3) / 1e12   # per GPU, like the peak
+        line = {
+            "metric": "clip-query pairs scored/sec (batched queries)", "value": pairs / (ms_step * 1e-3), "unit": "pairs/s",
+            "n_gpus": world, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16x2 (fp32 split into two bf16 terms, fp32 accumulate)",
+            "data": "synthetic (VQSYN-1 counter-based generator, on device)",
+            "config": {"workload": "configs[3]: batched %d-query scoring vs %d clips per GPU as tcgen05 GEMM + fused "
+                                   "per-query counts and top-%d" % (Q, n, TOPK), "clips_per_gpu": n, "global_clips": n * world,
+                       "queries": Q, "streams": 2, "dim": DIM, "topk": TOPK, "threshold": THRESHOLD, "near_miss": NEAR_MISS,
+                       "weights": list(WEIGHTS), "parallelism": "clip-range shards x%d" % world,
+                       "l2": "input %.1f GB per GPU > 126 MB L2, no flush" % (n * ROW_BYTES / 1e9)},
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "batch_scan_bf16 (K3) + batch_compact", "kernel_ms": ms_step,
+                         "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16, back to back)" if pk
+                         else "fallback 1590", "algorithmic_flops_per_step_per_gpu": flops / world,
+                         "executed_tflops_bf16x2": 3 * achieved, "frac_executed": 3 * achieved / peak,
+                         "note": "three bf16 MMAs per fp32 product (x1*t1 + x2*t1 + x1*t2): the tensor pipe executes 3x "
+                                 "the algorithmic flops"},
+            "e2e": {"value": pairs * steps / wall, "unit": "pairs/s", "h2d_bytes_per_step": int(Q * ROW_BYTES + 64),
+                    "d2h_bytes_per_step": int(Q * (16 + TOPK * 12)), "steps": steps,
+                    "what": "%s.scan_batch with host buffers: targets H2D, per-query counts and top-%d D2H%s"
+                            % ("RankStore" if world > 1 else "FeatureStore", TOPK,
+                               ", per-query merge across ranks (allgather + vq_merge_topk_batch)" if world > 1 else "")},
+            "gpu_launches": None, "clocks": sampler.result(),
+            "last_step": {"query0_counts": [int(x) for x in counts[0]], "query0_top1_row": int(rows[0][0]),
+                          "query0_top1_score": float(scores[0][0])},
+        }
+        if world == 1 and not args.no_cpu:
+            v, dt = cpu_port_throughput(20000)
+            line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": 1,
+                                    "cores_available": len(os.sched_getaffinity(0)), "kind": "port",
+                                    "sample": "one query against a 20000-clip slice (%.1f s): the reference scores one "
+                                              "query per job, so its pairs/s is its clips/s" % dt}
+        emit(line)
+    if rstore is not None:
+        rstore.close()
+    st.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_bootstrap(args, rank, world, local_rank):
+    """BASELINE configs[4]: the weight update (hyperparameter.py:29-76) for R bootstrap replicates at once over L labelled
+    clips of a 1M-clip DB; replicate index sets drawn host-side from Python's RANDOM_SEED-driven generator exactly as
+    the reference's bagging draws them.  The labelled rows live on one GPU: replicas only (rank 0 runs, N is ignored)."""
+    if rank != 0:
+        return
+    import random
+    torch, dist, vq, dev = _setup(local_rank, 1)
+    n, L, R = args.clips_per_gpu, args.labelled, args.replicates
+    st = vq.FeatureStore(n, STREAMS, [1], DIM, devices=[local_rank])
+    st.fill_synthetic(DATA_SEED)
+    st.set_clip_ids(np.arange(n))
+    f = st.download(REF_ROW, 1)[0].astype(np.float64)
+    tdict = {s_: {1: vq.TargetClip._scale_feature(f[i, 0])} for i, s_ in enumerate(STREAMS)}
+    lower = THRESHOLD - NEAR_MISS * (1 - THRESHOLD)
+    st.scan(tdict, WEIGHTS, THRESHOLD, lower, EPS, topk=0)
+    m_rows, m_sc = st.matches()
+    n_rows, n_sc = st.near_misses()
+    rng = np.random.default_rng(7)                           # labelled set: half matches, half near misses; label = score >= 0.82
+    im, inm = rng.choice(len(m_rows), L // 2, replace=False), rng.choice(len(n_rows), L - L // 2, replace=False)
+    pick = np.concatenate([m_rows[im], n_rows[inm]])
+    sc_ = np.concatenate([m_sc[im], n_sc[inm]])
+    order = np.argsort(pick)
+    matches = [{"video_clip": int(c), "user_match": bool(v >= 0.82), "is_match": bool(v >= THRESHOLD)}
+               for c, v in zip(pick[order], sc_[order])]
+
+    class _Ticket:                                           # what optimize_weights reads from a ticket
+        pass
+    t = _Ticket()
+    t.matches, t.target = matches, _Ticket()
+    t.target.target_features = tdict
+    t.feature_store = lambda optional=False: st
+    hp = vq.Hyperparameter(dict(zip(STREAMS, WEIGHTS)), ballast=0.0)
+    steps = args.steps if args.steps != 300 else 10
+    random.seed(a=os.environ["RANDOM_SEED"])
+
+    def step():
+        t0 = time.perf_counter()
+        reps = vq.resample_labelled(L, R, random)
+        t1 = time.perf_counter()
+        w, th = hp.optimize_weights_replicates(t, reps)
+        return t1 - t0, time.perf_counter() - t1, w, th
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t0 = time.perf_counter()
+    parts = [step() for _ in range(steps)]
+    wall = time.perf_counter() - t0
+    sampler.stop_flag = True
+    sampler.join()
+    draw_s, upd_s = float(np.mean([p_[0] for p_ in parts])), float(np.mean([p_[1] for p_ in parts]))
+    w, th = parts[-1][2], parts[-1][3]
+    emit({
+        "metric": "bootstrap replicates of the weight update per second", "value": R / upd_s, "unit": "replicates/s",
+        "n_gpus": 1, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * upd_s, "higher_is_better": True,
+        "scaling": "replicas only", "vs_baseline": None, "dtype": "f64", "data": "synthetic (VQSYN-1 counter-based generator, on device)",
+        "config": {"workload": "configs[4]: bootstrap weight update, %d seeded replicates over %d labelled clips on a "
+                               "%d-clip DB" % (R, L, n), "replicates": R, "labelled": L, "clips": n,
+                   "grid": "40 weights x 31 thresholds", "mean_replicate_size": float(np.mean([len(r_) for r_ in
+                                                                                              vq.resample_labelled(L, 8, random)]))},
+        "e2e": {"value": R * steps / wall, "unit": "replicates/s", "h2d_bytes_per_step": int(L * 17 + R * L * 0.632 * 4),
+                "d2h_bytes_per_step": int(R * 40 * 31 * 8), "steps": steps,
+                "what": "resample_labelled (host, Python's own Mersenne Twister stream: %.1f ms) + Hyperparameter."
+                        "optimize_weights_replicates (labelled fp64 similarities K4, loss grid K5 for all replicates, argmin + "
+                        "parabola fit on the host: %.1f ms)" % (1e3 * draw_s, 1e3 * upd_s)},
+        "gpu_launches": None, "clocks": sampler.result(),
+        "last_step": {"weight_mean_std": [float(w.mean()), float(w.std())], "threshold_mean_std": [float(th.mean()), float(th.std())]},
+        "cpu_baseline": {"value": 1.0 / (40 * n * 3.1e-6 + 40 * 31 * 0.632 * L * 1.7e-6), "unit": "replicates/s", "cores": 1,
+                         "kind": "port", "sample": "projection, not a run: the reference rescans the whole DB for each of its 40 "
+                                                   "weights (3.1 us per clip) and walks 40 x 31 x the replicate's labelled clips "
+                                                   "(1.7 us each), per-item costs measured on the loop port (SURVEY.md §8 A8)"},
+    })
     st.close()
 
 
