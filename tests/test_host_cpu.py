@@ -379,3 +379,44 @@ def test_host_mailbox_allgather_between_threads_and_its_failure_modes(built_lib)
         built_lib.check(-3, "vq_hostx_allgather")
     for h in hs:
         lib.vq_hostx_destroy(h)
+
+
+def _mailbox_process(rank, world, name, slot, n_calls, q):
+    try:
+        sys.path.insert(0, ROOT)
+        from video_query_algorithms_b200 import _ffi
+        lib = _ffi.lib()
+        h = ctypes.c_void_p()
+        _ffi.check(lib.vq_hostx_create(ctypes.byref(h), name, world, rank, slot), "vq_hostx_create")
+        rng = np.random.default_rng(99)
+        bad = 0
+        for c in range(n_calls):
+            n = int(rng.integers(1, slot // 8 + 1))
+            mine = np.full(n, (c << 8) | rank, np.int64)
+            out = np.empty((world, n), np.int64)
+            _ffi.check(lib.vq_hostx_allgather(h, _ffi.ptr(mine), mine.nbytes, _ffi.ptr(out), 60.0), "vq_hostx_allgather")
+            bad += int(not all(np.all(out[r] == ((c << 8) | r)) for r in range(world)))
+            if rank == c % world and c % 97 == 0:
+                sum(range(20000))                            # one rank lags now and then: the others wait in the call
+        lib.vq_hostx_destroy(h)
+        q.put((rank, bad))
+    except Exception as e:                                   # pragma: no cover
+        q.put((rank, repr(e)))
+
+
+def test_host_mailbox_between_processes(built_lib):
+    """The same all-gather between 4 separate processes (the real arrangement: one rank process per GPU), 2000 calls of
+    changing sizes; every record of every call must be the owner's, whole (no torn or stale slot)."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    world, slot, n_calls = 4, 2048, 2000
+    name = ("/vq-testp-%d" % os.getpid()).encode()
+    q = ctx.Queue()                                          # no ordering between the ranks: an early rank waits for
+    ps = [ctx.Process(target=_mailbox_process, args=(r, world, name, slot, n_calls, q)) for r in range(world)]
+    for p_ in reversed(ps):                                  # rank 0's segment (up to 2 s) instead of failing
+        p_.start()
+    res = sorted(q.get(timeout=120) for _ in range(world))
+    for p_ in ps:
+        p_.join(timeout=30)
+    assert res == [(r, 0) for r in range(world)], res
+    assert not os.path.exists("/dev/shm" + name.decode())    # rank 0's destroy removed the name

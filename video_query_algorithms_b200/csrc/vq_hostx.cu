@@ -74,22 +74,41 @@ int vq_hostx_create(vq_hostx **out, const char *name, int world, int rank, int64
                (long long)slot_bytes);
     const int64_t slot = (slot_bytes + (int64_t)kLine - 1) / (int64_t)kLine * (int64_t)kLine;
     const size_t bytes = kLine * (1 + (size_t)world) + 2 * (size_t)world * (size_t)slot;
-    // rank 0 creates the segment (it must not exist: names are unique per job), the others open it; the caller
-    // orders the two with a barrier of its own
-    int fd = rank == 0 ? shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600) : shm_open(name, O_RDWR, 0600);
-    VQ_REQUIRE(fd >= 0, "vq_hostx_create: shm_open(%s) by rank %d: %s", name, rank, strerror(errno));
-    if (rank == 0 && ftruncate(fd, (off_t)bytes) != 0) {
-        vq::set_error("vq_hostx_create: ftruncate(%zu): %s", bytes, strerror(errno));
-        close(fd);
-        shm_unlink(name);
-        return -1;
-    }
-    struct stat sb;
-    if (fstat(fd, &sb) != 0 || (size_t)sb.st_size != bytes) {
-        vq::set_error("vq_hostx_create: segment %s has %lld bytes, expected %zu (world / slot size differ between ranks?)",
-                      name, (long long)sb.st_size, bytes);
-        close(fd);
-        return -1;
+    // rank 0 creates the segment (it must not exist: names are unique per job), the others attach to it.  Callers put
+    // a barrier between the two; a rank that is early all the same waits up to 2 s for the segment to appear, to
+    // reach its size and (below) to be initialised, instead of failing on a half-made one.
+    const double give_up = now_s() + 2.0;
+    int fd = -1;
+    if (rank == 0) {
+        fd = shm_open(name, O_CREAT | O_EXCL | O_RDWR, 0600);
+        VQ_REQUIRE(fd >= 0, "vq_hostx_create: shm_open(%s) by rank 0: %s", name, strerror(errno));
+        if (ftruncate(fd, (off_t)bytes) != 0) {
+            vq::set_error("vq_hostx_create: ftruncate(%zu): %s", bytes, strerror(errno));
+            close(fd);
+            shm_unlink(name);
+            return -1;
+        }
+    } else {
+        struct stat sb;
+        for (;;) {
+            fd = shm_open(name, O_RDWR, 0600);
+            if (fd >= 0 && fstat(fd, &sb) == 0 && sb.st_size != 0) break;
+            if (fd >= 0) close(fd);
+            if ((fd >= 0 || errno == ENOENT) && now_s() < give_up) {
+                fd = -1;
+                usleep(1000);
+                continue;
+            }
+            vq::set_error("vq_hostx_create: shm_open(%s) by rank %d: %s", name, rank,
+                          fd >= 0 ? "segment stays empty" : strerror(errno));
+            return -1;
+        }
+        if ((size_t)sb.st_size != bytes) {
+            vq::set_error("vq_hostx_create: segment %s has %lld bytes, expected %zu (world / slot size differ between "
+                          "ranks?)", name, (long long)sb.st_size, bytes);
+            close(fd);
+            return -1;
+        }
     }
     void *p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
     close(fd);
@@ -106,12 +125,15 @@ int vq_hostx_create(vq_hostx **out, const char *name, int world, int rank, int64
     if (rank == 0) {                                   // a fresh segment is zero-filled: sequence numbers start at 0
         h->world = world, h->slot_bytes = slot;
         h->magic.store(kMagic, std::memory_order_release);
-    } else if (h->magic.load(std::memory_order_acquire) != kMagic || h->world != world || h->slot_bytes != slot) {
-        vq::set_error("vq_hostx_create: segment %s was not initialised by rank 0 with world %d, slot %lld", name, world,
-                      (long long)slot);
-        munmap(p, bytes);
-        delete x;
-        return -1;
+    } else {
+        while (h->magic.load(std::memory_order_acquire) != kMagic && now_s() < give_up) usleep(1000);
+        if (h->magic.load(std::memory_order_acquire) != kMagic || h->world != world || h->slot_bytes != slot) {
+            vq::set_error("vq_hostx_create: segment %s was not initialised by rank 0 with world %d, slot %lld", name, world,
+                          (long long)slot);
+            munmap(p, bytes);
+            delete x;
+            return -1;
+        }
     }
     *out = x;
     return 0;
