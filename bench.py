@@ -281,7 +281,7 @@ def main():
 
     def e2e_step():
         if rstore is not None:
-            g_cnt, g_lists, g_top = rstore.scan(tdict, WEIGHTS, THRESHOLD, lower, EPS, topk=TOPK)
+            g_cnt, g_lists, g_top = rstore.scan(tdict, WEIGHTS, THRESHOLD, lower, EPS, topk=TOPK, copy=False)
             return st.last, int(g_cnt[0]) + int(g_cnt[1]) + int(g_cnt[2])
         res = st.scan(tdict, WEIGHTS, THRESHOLD, lower, EPS, topk=TOPK)
         k_rows, k_sc = st.topk()
@@ -301,7 +301,7 @@ def main():
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = world * n * e2e_steps / float(e2e_s.item())
     h2d = ROW_BYTES + C.sizeof(_ffi.ScanParams)
-    d2h = 40 + TOPK * 12 + (res.n_match + res.n_near + res.n_tie) * 12      # this rank's shard -> its host
+    d2h = 40 + TOPK * 12 + n_listed * 12       # N = 1: the shard's lists; N > 1: the search set's lists, on every rank
     e2e_what = ("FeatureStore.scan + topk + matches + near_misses through the C ABI: target from a "
                 "host buffer, counts / top-k / ordered lists (int64 rows + fp32 scores) published into pinned host "
                 "memory inside the call; the shard stays resident in HBM between queries (the store outlives "
@@ -312,12 +312,12 @@ def main():
     if world > 1:
         small_how = ("through the shared-memory host mailbox, vq_hostx_allgather" if rstore.mailbox is not None
                      else "NCCL collectives staged through the devices")
-        e2e_what = ("RankStore.scan on every rank (one process per GPU): the local FeatureStore.scan as above, then the "
-                    "two exchanges that give EVERY rank the search set's result — an all-gather of one summary record per "
-                    "rank (counts, top-k, tie band; %s; merged on the host) and an NCCL allgather of the ordered match / near-miss "
-                    "lists packed as (local row, score) = 8 B per entry (%d entries in all, padded to the longest rank's); "
-                    "h2d / d2h bytes are this rank's shard-to-host traffic, the collectives' staging copies come on top"
-                    % (small_how, n_listed))
+        e2e_what = ("RankStore.scan on every rank (one process per GPU): the local scan with the lists left on the device, "
+                    "then two exchanges that give EVERY rank the search set's result — one summary record per rank (counts, "
+                    "top-k, tie band; %s; merged on the host) and one NCCL allgather of the ordered match / near-miss lists "
+                    "straight from device memory (int64 global rows + fp32 scores, %d entries in all, padded to the longest "
+                    "rank's), concatenated on the device and copied once into pinned host memory (views, like N = 1); "
+                    "h2d / d2h bytes are per rank" % (small_how, n_listed))
         sel_what = ("RankStore.scan_select + gather_many on every rank: lists stay on each rank's device; two exchanges (%s) — "
                     "one summary record per rank (counts, top-k, tie band, best near miss) and 16 B per position to fetch "
                     "the 19 sampled entries from the ranks that own them" % small_how)

@@ -124,6 +124,10 @@ typedef struct vq_scan_device_view {
     const int64_t *topk_rows_dev;   /* [VQ_MAX_TOPK] GLOBAL rows, -1 padded                   */
     const uint32_t *match_rows_dev; /* [n_match] LOCAL rows ascending                         */
     const uint32_t *near_rows_dev;  /* [n_near]                                               */
+    const float *match_scores_dev;  /* [n_match] scores of the listed rows, same order        */
+    const float *near_scores_dev;   /* [n_near]                                               */
+    const uint32_t *tie_rows_dev;   /* [n_tie]                                                */
+    const float *tie_scores_dev;    /* [n_tie]                                                */
 } vq_scan_device_view;
 int vq_scan_view(vq_store *s, vq_scan_device_view *out);
 

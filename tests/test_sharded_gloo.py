@@ -134,13 +134,18 @@ def _rank_collectives(rank, world, port, n_total, k, nq, out_dir):
     tiny = sharded.HostMailbox(dist, slot_bytes=64)          # records that do not fit the slots use `dist`
     assert not tiny.fits(rec) and sharded.exchange_summary(rec, k, dist, torch, mailbox=tiny).near_best == sm.near_best
     tiny.close()
-    mine = [(first + m, score0[m]), (first + nm, score0[nm]), (first + ties, score0[ties])]
-    (g_rows, g_sc), (n_rows, n_sc), (tie_rows, tie_sc) = sharded.gather_lists_packed(mine, [0, 1, 2], sm, dist, torch)
+    def dev(idx):                                            # what a scan leaves on the device: int32 LOCAL rows, fp32 scores
+        return torch.from_numpy(idx.astype(np.int32)), torch.from_numpy(score0[idx])
+
+    mine = [dev(m), dev(nm), dev(ties)]
+    (g_rows, g_sc), (n_rows, n_sc), (tie_rows, tie_sc) = sharded.gather_lists_torch(mine, [0, 1, 2], sm, dist, torch)
+    views = sharded.gather_lists_torch(mine[:2], [0, 1], sm, dist, torch, copy=False)
+    assert np.array_equal(views[0][0], g_rows) and np.array_equal(views[1][1], n_sc)
     # a short tie band rides in the summary record itself; k = 0 and no near miss at all
     rec2 = sharded.summary_record(first, [0, 0, 2], [], [], 0, None, (first + ties[:2], score0[ties[:2]]))
     sm2 = sharded.exchange_summary(rec2, 0, dist, torch)
     assert sm2.near_best is None and len(sm2.topk[0]) == 0 and list(sm2.total) == [0, 0, 2 * world]
-    assert sharded.gather_lists_packed([((), ())], [0], sm2, dist, torch)[0][0].shape == (0,)
+    assert sharded.gather_lists_torch([dev(np.empty(0, np.int64))], [0], sm2, dist, torch)[0][0].shape == (0,)
     # sampled positions of two lists with one collective: last, first, first of rank 1, repeats
     n_near = sm.counts[:, 1]
     pos = np.array([int(n_near.sum()) - 1, 0, int(n_near[0]), 3, 3], np.int64)

@@ -30,7 +30,9 @@ class ScanCounts(C.Structure):
 class ScanDeviceView(C.Structure):
     _fields_ = [("scores_dev", C.c_void_p), ("sims_dev", C.c_void_p), ("counts_dev", C.c_void_p),
                 ("topk_scores_dev", C.c_void_p), ("topk_rows_dev", C.c_void_p),
-                ("match_rows_dev", C.c_void_p), ("near_rows_dev", C.c_void_p)]
+                ("match_rows_dev", C.c_void_p), ("near_rows_dev", C.c_void_p),
+                ("match_scores_dev", C.c_void_p), ("near_scores_dev", C.c_void_p),
+                ("tie_rows_dev", C.c_void_p), ("tie_scores_dev", C.c_void_p)]
 
 
 _P = C.POINTER

@@ -1036,6 +1036,10 @@ extern "C" int vq_scan_view(vq_store *s, vq_scan_device_view *out) {
     out->topk_rows_dev = s->topk_rows;
     out->match_rows_dev = s->list_rows[0];
     out->near_rows_dev = s->list_rows[1];
+    out->match_scores_dev = s->list_scores[0];
+    out->near_scores_dev = s->list_scores[1];
+    out->tie_rows_dev = s->list_rows[2];
+    out->tie_scores_dev = s->list_scores[2];
     return 0;
 }
 

@@ -52,8 +52,8 @@ def merge_payloads_host(gathered, world, k):
 class _DevArray:
     """Zero-copy __cuda_array_interface__ view of library-owned device memory."""
 
-    def __init__(self, ptr_value, n_int64):
-        self.__cuda_array_interface__ = {"shape": (n_int64,), "typestr": "<i8", "data": (ptr_value, False), "version": 3}
+    def __init__(self, ptr_value, n, typestr="<i8"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr_value, False), "version": 3}
 
 
 class RankScan:
@@ -234,32 +234,6 @@ class HostMailbox:
             pass
 
 
-_STAGE = {}
-
-
-def _staged_all_gather_i32(buf, dist, torch, device):
-    """all_gather of a large int32 buffer through pinned staging tensors kept per device (pageable copies run at a
-    fraction of the PCIe rate and a 100M-clip job gathers tens of MB per query).  Returns a [world, n] int32 view of
-    the pinned result, valid until the next call on this device: the caller copies what it keeps."""
-    if device is None:
-        return all_gather_np(buf, dist, torch, None)
-    world, n = dist.get_world_size(), buf.size
-    st = _STAGE.get(str(device))
-    if st is None or st[0] < n:
-        cap = max(1 << 16, 1 << int(n - 1).bit_length())
-        st = (cap, torch.empty(cap, dtype=torch.int32, pin_memory=True),
-              torch.empty(world * cap, dtype=torch.int32, pin_memory=True),
-              torch.empty(cap, dtype=torch.int32, device=device), torch.empty(world * cap, dtype=torch.int32, device=device))
-        _STAGE[str(device)] = st
-    _, h_in, h_out, d_in, d_out = st
-    h_in.numpy()[:n] = buf
-    d_in[:n].copy_(h_in[:n], non_blocking=True)
-    dist.all_gather_into_tensor(d_out[:world * n], d_in[:n])
-    h_out[:world * n].copy_(d_out[:world * n], non_blocking=True)
-    torch.cuda.current_stream(device).synchronize()
-    return h_out.numpy()[:world * n].reshape(world, n)
-
-
 def gather_batch(counts, topk_rows, topk_scores, dist, torch, device=None):
     """Per-rank results of the batched path (counts [Q, 2], top-k global rows / scores [Q, k]) -> the search
     set's: counts summed, per-query top-k merged with the ranking rule (vq_merge_topk_batch).  One allgather of
@@ -358,39 +332,67 @@ def exchange_summary(rec, k, dist, torch, device=None, mailbox=None):
     return RankSummary(g[:, 0].copy(), counts, (t_rows, t_scores), best, ties)
 
 
-def gather_lists_packed(lists, which, summary, dist, torch, device=None):
-    """Several ordered lists of this rank -> the search set's, with ONE all_gather: the lists (columns `which` of the
-    summary's counts) go back to back into one buffer of two planes — int64 global rows, then fp32 scores, 12 bytes
-    per entry — padded to the longest rank's total.  Planes, not pairs, and no re-basing of the rows: every copy on
-    either side is a plain contiguous memcpy (numpy's casting loops run at ~1.5 ns per entry, slower than the wire)."""
-    rank = dist.get_rank()
+_HOST_OUT = {}
+
+
+def _host_out(torch, device, n):
+    """(int64 [>= n], fp32 [>= n]) host tensors the gathered lists land in — pinned for a CUDA device, kept per device
+    and grown geometrically (pinned allocations cost milliseconds)."""
+    key = str(device)
+    have = _HOST_OUT.get(key)
+    if have is None or have[0].numel() < n:
+        cap = max(1 << 16, 1 << int(max(n, 1) - 1).bit_length())
+        pin = device.type == "cuda"
+        have = (torch.empty(cap, dtype=torch.int64, pin_memory=pin), torch.empty(cap, dtype=torch.float32, pin_memory=pin))
+        _HOST_OUT[key] = have
+    return have
+
+
+def gather_lists_torch(lists, which, summary, dist, torch, copy=True):
+    """Several ordered lists of this rank -> the search set's, with ONE all_gather and no host staging on the way in:
+    `lists` = [(rows, scores)] as torch tensors on the rank's device — int32 LOCAL rows and fp32 scores, exactly what
+    the scan left in HBM — for the columns `which` of the summary's counts.  On the device: rows become int64 global
+    rows, the lists go back to back into one buffer of two planes (12 bytes per entry, padded to the longest rank's
+    total), one all_gather (NVLink), then each list's segments are concatenated in rank order = database order, which
+    the reference's seeded sampling walks (ticket.py:326-341).  One device-to-host copy per list into pinned memory, one
+    stream synchronisation.  copy=False returns views of that pinned memory, valid until the next call."""
+    rank, world = dist.get_rank(), dist.get_world_size()
     counts = summary.counts[:, which]
     cap = int(counts.sum(axis=1).max(initial=0))
+    cap += cap & 1                                            # int64 views of the gathered rows need even offsets
     if cap == 0:
         return [(np.empty(0, np.int64), np.empty(0, np.float32)) for _ in which]
-    buf = np.zeros(3 * cap, np.int32)                         # collectives carry int32 on every backend
-    b_rows, b_scores = buf[:2 * cap].view(np.int64), buf[2 * cap:].view(np.float32)
+    dev = lists[0][0].device
+    buf = torch.zeros(3 * cap, dtype=torch.int32, device=dev)
+    b_rows, b_scores = buf[:2 * cap].view(torch.int64), buf[2 * cap:].view(torch.float32)
     o = 0
     for (rows, scores), n in zip(lists, counts[rank]):
-        assert len(rows) == n
-        b_rows[o:o + n] = rows
-        b_scores[o:o + n] = scores
+        n = int(n)
+        if n:
+            b_rows[o:o + n] = rows[:n].to(torch.int64) + int(summary.first_rows[rank])
+            b_scores[o:o + n] = scores[:n]
         o += n
-    g = _staged_all_gather_i32(buf, dist, torch, device)
-    out = []
-    starts = np.concatenate([np.zeros((len(counts), 1), np.int64), np.cumsum(counts, axis=1)], axis=1)
+    out = torch.empty(world * 3 * cap, dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(out, buf)
+    g = out.view(world, 3 * cap)
+    starts = np.concatenate([np.zeros((world, 1), np.int64), np.cumsum(counts, axis=1)], axis=1)
+    h_rows, h_scores = _host_out(torch, dev, int(counts.sum()))
+    spans, o = [], 0
     for j in range(len(which)):
-        n_j = counts[:, j]
-        rows = np.empty(int(n_j.sum()), np.int64)
-        scores = np.empty(len(rows), np.float32)
-        o = 0
-        for r in range(len(counts)):
-            a, n = int(starts[r, j]), int(n_j[r])
-            rows[o:o + n] = g[r, :2 * cap].view(np.int64)[a:a + n]
-            scores[o:o + n] = g[r, 2 * cap:].view(np.float32)[a:a + n]
-            o += n
-        out.append((rows, scores))
-    return out
+        n_j = int(counts[:, j].sum())
+        if n_j:
+            seg = [(int(starts[r, j]), int(counts[r, j])) for r in range(world)]
+            h_rows[o:o + n_j].copy_(torch.cat([g[r, :2 * cap].view(torch.int64)[a:a + n] for r, (a, n) in enumerate(seg)]),
+                                    non_blocking=True)
+            h_scores[o:o + n_j].copy_(torch.cat([g[r, 2 * cap:].view(torch.float32)[a:a + n] for r, (a, n) in enumerate(seg)]),
+                                      non_blocking=True)
+        spans.append((o, n_j))
+        o += n_j
+    if dev.type == "cuda":
+        torch.cuda.current_stream(dev).synchronize()
+    np_rows, np_scores = h_rows.numpy(), h_scores.numpy()
+    res = [(np_rows[a:a + n], np_scores[a:a + n]) for a, n in spans]
+    return [(r.copy(), s_.copy()) for r, s_ in res] if copy else res
 
 
 def gather_positions_multi(requests, summary, local_gather, dist, torch, device=None, mailbox=None):
@@ -456,17 +458,32 @@ class RankStore:
         self.summary = exchange_summary(rec, k, self.dist, self.torch, self.device, self.mailbox)
         return ties
 
-    def scan(self, target_features, weights, threshold, lower_limit, eps, topk=0):
-        """Full single-query result with host buffers: counts [match, near, tie], ordered global match /
-        near-miss / tie lists and the merged top-k."""
-        res = self.store.scan(target_features, weights, threshold, lower_limit, eps, topk=topk)
-        ties = self._summarise(res, int(topk))
+    def _device_lists(self, columns):
+        """The last scan's ordered lists as torch views of the library's device memory (no copy)."""
+        torch, out = self.torch, []
+        dl = self.store.device_lists()
+        for c in columns:
+            rows_p, scores_p, n = dl[c]
+            if n == 0:
+                out.append((torch.empty(0, dtype=torch.int32, device=self.device),
+                            torch.empty(0, dtype=torch.float32, device=self.device)))
+            else:
+                out.append((torch.as_tensor(_DevArray(rows_p, n, "<i4"), device=self.device),
+                            torch.as_tensor(_DevArray(scores_p, n, "<f4"), device=self.device)))
+        return out
+
+    def scan(self, target_features, weights, threshold, lower_limit, eps, topk=0, copy=True):
+        """Full single-query result: counts [match, near, tie], ordered global match / near-miss / tie lists and the
+        merged top-k on every rank.  The match and near-miss lists never touch this rank's host on the way out: they are
+        gathered device to device and land once, whole, in pinned memory (copy=False: views of it, valid until the next
+        call, like FeatureStore.matches(copy=False))."""
+        res = self.store.scan(target_features, weights, threshold, lower_limit, eps, topk=topk, lists=False)
+        self._summarise(res, int(topk))
         sm = self.summary
-        mine = [self.store.matches(copy=False), self.store.near_misses(copy=False)]
+        which = [0, 1] if sm.ties is not None else [0, 1, 2]
+        lists = gather_lists_torch(self._device_lists(which), which, sm, self.dist, self.torch, copy=copy)
         if sm.ties is not None:
-            lists = gather_lists_packed(mine, [0, 1], sm, self.dist, self.torch, self.device) + [sm.ties]
-        else:
-            lists = gather_lists_packed(mine + [ties], [0, 1, 2], sm, self.dist, self.torch, self.device)
+            lists.append(sm.ties)
         return sm.total, lists, sm.topk
 
     def scan_select(self, target_features, weights, threshold, lower_limit, eps, topk=0):
@@ -476,10 +493,10 @@ class RankStore:
         (position in the search set's near-miss list, global row, score) or None); fetch sampled list entries with
         gather() / gather_many()."""
         res = self.store.scan(target_features, weights, threshold, lower_limit, eps, topk=topk, lists=False)
-        ties = self._summarise(res, int(topk), self.store.near_best())
+        self._summarise(res, int(topk), self.store.near_best())
         sm = self.summary
         tie_list = sm.ties if sm.ties is not None else \
-            gather_lists_packed([ties], [2], sm, self.dist, self.torch, self.device)[0]
+            gather_lists_torch(self._device_lists([2]), [2], sm, self.dist, self.torch)[0]
         return sm.total, sm.topk, tie_list, sm.near_best
 
     def gather_many(self, requests):

@@ -401,6 +401,18 @@ class FeatureStore:
             raise errs[0]
         return counts
 
+    def device_lists(self):
+        """Device addresses of the last scan's ordered lists on a single-shard store: [(rows pointer (uint32 LOCAL rows),
+        scores pointer (fp32), entries)] for matches, near misses, tie band — for consumers that move the lists between
+        devices without a host round trip (sharded.RankStore).  Valid until the next scan on this store."""
+        if len(self.shards) != 1:
+            raise VQError("device_lists: single-shard stores only (one store per rank)")
+        v = _ffi.ScanDeviceView()
+        check(lib().vq_scan_view(self.shards[0].handle, C.byref(v)), "vq_scan_view")
+        c = self._last_counts[0]
+        return [(v.match_rows_dev, v.match_scores_dev, c.n_match), (v.near_rows_dev, v.near_scores_dev, c.n_near),
+                (v.tie_rows_dev, v.tie_scores_dev, c.n_tie)]
+
     def _host_view(self, shard, which):
         """Read-only numpy views of the library's pinned host mirror (valid until the next scan)."""
         rp, sp, n = C.c_void_p(), C.c_void_p(), C.c_int64()
