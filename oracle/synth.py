@@ -1,7 +1,7 @@
 """VQSYN-1: counter-based synthetic feature database (CPU side).
 
 TEST INFRASTRUCTURE.  Only tests/, __graft_entry__.smoke() and bench.py may import this
-package.  The CUDA generator (`csrc/synth.cu`, `vq_synth_fill`) implements the same
+package.  The CUDA generator (`csrc/vq_store.cu`, `vq_store_fill_synthetic`) implements the same
 function; any row can be regenerated here bit-identically, which is how shards of a
 100M-clip database are spot-checked without ever holding it on the host.
 
