@@ -172,7 +172,12 @@ class Recorder:
         H.optimize_weights, C.get_target_features = optimize_weights, get_target_features
 
 
+ONLY = os.environ.get("VQ_GOLDEN_ONLY")     # e.g. F_shrp2_bagging_mu: write just that scenario, leave the other files alone
+
+
 def save_scenario(name, rounds, meta):
+    if ONLY and name != ONLY:
+        return
     if os.environ.get("VQ_GOLDEN_TIMING_ONLY"):
         print("timings after", name, json.dumps(TIMINGS[-len(rounds):]))
         return
@@ -246,10 +251,11 @@ def main():
         fx[key] = (os.path.basename(rel), nums, arrays)
         streams = ("rgb", "warped_optical_flow")
         splits = sorted(arrays["rgb"])
-        np.savez_compressed(os.path.join(HERE, "fixture_%s.npz" % key),
-                            clip_numbers=np.array(nums, np.int64), splits=np.array(splits, np.int64),
-                            X=np.array([[[arrays[s][p][i] for p in splits] for s in streams]
-                                        for i in range(len(nums))]))
+        if not ONLY:
+            np.savez_compressed(os.path.join(HERE, "fixture_%s.npz" % key),
+                                clip_numbers=np.array(nums, np.int64), splits=np.array(splits, np.int64),
+                                X=np.array([[[arrays[s][p][i] for p in splits] for s in streams]
+                                            for i in range(len(nums))]))
 
     streams = ("rgb", "warped_optical_flow")
     broker_defaults = dict(default_weights={"rgb": 1.0, "warped_optical_flow": 1.5},
@@ -331,11 +337,12 @@ def main():
     tc.get_target_features()
     tgt = np.array([[np.asarray(tc.target_features[s][p], np.float64) for p in sorted(tc.target_features[s])]
                     for s in streams])
-    np.savez_compressed(os.path.join(HERE, "scn_E_partial_update.npz"), target=tgt,
+    if not ONLY:
+      np.savez_compressed(os.path.join(HERE, "scn_E_partial_update.npz"), target=tgt,
                         previous=np.array([[job["latest_query_result"]["bootstrapped_target"][s][p]
                                             for p in sorted(job["latest_query_result"]["bootstrapped_target"][s])]
                                            for s in streams]))
-    with open(os.path.join(HERE, "scn_E_partial_update.json"), "w") as f:
+      with open(os.path.join(HERE, "scn_E_partial_update.json"), "w") as f:
         json.dump({"hp": _js(hpE), "fixture": ["shrp2"], "seed": RANDOM_SEED,
                    "matches": [{"video_clip": m["video_clip"], "user_match": m["user_match"]}
                                for m in api.matches.values()
@@ -363,6 +370,25 @@ def main():
                    "hp": _js(broker_defaults), "streams": streams, "label_rule": "score>=0.85",
                    "max_matches": 20, "dynamic_target_adjustment": False, "seed": RANDOM_SEED,
                    "eps": COMPUTE_EPS, "final_report": None})
+
+    # ---- F: shrp2, bagging x4 on valid + invalid labels with mu > 0 (the `_bootstrap_valid_plus_invalid` solve inside
+    #         `target_by_bagging`, target_clip.py:145-159,201-261), f_bootstrap 0.8, ballast 0.2, a narrow near-miss band,
+    #         four rounds with two label rules
+    api = FakeAPI(page_size=11); holder["api"] = api
+    v2, c2 = api.load_feature_arrays(n2, nums2, arr2)
+    ss = api.add_search_set("shrp2F", list(c2.values()))
+    qid = api.add_query("qF", v2, c2[nums2[70]], ss, max_matches=24, dynamic_target_adjustment=True)
+    hpF = dict(broker_defaults, bootstrap_type="bagging", nbags=4, mu=0.25, f_bootstrap=0.8, ballast=0.2,
+               near_miss_default=0.2, default_threshold=0.75)
+    rec.rounds = []
+    ruleF = lambda m: bool(m["score"] >= 0.85)
+    run_rounds(api, APIRepository, hpF,
+               [("new", None), ("revise", ruleF), ("revise", ruleF), ("finalize", ruleF)], rec, qid)
+    save_scenario("F_shrp2_bagging_mu", rec.rounds,
+                  {"fixture": ["shrp2"], "ref_clip_number": int(nums2[70]), "hp": _js(hpF), "streams": streams,
+                   "page_size": 11, "label_rule": "score>=0.85", "max_matches": 24,
+                   "dynamic_target_adjustment": True, "seed": RANDOM_SEED, "eps": COMPUTE_EPS,
+                   "final_report": api.uploaded_reports[-1] if api.uploaded_reports else None})
     print("golden written to", HERE)
 
 

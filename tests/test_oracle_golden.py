@@ -15,7 +15,7 @@ from oracle import bootstrap as ob
 from oracle import loop_port
 from oracle import scoring as sc
 from oracle import synth
-from scenarios import GOLDEN, SCENARIOS, Scenario, rng_digest
+from scenarios import GOLDEN, ORACLE_ONLY_SCENARIOS, SCENARIOS, Scenario, rng_digest
 
 
 def replay_round(scn, i, check):
@@ -84,7 +84,7 @@ def _check(name, got, want, rtol):
     assert err <= rtol, "%s: max rel err %.3e" % (name, err)
 
 
-@pytest.mark.parametrize("name", SCENARIOS)
+@pytest.mark.parametrize("name", SCENARIOS + ORACLE_ONLY_SCENARIOS)
 def test_oracle_replays_reference_rounds(name):
     scn = Scenario(name)
     for i in range(len(scn.rounds)):
