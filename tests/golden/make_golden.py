@@ -389,6 +389,23 @@ def main():
                    "page_size": 11, "label_rule": "score>=0.85", "max_matches": 24,
                    "dynamic_target_adjustment": True, "seed": RANDOM_SEED, "eps": COMPUTE_EPS,
                    "final_report": api.uploaded_reports[-1] if api.uploaded_reports else None})
+
+    # ---- G: brooklyn, the user rejects every clip shown (all labels False): no valid match -> the target stays the
+    #         reference clip although dynamic adjustment is on (ticket.py:98-107), optimize_weights sees only negatives,
+    #         finalize finds no user match at all (lowest_scoring_user_match keeps its initial 1, ticket.py:301-309)
+    api = FakeAPI(); holder["api"] = api
+    name, nums, arrays = fx["brooklyn"]
+    vid, cids = api.load_feature_arrays(name, nums, arrays)
+    ss = api.add_search_set("brooklynG", list(cids.values()))
+    qid = api.add_query("qG", vid, cids[nums[33]], ss, max_matches=10, dynamic_target_adjustment=True)
+    rec.rounds = []
+    ruleG = lambda m: False
+    run_rounds(api, APIRepository, broker_defaults,
+               [("new", None), ("revise", ruleG), ("finalize", ruleG)], rec, qid)
+    save_scenario("G_brooklyn_all_rejected", rec.rounds,
+                  {"fixture": ["brooklyn"], "ref_clip_number": int(nums[33]), "hp": _js(broker_defaults), "streams": streams,
+                   "label_rule": "False", "max_matches": 10, "dynamic_target_adjustment": True, "seed": RANDOM_SEED,
+                   "eps": COMPUTE_EPS, "final_report": api.uploaded_reports[-1] if api.uploaded_reports else None})
     print("golden written to", HERE)
 
 

@@ -11,7 +11,7 @@ import pytest
 
 from oracle import bootstrap as ob
 from oracle import scoring as sc
-from scenarios import SCENARIOS, Scenario
+from scenarios import ORACLE_ONLY_SCENARIOS, SCENARIOS, Scenario
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -93,7 +93,7 @@ def test_quad_fit_and_optimum_equal_oracle_on_golden_losses():
     from video_query_algorithms_b200 import Hyperparameter
     hp = Hyperparameter({"rgb": 1.0, "warped_optical_flow": 1.5})
     n = 0
-    for name in SCENARIOS:
+    for name in SCENARIOS + ORACLE_ONLY_SCENARIOS:           # incl. a grid-border optimum (G: every label False)
         scn = Scenario(name)
         for i, r in enumerate(scn.rounds):
             key = "r%d_losses" % i
@@ -104,7 +104,7 @@ def test_quad_fit_and_optimum_equal_oracle_on_golden_losses():
             assert [1.0, w] == pytest.approx(r["weights"], rel=1e-12)
             assert th - scn.eps == pytest.approx(r["threshold"], rel=1e-12)
             n += 1
-    assert n >= 7
+    assert n >= 12
     rng = np.random.default_rng(3)
     for _ in range(200):
         x = [sorted(rng.random(3) + 0.5), sorted(rng.random(3) + 0.5)]
@@ -420,3 +420,93 @@ def test_host_mailbox_between_processes(built_lib):
         p_.join(timeout=30)
     assert res == [(r, 0) for r in range(world)], res
     assert not os.path.exists("/dev/shm" + name.decode())    # rank 0's destroy removed the name
+
+
+# ---------------------------------------------------------------------------- Ticket.select_clips_to_review (host logic)
+class _ArrayStore:
+    """Test double for FeatureStore's result interface, serving a recorded score array: what the scan kernels would
+    return for these scores (ordered lists, tie band, best near miss).  It lets the product's selection logic — sampling
+    order, RNG consumption, forced clips — run against the reference's recorded rounds without a GPU."""
+
+    def __init__(self, clip_ids, scores):
+        from video_query_algorithms_b200.store import ScanResult
+        self._result = ScanResult
+        self.clip_ids, self.first_global_row = np.asarray(clip_ids, np.int64), 0
+        self.n_rows, self.streams = len(clip_ids), ("rgb", "warped_optical_flow")
+        self._s = np.asarray(scores, np.float64)
+        self._row = {int(c): i for i, c in enumerate(clip_ids)}
+
+    def has_clip(self, c):
+        return c is not None and int(c) in self._row
+
+    def row_of(self, c):
+        return self._row[int(c)]
+
+    def scan(self, target, weights, threshold, lower_limit, eps, topk=0, want_sims=False, lists=True):
+        s = self._s
+        self._l = {"matches": np.flatnonzero(s >= threshold), "near_misses": np.flatnonzero((s >= lower_limit) & (s < threshold)),
+                   "ties": np.flatnonzero((np.abs(s - threshold) < eps) | (np.abs(s - lower_limit) < eps))}
+        self.lists = lists
+        return self._result(len(self._l["matches"]), len(self._l["near_misses"]), len(self._l["ties"]), 0, 0.0)
+
+    def _list(self, which, need_lists):
+        assert self.lists or not need_lists, "whole lists read after a lists=False scan"
+        return self._l[which].astype(np.int64), self._s[self._l[which]]
+
+    def matches(self, copy=True):
+        return self._list("matches", True)
+
+    def near_misses(self, copy=True):
+        return self._list("near_misses", True)
+
+    def ties(self, copy=True):
+        return self._list("ties", False)
+
+    def gather(self, which, positions):
+        assert not self.lists, "gather is the lists=False round's call"
+        pos = np.asarray(positions, np.int64)
+        return self._l[which][pos].astype(np.int64), self._s[self._l[which][pos]]
+
+    def near_best(self):
+        n = self._l["near_misses"]
+        if not len(n):
+            return None
+        j = int(np.argmax(self._s[n]))
+        return j, int(n[j]), float(self._s[n[j]])
+
+    def topk(self):
+        return np.empty(0, np.int64), np.empty(0, np.float32)
+
+
+@pytest.mark.parametrize("name", SCENARIOS + ORACLE_ONLY_SCENARIOS)
+def test_ticket_selection_reproduces_reference_rounds_on_recorded_scores(name):
+    """Product `Ticket.select_clips_to_review` on the reference's recorded scores: same clips in the same order with
+    the same scores, and Python's generator left in the same state, for every round of every golden scenario (review
+    rounds take the lists=False + gather path, finalize rounds the whole-list path)."""
+    import types
+    from scenarios import rng_digest
+    from video_query_algorithms_b200 import Ticket
+    scn = Scenario(name)
+    hp = scn.hp()
+    for i, r in enumerate(scn.rounds):
+        random.seed(a=scn.seed)
+        prev = r.get("match_status_input")
+        if r["kind"] != "new" and prev:                      # advance the generator through the target bootstrap's draws
+            dyn = scn.meta["dynamic_target_adjustment"] and any(m["user_match"] is True for m in prev)
+            rows = lambda want: scn.X[[scn.row_of[m["video_clip"]] for m in prev if m["user_match"] is want]]
+            ob.get_target_features(scn.X[scn.row_of[r["ref_clip_id"]]], rows(True), rows(False), None, dyn, True,
+                                   hp["bootstrap_type"], hp["f_bootstrap"], hp["f_memory"], hp["nbags"], hp["mu"], random)
+        assert rng_digest() == r["rng_before_select"]
+        store = _ArrayStore(scn.clip_ids, scn.arr(i, "scores"))
+        job = {"query_id": 1, "video_id": 1, "ref_clip": 0, "ref_clip_id": r["ref_clip_id"], "search_set": 1,
+               "number_of_matches_to_review": scn.meta["max_matches"],
+               "dynamic_target_adjustment": scn.meta["dynamic_target_adjustment"], "user_matches": r["user_matches"]}
+        t = Ticket(job, "http://fake/", client=object(), schema=object(), store=store)
+        t.target = types.SimpleNamespace(target_features={})
+        t._weights = dict(zip(scn.streams, r["weights"]))
+        t._score_of = lambda clip, st=store: float(st._s[st.row_of(clip)])
+        th, mx, near = r["select_args"]
+        t.select_clips_to_review(th, mx, near)
+        assert store.lists == (mx == float("inf"))
+        assert list(t.matches.items()) == [(k, v) for k, v in r["selected"]]
+        assert rng_digest() == r["rng_after_select"]
