@@ -510,3 +510,112 @@ def test_ticket_selection_reproduces_reference_rounds_on_recorded_scores(name):
         assert store.lists == (mx == float("inf"))
         assert list(t.matches.items()) == [(k, v) for k, v in r["selected"]]
         assert rng_digest() == r["rng_after_select"]
+
+
+# ---------------------------------------------------------------------------- TargetClip (host logic)
+class _SolveStore:
+    """Test double for the store calls TargetClip makes: rows by clip id, and `bootstrap_target` answered by the
+    oracle's float64 solve (the stand-in for kernel K6), so that the product's own case analysis, resampling order,
+    bagging average and output format can be checked against the reference's recorded targets without a GPU."""
+
+    def __init__(self, scn):
+        self.scn, self.first_global_row, self.present = scn, 0, None
+        self.streams, self.splits = scn.streams, list(scn.splits)
+
+    def row_of(self, clip):
+        return self.scn.row_of[int(clip)]
+
+    def has_clip(self, clip):
+        return clip is not None and int(clip) in self.scn.row_of
+
+    def bootstrap_target(self, valid_rows, invalid_rows, mu):
+        X = self.scn.X
+        out = np.empty(X.shape[1:], np.float64)
+        for s in range(X.shape[1]):
+            for p in range(X.shape[2]):
+                out[s, p] = (ob.solve_valid_invalid(X[valid_rows, s, p], X[invalid_rows, s, p], mu) if len(invalid_rows)
+                             else ob.solve_valid(X[valid_rows, s, p]))
+        return out
+
+
+class _TargetClient:
+    """The two API actions TargetClip uses: the labelled matches of the previous round, paged, and the reference
+    clip's feature rows in the `video-clips/features` record layout."""
+
+    def __init__(self, scn, prev_matches, page_size=7):
+        self.scn, self.prev, self.page_size = scn, prev_matches or [], page_size
+
+    def action(self, schema, keys, params=None, **kw):
+        if keys == ["matches", "list"]:
+            a = (params["page"] - 1) * self.page_size
+            more = a + self.page_size < len(self.prev)
+            return {"results": self.prev[a:a + self.page_size], "pagination": {"nextPage": params["page"] + 1 if more else None}}
+        assert keys == ["video-clips", "features"]
+        row = self.scn.X[self.scn.row_of[params["id"]]]
+        return [{"dnn_stream_id": s, "dnn_stream_split": p, "name": "global_pool", "feature_vector": row[si, pi].tolist(),
+                 "video_clip_id": params["id"]} for si, s in enumerate(self.scn.streams) for pi, p in enumerate(self.scn.splits)]
+
+
+@pytest.mark.parametrize("name", SCENARIOS + ORACLE_ONLY_SCENARIOS)
+def test_target_clip_reproduces_reference_targets(name):
+    """Product `TargetClip.get_target_features` for every recorded round: the reference's target vectors (1e-9; the
+    solve itself is the oracle's here) and Python's generator in the reference's state afterwards."""
+    import types
+    from scenarios import rng_digest
+    from video_query_algorithms_b200 import Hyperparameter, TargetClip
+    scn = Scenario(name)
+    kw = scn.hp()
+    for i, r in enumerate(scn.rounds):
+        prev = r.get("match_status_input")
+        store = _SolveStore(scn)
+        dyn = scn.meta["dynamic_target_adjustment"]
+        if r["kind"] != "new" and dyn and prev is not None and not any(m["user_match"] is True for m in prev):
+            dyn = False                                      # what Ticket.catch_errors does (ticket.py:98-107)
+        ticket = types.SimpleNamespace(
+            client=_TargetClient(scn, prev), schema=None, dynamic_target_adjustment=dyn, ref_clip_id=r["ref_clip_id"],
+            latest_query_result=None if r["kind"] == "new" else {"id": 1, "round": i, "bootstrapped_target": None},
+            features_from_store=False, attach_store=lambda hp: store, feature_store=lambda optional=False: store)
+        random.seed(a=scn.seed)
+        tc = TargetClip(ticket, Hyperparameter(**kw))
+        tc.get_target_features()
+        got = np.array([[tc.target_features[s][p] for p in r["splits"]] for s in scn.streams])
+        want = scn.arr(i, "target")
+        assert got.shape == want.shape and np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-300)) < 1e-9
+        assert rng_digest() == r["rng_after_target"]
+        assert isinstance(tc.target_features[scn.streams[0]][r["splits"][0]], list)      # JSON-serialisable (ticket.py:296)
+        json_ok = __import__("json").dumps(tc.target_features)
+        assert json_ok
+
+
+@pytest.mark.parametrize("name", SCENARIOS + ORACLE_ONLY_SCENARIOS)
+def test_optimize_weights_reproduces_reference_on_recorded_similarities(name, monkeypatch):
+    """Product `Hyperparameter.optimize_weights` for every recorded revise / finalize round, with the two device calls
+    answered on the CPU (labelled similarities from the recording, loss grid by the oracle): label extraction and its
+    order, grid handling, optimum and threshold buffer must give the reference's weights and threshold."""
+    import types
+    from video_query_algorithms_b200 import Hyperparameter
+    from video_query_algorithms_b200 import store as product_store
+    scn = Scenario(name)
+    n = 0
+    for i, r in enumerate(scn.rounds):
+        prev = r.get("match_status_input")
+        if not prev or "r%d_losses" % i not in scn.arrays.files:
+            continue
+        sims_all = scn.arr(i, "sims")
+
+        def loss_grid(sims, labels, wg, tg, ballast, replicates=None, device=0):
+            return sc.loss_grid(sims, np.asarray(labels, bool), wg, tg, ballast)[None]
+
+        monkeypatch.setattr(product_store, "loss_grid", loss_grid)
+        fs = types.SimpleNamespace(shards=[types.SimpleNamespace(device=0)],
+                                   rows_of=lambda clips: np.array([scn.row_of[int(c)] for c in clips]),
+                                   labelled_sims=lambda target, rows: sims_all[rows])
+        ticket = types.SimpleNamespace(matches=prev, target=types.SimpleNamespace(target_features={}),
+                                       feature_store=lambda optional=False: fs)
+        hp = Hyperparameter(**scn.hp())
+        hp.optimize_weights(ticket)
+        assert [hp.weights[s] for s in scn.streams] == pytest.approx(r["weights"], rel=1e-10)
+        assert hp.threshold == pytest.approx(r["threshold"], rel=1e-10)
+        assert np.max(np.abs(hp.losses - scn.arr(i, "losses"))) < 1e-12
+        n += 1
+    assert n >= 1 or name == "never"
