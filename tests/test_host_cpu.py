@@ -619,3 +619,65 @@ def test_optimize_weights_reproduces_reference_on_recorded_similarities(name, mo
         assert np.max(np.abs(hp.losses - scn.arr(i, "losses"))) < 1e-12
         n += 1
     assert n >= 1 or name == "never"
+
+
+# ---------------------------------------------------------------------------- feature records -> store rows (A2)
+def _records(rng, n_clips, splits, dim, streams=("rgb", "warped_optical_flow")):
+    """A `search-sets/features`-style response with everything the filters and the dict semantics must cope with:
+    shuffled records, duplicates of a (clip, stream, split) slot, clips lacking splits, foreign streams and names."""
+    recs = []
+    for c in range(100, 100 + n_clips):
+        for s in streams + ("audio",):
+            for p in splits:
+                if rng.random() < 0.15 and not (s == streams[0] and p == splits[0]):
+                    continue                                                   # this clip lacks this slot
+                for _ in range(2 if rng.random() < 0.1 else 1):                # a duplicate record: the later one wins
+                    recs.append({"dnn_stream_id": s, "dnn_stream_split": p, "name": "global_pool" if rng.random() < 0.9 else "fc",
+                                 "feature_vector": rng.random(dim).tolist(), "video_clip_id": c})
+    order = rng.permutation(len(recs))
+    return [recs[i] for i in order]
+
+
+def test_pack_feature_rows_follows_the_reference_dict_semantics():
+    """store.pack_feature_rows against (a) a direct restatement of the reference's nested-dict build (ticket.py:367-381)
+    and, when the reference tree is present, (b) the reference's own `Ticket._get_candidate_features`."""
+    from video_query_algorithms_b200.store import pack_feature_rows
+    streams, rng = ("rgb", "warped_optical_flow"), np.random.default_rng(11)
+    ref_ticket = None
+    if os.path.isdir("/root/reference/src"):
+        import test_flow_cpu
+        test_flow_cpu.load_reference_driver()                                 # puts the reference on sys.path (stub coreapi)
+        import models.ticket as rticket
+        ref_ticket = object.__new__(rticket.Ticket)
+        ref_ticket.search_set = 1
+    for trial in range(6):
+        splits = [1, 2, 3] if trial % 2 else [1]
+        recs = _records(rng, 40, splits, 16)
+        order, got_splits, X, present = pack_feature_rows(recs, streams, "global_pool")
+        want = {s: {p: {} for p in splits} for s in streams}                  # the reference's structure
+        for tf in recs:
+            if tf["dnn_stream_id"] in streams and tf["name"] == "global_pool" and tf["dnn_stream_split"] in splits:
+                want[tf["dnn_stream_id"]][tf["dnn_stream_split"]][tf["video_clip_id"]] = tf["feature_vector"]
+        if ref_ticket is not None:
+            ref_ticket._request = lambda action, params, recs=recs: recs
+            hp = type("HP", (), {"streams": streams, "feature_name": "global_pool"})()
+            assert ref_ticket._get_candidate_features(splits, hp) == want
+        first_seen = list(dict.fromkeys(tf["video_clip_id"] for tf in recs
+                                        if tf["dnn_stream_id"] in streams and tf["name"] == "global_pool"))
+        assert order == first_seen and got_splits == sorted({p for s in want for p in want[s] if want[s][p]})
+        for si, s in enumerate(streams):
+            for pi, p in enumerate(got_splits):
+                for r, c in enumerate(order):
+                    v = want[s][p].get(c)
+                    assert present[r, si, pi] == (v is not None)
+                    assert np.array_equal(X[r, si, pi], np.asarray(v, np.float32) if v is not None else np.zeros(16, np.float32))
+        # append: clips a store already holds are dropped, the rest keep their first-appearance order
+        held_ids = set(order[::3])
+        o2, s2, X2, p2 = pack_feature_rows(recs, streams, "global_pool", held=lambda ids: np.array([c in held_ids for c in ids]))
+        keep = [r for r, c in enumerate(order) if c not in held_ids]
+        assert o2 == [order[r] for r in keep]
+        at = [got_splits.index(p) for p in s2]
+        assert np.array_equal(X2, X[keep][:, :, at]) and np.array_equal(p2, present[keep][:, :, at])
+    empty = pack_feature_rows([{"dnn_stream_id": "audio", "dnn_stream_split": 1, "name": "global_pool", "feature_vector": [1.0],
+                                "video_clip_id": 5}], streams, "global_pool")
+    assert empty[0] == [] and empty[2].shape[0] == 0

@@ -70,6 +70,47 @@ def _as_doubles(v):
     return array.array("d", v) if isinstance(v, list) else v
 
 
+def pack_feature_rows(feature_rows, streams, feature_name, held=None):
+    """`search-sets/features`-style records -> the store's row layout, in one pass (host code, no device call).
+    Applies the reference's filters (ticket.py:374-381: stream in `streams`, name == `feature_name`) and its dict
+    semantics: clips in order of first appearance (= the insertion order of the reference's `scores` dict, which its
+    seeded sampling walks), a later record of the same (clip, stream, split) overwrites an earlier one, slots no record
+    fills stay zero and are marked absent.  `held(clip ids) -> bool array` drops clips a store already holds (append).
+    Returns (clip ids in row order, sorted split numbers, X float32 [n, S, P, dim], present bool [n, S, P])."""
+    s_of = {s: i for i, s in enumerate(streams)}
+    row, cells, split_set = {}, [], set()
+    for tf in feature_rows:
+        si = s_of.get(tf["dnn_stream_id"])
+        if si is None or tf["name"] != feature_name:
+            continue
+        c, p = tf["video_clip_id"], int(tf["dnn_stream_split"])
+        r = row.get(c)
+        if r is None:
+            r = row[c] = len(row)
+        split_set.add(p)
+        cells.append((r, si, p, tf["feature_vector"]))
+    order = list(row)
+    remap = None
+    if held is not None and order:
+        keep = ~np.asarray(held(order), dtype=bool)
+        remap = np.where(keep, np.cumsum(keep) - 1, -1)
+        order = [c for c, k in zip(order, keep) if k]
+        cells = [(int(remap[r]), si, p, v) for r, si, p, v in cells if remap[r] >= 0]
+        split_set = {p for _, _, p, _ in cells}
+    splits = sorted(split_set)
+    if not order:
+        return order, splits, np.zeros((0, len(streams), len(splits), 0), np.float32), np.zeros((0, len(streams), len(splits)), bool)
+    p_of = {p: i for i, p in enumerate(splits)}
+    dim = len(cells[0][3])
+    X = np.zeros((len(order), len(streams), len(splits), dim), np.float32)
+    present = np.zeros((len(order), len(streams), len(splits)), bool)
+    for r, si, p, v in cells:
+        pi = p_of[p]
+        X[r, si, pi] = _as_doubles(v)
+        present[r, si, pi] = True
+    return order, splits, X, present
+
+
 class FeatureStore:
     """A search set's features in HBM, as one shard per device."""
 
@@ -247,31 +288,19 @@ class FeatureStore:
     def append_feature_rows(self, feature_rows, feature_name):
         """Append the clips of a `search-sets/features`-style response that the store does not hold yet (same
         filters and first-appearance order as from_feature_rows); returns the number of clips added."""
-        s_of = {s: i for i, s in enumerate(self.streams)}
-        p_of = {p: i for i, p in enumerate(self.splits)}
-        order, seen = [], set()
-        for tf in feature_rows:
-            if tf["dnn_stream_id"] in s_of and tf["name"] == feature_name:
-                c = tf["video_clip_id"]
-                if c not in seen:
-                    seen.add(c)
-                    order.append(c)
-        if order:                                                   # one vectorised lookup: keep the ids the store lacks
-            held = self._lookup(order) >= 0
-            order = [c for c, h in zip(order, held) if not h]
+        order, splits, X, present = pack_feature_rows(feature_rows, self.streams, feature_name,
+                                                      held=lambda ids: self._lookup(ids) >= 0)
         if not order:
             return 0
-        row = {c: i for i, c in enumerate(order)}
-        X = np.zeros((len(order),) + self.row_shape, np.float32)
-        present = np.zeros((len(order),) + self.row_shape[:2], bool)
-        for tf in feature_rows:
-            if tf["dnn_stream_id"] in s_of and tf["name"] == feature_name and tf["video_clip_id"] in row:
-                p = int(tf["dnn_stream_split"])
-                if p not in p_of:
-                    raise VQError("append_feature_rows: split %d is not one of the store's splits %s" % (p, self.splits))
-                i, si, pi = row[tf["video_clip_id"]], s_of[tf["dnn_stream_id"]], p_of[p]
-                X[i, si, pi] = _as_doubles(tf["feature_vector"])
-                present[i, si, pi] = True
+        extra = [p for p in splits if p not in self.splits]
+        if extra:
+            raise VQError("append_feature_rows: split %d is not one of the store's splits %s" % (extra[0], self.splits))
+        if splits != self.splits:                                   # the new clips lack some split: widen to the store's slots
+            at = [self.splits.index(p) for p in splits]
+            Xw = np.zeros((len(order),) + self.row_shape, np.float32)
+            pw = np.zeros((len(order),) + self.row_shape[:2], bool)
+            Xw[:, :, at], pw[:, :, at] = X, present
+            X, present = Xw, pw
         self.append(X, clip_ids=order, present=present)
         return len(order)
 
@@ -285,33 +314,10 @@ class FeatureStore:
         """Build from the `search-sets/features` API response (list of feature dicts), applying the
         reference's filters (ticket.py:374-381: stream in streams, name == feature_name)."""
         streams = tuple(streams)
-        order, seen, splits = [], set(), set()
-        for tf in feature_rows:
-            if tf["dnn_stream_id"] in streams and tf["name"] == feature_name:
-                splits.add(int(tf["dnn_stream_split"]))
-                c = tf["video_clip_id"]
-                if c not in seen:
-                    seen.add(c)
-                    order.append(c)
-        splits = sorted(splits)
+        order, splits, X, present = pack_feature_rows(feature_rows, streams, feature_name)
         if not order:
             raise VQError("search set has no '%s' features for streams %s" % (feature_name, streams))
-        dim = None
-        for tf in feature_rows:
-            if tf["dnn_stream_id"] in streams and tf["name"] == feature_name:
-                dim = len(tf["feature_vector"])
-                break
-        row = {c: i for i, c in enumerate(order)}
-        s_of = {s: i for i, s in enumerate(streams)}
-        p_of = {p: i for i, p in enumerate(splits)}
-        X = np.zeros((len(order), len(streams), len(splits), dim), np.float32)
-        present = np.zeros((len(order), len(streams), len(splits)), bool)
-        for tf in feature_rows:
-            if tf["dnn_stream_id"] in streams and tf["name"] == feature_name:
-                i, s, p = row[tf["video_clip_id"]], s_of[tf["dnn_stream_id"]], p_of[int(tf["dnn_stream_split"])]
-                X[i, s, p] = _as_doubles(tf["feature_vector"])       # later duplicates overwrite, like the dict does
-                present[i, s, p] = True
-        st = cls(len(order), streams, splits, dim, devices=devices, clip_ids=order)
+        st = cls(len(order), streams, splits, X.shape[3], devices=devices, clip_ids=order)
         st.upload(0, X)
         st.set_present(present)
         return st
