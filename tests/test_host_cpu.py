@@ -629,7 +629,7 @@ def _records(rng, n_clips, splits, dim, streams=("rgb", "warped_optical_flow")):
     for c in range(100, 100 + n_clips):
         for s in streams + ("audio",):
             for p in splits:
-                if rng.random() < 0.15 and not (s == streams[0] and p == splits[0]):
+                if rng.random() < 0.15 and p != splits[0]:                     # (every clip keeps its first split)
                     continue                                                   # this clip lacks this slot
                 for _ in range(2 if rng.random() < 0.1 else 1):                # a duplicate record: the later one wins
                     recs.append({"dnn_stream_id": s, "dnn_stream_split": p, "name": "global_pool" if rng.random() < 0.9 else "fc",
@@ -681,3 +681,57 @@ def test_pack_feature_rows_follows_the_reference_dict_semantics():
     empty = pack_feature_rows([{"dnn_stream_id": "audio", "dnn_stream_split": 1, "name": "global_pool", "feature_vector": [1.0],
                                 "video_clip_id": 5}], streams, "global_pool")
     assert empty[0] == [] and empty[2].shape[0] == 0
+
+
+class _RecordingLib:
+    """Stands in for libvq_b200 in host-glue tests: every call succeeds and is recorded (arrays copied)."""
+
+    def __init__(self):
+        self.calls = []
+
+    def __getattr__(self, name):
+        def fn(*args):
+            if name == "vq_device_count":
+                args[0]._obj.value = 1
+            self.calls.append((name,) + tuple(a.copy() if isinstance(a, np.ndarray) else a for a in args))
+            return 0
+        return fn
+
+    def of(self, name):
+        return [c for c in self.calls if c[0] == name]
+
+
+def test_store_build_and_append_from_feature_records_issue_the_right_uploads(monkeypatch):
+    """FeatureStore.from_feature_rows / append_feature_rows end to end on the host side (library calls recorded):
+    what is uploaded, in which row order, with which split weights — the glue around pack_feature_rows."""
+    from video_query_algorithms_b200 import store as ps
+    fake = _RecordingLib()
+    monkeypatch.setattr(ps, "lib", lambda: fake)
+    monkeypatch.setattr(ps, "ptr", lambda a: a)
+    streams, rng = ("rgb", "warped_optical_flow"), np.random.default_rng(4)
+    recs = _records(rng, 30, [1, 2, 3], 8)
+    st = ps.FeatureStore.from_feature_rows(recs, streams, "global_pool", devices=[0])
+    order, splits, X, present = ps.pack_feature_rows(recs, streams, "global_pool")
+    assert list(st.clip_ids) == order and st.splits == splits and st.n_rows == len(order) and st.dim == 8
+    (create,) = fake.of("vq_store_create")
+    assert create[2:] == (0, len(order), 2, 3, 8, 0)
+    (up,) = fake.of("vq_store_upload")
+    assert up[2:4] == (0, len(order)) and np.array_equal(up[4], X.reshape(len(order), -1))
+    (sw,) = fake.of("vq_store_set_split_weights")
+    assert np.allclose(sw[2], 1.0 / present.sum(axis=2)) and not present.all()
+    # append: a response that repeats held clips and brings new ones, some of which lack splits
+    more = _records(rng, 45, [1, 2], 8)                       # clips 100..144: 100..129 are held
+    fake.calls.clear()
+    added = st.append_feature_rows(more, "global_pool")
+    o2, s2, X2, p2 = ps.pack_feature_rows(more, streams, "global_pool", held=lambda ids: np.array([c < 130 for c in ids]))
+    assert added == len(o2) == 15 and list(st.clip_ids) == order + o2 and st.n_rows == len(order) + 15
+    (ap,) = fake.of("vq_store_append")
+    wide = np.zeros((15, 2, 3, 8), np.float32)
+    wide[:, :, :2] = X2                                       # the store's third split slot stays zero / absent
+    assert ap[2] == 15 and np.array_equal(ap[3], wide.reshape(15, -1))
+    (sw2,) = fake.of("vq_store_set_split_weights")
+    full = np.concatenate([present, np.concatenate([p2, np.zeros((15, 2, 1), bool)], axis=2)])
+    assert np.allclose(sw2[2], 1.0 / full.sum(axis=2))
+    assert st.append_feature_rows(more, "global_pool") == 0   # nothing new the second time
+    with pytest.raises(ps.VQError):
+        st.append_feature_rows(_records(rng, 50, [4], 8), "global_pool")          # a split the store does not have
