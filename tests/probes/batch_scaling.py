@@ -76,6 +76,7 @@ def main():
             "call_ms_host_buffers_allgather_merge": best_c, "clips_x_queries_per_s": n_total * a.queries / best_k * 1e3,
             "algorithmic_tflops": flops / best_k / 1e9, "executed_tflops_bf16x2": 3 * flops / best_k / 1e9,
             "query0_counts": counts[0].tolist(), "query0_top10_matches_float64": ok}), flush=True)
+    rs.close()
     st.close()
     dist.destroy_process_group()
 
