@@ -735,3 +735,30 @@ def test_store_build_and_append_from_feature_records_issue_the_right_uploads(mon
     assert st.append_feature_rows(more, "global_pool") == 0   # nothing new the second time
     with pytest.raises(ps.VQError):
         st.append_feature_rows(_records(rng, 50, [4], 8), "global_pool")          # a split the store does not have
+
+
+def test_every_entry_point_refuses_null_arguments_without_crashing(built_lib):
+    """The ABI contract: every function returns an int status and leaves a message — no crash, no exception across
+    the boundary.  Each entry point is called with null pointers and zeros (in a child process, so that a regression
+    shows as a failed test and not as a dead test run); the destroy calls accept null like free()."""
+    code = (
+        "import sys, ctypes as C\n"
+        "sys.path.insert(0, %r)\n"
+        "from video_query_algorithms_b200 import _ffi\n"
+        "lib = _ffi.lib()\n"
+        "for name, (res, args) in sorted(_ffi.PROTOTYPES.items()):\n"
+        "    vals = [0 if a in (C.c_int, C.c_int32, C.c_int64, C.c_uint64) else 0.0 if a is C.c_double else None for a in args]\n"
+        "    r = getattr(lib, name)(*vals)\n"
+        "    if res is C.c_int and name != 'vq_abi_version':\n"
+        "        print(name, r, len(lib.vq_last_error() or b''))\n" % ROOT)
+    p = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr[-500:]
+    seen = 0
+    for line in p.stdout.splitlines():
+        name, rc, msg_len = line.split()
+        if name.endswith("_destroy"):
+            assert int(rc) == 0, line
+        else:
+            assert int(rc) < 0 and int(msg_len) > 0, line
+        seen += 1
+    assert seen == len(built_lib.PROTOTYPES) - 2            # all but vq_last_error and vq_abi_version
