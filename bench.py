@@ -154,6 +154,11 @@ def run_reference(args, rank, world):
         "e2e": {"value": v, "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "the reference is single-threaded Python (GIL-bound loops); it cannot use more host threads",
     }
+    if not args.no_cpu:                                   # the 'fair CPU' row beside it: the same arithmetic vectorised, all cores
+        vv, vdt = cpu_vectorised_throughput(200000)
+        line["cpu_baseline"]["vectorised_numpy_f64"] = {
+            "value": vv, "unit": "clips/s", "cores": cores,
+            "sample": "200000-clip slice, one pass (%.1f s), float64 numpy restatement, BLAS on all cores" % vdt}
     emit(line)
 
 
