@@ -525,9 +525,6 @@ class FeatureStore:
             s = np.empty(c.n_topk, np.float32)
             check(lib().vq_fetch_topk(sh.handle, c.n_topk, ptr(r), ptr(s)), "vq_fetch_topk")
             sc[i, :c.n_topk], rw[i, :c.n_topk] = s, r
-        if n_l == 1:
-            n = self._last_counts[0].n_topk
-            return rw[0, :n].copy(), sc[0, :n].copy()
         so, ro, n = np.empty(k, np.float32), np.empty(k, np.int64), C.c_int32()
         check(lib().vq_merge_topk(n_l, k, ptr(sc), ptr(rw), ptr(so), ptr(ro), C.byref(n)), "vq_merge_topk")
         return ro[:n.value], so[:n.value]
