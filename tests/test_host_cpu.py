@@ -762,3 +762,48 @@ def test_every_entry_point_refuses_null_arguments_without_crashing(built_lib):
             assert int(rc) < 0 and int(msg_len) > 0, line
         seen += 1
     assert seen == len(built_lib.PROTOTYPES) - 2            # all but vq_last_error and vq_abi_version
+
+
+def test_topk_merges_hold_for_arbitrary_lists(built_lib):
+    """Property test (hypothesis) of vq_merge_topk / vq_merge_topk_batch: for any number of lists, any k, heavy ties,
+    short and empty lists, ranked or not, the merge is the k best under (score descending, global row ascending) with
+    -inf / -1 padding — the ranking rule of reference ticket.py:266."""
+    from hypothesis import given, settings, strategies as hs
+    from video_query_algorithms_b200.sharded import merge_payloads_host, pack_payload, unpack_payload
+    from video_query_algorithms_b200.store import merge_topk_batch
+
+    @settings(max_examples=150, deadline=None)
+    @given(hs.integers(1, 6), hs.integers(1, 5), hs.integers(1, 24), hs.integers(0, 2 ** 31), hs.booleans())
+    def prop(n_lists, n_q, k, seed, ranked):
+        rng = np.random.default_rng(seed)
+        levels = rng.random(max(2, k // 2)).astype(np.float32)                 # few distinct scores: many ties
+        rows = np.full((n_lists, n_q, k), -1, np.int64)
+        sc_ = np.full((n_lists, n_q, k), -np.inf, np.float32)
+        for q in range(n_q):
+            ids = rng.permutation(n_lists * k * 3)                             # distinct global rows per query
+            for l in range(n_lists):
+                n = int(rng.integers(0, k + 1))
+                r = ids[l * k:l * k + n].astype(np.int64)
+                s_ = rng.choice(levels, n)
+                if ranked:
+                    o = np.lexsort((r, -s_.astype(np.float64)))
+                    r, s_ = r[o], s_[o]
+                rows[l, q, :n], sc_[l, q, :n] = r, s_
+        got_r, got_s = merge_topk_batch(rows, sc_)
+        for q in range(n_q):
+            m = rows[:, q].reshape(-1) >= 0
+            ar, as_ = rows[:, q].reshape(-1)[m], sc_[:, q].reshape(-1)[m]
+            o = np.lexsort((ar, -as_.astype(np.float64)))[:k]
+            n = len(o)
+            assert np.array_equal(got_r[q, :n], ar[o]) and np.array_equal(got_s[q, :n], as_[o])
+            assert np.all(got_r[q, n:] == -1) and np.all(np.isneginf(got_s[q, n:]))
+        # the single-query merge of per-rank payloads (counts summed) must agree with the batched one on query 0
+        if ranked:
+            pay = np.stack([pack_payload([3, 2, 1, int((rows[l, 0] >= 0).sum())], rows[l, 0][rows[l, 0] >= 0],
+                                         sc_[l, 0][rows[l, 0] >= 0], k) for l in range(n_lists)])
+            counts, r1, s1 = unpack_payload(merge_payloads_host(pay, n_lists, k), k)
+            n = int((got_r[0] >= 0).sum())
+            assert list(counts[:3]) == [3 * n_lists, 2 * n_lists, n_lists] and counts[3] == n
+            assert np.array_equal(r1, got_r[0, :n]) and np.array_equal(s1, got_s[0, :n])
+
+    prop()
