@@ -807,3 +807,29 @@ def test_topk_merges_hold_for_arbitrary_lists(built_lib):
             assert np.array_equal(r1, got_r[0, :n]) and np.array_equal(s1, got_s[0, :n])
 
     prop()
+
+
+def test_native_csv_reader_agrees_with_float_on_arbitrary_decimals(tmp_path, built_lib):
+    """Property test (hypothesis): whatever finite double, in whatever of the spellings Python prints or accepts
+    (repr, %.17g, %e, %f, fixed with many digits, with padding blanks), the library parses the cell to the double
+    float() gives — bit for bit — because the store must hold exactly what the reference would have computed with."""
+    from hypothesis import given, settings, strategies as hs
+    from video_query_algorithms_b200 import ingest
+    spell = [repr, lambda x: "%.17g" % x, lambda x: "%e" % x, lambda x: "%.30f" % x if abs(x) < 1e15 else repr(x),
+             lambda x: " " + repr(x), lambda x: "%.3g" % x, lambda x: "%+.12E" % x]
+    path = tmp_path / "flow_global_pool_features.csv"
+
+    @settings(max_examples=60, deadline=None)
+    @given(hs.lists(hs.floats(allow_nan=False, allow_infinity=False, width=64), min_size=8, max_size=8), hs.integers(0, 10 ** 6))
+    def prop(values, salt):
+        cells = [[spell[(i + j + salt) % len(spell)](v) for j, v in enumerate(values)] for i in range(5)]
+        with open(path, "w") as f:
+            f.write("video =v, video url =../x/, CNN stream =warped_optical_flow, feature blob =global_pool, caffe model =/m.caffemodel\n")
+            for i, row in enumerate(cells):
+                f.write(",".join([str(i)] + row) + "\n")
+        _, clips, want = _python_csv(path)
+        got = ingest.read_feature_csv(str(path), n_threads=1 + salt % 3)
+        assert np.array_equal(got["clip_numbers"], clips)
+        assert np.array_equal(got["features"].view(np.uint64), want.view(np.uint64))
+
+    prop()
