@@ -833,3 +833,24 @@ def test_native_csv_reader_agrees_with_float_on_arbitrary_decimals(tmp_path, bui
         assert np.array_equal(got["features"].view(np.uint64), want.view(np.uint64))
 
     prop()
+
+
+def test_vectorised_draws_match_python_for_arbitrary_parameters():
+    """Property test (hypothesis) of _rng.choices_range / set_order: any seed (int or str), population size, draw
+    count and number of consecutive calls give random.choices' indices, leave the generator in random.choices' state,
+    and `set_order` gives list(set(...))'s order — the reference's resampling (target_clip.py:297-309) exactly."""
+    from hypothesis import given, settings, strategies as hs
+    from video_query_algorithms_b200._rng import choices_range, set_order
+
+    @settings(max_examples=120, deadline=None)
+    @given(hs.one_of(hs.integers(0, 2 ** 64), hs.text(min_size=1, max_size=12)), hs.integers(1, 3000), hs.integers(1, 400),
+           hs.integers(1, 4))
+    def prop(seed, n, k, repeats):
+        a, b = random.Random(seed), random.Random(seed)
+        want = [a.choices(range(n), k=k) for _ in range(repeats)]
+        got = choices_range(b, n, k, repeats=repeats)
+        assert np.array_equal(np.asarray(want).reshape(got.shape), got) and a.getstate() == b.getstate()
+        assert a.random() == b.random()
+        assert set_order(np.asarray(want[0]), n).tolist() == list(set(want[0]))
+
+    prop()
