@@ -1,0 +1,215 @@
+"""End-to-end replay of every golden scenario through the PRODUCT's host path on CPU: `compute_matches` -> Ticket /
+TargetClip / Hyperparameter -> store, against the in-memory fake API, with the device behind the store played by
+`OracleStore` — a test double that answers the FeatureStore calls with the float64 oracle (same interface, same result
+conventions: fp32 scores, lists in database order, float64 labelled similarities).  It is test infrastructure: the
+product has no such path and fails without its CUDA library.  What it checks is everything around the kernels —
+store construction from API records, lazy score views, the weight update, target bootstrapping, selection, forced
+clips, persistence, the final report — for all seven scenarios, including the two recorded after the round's GPU
+budget was spent (F, G), whose GPU replay is still to come."""
+import os
+import random
+import types
+
+import numpy as np
+import pytest
+
+from oracle import bootstrap as ob
+from oracle import scoring as sc
+from scenarios import ORACLE_ONLY_SCENARIOS, SCENARIOS, Scenario
+
+os.environ.setdefault("COMPUTE_EPS", ".000003")
+EPS = 3e-6
+
+
+def make_oracle_store_class():
+    from video_query_algorithms_b200 import store as ps
+
+    class OracleStore(ps.FeatureStore):
+        def __init__(self, n_rows, streams, splits, dim=1024, devices=None, clip_ids=None, first_global_row=0):
+            self.streams, self.splits = tuple(streams), [int(p) for p in splits]
+            self.dim, self.n_rows, self.first_global_row = int(dim), int(n_rows), int(first_global_row)
+            self.row_shape = (len(self.streams), len(self.splits), self.dim)
+            self.shards = [types.SimpleNamespace(device=0, first=self.first_global_row, n_rows=self.n_rows, handle=None,
+                                                 close=lambda: None)]
+            self.clip_ids, self._row_of, self._row_memo, self.present, self.last = None, None, {}, None, None
+            if clip_ids is not None:
+                self.set_clip_ids(clip_ids)
+            self.X = np.zeros((self.n_rows,) + self.row_shape, np.float32)
+            self.n_scans = 0
+
+        # ---- what the library would hold
+        def upload(self, first_row, rows):
+            rows = np.asarray(rows, np.float32).reshape((-1,) + self.row_shape)
+            self.X[first_row:first_row + len(rows)] = rows
+
+        def set_present(self, present):
+            present = np.asarray(present, bool)
+            self.present = None if present.all() else present
+
+        def _sync_split_weights_for_target(self, have):
+            pass
+
+        def close(self):
+            pass
+
+        # ---- the scan and its results (conventions of vq_scan: fp32 scores, comparisons on (double)score)
+        def scan(self, target_features, weights, threshold, lower_limit, eps, topk=0, want_sims=False, lists=True):
+            T, have = self.pack_target(target_features, np.float32)
+            present = np.ones((self.n_rows,) + self.row_shape[:2], bool) if self.present is None else self.present
+            sims, _ = sc.similarities(self.X, T.astype(np.float64), present & have[None])
+            w = [weights[s] for s in self.streams] if isinstance(weights, dict) else list(weights)
+            self._sims32 = sims.astype(np.float32)
+            self._scores32 = sc.scores(sims, w).astype(np.float32)
+            s = self._scores32.astype(np.float64)
+            self._l = {"matches": np.flatnonzero(s >= threshold), "near_misses": np.flatnonzero((s >= lower_limit) & (s < threshold)),
+                       "ties": np.flatnonzero((np.abs(s - threshold) < eps) | (np.abs(s - lower_limit) < eps))}
+            self._k, self._lists, self.n_scans = int(topk), bool(lists), self.n_scans + 1
+            self.last = ps.ScanResult(len(self._l["matches"]), len(self._l["near_misses"]), len(self._l["ties"]),
+                                      min(self._k, self.n_rows), 0.0)
+            return self.last
+
+        def _list(self, which):
+            rows = self._l[which]
+            return (self.first_global_row + rows).astype(np.int64), self._scores32[rows]
+
+        def matches(self, copy=True):
+            assert self._lists, "whole lists read after a lists=False scan"
+            return self._list("matches")
+
+        def near_misses(self, copy=True):
+            assert self._lists, "whole lists read after a lists=False scan"
+            return self._list("near_misses")
+
+        def ties(self, copy=True):
+            return self._list("ties")
+
+        def gather(self, which, positions):
+            rows, scores = self._list(which)
+            pos = np.asarray(positions, np.int64)
+            return rows[pos], scores[pos]
+
+        def near_best(self):
+            rows, scores = self._list("near_misses")
+            if not len(rows):
+                return None
+            j = int(np.argmax(scores))
+            return j, int(rows[j]), float(scores[j])
+
+        def topk(self):
+            rows = sc.topk_stable(self._scores32, self._k)
+            return (self.first_global_row + rows).astype(np.int64), self._scores32[rows]
+
+        def ranked(self, which="matches"):
+            rows, scores = self._list(which)
+            o = np.argsort(-scores, kind="stable")
+            return rows[o], scores[o]
+
+        def scores(self):
+            return self._scores32
+
+        def sims(self):
+            return self._sims32
+
+        # ---- labelled subset (float64, like K4 / K6)
+        def labelled_sims(self, target_features, global_rows):
+            T, have = self.pack_target(target_features, np.float64)
+            rows = np.asarray(global_rows, np.int64) - self.first_global_row
+            present = np.ones((len(rows),) + self.row_shape[:2], bool) if self.present is None else self.present[rows]
+            return sc.similarities(self.X[rows], T, present & have[None])[0]
+
+        def bootstrap_target(self, valid_rows, invalid_rows, mu):
+            X = self.X.astype(np.float64)
+            v = np.asarray(valid_rows, np.int64) - self.first_global_row
+            iv = np.asarray(invalid_rows if invalid_rows is not None else [], np.int64) - self.first_global_row
+            out = np.empty(self.row_shape, np.float64)
+            for s in range(self.row_shape[0]):
+                for p in range(self.row_shape[1]):
+                    out[s, p] = ob.solve_valid_invalid(X[v, s, p], X[iv, s, p], mu) if len(iv) else ob.solve_valid(X[v, s, p])
+            return out
+
+    return OracleStore
+
+
+@pytest.fixture
+def cpu_product(monkeypatch):
+    """The product package with the device side of the store, the loss grid and the one-score fetch played by the oracle."""
+    import video_query_algorithms_b200 as vq
+    from video_query_algorithms_b200 import store as ps
+    from video_query_algorithms_b200 import ticket as pt
+    monkeypatch.setattr(ps, "FeatureStore", make_oracle_store_class())
+    monkeypatch.setattr(ps, "loss_grid", lambda sims, labels, wg, tg, ballast, replicates=None, device=0:
+                        sc.loss_grid(np.asarray(sims, np.float64), np.asarray(labels, bool), wg, tg, ballast)[None])
+    monkeypatch.setattr(pt.Ticket, "_score_of", lambda self, clip: float(self.feature_store().scores()[self.feature_store().row_of(clip)]))
+    ps.invalidate()
+    yield vq
+    ps._REGISTRY.clear()
+
+
+def close(a, b, rel=1e-5):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return a.shape == b.shape and bool(np.all(np.abs(a - b) <= rel * np.maximum(np.abs(b), 0.05)))
+
+
+@pytest.mark.parametrize("name", SCENARIOS + ORACLE_ONLY_SCENARIOS)
+def test_product_host_path_replays_reference_rounds_end_to_end(cpu_product, name, tmp_path, monkeypatch):
+    vq = cpu_product
+    from fake_api import FakeRepository
+    scn = Scenario(name)
+    api, qid = scn.build_api()
+    (tmp_path / "work").mkdir()
+    monkeypatch.chdir(tmp_path / "work")                     # the final report goes to ../final_reports/
+    rule = (lambda m: False) if scn.meta["label_rule"] == "False" else scn.label_rule()
+    tickets = []
+
+    def factory(job, url):
+        t = vq.Ticket(job, url, client=api.client(), devices=[0])
+        t.topk = 10
+        tickets.append(t)
+        return t
+
+    for i, r in enumerate(scn.rounds):
+        if i > 0:
+            api.label_latest_round(qid, rule)
+        api.request(qid, r["kind"])
+        hp = vq.Hyperparameter(**scn.hp())
+        random.seed(a=scn.seed)                              # broker.py:83-84
+        vq.compute_matches(FakeRepository(api), hp, ticket_factory=factory)
+        t = tickets[-1]
+        assert api.queries[qid]["process_state"] == r["process_state"]
+        assert [hp.weights[s] for s in scn.streams] == pytest.approx(r["weights"], rel=1e-5)
+        assert hp.threshold == pytest.approx(r["threshold"], rel=1e-5)
+        assert np.array_equal(t.feature_store().clip_ids, scn.arr(i, "clip_order"))
+        assert close(t.scores.array(), scn.arr(i, "scores"))
+        T = np.array([[t.target.target_features[s][p] for p in r["splits"]] for s in scn.streams])
+        assert np.abs(T - scn.arr(i, "target")).max() <= 1e-6 * np.abs(scn.arr(i, "target")).max()
+        if "r%d_losses" % i in scn.arrays.files:
+            assert np.abs(hp.losses - scn.arr(i, "losses")).max() < 1e-6
+        got_ids, want_ids = list(t.matches), [k for k, _ in r["selected"]]
+        if not t.tie_band:
+            assert got_ids == want_ids
+            assert close([t.matches[k] for k in got_ids], [v for _, v in r["selected"]])
+        assert list(t.ranked[0]) == [int(scn.clip_ids[j]) for j in sc.topk_stable(t.scores.array(), len(t.ranked[0]))]
+        # persisted: one match entity per selected clip on the new query result, with the user's earlier label
+        res_id = max(api.query_results)
+        stored = [m for m in api.matches.values() if m["query_result"] == res_id]
+        assert [m["video_clip"] for m in stored] == got_ids
+    # the store is built once per search set and reused by later ticks (the reference re-downloads every job)
+    assert api.calls.count(("search-sets", "features")) == 1
+    if scn.rounds[-1]["kind"] == "finalize":
+        assert len(api.uploaded_reports) == 1
+        body, ref = api.uploaded_reports[0].splitlines(), scn.meta["final_report"].splitlines()
+        assert len(body) == len(ref)
+        n_sel = len(scn.rounds[-1]["selected"])
+        # lines that carry float64-vs-fp32 digits (checked above) or names the two harnesses chose differently
+        skip = ("number of reviews", "min score", "stream weights", "Search Set queried", "Query:")
+        for a, b in zip(body[:-n_sel], ref[:-n_sel]):
+            assert a == b or a.startswith(skip), (a, b)
+        cols = lambda ln: ln.split(",")
+        ref_score = {str(k): v for k, v in scn.rounds[-1]["selected"]}
+        assert sorted(cols(ln)[4] for ln in body[-n_sel:]) == sorted(cols(ln)[4] for ln in ref[-n_sel:]) or tickets[-1].tie_band
+        for a, b in zip(body[-n_sel:], ref[-n_sel:]):
+            ca, cb = cols(a), cols(b)
+            if ca[4] == cb[4]:
+                assert ca[:5] == cb[:5] and ca[6:] == cb[6:] and float(ca[5]) == pytest.approx(float(cb[5]), rel=1e-5)
+            else:                                            # equal-score clips may swap within COMPUTE_EPS
+                assert abs(ref_score[ca[4]] - ref_score[cb[4]]) < EPS
