@@ -42,6 +42,17 @@ def make_oracle_store_class():
             rows = np.asarray(rows, np.float32).reshape((-1,) + self.row_shape)
             self.X[first_row:first_row + len(rows)] = rows
 
+        def append(self, rows, clip_ids=None, present=None):
+            """The product's own bookkeeping (ids, row counts, split presence) with the one library call answered here."""
+            rows32 = np.asarray(rows, np.float32).reshape((-1,) + self.row_shape)
+            real = ps.lib
+            ps.lib = lambda: types.SimpleNamespace(vq_store_append=lambda handle, n, p: 0)
+            try:
+                super().append(rows, clip_ids=clip_ids, present=present)
+            finally:
+                ps.lib = real
+            self.X = np.concatenate([self.X, rows32])
+
         def set_present(self, present):
             present = np.asarray(present, bool)
             self.present = None if present.all() else present
@@ -213,3 +224,55 @@ def test_product_host_path_replays_reference_rounds_end_to_end(cpu_product, name
                 assert ca[:5] == cb[:5] and ca[6:] == cb[6:] and float(ca[5]) == pytest.approx(float(cb[5]), rel=1e-5)
             else:                                            # equal-score clips may swap within COMPUTE_EPS
                 assert abs(ref_score[ca[4]] - ref_score[cb[4]]) < EPS
+
+
+def test_job_error_states_follow_the_reference_on_cpu(cpu_product, tmp_path, monkeypatch):
+    """compute_matches.py:47-52,92-94 through the product's host path: a fatal query error -> state 5 + note; a
+    recoverable one -> note and the round goes on; an empty selection -> state 5 'No matches were found'."""
+    vq = cpu_product
+    from fake_api import FakeRepository
+    from video_query_algorithms_b200 import store as ps
+    scn = Scenario("A_brooklyn_bagging")
+    monkeypatch.chdir(tmp_path)
+    factory = lambda api: (lambda job, url: vq.Ticket(job, url, client=api.client(), devices=[0]))
+    api, qid = scn.build_api()                               # (1) reference time outside the video: no ref clip
+    api.queries[qid]["ref_clip_id"] = None
+    api.request(qid, "new")
+    vq.compute_matches(FakeRepository(api), vq.Hyperparameter(**scn.hp()), ticket_factory=factory(api))
+    assert api.queries[qid]["process_state"] == 5 and "Fatal Error" in api.queries[qid]["notes"]
+    ps.invalidate()                                          # (2) revise, dynamic target adjustment, nothing confirmed
+    api, qid = scn.build_api()
+    api.request(qid, "new")
+    random.seed(a=scn.seed)
+    vq.compute_matches(FakeRepository(api), vq.Hyperparameter(**scn.hp()), ticket_factory=factory(api))
+    api.label_latest_round(qid, lambda m: False)
+    api.request(qid, "revise")
+    vq.compute_matches(FakeRepository(api), vq.Hyperparameter(**scn.hp()), ticket_factory=factory(api))
+    assert api.queries[qid]["process_state"] == 4
+    assert "Changing dynamic target adjustment to False" in api.queries[qid]["notes"]
+    ps.invalidate()                                          # (3) nothing selectable
+    api, qid = scn.build_api()
+    ss = api.queries[qid]["search_set_to_query"]
+    api.search_sets[ss]["clip_ids"] = [c for c in api.search_sets[ss]["clip_ids"] if c != api.queries[qid]["ref_clip_id"]]
+    api.request(qid, "new")
+    hp = dict(scn.hp(), default_threshold=5.0, near_miss_default=0.0)
+    vq.compute_matches(FakeRepository(api), vq.Hyperparameter(**hp), ticket_factory=factory(api))
+    assert api.queries[qid]["process_state"] == 5 and "No matches were found" in api.queries[qid]["notes"]
+    # (4) the search set grows between ticks (load_db.py adds a video): the resident store appends the new clips only
+    ps.invalidate()
+    both = Scenario("B_both_simple_mu")
+    api, qid = both.build_api()
+    ss = api.queries[qid]["search_set_to_query"]
+    all_ids = list(api.search_sets[ss]["clip_ids"])
+    api.search_sets[ss]["clip_ids"] = all_ids[:120]
+    api.request(qid, "new")
+    random.seed(a=both.seed)
+    made = []
+    fac = lambda job, url: made.append(vq.Ticket(job, url, client=api.client(), devices=[0])) or made[-1]
+    vq.compute_matches(FakeRepository(api), vq.Hyperparameter(**both.hp()), ticket_factory=fac)
+    st = made[-1].feature_store()
+    assert st.n_rows == 120
+    api.search_sets[ss]["clip_ids"] = all_ids
+    rows = api.client().action(None, ["search-sets", "features"], params={"id": ss})
+    assert st.append_feature_rows(rows, both.hp()["feature_name"]) == len(all_ids) - 120
+    assert list(st.clip_ids) == all_ids and st.X.shape[0] == len(all_ids)
