@@ -413,8 +413,8 @@ def test_host_mailbox_between_processes(built_lib):
     name = ("/vq-testp-%d" % os.getpid()).encode()
     q = ctx.Queue()                                          # no ordering between the ranks: an early rank waits for
     ps = [ctx.Process(target=_mailbox_process, args=(r, world, name, slot, n_calls, q)) for r in range(world)]
-    for p_ in reversed(ps):                                  # rank 0's segment (up to 2 s) instead of failing
-        p_.start()
+    for p_ in ps:                                            # rank 0's segment (up to 2 s) instead of failing; rank 0 is
+        p_.start()                                           # started first, so a loaded machine does not stretch that wait
     res = sorted(q.get(timeout=120) for _ in range(world))
     for p_ in ps:
         p_.join(timeout=30)
