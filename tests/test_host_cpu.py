@@ -662,9 +662,10 @@ def test_pack_feature_rows_follows_the_reference_dict_semantics():
             ref_ticket._request = lambda action, params, recs=recs: recs
             hp = type("HP", (), {"streams": streams, "feature_name": "global_pool"})()
             assert ref_ticket._get_candidate_features(splits, hp) == want
-        first_seen = list(dict.fromkeys(tf["video_clip_id"] for tf in recs
-                                        if tf["dnn_stream_id"] in streams and tf["name"] == "global_pool"))
-        assert order == first_seen and got_splits == sorted({p for s in want for p in want[s] if want[s][p]})
+        # row order = insertion order of the reference's scores dict: first stream, split by split (ticket.py:146-160)
+        ref_order = list(dict.fromkeys(c for p in splits for c in want[streams[0]][p]))
+        ref_order += [c for c in dict.fromkeys(c for p in splits for c in want[streams[1]][p]) if c not in set(ref_order)]
+        assert order == ref_order and got_splits == sorted({p for s in want for p in want[s] if want[s][p]})
         for si, s in enumerate(streams):
             for pi, p in enumerate(got_splits):
                 for r, c in enumerate(order):
@@ -854,3 +855,52 @@ def test_vectorised_draws_match_python_for_arbitrary_parameters():
         assert set_order(np.asarray(want[0]), n).tolist() == list(set(want[0]))
 
     prop()
+
+
+def test_row_order_on_ragged_search_sets_is_the_reference_scores_order():
+    """A search set whose clips lack arbitrary (stream, split) records: the store's row order must be the insertion order
+    of the reference's `scores` dict (its seeded sampling walks that order, ticket.py:326-341), which the reference builds
+    while walking the first stream split by split (ticket.py:146-160) — not simply the order of first appearance.  Spelled
+    out on a small case and, where the reference tree is present, against `Ticket.compute_similarities` itself."""
+    import types
+    from video_query_algorithms_b200.store import pack_feature_rows
+    streams = ("rgb", "warped_optical_flow")
+
+    def response(rng, clips, splits, lacks):
+        recs = []
+        for p in splits:                                         # load_db.py order: split dirs, then one file per stream
+            for s in streams:
+                for c in clips:
+                    if (c, s, p) not in lacks:
+                        recs.append({"dnn_stream_id": s, "dnn_stream_split": p, "name": "global_pool",
+                                     "feature_vector": rng.random(4).tolist(), "video_clip_id": c})
+        return recs
+
+    rng = np.random.default_rng(2)
+    small = response(rng, (1, 2, 3, 4), (1, 2), {(3, "rgb", 1), (1, "rgb", 1), (1, "warped_optical_flow", 1)})
+    assert pack_feature_rows(small, streams, "global_pool")[0] == [2, 4, 1, 3]       # by first appearance it would be 2, 4, 3, 1
+    if not os.path.isdir("/root/reference/src"):
+        return
+    import test_flow_cpu
+    test_flow_cpu.load_reference_driver()
+    import models.ticket as rticket
+    for trial in range(20):
+        clips, splits = list(range(10, 40)), (1, 2, 3)
+        lacks = set()
+        for c in clips:
+            for s in streams:
+                drop = [p for p in splits if rng.random() < 0.3]
+                for p in drop[:2]:                                # every clip keeps at least one split of every stream
+                    lacks.add((c, s, p))
+        recs = response(rng, clips, splits, lacks)
+        t = object.__new__(rticket.Ticket)
+        t.search_set, t._request = 1, (lambda action, params, recs=recs: recs)
+        t.target = types.SimpleNamespace(splits=set(splits), target_features={s: {p: [1.0, 0.0, 0.0, 0.0] for p in splits} for s in streams})
+        t.compute_similarities(types.SimpleNamespace(streams=streams, feature_name="global_pool"))
+        order, got_splits, X, present = pack_feature_rows(recs, streams, "global_pool")
+        assert order == list(t.similarities), trial
+        # and the per-clip split counts the reference records next to each similarity (ticket.py:160)
+        for r, c in enumerate(order):
+            assert [int(present[r, si].sum()) for si in range(2)] == [t.similarities[c][s][1] for s in streams]
+            assert [float(X[r, si, :, 0].sum() / present[r, si].sum()) for si in range(2)] == \
+                pytest.approx([t.similarities[c][s][0] for s in streams], rel=1e-6)

@@ -76,9 +76,13 @@ def pack_feature_rows(feature_rows, streams, feature_name, held=None):
     semantics: clips in order of first appearance (= the insertion order of the reference's `scores` dict, which its
     seeded sampling walks), a later record of the same (clip, stream, split) overwrites an earlier one, slots no record
     fills stay zero and are marked absent.  `held(clip ids) -> bool array` drops clips a store already holds (append).
+    Row order on ragged data: the reference's `scores` dict is filled while it walks the FIRST stream split by split
+    (ticket.py:146-160), so a clip enters at its first record of (first stream, lowest split it has there) — for
+    complete data simply the order of first appearance, otherwise clips that lack the first split come after all
+    clips that have it.  Clips without any first-stream record (the reference raises KeyError for them) go last.
     Returns (clip ids in row order, sorted split numbers, X float32 [n, S, P, dim], present bool [n, S, P])."""
     s_of = {s: i for i, s in enumerate(streams)}
-    row, cells, split_set = {}, [], set()
+    row, cells, split_set, enters = {}, [], set(), {}
     for tf in feature_rows:
         si = s_of.get(tf["dnn_stream_id"])
         if si is None or tf["name"] != feature_name:
@@ -88,8 +92,17 @@ def pack_feature_rows(feature_rows, streams, feature_name, held=None):
         if r is None:
             r = row[c] = len(row)
         split_set.add(p)
+        if si == 0:
+            key = (p, len(cells))
+            if key < enters.get(r, (float("inf"), 0)):
+                enters[r] = key
         cells.append((r, si, p, tf["feature_vector"]))
     order = list(row)
+    perm = sorted(range(len(order)), key=lambda r: enters.get(r, (float("inf"), r)))
+    if perm != list(range(len(order))):                       # ragged first stream: re-seat the rows
+        seat = {old: new for new, old in enumerate(perm)}
+        order = [order[old] for old in perm]
+        cells = [(seat[r], si, p, v) for r, si, p, v in cells]
     remap = None
     if held is not None and order:
         keep = ~np.asarray(held(order), dtype=bool)
