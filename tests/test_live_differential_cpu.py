@@ -29,7 +29,9 @@ def reference(monkeypatch):
     real_sample = random.sample
     mg.install_shims(holder)                                  # stub coreapi, no auth, random.sample accepts Set populations
     import models.compute_matches as rcm
+    import models.ticket as rticket
     from models import Hyperparameter as RefHP
+    rticket.coreapi = sys.modules["coreapi"]                  # another test may have imported the reference with its own stub
     yield holder, rcm, RefHP
     random.sample = real_sample
 
