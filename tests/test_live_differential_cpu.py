@@ -156,3 +156,81 @@ def test_reference_and_product_agree_on_random_jobs(reference, cpu_product, tmp_
             compared += 1
     assert compared >= n_trials, (compared, ties, plateaus)    # measured: ~1.4 compared rounds per job, ~0.2 tie-band and
                                                                # ~0.35 plateau rounds per job (both end that job's comparison)
+
+
+def test_several_jobs_in_one_tick_share_the_generator_like_the_reference(reference, cpu_product, tmp_path, monkeypatch):
+    """One `compute_matches` call with a revise, a new and a finalize job pending at once (three queries on one search
+    set): the jobs run in the repository's order revise -> new -> finalize on ONE seeded generator (broker.py:83-87), so
+    every later job's sampling depends on how many draws the earlier ones consumed.  Reference and product side by side."""
+    holder, rcm, RefHP = reference
+    vq = cpu_product
+    from fake_api import FakeRepository
+    from video_query_algorithms_b200 import store as ps
+    for d in ("ref/work", "prod/work"):
+        (tmp_path / d).mkdir(parents=True)
+    monkeypatch.chdir(tmp_path)
+    rng = np.random.default_rng(77)
+    done = 0
+    for trial in range(8):
+        job = draw_job(rng)
+        if job["ragged"]:
+            continue
+        sides = []
+        for side in ("ref", "prod"):
+            api, q1 = build_api(job, "%da" % trial)
+            ss, vid = api.queries[q1]["search_set_to_query"], api.queries[q1]["video"]
+            ids = api.search_sets[ss]["clip_ids"]
+            q2 = api.add_query("q%db" % trial, vid, ids[(job["ref_row"] + 5) % len(ids)], ss, max_matches=job["max_matches"],
+                               dynamic_target_adjustment=job["dyn"])
+            q3 = api.add_query("q%dc" % trial, vid, ids[(job["ref_row"] + 9) % len(ids)], ss, max_matches=job["max_matches"],
+                               dynamic_target_adjustment=True)
+            api.queries[q2]["pending"] = api.queries[q3]["pending"] = None
+            sides.append((side, api, (q1, q2, q3)))
+        (_, api_r, qs_r), (_, api_p, qs_p) = sides
+        holder["api"] = api_r
+        ps.invalidate()
+        tickets = []
+        factory = lambda j, url: tickets.append(vq.Ticket(j, url, client=api_p.client(), devices=[0])) or tickets[-1]
+
+        def tick(pending):
+            """pending: {query index: kind}; one compute_matches call per side on the same seed"""
+            out = []
+            for side, api, qs in sides:
+                for q in qs:
+                    api.queries[q]["pending"] = None
+                for qi, kind in pending.items():
+                    api.request(qs[qi], kind)
+                hp = (RefHP if side == "ref" else vq.Hyperparameter)(**job["hp"])
+                random.seed(a=job["seed"])
+                os.chdir(tmp_path / side / "work")
+                if side == "ref":
+                    rcm.compute_matches(FakeRepository(api), hp)
+                else:
+                    vq.compute_matches(FakeRepository(api), hp, ticket_factory=factory)
+                out.append(([snapshot(api, q, hp) for q in qs], random.getstate()))
+            return out
+
+        def label(qi):
+            shown = {m["video_clip"]: m["score"] for m in api_r.matches.values()
+                     if m["query_result"] == api_r._latest_result(qs_r[qi])["id"]}
+            cut = float(np.quantile(list(shown.values()), job["label_quantile"])) + 1e-4
+            labels = {c: bool(v >= cut) for c, v in shown.items()}
+            for _, api, qs in sides:
+                api.label_latest_round(qs[qi], lambda m: labels[m["video_clip"]])
+
+        ok = True
+        for pending in ({0: "new"}, {2: "new"}, {0: "revise", 1: "new", 2: "finalize"}):
+            if len(pending) == 3:
+                label(0), label(2)
+            (snap_r, state_r), (snap_p, state_p) = tick(pending)
+            if any(t.tie_band for t in tickets[-len(pending):]) or any(
+                    t._hp is not None and t._hp.losses is not None and int(np.sum(t._hp.losses - t._hp.losses.min() < 1e-9)) > 1
+                    for t in tickets[-len(pending):]):
+                ok = False                                     # boundary tie or loss plateau (see the test above): not comparable
+                break
+            for a, b in zip(snap_r, snap_p):
+                assert a["state"] == b["state"] and a["round"] == b["round"] and a["notes"] == b["notes"], (trial, pending)
+                assert a["clips"] == b["clips"] and close(b["scores"], a["scores"]), (trial, pending)
+            assert state_r == state_p, (trial, pending)
+        done += ok
+    assert done >= 2
