@@ -95,11 +95,11 @@ def test_reference_and_product_agree_on_random_jobs(reference, cpu_product, tmp_
         (tmp_path / d).mkdir(parents=True)
     rng = np.random.default_rng(int(os.environ.get("VQ_DIFF_SEED", "20261018")))
     monkeypatch.chdir(tmp_path)                                # restored at teardown
-    compared = ties = plateaus = 0
+    compared = ties = plateaus = ref_crashes = 0
     n_trials = int(os.environ.get("VQ_DIFF_TRIALS", "30"))
     for trial in range(n_trials):
         job = draw_job(rng)
-        kinds = ["new"] if job["ragged"] else ["new", "revise", "finalize"][:int(rng.integers(2, 4))]
+        kinds = ["new", "revise", "finalize"][:int(rng.integers(2, 4))]
         api_r, q_r = build_api(job, str(trial))              # (the report's file name carries the query name)
         api_p, q_p = build_api(job, str(trial))
         holder["api"] = api_r
@@ -131,6 +131,12 @@ def test_reference_and_product_agree_on_random_jobs(reference, cpu_product, tmp_
                 vq.compute_matches(FakeRepository(api_p), hp_p, ticket_factory=factory)
             except Exception as e:
                 err_p = type(e).__name__
+            if err_r and not err_p and job["ragged"] and kind != "new":
+                # ragged labelled clips: a (stream, split) slot that no rejected (or no confirmed) clip has leaves the
+                # reference with an empty per-slot list, on which its solve raises (target_clip.py:250: trace of an
+                # empty array); the product solves that slot from the clips that have it.  Counted, not compared.
+                ref_crashes += 1
+                break
             if err_r or err_p:
                 assert (err_r is None) == (err_p is None), (trial, kind, err_r, err_p)
                 break
@@ -154,7 +160,7 @@ def test_reference_and_product_agree_on_random_jobs(reference, cpu_product, tmp_
             assert b["weights"] == pytest.approx(a["weights"], rel=1e-5) and b["threshold"] == pytest.approx(a["threshold"], rel=1e-5), where
             assert random.getstate() == state_r, where         # the generator ends where the reference left it
             compared += 1
-    assert compared >= n_trials, (compared, ties, plateaus)    # measured: ~1.4 compared rounds per job, ~0.2 tie-band and
+    assert compared >= n_trials, (compared, ties, plateaus, ref_crashes)    # measured: ~1.4 compared rounds per job, ~0.2 tie-band and
                                                                # ~0.35 plateau rounds per job (both end that job's comparison)
 
 

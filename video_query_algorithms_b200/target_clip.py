@@ -92,8 +92,30 @@ class TargetClip:
             invalid_rows = self._random_fraction(invalid_rows, b_fraction, replacement)
         elif b_fraction != 1 or replacement is True:
             valid_rows = self._random_fraction(valid_rows, b_fraction, replacement)
-        w = store.bootstrap_target(valid_rows, invalid_rows, mu)          # [S, P, dim] float64
+        w = self._solve_slots(store, valid_rows, invalid_rows, mu)        # [S, P, dim] float64
         return self._as_feature_dict(w, store, splits)
+
+    @staticmethod
+    def _solve_slots(store, valid_rows, invalid_rows, mu):
+        """One `vq_bootstrap_target` call solves every (stream, split) slot from the same labelled rows.  On a ragged
+        search set a labelled clip may lack a slot (a zero row in the store); the reference then solves that slot with
+        the clips that do have it — its per-slot feature lists only receive the rows a clip has
+        (target_clip.py:184-187, 232-240) — so the slot's rows are filtered the same way, one call per slot (the slots
+        of a call are independent problems; only the filtered slot's answer is kept, the others may be singular)."""
+        valid_rows, invalid_rows = np.asarray(valid_rows, np.int64), np.asarray(invalid_rows, np.int64)
+        if store.present is None:
+            return store.bootstrap_target(valid_rows, invalid_rows, mu)
+        has_v = store.present[valid_rows - store.first_global_row]
+        has_i = store.present[invalid_rows - store.first_global_row]
+        if has_v.all() and has_i.all():
+            return store.bootstrap_target(valid_rows, invalid_rows, mu)
+        w = np.zeros(has_v.shape[1:] + (store.dim,), np.float64)
+        for si in range(has_v.shape[1]):
+            for pi in range(has_v.shape[2]):
+                v, iv = valid_rows[has_v[:, si, pi]], invalid_rows[has_i[:, si, pi]]
+                if len(v):                                                 # no labelled clip has the slot: it stays zero
+                    w[si, pi] = store.bootstrap_target(v, iv, mu)[si, pi]
+        return w
 
     def target_by_bagging(self, valid_rows, invalid_rows, splits):
         """Mean of nbags targets, each from a with-replacement resample (target_clip.py:145-159)."""
