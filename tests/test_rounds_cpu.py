@@ -136,7 +136,8 @@ def make_oracle_store_class():
             for s in range(self.row_shape[0]):
                 for p in range(self.row_shape[1]):
                     try:
-                        out[s, p] = ob.solve_valid_invalid(X[v, s, p], X[iv, s, p], mu) if len(iv) else ob.solve_valid(X[v, s, p])
+                        with np.errstate(all="ignore"):
+                            out[s, p] = ob.solve_valid_invalid(X[v, s, p], X[iv, s, p], mu) if len(iv) else ob.solve_valid(X[v, s, p])
                     except np.linalg.LinAlgError:            # the kernel's LU has no singularity check: that slot is not finite
                         out[s, p] = np.nan
             return out
