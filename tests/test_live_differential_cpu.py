@@ -38,7 +38,10 @@ def reference(monkeypatch):
 
 def draw_job(rng):
     """One random job description: search set, reference clip, hyperparameters, rounds."""
-    n, dim = int(rng.integers(24, 70)), int(rng.choice([16, 48]))
+    # dim stays above the number of clips a user can confirm over three rounds: with more confirmed clips than
+    # dimensions the bootstrap's Gram matrix is singular and the reference's inv() returns garbage (SURVEY.md §8 A10;
+    # the library refuses such a solve), so there is nothing to compare
+    n, dim = int(rng.integers(24, 70)), int(rng.choice([48, 64]))
     splits = [1, 2, 3][:int(rng.integers(1, 4))]
     base = rng.random((2, len(splits), dim)) + 0.2
     alpha = rng.random(n) ** 0.5                               # scores spread over the band, like VQSYN-1
@@ -52,13 +55,14 @@ def draw_job(rng):
                     lacks.add((c, s, int(rng.choice(splits))))
     kind = str(rng.choice(["bagging", "simple"]))
     hp = dict(default_weights={"rgb": 1.0, "warped_optical_flow": float(rng.choice([0.8, 1.5, 2.2]))},
-              default_threshold=float(rng.choice([0.6, 0.7, 0.8])), ballast=float(rng.choice([0.0, 0.2])),
+              default_threshold=float(rng.choice([0.6, 0.7, 0.8, 0.97])), ballast=float(rng.choice([0.0, 0.2])),
               near_miss_default=float(rng.choice([0.2, 0.35, 0.6])), mu=float(rng.choice([0.0, 0.3])), streams=STREAMS,
               feature_name="global_pool", f_bootstrap=float(rng.choice([0.5, 0.8, 1])), f_memory=0.7, bootstrap_type=kind,
               nbags=int(rng.integers(2, 5)))
     return {"X": X, "splits": splits, "lacks": lacks, "ragged": ragged, "hp": hp, "ref_row": int(np.argmax(alpha)),
             "max_matches": int(rng.choice([6, 9, 12, 20])), "dyn": bool(rng.random() < 0.7),
-            "label_quantile": float(rng.choice([0.3, 0.5, 0.7])), "seed": str(int(rng.integers(1, 10 ** 9)))}
+            "label_quantile": float(rng.choice([0.3, 0.5, 0.7])), "seed": str(int(rng.integers(1, 10 ** 9))),
+            "unlabelled": float(rng.choice([0.0, 0.0, 0.3])), "ref_outside": bool(rng.random() < 0.15)}
 
 
 def build_api(job, tag=""):
@@ -72,7 +76,7 @@ def build_api(job, tag=""):
             for c in range(n):
                 if (c, s_i, p) not in job["lacks"] or c == job["ref_row"]:
                     api.add_feature(ids[c], s, p, [float(x) for x in job["X"][c, s_i, p_i]])
-    ss = api.add_search_set("s", ids)
+    ss = api.add_search_set("s", [c for i, c in enumerate(ids) if not (job["ref_outside"] and i == job["ref_row"])])
     qid = api.add_query("q" + tag, vid, ids[job["ref_row"]], ss, max_matches=job["max_matches"], dynamic_target_adjustment=job["dyn"])
     return api, qid
 
@@ -112,6 +116,9 @@ def test_reference_and_product_agree_on_random_jobs(reference, cpu_product, tmp_
                          if m["query_result"] == api_r._latest_result(q_r)["id"]}
                 cut = float(np.quantile(list(shown.values()), job["label_quantile"])) + 1e-4
                 labels = {c: bool(v >= cut) for c, v in shown.items()}
+                for c in sorted(labels):                       # the user skips some clips: label None -> is_match decides
+                    if rng.random() < job["unlabelled"]:
+                        labels[c] = None
                 api_r.label_latest_round(q_r, lambda m: labels[m["video_clip"]])
                 api_p.label_latest_round(q_p, lambda m: labels[m["video_clip"]])
             api_r.request(q_r, kind)
@@ -120,10 +127,19 @@ def test_reference_and_product_agree_on_random_jobs(reference, cpu_product, tmp_
             random.seed(a=job["seed"])
             err_r = err_p = None
             os.chdir(tmp_path / "ref" / "work")
+            grid_r, real_argmin = {}, np.argmin
+
+            def argmin(a, axis=None, **kw):                    # the reference keeps no copy of its loss grid: take one
+                grid_r["losses"] = np.array(a, copy=True)
+                return real_argmin(a, axis=axis, **kw)
+
+            np.argmin = argmin
             try:
                 rcm.compute_matches(FakeRepository(api_r), hp_r)
             except Exception as e:                             # e.g. a singular Gram matrix: both must fail alike
                 err_r = type(e).__name__
+            finally:
+                np.argmin = real_argmin
             state_r = random.getstate()
             random.seed(a=job["seed"])
             os.chdir(tmp_path / "prod" / "work")
@@ -155,9 +171,15 @@ def test_reference_and_product_agree_on_random_jobs(reference, cpu_product, tmp_
             if L is not None and kind != "new" and int(np.sum(L - L.min() < 1e-9)) > 1:
                 plateaus += 1
                 break
-            assert a["clips"] == b["clips"], where
+            if a["clips"] != b["clips"] and "losses" in grid_r and os.environ.get("VQ_DIFF_DEBUG"):
+                Lr, Lp = grid_r["losses"], hp_p.losses
+                ir, ip = np.unravel_index(real_argmin(Lr), Lr.shape), np.unravel_index(real_argmin(Lp), Lp.shape)
+                print("DEBUG", where, "ref argmin", ir, Lr[ir], Lr[ip], "prod argmin", ip, Lp[ip], Lp[ir], "max diff", np.abs(Lr - Lp).max())
+            assert a["clips"] == b["clips"], (where, a["weights"], b["weights"], a["threshold"], b["threshold"])
             assert close(b["scores"], a["scores"]), where
-            assert b["weights"] == pytest.approx(a["weights"], rel=1e-5) and b["threshold"] == pytest.approx(a["threshold"], rel=1e-5), where
+            # (1e-4, not the 1e-5 of the recorded scenarios: the store holds fp32 features, and on random data the parabola fit
+            # through five nearly equal losses can turn that 1e-8 into 2e-5 on the weight)
+            assert b["weights"] == pytest.approx(a["weights"], rel=1e-4) and b["threshold"] == pytest.approx(a["threshold"], rel=1e-4), where
             assert random.getstate() == state_r, where         # the generator ends where the reference left it
             compared += 1
     assert compared >= n_trials, (compared, ties, plateaus, ref_crashes)    # measured: ~1.4 compared rounds per job, ~0.2 tie-band and
