@@ -206,3 +206,27 @@ def test_driver_key_sequences_without_the_reference():
     empty = run_product(dict(base, kind="revise", selected=(), jobs={"revise": job("revise"), "new": None, "finalize": None}))
     assert empty[-2][1:] == ("change_process_state", "5",
                              repr("*** Error: No matches were found for round 2 of query 7! ***"))
+
+
+def test_ticket_error_texts_and_hyperparameter_defaults_equal_the_reference():
+    """`Ticket.catch_errors` (ticket.py:80-110) on every combination of its three conditions, and the constructor
+    defaults / grids of `Hyperparameter` (hyperparameter.py:9-27), against the reference's own classes."""
+    load_reference_driver()
+    import models.hyperparameter as rhp
+    import models.ticket as rticket
+    from video_query_algorithms_b200 import Hyperparameter, Ticket
+    import numpy as np
+    for ref_clip_id, kind, matches, dyn in itertools.product(
+            (None, 30), ("new", "revise", "finalize"),
+            ([], [{"user_match": True}], [{"user_match": False}, {"user_match": None}]), (True, False)):
+        out = []
+        for cls in (rticket.Ticket, Ticket):
+            t = object.__new__(cls)
+            t.ref_clip_id, t.matches, t.dynamic_target_adjustment = ref_clip_id, list(matches), dyn
+            out.append((t.catch_errors(kind), t.dynamic_target_adjustment))
+        assert out[0] == out[1], (ref_clip_id, kind, matches, dyn)
+    a, b = rhp.Hyperparameter({"rgb": 1.0, "warped_optical_flow": 1.5}), Hyperparameter({"rgb": 1.0, "warped_optical_flow": 1.5})
+    for name, value in vars(a).items():
+        got = getattr(b, name)
+        assert np.array_equal(got, value) if isinstance(value, np.ndarray) else got == value, name
+    assert len(b.weight_grid) == 40 and len(b.threshold_grid) == 31

@@ -170,9 +170,11 @@ class Ticket:
             fatal.append("*** Fatal Error: A video clip corresponding to the reference time does "
                          "not exist in the database. ***")
         if job_type != "new" and not self.matches:
-            fatal.append("*** Fatal Error: This is not a new query but there are 0 matches computed "
-                         "for the previous round. Cannot update without matches. Check database consistency "
-                         "for this query")
+            # byte for byte the note the reference writes: its string literal continues across lines inside the quotes
+            # (ticket.py:92-94), so the text carries two stray quote pairs with 34 and 35 blanks between them
+            fatal.append("*** Fatal Error: This is not a new query but there are 0 matches computed '" + " " * 34 +
+                         "'for the previous round. Cannot update without matches. Check database consistency '" + " " * 35 +
+                         "'for this query")
         if job_type != "new" and self.dynamic_target_adjustment is True:
             if not any(match["user_match"] is True for match in self.matches):
                 recoverable.append('*** Error: Dynamic target adjustment is True but there are no user matches '
