@@ -99,7 +99,7 @@ def test_reference_and_product_agree_on_random_jobs(reference, cpu_product, tmp_
         (tmp_path / d).mkdir(parents=True)
     rng = np.random.default_rng(int(os.environ.get("VQ_DIFF_SEED", "20261018")))
     monkeypatch.chdir(tmp_path)                                # restored at teardown
-    compared = ties = plateaus = ref_crashes = 0
+    compared = ties = plateaus = ref_crashes = reports = 0
     n_trials = int(os.environ.get("VQ_DIFF_TRIALS", "30"))
     for trial in range(n_trials):
         job = draw_job(rng)
@@ -181,8 +181,22 @@ def test_reference_and_product_agree_on_random_jobs(reference, cpu_product, tmp_
             # through five nearly equal losses can turn that 1e-8 into 2e-5 on the weight)
             assert b["weights"] == pytest.approx(a["weights"], rel=1e-4) and b["threshold"] == pytest.approx(a["threshold"], rel=1e-4), where
             assert random.getstate() == state_r, where         # the generator ends where the reference left it
+            if kind == "finalize" and a["state"] == 7:         # the final report: same header, same rows in the same order
+                rep_r, rep_p = api_r.uploaded_reports[-1].splitlines(), api_p.uploaded_reports[-1].splitlines()
+                assert len(rep_r) == len(rep_p), where
+                n_rows = len(a["clips"])
+                for x, y in zip(rep_r[:-n_rows], rep_p[:-n_rows]):
+                    assert x == y or x.startswith(("min score", "stream weights")), (where, x, y)   # fp32-vs-float64 digits
+                for x, y in zip(rep_r[-n_rows:], rep_p[-n_rows:]):
+                    cx, cy = x.split(","), y.split(",")
+                    if cx[4] == cy[4]:
+                        assert cx[:5] == cy[:5] and cx[6:] == cy[6:] and float(cy[5]) == pytest.approx(float(cx[5]), rel=1e-5), where
+                    else:                                      # equal-score clips may swap (stable sort on fp32 vs float64 scores)
+                        sc_r = dict(zip(a["clips"], a["scores"]))
+                        assert abs(sc_r[int(cx[4])] - sc_r[int(cy[4])]) < 3e-6, (where, x, y)
+                reports += 1
             compared += 1
-    assert compared >= n_trials, (compared, ties, plateaus, ref_crashes)    # measured: ~1.4 compared rounds per job, ~0.2 tie-band and
+    assert compared >= n_trials and reports >= 1, (compared, ties, plateaus, ref_crashes, reports)    # measured: ~1.4 compared rounds per job, ~0.2 tie-band and
                                                                # ~0.35 plateau rounds per job (both end that job's comparison)
 
 
