@@ -98,8 +98,9 @@ def pack_feature_rows(feature_rows, streams, feature_name, held=None):
                 enters[r] = key
         cells.append((r, si, p, tf["feature_vector"]))
     order = list(row)
-    perm = sorted(range(len(order)), key=lambda r: enters.get(r, (float("inf"), r)))
-    if perm != list(range(len(order))):                       # ragged first stream: re-seat the rows
+    keys = [enters.get(r, (float("inf"), r)) for r in range(len(order))]
+    if any(a > b for a, b in zip(keys, keys[1:])):            # ragged first stream: re-seat the rows
+        perm = sorted(range(len(order)), key=keys.__getitem__)
         seat = {old: new for new, old in enumerate(perm)}
         order = [order[old] for old in perm]
         cells = [(seat[r], si, p, v) for r, si, p, v in cells]
