@@ -31,7 +31,7 @@ extern "C" {
 
 #define VQ_MAX_STREAMS 4
 #define VQ_MAX_TOPK 1024
-#define VQ_ABI_VERSION 1
+#define VQ_ABI_VERSION 2
 
 typedef struct vq_store vq_store;
 
@@ -96,6 +96,16 @@ int vq_scan_select(vq_store *s, const float *target, const vq_scan_params *p, vq
                    int64_t *near_best_pos, int64_t *near_best_row, float *near_best_score);
 int vq_gather_list(vq_store *s, int32_t which, int64_t n_idx, const int64_t *positions, int64_t *rows_out,
                    float *scores_out);
+/* The broker's arrangement — ONE process, one job at a time (reference src/broker.py:62-92) — with the search set sharded
+ * over the GPUs of the box: the same scan on every shard from one call and one thread.  The target copy, K1, K2 and the
+ * publish kernel are enqueued on every shard's own stream first, then each stream is waited for once; the shards'
+ * ranked top-k lists are merged into the search set's (score descending, global row ascending).  lists = 1 behaves like
+ * vq_scan on every shard (whole lists in the host mirrors), lists = 0 like vq_scan_select.  counts_out [n_shards];
+ * near_best_out [n_shards][3] = position in the shard's near-miss list, global row (-1: none), fp32 score bits;
+ * list positions are per shard: the shards' lists in shard order are the search set's lists in database order.      */
+int vq_scan_multi(vq_store *const *shards, int32_t n_shards, const float *target, const vq_scan_params *p,
+                  int32_t lists, vq_scan_counts *counts_out, int64_t *near_best_out, int32_t topk_cap,
+                  int64_t *topk_rows_out, float *topk_scores_out, int32_t *n_topk_out);
 /* Same work, enqueued only: target already on the device, nothing copied back, no sync.
  * Used for device-side timing and for multi-GPU merges that read the results in place.      */
 int vq_scan_enqueue(vq_store *s, const float *target_dev, const vq_scan_params *p, void *stream);
@@ -112,7 +122,15 @@ int vq_scan_host_list(vq_store *s, int32_t which, const int64_t **rows, const fl
 /* Full ranking of a list of the last scan (which = 0 matches, 1 near misses), sorted on the device: score descending,
  * database order among equal scores (the report order of ticket.py:266).                                         */
 int vq_fetch_ranked(vq_store *s, int32_t which, int64_t cap, int64_t *rows_out, float *scores_out);
+/* The same list sorted by (score descending, caller's tie-break ascending): the report order of ticket.py:266 is a stable
+ * sort of the clips in SELECTION order (for a finalize round a seeded permutation of the lists, ticket.py:333,341), so
+ * equal scores keep that order, not the database's.  tiebreak [n] = each list entry's rank in selection order (distinct
+ * values < 2^32 - 16); tiebreak_out [n] = the same values in report order, scores_out their scores.                   */
+int vq_rank_list(vq_store *s, int32_t which, int64_t n, const uint32_t *tiebreak, uint32_t *tiebreak_out,
+                 float *scores_out);
 int vq_fetch_scores(vq_store *s, int64_t first_row, int64_t n_rows, float *scores_out);
+/* scores of the last scan at n arbitrary LOCAL rows in one round trip (the forced clips of ticket.py:346-356)          */
+int vq_fetch_scores_at(vq_store *s, int64_t n, const int64_t *local_rows, float *scores_out);
 int vq_fetch_sims(vq_store *s, int64_t first_row, int64_t n_rows, float *sims_out);
 
 /* device views of the last scan's results (valid until the next scan on this store)         */
@@ -155,6 +173,13 @@ int vq_scan_exchange_enqueue(vq_store *s, vq_exchange *x, void *stream);
 int vq_scan_exchange_enqueue_lagged(vq_store *s, vq_exchange *x, void *stream);
 int vq_exchange_flush_enqueue(vq_exchange *x, void *stream);
 int vq_exchange_merged(vq_exchange *x, const int64_t **merged_dev /* [4 + 2*topk] */);
+/* The exchange kernel runs on a stream of its own behind the scan stream (the next scan does not queue behind it, nor
+ * behind the peer it may be waiting for); vq_exchange_flush_enqueue also makes `stream` wait for it, so call it before
+ * reading the merged buffer on `stream`.  A peer that never delivers ends the kernel after VQ_EXCHANGE_TIMEOUT_S
+ * (default 10 s) with negative counts in the merged buffer: vq_exchange_check (after a synchronisation) reports it.
+ * vq_exchange_kernel_times: device time of each exchange kernel since the last call (ring of 256), in ms.           */
+int vq_exchange_check(vq_exchange *x);
+int vq_exchange_kernel_times(vq_exchange *x, int32_t cap, float *ms_out, int32_t *n_out);
 
 /* Host mailbox: all-gather of small records (up to slot_bytes each) between the rank processes of ONE box through a
  * POSIX shared-memory segment — the host-side twin of the exchange above, for what the host needs from its peers per
@@ -171,6 +196,8 @@ int vq_hostx_destroy(vq_hostx *x);
 
 /* per-launch device times of K1 recorded since the last call (ring of 1024), in ms           */
 int vq_scan_kernel_times(vq_store *s, int32_t cap, float *ms_out, int32_t *n_out);
+/* the same ring split by phase: K1 (scan) and K2a-c (selection) per launch; either output may be NULL                */
+int vq_scan_phase_times(vq_store *s, int32_t cap, float *scan_ms_out, float *select_ms_out, int32_t *n_out);
 /* merge per-shard top-k lists (score desc, global row asc) — the host/rank-0 side of the
  * NCCL allgather merge; lists: [n_lists][k] with -inf / -1 padding.                          */
 int vq_merge_topk(int32_t n_lists, int32_t k, const float *scores, const int64_t *rows,
@@ -210,6 +237,12 @@ int vq_scan_batch(vq_store *s, const float *targets /* [Q][S][P][dim] */, int32_
 /* Test hook: the full [Q][n_rows] fp32 score matrix of the batched path (small shards only). */
 int vq_scan_batch_scores(vq_store *s, const float *targets, int32_t n_queries, const vq_scan_params *p,
                          float *scores_out);
+
+/* ---------------------------------------------------------------- seeded sampling (host code)
+ * `random.sample(range(n), k)` on CPython's Mersenne Twister state (ticket.py:333,341 draw the review set with it; the
+ * finalize round permutes EVERY match, one interpreter loop iteration per clip): same picks, same state afterwards.
+ * mt_state [624] and mt_pos are random.getstate()[1][:624] and [624], updated in place.                              */
+int vq_mt_sample_range(uint32_t *mt_state, int32_t *mt_pos, int64_t n, int64_t k, int64_t *picks_out);
 
 /* ---------------------------------------------------------------- feature-CSV ingest (host code)
  * The files the TSN extractor writes and load_db.py loads (src/api/api_load_records.py:41-58:

@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol(built_lib):
     for n in names:
         assert hasattr(handle, n), "libvq_b200.so does not export " + n
     assert sorted(built_lib.PROTOTYPES) == names            # the ctypes table covers the header exactly
-    assert built_lib.lib().vq_abi_version() == 1
+    assert built_lib.lib().vq_abi_version() == 2
 
 
 def test_header_is_plain_c(tmp_path):
@@ -477,6 +477,17 @@ class _ArrayStore:
     def topk(self):
         return np.empty(0, np.int64), np.empty(0, np.float32)
 
+    def rows_of(self, clips):
+        return np.array([self._row[int(c)] for c in clips], np.int64)
+
+    def scores_at(self, rows):
+        return self._s[np.asarray(rows, np.int64)]
+
+    def rank_list(self, which, place):
+        sc = self._s[self._l[which]]
+        order = np.lexsort((np.asarray(place), -sc))
+        return np.asarray(place)[order], sc[order]
+
 
 @pytest.mark.parametrize("name", SCENARIOS + ORACLE_ONLY_SCENARIOS)
 def test_ticket_selection_reproduces_reference_rounds_on_recorded_scores(name):
@@ -504,12 +515,14 @@ def test_ticket_selection_reproduces_reference_rounds_on_recorded_scores(name):
         t = Ticket(job, "http://fake/", client=object(), schema=object(), store=store)
         t.target = types.SimpleNamespace(target_features={})
         t._weights = dict(zip(scn.streams, r["weights"]))
-        t._score_of = lambda clip, st=store: float(st._s[st.row_of(clip)])
         th, mx, near = r["select_args"]
         t.select_clips_to_review(th, mx, near)
         assert store.lists == (mx == float("inf"))
         assert list(t.matches.items()) == [(k, v) for k, v in r["selected"]]
         assert rng_digest() == r["rng_after_select"]
+        if mx == float("inf"):                               # report order: the reference's stable descending sort of the dict
+            want = sorted(t.matches.items(), key=lambda kv: kv[1], reverse=True)
+            assert t.ranked_selection() == want
 
 
 # ---------------------------------------------------------------------------- TargetClip (host logic)

@@ -118,6 +118,14 @@ def make_oracle_store_class():
         def scores(self):
             return self._scores32
 
+        def scores_at(self, global_rows):
+            return self._scores32[np.asarray(global_rows, np.int64) - self.first_global_row]
+
+        def rank_list(self, which, place):
+            _, scores = self._list(which)
+            order = np.lexsort((np.asarray(place), -scores.astype(np.float64)))
+            return np.asarray(place)[order], scores[order]
+
         def sims(self):
             return self._sims32
 
@@ -154,7 +162,6 @@ def cpu_product(monkeypatch):
     monkeypatch.setattr(ps, "FeatureStore", make_oracle_store_class())
     monkeypatch.setattr(ps, "loss_grid", lambda sims, labels, wg, tg, ballast, replicates=None, device=0:
                         sc.loss_grid(np.asarray(sims, np.float64), np.asarray(labels, bool), wg, tg, ballast)[None])
-    monkeypatch.setattr(pt.Ticket, "_score_of", lambda self, clip: float(self.feature_store().scores()[self.feature_store().row_of(clip)]))
     ps.invalidate()
     yield vq
     ps._REGISTRY.clear()

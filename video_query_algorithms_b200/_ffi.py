@@ -56,6 +56,13 @@ PROTOTYPES = {
     "vq_scan": (C.c_int, [_vp, _vp, _P(ScanParams), _P(ScanCounts)]),
     "vq_scan_select": (C.c_int, [_vp, _vp, _P(ScanParams), _P(ScanCounts), _i64p, _i64p, _f32p]),
     "vq_gather_list": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _vp]),
+    "vq_scan_multi": (C.c_int, [_vp, _i32, _vp, _P(ScanParams), _i32, _vp, _vp, _i32, _vp, _vp, _P(_i32)]),
+    "vq_fetch_scores_at": (C.c_int, [_vp, _i64, _vp, _vp]),
+    "vq_scan_phase_times": (C.c_int, [_vp, _i32, _vp, _vp, _P(_i32)]),
+    "vq_exchange_check": (C.c_int, [_vp]),
+    "vq_exchange_kernel_times": (C.c_int, [_vp, _i32, _vp, _P(_i32)]),
+    "vq_rank_list": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _vp]),
+    "vq_mt_sample_range": (C.c_int, [_vp, _P(_i32), _i64, _i64, _vp]),
     "vq_scan_enqueue": (C.c_int, [_vp, _vp, _P(ScanParams), _vp]),
     "vq_scan_wait": (C.c_int, [_vp, _vp, _P(ScanCounts)]),
     "vq_fetch_matches": (C.c_int, [_vp, _i64, _vp, _vp]),

@@ -27,6 +27,33 @@ def choices_range(rng, n, k, repeats=1):
     return idx if repeats == 1 else idx.reshape(repeats, k)
 
 
+NATIVE_SAMPLE_MIN = 64       # below this many picks Python's own loop is as fast as the state transfer
+
+
+def sample_range(rng, n, k):
+    """`rng.sample(range(n), k)` as an int64 array, leaving `rng` in the state the call would have left it in.
+    The review rounds draw a few dozen list positions; the finalize round has no size limit (compute_matches.py:78-84)
+    and the reference's `random.sample(M.items(), len(M))` is then a seeded permutation of every match — one
+    interpreter loop iteration per clip.  Large draws run in the library on the generator's state (vq_mt_sample_range,
+    csrc/vq_rng.cu); small ones, and generators that are not CPython's MT19937, take `rng.sample` itself."""
+    n, k = int(n), int(k)
+    if k < NATIVE_SAMPLE_MIN:
+        return np.asarray(rng.sample(range(n), k), dtype=np.int64)
+    version, internal, gauss_next = rng.getstate()
+    if version != 3 or len(internal) != 625:
+        return np.asarray(rng.sample(range(n), k), dtype=np.int64)
+    if not 0 <= k <= n:
+        raise ValueError("Sample larger than population or is negative")
+    import ctypes as C
+    from ._ffi import check, lib, ptr
+    state = np.asarray(internal[:624], dtype=np.uint32)
+    pos = C.c_int32(int(internal[624]))
+    out = np.empty(k, np.int64)
+    check(lib().vq_mt_sample_range(ptr(state), C.byref(pos), n, k, ptr(out)), "vq_mt_sample_range")
+    rng.setstate((version, tuple(state.tolist()) + (pos.value,), gauss_next))
+    return out
+
+
 def _cpython_set_table_size(n_unique):
     """Table size of a CPython set after inserting n_unique distinct keys one by one (setobject.c: resize when
     fill * 5 >= mask * 3, to the first power of two above used * 4, or used * 2 beyond 50000 keys)."""

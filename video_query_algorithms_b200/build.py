@@ -9,7 +9,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 LIB = os.path.join(PKG, "lib", "libvq_b200.so")
-SOURCES = ["vq_store.cu", "vq_scan.cu", "vq_labelled.cu", "vq_batch.cu", "vq_exchange.cu", "vq_ingest.cu", "vq_hostx.cu"]
+SOURCES = ["vq_store.cu", "vq_scan.cu", "vq_labelled.cu", "vq_batch.cu", "vq_exchange.cu", "vq_ingest.cu", "vq_hostx.cu", "vq_rng.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--expt-relaxed-constexpr"]
 

@@ -76,8 +76,13 @@ struct vq_store {
     int64_t *topk_rows = nullptr;    // [VQ_MAX_TOPK]
     int last_topk = 0;
     int64_t *pack = nullptr;         // [4 + 2*VQ_MAX_TOPK] counts | top-k rows | top-k score bits (allgather payload)
+    // an exchange kernel running on another stream reads `pack`: it records this event (created on first use, owned by the
+    // store) behind itself and the next select_compact waits for it before rewriting the payload (vq_exchange.cu)
+    cudaEvent_t pack_reader_done = nullptr;
+    bool pack_reader_pending = false;
 
-    cudaEvent_t ev_start[vq::kTimeRing], ev_stop[vq::kTimeRing];
+    cudaEvent_t ev_start[vq::kTimeRing], ev_stop[vq::kTimeRing];   // around K1
+    cudaEvent_t ev_sel_stop[vq::kTimeRing];                         // after K2c: ev_stop .. ev_sel_stop = the selection kernels
     bool ev_made = false;
     int ev_head = 0, ev_count = 0;
     void *pinned_stage = nullptr;    // small pinned buffer for targets / params
@@ -94,8 +99,22 @@ struct vq_store {
     int64_t h_rank_cap = 0;
     bool staged = false;             // the mirror holds all three lists + top-k of the last scan (vq_scan)
     bool staged_ties = false;        // ... at least the tie band + top-k (vq_scan, vq_scan_select)
-    void *h_gather = nullptr;        // pinned staging of vq_gather_list
+    void *h_gather = nullptr;        // pinned staging of vq_gather_list / vq_fetch_scores_at (grow-only)
+    int64_t h_gather_cap = 0;        // entries
+    // grow-only device + pinned scratch of the labelled path and of the list ranking (vq::scratch_reserve): no allocation per call once warm
+    char *lab_dev = nullptr;
+    size_t lab_dev_cap = 0;
+    char *lab_host = nullptr;
+    size_t lab_host_cap = 0;
     // scratch of the batched path (vq_batch.cu), allocated on its first call and kept: a batched scan allocates nothing
     void *batch_scratch = nullptr;
     void (*batch_scratch_free)(void *) = nullptr;
 };
+
+namespace vq {
+// Grow-only scratch owned by the store: one device block (s->lab_dev) and one pinned host block (s->lab_host).  With a
+// multi-gigabyte shard resident a cudaMalloc / cudaFree pair costs ~2 ms — more than the kernels of a revise round —
+// so nothing is allocated per call once the blocks are large enough; copies go through the pinned block on the store's
+// stream.  Calls on one store are serialised by contract (vq.h), so one block serves every user.
+int scratch_reserve(vq_store *s, size_t dev_bytes, size_t host_bytes);
+}  // namespace vq

@@ -10,6 +10,7 @@
 #include <chrono>
 #include <mutex>
 #include <stdlib.h>
+#include <string.h>
 
 #include "vq_internal.cuh"
 
@@ -135,7 +136,9 @@ __global__ void gram_kernel(const float *__restrict__ rows, const long long *__r
 
 // Block-cooperative LU with partial pivoting on A (n x n, row-major, in global scratch), applied
 // to nrhs right-hand sides B (n x nrhs, row-major).  On return B holds the solutions.
-__device__ void lu_solve(double *A, double *B, int n, int nrhs, int *piv_s) {
+// A zero (or non-finite) pivot — a duplicated labelled clip, more independent rows than dimensions — sets *singular:
+// numpy.linalg.inv raises LinAlgError for such a matrix (target_clip.py:194,248), the caller here turns the flag into an error.
+__device__ void lu_solve(double *A, double *B, int n, int nrhs, int *piv_s, int *singular) {
     for (int k = 0; k < n; ++k) {
         if (threadIdx.x == 0) {
             int p = k;
@@ -162,6 +165,7 @@ __device__ void lu_solve(double *A, double *B, int n, int nrhs, int *piv_s) {
         }
         __syncthreads();
         const double pivot = A[(size_t)k * n + k];
+        if (threadIdx.x == 0 && !(fabs(pivot) > 0.0 && fabs(pivot) < 1.0e300)) *singular = 1;
         for (int i = k + 1 + threadIdx.x; i < n; i += blockDim.x) A[(size_t)i * n + k] /= pivot;
         __syncthreads();
         const int rem = n - k - 1;
@@ -196,7 +200,7 @@ __device__ void lu_solve(double *A, double *B, int n, int nrhs, int *piv_s) {
 // Scratch per slot (doubles): Bm[n*n] | R[n*2] | Ky[m*m] | Z[m*(n+1)] | tmp[n+m]
 __global__ void __launch_bounds__(256)
 bootstrap_solve_kernel(const double *__restrict__ G, int n, int m, double mu, double *scratch,
-                       size_t scratch_per_slot, double *coef) {
+                       size_t scratch_per_slot, double *coef, int *singular) {
     __shared__ int piv_s;
     __shared__ double c_s;
     const int slot = blockIdx.x;
@@ -236,7 +240,7 @@ bootstrap_solve_kernel(const double *__restrict__ G, int n, int m, double mu, do
             Z[e] = v;
         }
         __syncthreads();
-        lu_solve(Ky, Z, m, n + 1, &piv_s);
+        lu_solve(Ky, Z, m, n + 1, &piv_s, singular);
     }
     // B = Gxx - Gxy (K Gyx);  R = [1 | Gxy gamma],  gamma = 1 - K Gyy 1
     for (int e = threadIdx.x; e < n * n; e += blockDim.x) {
@@ -254,7 +258,7 @@ bootstrap_solve_kernel(const double *__restrict__ G, int n, int m, double mu, do
         R[2 * i + 1] = v;
     }
     __syncthreads();
-    lu_solve(Bm, R, n, 2, &piv_s);                 // R[:,0] = beta, R[:,1] = delta
+    lu_solve(Bm, R, n, 2, &piv_s, singular);                 // R[:,0] = beta, R[:,1] = delta
     for (int i = threadIdx.x; i < n; i += blockDim.x) co[i] = R[2 * i] - c * R[2 * i + 1];
     for (int j = threadIdx.x; j < m; j += blockDim.x) {
         double v = 0.0;
@@ -288,12 +292,20 @@ __global__ void combine_kernel(const float *__restrict__ rows, const long long *
     out[i] = acc;
 }
 
-struct DevBuf {
-    void *p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 8); }
-    template <class T> T *as() { return reinterpret_cast<T *>(p); }
+using vq::scratch_reserve;
+static inline int lab_reserve(vq_store *s, size_t dev_bytes, size_t host_bytes) { return scratch_reserve(s, dev_bytes, host_bytes); }
+
+struct Carver {                                   // 256-byte aligned pieces of a block
+    char *base;
+    size_t off = 0;
+    explicit Carver(char *b) : base(b) {}
+    template <class T> T *take(size_t n) {
+        T *p = reinterpret_cast<T *>(base + off);
+        off += (n * sizeof(T) + 255) & ~(size_t)255;
+        return p;
+    }
 };
+inline size_t padded(size_t bytes) { return (bytes + 255) & ~(size_t)255; }
 
 int local_rows(const vq_store *s, const int64_t *rows, int64_t n, std::vector<long long> &out, const char *who) {
     out.resize((size_t)n);
@@ -313,24 +325,32 @@ extern "C" int vq_labelled_sims(vq_store *s, const double *target, const int64_t
                                 double *sims_out) {
     VQ_REQUIRE(s && target && (rows || n == 0) && (sims_out || n == 0), "vq_labelled_sims: null argument");
     if (n == 0) return 0;
-    std::vector<long long> loc;
-    if (int r = local_rows(s, rows, n, loc, "vq_labelled_sims")) return r;
     VQ_CUDA(cudaSetDevice(s->device));
-    DevBuf d_t, d_ids, d_out;
-    VQ_CUDA(d_t.alloc(s->row_floats * sizeof(double)));
-    VQ_CUDA(d_ids.alloc((size_t)n * sizeof(long long)));
-    VQ_CUDA(d_out.alloc((size_t)n * s->n_streams * sizeof(double)));
-    VQ_CUDA(cudaMemcpyAsync(d_t.p, target, s->row_floats * sizeof(double), cudaMemcpyHostToDevice, s->stream));
-    VQ_CUDA(cudaMemcpyAsync(d_ids.p, loc.data(), (size_t)n * sizeof(long long), cudaMemcpyHostToDevice, s->stream));
+    const size_t t_bytes = s->row_floats * sizeof(double), id_bytes = (size_t)n * sizeof(long long),
+                 out_bytes = (size_t)n * s->n_streams * sizeof(double);
+    const size_t total = padded(t_bytes) + padded(id_bytes) + padded(out_bytes);
+    if (int r = lab_reserve(s, total, total)) return r;
+    Carver h(s->lab_host), d(s->lab_dev);
+    double *h_t = h.take<double>(s->row_floats), *d_t = d.take<double>(s->row_floats);
+    long long *h_ids = h.take<long long>((size_t)n), *d_ids = d.take<long long>((size_t)n);
+    double *h_out = h.take<double>((size_t)n * s->n_streams), *d_out = d.take<double>((size_t)n * s->n_streams);
+    memcpy(h_t, target, t_bytes);
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t r = rows[i] - s->first_global_row;
+        VQ_REQUIRE(r >= 0 && r < s->n_rows, "vq_labelled_sims: global row %lld is not in this shard [%lld, %lld)",
+                   (long long)rows[i], (long long)s->first_global_row, (long long)(s->first_global_row + s->n_rows));
+        h_ids[i] = r;
+    }
+    // target and ids are adjacent in both blocks: one copy in
+    VQ_CUDA(cudaMemcpyAsync(d_t, h_t, padded(t_bytes) + id_bytes, cudaMemcpyHostToDevice, s->stream));
     const long long warps = n * s->n_streams;
     const int blocks = (int)((warps * 32 + 255) / 256);
-    labelled_sims_kernel<<<blocks, 256, 0, s->stream>>>(s->rows, d_t.as<double>(), d_ids.as<long long>(),
-                                                        s->inv_counts, n, s->n_streams, s->n_splits, s->dim,
-                                                        d_out.as<double>());
+    labelled_sims_kernel<<<blocks, 256, 0, s->stream>>>(s->rows, d_t, d_ids, s->inv_counts, n, s->n_streams, s->n_splits,
+                                                        s->dim, d_out);
     VQ_CUDA(cudaGetLastError());
-    VQ_CUDA(cudaMemcpyAsync(sims_out, d_out.p, (size_t)n * s->n_streams * sizeof(double), cudaMemcpyDeviceToHost,
-                            s->stream));
+    VQ_CUDA(cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, s->stream));
     VQ_CUDA(cudaStreamSynchronize(s->stream));
+    memcpy(sims_out, h_out, out_bytes);
     return 0;
 }
 
@@ -361,17 +381,20 @@ extern "C" int vq_loss_grid(int device, const double *sims, const uint8_t *label
     auto t_start = now();
     // One grow-only arena per device, kept for the life of the process: with a multi-gigabyte store resident, every
     // cudaMalloc / cudaFree costs ~2 ms, which was most of this call (8 of each per call before).
-    struct Arena { char *p = nullptr; size_t cap = 0; };
+    struct Arena { char *p = nullptr; size_t cap = 0; char *h = nullptr; size_t hcap = 0; cudaStream_t st = nullptr; };
     static Arena arenas[64];
     static std::mutex arena_mutex;
     std::lock_guard<std::mutex> lock(arena_mutex);
     VQ_REQUIRE(device >= 0 && device < 64, "vq_loss_grid: device %d", device);
+    // inputs back to back (one pinned block, one copy in), then the score table and the output grid
     const size_t sizes[8] = {(size_t)L * 2 * sizeof(double), (size_t)L, (size_t)n_w * sizeof(double), (size_t)n_th * sizeof(double),
                              (size_t)(R + 1) * sizeof(int), (size_t)n_idx * sizeof(int), (size_t)L * n_w * sizeof(double),
                              (size_t)R * n_w * n_th * sizeof(double)};
     size_t offs[8], total = 0;
     for (int i = 0; i < 8; ++i) { offs[i] = total; total += (sizes[i] + 255) & ~(size_t)255; }
+    const size_t in_bytes = offs[6], out_bytes = sizes[7];
     Arena &ar = arenas[device];
+    if (!ar.st) VQ_CUDA(cudaStreamCreateWithFlags(&ar.st, cudaStreamNonBlocking));
     if (total > ar.cap) {
         if (ar.p) cudaFree(ar.p);
         ar.p = nullptr;
@@ -380,28 +403,32 @@ extern "C" int vq_loss_grid(int device, const double *sims, const uint8_t *label
         VQ_CUDA(cudaMalloc((void **)&ar.p, want));
         ar.cap = want;
     }
+    const size_t host_need = in_bytes + out_bytes;
+    if (host_need > ar.hcap) {
+        if (ar.h) cudaFreeHost(ar.h);
+        ar.h = nullptr;
+        ar.hcap = 0;
+        const size_t want = host_need + host_need / 2;
+        VQ_CUDA(cudaMallocHost((void **)&ar.h, want));
+        ar.hcap = want;
+    }
     ArenaView d_sims{ar.p + offs[0]}, d_lab{ar.p + offs[1]}, d_w{ar.p + offs[2]}, d_th{ar.p + offs[3]}, d_off{ar.p + offs[4]},
         d_idx{ar.p + offs[5]}, d_tab{ar.p + offs[6]}, d_out{ar.p + offs[7]};
     if (timing) fprintf(stderr, "[vq_loss_grid] alloc %.2f ms\n", ms_since(t_start));
     t_start = now();
-    VQ_CUDA(cudaMemcpy(d_sims.p, sims, (size_t)L * 2 * sizeof(double), cudaMemcpyHostToDevice));
-    VQ_CUDA(cudaMemcpy(d_lab.p, labels, (size_t)L, cudaMemcpyHostToDevice));
-    VQ_CUDA(cudaMemcpy(d_w.p, weight_grid, (size_t)n_w * sizeof(double), cudaMemcpyHostToDevice));
-    VQ_CUDA(cudaMemcpy(d_th.p, threshold_grid, (size_t)n_th * sizeof(double), cudaMemcpyHostToDevice));
-    VQ_CUDA(cudaMemcpy(d_off.p, rep_offset, (size_t)(R + 1) * sizeof(int), cudaMemcpyHostToDevice));
-    VQ_CUDA(cudaMemcpy(d_idx.p, rep_index, (size_t)n_idx * sizeof(int), cudaMemcpyHostToDevice));
-    if (timing) fprintf(stderr, "[vq_loss_grid] h2d %.2f ms\n", ms_since(t_start));
-    t_start = now();
-    score_table_kernel<<<(unsigned int)((L * n_w + 255) / 256), 256>>>(d_sims.as<double>(), L, d_w.as<double>(),
-                                                                      n_w, d_tab.as<double>());
-    loss_grid_kernel<<<(unsigned int)(R * n_w), kLossThreads>>>(d_tab.as<double>(), d_lab.as<unsigned char>(), L,
-                                                               d_th.as<double>(), n_th, n_w, ballast,
-                                                               d_off.as<int>(), d_idx.as<int>(), d_out.as<double>());
+    const void *src[6] = {sims, labels, weight_grid, threshold_grid, rep_offset, rep_index};
+    for (int i = 0; i < 6; ++i) memcpy(ar.h + offs[i], src[i], sizes[i]);
+    VQ_CUDA(cudaMemcpyAsync(ar.p, ar.h, in_bytes, cudaMemcpyHostToDevice, ar.st));
+    score_table_kernel<<<(unsigned int)((L * n_w + 255) / 256), 256, 0, ar.st>>>(d_sims.as<double>(), L, d_w.as<double>(),
+                                                                                 n_w, d_tab.as<double>());
+    loss_grid_kernel<<<(unsigned int)(R * n_w), kLossThreads, 0, ar.st>>>(d_tab.as<double>(), d_lab.as<unsigned char>(), L,
+                                                                          d_th.as<double>(), n_th, n_w, ballast,
+                                                                          d_off.as<int>(), d_idx.as<int>(), d_out.as<double>());
     VQ_CUDA(cudaGetLastError());
-    if (timing) { cudaDeviceSynchronize(); fprintf(stderr, "[vq_loss_grid] kernels %.2f ms\n", ms_since(t_start)); }
-    t_start = now();
-    VQ_CUDA(cudaMemcpy(losses_out, d_out.p, (size_t)R * n_w * n_th * sizeof(double), cudaMemcpyDeviceToHost));
-    if (timing) fprintf(stderr, "[vq_loss_grid] d2h %.2f ms\n", ms_since(t_start));
+    VQ_CUDA(cudaMemcpyAsync(ar.h + in_bytes, d_out.p, out_bytes, cudaMemcpyDeviceToHost, ar.st));
+    VQ_CUDA(cudaStreamSynchronize(ar.st));
+    memcpy(losses_out, ar.h + in_bytes, out_bytes);
+    if (timing) fprintf(stderr, "[vq_loss_grid] copies + kernels %.2f ms\n", ms_since(t_start));
     return 0;
 }
 
@@ -422,23 +449,36 @@ extern "C" int vq_bootstrap_target(vq_store *s, const int64_t *valid_rows, int32
     }
     VQ_CUDA(cudaSetDevice(s->device));
     const size_t per_slot = (size_t)n * n + (size_t)n * 2 + (size_t)m * m + (size_t)m * (n + 1) + (size_t)nz + 8;
-    DevBuf d_ids, d_G, d_scr, d_coef, d_out;
-    VQ_CUDA(d_ids.alloc((size_t)nz * sizeof(long long)));
-    VQ_CUDA(d_G.alloc((size_t)n_slots * nz * nz * sizeof(double)));
-    VQ_CUDA(d_scr.alloc((size_t)n_slots * per_slot * sizeof(double)));
-    VQ_CUDA(d_coef.alloc((size_t)n_slots * nz * sizeof(double)));
-    VQ_CUDA(d_out.alloc((size_t)n_slots * s->dim * sizeof(double)));
-    VQ_CUDA(cudaMemcpyAsync(d_ids.p, loc.data(), (size_t)nz * sizeof(long long), cudaMemcpyHostToDevice, s->stream));
+    const size_t out_doubles = (size_t)n_slots * s->dim;
+    const size_t dev_total = padded((size_t)nz * 8) + padded(16) + padded((size_t)n_slots * nz * nz * 8) +
+                             padded((size_t)n_slots * per_slot * 8) + padded((size_t)n_slots * nz * 8) + padded(out_doubles * 8);
+    const size_t host_total = padded((size_t)nz * 8) + padded(16) + padded(out_doubles * 8);
+    if (int r = lab_reserve(s, dev_total, host_total)) return r;
+    Carver d(s->lab_dev), h(s->lab_host);
+    long long *d_ids = d.take<long long>((size_t)nz), *h_ids = h.take<long long>((size_t)nz);
+    int *d_flag = d.take<int>(4), *h_flag = h.take<int>(4);
+    double *d_G = d.take<double>((size_t)n_slots * nz * nz);
+    double *d_scr = d.take<double>((size_t)n_slots * per_slot);
+    double *d_coef = d.take<double>((size_t)n_slots * nz);
+    double *d_out = d.take<double>(out_doubles), *h_out = h.take<double>(out_doubles);
+    memcpy(h_ids, loc.data(), (size_t)nz * sizeof(long long));
+    h_flag[0] = 0;
+    VQ_CUDA(cudaMemcpyAsync(d_ids, h_ids, padded((size_t)nz * 8) + sizeof(int), cudaMemcpyHostToDevice, s->stream));   // ids + cleared flag
     const long long warps = (long long)nz * nz * n_slots;
-    gram_kernel<<<(unsigned int)((warps * 32 + 255) / 256), 256, 0, s->stream>>>(
-        s->rows, d_ids.as<long long>(), nz, n_slots, s->dim, s->row_floats, d_G.as<double>());
-    bootstrap_solve_kernel<<<n_slots, 256, 0, s->stream>>>(d_G.as<double>(), n, m, mu, d_scr.as<double>(), per_slot,
-                                                           d_coef.as<double>());
-    combine_kernel<<<(n_slots * s->dim + 255) / 256, 256, 0, s->stream>>>(
-        s->rows, d_ids.as<long long>(), nz, n_slots, s->dim, s->row_floats, d_coef.as<double>(), d_out.as<double>());
+    gram_kernel<<<(unsigned int)((warps * 32 + 255) / 256), 256, 0, s->stream>>>(s->rows, d_ids, nz, n_slots, s->dim,
+                                                                               s->row_floats, d_G);
+    bootstrap_solve_kernel<<<n_slots, 256, 0, s->stream>>>(d_G, n, m, mu, d_scr, per_slot, d_coef, d_flag);
+    combine_kernel<<<(n_slots * s->dim + 255) / 256, 256, 0, s->stream>>>(s->rows, d_ids, nz, n_slots, s->dim, s->row_floats,
+                                                                         d_coef, d_out);
     VQ_CUDA(cudaGetLastError());
-    VQ_CUDA(cudaMemcpyAsync(target_out, d_out.p, (size_t)n_slots * s->dim * sizeof(double), cudaMemcpyDeviceToHost,
-                            s->stream));
+    VQ_CUDA(cudaMemcpyAsync(h_out, d_out, out_doubles * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    VQ_CUDA(cudaMemcpyAsync(h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     VQ_CUDA(cudaStreamSynchronize(s->stream));
+    VQ_REQUIRE(h_flag[0] == 0, "vq_bootstrap_target: singular system (a labelled clip appears twice, or the labelled rows are "
+               "linearly dependent): numpy.linalg.inv raises LinAlgError here (target_clip.py:194,248)");
+    for (size_t i = 0; i < out_doubles; ++i)
+        VQ_REQUIRE(h_out[i] == h_out[i] && h_out[i] - h_out[i] == 0.0, "vq_bootstrap_target: the solve produced a non-finite target "
+                   "(ill-conditioned labelled set)");
+    memcpy(target_out, h_out, out_doubles * sizeof(double));
     return 0;
 }

@@ -657,12 +657,17 @@ extern "C" int vq_scan_enqueue(vq_store *s, const float *target_dev, const vq_sc
                                              (long long *)s->counts, s->hist, s->cand_count, s->cand_keys,
                                              s->cand_cap, a.topk, s->first_global_row, s->topk_scores,
                                              (long long *)s->topk_rows);
+    if (s->pack_reader_pending) {                      // an exchange kernel on another stream may still be reading the payload
+        VQ_CUDA(cudaStreamWaitEvent(st, s->pack_reader_done, 0));
+        s->pack_reader_pending = false;
+    }
     select_compact<<<sel_blocks, kSelThreads, 0, st>>>(
         s->scores, s->n_rows, a, s->chunk_offsets, sel_chunks, s->list_rows[0], s->list_scores[0],
         s->list_rows[1], s->list_scores[1], s->list_rows[2], s->list_scores[2], (const long long *)s->counts,
         s->topk_scores, (const long long *)s->topk_rows, (long long *)s->pack,
         reinterpret_cast<const unsigned long long *>(s->hist + kHistBins + 2), reinterpret_cast<long long *>(s->hist + kHistBins + 4));
     VQ_CUDA(cudaGetLastError());
+    VQ_CUDA(cudaEventRecord(s->ev_sel_stop[slot], st));
     return 0;
 }
 
@@ -702,7 +707,7 @@ static int grow_mirror(vq_store *s, int which, int64_t need) {
     return 0;
 }
 
-static int publish(vq_store *s, int lists) {
+static int publish_launch(vq_store *s, int lists) {
     if (!s->h_topk_rows) {
         VQ_CUDA(cudaMallocHost((void **)&s->h_topk_rows, VQ_MAX_TOPK * sizeof(int64_t)));
         VQ_CUDA(cudaMallocHost((void **)&s->h_topk_scores, VQ_MAX_TOPK * sizeof(float)));
@@ -728,11 +733,19 @@ static int publish(vq_store *s, int lists) {
     a.lists = lists;
     publish_results<<<lists ? s->sm_count : 8, 256, 0, s->stream>>>(a);
     VQ_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static int publish(vq_store *s, int lists) {
+    if (int r = publish_launch(s, lists)) return r;
     VQ_CUDA(cudaStreamSynchronize(s->stream));
     return 0;
 }
 
-static int scan_host(vq_store *s, const float *target, const vq_scan_params *p, vq_scan_counts *out, int lists, const char *who) {
+// vq_scan / vq_scan_select / vq_scan_multi in two halves: everything that is enqueued (target copy, K1, K2, publish) and
+// everything that waits (one stream synchronisation, then host bookkeeping), so that a caller holding several shards
+// can enqueue on all of them before it waits on any.
+static int scan_host_begin(vq_store *s, const float *target, const vq_scan_params *p, int lists, const char *who) {
     VQ_REQUIRE(s && target, "%s: null argument", who);
     VQ_CUDA(cudaSetDevice(s->device));
     const size_t bytes = s->row_floats * sizeof(float);
@@ -744,7 +757,12 @@ static int scan_host(vq_store *s, const float *target, const vq_scan_params *p, 
     for (int i = lists ? 0 : 2; i < 3; ++i)
         if (s->h_cap[i] == 0)
             if (int r = grow_mirror(s, i, lists ? first_cap : 65536)) return r;
-    if (int r = publish(s, lists)) return r;
+    return publish_launch(s, lists);
+}
+
+static int scan_host_finish(vq_store *s, vq_scan_counts *out, int lists) {
+    VQ_CUDA(cudaSetDevice(s->device));
+    VQ_CUDA(cudaStreamSynchronize(s->stream));
     if (s->h_result[4]) {                                  // a list outgrew its mirror: grow, publish again
         for (int i = lists ? 0 : 2; i < 3; ++i)
             if (int r = grow_mirror(s, i, s->h_result[i])) return r;
@@ -768,6 +786,11 @@ static int scan_host(vq_store *s, const float *target, const vq_scan_params *p, 
     return 0;
 }
 
+static int scan_host(vq_store *s, const float *target, const vq_scan_params *p, vq_scan_counts *out, int lists, const char *who) {
+    if (int r = scan_host_begin(s, target, p, lists, who)) return r;
+    return scan_host_finish(s, out, lists);
+}
+
 extern "C" int vq_scan(vq_store *s, const float *target, const vq_scan_params *p, vq_scan_counts *out) {
     return scan_host(s, target, p, out, 1, "vq_scan");
 }
@@ -780,6 +803,60 @@ extern "C" int vq_scan_select(vq_store *s, const float *target, const vq_scan_pa
     if (near_best_score) {
         const uint32_t bits = (uint32_t)s->h_result[6];
         memcpy(near_best_score, &bits, sizeof(float));
+    }
+    return 0;
+}
+
+// The broker's arrangement (reference src/broker.py:62-92: ONE process, one job at a time): a search set sharded over the
+// GPUs of the box is scanned by one call from one thread — the target copy, K1, K2 and the publish kernel are enqueued on
+// every shard's own stream first, then each stream is waited for once.  The per-shard top-k lists (ranked, in the pinned
+// mirrors) are merged here into the search set's top-k; counts and the best near miss come back per shard because list
+// positions are per shard (the shards' lists, in shard order, ARE the search set's lists in database order).
+extern "C" int vq_scan_multi(vq_store *const *shards, int32_t n_shards, const float *target, const vq_scan_params *p,
+                             int32_t lists, vq_scan_counts *counts_out, int64_t *near_best_out, int32_t topk_cap,
+                             int64_t *topk_rows_out, float *topk_scores_out, int32_t *n_topk_out) {
+    VQ_REQUIRE(shards && n_shards >= 1 && target && p && counts_out, "vq_scan_multi: null argument");
+    for (int i = 0; i < n_shards; ++i) VQ_REQUIRE(shards[i], "vq_scan_multi: shard %d is null", i);
+    for (int i = 0; i < n_shards; ++i)
+        if (int r = scan_host_begin(shards[i], target, p, lists, "vq_scan_multi")) {
+            for (int j = 0; j < i; ++j) {                    // leave no stream busy behind an error
+                cudaSetDevice(shards[j]->device);
+                cudaStreamSynchronize(shards[j]->stream);
+            }
+            return r;
+        }
+    int rc = 0;
+    for (int i = 0; i < n_shards; ++i)
+        if (int r = scan_host_finish(shards[i], &counts_out[i], lists)) rc = rc ? rc : r;
+    if (rc) return rc;
+    if (near_best_out)
+        for (int i = 0; i < n_shards; ++i) {
+            near_best_out[3 * i] = shards[i]->h_result[7];         // position in the shard's near-miss list
+            near_best_out[3 * i + 1] = shards[i]->h_result[5];     // global row, -1 = none
+            near_best_out[3 * i + 2] = shards[i]->h_result[6];     // score bits
+        }
+    if (n_topk_out) {
+        // k-way merge of the shards' ranked lists under (score descending, global row ascending)
+        VQ_REQUIRE(topk_rows_out && topk_scores_out && topk_cap >= 0, "vq_scan_multi: null top-k output");
+        std::vector<int> head((size_t)n_shards, 0);
+        int n = 0;
+        const int want = p->topk < topk_cap ? p->topk : topk_cap;
+        for (; n < want; ++n) {
+            int best = -1;
+            for (int i = 0; i < n_shards; ++i) {
+                const int h = head[(size_t)i];
+                if (h >= (int)shards[i]->counts_host[3]) continue;
+                if (best < 0) { best = i; continue; }
+                const int hb = head[(size_t)best];
+                const float sa = shards[i]->h_topk_scores[h], sb = shards[best]->h_topk_scores[hb];
+                if (sa > sb || (sa == sb && shards[i]->h_topk_rows[h] < shards[best]->h_topk_rows[hb])) best = i;
+            }
+            if (best < 0) break;
+            const int h = head[(size_t)best]++;
+            topk_rows_out[n] = shards[best]->h_topk_rows[h];
+            topk_scores_out[n] = shards[best]->h_topk_scores[h];
+        }
+        *n_topk_out = n;
     }
     return 0;
 }
@@ -797,29 +874,71 @@ __global__ void gather_list(const unsigned int *__restrict__ rows, const float *
 }
 }  // namespace
 
+static int grow_gather(vq_store *s, int64_t n) {
+    if (n <= s->h_gather_cap) return 0;
+    if (s->h_gather) cudaFreeHost(s->h_gather);
+    s->h_gather = nullptr;
+    s->h_gather_cap = 0;
+    const int64_t cap = n + n / 2 + 4096;
+    VQ_CUDA(cudaMallocHost((void **)&s->h_gather, (size_t)cap * (8 + 8 + 4)));
+    s->h_gather_cap = cap;
+    return 0;
+}
+
 extern "C" int vq_gather_list(vq_store *s, int32_t which, int64_t n_idx, const int64_t *positions, int64_t *rows_out,
                               float *scores_out) {
     VQ_REQUIRE(s && (n_idx == 0 || (positions && rows_out && scores_out)), "vq_gather_list: null argument");
     VQ_REQUIRE(which >= 0 && which <= 2, "vq_gather_list: list %d outside 0..2 (matches, near misses, ties)", which);
+    VQ_REQUIRE(n_idx >= 0 && n_idx < (1ll << 31), "vq_gather_list: %lld positions", (long long)n_idx);
+    if (n_idx == 0) return 0;
     VQ_CUDA(cudaSetDevice(s->device));
     const int64_t n_list = s->counts_host[which];
+    // one round trip whatever the number of positions: the pinned staging is device-mapped, the kernel reads the
+    // positions from it and writes rows / scores into it; a position outside the list comes back as row -1
+    if (int r = grow_gather(s, n_idx)) return r;
+    long long *h_pos = (long long *)s->h_gather, *h_rows = h_pos + s->h_gather_cap;
+    float *h_sc = (float *)(h_rows + s->h_gather_cap);
+    memcpy(h_pos, positions, (size_t)n_idx * sizeof(int64_t));
+    gather_list<<<(unsigned int)((n_idx + 255) / 256), 256, 0, s->stream>>>(s->list_rows[which], s->list_scores[which], n_list,
+                                                                        h_pos, (int)n_idx, s->first_global_row, h_rows, h_sc);
+    VQ_CUDA(cudaGetLastError());
+    VQ_CUDA(cudaStreamSynchronize(s->stream));
     for (int64_t i = 0; i < n_idx; ++i)
-        VQ_REQUIRE(positions[i] >= 0 && positions[i] < n_list, "vq_gather_list: position %lld outside the list of %lld entries",
+        VQ_REQUIRE(h_rows[i] >= 0, "vq_gather_list: position %lld outside the list of %lld entries",
                    (long long)positions[i], (long long)n_list);
-    constexpr int kStep = 4096;                         // entries per round trip; the staging is pinned and device-mapped
-    if (!s->h_gather) VQ_CUDA(cudaMallocHost((void **)&s->h_gather, (size_t)kStep * (8 + 8 + 4)));
-    long long *h_pos = (long long *)s->h_gather, *h_rows = h_pos + kStep;
-    float *h_sc = (float *)(h_rows + kStep);
-    for (int64_t base = 0; base < n_idx; base += kStep) {
-        const int n = (int)(n_idx - base < kStep ? n_idx - base : kStep);
-        memcpy(h_pos, positions + base, (size_t)n * sizeof(int64_t));
-        gather_list<<<(n + 255) / 256, 256, 0, s->stream>>>(s->list_rows[which], s->list_scores[which], n_list, h_pos, n,
-                                                            s->first_global_row, h_rows, h_sc);
-        VQ_CUDA(cudaGetLastError());
-        VQ_CUDA(cudaStreamSynchronize(s->stream));
-        memcpy(rows_out + base, h_rows, (size_t)n * sizeof(int64_t));
-        memcpy(scores_out + base, h_sc, (size_t)n * sizeof(float));
-    }
+    memcpy(rows_out, h_rows, (size_t)n_idx * sizeof(int64_t));
+    memcpy(scores_out, h_sc, (size_t)n_idx * sizeof(float));
+    return 0;
+}
+
+namespace {
+__global__ void gather_scores(const float *__restrict__ scores, long long n_rows, const long long *__restrict__ rows, int n,
+                              float *out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long long r = rows[i];
+    out[i] = (r >= 0 && r < n_rows) ? scores[r] : __int_as_float(0x7fc00000);
+}
+}  // namespace
+
+// Scores of the last scan at arbitrary LOCAL rows, one round trip (the forced clips of ticket.py:346-356: the reference
+// clip and every user-confirmed clip — thousands on a finalize round with many labels).
+extern "C" int vq_fetch_scores_at(vq_store *s, int64_t n, const int64_t *local_rows, float *scores_out) {
+    VQ_REQUIRE(s && (n == 0 || (local_rows && scores_out)), "vq_fetch_scores_at: null argument");
+    VQ_REQUIRE(n >= 0 && n < (1ll << 31), "vq_fetch_scores_at: %lld rows", (long long)n);
+    if (n == 0) return 0;
+    for (int64_t i = 0; i < n; ++i)
+        VQ_REQUIRE(local_rows[i] >= 0 && local_rows[i] < s->n_rows, "vq_fetch_scores_at: row %lld outside the shard of %lld rows",
+                   (long long)local_rows[i], (long long)s->n_rows);
+    VQ_CUDA(cudaSetDevice(s->device));
+    if (int r = grow_gather(s, n)) return r;
+    long long *h_rows = (long long *)s->h_gather;
+    float *h_sc = (float *)(h_rows + 2 * s->h_gather_cap);
+    memcpy(h_rows, local_rows, (size_t)n * sizeof(int64_t));
+    gather_scores<<<(unsigned int)((n + 255) / 256), 256, 0, s->stream>>>(s->scores, s->n_rows, h_rows, (int)n, h_sc);
+    VQ_CUDA(cudaGetLastError());
+    VQ_CUDA(cudaStreamSynchronize(s->stream));
+    memcpy(scores_out, h_sc, (size_t)n * sizeof(float));
     return 0;
 }
 
@@ -964,18 +1083,13 @@ __global__ void rank_unpack(const unsigned long long *__restrict__ keys, long lo
 
 }  // namespace
 
-extern "C" int vq_fetch_ranked(vq_store *s, int32_t which, int64_t cap, int64_t *rows_out, float *scores_out) {
-    VQ_REQUIRE(s && rows_out && scores_out, "vq_fetch_ranked: null argument");
-    VQ_REQUIRE(which == 0 || which == 1, "vq_fetch_ranked: list %d (0 = matches, 1 = near misses)", which);
-    VQ_CUDA(cudaSetDevice(s->device));
-    const int64_t n = s->counts_host[which];
-    VQ_REQUIRE(cap >= n, "vq_fetch_ranked: capacity %lld < %lld entries", (long long)cap, (long long)n);
-    if (n == 0) return 0;
-    VQ_REQUIRE(n <= s->cand_cap, "vq_fetch_ranked: list longer than the key scratch");
+// keys of list `which` in s->cand_keys, sorted descending (n <= cand_cap); second key word = rows (database order among
+// equal scores) or a caller-supplied tie-break per list entry
+static int rank_sort_list(vq_store *s, int which, int64_t n, const unsigned int *second_dev) {
     cudaStream_t st = s->stream;
     unsigned long long *keys = s->cand_keys;           // free between scans (the top-k pass has consumed it)
     const unsigned int nb = (unsigned int)((n + 255) / 256);
-    rank_make_keys<<<nb, 256, 0, st>>>(s->list_rows[which], s->list_scores[which], n, keys);
+    rank_make_keys<<<nb, 256, 0, st>>>(second_dev ? second_dev : s->list_rows[which], s->list_scores[which], n, keys);
     const unsigned int tiles = (unsigned int)((n + kSortTile - 1) / kSortTile);
     rank_sort_tile<<<tiles, kSortTile / 2, 0, st>>>(keys, n, true);
     long long P = kSortTile;
@@ -987,22 +1101,70 @@ extern "C" int vq_fetch_ranked(vq_store *s, int32_t which, int64_t cap, int64_t 
             rank_sort_step<<<pairs_blocks, 256, 0, st>>>(keys, n, size, stride, false);
         rank_sort_tile<<<tiles, kSortTile / 2, 0, st>>>(keys, n, false);
     }
-    // unpack into device-visible pinned staging (its own: the scan's host mirror keeps the database-order lists)
-    if (n > s->h_rank_cap) {
-        if (s->h_rank_rows) cudaFreeHost(s->h_rank_rows);
-        if (s->h_rank_scores) cudaFreeHost(s->h_rank_scores);
-        s->h_rank_rows = nullptr;
-        s->h_rank_scores = nullptr;
-        s->h_rank_cap = 0;
-        const int64_t c = n + n / 4 + 1024;
-        VQ_CUDA(cudaMallocHost((void **)&s->h_rank_rows, (size_t)c * sizeof(int64_t)));
-        VQ_CUDA(cudaMallocHost((void **)&s->h_rank_scores, (size_t)c * sizeof(float)));
-        s->h_rank_cap = c;
-    }
-    rank_unpack<<<nb, 256, 0, st>>>(keys, n, s->first_global_row, (long long *)s->h_rank_rows, s->h_rank_scores);
     VQ_CUDA(cudaGetLastError());
-    VQ_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+static int grow_rank_staging(vq_store *s, int64_t n) {
+    if (n <= s->h_rank_cap) return 0;
+    if (s->h_rank_rows) cudaFreeHost(s->h_rank_rows);
+    if (s->h_rank_scores) cudaFreeHost(s->h_rank_scores);
+    s->h_rank_rows = nullptr;
+    s->h_rank_scores = nullptr;
+    s->h_rank_cap = 0;
+    const int64_t c = n + n / 4 + 1024;
+    VQ_CUDA(cudaMallocHost((void **)&s->h_rank_rows, (size_t)c * sizeof(int64_t)));
+    VQ_CUDA(cudaMallocHost((void **)&s->h_rank_scores, (size_t)c * sizeof(float)));
+    s->h_rank_cap = c;
+    return 0;
+}
+
+extern "C" int vq_fetch_ranked(vq_store *s, int32_t which, int64_t cap, int64_t *rows_out, float *scores_out) {
+    VQ_REQUIRE(s && rows_out && scores_out, "vq_fetch_ranked: null argument");
+    VQ_REQUIRE(which == 0 || which == 1, "vq_fetch_ranked: list %d (0 = matches, 1 = near misses)", which);
+    VQ_CUDA(cudaSetDevice(s->device));
+    const int64_t n = s->counts_host[which];
+    VQ_REQUIRE(cap >= n, "vq_fetch_ranked: capacity %lld < %lld entries", (long long)cap, (long long)n);
+    if (n == 0) return 0;
+    VQ_REQUIRE(n <= s->cand_cap, "vq_fetch_ranked: list longer than the key scratch");
+    if (int r = rank_sort_list(s, which, n, nullptr)) return r;
+    // unpack into device-visible pinned staging (its own: the scan's host mirror keeps the database-order lists)
+    if (int r = grow_rank_staging(s, n)) return r;
+    rank_unpack<<<(unsigned int)((n + 255) / 256), 256, 0, s->stream>>>(s->cand_keys, n, s->first_global_row,
+                                                                      (long long *)s->h_rank_rows, s->h_rank_scores);
+    VQ_CUDA(cudaGetLastError());
+    VQ_CUDA(cudaStreamSynchronize(s->stream));
     memcpy(rows_out, s->h_rank_rows, (size_t)n * sizeof(int64_t));
+    memcpy(scores_out, s->h_rank_scores, (size_t)n * sizeof(float));
+    return 0;
+}
+
+// The report order of ticket.py:266 is a STABLE descending sort of the selected clips in the order the selection put
+// them into its dict — for the finalize round a seeded permutation of the lists (ticket.py:333,341) — so equal scores
+// keep the selection's order, not the database's.  The caller passes each list entry's rank in that order as the
+// tie-break; the list is sorted on the device by (score descending, tie-break ascending) and the tie-breaks come back
+// in report order (they identify the entries), with the scores beside them.
+extern "C" int vq_rank_list(vq_store *s, int32_t which, int64_t n, const uint32_t *tiebreak, uint32_t *tiebreak_out,
+                            float *scores_out) {
+    VQ_REQUIRE(s && (n == 0 || (tiebreak && tiebreak_out && scores_out)), "vq_rank_list: null argument");
+    VQ_REQUIRE(which == 0 || which == 1, "vq_rank_list: list %d (0 = matches, 1 = near misses)", which);
+    VQ_REQUIRE(n == s->counts_host[which], "vq_rank_list: %lld tie-breaks for a list of %lld entries", (long long)n,
+               (long long)s->counts_host[which]);
+    if (n == 0) return 0;
+    VQ_REQUIRE(n <= s->cand_cap, "vq_rank_list: list longer than the key scratch");
+    VQ_CUDA(cudaSetDevice(s->device));
+    const size_t bytes = (size_t)n * sizeof(uint32_t);
+    if (int r = vq::scratch_reserve(s, bytes, bytes)) return r;
+    if (int r = grow_rank_staging(s, n)) return r;
+    memcpy(s->lab_host, tiebreak, bytes);
+    VQ_CUDA(cudaMemcpyAsync(s->lab_dev, s->lab_host, bytes, cudaMemcpyHostToDevice, s->stream));
+    if (int r = rank_sort_list(s, which, n, reinterpret_cast<const unsigned int *>(s->lab_dev))) return r;
+    // rank_unpack with first_global_row = 0 hands the second key word back as an int64
+    rank_unpack<<<(unsigned int)((n + 255) / 256), 256, 0, s->stream>>>(s->cand_keys, n, 0, (long long *)s->h_rank_rows,
+                                                                      s->h_rank_scores);
+    VQ_CUDA(cudaGetLastError());
+    VQ_CUDA(cudaStreamSynchronize(s->stream));
+    for (int64_t i = 0; i < n; ++i) tiebreak_out[i] = (uint32_t)s->h_rank_rows[i];
     memcpy(scores_out, s->h_rank_scores, (size_t)n * sizeof(float));
     return 0;
 }
@@ -1061,20 +1223,34 @@ extern "C" int vq_merge_payloads_enqueue(int device, const int64_t *gathered_dev
     return 0;
 }
 
-extern "C" int vq_scan_kernel_times(vq_store *s, int32_t cap, float *ms_out, int32_t *n_out) {
-    VQ_REQUIRE(s && n_out, "vq_scan_kernel_times: null argument");
+static int phase_times(vq_store *s, int phase, int32_t cap, float *ms_out, int32_t *n_out, bool reset) {
     VQ_CUDA(cudaSetDevice(s->device));
     int n = s->ev_count < cap ? s->ev_count : cap;
     int got = 0;
     for (int i = 0; i < n; ++i) {
         const int slot = (s->ev_head + vq::kTimeRing - n + i) % vq::kTimeRing;
         float ms = 0.f;
-        cudaError_t e = cudaEventElapsedTime(&ms, s->ev_start[slot], s->ev_stop[slot]);
+        cudaError_t e = phase == 0 ? cudaEventElapsedTime(&ms, s->ev_start[slot], s->ev_stop[slot])
+                                   : cudaEventElapsedTime(&ms, s->ev_stop[slot], s->ev_sel_stop[slot]);
         if (e == cudaSuccess && ms_out) ms_out[got++] = ms;
     }
     cudaGetLastError();
     *n_out = got;
-    s->ev_count = 0;
+    if (reset) s->ev_count = 0;
+    return 0;
+}
+
+extern "C" int vq_scan_kernel_times(vq_store *s, int32_t cap, float *ms_out, int32_t *n_out) {
+    VQ_REQUIRE(s && n_out, "vq_scan_kernel_times: null argument");
+    return phase_times(s, 0, cap, ms_out, n_out, true);
+}
+
+extern "C" int vq_scan_phase_times(vq_store *s, int32_t cap, float *scan_ms_out, float *select_ms_out, int32_t *n_out) {
+    VQ_REQUIRE(s && n_out, "vq_scan_phase_times: null argument");
+    int32_t n0 = 0, n1 = 0;
+    if (int r = phase_times(s, 0, cap, scan_ms_out, &n0, false)) return r;
+    if (int r = phase_times(s, 1, cap, select_ms_out, &n1, true)) return r;
+    *n_out = n0 < n1 ? n0 : n1;
     return 0;
 }
 

@@ -16,6 +16,26 @@ void set_error(const char *fmt, ...) {
 }
 }  // namespace vq
 
+int vq::scratch_reserve(vq_store *s, size_t dev_bytes, size_t host_bytes) {
+    if (dev_bytes > s->lab_dev_cap) {
+        if (s->lab_dev) cudaFree(s->lab_dev);
+        s->lab_dev = nullptr;
+        s->lab_dev_cap = 0;
+        const size_t want = dev_bytes + dev_bytes / 2 + 4096;
+        VQ_CUDA(cudaMalloc((void **)&s->lab_dev, want));
+        s->lab_dev_cap = want;
+    }
+    if (host_bytes > s->lab_host_cap) {
+        if (s->lab_host) cudaFreeHost(s->lab_host);
+        s->lab_host = nullptr;
+        s->lab_host_cap = 0;
+        const size_t want = host_bytes + host_bytes / 2 + 4096;
+        VQ_CUDA(cudaMallocHost((void **)&s->lab_host, want));
+        s->lab_host_cap = want;
+    }
+    return 0;
+}
+
 extern "C" const char *vq_last_error(void) { return vq::g_err; }
 extern "C" int vq_abi_version(void) { return VQ_ABI_VERSION; }
 
@@ -64,6 +84,8 @@ static void store_free(vq_store *s) {
     s->batch_scratch = nullptr;
     if (s->h_result) cudaFreeHost(s->h_result);
     if (s->h_gather) cudaFreeHost(s->h_gather);
+    if (s->lab_dev) cudaFree(s->lab_dev);
+    if (s->lab_host) cudaFreeHost(s->lab_host);
     if (s->h_rank_rows) cudaFreeHost(s->h_rank_rows);
     if (s->h_rank_scores) cudaFreeHost(s->h_rank_scores);
     if (s->h_topk_rows) cudaFreeHost(s->h_topk_rows);
@@ -72,7 +94,9 @@ static void store_free(vq_store *s) {
         for (int i = 0; i < vq::kTimeRing; ++i) {
             cudaEventDestroy(s->ev_start[i]);
             cudaEventDestroy(s->ev_stop[i]);
+            cudaEventDestroy(s->ev_sel_stop[i]);
         }
+    if (s->pack_reader_done) cudaEventDestroy(s->pack_reader_done);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -167,6 +191,7 @@ extern "C" int vq_store_create(vq_store **out, int device, int64_t n_rows, int n
     for (int i = 0; i < vq::kTimeRing; ++i) {
         cudaEventCreate(&s->ev_start[i]);
         cudaEventCreate(&s->ev_stop[i]);
+        cudaEventCreate(&s->ev_sel_stop[i]);
     }
     s->ev_made = true;
     cudaMemsetAsync(s->counts, 0, 8 * sizeof(int64_t), s->stream);

@@ -249,6 +249,8 @@ class FeatureStore:
     def set_present(self, present):
         """present: bool [N, S, P]; slots that are False must have been uploaded as zeros."""
         present = np.asarray(present, dtype=bool)
+        self._present_version = getattr(self, "_present_version", 0) + 1
+        self._eff_key = None                                    # the device table is rewritten below: no target-specific one is loaded
         if present.all():
             self.present = None
             for sh in self.shards:
@@ -256,6 +258,7 @@ class FeatureStore:
             return
         self.present = present
         self._apply_split_weights(present.sum(axis=2))
+        self._eff_key = (np.ones(self.row_shape[:2], bool).tobytes(), self._present_version)
 
     def _apply_split_weights(self, counts):
         if (counts == 0).any():
@@ -292,10 +295,11 @@ class FeatureStore:
             self.clip_ids = np.concatenate([self.clip_ids, new_ids])
             self._row_of = None
             self._row_memo = {}
+        self._eff_key = None                                    # the library drops the per-row split weights on an append
+        self._present_version = getattr(self, "_present_version", 0) + 1
         if self.present is not None or present is not None:
             old = self.present if self.present is not None else np.ones((self.n_rows - n_new,) + self.row_shape[:2], bool)
             new = np.ones((n_new,) + self.row_shape[:2], bool) if present is None else np.asarray(present, dtype=bool)
-            self._eff_key = None
             self.set_present(np.concatenate([old, new]))
         self.last = None
 
@@ -356,14 +360,20 @@ class FeatureStore:
         return T, have
 
     def _sync_split_weights_for_target(self, have):
-        """The reference averages over splits that BOTH the target and the clip have."""
+        """The reference averages over splits that BOTH the target and the clip have (ticket.py:146-160), so the per-row
+        1/n_splits table on the device depends on the target of the job at hand.  The store is shared by all jobs of a
+        search set: what an earlier job uploaded is replaced — or dropped, when this target and every clip have every
+        split — before anything is scanned.  `_eff_key` names what the device holds (None = the default 1/n_splits)."""
         if have.all() and self.present is None:
+            if getattr(self, "_eff_key", None) is not None:
+                for sh in self.shards:
+                    check(lib().vq_store_set_split_weights(sh.handle, None), "vq_store_set_split_weights")
+                self._eff_key = None
             return
-        present = np.ones((self.n_rows,) + self.row_shape[:2], bool) if self.present is None else self.present
-        eff = present & have[None]
-        key = eff.tobytes() if eff.size < (1 << 22) else None
-        if getattr(self, "_eff_key", None) != key or key is None:
-            self._apply_split_weights(eff.sum(axis=2))
+        key = (have.tobytes(), getattr(self, "_present_version", 0))
+        if getattr(self, "_eff_key", None) != key:
+            present = np.ones((self.n_rows,) + self.row_shape[:2], bool) if self.present is None else self.present
+            self._apply_split_weights((present & have[None]).sum(axis=2))
             self._eff_key = key
 
     # ------------------------------------------------------------------ scan
@@ -378,6 +388,7 @@ class FeatureStore:
         Tc = np.ascontiguousarray(T)
         # enqueue on every shard first (each has its own stream), then wait: shards run concurrently
         self._near_best = [None] * len(self.shards)
+        self._merged_topk = None
         if len(self.shards) == 1:
             c = ScanCounts()
             self._scan_shard(0, Tc, p, c, lists)
@@ -402,24 +413,21 @@ class FeatureStore:
             self._near_best[i] = (pos.value, row.value, sc.value)
 
     def _scan_multi(self, Tc, p, lists=True):
-        import threading
-        counts = [ScanCounts() for _ in self.shards]
-        errs = []
-
-        def run(i):
-            try:
-                self._scan_shard(i, Tc, p, counts[i], lists)
-            except Exception as e:       # surfaced below
-                errs.append(e)
-
-        ts = [threading.Thread(target=run, args=(i,)) for i in range(len(self.shards))]
-        for t in ts:
-            t.start()
-        for t in ts:
-            t.join()
-        if errs:
-            raise errs[0]
-        return counts
+        """All shards with ONE library call from this thread (vq_scan_multi): the work is enqueued on every shard's
+        stream before any of them is waited for, and the shards' top-k lists come back merged."""
+        n = len(self.shards)
+        handles = (C.c_void_p * n)(*[sh.handle for sh in self.shards])
+        counts = (ScanCounts * n)()
+        near = np.empty((n, 3), np.int64)
+        k = max(int(p.topk), 1)
+        rows, scores, n_top = np.empty(k, np.int64), np.empty(k, np.float32), C.c_int32()
+        check(lib().vq_scan_multi(handles, n, ptr(Tc), C.byref(p), int(bool(lists)), counts, ptr(near), k, ptr(rows), ptr(scores),
+                                  C.byref(n_top)), "vq_scan_multi")
+        if not lists:
+            self._near_best = [(int(a), int(b), float(np.array([c], np.int64).astype(np.uint32).view(np.float32)[0]))
+                               for a, b, c in near]
+        self._merged_topk = (rows[:n_top.value], scores[:n_top.value])
+        return list(counts)
 
     def device_lists(self):
         """Device addresses of the last scan's ordered lists on a single-shard store: [(rows pointer (uint32 LOCAL rows),
@@ -522,11 +530,36 @@ class FeatureStore:
         order = np.lexsort((r, -s.astype(np.float64)))
         return r[order], s[order]
 
+    def rank_list(self, which, place):
+        """The match (or near-miss) list of the last scan sorted on the device by (score descending, `place` ascending):
+        `place` [n] is each list entry's rank in the caller's own order (the tie-break; distinct values).  Returns
+        (the places in sorted order, fp32 scores).  Shards are sorted separately (K7) and merged here."""
+        idx = {"matches": 0, "near_misses": 1}[which]
+        attr = ("n_match", "n_near")[idx]
+        place = np.ascontiguousarray(place, dtype=np.uint32)
+        outs, base = [], 0
+        for sh, c in zip(self.shards, self._last_counts):
+            n = getattr(c, attr)
+            o, sc = np.empty(n, np.uint32), np.empty(n, np.float32)
+            check(lib().vq_rank_list(sh.handle, idx, n, ptr(np.ascontiguousarray(place[base:base + n])), ptr(o), ptr(sc)),
+                  "vq_rank_list")
+            outs.append((o, sc))
+            base += n
+        if base != len(place):
+            raise VQError("rank_list: %d places for a %s list of %d entries" % (len(place), which, base))
+        if len(outs) == 1:
+            return outs[0]
+        o, sc = np.concatenate([a for a, _ in outs]), np.concatenate([b for _, b in outs])
+        order = np.lexsort((o, -sc.astype(np.float64)))
+        return o[order], sc[order]
+
     def topk(self):
         k = self._last_topk
         if k == 0:
             return np.empty(0, np.int64), np.empty(0, np.float32)
         n_l = len(self.shards)
+        if n_l > 1 and getattr(self, "_merged_topk", None) is not None:
+            return self._merged_topk                               # merged inside vq_scan_multi
         if n_l == 1:
             n = self._last_counts[0].n_topk
             r, s = np.empty(n, np.int64), np.empty(n, np.float32)
@@ -552,6 +585,22 @@ class FeatureStore:
             out[lo:lo + sh.n_rows] = part
         return out
 
+    def scores_at(self, global_rows):
+        """fp32 scores of the last scan at the given global rows: one round trip per shard that holds any of them."""
+        rows = np.asarray(global_rows, dtype=np.int64).reshape(-1)
+        out = np.empty(len(rows), np.float32)
+        lo_g, hi_g = self.first_global_row, self.first_global_row + self.n_rows
+        if len(rows) and (rows.min() < lo_g or rows.max() >= hi_g):
+            raise VQError("scores_at: rows outside the store [%d, %d)" % (lo_g, hi_g))
+        for sh in self.shards:
+            sel = np.flatnonzero((rows >= sh.first) & (rows < sh.first + sh.n_rows))
+            if len(sel):
+                local = np.ascontiguousarray(rows[sel] - sh.first)
+                part = np.empty(len(sel), np.float32)
+                check(lib().vq_fetch_scores_at(sh.handle, len(sel), ptr(local), ptr(part)), "vq_fetch_scores_at")
+                out[sel] = part
+        return out
+
     def sims(self):
         out = np.empty((self.n_rows, len(self.streams)), np.float32)
         for sh in self.shards:
@@ -569,8 +618,15 @@ class FeatureStore:
         or, with debug_scores, the fp32 score matrix [Q, n_rows] (single-shard stores only)."""
         if isinstance(targets, np.ndarray):
             T = np.ascontiguousarray(targets, dtype=np.float32).reshape((-1,) + self.row_shape)
+            have = np.ones(self.row_shape[:2], bool)
         else:
-            T = np.stack([self.pack_target(t, np.float32)[0] for t in targets])
+            packed = [self.pack_target(t, np.float32) for t in targets]
+            T = np.stack([t for t, _ in packed])
+            have = packed[0][1]
+            if any(not np.array_equal(h, have) for _, h in packed[1:]):
+                raise VQError("scan_batch: the targets of one batch must have the same (stream, split) slots — the mean over "
+                              "splits (ticket.py:155-157) is one per-row table for the whole pass")
+        self._sync_split_weights_for_target(have)              # never inherit what an earlier single-query job left
         Q = T.shape[0]
         w = [weights[s] for s in self.streams] if isinstance(weights, dict) else list(weights)
         p = make_params(w, threshold, lower_limit, 0.0, topk)

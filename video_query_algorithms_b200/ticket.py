@@ -26,6 +26,7 @@ import numpy as np
 
 from . import store as _store
 from ._ffi import VQError
+from ._rng import sample_range
 
 try:
     from requests import ConnectionError
@@ -307,12 +308,13 @@ class Ticket:
         lower_limit = threshold - near_miss * (1 - threshold)
         st = self.feature_store()
         # A review round samples a few dozen clips: the lists stay on the device and only the sampled entries are
-        # fetched.  The finalize round (max = inf) returns every clip above the criterion: whole lists come back.
+        # fetched.  The finalize round (max = inf) returns every clip above the criterion: whole lists come back, and
+        # everything below is array work — no per-clip Python objects until the final dict.
         sampled = max_number_matches != float("inf")
         res = self._scan(threshold, lower_limit, lists=not sampled)
-        ids = st.clip_ids
+        ids, first = st.clip_ids, st.first_global_row
         t_rows, _ = st.ties(copy=False)
-        self.tie_band = [int(ids[r - st.first_global_row]) for r in t_rows]
+        self.tie_band = ids[t_rows - first].tolist()
         if self.tie_band:
             logging.info("query %s: %d clip(s) within COMPUTE_EPS of a selection boundary: %s",
                          self.query_id, len(self.tie_band), self.tie_band[:20])
@@ -320,65 +322,91 @@ class Ticket:
         m_near_scores = int(min(max_number_matches - mscores, res.n_near))
         # random.sample(population, k) draws depend only on (len(population), k): sampling the index
         # range consumes the generator exactly like sampling the reference's dict items (:333).
-        picked = random.sample(range(res.n_match), mscores)
+        picked = sample_range(random, res.n_match, mscores)
         if sampled:
             m_rows, m_sc = st.gather("matches", picked)
-            chosen = [(int(ids[r - st.first_global_row]), float(s)) for r, s in zip(m_rows, m_sc)]
         else:
-            m_rows, m_sc = st.matches(copy=False)         # views of the scan's host mirror: consumed before the next scan
-            chosen = [(int(ids[m_rows[j] - st.first_global_row]), float(m_sc[j])) for j in picked]
-        near_best = {}
+            all_rows, all_sc = st.matches(copy=False)     # views of the scan's host mirror: consumed before the next scan
+            m_rows, m_sc = all_rows[picked], all_sc[picked]
+        jbest, best_row, best_sc = None, None, None
         n_left = res.n_near
-        jbest = None
         if m_near_scores > 0:
             m_near_scores -= 1
             n_left -= 1
             if sampled:
-                jbest, brow, bsc = st.near_best()          # first maximum in database order (:338), found on the device
-                near_best = {int(ids[brow - st.first_global_row]): float(bsc)}
+                jbest, best_row, best_sc = st.near_best()  # first maximum in database order (:338), found on the device
             else:
-                n_rows, n_sc = st.near_misses(copy=False)
-                jbest = int(np.argmax(n_sc))
-                near_best = {int(ids[n_rows[jbest] - st.first_global_row]): float(n_sc[jbest])}
-        picked = random.sample(range(n_left), m_near_scores)
+                nm_rows, nm_sc = st.near_misses(copy=False)
+                jbest = int(np.argmax(nm_sc))
+                best_row, best_sc = int(nm_rows[jbest]), float(nm_sc[jbest])
+        picked_n = sample_range(random, n_left, m_near_scores)
         # positions in the list with the best near miss deleted (:340) -> positions in the full list
-        pos = [j if jbest is None or j < jbest else j + 1 for j in picked]
+        pos = picked_n if jbest is None else picked_n + (picked_n >= jbest)
         if sampled:
             n_rows_p, n_sc_p = st.gather("near_misses", pos)
-            chosen += [(int(ids[r - st.first_global_row]), float(s)) for r, s in zip(n_rows_p, n_sc_p)]
         else:
-            n_rows, n_sc = st.near_misses(copy=False)
-            chosen += [(int(ids[n_rows[j] - st.first_global_row]), float(n_sc[j])) for j in pos]
-        self.matches = dict(chosen)
-        self.matches.update(near_best)
-        forced = {}
+            nm_rows, nm_sc = st.near_misses(copy=False)
+            n_rows_p, n_sc_p = nm_rows[pos], nm_sc[pos]
+        sel_rows = np.concatenate([m_rows, n_rows_p] + ([[best_row]] if best_row is not None else [])).astype(np.int64)
+        sel_sc = np.concatenate([m_sc, n_sc_p] + ([[best_sc]] if best_row is not None else []))
+        sel_ids = ids[sel_rows - first]
+        self.matches = dict(zip(sel_ids.tolist(), sel_sc.tolist()))
+        forced = []
         if st.has_clip(self.ref_clip_id):
-            forced[self.ref_clip_id] = self._score_of(self.ref_clip_id)
+            forced.append(self.ref_clip_id)
         if self.user_matches:
-            for clip, value in self.user_matches.items():
-                if value is True:
-                    forced[int(clip)] = self._score_of(int(clip))
-        self.matches.update(forced)
+            forced += [int(clip) for clip, value in self.user_matches.items() if value is True]
+        if forced:
+            f_sc = st.scores_at(st.rows_of(forced))        # one round trip for all forced clips (:346-356)
+            self.matches.update(zip(forced, f_sc.tolist()))
+        # what the final report needs to rank on the device (ranked_selection): the lists' entries in selection order
+        self._selection = None if sampled else {
+            "n_match": res.n_match, "n_near": res.n_near, "picked": picked, "pos": pos, "jbest": jbest, "n_listed": len(sel_ids)}
 
-    def ranked_selection(self, which="matches"):
-        """[(clip id, score)] of the last selection's whole match (or near-miss) set in report order — score descending,
-        database order among equal scores (ticket.py:266) — ranked on the device: the finalize round returns every clip
-        above min(threshold, lowest user match), which is far too many to sort as Python tuples."""
+    def ranked_selection(self):
+        """[(clip id, score)] of the last finalize selection in REPORT order: score descending, ties in the order the
+        selection inserted the clips (the reference's stable sort of its dict's items, ticket.py:266).  The match and
+        near-miss lists are ranked on the device (vq_rank_list, K7) with each entry's place in the selection order as the
+        tie-break; forced clips that sit in neither list (a reference clip or a confirmed clip below the band) are few
+        and are merged in here.  Every match outranks every near miss, so the two ranked lists are simply concatenated."""
+        sel = getattr(self, "_selection", None)
+        if sel is None:
+            raise VQError("ranked_selection: the last selection was not a finalize round (max_number_matches = inf)")
         st = self.feature_store()
-        rows, sc = st.ranked(which)
-        ids = st.clip_ids[rows - st.first_global_row]
-        return list(zip(ids.tolist(), sc.tolist()))
+        ids, first = st.clip_ids, st.first_global_row
+        n_m, n_n = sel["n_match"], sel["n_near"]
+        place_m = np.empty(n_m, np.uint32)
+        place_m[sel["picked"]] = np.arange(n_m, dtype=np.uint32)              # list entry -> place in the selection order
+        place_n = np.empty(n_n, np.uint32)
+        if n_n:
+            place_n[sel["pos"]] = np.arange(n_n - 1, dtype=np.uint32)
+            place_n[sel["jbest"]] = n_n - 1                                    # the best near miss is inserted last (:343)
+        m_rows, m_sc = st.matches(copy=False)
+        nm_rows, nm_sc = st.near_misses(copy=False)
+        om, sm = st.rank_list("matches", place_m)
+        on, sn = st.rank_list("near_misses", place_n)
+        inv_m = np.empty(n_m, np.int64)
+        inv_m[place_m] = np.arange(n_m)
+        inv_n = np.empty(n_n, np.int64)
+        inv_n[place_n] = np.arange(n_n)
+        r_ids = np.concatenate([ids[m_rows[inv_m[om]] - first], ids[nm_rows[inv_n[on]] - first]])
+        r_sc = np.concatenate([sm, sn])
+        listed = n_m + n_n
+        if len(self.matches) > listed:                                         # forced clips outside both lists, in dict order
+            extra = list(self.matches.items())[listed:]
+            r_ids = np.concatenate([r_ids, np.array([c for c, _ in extra], dtype=r_ids.dtype)])
+            r_sc = np.concatenate([r_sc, np.array([v for _, v in extra], dtype=np.float32)])
+            # stable: an extra clip lands after every listed clip of equal score (it was inserted later); the listed part
+            # is already in order, so this is one merge pass
+            order = np.argsort(-r_sc.astype(np.float64), kind="stable")
+            r_ids, r_sc = r_ids[order], r_sc[order]
+        return list(zip(r_ids.tolist(), r_sc.tolist()))
 
     def _score_of(self, clip):
         st = self.feature_store()
         if not st.has_clip(clip):
             raise KeyError(clip)
-        g = st.first_global_row + st.row_of(clip)
-        sh = st._shard_of(g)
-        out = np.empty(1, np.float32)
-        from ._ffi import check, lib, ptr
-        check(lib().vq_fetch_scores(sh.handle, g - sh.first, 1, ptr(out)), "vq_fetch_scores")
-        return float(out[0])
+        return float(st.scores_at(st.rows_of([clip]))[0])
 
     # ------------------------------------------------------------------ final report (A7)
     def create_final_report(self, hyperparameters, query_result_id):
@@ -421,8 +449,14 @@ class Ticket:
                    ['List of all clips with scores greater than min(threshold, score of lowest scoring'
                     ' user validated match)'],
                    ['clip #', 'start time', 'match type', 'video pk', 'video clip id', 'score', 'duration', 'notes']]
+        # report order = stable descending sort of the selection (ticket.py:266), ranked on the device for a finalize
+        # selection; any other producer of self.matches gets the same order from the host sort below
+        if getattr(self, "_selection", None) is not None and self._selection["n_listed"] <= len(self.matches):
+            ordered, presorted = self.ranked_selection(), True
+        else:
+            ordered, presorted = list(self.matches.items()), False
         rows = []
-        for video_clip_id, score in self.matches.items():
+        for video_clip_id, score in ordered:
             label = self.user_matches.get(str(video_clip_id))
             if str(video_clip_id) in self.user_matches:
                 match_type = "user-identified match" if label is True else "user-identified non-match"
@@ -435,7 +469,8 @@ class Ticket:
             start = int(match["results"][0]["match_video_time_span"].split(",")[0])
             rows.append([clip['clip'], str(timedelta(seconds=start)), match_type, clip['video'], video_clip_id,
                          score, clip['duration'], clip['notes']])
-        rows.sort(key=lambda r: r[5], reverse=True)
+        if not presorted:
+            rows.sort(key=lambda r: r[5], reverse=True)
         with open(path, 'x', newline='') as f:
             w = csv.writer(f)
             w.writerows(header)
