@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--replicates", type=int, default=1000, help="config5: bootstrap replicates per step")
     ap.add_argument("--no-cold", action="store_true", help="skip the cold end-to-end leg (8 GB upload per step)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-config3", action="store_true", help="skip the 12.5M-clips-per-GPU leg (config3_shard)")
+    ap.add_argument("--no-extra", action="store_true", help="N = 1: skip the short config4 / config5 legs (other_workloads)")
     ap.add_argument("--exchange", default="p2p-lagged", choices=["p2p-lagged", "p2p", "nccl"],
                     help="N > 1: peer-memory push + fused merge kernel, merging the previous step's payloads while this "
                          "step's are in flight (default; the last step is flushed inside the timed region), the same "
@@ -189,9 +191,15 @@ def main():
     if args.impl == "reference":
         return run_reference(args, rank, world)
     if args.workload == "config4":
-        return run_batched(args, rank, world, local_rank)
+        line = run_batched(args, rank, world, local_rank)
+        if line is not None:
+            emit(line)
+        return
     if args.workload == "config5":
-        return run_bootstrap(args, rank, world, local_rank)
+        line = run_bootstrap(args, rank, world, local_rank)
+        if line is not None:
+            emit(line)
+        return
 
     import torch
     import torch.distributed as dist
@@ -204,9 +212,11 @@ def main():
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    host_group = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
+        host_group = dist.new_group(backend="gloo")      # host-only barrier: ranks that wait leave their GPU idle
     n = args.clips_per_gpu
     st = vq.FeatureStore(n, STREAMS, [1], DIM, devices=[local_rank], first_global_row=rank * n)
     st.fill_synthetic(DATA_SEED)
@@ -231,11 +241,6 @@ def main():
     sptr = C.c_void_p(stream.cuda_stream)
     assert stream.cuda_stream != 0
     from video_query_algorithms_b200.sharded import RankScan
-    rank_scan = RankScan(handle, TOPK, local_rank, dist if world > 1 else None, torch, exchange=args.exchange)
-
-    def step():
-        # local fused scan + selection; for N > 1 one NCCL allgather of the 1.6 KB payload + device merge
-        rank_scan.enqueue(target_dev.data_ptr(), params, stream.cuda_stream)
 
     def barrier():
         torch.cuda.synchronize()
@@ -243,70 +248,99 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    rank_scan.flush(stream.cuda_stream)
-    barrier()
-    tmp = np.empty(1024, np.float32)
-    cnt = C.c_int32()
-    lib.vq_scan_kernel_times(handle, 1024, _ffi.ptr(tmp), C.byref(cnt))        # drop warm-up timings
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for _ in range(args.steps):
-        step()
-    rank_scan.flush(stream.cuda_stream)              # lagged exchange: the last step's merge belongs to the timed region
-    ev1.record(stream)
-    barrier()
-    sampler.stop_flag = True
-    sampler.join()
-    ms_total = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms_total, op=dist.ReduceOp.MAX)
-    ms_total = float(ms_total.item())
-    ktimes = np.empty(1024, np.float32)
-    _ffi.check(lib.vq_scan_kernel_times(handle, 1024, _ffi.ptr(ktimes), C.byref(cnt)), "vq_scan_kernel_times")
-    k1_ms = float(np.mean(ktimes[:cnt.value])) if cnt.value else float("nan")
-    value = world * n * args.steps / (ms_total * 1e-3)
+    def max_over_ranks(x):
+        t_ = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        return float(t_.item())
+
+    def device_leg(handle_, n_local, steps, warmup, sampler=None):
+        """K1 + K2 (+ exchange) per step on this rank's resident shard, timed on the device: W warm-up steps, a barrier,
+        then exactly `steps` steps between two events on the launching stream; max over ranks.  Returns the whole-job
+        ms per step and the per-phase kernel times (max over ranks of each rank's mean)."""
+        rs = RankScan(handle_, TOPK, local_rank, dist if world > 1 else None, torch, exchange=args.exchange)
+        for _ in range(warmup):
+            rs.enqueue(target_dev.data_ptr(), params, stream.cuda_stream)
+        rs.flush(stream.cuda_stream)
+        barrier()
+        tmp = np.empty(1024, np.float32)
+        cnt = C.c_int32()
+        lib.vq_scan_kernel_times(handle_, 1024, _ffi.ptr(tmp), C.byref(cnt))       # drop the warm-up timings
+        rs.exchange_times()
+        if sampler is not None:
+            sampler.start()                          # NVML was initialised when the sampler was built: nothing slow from here on
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()                                    # every rank starts its timed region together
+        ev0.record(stream)
+        for _ in range(steps):
+            rs.enqueue(target_dev.data_ptr(), params, stream.cuda_stream)
+        rs.flush(stream.cuda_stream)                 # the last step's merge (and the exchange stream) belong to the timed region
+        ev1.record(stream)
+        barrier()
+        if sampler is not None:
+            sampler.stop_flag = True
+            sampler.join()
+        ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+        k1, sel = np.empty(1024, np.float32), np.empty(1024, np.float32)
+        _ffi.check(lib.vq_scan_phase_times(handle_, 1024, _ffi.ptr(k1), _ffi.ptr(sel), C.byref(cnt)), "vq_scan_phase_times")
+        xt = rs.exchange_times()
+        k1_mine = float(np.mean(k1[:cnt.value])) if cnt.value else float("nan")
+        phases = {"k1_ms": max_over_ranks(k1_mine), "k1_ms_rank0": k1_mine,
+                  "select_ms": max_over_ranks(float(np.mean(sel[:cnt.value])) if cnt.value else float("nan")),
+                  "exchange_ms": max_over_ranks(float(np.mean(xt))) if len(xt) else 0.0,
+                  "launches_timed": int(cnt.value)}
+        return ms_total / steps, phases, rs
+
+    sampler = ClockSampler(local_rank)               # NVML init happens here, outside every timed region
+    warm = max(args.warmup, 3)
+    ms_step, phases, rank_scan = device_leg(handle, n, args.steps, warm, sampler)
+    k1_ms = phases["k1_ms_rank0"]
+    value = world * n * args.steps / (ms_step * args.steps * 1e-3)
 
     # counts of the last step (sanity: the work is real)
     sc_counts = _ffi.ScanCounts()
     _ffi.check(lib.vq_scan_wait(handle, sptr, C.byref(sc_counts)), "vq_scan_wait")
-
     g_counts, g_rows, g_scores = rank_scan.result()
-    # ---- end to end through the public API, host buffers: target H2D, counts + lists + top-k D2H
-    # N > 1: through RankStore, whose methods are collectives — every rank ends each step holding the SEARCH SET's result
-    # (counts, merged top-k, the ordered lists of all ranks concatenated in database order), not just its shard's
+    kernels_per_step = rank_scan.kernels_per_step()
+    exchange_mode = rank_scan.exchange
+    rank_scan.close()
+
+    # ---- end to end through the public API, host buffers: target H2D, counts + lists + top-k D2H.
+    # N > 1 (one process per GPU): RankStore — every rank ends each step with the search set's counts and merged top-k and
+    # with ITS segment of the ordered lists in pinned host memory (the segments in rank order are the lists; nothing is
+    # replicated, no consumer of the path needs that).  e2e_root: the whole lists on rank 0 only.
     e2e_steps = max(3, min(args.steps, 100))
     rstore = None
     if world > 1:
         from video_query_algorithms_b200.sharded import RankStore
         rstore = RankStore(st, dist, torch, dev)
 
+    def timed(fn, steps):
+        for _ in range(2):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        barrier()
+        return max_over_ranks(time.perf_counter() - t0), out
+
     def e2e_step():
         if rstore is not None:
-            g_cnt, g_lists, g_top = rstore.scan(tdict, WEIGHTS, THRESHOLD, lower, EPS, topk=TOPK, copy=False)
-            return st.last, int(g_cnt[0]) + int(g_cnt[1]) + int(g_cnt[2])
+            g_cnt, sh, g_top = rstore.scan(tdict, WEIGHTS, THRESHOLD, lower, EPS, topk=TOPK, copy=False)
+            mine = sum(len(sh.local(w)[0]) for w in ("matches", "near_misses", "ties"))
+            return st.last, mine
         res = st.scan(tdict, WEIGHTS, THRESHOLD, lower, EPS, topk=TOPK)
         k_rows, k_sc = st.topk()
         m_rows, m_sc = st.matches(copy=False)          # as Ticket.select_clips_to_review reads them: views of the
         nm_rows, nm_sc = st.near_misses(copy=False)    # pinned host mirror the scan's publish kernel wrote
         return res, res.n_match + res.n_near + res.n_tie
 
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        res, n_listed = e2e_step()
-    barrier()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = world * n * e2e_steps / float(e2e_s.item())
+    e2e_s, (res, n_listed) = timed(e2e_step, e2e_steps)
+    e2e_value = world * n * e2e_steps / e2e_s
     h2d = ROW_BYTES + C.sizeof(_ffi.ScanParams)
-    d2h = 40 + TOPK * 12 + n_listed * 12       # N = 1: the shard's lists; N > 1: the search set's lists, on every rank
+    d2h = 40 + TOPK * 12 + n_listed * 12       # per rank: its shard's lists
     e2e_what = ("FeatureStore.scan + topk + matches + near_misses through the C ABI: target from a "
                 "host buffer, counts / top-k / ordered lists (int64 rows + fp32 scores) published into pinned host "
                 "memory inside the call; the shard stays resident in HBM between queries (the store outlives "
@@ -314,18 +348,29 @@ def main():
     sel_what = ("the review round as Ticket.select_clips_to_review runs it: FeatureStore.scan(lists=False) "
                 "+ topk + tie band + gather of 10 sampled matches and 9 sampled near misses + best near miss; "
                 "the match / near-miss lists stay on the device")
+    e2e_root = None
     if world > 1:
         small_how = ("through the shared-memory host mailbox, vq_hostx_allgather" if rstore.mailbox is not None
                      else "NCCL collectives staged through the devices")
-        e2e_what = ("RankStore.scan on every rank (one process per GPU): the local scan with the lists left on the device, "
-                    "then two exchanges that give EVERY rank the search set's result — one summary record per rank (counts, "
-                    "top-k, tie band; %s; merged on the host) and one NCCL allgather of the ordered match / near-miss lists "
-                    "straight from device memory (int64 global rows + fp32 scores, %d entries in all, padded to the longest "
-                    "rank's), concatenated on the device and copied once into pinned host memory (views, like N = 1); "
-                    "h2d / d2h bytes are per rank" % (small_how, n_listed))
+        e2e_what = ("RankStore.scan on every rank (one process per GPU): the same call as N = 1 on the rank's shard — target "
+                    "from a host buffer, the rank's segment of the ordered lists (int64 global rows + fp32 scores, %d entries on "
+                    "rank 0) published into its pinned host memory — plus ONE exchange of a summary record per rank (%s) that "
+                    "gives every rank the search set's counts, the merged top-k, the tie band and every segment's length; "
+                    "the segments in rank order are the search set's lists in database order, nothing is replicated; "
+                    "h2d / d2h bytes are per rank" % (n_listed, small_how))
         sel_what = ("RankStore.scan_select + gather_many on every rank: lists stay on each rank's device; two exchanges (%s) — "
                     "one summary record per rank (counts, top-k, tie band, best near miss) and 16 B per position to fetch "
                     "the 19 sampled entries from the ranks that own them" % small_how)
+
+        def root_step():
+            g_cnt, lists, g_top = rstore.scan(tdict, WEIGHTS, THRESHOLD, lower, EPS, topk=TOPK, copy=False, lists="root")
+            return int(g_cnt[0]) + int(g_cnt[1]) + int(g_cnt[2])
+        root_s, n_all = timed(root_step, e2e_steps)
+        e2e_root = {"value": world * n * e2e_steps / root_s, "unit": "clips/s", "steps": e2e_steps,
+                    "d2h_bytes_per_step_rank0": int(40 + TOPK * 12 + n_all * 12),
+                    "what": "the same with the WHOLE lists (%d entries) delivered to rank 0 only (the rank that talks to the API): "
+                            "unpadded NCCL send / recv of each rank's segment device to device, one copy into rank 0's pinned "
+                            "memory (RankStore.scan(lists='root'))" % n_all}
 
     # ---- the review round's call (Ticket.select_clips_to_review): lists stay on the device, the host draws 20 list
     # positions with the reference's RNG and gathers just those entries + the best near miss
@@ -349,17 +394,8 @@ def main():
             st.gather("matches", pos_m)
             st.gather("near_misses", pos_n)
 
-    for _ in range(2):
-        select_step()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        select_step()
-    barrier()
-    sel_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(sel_s, op=dist.ReduceOp.MAX)
-    e2e_select_value = world * n * e2e_steps / float(sel_s.item())
+    sel_s, _ = timed(select_step, e2e_steps)
+    e2e_select_value = world * n * e2e_steps / sel_s
 
     # ---- cold end to end: the shard itself is uploaded from pinned host memory every step
     cold = None
@@ -385,6 +421,86 @@ def main():
         except Exception as e:                            # pragma: no cover
             cold = {"value": None, "error": repr(e)[:200]}
 
+    if rstore is not None:
+        rstore.close()
+    st.close()
+
+    # ---- the broker's arrangement: ONE process drives every GPU of the box (reference src/broker.py:62-92; this is what
+    # compute_matches -> Ticket -> FeatureStore.scan does): rank 0 holds a store of N x clips_per_gpu clips sharded over
+    # all N devices and scans it with one library call per query (vq_scan_multi); the other ranks wait on a host barrier
+    single = None
+    if world > 1:
+        dist.barrier(group=host_group)
+        if rank == 0:
+            try:
+                big = vq.FeatureStore(world * n, STREAMS, [1], DIM, devices=list(range(world)))
+                big.fill_synthetic(DATA_SEED)
+
+                def sp_step():
+                    r_ = big.scan(tdict, WEIGHTS, THRESHOLD, lower, EPS, topk=TOPK)
+                    big.topk()
+                    big.matches(copy=False)
+                    big.near_misses(copy=False)
+                    return r_
+                for _ in range(3):
+                    sp_step()
+                t0 = time.perf_counter()
+                for _ in range(e2e_steps):
+                    r_ = sp_step()
+                dt = time.perf_counter() - t0
+
+                def sp_select():
+                    r2 = big.scan(tdict, WEIGHTS, THRESHOLD, lower, EPS, topk=TOPK, lists=False)
+                    big.topk(); big.ties(copy=False); big.near_best()
+                    big.gather("matches", _random.sample(range(r2.n_match), 10))
+                    big.gather("near_misses", _random.sample(range(r2.n_near - 1), 9))
+                for _ in range(3):
+                    sp_select()
+                t1 = time.perf_counter()
+                for _ in range(e2e_steps):
+                    sp_select()
+                dt_sel = time.perf_counter() - t1
+                single = {"value": world * n * e2e_steps / dt, "unit": "clips/s", "steps": e2e_steps,
+                          "ms_per_query": 1e3 * dt / e2e_steps, "select_value": world * n * e2e_steps / dt_sel,
+                          "select_ms_per_query": 1e3 * dt_sel / e2e_steps,
+                          "k1_ms_max_over_shards": float(r_.scan_ms), "n_match": int(r_.n_match), "n_near": int(r_.n_near),
+                          "d2h_bytes_per_step": int(40 * world + TOPK * 12 * world + (r_.n_match + r_.n_near + r_.n_tie) * 12),
+                          "what": "ONE process, one thread, %d GPUs: FeatureStore(devices=[0..%d]).scan + topk + matches + "
+                                  "near_misses — the call compute_matches makes — through vq_scan_multi (target copy, K1, K2 and "
+                                  "the publish kernel enqueued on every shard's stream, then one wait per stream; top-k merged "
+                                  "in the call); select_value: the review round's variant (lists stay on the devices, 19 "
+                                  "sampled entries gathered)" % (world, world - 1)}
+                big.close()
+            except Exception as e:                        # pragma: no cover
+                single = {"value": None, "error": repr(e)[:300]}
+        dist.barrier(group=host_group)
+
+    # ---- BASELINE configs[2], one shard of it: 12.5M clips per GPU (102.4 GB; 8 GPUs = the 100M-clip database), a few
+    # device-timed steps with the same kernels and exchange
+    shard3 = None
+    n3 = 12_500_000
+    free_b, total_b = torch.cuda.mem_get_info(dev)
+    fits = torch.tensor([1 if (not args.no_config3 and free_b > n3 * ROW_BYTES * 1.04 + (2 << 30)) else 0], device=dev)
+    if world > 1:
+        dist.all_reduce(fits, op=dist.ReduceOp.MIN)
+    if int(fits.item()) == 1:
+        st3 = vq.FeatureStore(n3, STREAMS, [1], DIM, devices=[local_rank], first_global_row=rank * n3)
+        st3.fill_synthetic(DATA_SEED)
+        steps3 = 10
+        sampler3 = ClockSampler(local_rank)
+        ms3, ph3, rs3 = device_leg(st3.shards[0].handle, n3, steps3, 3, sampler3)
+        c3, _, _ = rs3.result()
+        rs3.close()
+        st3.close()
+        shard3 = {"clips_per_gpu": n3, "global_clips": n3 * world, "steps": steps3, "warmup": 3, "ms_per_step": ms3,
+                  "value": world * n3 / (ms3 * 1e-3), "unit": "clips/s", "hbm_gbs_aggregate": world * n3 * ROW_BYTES / (ms3 * 1e-3) / 1e9,
+                  "frac_of_nominal_8TBs_per_gpu": n3 * ROW_BYTES / (ms3 * 1e-3) / 1e9 / 8000.0, "kernel_times": ph3,
+                  "global_counts": {"n_match": int(c3[0]), "n_near": int(c3[1]), "n_tie": int(c3[2])},
+                  "clocks": sampler3.result(),
+                  "what": "weak-scaled shard of BASELINE configs[2]: %d clips (%.1f GB) resident per GPU; N = 8 is the 100M-clip, "
+                          "819 GB database of the north star (target: <= 16.0 ms per query = 80 %% of 8 x 8 TB/s)"
+                          % (n3, n3 * ROW_BYTES / 1e9)}
+
     if rank == 0:
         peaks = {}
         try:
@@ -394,33 +510,38 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         achieved = n * ROW_BYTES / (k1_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_src = None, None
         try:
             with open(os.path.join(ROOT, "profiles", "k1_traffic.json")) as f:
                 tj = json.load(f)
-                # ncu figure is per launch of a 1M-clip scan; traffic scales with the clips per launch
-                traffic = int(tj["dram_bytes_per_launch"] * (n / 1_000_000))
+            if int(tj["clips_per_launch"]) == n:          # one ncu --set full capture of this very launch shape; never rescaled
+                traffic, traffic_src = int(tj["dram_bytes_per_launch"]), tj.get("source")
         except Exception:
             pass
         line = {
             "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic (VQSYN-1 counter-based generator, on device)",
             "config": workload_config(args, world),
             "hbm_gbs_whole_step": value * ROW_BYTES / 1e9,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "scan_rows_reg<2,8> (K1)", "kernel_ms": k1_ms,
+                         "traffic": traffic, "traffic_source": traffic_src, "kernel": "scan_rows_reg<2,8> (K1)", "kernel_ms": k1_ms,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650",
                          "frac_of_nominal_8TBs": achieved / 8000.0,
                          "algorithmic_bytes_per_launch": n * ROW_BYTES},
+            "kernel_times": dict(phases, what="CUDA events inside the timed region, mean per launch, max over ranks: K1 scan, "
+                                 "K2a-c selection, exchange kernel (on its own stream: overlaps the next step's K1)"),
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "what": e2e_what},
             "e2e_select": {"value": e2e_select_value, "unit": "clips/s", "h2d_bytes_per_step": int(h2d + 19 * 8),
                            "d2h_bytes_per_step": int(64 + TOPK * 12 + res.n_tie * 12 + 19 * 12), "steps": e2e_steps,
                            "what": sel_what},
+            "e2e_root": e2e_root,
+            "e2e_single_process": single,
             "e2e_cold": cold,
-            "gpu_launches": rank_scan.kernels_per_step() * args.steps,
-            "exchange": rank_scan.exchange,
+            "config3_shard": shard3,
+            "gpu_launches": kernels_per_step * args.steps,
+            "exchange": exchange_mode,
             "clocks": sampler.result(),
             "last_step_counts": {"n_match": int(sc_counts.n_match), "n_near": int(sc_counts.n_near),
                                  "n_tie": int(sc_counts.n_tie), "n_topk": int(sc_counts.n_topk)},
@@ -428,6 +549,19 @@ def main():
                                  "top1_row": int(g_rows[0]) if len(g_rows) else None,
                                  "top1_score": float(g_scores[0]) if len(g_scores) else None},
         }
+        if world == 1 and not args.no_extra:
+            # the other two GPU configurations of BASELINE.json, a few steps each, so that every round has driver-timed numbers
+            extra = {}
+            for name, fn, kw in (("config4", run_batched, {"steps": 5, "clips_per_gpu": 10_000_000}),
+                                 ("config5", run_bootstrap, {"steps": 5, "clips_per_gpu": 1_000_000})):
+                try:
+                    a2 = argparse.Namespace(**dict(vars(args), no_cpu=True, **kw))
+                    sub = fn(a2, 0, 1, local_rank, steps=kw["steps"])
+                    extra[name] = {k_: sub[k_] for k_ in ("metric", "value", "unit", "steps", "warmup", "ms_per_step", "dtype",
+                                                          "config", "roofline", "e2e", "clocks", "last_step") if k_ in sub}
+                except Exception as e:                    # pragma: no cover
+                    extra[name] = {"error": repr(e)[:300]}
+            line["other_workloads"] = extra
         if world == 1 and not args.no_cpu:
             cores = len(os.sched_getaffinity(0))
             v, dt = cpu_port_throughput(40000)
@@ -439,13 +573,8 @@ def main():
                 "vectorised_numpy_f64": {"value": vv, "unit": "clips/s", "cores": cores,
                                          "sample": "200000-clip slice, one pass (%.1f s), BLAS on all cores" % vdt}}
         emit(line)
-    # global result of the last timed step (all ranks hold the same merged payload)
-    if rstore is not None:
-        rstore.close()
-    rank_scan.close()
     if world > 1:
         dist.destroy_process_group()
-    st.close()
 
 
 # ------------------------------------------------------------------------------------ the other GPU configs
@@ -471,7 +600,7 @@ def _setup(local_rank, world):
     return torch, dist, vq, dev
 
 
-def run_batched(args, rank, world, local_rank):
+def run_batched(args, rank, world, local_rank, steps=None):
     """BASELINE configs[3]: Q targets against every rank's resident shard in one pass on the tensor cores (K3), per-query
     counts + top-k; N > 1: weak scaling, per-query top-k merged across ranks (RankStore.scan_batch).  A step = one
     scan_batch call with host buffers in and out; `value` uses the device time of its kernels (CUDA events on the
@@ -504,7 +633,8 @@ def run_batched(args, rank, world, local_rank):
 
     for _ in range(max(args.warmup, 3)):
         call(targets, WEIGHTS, THRESHOLD, lower, topk=TOPK)
-    steps = args.steps if args.steps != 300 else 20          # the default K is config2's; a step here is ~30 ms
+    if steps is None:
+        steps = args.steps if args.steps != 300 else 20      # the default K is config2's; a step here is ~30 ms
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -522,6 +652,7 @@ def run_batched(args, rank, world, local_rank):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     tt = tt.tolist()
     k_ms, wall = tt[:-1], tt[-1]
+    line = None
     if rank == 0:
         ms_step = float(np.mean(k_ms))
         pairs = float(world) * n * Q
@@ -561,20 +692,20 @@ def run_batched(args, rank, world, local_rank):
                                     "cores_available": len(os.sched_getaffinity(0)), "kind": "port",
                                     "sample": "one query against a 20000-clip slice (%.1f s): the reference scores one "
                                               "query per job, so its pairs/s is its clips/s" % dt}
-        emit(line)
     if rstore is not None:
         rstore.close()
     st.close()
     if world > 1:
         dist.destroy_process_group()
+    return line if rank == 0 else None
 
 
-def run_bootstrap(args, rank, world, local_rank):
+def run_bootstrap(args, rank, world, local_rank, steps=None):
     """BASELINE configs[4]: the weight update (hyperparameter.py:29-76) for R bootstrap replicates at once over L labelled
     clips of a 1M-clip DB; replicate index sets drawn host-side from Python's RANDOM_SEED-driven generator exactly as
     the reference's bagging draws them.  The labelled rows live on one GPU: replicas only (rank 0 runs, N is ignored)."""
     if rank != 0:
-        return
+        return None
     import random
     torch, dist, vq, dev = _setup(local_rank, 1)
     n, L, R = args.clips_per_gpu, args.labelled, args.replicates
@@ -602,7 +733,8 @@ def run_bootstrap(args, rank, world, local_rank):
     t.target.target_features = tdict
     t.feature_store = lambda optional=False: st
     hp = vq.Hyperparameter(dict(zip(STREAMS, WEIGHTS)), ballast=0.0)
-    steps = args.steps if args.steps != 300 else 10
+    if steps is None:
+        steps = args.steps if args.steps != 300 else 10
     random.seed(a=os.environ["RANDOM_SEED"])
 
     def step():
@@ -624,7 +756,7 @@ def run_bootstrap(args, rank, world, local_rank):
     sampler.join()
     draw_s, upd_s = float(np.mean([p_[0] for p_ in parts])), float(np.mean([p_[1] for p_ in parts]))
     w, th = parts[-1][2], parts[-1][3]
-    emit({
+    line = {
         "metric": "bootstrap replicates of the weight update per second", "value": R / upd_s, "unit": "replicates/s",
         "n_gpus": 1, "steps": steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * upd_s, "higher_is_better": True,
         "scaling": "replicas only", "vs_baseline": None, "dtype": "f64", "data": "synthetic (VQSYN-1 counter-based generator, on device)",
@@ -643,8 +775,9 @@ def run_bootstrap(args, rank, world, local_rank):
                          "kind": "port", "sample": "projection, not a run: the reference rescans the whole DB for each of its 40 "
                                                    "weights (3.1 us per clip) and walks 40 x 31 x the replicate's labelled clips "
                                                    "(1.7 us each), per-item costs measured on the loop port (SURVEY.md §8 A8)"},
-    })
+    }
     st.close()
+    return line
 
 
 if __name__ == "__main__":

@@ -57,6 +57,13 @@ int vq_store_describe(const vq_store *s, int64_t *n_rows, int *n_streams, int *n
  * asynchronously on the store's stream; the call returns after the copy has completed.       */
 int vq_store_upload(vq_store *s, int64_t first_row, int64_t n_rows, const float *rows);
 int vq_store_download(vq_store *s, int64_t first_row, int64_t n_rows, float *rows_out);
+/* Pipelined ingest (north_star item 1: "uploaded from pinned memory"): the host fills one pinned chunk while the
+ * previous one is in flight.  vq_store_upload_async only enqueues ONE copy on the store's stream (rows must stay
+ * untouched until vq_store_sync returns); vq_pinned_alloc / vq_pinned_free hand out page-locked staging buffers.       */
+int vq_store_upload_async(vq_store *s, int64_t first_row, int64_t n_rows, const float *rows_pinned);
+int vq_store_sync(vq_store *s);
+int vq_pinned_alloc(void **out, int64_t bytes);
+int vq_pinned_free(void *p);
 /* 1 / (number of splits the clip actually has) per (row, stream); NULL restores "all present".
  * Missing (row, stream, split) slots must be uploaded as zeros (ticket.py:155-157).          */
 int vq_store_set_split_weights(vq_store *s, const float *inv_counts /* [n_rows][n_streams] */);

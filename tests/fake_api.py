@@ -26,6 +26,7 @@ class FakeSchema:
 
 class FakeAPI:
     def __init__(self, page_size=50):
+        self.search_set_record = "members"                    # or "bare": search-sets/read returns id and name only
         self.videos = {}          # id -> dict
         self.clips = {}           # id -> dict(id, clip, video, duration, notes)
         self.features = []        # list of feature rows, in insertion (= response) order
@@ -179,7 +180,10 @@ class FakeAPI:
             return [r for r in self.features if r["video_clip_id"] in ids]
         if keys == ("search-sets", "read"):
             s = self.search_sets[params["id"]]
-            return {"id": s["id"], "name": s["name"]}
+            if self.search_set_record == "bare":              # an API whose record says nothing about the members
+                return {"id": s["id"], "name": s["name"]}
+            videos = sorted({self.clips[c]["video"] for c in s["clip_ids"]})
+            return {"id": s["id"], "name": s["name"], "videos": videos, "number_of_clips": len(s["clip_ids"])}
         if keys == ("video-clips", "features"):
             return list(self.features_by_clip[params["id"]])
         if keys == ("video-clips", "read"):

@@ -48,7 +48,26 @@ def main():
     from video_query_algorithms_b200.sharded import RankStore
     rstore = RankStore(st, dist, torch, dev)
     tf = {s: {1: T[i, 0]} for i, s in enumerate(S)}
-    r_counts, r_lists, (r_trows, r_tsc) = rstore.scan(tf, (1.0, 1.5), 0.81, 0.73, 3e-6, topk=k)
+    r_counts, r_lists, (r_trows, r_tsc) = rstore.scan(tf, (1.0, 1.5), 0.81, 0.73, 3e-6, topk=k, lists="all")
+    # the default: every rank keeps its own segment of the lists (nothing replicated), and rank 1 alone gets them whole
+    d_counts, d_sh, (d_trows, d_tsc) = rstore.scan(tf, (1.0, 1.5), 0.81, 0.73, 3e-6, topk=k)
+    seg_ok = True
+    for c, name in enumerate(("matches", "near_misses", "ties")):
+        a, b = d_sh.span(name)
+        rows_l, sc_l = d_sh.local(name)
+        seg_ok = seg_ok and np.array_equal(rows_l, r_lists[c][0][a:b]) and np.array_equal(sc_l, r_lists[c][1][a:b])
+        seg_ok = seg_ok and d_sh.total(name) == len(r_lists[c][0]) and (b == a or d_sh.owner(name, a) == rank)
+    seg_ok = seg_ok and list(d_counts) == list(r_counts) and np.array_equal(d_trows, r_trows) and np.array_equal(d_tsc, r_tsc)
+    root = world - 1
+    o_counts, o_lists, _ = rstore.scan(tf, (1.0, 1.5), 0.81, 0.73, 3e-6, topk=k, lists="root", root=root)
+    if rank == root:
+        seg_ok = seg_ok and all(np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) for a, b in zip(o_lists, r_lists))
+    else:
+        seg_ok = seg_ok and o_lists is None
+    seg_flag = torch.tensor([1 if seg_ok else 0], device=dev)
+    dist.all_reduce(seg_flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("rank store sharded lists and root-only gather agree with the replicated lists: %s" % bool(seg_flag.item()))
     # review round: lists stay on the ranks; counts / top-k / tie band / best near miss / sampled positions cross
     s_counts, (s_trows, s_tsc), s_ties, s_best = rstore.scan_select(tf, (1.0, 1.5), 0.81, 0.73, 3e-6, topk=k)
     rng = np.random.default_rng(5)                           # same positions on every rank
@@ -64,7 +83,7 @@ def main():
     z_counts, z_rows, _, _ = rstore.scan_batch(Tq, (1.0, 1.5), 0.81, 0.73, topk=0)
     labelled = np.arange(7, n_local * world, 997, dtype=np.int64)
     l_sims = rstore.labelled_sims(tf, labelled)
-    ok = True
+    ok = bool(seg_flag.item())
     if rank == 0:
         full = vq.FeatureStore(n_local * world, S, [1], 1024, devices=[local])
         full.fill_synthetic(seed)

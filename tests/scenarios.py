@@ -9,10 +9,9 @@ import random
 import numpy as np
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-SCENARIOS = ["A_brooklyn_bagging", "B_both_simple_mu", "C_shrp2_simple", "D_synth10k"]
-# recorded from the reference and replayed by the oracle on CPU; the GPU replay (tests/test_gpu_parity.py walks SCENARIOS)
-# takes it over once it has run on a B200 — it was added after the round's GPU budget was spent
-ORACLE_ONLY_SCENARIOS = ["F_shrp2_bagging_mu", "G_brooklyn_all_rejected"]
+SCENARIOS = ["A_brooklyn_bagging", "B_both_simple_mu", "C_shrp2_simple", "D_synth10k", "F_shrp2_bagging_mu",
+             "G_brooklyn_all_rejected"]
+ORACLE_ONLY_SCENARIOS = []         # every recorded scenario is replayed on the GPU (tests/test_gpu_parity.py walks SCENARIOS)
 FIXTURE_VIDEO = {"brooklyn": "DowntownBrooklynDrive_480p",
                  "shrp2": "S06NDS_Sample_120406_1451_00186_Forward"}
 
@@ -91,4 +90,5 @@ class Scenario:
                 "score>=0.86": lambda m: bool(m["score"] >= 0.86),
                 "score>=0.85": lambda m: bool(m["score"] >= 0.85),
                 "True if score>=0.84 else None": lambda m: True if m["score"] >= 0.84 else None,
+                "False": lambda m: False,
                 }[self.meta["label_rule"]]

@@ -757,3 +757,345 @@ def test_full_size_scan_properties(vq, n, first):
         if not (ok_m and ok_n):
             assert r in t_rows, "row %d flipped outside the reported tie band" % r
     st.close()
+
+
+# ---------------------------------------------------------------------------- round-2 additions
+def test_partial_update_target_on_the_gpu_matches_reference(vq):
+    """Scenario E: bootstrap_type 'partial_update' (target_clip.py:75-82: blend of the new target with the stored one)
+    through the product's TargetClip with the real store behind it — the solve runs in vq_bootstrap_target (K6).
+    Recorded by calling the reference's TargetClip directly (through compute_matches the reference crashes on it)."""
+    import json
+    import types
+    from scenarios import GOLDEN, rng_digest
+    with open(os.path.join(GOLDEN, "scn_E_partial_update.json")) as f:
+        js = json.load(f)
+    z = np.load(os.path.join(GOLDEN, "scn_E_partial_update.npz"))
+    fx = np.load(os.path.join(GOLDEN, "fixture_shrp2.npz"))
+    X, splits = fx["X"], [int(p) for p in fx["splits"]]
+    ids = np.arange(js["first_clip_id"], js["first_clip_id"] + len(X))
+    st = vq.FeatureStore(len(X), STREAMS, splits, 1024, devices=[0], clip_ids=ids)
+    st.upload(0, X)
+    prev = {s: {p: z["previous"][si, pi].tolist() for pi, p in enumerate(splits)} for si, s in enumerate(STREAMS)}
+
+    class Client:
+        def action(self, schema, keys, params=None, **kw):
+            assert tuple(keys) == ("matches", "list")
+            return {"results": js["matches"], "pagination": {"nextPage": None}}
+
+    ticket = types.SimpleNamespace(client=Client(), schema=None, dynamic_target_adjustment=True, ref_clip_id=int(ids[0]),
+                                   latest_query_result={"id": 1, "round": 1, "bootstrapped_target": prev},
+                                   features_from_store=True, attach_store=lambda hp: st, feature_store=lambda optional=False: st)
+    hp = dict(js["hp"])
+    hp["streams"] = tuple(hp["streams"])
+    random.seed(a=js["seed"])
+    tc = vq.TargetClip(ticket, vq.Hyperparameter(**hp))
+    tc.get_target_features()
+    got = np.array([[tc.target_features[s][p] for p in splits] for s in STREAMS])
+    assert np.abs(got - z["target"]).max() <= 1e-6 * np.abs(z["target"]).max()
+    assert rng_digest() == js["rng_after"]
+    assert json.dumps(tc.target_features)
+    st.close()
+
+
+def _ragged_api(vq, rng, n_clips=400, splits=(1, 2, 3), dim=256):
+    """A fake API whose search set is ragged: every clip has split 1 of both streams... except some that lack it in the
+    first stream (they must move behind the others, ticket.py:146-160), and many lack other slots."""
+    from fake_api import FakeAPI
+    api = FakeAPI(page_size=13)
+    base = rng.random((2, len(splits), dim))
+    X = np.zeros((n_clips, 2, len(splits), dim))
+    alpha = rng.random(n_clips) ** 0.5
+    for c in range(n_clips):
+        X[c] = alpha[c] * base + (1 - alpha[c]) * rng.random((2, len(splits), dim)) * 0.7
+    present = rng.random((n_clips, 2, len(splits))) > 0.25
+    present[:, 1, 0] = True                                    # every clip keeps one split of the second stream
+    present[:, 0, 1] |= ~present[:, 0, 0]                      # ... and at least one of the first
+    present[7] = True                                          # the reference clip is complete
+    vid = api.add_video("ragged")
+    cids = [api.add_clip(vid, c) for c in range(n_clips)]
+    order = rng.permutation(n_clips * 2 * len(splits))         # records in arbitrary order
+    for o in order:
+        c, rest = divmod(int(o), 2 * len(splits))
+        si, pi = divmod(rest, len(splits))
+        if present[c, si, pi]:
+            api.add_feature(cids[c], STREAMS[si], splits[pi], X[c, si, pi].tolist())
+    ss = api.add_search_set("ragged", cids)
+    qid = api.add_query("qr", vid, cids[7], ss, max_matches=16, dynamic_target_adjustment=True)
+    return api, qid, cids, X, present
+
+
+def test_compute_matches_on_a_ragged_search_set_follows_the_oracle(vq, tmp_path, monkeypatch):
+    """A ragged search set (missing (clip, stream, split) slots, clips lacking the first split of the first stream, records
+    in arbitrary order) through compute_matches on the GPU — new, revise and finalize rounds — against the float64 oracle
+    on the same records: row order (the reference's dict order, ticket.py:146-160), per-clip split means, scores, weights,
+    the selected clips in order."""
+    from fake_api import FakeRepository
+    rng = np.random.default_rng(77)
+    api, qid, cids, X, present = _ragged_api(vq, rng)
+    (tmp_path / "work").mkdir()
+    monkeypatch.chdir(tmp_path / "work")
+    vq.invalidate()
+    tickets = []
+
+    def factory(job, url):
+        t = vq.Ticket(job, url, client=api.client(), devices=[0])
+        tickets.append(t)
+        return t
+
+    hp_kw = dict(default_weights={"rgb": 1.0, "warped_optical_flow": 1.5}, default_threshold=0.7, near_miss_default=0.4,
+                 bootstrap_type="simple", mu=0.2, ballast=0.1, f_bootstrap=0.7)
+    for i, kind in enumerate(("new", "revise", "finalize")):
+        if i > 0:
+            api.label_latest_round(qid, lambda m: bool(m["score"] >= 0.78))
+        api.request(qid, kind)
+        hp = vq.Hyperparameter(**hp_kw)
+        random.seed(a="ragged-%d" % i)
+        state = random.getstate()
+        vq.compute_matches(FakeRepository(api), hp, ticket_factory=factory)
+        t = tickets[-1]
+        st = t.feature_store()
+        assert api.queries[qid]["process_state"] in (4, 7), api.queries[qid].get("notes")
+        # the oracle on the same records: rows in the product's order must be the reference's dict order
+        rows = api.action(("search-sets", "features"), {"id": api.queries[qid]["search_set_to_query"]})
+        first_seen, lowest = {}, {}
+        for j, r_ in enumerate(rows):
+            if r_["dnn_stream_id"] == STREAMS[0]:
+                key = (int(r_["dnn_stream_split"]), j)
+                if key < lowest.get(r_["video_clip_id"], (99, 0)):
+                    lowest[r_["video_clip_id"]] = key
+        want_order = sorted(lowest, key=lowest.get)
+        assert st.clip_ids.tolist() == want_order
+        row_of = {c: k for k, c in enumerate(cids)}
+        perm = np.array([row_of[c] for c in want_order])
+        Xo, Po = X[perm].astype(np.float32).astype(np.float64), present[perm]
+        Xo = Xo * Po[..., None]
+        T = np.array([[t.target.target_features[s].get(p, np.zeros(X.shape[3])) for p in st.splits] for s in STREAMS], np.float64)
+        have = np.array([[p in t.target.target_features[s] for p in st.splits] for s in STREAMS])
+        sims64, _ = sc.similarities(Xo, T, Po & have[None])
+        w = [hp.weights[s] for s in STREAMS]
+        s64 = sc.scores(sims64, w)
+        assert_scores_close(t.scores.array(), s64)
+        if kind == "new":
+            random.setstate(state)
+            want_T = sc.scale_target(X[7])
+            assert np.abs(T - want_T).max() <= 1e-6 * np.abs(want_T).max()
+            th, near = hp.threshold, hp.near_miss_default
+            m64, nm64 = sc.classify(s64, th, near)
+            if not t.tie_band:
+                picked = random.sample(range(len(m64)), int(min(16 / 2, len(m64))))
+                assert list(t.matches)[:len(picked)] == [want_order[m64[j]] for j in picked]
+    assert api.calls.count(("search-sets", "features")) == 1 + 3      # built once; the test itself read it three times
+    vq.invalidate()
+
+
+def test_partial_target_then_full_target_on_the_shared_store(vq):
+    """The resident store is shared by every job of a search set: the per-row split-weight table a job with a PARTIAL
+    target uploads (the reference averages over splits that both the target and the clip have, ticket.py:146-160) must
+    not leak into the next job's scan, its labelled similarities or a batched scan."""
+    rng = np.random.default_rng(3)
+    n, S, P, dim = 3000, 2, 3, 256
+    X = (rng.random((n, S, P, dim)) * rng.random((n, 1, 1, 1))).astype(np.float32)
+    st = vq.FeatureStore(n, STREAMS, [1, 2, 3], dim, devices=[0])
+    st.upload(0, X)
+    X64 = X.astype(np.float64)
+    T = sc.scale_target(X64[5])
+    full = {s: {p: T[si, pi] for pi, p in enumerate([1, 2, 3])} for si, s in enumerate(STREAMS)}
+    part = {s: {p: T[si, pi] for pi, p in enumerate([1, 2, 3]) if not (si == 1 and p == 3)} for si, s in enumerate(STREAMS)}
+    have = np.ones((S, P), bool)
+    have[1, 2] = False
+    ones = np.ones((n, S, P), bool)
+    w = (1.0, 1.5)
+    want_full = sc.scores(sc.similarities(X64, T, ones)[0], w)
+    want_part = sc.scores(sc.similarities(X64, T * have[..., None], ones & have[None])[0], w)
+    rows = np.arange(0, n, 97, dtype=np.int64)
+    for target, want in ((full, want_full), (part, want_part), (full, want_full), (part, want_part), (part, want_part),
+                         (full, want_full)):
+        st.scan(target, w, 0.7, 0.6, EPS, topk=10)
+        assert_scores_close(st.scores(), want)
+        T_here = T * have[..., None] if target is part else T
+        l64 = sc.similarities(X64[rows], T_here, (ones & have[None])[rows] if target is part else ones[rows])[0]
+        assert np.abs(st.labelled_sims(target, rows) - l64).max() <= 1e-9 * np.abs(l64).max()
+    st.scan(part, w, 0.7, 0.6, EPS)
+    got = st.scan_batch([full, full], w, 0.7, 0.6, debug_scores=True)       # a batch after a partial single-query job
+    assert_scores_close(got[0], want_full, floor=0.25)
+    with pytest.raises(vq.VQError):
+        st.scan_batch([full, part], w, 0.7, 0.6, topk=3)                  # one table per pass: mixed slot sets are refused
+    # an append between two jobs with the same partial target: the table is applied again to the grown shard
+    st.scan(part, w, 0.7, 0.6, EPS)
+    extra = (rng.random((50, S, P, dim)) * 0.5).astype(np.float32)
+    st.append(extra)
+    st.scan(part, w, 0.7, 0.6, EPS)
+    Xg = np.concatenate([X64, extra.astype(np.float64)])
+    want = sc.scores(sc.similarities(Xg, T * have[..., None], np.ones((n + 50, S, P), bool) & have[None])[0], w)
+    assert_scores_close(st.scores(), want)
+    st.close()
+
+
+def test_singular_labelled_set_is_an_error_not_a_nan_target(vq):
+    """A labelled clip listed twice makes the Gram matrix singular: numpy.linalg.inv raises in the reference
+    (target_clip.py:194); here the solve kernel flags the zero pivot and the call fails loudly instead of returning NaNs."""
+    X = synth.database(8, 60)[:, :, None, :]
+    st = vq.FeatureStore(60, STREAMS, [1], 1024, devices=[0])
+    st.upload(0, X)
+    with pytest.raises(vq.VQError, match="singular"):
+        st.bootstrap_target(np.array([3, 9, 3]), None, 0.0)
+    ok = st.bootstrap_target(np.array([3, 9, 12]), np.array([20, 21]), 0.3)
+    assert np.isfinite(ok).all()
+    st.close()
+
+
+def test_finalize_selection_of_a_large_search_set_is_array_work(vq, tmp_path, monkeypatch):
+    """Finalize on a 1M-clip store with ~90k matches: select_clips_to_review (max = inf: a seeded permutation of every
+    match and near miss, ticket.py:333,341) and the report order (stable descending sort of the selection, ticket.py:266,
+    ranked on the device with vq_rank_list) against their plain-Python restatement on the device's scores, and the host
+    time of both (the per-clip HTTP calls of persistence are the API's contract and are not part of this)."""
+    import time
+    import types
+    n, seed = 1_000_000, synth.DEFAULT_SEED
+    st = vq.FeatureStore(n, STREAMS, [1], 1024, devices=[0], clip_ids=np.arange(n) * 2 + 10)
+    st.fill_synthetic(seed)
+    T = sc.scale_target(synth.rows(seed, [18120]).astype(np.float64)[0][:, None, :])
+    user = {str(10 + 2 * r): (r % 3 != 0) for r in range(1000, 600_000, 997)}        # ~600 labelled clips, a third rejected
+    job = {"query_id": 1, "video_id": 1, "ref_clip": 0, "ref_clip_id": 10 + 2 * 18120, "search_set": 1,
+           "number_of_matches_to_review": 20, "dynamic_target_adjustment": False, "user_matches": user}
+    t = vq.Ticket(job, "http://fake/", client=object(), schema=object(), store=st)
+    t.target = types.SimpleNamespace(target_features=tdict(T), splits={1})
+    t._hp = vq.Hyperparameter({"rgb": 1.0, "warped_optical_flow": 1.5})
+    t._weights = {"rgb": 1.0, "warped_optical_flow": 1.5}
+    th, near = 0.8, 0.35
+    random.seed(a="finalize")
+    t.select_clips_to_review(th, float("inf"), near)                 # warm-up (mirror growth, staging allocations)
+    random.seed(a="finalize")
+    t0 = time.perf_counter()
+    t.select_clips_to_review(th, float("inf"), near)
+    t_sel = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    ranked = t.ranked_selection()
+    t_rank = time.perf_counter() - t0
+    state_after = None
+    # the reference's selection, restated on the device's own scores
+    scores = st.scores()
+    ids = st.clip_ids
+    g = scores.astype(np.float64)
+    lo = th - near * (1 - th)
+    M = {int(ids[r]): float(scores[r]) for r in np.flatnonzero(g >= th)}
+    NM = {int(ids[r]): float(scores[r]) for r in np.flatnonzero((g >= lo) & (g < th))}
+    assert len(M) >= 50_000
+    random.seed(a="finalize")
+    picked = random.sample(list(M.items()), len(M))
+    best = max(NM, key=lambda k: NM[k])
+    best_item = {best: NM.pop(best)}
+    picked_n = random.sample(list(NM.items()), len(NM))
+    want = dict(picked + picked_n)
+    want.update(best_item)
+    forced = {job["ref_clip_id"]: float(scores[18120])}
+    forced.update({int(c): float(scores[(int(c) - 10) // 2]) for c, v in user.items() if v is True})
+    want.update(forced)
+    assert list(t.matches.items()) == list(want.items())
+    assert ranked == sorted(want.items(), key=lambda kv: kv[1], reverse=True)
+    print("finalize on %d clips: %d selected; selection %.1f ms (scan included), report order %.1f ms"
+          % (n, len(want), 1e3 * t_sel, 1e3 * t_rank))
+    assert t_sel + t_rank < 0.25, (t_sel, t_rank)      # the Python-object floor: two dicts of ~180k entries
+    st.close()
+
+
+def test_store_follows_a_growing_search_set_on_the_gpu(vq, tmp_path, monkeypatch):
+    """load_db.py adds clips between ticks (reference load_db.py:10-28; the reference re-reads the search set per job): the
+    resident store notices (the search-set record changed) and appends the new clips — results equal a store built fresh."""
+    from fake_api import FakeRepository
+    scn = Scenario("B_both_simple_mu")
+    api, qid = scn.build_api()
+    monkeypatch.chdir(tmp_path)
+    vq.invalidate()
+    ss = api.queries[qid]["search_set_to_query"]
+    all_ids = list(api.search_sets[ss]["clip_ids"])
+    made = []
+    fac = lambda job, url: made.append(vq.Ticket(job, url, client=api.client(), devices=[0])) or made[-1]
+    api.search_sets[ss]["clip_ids"] = all_ids[:120]
+    api.request(qid, "new")
+    random.seed(a=scn.seed)
+    vq.compute_matches(FakeRepository(api), vq.Hyperparameter(**scn.hp()), ticket_factory=fac)
+    st = made[-1].feature_store()
+    assert st.n_rows == 120
+    api.search_sets[ss]["clip_ids"] = all_ids
+    api.request(qid, "new")
+    random.seed(a=scn.seed)
+    vq.compute_matches(FakeRepository(api), vq.Hyperparameter(**scn.hp()), ticket_factory=fac)
+    assert made[-1].feature_store() is st and st.clip_ids.tolist() == all_ids
+    grown_scores, grown_sel = made[-1].scores.array().copy(), list(made[-1].matches.items())
+    assert_scores_close(grown_scores, scn.arr(0, "scores"))
+    vq.invalidate()
+    api.request(qid, "new")
+    random.seed(a=scn.seed)
+    vq.compute_matches(FakeRepository(api), vq.Hyperparameter(**scn.hp()), ticket_factory=fac)
+    assert made[-1].feature_store() is not st
+    assert np.array_equal(made[-1].scores.array(), grown_scores) and list(made[-1].matches.items()) == grown_sel
+    vq.invalidate()
+
+
+def test_config4_batched_scan_at_size_matches_float64_on_sampled_rows(vq):
+    """BASELINE configs[3] at a size the tensor-core pipeline runs in steady state (2M clips x 256 queries, several launches
+    of 16 tiles per CTA): per-query counts against the single-query scan, every top-k row and a seeded sample of rows
+    against float64 on rows regenerated on the CPU."""
+    n, Q, seed = 2_000_000, 256, 20261018
+    st = vq.FeatureStore(n, STREAMS, [1], 1024, devices=[0])
+    st.fill_synthetic(seed)
+    qrows = 18120 + 37 * np.arange(Q)
+    Xq = synth.rows(seed, qrows).astype(np.float64)[:, :, None, :]
+    T = np.stack([sc.scale_target(x) for x in Xq]).astype(np.float32)
+    w, th, lo = (1.0, 1.5), 0.8, sc.lower_limit(0.8, 0.35)
+    counts, rows, scores, ms = st.scan_batch(T, w, th, lo, topk=100)
+    assert rows.shape == (Q, 100) and (rows >= 0).all()
+    for q in (0, 100, 255):
+        res = st.scan(tdict(T[q].astype(np.float64)), w, th, lo, EPS, topk=100)
+        single = st.scores()
+        # fp32 CUDA-core scores vs tensor-core scores differ by ~1e-6: counts agree up to the rows that close to a boundary
+        g = single.astype(np.float64)
+        slack_m = np.count_nonzero(np.abs(g - th) < 1e-5)
+        slack_n = slack_m + np.count_nonzero(np.abs(g - lo) < 1e-5)
+        assert abs(int(counts[q, 0]) - res.n_match) <= slack_m and abs(int(counts[q, 1]) - res.n_near) <= slack_n
+        rng = np.random.default_rng(q)
+        chk = np.unique(np.concatenate([rows[q], rng.integers(0, n, 400)]))
+        Xc = synth.rows(seed, chk).astype(np.float64)[:, :, None, :]
+        s64 = sc.scores(sc.similarities(Xc, T[q].astype(np.float64))[0], w)
+        at = np.searchsorted(chk, rows[q])
+        assert_scores_close(scores[q], s64[at])
+        assert np.all(np.diff(scores[q]) <= 0)
+        # the k-th best of the batch is at least as good as every sampled row outside the top-k (up to the error budget)
+        outside = np.setdiff1d(np.arange(len(chk)), at)
+        assert s64[outside].max() <= float(scores[q][-1]) + 1e-5
+    assert rows[0][0] == 18120 and scores[0][0] == pytest.approx(1.0, abs=2e-6)
+    st.close()
+
+
+def test_config5_replicate_weight_update_at_size_matches_oracle(vq):
+    """BASELINE configs[4] at its size: 1000 seeded replicates over 5000 labelled clips (labelled similarities in fp64 on
+    the GPU, one loss-grid launch for all replicates) — replicate index sets equal to the reference's draws
+    (random.choices + set, target_clip.py:297-309), loss grids equal to the oracle's on a sample of replicates."""
+    L, R, n, seed = 5000, 1000, 200_000, 20261018
+    st = vq.FeatureStore(n, STREAMS, [1], 1024, devices=[0], clip_ids=np.arange(n))
+    st.fill_synthetic(seed)
+    T = sc.scale_target(synth.rows(seed, [18120]).astype(np.float64)[0][:, None, :])
+    rows = np.sort(np.random.default_rng(7).choice(n, L, replace=False)).astype(np.int64)
+    sims = st.labelled_sims(tdict(T), rows)
+    X64 = synth.rows(seed, rows[:200]).astype(np.float64)[:, :, None, :]
+    want_sims, _ = sc.similarities(X64, T)
+    assert np.abs(sims[:200] - want_sims).max() <= 1e-12 * np.abs(want_sims).max()
+    labels = sc.scores(sims, (1.0, 1.5)) >= 0.62
+    random.seed("73459912436")
+    state = random.getstate()
+    reps = vq.resample_labelled(L, R, random)
+    after = random.getstate()
+    random.setstate(state)
+    for r in (0, 1, R - 1):                                     # the reference's own draws for the first replicates ...
+        want = list(set(random.choices(range(L), k=L)))
+        if r < 2:
+            assert reps[r].tolist() == want
+    wg, tg = sc.weight_grid(), sc.threshold_grid()
+    got = vq.loss_grid(sims, labels, wg, tg, 0.1, replicates=reps)
+    assert got.shape == (R, 40, 31)
+    for r in (0, 17, 500, R - 1):
+        want = sc.loss_grid_fast(sims[reps[r]], labels[reps[r]], wg, tg, 0.1)
+        assert np.abs(got[r] - want).max() < 1e-13
+    random.setstate(after)
+    st.close()

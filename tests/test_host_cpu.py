@@ -722,6 +722,9 @@ def test_store_build_and_append_from_feature_records_issue_the_right_uploads(mon
     fake = _RecordingLib()
     monkeypatch.setattr(ps, "lib", lambda: fake)
     monkeypatch.setattr(ps, "ptr", lambda a: a)
+    monkeypatch.setattr(ps.FeatureStore, "_alloc_staging", lambda self, n: np.empty(int(n), np.float32))   # pinned in the product
+    monkeypatch.setattr(ps.FeatureStore, "_free_staging", lambda self, a: None)
+    monkeypatch.setattr(ps.FeatureStore, "CHUNK_BYTES", 7 * 2 * 3 * 8 * 4)                              # 7 rows per staging chunk
     streams, rng = ("rgb", "warped_optical_flow"), np.random.default_rng(4)
     recs = _records(rng, 30, [1, 2, 3], 8)
     st = ps.FeatureStore.from_feature_rows(recs, streams, "global_pool", devices=[0])
@@ -729,8 +732,11 @@ def test_store_build_and_append_from_feature_records_issue_the_right_uploads(mon
     assert list(st.clip_ids) == order and st.splits == splits and st.n_rows == len(order) and st.dim == 8
     (create,) = fake.of("vq_store_create")
     assert create[2:] == (0, len(order), 2, 3, 8, 0)
-    (up,) = fake.of("vq_store_upload")
-    assert up[2:4] == (0, len(order)) and np.array_equal(up[4], X.reshape(len(order), -1))
+    ups = fake.of("vq_store_upload_async")                      # the ingest pipeline: 7-row chunks through two staging buffers
+    assert [u[2:4] for u in ups] == [(r, min(7, len(order) - r)) for r in range(0, len(order), 7)]
+    assert np.array_equal(np.concatenate([u[4] for u in ups]), X.reshape(-1))
+    names = [c[0] for c in fake.calls if c[0] in ("vq_store_upload_async", "vq_store_sync")]
+    assert names[:2] == ["vq_store_upload_async"] * 2 and names[2] == "vq_store_sync" and names[-1] == "vq_store_sync"
     (sw,) = fake.of("vq_store_set_split_weights")
     assert np.allclose(sw[2], 1.0 / present.sum(axis=2)) and not present.all()
     # append: a response that repeats held clips and brings new ones, some of which lack splits
@@ -770,7 +776,7 @@ def test_every_entry_point_refuses_null_arguments_without_crashing(built_lib):
     seen = 0
     for line in p.stdout.splitlines():
         name, rc, msg_len = line.split()
-        if name.endswith("_destroy"):
+        if name.endswith("_destroy") or name.endswith("_free"):
             assert int(rc) == 0, line
         else:
             assert int(rc) < 0 and int(msg_len) > 0, line

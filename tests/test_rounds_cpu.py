@@ -57,6 +57,18 @@ def make_oracle_store_class():
             present = np.asarray(present, bool)
             self.present = None if present.all() else present
 
+        def _alloc_staging(self, n_floats):
+            return np.empty(int(n_floats), np.float32)
+
+        def _free_staging(self, a):
+            pass
+
+        def _upload_async(self, first_row, flat):
+            self.upload(first_row, np.array(flat))
+
+        def _sync_uploads(self):
+            pass
+
         def _sync_split_weights_for_target(self, have):
             pass
 
@@ -180,7 +192,7 @@ def test_product_host_path_replays_reference_rounds_end_to_end(cpu_product, name
     api, qid = scn.build_api()
     (tmp_path / "work").mkdir()
     monkeypatch.chdir(tmp_path / "work")                     # the final report goes to ../final_reports/
-    rule = (lambda m: False) if scn.meta["label_rule"] == "False" else scn.label_rule()
+    rule = scn.label_rule()
     tickets = []
 
     def factory(job, url):
@@ -283,7 +295,52 @@ def test_job_error_states_follow_the_reference_on_cpu(cpu_product, tmp_path, mon
     vq.compute_matches(FakeRepository(api), vq.Hyperparameter(**both.hp()), ticket_factory=fac)
     st = made[-1].feature_store()
     assert st.n_rows == 120
+    # load_db.py adds clips: the next job sees them without anybody telling the store (the search-set record changed)
+    api.search_sets[ss]["clip_ids"] = all_ids[:150]
+    api.request(qid, "new")
+    random.seed(a=both.seed)
+    vq.compute_matches(FakeRepository(api), vq.Hyperparameter(**both.hp()), ticket_factory=fac)
+    assert made[-1].feature_store() is st and st.n_rows == 150 and list(st.clip_ids) == all_ids[:150] and st.X.shape[0] == 150
+    assert api.calls.count(("search-sets", "features")) == 2
+    api.request(qid, "new")                                   # nothing changed: no second download
+    vq.compute_matches(FakeRepository(api), vq.Hyperparameter(**both.hp()), ticket_factory=fac)
+    assert api.calls.count(("search-sets", "features")) == 2 and made[-1].feature_store() is st
+    # an API whose search-set record does not change: VQ_STORE_FRESHNESS=always re-reads per job like the reference
+    api.search_set_record = "bare"
+    api.request(qid, "new")
+    vq.compute_matches(FakeRepository(api), vq.Hyperparameter(**both.hp()), ticket_factory=fac)   # record changed shape: one re-read
+    n_calls = api.calls.count(("search-sets", "features"))
+    api.search_sets[ss]["clip_ids"] = all_ids[:170]
+    api.request(qid, "new")
+    vq.compute_matches(FakeRepository(api), vq.Hyperparameter(**both.hp()), ticket_factory=fac)
+    assert st.n_rows == 150 and api.calls.count(("search-sets", "features")) == n_calls       # the probe cannot see it ...
+    monkeypatch.setenv("VQ_STORE_FRESHNESS", "always")
+    api.request(qid, "new")
+    vq.compute_matches(FakeRepository(api), vq.Hyperparameter(**both.hp()), ticket_factory=fac)
+    assert made[-1].feature_store() is st and st.n_rows == 170                                  # ... `always` does
+    monkeypatch.delenv("VQ_STORE_FRESHNESS")
+    # ... and so does a job that names a clip the store does not hold (a label on a new clip)
+    api.search_sets[ss]["clip_ids"] = all_ids[:180]
+    api.request(qid, "new")
+    job_holder = {}
+    real_status = FakeRepository.get_status
+    def with_label(self):
+        status = real_status(self)
+        status["new"]["user_matches"] = {str(all_ids[175]): True}
+        return status
+    monkeypatch.setattr(FakeRepository, "get_status", with_label)
+    vq.compute_matches(FakeRepository(api), vq.Hyperparameter(**both.hp()), ticket_factory=fac)
+    monkeypatch.setattr(FakeRepository, "get_status", real_status)
+    assert st.n_rows == 180 and all_ids[175] in made[-1].matches
+    # clips removed (or reordered): the store is rebuilt from the response
+    api.search_set_record = "members"
+    api.search_sets[ss]["clip_ids"] = all_ids[5:100]
+    api.request(qid, "new")
+    vq.compute_matches(FakeRepository(api), vq.Hyperparameter(**both.hp()), ticket_factory=fac)
+    st2 = made[-1].feature_store()
+    assert st2 is not st and list(st2.clip_ids) == all_ids[5:100]
+    st = st2
     api.search_sets[ss]["clip_ids"] = all_ids
     rows = api.client().action(None, ["search-sets", "features"], params={"id": ss})
-    assert st.append_feature_rows(rows, both.hp()["feature_name"]) == len(all_ids) - 120
-    assert list(st.clip_ids) == all_ids and st.X.shape[0] == len(all_ids)
+    assert st.append_feature_rows(rows, both.hp()["feature_name"]) == len(all_ids) - 95
+    assert sorted(st.clip_ids) == sorted(all_ids) and st.X.shape[0] == len(all_ids)

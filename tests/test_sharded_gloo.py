@@ -141,6 +141,20 @@ def _rank_collectives(rank, world, port, n_total, k, nq, out_dir):
     (g_rows, g_sc), (n_rows, n_sc), (tie_rows, tie_sc) = sharded.gather_lists_torch(mine, [0, 1, 2], sm, dist, torch)
     views = sharded.gather_lists_torch(mine[:2], [0, 1], sm, dist, torch, copy=False)
     assert np.array_equal(views[0][0], g_rows) and np.array_equal(views[1][1], n_sc)
+    # the same lists delivered to ONE rank (unpadded point-to-point segments), and left sharded
+    for root in (0, 1):
+        at_root = sharded.gather_lists_root(mine, [0, 1, 2], sm, dist, torch, root=root)
+        if rank == root:
+            for (a_r, a_s), (b_r, b_s) in zip(at_root, [(g_rows, g_sc), (n_rows, n_sc), (tie_rows, tie_sc)]):
+                assert np.array_equal(a_r, b_r) and np.array_equal(a_s, b_s)
+        else:
+            assert at_root is None
+    sh = sharded.ShardedLists(sm, rank, [(first + m, score0[m]), (first + nm, score0[nm]), (first + ties, score0[ties])])
+    for name, (w_rows, w_sc) in (("matches", (g_rows, g_sc)), ("near_misses", (n_rows, n_sc)), ("ties", (tie_rows, tie_sc))):
+        a, b = sh.span(name)
+        assert np.array_equal(sh.local(name)[0], w_rows[a:b]) and np.array_equal(sh.local(name)[1], w_sc[a:b])
+        assert sh.total(name) == len(w_rows) and all(sh.owner(name, p) == rank for p in range(a, b))
+        assert sh.span(name, 0)[1] == sh.span(name, 1)[0] and sh.span(name, 0)[0] == 0
     # a short tie band rides in the summary record itself; k = 0 and no near miss at all
     rec2 = sharded.summary_record(first, [0, 0, 2], [], [], 0, None, (first + ties[:2], score0[ties[:2]]))
     sm2 = sharded.exchange_summary(rec2, 0, dist, torch)

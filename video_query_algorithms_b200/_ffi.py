@@ -49,6 +49,10 @@ PROTOTYPES = {
     "vq_store_append": (C.c_int, [_vp, _i64, _vp]),
     "vq_store_describe": (C.c_int, [_vp, _i64p, _P(C.c_int), _P(C.c_int), _P(C.c_int), _i64p, _P(C.c_int)]),
     "vq_store_upload": (C.c_int, [_vp, _i64, _i64, _vp]),
+    "vq_store_upload_async": (C.c_int, [_vp, _i64, _i64, _vp]),
+    "vq_store_sync": (C.c_int, [_vp]),
+    "vq_pinned_alloc": (C.c_int, [_P(_vp), _i64]),
+    "vq_pinned_free": (C.c_int, [_vp]),
     "vq_store_download": (C.c_int, [_vp, _i64, _i64, _vp]),
     "vq_store_set_split_weights": (C.c_int, [_vp, _vp]),
     "vq_store_fill_synthetic": (C.c_int, [_vp, C.c_uint64, _vp]),
@@ -119,6 +123,32 @@ def lib():
             fn.restype, fn.argtypes = res, args
         _lib = handle
     return _lib
+
+
+PYHOST_PATH = os.path.join(HERE, "lib", "libvq_pyhost.so")
+_pyhost = None
+
+
+def pyhost():
+    """libvq_pyhost.so (csrc/vq_pyhost.c): unboxes API records into the store's row layout.  PyDLL: its functions take
+    Python objects and are called with the GIL held."""
+    global _pyhost
+    if _pyhost is None:
+        if not os.path.exists(PYHOST_PATH):
+            raise VQError("libvq_pyhost.so is not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+        h = C.PyDLL(PYHOST_PATH)
+        h.vq_py_last_error.restype = C.c_char_p
+        h.vq_py_index_records.restype = C.c_int
+        h.vq_py_index_records.argtypes = [C.py_object, C.py_object, C.py_object, _vp, _vp, _vp, _vp]
+        h.vq_py_fill_chunk.restype = C.c_int
+        h.vq_py_fill_chunk.argtypes = [C.py_object, _vp, _vp, _i64, _i64, _vp, _i32]
+        _pyhost = h
+    return _pyhost
+
+
+def check_py(rc, what):
+    if rc != 0:
+        raise VQError("%s failed: %s" % (what, (pyhost().vq_py_last_error() or b"?").decode()))
 
 
 def check(rc, what=""):

@@ -14,12 +14,26 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--expt-relaxed-constexpr"]
 
 
+PYHOST = os.path.join(PKG, "lib", "libvq_pyhost.so")     # CPython-API glue (record unboxing), plain C, no CUDA
+
+
 def needs_build():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(PYHOST):
         return True
-    t = os.path.getmtime(LIB)
+    t = min(os.path.getmtime(LIB), os.path.getmtime(PYHOST))
     deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "vq.h")]
     return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_pyhost():
+    import sysconfig
+    cc = os.environ.get("CC", "gcc")
+    cmd = [cc, "-O3", "-fPIC", "-shared", "-pthread", "-I", sysconfig.get_paths()["include"], "-o", PYHOST,
+           os.path.join(CSRC, "vq_pyhost.c")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building libvq_pyhost.so failed:\n" + r.stdout + r.stderr)
+    return PYHOST
 
 
 def build(force=False, verbose=False):
@@ -37,6 +51,7 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
     if verbose:
         print(r.stderr)
+    build_pyhost()
     return LIB
 
 

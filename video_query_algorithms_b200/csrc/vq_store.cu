@@ -293,6 +293,37 @@ extern "C" int vq_store_upload(vq_store *s, int64_t first_row, int64_t n_rows, c
     return 0;
 }
 
+// Pipelined ingest: the caller fills a pinned chunk (vq_pinned_alloc) while the previous chunk is still in flight —
+// enqueue only, one cudaMemcpyAsync per call; vq_store_sync waits for everything enqueued on the store's stream.
+extern "C" int vq_store_upload_async(vq_store *s, int64_t first_row, int64_t n_rows, const float *rows_pinned) {
+    if (int r = check_range(s, first_row, n_rows, "vq_store_upload_async")) return r;
+    VQ_REQUIRE(rows_pinned || n_rows == 0, "vq_store_upload_async: null rows");
+    if (n_rows == 0) return 0;
+    VQ_CUDA(cudaSetDevice(s->device));
+    VQ_CUDA(cudaMemcpyAsync(s->rows + (size_t)first_row * s->row_floats, rows_pinned, (size_t)n_rows * s->row_floats * sizeof(float),
+                            cudaMemcpyHostToDevice, s->stream));
+    return 0;
+}
+
+extern "C" int vq_store_sync(vq_store *s) {
+    VQ_REQUIRE(s, "vq_store_sync: null store");
+    VQ_CUDA(cudaSetDevice(s->device));
+    VQ_CUDA(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+extern "C" int vq_pinned_alloc(void **out, int64_t bytes) {
+    VQ_REQUIRE(out && bytes > 0, "vq_pinned_alloc: bad argument");
+    *out = nullptr;
+    VQ_CUDA(cudaMallocHost(out, (size_t)bytes));
+    return 0;
+}
+
+extern "C" int vq_pinned_free(void *p) {
+    if (p) cudaFreeHost(p);
+    return 0;
+}
+
 extern "C" int vq_store_download(vq_store *s, int64_t first_row, int64_t n_rows, float *rows_out) {
     if (int r = check_range(s, first_row, n_rows, "vq_store_download")) return r;
     VQ_REQUIRE(rows_out || n_rows == 0, "vq_store_download: null output");

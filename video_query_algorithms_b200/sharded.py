@@ -125,8 +125,9 @@ class RankScan:
                   "vq_merge_payloads_enqueue")
 
     def flush(self, stream_ptr):
-        """Lagged exchange: merge the last pushed step (enqueued; no host sync).  No-op for the other modes."""
-        if self.exchange == "p2p-lagged":
+        """Peer-memory exchange: merge the last pushed step if it is lagged, and make the caller's stream wait for the
+        exchange's own stream (enqueued; no host sync).  No-op for NCCL."""
+        if self.exchange in ("p2p", "p2p-lagged"):           # also joins the exchange's own stream into `stream_ptr`
             check(lib().vq_exchange_flush_enqueue(self._x, C.c_void_p(stream_ptr)), "vq_exchange_flush_enqueue")
 
     def kernels_per_step(self):
@@ -134,8 +135,18 @@ class RankScan:
 
     def result(self):
         """(counts[4], global top-k rows, scores) after the stream has been synchronised."""
+        if self._x is not None:
+            check(lib().vq_exchange_check(self._x), "vq_exchange_check")       # a peer that never delivered -> VQError, not a hang
         t = self.merged if self.world > 1 else self._payload_view()
         return unpack_payload(t.cpu().numpy(), self.k)
+
+    def exchange_times(self):
+        """device times (ms) of the exchange kernels since the last call (after a synchronisation)"""
+        if self._x is None:
+            return np.empty(0, np.float32)
+        out, n = np.empty(256, np.float32), C.c_int32()
+        check(lib().vq_exchange_kernel_times(self._x, 256, ptr(out), C.byref(n)), "vq_exchange_kernel_times")
+        return out[:n.value]
 
 
 def exchange_host(payload, dist, torch, k):
@@ -395,6 +406,90 @@ def gather_lists_torch(lists, which, summary, dist, torch, copy=True):
     return [(r.copy(), s_.copy()) for r, s_ in res] if copy else res
 
 
+def gather_lists_root(lists, which, summary, dist, torch, root=0, copy=True):
+    """The same lists delivered to ONE rank only (the rank that talks to the API; nobody else consumes whole lists):
+    every other rank sends its entries — exactly as many as it has, no padding — straight from device memory to `root`
+    (NCCL send / recv over NVLink; gloo in the CPU tests); `root` receives all segments into one device buffer in rank
+    order = database order, makes the rows global there and copies each list once into pinned host memory.  Returns the
+    lists on `root` (copy=False: views of the pinned memory, valid until the next call) and None elsewhere.  Against the
+    all-gather this moves 1/world of the bytes over the fabric and 1/world of them over PCIe, on one rank instead of all."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    counts = summary.counts[:, which]                          # [world, len(which)]
+    per_rank = counts.sum(axis=1)
+    n_mine = int(per_rank[rank])
+    dev = lists[0][0].device
+    # my segment: int32 local rows of all lists back to back, then their fp32 scores (bit pattern) — 8 bytes per entry
+    mine = torch.empty(2 * n_mine, dtype=torch.int32, device=dev)
+    o = 0
+    for (rows, scores), n in zip(lists, counts[rank]):
+        n = int(n)
+        if n:
+            mine[o:o + n] = rows[:n]
+            mine[n_mine + o:n_mine + o + n] = scores[:n].view(torch.int32)
+        o += n
+    if rank != root:
+        if n_mine:
+            dist.send(mine, root)
+        return None
+    total = int(per_rank.sum())
+    if total == 0:
+        return [(np.empty(0, np.int64), np.empty(0, np.float32)) for _ in which]
+    segs = [mine if r == rank else torch.empty(2 * int(per_rank[r]), dtype=torch.int32, device=dev) for r in range(world)]
+    ops = [dist.P2POp(dist.irecv, segs[r], r) for r in range(world) if r != rank and int(per_rank[r])]
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    h_rows, h_scores = _host_out(torch, dev, total)
+    spans, o = [], 0
+    starts = np.concatenate([np.zeros((world, 1), np.int64), np.cumsum(counts, axis=1)], axis=1)
+    for j in range(len(which)):
+        n_j = int(counts[:, j].sum())
+        if n_j:
+            r_parts, s_parts = [], []
+            for r in range(world):
+                a, n, nr = int(starts[r, j]), int(counts[r, j]), int(per_rank[r])
+                if n:
+                    r_parts.append(segs[r][a:a + n].to(torch.int64) + int(summary.first_rows[r]))
+                    s_parts.append(segs[r][nr + a:nr + a + n].view(torch.float32))
+            h_rows[o:o + n_j].copy_(torch.cat(r_parts), non_blocking=True)
+            h_scores[o:o + n_j].copy_(torch.cat(s_parts), non_blocking=True)
+        spans.append((o, n_j))
+        o += n_j
+    if dev.type == "cuda":
+        torch.cuda.current_stream(dev).synchronize()
+    np_rows, np_scores = h_rows.numpy(), h_scores.numpy()
+    res = [(np_rows[a:a + n], np_scores[a:a + n]) for a, n in spans]
+    return [(r.copy(), s_.copy()) for r, s_ in res] if copy else res
+
+
+class ShardedLists:
+    """The search set's ordered match / near-miss / tie lists left where the scan put them: every rank holds its own
+    segment (global rows + fp32 scores in its pinned host mirror); the segments in rank order ARE the lists in database
+    order, and the per-rank counts every rank received with the summary record map a list position to its owner without
+    further traffic.  `local(which)` = this rank's segment; `span(which, rank)` = the positions it covers."""
+
+    _COL = {"matches": 0, "near_misses": 1, "ties": 2}
+
+    def __init__(self, summary, rank, local_lists):
+        self.counts = summary.counts                           # [world, 3]
+        self.offsets = np.concatenate([np.zeros((1, 3), np.int64), np.cumsum(summary.counts, axis=0)])[:-1]
+        self.rank, self._local = rank, local_lists
+
+    def local(self, which):
+        return self._local[self._COL[which]]
+
+    def span(self, which, rank=None):
+        r, c = self.rank if rank is None else rank, self._COL[which]
+        return int(self.offsets[r, c]), int(self.offsets[r, c] + self.counts[r, c])
+
+    def total(self, which):
+        return int(self.counts[:, self._COL[which]].sum())
+
+    def owner(self, which, position):
+        c = self._COL[which]
+        return int(np.searchsorted(self.offsets[:, c] + self.counts[:, c], position, side="right"))
+
+
 def gather_positions_multi(requests, summary, local_gather, dist, torch, device=None, mailbox=None):
     """requests: [(list column in the summary's counts, positions in the search set's list)], the same on every
     rank.  Each rank fetches the entries its own lists hold with `local_gather(column, local positions) -> (global
@@ -472,19 +567,35 @@ class RankStore:
                             torch.as_tensor(_DevArray(scores_p, n, "<f4"), device=self.device)))
         return out
 
-    def scan(self, target_features, weights, threshold, lower_limit, eps, topk=0, copy=True):
-        """Full single-query result: counts [match, near, tie], ordered global match / near-miss / tie lists and the
-        merged top-k on every rank.  The match and near-miss lists never touch this rank's host on the way out: they are
-        gathered device to device and land once, whole, in pinned memory (copy=False: views of it, valid until the next
-        call, like FeatureStore.matches(copy=False))."""
+    def scan(self, target_features, weights, threshold, lower_limit, eps, topk=0, copy=True, lists="sharded", root=0):
+        """Full single-query result: counts [match, near, tie] and the merged top-k on every rank, plus the ordered
+        global match / near-miss / tie lists:
+          lists="sharded" (default): each rank publishes ITS segment into its pinned host mirror exactly like a single-GPU
+            scan and nothing else moves — the result is a ShardedLists (segments in rank order = the lists in database
+            order; every rank knows every segment's length).  No consumer of the path needs the whole lists on every rank.
+          lists="root": the whole lists on rank `root` only (the one that talks to the API; None elsewhere), sent device to
+            device without padding (gather_lists_root).
+          lists="all": replicated on every rank with one padded all-gather (gather_lists_torch) — world x the bytes.
+        One exchange of a fixed-size summary record per rank (host mailbox) in every mode."""
+        if lists == "sharded":
+            res = self.store.scan(target_features, weights, threshold, lower_limit, eps, topk=topk, lists=True)
+            self._summarise(res, int(topk))
+            sm = self.summary
+            local = [self.store.matches(copy=copy), self.store.near_misses(copy=copy), self.store.ties(copy=copy)]
+            return sm.total, ShardedLists(sm, self.dist.get_rank(), local), sm.topk
         res = self.store.scan(target_features, weights, threshold, lower_limit, eps, topk=topk, lists=False)
         self._summarise(res, int(topk))
         sm = self.summary
         which = [0, 1] if sm.ties is not None else [0, 1, 2]
-        lists = gather_lists_torch(self._device_lists(which), which, sm, self.dist, self.torch, copy=copy)
+        if lists == "root":
+            out = gather_lists_root(self._device_lists(which), which, sm, self.dist, self.torch, root=root, copy=copy)
+            if out is not None and sm.ties is not None:
+                out.append(sm.ties)
+            return sm.total, out, sm.topk
+        out = gather_lists_torch(self._device_lists(which), which, sm, self.dist, self.torch, copy=copy)
         if sm.ties is not None:
-            lists.append(sm.ties)
-        return sm.total, lists, sm.topk
+            out.append(sm.ties)
+        return sm.total, out, sm.topk
 
     def scan_select(self, target_features, weights, threshold, lower_limit, eps, topk=0):
         """The review round's variant (ticket.py:311-356 samples a few dozen clips): every rank's match / near-miss

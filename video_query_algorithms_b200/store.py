@@ -9,7 +9,6 @@ its seeded `random.sample` depends on (ticket.py:326-333).
 """
 from __future__ import annotations
 
-import array
 import ctypes as C
 from dataclasses import dataclass
 
@@ -64,65 +63,115 @@ def make_params(weights, threshold, lower_limit, eps, topk=0, want_sims=False):
     return p
 
 
-def _as_doubles(v):
-    """A feature vector as the API delivers it (list of Python floats) in a form numpy copies without per-element
-    dispatch: array('d') unboxes a list ~1.7x faster than assigning the list to an ndarray row (13 vs 23 us per 1024)."""
-    return array.array("d", v) if isinstance(v, list) else v
+class RecordIndex:
+    """What one pass over a `search-sets/features`-style response says about the rows it fills (host code, no device
+    call, no vector touched yet): clip ids in row order, the split numbers, the feature length, which (row, stream,
+    split) slots are present and — per slot — the record that fills it."""
+
+    def __init__(self, order, splits, dim, n_streams, rec, row, si, pi):
+        self.order, self.splits, self.dim, self.n_streams = order, splits, int(dim), int(n_streams)
+        self.n_rows = len(order)
+        self.rec, self.row, self.si, self.pi = rec, row, si, pi            # one entry per filled slot, sorted by row
+        self.row_floats = self.n_streams * len(splits) * self.dim
+        self.present = np.zeros((self.n_rows, self.n_streams, len(splits)), bool)
+        self.present[row, si, pi] = True
+
+    def fill(self, feature_rows, r0, r1, out, threads=0):
+        """float32(feature vectors) of rows [r0, r1) into `out` (float32 [>= (r1 - r0) * row_floats], C-contiguous); slots
+        no record fills are zeroed.  The unboxing runs in libvq_pyhost (several threads, csrc/vq_pyhost.c)."""
+        lo, hi = np.searchsorted(self.row, [r0, r1])
+        n_slots = (r1 - r0) * self.n_streams * len(self.splits)
+        flat = out.reshape(-1)[:(r1 - r0) * self.row_floats]
+        if hi - lo != n_slots:
+            flat[:] = 0
+        if hi == lo:
+            return
+        P = len(self.splits)
+        dest = np.ascontiguousarray((((self.row[lo:hi] - r0) * self.n_streams + self.si[lo:hi]) * P + self.pi[lo:hi])
+                                    * self.dim, dtype=np.int64)
+        rec = np.ascontiguousarray(self.rec[lo:hi], dtype=np.int64)
+        if threads <= 0:
+            import os
+            threads = min(len(os.sched_getaffinity(0)), 16)
+        _ffi.check_py(_ffi.pyhost().vq_py_fill_chunk(feature_rows, _ffi.ptr(rec), _ffi.ptr(dest), len(rec), self.dim,
+                                                     _ffi.ptr(flat), threads), "vq_py_fill_chunk")
 
 
-def pack_feature_rows(feature_rows, streams, feature_name, held=None):
-    """`search-sets/features`-style records -> the store's row layout, in one pass (host code, no device call).
+def index_feature_rows(feature_rows, streams, feature_name, held=None):
+    """One pass over `search-sets/features`-style records -> RecordIndex (and the records as a list).
     Applies the reference's filters (ticket.py:374-381: stream in `streams`, name == `feature_name`) and its dict
     semantics: clips in order of first appearance (= the insertion order of the reference's `scores` dict, which its
     seeded sampling walks), a later record of the same (clip, stream, split) overwrites an earlier one, slots no record
-    fills stay zero and are marked absent.  `held(clip ids) -> bool array` drops clips a store already holds (append).
+    fills are absent.  `held(clip ids) -> bool array` drops clips a store already holds (append).
     Row order on ragged data: the reference's `scores` dict is filled while it walks the FIRST stream split by split
     (ticket.py:146-160), so a clip enters at its first record of (first stream, lowest split it has there) — for
     complete data simply the order of first appearance, otherwise clips that lack the first split come after all
-    clips that have it.  Clips without any first-stream record (the reference raises KeyError for them) go last.
-    Returns (clip ids in row order, sorted split numbers, X float32 [n, S, P, dim], present bool [n, S, P])."""
-    s_of = {s: i for i, s in enumerate(streams)}
-    row, cells, split_set, enters = {}, [], set(), {}
-    for tf in feature_rows:
-        si = s_of.get(tf["dnn_stream_id"])
-        if si is None or tf["name"] != feature_name:
-            continue
-        c, p = tf["video_clip_id"], int(tf["dnn_stream_split"])
-        r = row.get(c)
-        if r is None:
-            r = row[c] = len(row)
-        split_set.add(p)
-        if si == 0:
-            key = (p, len(cells))
-            if key < enters.get(r, (float("inf"), 0)):
-                enters[r] = key
-        cells.append((r, si, p, tf["feature_vector"]))
-    order = list(row)
-    keys = [enters.get(r, (float("inf"), r)) for r in range(len(order))]
-    if any(a > b for a, b in zip(keys, keys[1:])):            # ragged first stream: re-seat the rows
-        perm = sorted(range(len(order)), key=keys.__getitem__)
-        seat = {old: new for new, old in enumerate(perm)}
-        order = [order[old] for old in perm]
-        cells = [(seat[r], si, p, v) for r, si, p, v in cells]
-    remap = None
-    if held is not None and order:
-        keep = ~np.asarray(held(order), dtype=bool)
+    clips that have it.  Clips without any first-stream record (the reference raises KeyError for them) go last."""
+    if not isinstance(feature_rows, list):
+        feature_rows = list(feature_rows)
+    streams = tuple(streams)
+    n = len(feature_rows)
+    clip, stream = np.empty(n, np.int64), np.empty(n, np.int32)
+    split, length = np.empty(n, np.int32), np.empty(n, np.int32)
+    _ffi.check_py(_ffi.pyhost().vq_py_index_records(feature_rows, streams, feature_name, _ffi.ptr(clip), _ffi.ptr(stream),
+                                                    _ffi.ptr(split), _ffi.ptr(length)), "vq_py_index_records")
+    rec = np.flatnonzero(stream >= 0)                          # kept records, in response order
+    clip, si, sp, length = clip[rec], stream[rec].astype(np.int64), split[rec].astype(np.int64), length[rec]
+    u, first_idx, inv = np.unique(clip, return_index=True, return_inverse=True)
+    by_first = np.argsort(first_idx, kind="stable")
+    rank = np.empty(len(u), np.int64)
+    rank[by_first] = np.arange(len(u))
+    row = rank[inv]                                            # row of each kept record: first appearance of its clip
+    order = u[by_first]
+    n_rows = len(order)
+    # ragged first stream: re-seat the rows by (lowest first-stream split, position of that record)
+    s0 = np.flatnonzero(si == 0)
+    key0 = np.full(n_rows, np.inf)
+    key1 = np.arange(n_rows, dtype=np.float64)
+    if len(s0):
+        o = np.lexsort((s0, sp[s0], row[s0]))
+        r_sorted = row[s0][o]
+        firsts = np.concatenate([[True], r_sorted[1:] != r_sorted[:-1]])
+        er = r_sorted[firsts]
+        key0[er] = sp[s0][o][firsts]
+        key1[er] = s0[o][firsts]
+    if n_rows > 1 and (np.any(key0[1:] < key0[:-1]) or np.any((key0[1:] == key0[:-1]) & (key1[1:] < key1[:-1]))):
+        perm = np.lexsort((key1, key0))
+        seat = np.empty(n_rows, np.int64)
+        seat[perm] = np.arange(n_rows)
+        order, row = order[perm], seat[row]
+    if held is not None and n_rows:
+        keep = ~np.asarray(held(order.tolist()), dtype=bool)
         remap = np.where(keep, np.cumsum(keep) - 1, -1)
-        order = [c for c, k in zip(order, keep) if k]
-        cells = [(int(remap[r]), si, p, v) for r, si, p, v in cells if remap[r] >= 0]
-        split_set = {p for _, _, p, _ in cells}
-    splits = sorted(split_set)
+        order = order[keep]
+        row = remap[row]
+        live = row >= 0
+        rec, row, si, sp, length = rec[live], row[live], si[live], sp[live], length[live]
+        n_rows = len(order)
+    splits = sorted(set(sp.tolist()))
+    dim = int(length[0]) if len(length) else 0
+    pi = np.searchsorted(np.asarray(splits, np.int64), sp) if len(sp) else sp
+    # one record per slot — the last one in response order — sorted by row
+    slot = (row * len(streams) + si) * max(len(splits), 1) + pi
+    if len(slot):
+        _, last_rev = np.unique(slot[::-1], return_index=True)
+        keep = np.sort(len(slot) - 1 - last_rev)
+        o = keep[np.argsort(row[keep], kind="stable")]
+        rec, row, si, pi = rec[o], row[o], si[o], pi[o]
+    return RecordIndex(order, splits, dim, len(streams), rec, row, si, pi), feature_rows
+
+
+def pack_feature_rows(feature_rows, streams, feature_name, held=None):
+    """`search-sets/features`-style records -> the store's row layout in host memory (see index_feature_rows for the
+    filters and the row order).  Returns (clip ids in row order, sorted split numbers, X float32 [n, S, P, dim],
+    present bool [n, S, P]).  FeatureStore.from_feature_rows does the same through pinned chunks without ever holding X."""
+    idx, feature_rows = index_feature_rows(feature_rows, streams, feature_name, held=held)
+    order = idx.order.tolist()
     if not order:
-        return order, splits, np.zeros((0, len(streams), len(splits), 0), np.float32), np.zeros((0, len(streams), len(splits)), bool)
-    p_of = {p: i for i, p in enumerate(splits)}
-    dim = len(cells[0][3])
-    X = np.zeros((len(order), len(streams), len(splits), dim), np.float32)
-    present = np.zeros((len(order), len(streams), len(splits)), bool)
-    for r, si, p, v in cells:
-        pi = p_of[p]
-        X[r, si, pi] = _as_doubles(v)
-        present[r, si, pi] = True
-    return order, splits, X, present
+        return order, idx.splits, np.zeros((0, len(streams), len(idx.splits), 0), np.float32), np.zeros((0, len(streams), len(idx.splits)), bool)
+    X = np.empty((idx.n_rows, len(streams), len(idx.splits), idx.dim), np.float32)
+    idx.fill(feature_rows, 0, idx.n_rows, X)
+    return order, idx.splits, X, idx.present
 
 
 class FeatureStore:
@@ -306,39 +355,117 @@ class FeatureStore:
     def append_feature_rows(self, feature_rows, feature_name):
         """Append the clips of a `search-sets/features`-style response that the store does not hold yet (same
         filters and first-appearance order as from_feature_rows); returns the number of clips added."""
-        order, splits, X, present = pack_feature_rows(feature_rows, self.streams, feature_name,
-                                                      held=lambda ids: self._lookup(ids) >= 0)
-        if not order:
+        idx, feature_rows = index_feature_rows(feature_rows, self.streams, feature_name, held=lambda ids: self._lookup(ids) >= 0)
+        return self._append_indexed(idx, feature_rows)
+
+    def _append_indexed(self, idx, feature_rows):
+        if not idx.n_rows:
             return 0
-        extra = [p for p in splits if p not in self.splits]
+        extra = [p for p in idx.splits if p not in self.splits]
         if extra:
             raise VQError("append_feature_rows: split %d is not one of the store's splits %s" % (extra[0], self.splits))
-        if splits != self.splits:                                   # the new clips lack some split: widen to the store's slots
-            at = [self.splits.index(p) for p in splits]
-            Xw = np.zeros((len(order),) + self.row_shape, np.float32)
-            pw = np.zeros((len(order),) + self.row_shape[:2], bool)
+        if idx.dim != self.dim:
+            raise VQError("append_feature_rows: feature length %d, the store holds %d" % (idx.dim, self.dim))
+        X = np.empty((idx.n_rows, len(self.streams), len(idx.splits), idx.dim), np.float32)
+        idx.fill(feature_rows, 0, idx.n_rows, X)
+        present = idx.present
+        if idx.splits != self.splits:                               # the new clips lack some split: widen to the store's slots
+            at = [self.splits.index(p) for p in idx.splits]
+            Xw = np.zeros((idx.n_rows,) + self.row_shape, np.float32)
+            pw = np.zeros((idx.n_rows,) + self.row_shape[:2], bool)
             Xw[:, :, at], pw[:, :, at] = X, present
             X, present = Xw, pw
-        self.append(X, clip_ids=order, present=present)
-        return len(order)
+        self.append(X, clip_ids=idx.order, present=present)
+        return idx.n_rows
+
+    def sync_feature_rows(self, feature_rows, feature_name):
+        """Bring the resident store up to date with a fresh `search-sets/features` response (load_db.py adds clips to a
+        search set between ticks, reference load_db.py:10-28; the reference itself re-reads everything per job).
+        Returns the number of clips appended (0: nothing new), or None when the response is not the store's rows plus
+        new ones at the end — clips removed, reordered, other splits — and the caller must rebuild from the response."""
+        idx, feature_rows = index_feature_rows(feature_rows, self.streams, feature_name)
+        n_old = self.n_rows
+        if idx.n_rows < n_old or not np.array_equal(idx.order[:n_old], self.clip_ids) or \
+                any(p not in self.splits for p in idx.splits) or (idx.n_rows and idx.dim != self.dim):
+            return None
+        at = [self.splits.index(p) for p in idx.splits]
+        old_present = np.ones((n_old,) + self.row_shape[:2], bool) if self.present is None else self.present
+        new_present = np.zeros((n_old,) + self.row_shape[:2], bool)
+        new_present[:, :, at] = idx.present[:n_old]
+        if not np.array_equal(old_present, new_present):
+            return None                                             # an old clip gained or lost a feature row
+        if idx.n_rows == n_old:
+            return 0
+        tail = idx.row >= n_old
+        sub = RecordIndex(idx.order[n_old:], idx.splits, idx.dim, idx.n_streams, idx.rec[tail], idx.row[tail] - n_old,
+                          idx.si[tail], idx.pi[tail])
+        return self._append_indexed(sub, feature_rows)
 
     def fill_synthetic(self, seed, means=None):
         m = None if means is None else np.asarray(means, dtype=np.float32)
         for sh in self.shards:
             check(lib().vq_store_fill_synthetic(sh.handle, int(seed), ptr(m)), "vq_store_fill_synthetic")
 
+    CHUNK_BYTES = 64 << 20           # pinned staging per buffer of the ingest pipeline (two buffers)
+
     @classmethod
     def from_feature_rows(cls, feature_rows, streams, feature_name, devices=None):
         """Build from the `search-sets/features` API response (list of feature dicts), applying the
-        reference's filters (ticket.py:374-381: stream in streams, name == feature_name)."""
+        reference's filters (ticket.py:374-381: stream in streams, name == feature_name).  The rows never exist as one
+        host array: they are unboxed chunk by chunk into pinned staging while the previous chunk is on its way to HBM."""
         streams = tuple(streams)
-        order, splits, X, present = pack_feature_rows(feature_rows, streams, feature_name)
-        if not order:
+        idx, feature_rows = index_feature_rows(feature_rows, streams, feature_name)
+        if not idx.n_rows:
             raise VQError("search set has no '%s' features for streams %s" % (feature_name, streams))
-        st = cls(len(order), streams, splits, X.shape[3], devices=devices, clip_ids=order)
-        st.upload(0, X)
-        st.set_present(present)
+        st = cls(idx.n_rows, streams, idx.splits, idx.dim, devices=devices, clip_ids=idx.order)
+        st._ingest(idx, feature_rows)
+        st.set_present(idx.present)
         return st
+
+    def _ingest(self, idx, feature_rows):
+        """Two pinned buffers: fill one (libvq_pyhost, several threads) while the other is in flight (one
+        cudaMemcpyAsync per chunk and shard); a buffer is refilled only after its copy has completed."""
+        rows_per = max(1, min(idx.n_rows, self.CHUNK_BYTES // (idx.row_floats * 4)))
+        bufs = [self._alloc_staging(rows_per * idx.row_floats) for _ in range(2 if idx.n_rows > rows_per else 1)]
+        try:
+            for i, r0 in enumerate(range(0, idx.n_rows, rows_per)):
+                r1 = min(r0 + rows_per, idx.n_rows)
+                buf = bufs[i % len(bufs)]
+                if i >= len(bufs):
+                    self._sync_uploads()                            # the copy out of this buffer (chunk i - 2) must be done;
+                idx.fill(feature_rows, r0, r1, buf)                 # chunk i - 1 is at most still in flight while this fills
+                self._upload_async(r0, buf[:(r1 - r0) * idx.row_floats])
+            self._sync_uploads()
+        finally:
+            for b in bufs:
+                self._free_staging(b)
+
+    # staging / asynchronous upload primitives (test doubles replace these four)
+    def _alloc_staging(self, n_floats):
+        p = C.c_void_p()
+        check(lib().vq_pinned_alloc(C.byref(p), int(n_floats) * 4), "vq_pinned_alloc")
+        a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(int(n_floats),))
+        self.__dict__.setdefault("_staging_ptrs", {})[a.ctypes.data] = p
+        return a
+
+    def _free_staging(self, a):
+        p = self.__dict__.get("_staging_ptrs", {}).pop(a.ctypes.data, None)
+        if p is not None:
+            lib().vq_pinned_free(p)
+
+    def _upload_async(self, first_row, flat):
+        n = len(flat) // int(np.prod(self.row_shape))
+        g0 = self.first_global_row + first_row
+        rf = int(np.prod(self.row_shape))
+        for sh in self.shards:
+            lo, hi = max(g0, sh.first), min(g0 + n, sh.first + sh.n_rows)
+            if hi > lo:
+                part = flat[(lo - g0) * rf:(hi - g0) * rf]
+                check(lib().vq_store_upload_async(sh.handle, lo - sh.first, hi - lo, ptr(part)), "vq_store_upload_async")
+
+    def _sync_uploads(self):
+        for sh in self.shards:
+            check(lib().vq_store_sync(sh.handle), "vq_store_sync")
 
     def close(self):
         for sh in self.shards:

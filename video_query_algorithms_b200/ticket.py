@@ -18,6 +18,7 @@ import json
 import logging
 import os
 import random
+import time
 from collections.abc import Mapping
 from datetime import datetime, timedelta
 from time import sleep
@@ -224,18 +225,70 @@ class Ticket:
         return self._store
 
     def _get_candidate_features(self, splits, hyperparameters):
-        """The resident store of this job's search set (built on first use from the same API action
-        the reference calls every job, ticket.py:363-365)."""
+        """The resident store of this job's search set: built on first use from the same API action the reference calls
+        every job (ticket.py:363-365), then kept across ticks — and kept CURRENT: the reference re-reads the search set
+        per job, so clips that load_db.py added since the last tick (reference load_db.py:10-28) must be scored too."""
         if self._store is not None:
             return self._store
         key = (self.api_url, self.search_set, tuple(hyperparameters.streams), hyperparameters.feature_name)
-
-        def build():
+        st = _store._REGISTRY.get(key)
+        if st is None:
+            st = self._build_store(key, hyperparameters, self._request(["search-sets", "features"], {"id": self.search_set}))
+        elif self._store_is_stale(st):
             rows = self._request(["search-sets", "features"], {"id": self.search_set})
-            return _store.FeatureStore.from_feature_rows(rows, hyperparameters.streams,
-                                                         hyperparameters.feature_name, devices=self.devices)
-        self._store = _store.get_store(key, build)
-        return self._store
+            added = st.sync_feature_rows(rows, hyperparameters.feature_name)
+            if added is None:                                 # not "what we hold plus new clips at the end": rebuild from the response
+                logging.info("search set %s changed in place: rebuilding its feature store", self.search_set)
+                _store.invalidate(key)
+                st = self._build_store(key, hyperparameters, rows)
+            else:
+                if added:
+                    logging.info("search set %s grew by %d clip(s): appended to the resident store", self.search_set, added)
+                st.freshness = self._freshness_probe()
+                st.built_at = time.monotonic()
+        self._store = st
+        return st
+
+    def _build_store(self, key, hyperparameters, rows):
+        st = _store.FeatureStore.from_feature_rows(rows, hyperparameters.streams, hyperparameters.feature_name,
+                                                   devices=self.devices)
+        st.freshness = self._freshness_probe()
+        st.built_at = time.monotonic()
+        _store.register_store(key, st)
+        return st
+
+    def _freshness_probe(self):
+        """A cheap API fact that changes when the search set does: the `search-sets/read` record (ticket.py:197-199
+        reads it for the report), canonicalised.  Whatever the API puts there — member videos, counts, a modification
+        stamp — takes part; fields that never change cost nothing."""
+        if os.environ.get("VQ_STORE_FRESHNESS", "probe") != "probe":
+            return None
+        try:
+            return json.dumps(self._request(["search-sets", "read"], {"id": self.search_set}), sort_keys=True, default=str)
+        except ConnectionError:
+            raise
+        except Exception:                                     # an API without that action: the other signals still apply
+            return None
+
+    def _store_is_stale(self, st):
+        """VQ_STORE_FRESHNESS = probe (default): stale when the search-set record changed, when this job names a clip
+        the store does not hold (the previous round's matches and the user's labels come from this search set), or when
+        the store is older than VQ_STORE_MAX_AGE_S (unset: no age limit).  `always` re-reads the search set every job
+        like the reference (only new clips are uploaded); `never` trusts the resident store."""
+        mode = os.environ.get("VQ_STORE_FRESHNESS", "probe")
+        if mode == "never":
+            return False
+        if mode == "always":
+            return True
+        prev = getattr(self, "matches", None)
+        named = [m["video_clip"] for m in prev] if isinstance(prev, list) else []
+        named += [int(c) for c in self.user_matches]
+        if named and (st._lookup(named) < 0).any():
+            return True
+        max_age = os.environ.get("VQ_STORE_MAX_AGE_S")
+        if max_age and time.monotonic() - getattr(st, "built_at", 0.0) > float(max_age):
+            return True
+        return self._freshness_probe() != getattr(st, "freshness", None)
 
     def attach_store(self, hyperparameters):
         """Resolve the store before the target is built (TargetClip reads labelled rows from it)."""
