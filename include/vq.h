@@ -232,7 +232,10 @@ int vq_loss_grid(int device, const double *sims /* [L][2] */, const uint8_t *lab
  * problem per slot, all solved in one call.  Resampling stays with the caller (Python RNG).  */
 int vq_bootstrap_target(vq_store *s, const int64_t *valid_rows, int32_t n_valid,
                         const int64_t *invalid_rows, int32_t n_invalid, double mu,
-                        double *target_out /* [S][P][dim] */);
+                        const uint8_t *slot_mask /* [S][P] nonzero = solve this slot; NULL = all */,
+                        double *target_out /* [S][P][dim]; slots not solved are zero */);
+/* A singular system in a solved slot (a labelled clip listed twice, dependent rows: numpy.linalg.inv raises LinAlgError in
+ * the reference, target_clip.py:194,248) or a non-finite result is an error, not a NaN target.                        */
 
 /* ---------------------------------------------------------------- batched queries (tcgen05)
  * Q targets scored against the shard in one pass; per query: counts and top-k.               */
@@ -240,6 +243,15 @@ int vq_scan_batch(vq_store *s, const float *targets /* [Q][S][P][dim] */, int32_
                   const vq_scan_params *p, int64_t *counts_out /* [Q][2] match, near */,
                   int64_t *topk_rows_out /* [Q][topk] */, float *topk_scores_out /* [Q][topk] */,
                   float *kernel_ms_out);
+
+/* The same plus every query's tie band (north_star: ties within COMPUTE_EPS of a boundary are reported): rows whose
+ * fp32 score is within p->eps of the threshold or of the near-miss limit, compared in double like the single-query scan.
+ * tie_counts_out [Q] (exact); tie_rows_out / tie_scores_out [Q][tie_cap] in database order, -1 / -inf padded, may be
+ * NULL; at most 4096 entries per query are kept.  p->eps <= 0: counts are zero and the faster kernel runs.            */
+int vq_scan_batch_ties(vq_store *s, const float *targets, int32_t n_queries, const vq_scan_params *p,
+                       int64_t *counts_out, int64_t *topk_rows_out, float *topk_scores_out,
+                       int64_t *tie_counts_out, int32_t tie_cap, int64_t *tie_rows_out, float *tie_scores_out,
+                       float *kernel_ms_out);
 
 /* Test hook: the full [Q][n_rows] fp32 score matrix of the batched path (small shards only). */
 int vq_scan_batch_scores(vq_store *s, const float *targets, int32_t n_queries, const vq_scan_params *p,

@@ -487,6 +487,21 @@ def test_batched_tensor_core_scan_matches_oracle(vq, n, nq):
         assert np.array_equal(scores[q], got[q][rows[q]])
         for a, b in zip(rows[q], sc.topk_stable(s64, k)):
             assert a == b or abs(s64[a] - s64[b]) < EPS
+    # the tie band per query (rows within eps of the threshold or of the near-miss limit, compared in double like K2):
+    # a wide band so that it is populated; same counts / top-k as the run without it
+    wide = 2e-3
+    c2, r2, s2, _ = st.scan_batch(T.astype(np.float32), w, th, lo, topk=k, eps=wide)
+    assert np.array_equal(c2, counts) and np.array_equal(r2, rows) and np.array_equal(s2, scores)
+    t_counts, t_lists = st.batch_ties
+    n_band = 0
+    for q in range(nq):
+        g = got[q].astype(np.float64)
+        want = np.flatnonzero((np.abs(g - th) < wide) | (np.abs(g - lo) < wide))
+        assert t_counts[q] == len(want) and np.array_equal(t_lists[q][0], want) and np.array_equal(t_lists[q][1], got[q][want])
+        n_band += len(want)
+    assert n_band > nq
+    st.scan_batch(T.astype(np.float32), w, th, lo, topk=k)
+    assert st.batch_ties is None
     st.close()
 
 

@@ -541,7 +541,7 @@ class _SolveStore:
     def has_clip(self, clip):
         return clip is not None and int(clip) in self.scn.row_of
 
-    def bootstrap_target(self, valid_rows, invalid_rows, mu):
+    def bootstrap_target(self, valid_rows, invalid_rows, mu, slots=None):
         X = self.scn.X
         out = np.empty(X.shape[1:], np.float64)
         for s in range(X.shape[1]):

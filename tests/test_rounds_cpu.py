@@ -148,7 +148,7 @@ def make_oracle_store_class():
             present = np.ones((len(rows),) + self.row_shape[:2], bool) if self.present is None else self.present[rows]
             return sc.similarities(self.X[rows], T, present & have[None])[0]
 
-        def bootstrap_target(self, valid_rows, invalid_rows, mu):
+        def bootstrap_target(self, valid_rows, invalid_rows, mu, slots=None):
             X = self.X.astype(np.float64)
             v = np.asarray(valid_rows, np.int64) - self.first_global_row
             iv = np.asarray(invalid_rows if invalid_rows is not None else [], np.int64) - self.first_global_row

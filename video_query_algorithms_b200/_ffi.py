@@ -97,8 +97,9 @@ PROTOTYPES = {
     "vq_merge_topk_batch": (C.c_int, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "vq_labelled_sims": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "vq_loss_grid": (C.c_int, [C.c_int, _vp, _vp, _i64, _vp, _i32, _vp, _i32, C.c_double, _vp, _vp, _i32, _vp]),
-    "vq_bootstrap_target": (C.c_int, [_vp, _vp, _i32, _vp, _i32, C.c_double, _vp]),
+    "vq_bootstrap_target": (C.c_int, [_vp, _vp, _i32, _vp, _i32, C.c_double, _vp, _vp]),
     "vq_scan_batch": (C.c_int, [_vp, _vp, _i32, _P(ScanParams), _vp, _vp, _vp, _vp]),
+    "vq_scan_batch_ties": (C.c_int, [_vp, _vp, _i32, _P(ScanParams), _vp, _vp, _vp, _vp, _i32, _vp, _vp, _vp]),
     "vq_scan_batch_scores": (C.c_int, [_vp, _vp, _i32, _P(ScanParams), _vp]),
     "vq_csv_shape": (C.c_int, [C.c_char_p, _i64p, _P(_i32), C.c_char_p, _i32]),
     "vq_csv_read": (C.c_int, [C.c_char_p, _i32, _i64, _i32, _vp, _vp, _i64p]),

@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "vq_internal.cuh"
@@ -39,6 +40,9 @@ struct BatchArgs {
     int n_tiles;                   // tiles in this chunk
     int n_mma;                     // queries of this pass rounded up to 16 (the UMMA N)
     long long cand_cap;
+    // tie band: closed fp32 intervals holding exactly the floats s with |(double)s - th| < eps (0) and |(double)s - lo| < eps (1)
+    float tie_lo0, tie_hi0, tie_lo1, tie_hi1;
+    long long tie_cap;
 };
 
 #include "vq_batch_bf16.cuh"
@@ -118,6 +122,22 @@ float float_ceil_of(double x) {
     return f;
 }
 
+// [lo, hi] = the floats f with fabs((double)f - c) < eps (the test of vq_scan.cu classify()); empty (lo > hi) when eps <= 0
+void tie_interval(double c, double eps, float *lo, float *hi) {
+    *lo = INFINITY;
+    *hi = -INFINITY;
+    if (!(eps > 0.0) || !(c == c) || fabs(c) > 1e30) return;
+    float l = (float)(c - eps), h = (float)(c + eps);
+    for (int i = 0; i < 8 && !(fabs((double)l - c) < eps); ++i) l = nextafterf(l, INFINITY);
+    for (int i = 0; i < 8 && !(fabs((double)h - c) < eps); ++i) h = nextafterf(h, -INFINITY);
+    if (fabs((double)l - c) < eps && fabs((double)h - c) < eps && l <= h) {
+        *lo = l;
+        *hi = h;
+    }
+}
+
+constexpr long long kTieCap = 4096;      // tie-band entries kept per query (the band is 2 * COMPUTE_EPS wide: ~1e-5 of the rows)
+
 struct Dev {
     void *p = nullptr;
     ~Dev() { if (p) cudaFree(p); }
@@ -127,7 +147,7 @@ struct Dev {
 
 // Scratch of the batched path, owned by the store: allocated on the first batched scan, reused by every later one.
 struct BatchScratch {
-    Dev t, t1, t2, cut, counts, cnt, keys, rows, sc, park;
+    Dev t, t1, t2, cut, counts, cnt, keys, rows, sc, park, tie_cnt, tie_keys;
     void *pinned_t = nullptr;            // pinned staging for one pass of targets
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     ~BatchScratch() {
@@ -150,6 +170,8 @@ int alloc_batch_scratch(const vq_store *s, size_t K, long long cap, BatchScratch
     VQ_CUDA(b->rows.alloc((size_t)QN * VQ_MAX_TOPK * 8));
     VQ_CUDA(b->sc.alloc((size_t)QN * VQ_MAX_TOPK * 4));
     VQ_CUDA(b->park.alloc((size_t)s->sm_count * QN * bf::BM * 4));
+    VQ_CUDA(b->tie_cnt.alloc(QN * 4));
+    VQ_CUDA(b->tie_keys.alloc((size_t)QN * kTieCap * 8));
     VQ_CUDA(cudaMallocHost(&b->pinned_t, (size_t)QN * K * 4));
     VQ_CUDA(cudaEventCreate(&b->e0));
     VQ_CUDA(cudaEventCreate(&b->e1));
@@ -172,7 +194,9 @@ int get_batch_scratch(vq_store *s, size_t K, long long cap, BatchScratch **out) 
 
 // The batched path: bf16x2 kernel (vq_batch_bf16.cuh), 256 queries per pass over the shard.
 int run_batch_bf16(vq_store *s, const float *targets, int n_queries, const vq_scan_params *p, int64_t *counts_out,
-                   int64_t *topk_rows_out, float *topk_scores_out, float *kernel_ms_out, float *scores_dbg_host) {
+                   int64_t *topk_rows_out, float *topk_scores_out, float *kernel_ms_out, float *scores_dbg_host,
+                   int64_t *tie_counts_out = nullptr, int32_t tie_cap_out = 0, int64_t *tie_rows_out = nullptr,
+                   float *tie_scores_out = nullptr) {
     VQ_REQUIRE(s && targets && p, "vq_scan_batch: null argument");
     VQ_REQUIRE(n_queries >= 1, "vq_scan_batch: need at least one query");
     VQ_REQUIRE(s->stream_len % bf::BK == 0, "vq_scan_batch: stream length %d is not a multiple of %d", s->stream_len, bf::BK);
@@ -191,8 +215,12 @@ int run_batch_bf16(vq_store *s, const float *targets, int n_queries, const vq_sc
     const long long first_rows = (long long)s->sm_count * bf::BM;
     const long long chunk_rows = (long long)s->sm_count * bf::BM * 16;
     const long long cap = chunk_rows + VQ_MAX_TOPK;
-    VQ_CUDA(cudaFuncSetAttribute(bf::batch_scan_bf16<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf::Ring<256>::SMEM));
-    VQ_CUDA(cudaFuncSetAttribute(bf::batch_scan_bf16<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf::Ring<128>::SMEM));
+    VQ_CUDA(cudaFuncSetAttribute(bf::batch_scan_bf16<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf::Ring<256>::SMEM));
+    VQ_CUDA(cudaFuncSetAttribute(bf::batch_scan_bf16<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf::Ring<128>::SMEM));
+    VQ_CUDA(cudaFuncSetAttribute(bf::batch_scan_bf16<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf::Ring<256>::SMEM));
+    VQ_CUDA(cudaFuncSetAttribute(bf::batch_scan_bf16<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bf::Ring<128>::SMEM));
+    const bool want_ties = tie_counts_out != nullptr && p->eps > 0.0;
+    VQ_REQUIRE(!tie_rows_out || (tie_scores_out && tie_cap_out > 0), "vq_scan_batch_ties: tie lists need scores and a capacity");
     BatchScratch *bs = nullptr;
     if (int r = get_batch_scratch(s, K, cap, &bs)) return r;
     Dev &d_t = bs->t, &d_t1 = bs->t1, &d_t2 = bs->t2, &d_cut = bs->cut, &d_counts = bs->counts, &d_cnt = bs->cnt,
@@ -222,6 +250,7 @@ int run_batch_bf16(vq_store *s, const float *targets, int n_queries, const vq_sc
         fill_f32<<<1, QN, 0, st>>>(d_cut.as<float>(), topk > 0 ? -INFINITY : INFINITY, QN);   // no top-k: nothing is a candidate
         VQ_CUDA(cudaMemsetAsync(d_counts.p, 0, QN * 2 * 8, st));
         VQ_CUDA(cudaMemsetAsync(d_cnt.p, 0, QN * 4, st));
+        VQ_CUDA(cudaMemsetAsync(bs->tie_cnt.p, 0, QN * 4, st));
         CUtensorMap map_a, map_t1, map_t2;
         if (s->n_rows > 0) {
             if ((rc = encode_map(&map_a, s->rows, K, (uint64_t)s->n_rows, bf::BM))) break;
@@ -243,6 +272,9 @@ int run_batch_bf16(vq_store *s, const float *targets, int n_queries, const vq_sc
         a.n_streams = s->n_streams;
         a.n_rows_total = s->n_rows;
         a.cand_cap = cap;
+        tie_interval(p->threshold, want_ties ? p->eps : 0.0, &a.tie_lo0, &a.tie_hi0);
+        tie_interval(p->lower_limit, want_ties ? p->eps : 0.0, &a.tie_lo1, &a.tie_hi1);
+        a.tie_cap = kTieCap;
         VQ_CUDA(cudaEventRecord(e0, st));
         for (long long r0 = 0, step = first_rows; r0 < s->n_rows; r0 += step, step = chunk_rows) {
             const long long nr = (s->n_rows - r0 < step) ? (s->n_rows - r0) : step;
@@ -250,9 +282,12 @@ int run_batch_bf16(vq_store *s, const float *targets, int n_queries, const vq_sc
             a.n_tiles = (int)((nr + bf::BM - 1) / bf::BM);
             a.row_end = r0 + nr;
             const int units = a.n_tiles < s->sm_count ? a.n_tiles : s->sm_count;
-            (a.n_mma > 128 ? bf::batch_scan_bf16<256> : bf::batch_scan_bf16<128>)<<<units, bf::THREADS, a.n_mma > 128 ? bf::Ring<256>::SMEM : bf::Ring<128>::SMEM, st>>>(
+            auto kernel = a.n_mma > 128 ? (want_ties ? bf::batch_scan_bf16<256, true> : bf::batch_scan_bf16<256, false>)
+                                        : (want_ties ? bf::batch_scan_bf16<128, true> : bf::batch_scan_bf16<128, false>);
+            kernel<<<units, bf::THREADS, a.n_mma > 128 ? bf::Ring<256>::SMEM : bf::Ring<128>::SMEM, st>>>(
                 map_a, map_t1, map_t2, a, s->inv_counts, d_cut.as<float>(), d_counts.as<unsigned long long>(),
-                d_cnt.as<unsigned int>(), d_keys.as<unsigned long long>(), d_park.as<float>(),
+                d_cnt.as<unsigned int>(), d_keys.as<unsigned long long>(), bs->tie_cnt.as<unsigned int>(),
+                bs->tie_keys.as<unsigned long long>(), d_park.as<float>(),
                 scores_dbg_host ? d_dbg.as<float>() : nullptr, want_prof ? d_prof.as<long long>() : nullptr);
             if (topk > 0)
                 batch_compact<<<QN, 1024, 0, st>>>(d_cnt.as<unsigned int>(), d_keys.as<unsigned long long>(), cap, topk,
@@ -306,6 +341,37 @@ int run_batch_bf16(vq_store *s, const float *targets, int n_queries, const vq_sc
             VQ_CUDA(cudaMemcpyAsync(scores_dbg_host + (size_t)q0 * s->n_rows, d_dbg.p, (size_t)nq * s->n_rows * 4,
                                     cudaMemcpyDeviceToHost, st));
         VQ_CUDA(cudaStreamSynchronize(st));
+        if (tie_counts_out) {
+            // tie band: counts always; the lists (global rows ascending = database order) up to the caller's capacity
+            std::vector<unsigned int> hc(QN, 0u);
+            if (want_ties) VQ_CUDA(cudaMemcpy(hc.data(), bs->tie_cnt.p, QN * 4, cudaMemcpyDeviceToHost));
+            std::vector<unsigned long long> hk;
+            for (int q = 0; q < nq; ++q) {
+                tie_counts_out[q0 + q] = (int64_t)hc[(size_t)q];
+                if (!tie_rows_out) continue;
+                const long long have = hc[(size_t)q] < (unsigned long long)kTieCap ? (long long)hc[(size_t)q] : kTieCap;
+                hk.resize((size_t)have);
+                if (have)
+                    VQ_CUDA(cudaMemcpy(hk.data(), bs->tie_keys.as<unsigned long long>() + (size_t)q * kTieCap, (size_t)have * 8,
+                                       cudaMemcpyDeviceToHost));
+                std::sort(hk.begin(), hk.end(), [](unsigned long long x, unsigned long long y) { return (x & 0xFFFFFFFFull) > (y & 0xFFFFFFFFull); });
+                for (int i = 0; i < tie_cap_out; ++i) {
+                    const size_t at = (size_t)(q0 + q) * tie_cap_out + i;
+                    if (i < have) {
+                        const unsigned long long key = hk[(size_t)i];
+                        unsigned int u = (unsigned int)(key >> 32);
+                        u = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+                        float f;
+                        memcpy(&f, &u, 4);
+                        tie_rows_out[at] = s->first_global_row + (int64_t)(0xFFFFFFFFu - (unsigned int)(key & 0xFFFFFFFFull));
+                        tie_scores_out[at] = f;
+                    } else {
+                        tie_rows_out[at] = -1;
+                        tie_scores_out[at] = -INFINITY;
+                    }
+                }
+            }
+        }
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) total_ms += ms;
     }
@@ -319,6 +385,18 @@ extern "C" int vq_scan_batch(vq_store *s, const float *targets, int32_t n_querie
                              int64_t *counts_out, int64_t *topk_rows_out, float *topk_scores_out,
                              float *kernel_ms_out) {
     return run_batch_bf16(s, targets, n_queries, p, counts_out, topk_rows_out, topk_scores_out, kernel_ms_out, nullptr);
+}
+
+// The same with the tie band of every query (north_star: "ties within COMPUTE_EPS of the threshold ... are reported"):
+// rows whose fp32 score is within p->eps of the threshold or of the near-miss limit, compared in double like the
+// single-query scan.  tie_counts_out [Q]; tie_rows_out / tie_scores_out [Q][tie_cap] in database order, -1 / -inf padded
+// (may be NULL: counts only).  At most 4096 entries per query are kept on the device; the counts are exact.
+extern "C" int vq_scan_batch_ties(vq_store *s, const float *targets, int32_t n_queries, const vq_scan_params *p,
+                                  int64_t *counts_out, int64_t *topk_rows_out, float *topk_scores_out, int64_t *tie_counts_out,
+                                  int32_t tie_cap, int64_t *tie_rows_out, float *tie_scores_out, float *kernel_ms_out) {
+    VQ_REQUIRE(tie_counts_out, "vq_scan_batch_ties: null tie_counts_out");
+    return run_batch_bf16(s, targets, n_queries, p, counts_out, topk_rows_out, topk_scores_out, kernel_ms_out, nullptr,
+                          tie_counts_out, tie_cap, tie_rows_out, tie_scores_out);
 }
 
 extern "C" int vq_scan_batch_scores(vq_store *s, const float *targets, int32_t n_queries, const vq_scan_params *p,

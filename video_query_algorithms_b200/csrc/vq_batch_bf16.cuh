@@ -254,12 +254,16 @@ __device__ __forceinline__ void convert_blocks(const int t, const int lane, cons
     }
 }
 
-template <int QT>
+// kTies: also report, per query, the rows within COMPUTE_EPS of the threshold or of the near-miss limit (the tie band of
+// the single-query scan, vq_scan.cu classify()): four more compares per score in the scoring phase, so it is a separate
+// instantiation that only runs when the caller passes eps > 0.
+template <int QT, bool kTies>
 __global__ void __launch_bounds__(THREADS, 1)
 batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_t1,
                 const __grid_constant__ CUtensorMap map_t2, const BatchArgs a, const float *__restrict__ inv_counts,
                 const float *__restrict__ cut_g, unsigned long long *counts_g /*[QN][2]*/, unsigned int *cand_cnt /*[QN]*/,
-                unsigned long long *cand_keys /*[QN][cap]*/, float *park_g /*[grid][QN][BM], L2 park only*/, float *scores_dbg /*[Q][n_rows] or null*/, long long *prof /*[grid][8] or null*/) {
+                unsigned long long *cand_keys /*[QN][cap]*/, unsigned int *tie_cnt /*[QN]*/, unsigned long long *tie_keys /*[QN][tie_cap]*/,
+                float *park_g /*[grid][QN][BM], L2 park only*/, float *scores_dbg /*[Q][n_rows] or null*/, long long *prof /*[grid][8] or null*/) {
     using R = Ring<QT>;
     constexpr int NA = R::NA, NXR = R::NXR, NT = R::NT, N_BARS = R::N_BARS;
     constexpr uint32_t T_BYTES = R::T_BYTES, RING_X = R::RING_X, RING_T = R::RING_T, RING_END = R::RING_END;
@@ -499,13 +503,13 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 // the warp (lane j ends up with the 32 rows' bits of query j).  Phase 3: candidate appends, only for
                 // the (rare, after the first chunk) queries some row of this warp beats the cut of.
                 const long long t1 = VQ_CLOCK();
-                unsigned int m_th[4], m_nm[4], m_cd[4];
+                unsigned int m_th[4], m_nm[4], m_cd[4], m_tz[4];
                 const unsigned int rowmask = row_ok ? 0xffffffffu : 0u;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
-                    m_th[c] = m_nm[c] = m_cd[c] = 0u;
+                    m_th[c] = m_nm[c] = m_cd[c] = m_tz[c] = 0u;
                     if (c < nch) {
-                        unsigned int bt = 0, bl = 0, bc = 0;
+                        unsigned int bt = 0, bl = 0, bc = 0, bz = 0;
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const int ql = 32 * c + j;
@@ -514,12 +518,15 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                             bt |= (sc >= a.th_f ? 1u : 0u) << j;
                             bl |= (sc >= a.lo_f ? 1u : 0u) << j;
                             bc |= (sc > cut_s[half * 128 + ql] ? 1u : 0u) << j;
+                            if constexpr (kTies)
+                                bz |= (((sc >= a.tie_lo0) & (sc <= a.tie_hi0)) | ((sc >= a.tie_lo1) & (sc <= a.tie_hi1)) ? 1u : 0u) << j;
                         }
                         const int nlive = a.n_queries - (half * 128 + 32 * c);          // live queries of this chunk
                         const unsigned int lm = rowmask & (nlive >= 32 ? 0xffffffffu : (nlive <= 0 ? 0u : ((1u << nlive) - 1u)));
                         m_th[c] = bt & lm;
                         m_nm[c] = bl & ~bt & lm;
                         m_cd[c] = bc & lm;
+                        m_tz[c] = bz & lm;
                     }
                 }
                 if (scores_dbg && row_ok) {
@@ -540,28 +547,32 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                         my_cnt[(c * 32 + lane) * 2 + 1] += __popc(transpose32(m_nm[c], lane));
                     }
                 }
+                // rare after the seeding chunk: a real loop over the hot queries (compact code, the score comes out
+                // of the register file through a select tree on the warp-uniform index); the tie band uses the same loop
+                auto append_hot = [&](const unsigned int (&mask)[4], unsigned int *cnt, unsigned long long *keys, const long long cap) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    unsigned int h = __reduce_or_sync(0xffffffffu, m_cd[c]);
-                    // rare after the seeding chunk: a real loop over the hot queries (compact code, the score comes out
-                    // of the register file through a select tree on the warp-uniform index)
-                    while (h) {
-                        const int j = __ffs(h) - 1;
-                        h &= h - 1;
-                        const float sc = select32(run, 32 * c, j);
-                        const int q = half * 128 + c * 32 + j;
-                        const bool cand = (m_cd[c] >> j) & 1u;
-                        const unsigned int bc = __ballot_sync(0xffffffffu, cand);
-                        const int leader_lane = __ffs(bc) - 1;
-                        unsigned int base = 0;
-                        if (lane == leader_lane) base = atomicAdd(&cand_cnt[q], (unsigned int)__popc(bc));
-                        base = __shfl_sync(0xffffffffu, base, leader_lane);
-                        if (cand) {
-                            const long long slot = (long long)base + __popc(bc & ((1u << lane) - 1u));
-                            if (slot < a.cand_cap) cand_keys[(size_t)q * a.cand_cap + slot] = vq::make_key(sc, (unsigned int)row);
+                    for (int c = 0; c < 4; ++c) {
+                        unsigned int h = __reduce_or_sync(0xffffffffu, mask[c]);
+                        while (h) {
+                            const int j = __ffs(h) - 1;
+                            h &= h - 1;
+                            const float sc = select32(run, 32 * c, j);
+                            const int q = half * 128 + c * 32 + j;
+                            const bool cand = (mask[c] >> j) & 1u;
+                            const unsigned int bc = __ballot_sync(0xffffffffu, cand);
+                            const int leader_lane = __ffs(bc) - 1;
+                            unsigned int base = 0;
+                            if (lane == leader_lane) base = atomicAdd(&cnt[q], (unsigned int)__popc(bc));
+                            base = __shfl_sync(0xffffffffu, base, leader_lane);
+                            if (cand) {
+                                const long long slot = (long long)base + __popc(bc & ((1u << lane) - 1u));
+                                if (slot < cap) keys[(size_t)q * cap + slot] = vq::make_key(sc, (unsigned int)row);
+                            }
                         }
                     }
-                }
+                };
+                append_hot(m_cd, cand_cnt, cand_keys, a.cand_cap);
+                if constexpr (kTies) append_hot(m_tz, tie_cnt, tie_keys, a.tie_cap);
                 e_score += VQ_CLOCK() - t1;
             }
         }

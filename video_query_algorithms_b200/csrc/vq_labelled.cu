@@ -200,11 +200,15 @@ __device__ void lu_solve(double *A, double *B, int n, int nrhs, int *piv_s, int 
 // Scratch per slot (doubles): Bm[n*n] | R[n*2] | Ky[m*m] | Z[m*(n+1)] | tmp[n+m]
 __global__ void __launch_bounds__(256)
 bootstrap_solve_kernel(const double *__restrict__ G, int n, int m, double mu, double *scratch,
-                       size_t scratch_per_slot, double *coef, int *singular) {
+                       size_t scratch_per_slot, double *coef, int *singular, const unsigned char *__restrict__ slot_mask) {
     __shared__ int piv_s;
     __shared__ double c_s;
     const int slot = blockIdx.x;
     const int nz = n + m;
+    if (slot_mask && !slot_mask[slot]) {                 // a slot the caller does not want: zero coefficients, no solve
+        for (int i = threadIdx.x; i < nz; i += blockDim.x) coef[(size_t)slot * nz + i] = 0.0;
+        return;
+    }
     const double *Gs = G + (size_t)slot * nz * nz;
     double *Bm = scratch + (size_t)slot * scratch_per_slot;
     double *R = Bm + (size_t)n * n;
@@ -433,7 +437,8 @@ extern "C" int vq_loss_grid(int device, const double *sims, const uint8_t *label
 }
 
 extern "C" int vq_bootstrap_target(vq_store *s, const int64_t *valid_rows, int32_t n_valid,
-                                   const int64_t *invalid_rows, int32_t n_invalid, double mu, double *target_out) {
+                                   const int64_t *invalid_rows, int32_t n_invalid, double mu, const uint8_t *slot_mask,
+                                   double *target_out) {
     VQ_REQUIRE(s && valid_rows && target_out, "vq_bootstrap_target: null argument");
     VQ_REQUIRE(n_valid >= 1 && n_invalid >= 0 && (n_invalid == 0 || invalid_rows),
                "vq_bootstrap_target: need at least one valid row");
@@ -450,24 +455,27 @@ extern "C" int vq_bootstrap_target(vq_store *s, const int64_t *valid_rows, int32
     VQ_CUDA(cudaSetDevice(s->device));
     const size_t per_slot = (size_t)n * n + (size_t)n * 2 + (size_t)m * m + (size_t)m * (n + 1) + (size_t)nz + 8;
     const size_t out_doubles = (size_t)n_slots * s->dim;
-    const size_t dev_total = padded((size_t)nz * 8) + padded(16) + padded((size_t)n_slots * nz * nz * 8) +
+    const size_t dev_total = padded((size_t)nz * 8) + padded(16) + padded((size_t)n_slots) + padded((size_t)n_slots * nz * nz * 8) +
                              padded((size_t)n_slots * per_slot * 8) + padded((size_t)n_slots * nz * 8) + padded(out_doubles * 8);
-    const size_t host_total = padded((size_t)nz * 8) + padded(16) + padded(out_doubles * 8);
+    const size_t host_total = padded((size_t)nz * 8) + padded(16) + padded((size_t)n_slots) + padded(out_doubles * 8);
     if (int r = lab_reserve(s, dev_total, host_total)) return r;
     Carver d(s->lab_dev), h(s->lab_host);
     long long *d_ids = d.take<long long>((size_t)nz), *h_ids = h.take<long long>((size_t)nz);
     int *d_flag = d.take<int>(4), *h_flag = h.take<int>(4);
+    unsigned char *d_mask = d.take<unsigned char>((size_t)n_slots), *h_mask = h.take<unsigned char>((size_t)n_slots);
+    for (int i = 0; i < n_slots; ++i) h_mask[i] = slot_mask ? (slot_mask[i] ? 1 : 0) : 1;
     double *d_G = d.take<double>((size_t)n_slots * nz * nz);
     double *d_scr = d.take<double>((size_t)n_slots * per_slot);
     double *d_coef = d.take<double>((size_t)n_slots * nz);
     double *d_out = d.take<double>(out_doubles), *h_out = h.take<double>(out_doubles);
     memcpy(h_ids, loc.data(), (size_t)nz * sizeof(long long));
     h_flag[0] = 0;
-    VQ_CUDA(cudaMemcpyAsync(d_ids, h_ids, padded((size_t)nz * 8) + sizeof(int), cudaMemcpyHostToDevice, s->stream));   // ids + cleared flag
+    VQ_CUDA(cudaMemcpyAsync(d_ids, h_ids, padded((size_t)nz * 8) + padded(16) + (size_t)n_slots, cudaMemcpyHostToDevice,
+                            s->stream));                                                          // ids + cleared flag + mask
     const long long warps = (long long)nz * nz * n_slots;
     gram_kernel<<<(unsigned int)((warps * 32 + 255) / 256), 256, 0, s->stream>>>(s->rows, d_ids, nz, n_slots, s->dim,
                                                                                s->row_floats, d_G);
-    bootstrap_solve_kernel<<<n_slots, 256, 0, s->stream>>>(d_G, n, m, mu, d_scr, per_slot, d_coef, d_flag);
+    bootstrap_solve_kernel<<<n_slots, 256, 0, s->stream>>>(d_G, n, m, mu, d_scr, per_slot, d_coef, d_flag, d_mask);
     combine_kernel<<<(n_slots * s->dim + 255) / 256, 256, 0, s->stream>>>(s->rows, d_ids, nz, n_slots, s->dim, s->row_floats,
                                                                          d_coef, d_out);
     VQ_CUDA(cudaGetLastError());

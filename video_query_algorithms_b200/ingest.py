@@ -106,6 +106,6 @@ def store_from_feature_tree(src_dir, streams=("rgb", "warped_optical_flow"), fea
     X = np.concatenate(blocks)
     st = FeatureStore(X.shape[0], streams, splits, dim, devices=devices,
                       clip_ids=np.arange(first_clip_id, first_clip_id + X.shape[0]))
-    st.upload(0, X)
+    st.upload_pipelined(0, X)
     st.set_present(np.concatenate(present))
     return st, ids

@@ -440,6 +440,30 @@ class FeatureStore:
             for b in bufs:
                 self._free_staging(b)
 
+    def upload_pipelined(self, first_row, rows):
+        """upload() for large host arrays: the rows go through two pinned staging buffers, the copy into one overlapping
+        the transfer out of the other (a pageable source is otherwise staged by the driver in small synchronous pieces)."""
+        rf = int(np.prod(self.row_shape))
+        rows = np.ascontiguousarray(rows, dtype=np.float32).reshape(-1, rf)
+        n = rows.shape[0]
+        self._check_range(first_row, n, "upload_pipelined")
+        rows_per = max(1, self.CHUNK_BYTES // (rf * 4))
+        if n <= rows_per:
+            return self.upload(first_row, rows)
+        bufs = [self._alloc_staging(rows_per * rf) for _ in range(2)]
+        try:
+            for i, r0 in enumerate(range(0, n, rows_per)):
+                r1 = min(r0 + rows_per, n)
+                buf = bufs[i % 2]
+                if i >= 2:
+                    self._sync_uploads()
+                buf[:(r1 - r0) * rf] = rows[r0:r1].reshape(-1)
+                self._upload_async(first_row + r0, buf[:(r1 - r0) * rf])
+            self._sync_uploads()
+        finally:
+            for b in bufs:
+                self._free_staging(b)
+
     # staging / asynchronous upload primitives (test doubles replace these four)
     def _alloc_staging(self, n_floats):
         p = C.c_void_p()
@@ -738,11 +762,15 @@ class FeatureStore:
         return out
 
     # ------------------------------------------------------------------ batched queries (tcgen05)
-    def scan_batch(self, targets, weights, threshold, lower_limit, topk=0, debug_scores=False):
+    TIE_CAP = 4096               # tie-band entries kept per query and shard by the batched kernel
+
+    def scan_batch(self, targets, weights, threshold, lower_limit, topk=0, debug_scores=False, eps=0.0):
         """Score Q targets against the whole store in one pass per shard on the tensor cores.
         targets: list of {stream: {split: vector}} or array [Q, S, P, dim].
         Returns (counts [Q, 2] = matches, near misses; topk_rows [Q, k]; topk_scores [Q, k]; kernel ms)
-        or, with debug_scores, the fp32 score matrix [Q, n_rows] (single-shard stores only)."""
+        or, with debug_scores, the fp32 score matrix [Q, n_rows] (single-shard stores only).
+        eps > 0 also reports every query's tie band — rows within eps of the threshold or of the near-miss limit —
+        in self.batch_ties = (counts [Q], [(global rows ascending, fp32 scores) per query])."""
         if isinstance(targets, np.ndarray):
             T = np.ascontiguousarray(targets, dtype=np.float32).reshape((-1,) + self.row_shape)
             have = np.ones(self.row_shape[:2], bool)
@@ -756,7 +784,8 @@ class FeatureStore:
         self._sync_split_weights_for_target(have)              # never inherit what an earlier single-query job left
         Q = T.shape[0]
         w = [weights[s] for s in self.streams] if isinstance(weights, dict) else list(weights)
-        p = make_params(w, threshold, lower_limit, 0.0, topk)
+        p = make_params(w, threshold, lower_limit, float(eps), topk)
+        self.batch_ties = None
         if debug_scores:
             if len(self.shards) != 1:
                 raise VQError("scan_batch(debug_scores=True) needs a single-shard store")
@@ -771,12 +800,21 @@ class FeatureStore:
         rows_l = [np.full((Q, k), -1, np.int64) for _ in range(n_sh)]
         sc_l = [np.full((Q, k), -np.inf, np.float32) for _ in range(n_sh)]
         ms_l = [C.c_float() for _ in range(n_sh)]
+        want_ties = eps > 0
+        tc_l = [np.zeros(Q, np.int64) for _ in range(n_sh)] if want_ties else None
+        tr_l = [np.empty((Q, self.TIE_CAP), np.int64) for _ in range(n_sh)] if want_ties else None
+        ts_l = [np.empty((Q, self.TIE_CAP), np.float32) for _ in range(n_sh)] if want_ties else None
         errs = []
 
         def run(i):                                   # one call per shard; ctypes releases the GIL, devices run concurrently
             try:
-                check(lib().vq_scan_batch(self.shards[i].handle, ptr(T), Q, C.byref(p), ptr(c_l[i]), ptr(rows_l[i]),
-                                          ptr(sc_l[i]), C.byref(ms_l[i])), "vq_scan_batch")
+                if want_ties:
+                    check(lib().vq_scan_batch_ties(self.shards[i].handle, ptr(T), Q, C.byref(p), ptr(c_l[i]), ptr(rows_l[i]),
+                                                   ptr(sc_l[i]), ptr(tc_l[i]), self.TIE_CAP, ptr(tr_l[i]), ptr(ts_l[i]),
+                                                   C.byref(ms_l[i])), "vq_scan_batch_ties")
+                else:
+                    check(lib().vq_scan_batch(self.shards[i].handle, ptr(T), Q, C.byref(p), ptr(c_l[i]), ptr(rows_l[i]),
+                                              ptr(sc_l[i]), C.byref(ms_l[i])), "vq_scan_batch")
             except Exception as e:                    # surfaced below
                 errs.append(e)
 
@@ -793,6 +831,13 @@ class FeatureStore:
             raise errs[0]
         for c in c_l:
             counts += c
+        if want_ties:
+            lists = []
+            for q in range(Q):
+                parts = [(tr_l[i][q, :min(int(tc_l[i][q]), self.TIE_CAP)], ts_l[i][q, :min(int(tc_l[i][q]), self.TIE_CAP)])
+                         for i in range(n_sh)]
+                lists.append((np.concatenate([a for a, _ in parts]), np.concatenate([b for _, b in parts])))
+            self.batch_ties = (sum(tc_l), lists)
         ms = max(m.value for m in ms_l)
         if topk == 0:
             return counts, np.empty((Q, 0), np.int64), np.empty((Q, 0), np.float32), ms
@@ -821,10 +866,11 @@ class FeatureStore:
                 out[sel] = o
         return out
 
-    def bootstrap_target(self, valid_rows, invalid_rows, mu):
+    def bootstrap_target(self, valid_rows, invalid_rows, mu, slots=None):
         """float64 [S, P, dim]: new target from labelled rows (target_clip.py:161-261), solved on
         the GPU that holds the rows.  Labelled rows spread over several shards are first gathered
-        onto the first shard's device through a scratch store."""
+        onto the first shard's device through a scratch store.  slots: bool [S, P], the (stream, split) problems to
+        solve (default all); the others come back zero.  A singular system raises VQError."""
         valid = np.ascontiguousarray(valid_rows, dtype=np.int64)
         invalid = np.ascontiguousarray(invalid_rows if invalid_rows is not None else [], dtype=np.int64)
         allr = np.concatenate([valid, invalid])
@@ -833,13 +879,14 @@ class FeatureStore:
             raise VQError("bootstrap_target: need >= 1 valid row and all rows inside the store [%d, %d)" % (lo_g, hi_g))
         sh = self._shard_of(int(allr[0]))
         if not all(sh.first <= r < sh.first + sh.n_rows for r in allr):
-            return self._bootstrap_gathered(valid, invalid, mu)
+            return self._bootstrap_gathered(valid, invalid, mu, slots)
         out = np.empty(self.row_shape, np.float64)
+        mask = None if slots is None else np.ascontiguousarray(np.asarray(slots, bool).reshape(self.row_shape[:2]), dtype=np.uint8)
         check(lib().vq_bootstrap_target(sh.handle, ptr(valid), len(valid), ptr(invalid) if len(invalid) else None,
-                                        len(invalid), float(mu), ptr(out)), "vq_bootstrap_target")
+                                        len(invalid), float(mu), ptr(mask), ptr(out)), "vq_bootstrap_target")
         return out
 
-    def _bootstrap_gathered(self, valid, invalid, mu):
+    def _bootstrap_gathered(self, valid, invalid, mu, slots=None):
         allr = np.concatenate([valid, invalid])
         uniq = np.unique(allr)
         feats = np.concatenate([self.download(int(r) - self.first_global_row, 1) for r in uniq])
@@ -849,7 +896,7 @@ class FeatureStore:
             pos = {int(r): i for i, r in enumerate(uniq)}
             v = np.array([pos[int(r)] for r in valid], np.int64)
             iv = np.array([pos[int(r)] for r in invalid], np.int64)
-            return tmp.bootstrap_target(v, iv, mu)
+            return tmp.bootstrap_target(v, iv, mu, slots)
         finally:
             tmp.close()
 

@@ -100,8 +100,8 @@ class TargetClip:
         """One `vq_bootstrap_target` call solves every (stream, split) slot from the same labelled rows.  On a ragged
         search set a labelled clip may lack a slot (a zero row in the store); the reference then solves that slot with
         the clips that do have it — its per-slot feature lists only receive the rows a clip has
-        (target_clip.py:184-187, 232-240) — so the slot's rows are filtered the same way, one call per slot (the slots
-        of a call are independent problems; only the filtered slot's answer is kept, the others may be singular)."""
+        (target_clip.py:184-187, 232-240) — so the slot's rows are filtered the same way, one call per slot with only
+        that slot solved (the other slots of such a call would see zero rows: singular systems)."""
         valid_rows, invalid_rows = np.asarray(valid_rows, np.int64), np.asarray(invalid_rows, np.int64)
         if store.present is None:
             return store.bootstrap_target(valid_rows, invalid_rows, mu)
@@ -114,7 +114,9 @@ class TargetClip:
             for pi in range(has_v.shape[2]):
                 v, iv = valid_rows[has_v[:, si, pi]], invalid_rows[has_i[:, si, pi]]
                 if len(v):                                                 # no labelled clip has the slot: it stays zero
-                    w[si, pi] = store.bootstrap_target(v, iv, mu)[si, pi]
+                    only = np.zeros(has_v.shape[1:], bool)
+                    only[si, pi] = True
+                    w[si, pi] = store.bootstrap_target(v, iv, mu, slots=only)[si, pi]
         return w
 
     def target_by_bagging(self, valid_rows, invalid_rows, splits):
