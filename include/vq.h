@@ -109,10 +109,14 @@ int vq_gather_list(vq_store *s, int32_t which, int64_t n_idx, const int64_t *pos
  * ranked top-k lists are merged into the search set's (score descending, global row ascending).  lists = 1 behaves like
  * vq_scan on every shard (whole lists in the host mirrors), lists = 0 like vq_scan_select.  counts_out [n_shards];
  * near_best_out [n_shards][3] = position in the shard's near-miss list, global row (-1: none), fp32 score bits;
- * list positions are per shard: the shards' lists in shard order are the search set's lists in database order.      */
+ * list positions are per shard: the shards' lists in shard order are the search set's lists in database order.
+ * With lists = 1 the match and near-miss lists of ALL shards land back to back in one host mirror (every device writes its
+ * segment at the offset the counts give): vq_scan_multi_host_list hands out views of the search set's lists, no host copy;
+ * the tie band, the top-k and the counts stay per shard (vq_scan_host_list which = 2, 3).                             */
 int vq_scan_multi(vq_store *const *shards, int32_t n_shards, const float *target, const vq_scan_params *p,
                   int32_t lists, vq_scan_counts *counts_out, int64_t *near_best_out, int32_t topk_cap,
                   int64_t *topk_rows_out, float *topk_scores_out, int32_t *n_topk_out);
+int vq_scan_multi_host_list(vq_store *first_shard, int32_t which, const int64_t **rows, const float **scores, int64_t *n);
 /* Same work, enqueued only: target already on the device, nothing copied back, no sync.
  * Used for device-side timing and for multi-GPU merges that read the results in place.      */
 int vq_scan_enqueue(vq_store *s, const float *target_dev, const vq_scan_params *p, void *stream);
@@ -200,6 +204,16 @@ int vq_hostx_create(vq_hostx **out, const char *name, int world, int rank, int64
 int vq_hostx_unlink(vq_hostx *x);
 int vq_hostx_allgather(vq_hostx *x, const void *mine, int64_t nbytes, void *all_out, double timeout_s);
 int vq_hostx_destroy(vq_hostx *x);
+
+/* Per-query summary record of the rank-level path (one process per GPU): what a rank tells its peers after its local
+ * scan — first global row, counts, ranked top-k, best near miss, tie band (up to tie_cap entries) — as
+ * int64 [5 + 2k + 3 + 2 tie_cap], and the merge of the gathered records of all ranks (host code; on the per-query path). */
+int vq_summary_pack(int64_t first_row, const int64_t *counts3, int32_t k, int32_t n_topk, const int64_t *topk_rows,
+                    const float *topk_scores, const int64_t *near_best, int32_t tie_cap, int32_t n_ties,
+                    const int64_t *tie_rows, const float *tie_scores, int64_t *rec_out);
+int vq_summary_merge(const int64_t *gathered, int32_t world, int32_t k, int32_t tie_cap, int64_t *first_rows_out,
+                     int64_t *counts_out, int64_t *topk_rows_out, float *topk_scores_out, int32_t *n_topk_out,
+                     int64_t *best_out, int64_t *tie_rows_out, float *tie_scores_out, int64_t *n_ties_out);
 
 /* per-launch device times of K1 recorded since the last call (ring of 1024), in ms           */
 int vq_scan_kernel_times(vq_store *s, int32_t cap, float *ms_out, int32_t *n_out);

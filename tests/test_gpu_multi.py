@@ -51,7 +51,8 @@ def test_single_process_store_over_real_devices_equals_one_device():
     assert len(many.shards) == len(devs) and {sh.device for sh in many.shards} == set(devs)
     one.fill_synthetic(seed)
     many.fill_synthetic(seed)
-    T = sc.scale_target(synth.rows(seed, [4242]).astype(np.float64)[0][:, None, :])
+    ref = synth.pick_reference_row(seed, n)
+    T = sc.scale_target(synth.rows(seed, [ref]).astype(np.float64)[0][:, None, :])
     tf = {s: {1: T[i, 0]} for i, s in enumerate(S)}
     lo = sc.lower_limit(0.8, 0.35)
     for lists in (True, False):

@@ -61,6 +61,7 @@ PROTOTYPES = {
     "vq_scan_select": (C.c_int, [_vp, _vp, _P(ScanParams), _P(ScanCounts), _i64p, _i64p, _f32p]),
     "vq_gather_list": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _vp]),
     "vq_scan_multi": (C.c_int, [_vp, _i32, _vp, _P(ScanParams), _i32, _vp, _vp, _i32, _vp, _vp, _P(_i32)]),
+    "vq_scan_multi_host_list": (C.c_int, [_vp, _i32, _P(_vp), _P(_vp), _i64p]),
     "vq_fetch_scores_at": (C.c_int, [_vp, _i64, _vp, _vp]),
     "vq_scan_phase_times": (C.c_int, [_vp, _i32, _vp, _vp, _P(_i32)]),
     "vq_exchange_check": (C.c_int, [_vp]),
@@ -92,6 +93,8 @@ PROTOTYPES = {
     "vq_hostx_unlink": (C.c_int, [_vp]),
     "vq_hostx_allgather": (C.c_int, [_vp, _vp, _i64, _vp, C.c_double]),
     "vq_hostx_destroy": (C.c_int, [_vp]),
+    "vq_summary_pack": (C.c_int, [_i64, _vp, _i32, _i32, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _vp]),
+    "vq_summary_merge": (C.c_int, [_vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _P(_i32), _vp, _vp, _vp, _i64p]),
     "vq_scan_kernel_times": (C.c_int, [_vp, _i32, _vp, _P(_i32)]),
     "vq_merge_topk": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _P(_i32)]),
     "vq_merge_topk_batch": (C.c_int, [_i32, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
@@ -162,5 +165,5 @@ def ptr(a):
     """void* of a C-contiguous numpy array (or None)."""
     if a is None:
         return None
-    assert a.flags["C_CONTIGUOUS"]
-    return a.ctypes.data_as(C.c_void_p)
+    assert a.flags.c_contiguous
+    return C.c_void_p(a.ctypes.data)          # (`data_as` costs twice as much, and this sits on the per-query path)

@@ -34,7 +34,7 @@ struct vq_exchange {
     // before the next select_compact overwrites the payload (vq_store::pack_reader_done).
     cudaStream_t side = nullptr;
     cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
-    cudaEvent_t ev_t0[256], ev_t1[256];         // ring: device time of the exchange kernel per step
+    unsigned long long *t_ring = nullptr;       // pinned, device-mapped [256][2]: start / end of each exchange kernel (global timer, ns)
     int ev_head = 0, ev_count = 0;
     double timeout_s = 10.0;                    // a peer that never arrives ends the kernel with an error marker instead of a hang
 };
@@ -43,6 +43,7 @@ namespace {
 constexpr int kSlot = 4 + 2 * VQ_MAX_TOPK;      // int64 per payload slot
 constexpr int kSlots = 4;                       // inbox slots (sequence number mod 4)
 constexpr int kRing = 256;
+constexpr int kXThreads = 128;                   // see exchange_push_merge
 constexpr int kMergeShared = 4096;              // candidates (world * k) merged out of shared memory
 __host__ __device__ inline size_t flags_offset(int world) { return (size_t)kSlots * world * kSlot; }
 
@@ -100,11 +101,17 @@ __device__ __forceinline__ void merge_ranked(RowPtr rows, ScorePtr scs, const in
     }
 }
 
-__global__ void __launch_bounds__(1024)
+// One block of kXThreads = 128 threads at <= 48 registers: small enough to be co-resident with the scan kernel of the NEXT
+// step (K1 keeps 3 blocks of 128 threads x 150 registers on every SM, which leaves 7168 registers per SM), so that it runs
+// as soon as its inputs are ready instead of queueing behind a 1.1 ms scan.  t_ns (when not null) receives the kernel's
+// own start and end on the global timer: CUDA events around a kernel on a side stream would also count the time it
+// waits for an SM.
+__global__ void __launch_bounds__(kXThreads, 10)
 exchange_push_merge(const long long *__restrict__ payload, long long *const *__restrict__ peers, const int world,
                     const int rank, const int k, const unsigned long long push_seq /* 0: nothing to push */,
                     const unsigned long long merge_seq /* 0: nothing to merge */, long long *merged, long long *scratch,
-                    const unsigned long long timeout_ns) {
+                    const unsigned long long timeout_ns, unsigned long long *t_ns) {
+    const unsigned long long t_begin = global_ns();
     extern __shared__ long long sm_rows[];          // [world * k] rows, then [world * k] fp32 scores (when they fit)
     __shared__ int len_s[64];
     __shared__ int timed_out;
@@ -124,7 +131,10 @@ exchange_push_merge(const long long *__restrict__ payload, long long *const *__r
             st_release_sys(flag, push_seq);
         }
     }
-    if (!merge_seq) return;
+    if (!merge_seq) {
+        if (t_ns && threadIdx.x == 0) { t_ns[0] = t_begin; t_ns[1] = global_ns(); }
+        return;
+    }
     // 2. wait until every rank's payload for the sequence number to merge has landed in my inbox; a peer that has died
     //    or fallen out of step must not wedge the GPU: past the deadline the kernel leaves an error marker and ends
     const int slot = (int)(merge_seq % kSlots);
@@ -182,6 +192,7 @@ exchange_push_merge(const long long *__restrict__ payload, long long *const *__r
         long long tot = 0;
         for (int l = 0; l < world; ++l) tot += len_s[l];
         merged[3] = tot < k ? tot : k;
+        if (t_ns) { t_ns[0] = t_begin; t_ns[1] = global_ns(); }
     }
 }
 }  // namespace
@@ -212,10 +223,8 @@ extern "C" int vq_exchange_create(vq_exchange **out, int device, int world, int 
         VQ_CUDA(cudaEventCreateWithFlags(&x->ev_ready, cudaEventDisableTiming));
         VQ_CUDA(cudaEventCreateWithFlags(&x->ev_done, cudaEventDisableTiming));
     }
-    for (int i = 0; i < kRing; ++i) {
-        VQ_CUDA(cudaEventCreate(&x->ev_t0[i]));
-        VQ_CUDA(cudaEventCreate(&x->ev_t1[i]));
-    }
+    VQ_CUDA(cudaMallocHost((void **)&x->t_ring, kRing * 2 * sizeof(unsigned long long)));
+    memset(x->t_ring, 0, kRing * 2 * sizeof(unsigned long long));
     if (const char *t = getenv("VQ_EXCHANGE_TIMEOUT_S")) x->timeout_s = atof(t) > 0 ? atof(t) : x->timeout_s;
     cudaFuncSetAttribute(exchange_push_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, kMergeShared * 12);
     *out = x;
@@ -254,10 +263,7 @@ extern "C" int vq_exchange_destroy(vq_exchange *x) {
     cudaDeviceSynchronize();
     for (int r = 0; r < x->world; ++r)
         if (r != x->rank && x->peer_inbox[r]) cudaIpcCloseMemHandle(x->peer_inbox[r]);
-    for (int i = 0; i < kRing; ++i) {
-        if (x->ev_t0[i]) cudaEventDestroy(x->ev_t0[i]);
-        if (x->ev_t1[i]) cudaEventDestroy(x->ev_t1[i]);
-    }
+    if (x->t_ring) cudaFreeHost(x->t_ring);
     if (x->ev_ready) cudaEventDestroy(x->ev_ready);
     if (x->ev_done) cudaEventDestroy(x->ev_done);
     if (x->side) cudaStreamDestroy(x->side);
@@ -286,12 +292,10 @@ static int launch_exchange(vq_exchange *x, vq_store *s, cudaStream_t scan_st, co
     const int slot = x->ev_head;
     x->ev_head = (x->ev_head + 1) % kRing;
     if (x->ev_count < kRing) x->ev_count++;
-    VQ_CUDA(cudaEventRecord(x->ev_t0[slot], run));
-    exchange_push_merge<<<1, 1024, merge_smem(x->world, x->topk), run>>>(
+    exchange_push_merge<<<1, kXThreads, merge_smem(x->world, x->topk), run>>>(
         payload, x->peer_table_dev, x->world, x->rank, x->topk, push_seq, merge_seq, x->merged, x->scratch,
-        (unsigned long long)(x->timeout_s * 1e9));
+        (unsigned long long)(x->timeout_s * 1e9), x->t_ring + 2 * slot);
     VQ_CUDA(cudaGetLastError());
-    VQ_CUDA(cudaEventRecord(x->ev_t1[slot], run));
     if (x->side && s) {                              // the next select_compact on this store waits for this kernel before it rewrites the payload
         if (!s->pack_reader_done) VQ_CUDA(cudaEventCreateWithFlags(&s->pack_reader_done, cudaEventDisableTiming));
         VQ_CUDA(cudaEventRecord(s->pack_reader_done, x->side));
@@ -348,7 +352,9 @@ extern "C" int vq_exchange_merged(vq_exchange *x, const int64_t **merged_dev) {
     return 0;
 }
 
-// Device times (ms) of the exchange kernels launched since the last call (ring of 256); call after a synchronisation.
+// Device times (ms) of the exchange kernels launched since the last call (ring of 256), taken by the kernels themselves on
+// the global timer (start of the block to its last store: pushes, the wait for the peers' flags and the merge); call after a
+// synchronisation.
 extern "C" int vq_exchange_kernel_times(vq_exchange *x, int32_t cap, float *ms_out, int32_t *n_out) {
     VQ_REQUIRE(x && n_out, "vq_exchange_kernel_times: null argument");
     VQ_CUDA(cudaSetDevice(x->device));
@@ -356,10 +362,9 @@ extern "C" int vq_exchange_kernel_times(vq_exchange *x, int32_t cap, float *ms_o
     int got = 0;
     for (int i = 0; i < n; ++i) {
         const int slot = (x->ev_head + kRing - n + i) % kRing;
-        float ms = 0.f;
-        if (cudaEventElapsedTime(&ms, x->ev_t0[slot], x->ev_t1[slot]) == cudaSuccess && ms_out) ms_out[got++] = ms;
+        const unsigned long long t0 = x->t_ring[2 * slot], t1 = x->t_ring[2 * slot + 1];
+        if (t1 >= t0 && t0 != 0 && ms_out) ms_out[got++] = (float)((double)(t1 - t0) * 1e-6);
     }
-    cudaGetLastError();
     *n_out = got;
     x->ev_count = 0;
     return 0;

@@ -194,3 +194,119 @@ int vq_hostx_allgather(vq_hostx *x, const void *mine, int64_t nbytes, void *all_
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------ per-query summary record
+// What one rank tells the others after its local scan (sharded.RankSummary): int64
+//   [0] first global row | [1..4] n_match n_near n_tie n_topk | [5 .. 5+k) top-k global rows (-1 padded) |
+//   [5+k .. 5+2k) top-k fp32 score bits | 3: best near miss (position in this rank's near-miss list, global row or -1,
+//   score bits) | tie_cap tie rows (-1 padded) | tie_cap tie score bits.
+// Packing and merging are on the per-query path of every rank (twice per query in Python cost 130 us at 8 ranks).
+extern "C" int vq_summary_pack(int64_t first_row, const int64_t *counts3, int32_t k, int32_t n_topk, const int64_t *topk_rows,
+                               const float *topk_scores, const int64_t *near_best /* pos, row, score bits; NULL = none */,
+                               int32_t tie_cap, int32_t n_ties, const int64_t *tie_rows, const float *tie_scores,
+                               int64_t *rec_out /* [5 + 2k + 3 + 2 tie_cap] */) {
+    VQ_REQUIRE(counts3 && rec_out && k >= 0 && n_topk >= 0 && n_topk <= k && tie_cap >= 0 && n_ties >= 0,
+               "vq_summary_pack: bad argument");
+    VQ_REQUIRE((n_topk == 0 || (topk_rows && topk_scores)) && (n_ties == 0 || n_ties > tie_cap || (tie_rows && tie_scores)),
+               "vq_summary_pack: null list");
+    const uint32_t ninf = 0xff800000u;
+    rec_out[0] = first_row;
+    rec_out[1] = counts3[0];
+    rec_out[2] = counts3[1];
+    rec_out[3] = counts3[2];
+    rec_out[4] = n_topk;
+    for (int i = 0; i < k; ++i) {
+        uint32_t bits = ninf;
+        if (i < n_topk) memcpy(&bits, &topk_scores[i], 4);
+        rec_out[5 + i] = i < n_topk ? topk_rows[i] : -1;
+        rec_out[5 + k + i] = (int64_t)bits;
+    }
+    int64_t *o = rec_out + 5 + 2 * k;
+    o[0] = -1; o[1] = -1; o[2] = 0;
+    if (near_best && near_best[1] >= 0) { o[0] = near_best[0]; o[1] = near_best[1]; o[2] = near_best[2]; }
+    o += 3;
+    const bool fits = n_ties <= tie_cap;                 // a longer band rides with the lists; the count says so
+    for (int i = 0; i < tie_cap; ++i) {
+        uint32_t bits = ninf;
+        if (fits && i < n_ties) memcpy(&bits, &tie_scores[i], 4);
+        o[i] = (fits && i < n_ties) ? tie_rows[i] : -1;
+        o[tie_cap + i] = (int64_t)bits;
+    }
+    return 0;
+}
+
+// gathered [world][rec_len] -> per-rank first rows and counts, the merged top-k (k-way merge of the ranked lists under
+// score descending, global row ascending), the best near miss of the search set (highest score; equal scores: the lower
+// rank = the earlier rows; position in the search set's near-miss list), the tie band in database order (n_ties_out = -1
+// when some rank's band did not fit its record).
+extern "C" int vq_summary_merge(const int64_t *gathered, int32_t world, int32_t k, int32_t tie_cap, int64_t *first_rows_out,
+                                int64_t *counts_out /* [world][3] */, int64_t *topk_rows_out, float *topk_scores_out,
+                                int32_t *n_topk_out, int64_t *best_out /* pos, row (-1 none), score bits */,
+                                int64_t *tie_rows_out /* [world * tie_cap] */, float *tie_scores_out, int64_t *n_ties_out) {
+    VQ_REQUIRE(gathered && world >= 1 && k >= 0 && tie_cap >= 0 && first_rows_out && counts_out && n_topk_out && best_out &&
+               n_ties_out && (k == 0 || (topk_rows_out && topk_scores_out)), "vq_summary_merge: bad argument");
+    const size_t len = (size_t)5 + 2 * (size_t)k + 3 + 2 * (size_t)tie_cap;
+    auto score_of = [](int64_t bits) { const uint32_t u = (uint32_t)bits; float f; memcpy(&f, &u, 4); return f; };
+    int head[64];
+    VQ_REQUIRE(world <= 64, "vq_summary_merge: at most 64 ranks");
+    bool ties_fit = true;
+    for (int r = 0; r < world; ++r) {
+        const int64_t *g = gathered + (size_t)r * len;
+        first_rows_out[r] = g[0];
+        counts_out[3 * r] = g[1];
+        counts_out[3 * r + 1] = g[2];
+        counts_out[3 * r + 2] = g[3];
+        VQ_REQUIRE(g[4] >= 0 && g[4] <= k, "vq_summary_merge: rank %d reports %lld top-k entries of %d", r, (long long)g[4], k);
+        head[r] = 0;
+        if (g[3] > tie_cap) ties_fit = false;
+    }
+    int n = 0;
+    for (; n < k; ++n) {
+        int best = -1;
+        float bs = 0.f;
+        int64_t br = 0;
+        for (int r = 0; r < world; ++r) {
+            const int64_t *g = gathered + (size_t)r * len;
+            if (head[r] >= (int)g[4]) continue;
+            const float s = score_of(g[5 + k + head[r]]);
+            const int64_t row = g[5 + head[r]];
+            if (best < 0 || s > bs || (s == bs && row < br)) { best = r; bs = s; br = row; }
+        }
+        if (best < 0) break;
+        ++head[best];
+        topk_rows_out[n] = br;
+        topk_scores_out[n] = bs;
+    }
+    *n_topk_out = n;
+    best_out[0] = -1; best_out[1] = -1; best_out[2] = 0;
+    int64_t base = 0;
+    float best_score = 0.f;
+    for (int r = 0; r < world; ++r) {
+        const int64_t *o = gathered + (size_t)r * len + 5 + 2 * (size_t)k;
+        if (o[1] >= 0) {
+            const float s = score_of(o[2]);
+            if (best_out[1] < 0 || s > best_score) {
+                best_out[0] = base + o[0];
+                best_out[1] = o[1];
+                best_out[2] = o[2];
+                best_score = s;
+            }
+        }
+        base += gathered[(size_t)r * len + 2];
+    }
+    *n_ties_out = -1;
+    if (ties_fit) {
+        int64_t m = 0;
+        for (int r = 0; r < world; ++r) {
+            const int64_t *g = gathered + (size_t)r * len;
+            const int64_t *o = g + 5 + 2 * (size_t)k + 3;
+            for (int64_t i = 0; i < g[3]; ++i) {
+                if (tie_rows_out) tie_rows_out[m] = o[i];
+                if (tie_scores_out) tie_scores_out[m] = score_of(o[tie_cap + i]);
+                ++m;
+            }
+        }
+        *n_ties_out = m;
+    }
+    return 0;
+}

@@ -98,6 +98,7 @@ struct vq_store {
     float *h_rank_scores = nullptr;
     int64_t h_rank_cap = 0;
     bool staged = false;             // the mirror holds all three lists + top-k of the last scan (vq_scan)
+    int64_t group_n[2] = {-1, -1};   // first shard of a vq_scan_multi(lists = 1): h_rows[0/1] hold ALL shards' lists, this many entries
     bool staged_ties = false;        // ... at least the tie band + top-k (vq_scan, vq_scan_select)
     void *h_gather = nullptr;        // pinned staging of vq_gather_list / vq_fetch_scores_at (grow-only)
     int64_t h_gather_cap = 0;        // entries

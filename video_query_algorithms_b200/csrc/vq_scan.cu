@@ -577,6 +577,24 @@ publish_results(const PublishArgs a) {
     }
 }
 
+// Second phase of vq_scan_multi: this shard's match and near-miss lists into the search set's host mirror (pinned memory
+// owned by the first shard, written by every device) at the offsets the host computed from all shards' counts.
+__global__ void __launch_bounds__(256)
+publish_lists_at(const unsigned int *__restrict__ rows_m, const float *__restrict__ sc_m, long long n_m,
+                 const unsigned int *__restrict__ rows_n, const float *__restrict__ sc_n, long long n_n, long long first_global_row,
+                 long long *h_rows_m, float *h_sc_m, long long *h_rows_n, float *h_sc_n) {
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long nth = (long long)gridDim.x * blockDim.x;
+    for (long long i = tid; i < n_m; i += nth) {
+        h_rows_m[i] = first_global_row + (long long)rows_m[i];
+        h_sc_m[i] = sc_m[i];
+    }
+    for (long long i = tid; i < n_n; i += nth) {
+        h_rows_n[i] = first_global_row + (long long)rows_n[i];
+        h_sc_n[i] = sc_n[i];
+    }
+}
+
 int fill_args(const vq_store *s, const vq_scan_params *p, ScanArgs *a) {
     VQ_REQUIRE(p, "scan: null params");
     VQ_REQUIRE(p->topk >= 0 && p->topk <= VQ_MAX_TOPK, "scan: topk %d outside 0..%d", p->topk, VQ_MAX_TOPK);
@@ -748,6 +766,7 @@ static int publish(vq_store *s, int lists) {
 static int scan_host_begin(vq_store *s, const float *target, const vq_scan_params *p, int lists, const char *who) {
     VQ_REQUIRE(s && target, "%s: null argument", who);
     VQ_CUDA(cudaSetDevice(s->device));
+    s->group_n[0] = s->group_n[1] = -1;
     const size_t bytes = s->row_floats * sizeof(float);
     memcpy(s->pinned_stage, target, bytes);
     VQ_CUDA(cudaMemcpyAsync(s->target, s->pinned_stage, bytes, cudaMemcpyHostToDevice, s->stream));
@@ -817,8 +836,9 @@ extern "C" int vq_scan_multi(vq_store *const *shards, int32_t n_shards, const fl
                              int64_t *topk_rows_out, float *topk_scores_out, int32_t *n_topk_out) {
     VQ_REQUIRE(shards && n_shards >= 1 && target && p && counts_out, "vq_scan_multi: null argument");
     for (int i = 0; i < n_shards; ++i) VQ_REQUIRE(shards[i], "vq_scan_multi: shard %d is null", i);
+    // phase 1: everything but the two long lists — scan, selection, counts / top-k / tie band / best near miss published
     for (int i = 0; i < n_shards; ++i)
-        if (int r = scan_host_begin(shards[i], target, p, lists, "vq_scan_multi")) {
+        if (int r = scan_host_begin(shards[i], target, p, 0, "vq_scan_multi")) {
             for (int j = 0; j < i; ++j) {                    // leave no stream busy behind an error
                 cudaSetDevice(shards[j]->device);
                 cudaStreamSynchronize(shards[j]->stream);
@@ -827,8 +847,48 @@ extern "C" int vq_scan_multi(vq_store *const *shards, int32_t n_shards, const fl
         }
     int rc = 0;
     for (int i = 0; i < n_shards; ++i)
-        if (int r = scan_host_finish(shards[i], &counts_out[i], lists)) rc = rc ? rc : r;
+        if (int r = scan_host_finish(shards[i], &counts_out[i], 0)) rc = rc ? rc : r;
     if (rc) return rc;
+    vq_store *s0 = shards[0];
+    s0->group_n[0] = s0->group_n[1] = -1;
+    if (lists) {
+        // phase 2: the match / near-miss lists of all shards back to back (shard order = database order) in ONE host
+        // mirror, each device writing its segment: the caller gets the search set's lists without a host-side copy
+        int64_t tot[2] = {0, 0};
+        for (int i = 0; i < n_shards; ++i) { tot[0] += shards[i]->counts_host[0]; tot[1] += shards[i]->counts_host[1]; }
+        for (int w = 0; w < 2; ++w)
+            if (tot[w] > s0->h_cap[w]) {
+                const int64_t keep_rows = s0->n_rows;        // grow_mirror caps at the shard size: the group mirror holds all shards
+                int64_t all_rows = 0;
+                for (int i = 0; i < n_shards; ++i) all_rows += shards[i]->n_rows;
+                s0->n_rows = all_rows;
+                VQ_CUDA(cudaSetDevice(s0->device));
+                const int r = grow_mirror(s0, w, tot[w]);
+                s0->n_rows = keep_rows;
+                if (r) return r;
+            }
+        int64_t off[2] = {0, 0};
+        for (int i = 0; i < n_shards; ++i) {
+            vq_store *s = shards[i];
+            const int64_t nm = s->counts_host[0], nn = s->counts_host[1];
+            if (nm + nn > 0) {
+                VQ_CUDA(cudaSetDevice(s->device));
+                publish_lists_at<<<s->sm_count, 256, 0, s->stream>>>(
+                    s->list_rows[0], s->list_scores[0], nm, s->list_rows[1], s->list_scores[1], nn, s->first_global_row,
+                    (long long *)s0->h_rows[0] + off[0], s0->h_scores[0] + off[0], (long long *)s0->h_rows[1] + off[1],
+                    s0->h_scores[1] + off[1]);
+                VQ_CUDA(cudaGetLastError());
+            }
+            off[0] += nm;
+            off[1] += nn;
+        }
+        for (int i = 0; i < n_shards; ++i) {
+            VQ_CUDA(cudaSetDevice(shards[i]->device));
+            VQ_CUDA(cudaStreamSynchronize(shards[i]->stream));
+        }
+        s0->group_n[0] = tot[0];
+        s0->group_n[1] = tot[1];
+    }
     if (near_best_out)
         for (int i = 0; i < n_shards; ++i) {
             near_best_out[3 * i] = shards[i]->h_result[7];         // position in the shard's near-miss list
@@ -858,6 +918,18 @@ extern "C" int vq_scan_multi(vq_store *const *shards, int32_t n_shards, const fl
         }
         *n_topk_out = n;
     }
+    return 0;
+}
+
+// The search set's match (which = 0) or near-miss (1) list of the last vq_scan_multi(lists = 1) whose first shard is `first`:
+// read-only views of the host mirror all shards published into, global rows in database order; valid until the next scan.
+extern "C" int vq_scan_multi_host_list(vq_store *first, int32_t which, const int64_t **rows, const float **scores, int64_t *n) {
+    VQ_REQUIRE(first && rows && scores && n, "vq_scan_multi_host_list: null argument");
+    VQ_REQUIRE(which == 0 || which == 1, "vq_scan_multi_host_list: list %d (0 = matches, 1 = near misses)", which);
+    VQ_REQUIRE(first->group_n[which] >= 0, "vq_scan_multi_host_list: the last scan on these shards was not vq_scan_multi with lists");
+    *rows = first->h_rows[which];
+    *scores = first->h_scores[which];
+    *n = first->group_n[which];
     return 0;
 }
 

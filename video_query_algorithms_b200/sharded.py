@@ -298,49 +298,73 @@ class RankSummary:
         return self.counts.sum(axis=0)
 
 
+class _Scratch:
+    """Persistent numpy buffers with their addresses taken once: the summary record is packed and merged on every rank's
+    per-query path, where `ndarray.ctypes` (about 4 us per pointer) would cost more than the work itself."""
+
+    def __init__(self, **shapes):
+        self.a, self.p = {}, {}
+        for name, (shape, dtype) in shapes.items():
+            self.a[name] = np.empty(shape, dtype)
+            self.p[name] = self.a[name].ctypes.data
+
+
+_PACK, _MERGE = {}, {}
+
+
 def summary_record(first_row, counts3, topk_rows, topk_scores, k, near_best=None, ties=None):
     """int64 [5 + 2k + 3 + 2*TIE_CAP]: first row | n_match n_near n_tie n_topk | top-k rows | top-k score bits |
-    best near miss (position in this rank's near-miss list, global row, score bits; row -1 = none) | tie rows | tie bits."""
-    rec = np.empty(5 + 2 * k + 3 + 2 * TIE_CAP, np.int64)
-    rec[0] = first_row
-    rec[1:5] = pack_payload(list(counts3) + [len(topk_rows)], topk_rows, topk_scores, k)[:4]
-    rec[5:5 + 2 * k] = pack_payload([0, 0, 0, 0], topk_rows, topk_scores, k)[4:]
-    o = 5 + 2 * k
-    rec[o:o + 3] = (-1, -1, 0)
+    best near miss (position in this rank's near-miss list, global row, score bits; row -1 = none) | tie rows | tie bits.
+    Packed by the library (vq_summary_pack)."""
+    k = int(k)
+    sc = _PACK.get((k, TIE_CAP))
+    if sc is None:
+        sc = _PACK[(k, TIE_CAP)] = _Scratch(c3=(3, np.int64), t_rows=(max(k, 1), np.int64), t_sc=(max(k, 1), np.float32),
+                                           nb=(3, np.int64), nb_sc=(1, np.float32), tie_r=(TIE_CAP, np.int64), tie_s=(TIE_CAP, np.float32))
+    A, P = sc.a, sc.p
+    A["c3"][:] = counts3
+    n_top = len(topk_rows)
+    A["t_rows"][:n_top] = topk_rows
+    A["t_sc"][:n_top] = topk_scores
+    nb_p = None
     if near_best is not None and near_best[1] >= 0:
-        rec[o:o + 3] = near_best[0], near_best[1], _bits([near_best[2]])[0]
-    o += 3
-    rec[o:o + TIE_CAP] = -1
-    rec[o + TIE_CAP:] = _F32_NINF_BITS
-    if ties is not None and len(ties[0]) <= TIE_CAP:
-        rec[o:o + len(ties[0])] = ties[0]
-        rec[o + TIE_CAP:o + TIE_CAP + len(ties[0])] = _bits(ties[1])
+        A["nb_sc"][0] = near_best[2]
+        A["nb"][0], A["nb"][1], A["nb"][2] = near_best[0], near_best[1], int(A["nb_sc"].view(np.uint32)[0])
+        nb_p = P["nb"]
+    n_ties = int(A["c3"][2])
+    if ties is not None:
+        n_ties = len(ties[0])
+        if n_ties <= TIE_CAP:
+            A["tie_r"][:n_ties] = ties[0]
+            A["tie_s"][:n_ties] = ties[1]
+    elif n_ties:
+        n_ties = TIE_CAP + 1                                 # no list at hand: marked as "rides with the lists"
+    rec = np.empty(5 + 2 * k + 3 + 2 * TIE_CAP, np.int64)
+    check(lib().vq_summary_pack(int(first_row), P["c3"], k, n_top, P["t_rows"], P["t_sc"], nb_p, TIE_CAP, n_ties,
+                                P["tie_r"], P["tie_s"], rec.ctypes.data), "vq_summary_pack")
     return rec
 
 
 def exchange_summary(rec, k, dist, torch, device=None, mailbox=None):
     """all_gather of summary_record -> RankSummary (identical on every rank); through the host mailbox when there
-    is one and the record fits its slots, else a collective of `dist`."""
+    is one and the record fits its slots, else a collective of `dist`.  Merged by the library (vq_summary_merge)."""
     g = mailbox.all_gather(rec) if mailbox is not None and mailbox.fits(rec) else all_gather_np(rec, dist, torch, device)
-    world = g.shape[0]
-    counts = g[:, 1:4].copy()
-    pay = np.concatenate([g[:, 1:5], g[:, 5:5 + 2 * k]], axis=1)
-    _, t_rows, t_scores = unpack_payload(merge_payloads_host(pay, world, k), k) if k else \
-        (None, np.empty(0, np.int64), np.empty(0, np.float32))
-    o = 5 + 2 * k
-    best, base = None, 0
-    for r in range(world):                                   # highest score; equal scores: the lower rank = the earlier rows
-        if g[r, o + 1] >= 0:
-            sc = float(_floats(g[r, o + 2:o + 3])[0])
-            if best is None or sc > best[2]:
-                best = (base + int(g[r, o]), int(g[r, o + 1]), sc)
-        base += int(counts[r, 1])
-    o += 3
-    ties = None
-    if int(counts[:, 2].max(initial=0)) <= TIE_CAP:
-        ties = (np.concatenate([g[r, o:o + counts[r, 2]] for r in range(world)]),
-                _floats(np.concatenate([g[r, o + TIE_CAP:o + TIE_CAP + counts[r, 2]] for r in range(world)])))
-    return RankSummary(g[:, 0].copy(), counts, (t_rows, t_scores), best, ties)
+    g = np.ascontiguousarray(g, dtype=np.int64)
+    world, k = g.shape[0], int(k)
+    sc = _MERGE.get((world, k, TIE_CAP))
+    if sc is None:
+        sc = _MERGE[(world, k, TIE_CAP)] = _Scratch(
+            first=(world, np.int64), counts=((world, 3), np.int64), t_rows=(max(k, 1), np.int64), t_sc=(max(k, 1), np.float32),
+            best=(3, np.int64), tie_r=(world * TIE_CAP, np.int64), tie_s=(world * TIE_CAP, np.float32))
+    A, P = sc.a, sc.p
+    n_top, n_ties = C.c_int32(), C.c_int64()
+    check(lib().vq_summary_merge(g.ctypes.data, world, k, TIE_CAP, P["first"], P["counts"], P["t_rows"], P["t_sc"],
+                                 C.byref(n_top), P["best"], P["tie_r"], P["tie_s"], C.byref(n_ties)), "vq_summary_merge")
+    best = A["best"]
+    near_best = None if best[1] < 0 else (int(best[0]), int(best[1]), float(best[2:3].astype(np.uint32).view(np.float32)[0]))
+    ties = None if n_ties.value < 0 else (A["tie_r"][:n_ties.value].copy(), A["tie_s"][:n_ties.value].copy())
+    return RankSummary(A["first"].copy(), A["counts"].copy(), (A["t_rows"][:n_top.value].copy(), A["t_sc"][:n_top.value].copy()),
+                       near_best, ties)
 
 
 _HOST_OUT = {}

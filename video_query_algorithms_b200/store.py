@@ -636,6 +636,20 @@ class FeatureStore:
         return rows, scores
 
     def _fetch_list(self, fn, attr, which, copy):
+        if len(self.shards) > 1 and which < 2 and self._lists_on_host:
+            # vq_scan_multi published every shard's segment into one host mirror: the search set's list, no concatenation
+            rp, sp, n = C.c_void_p(), C.c_void_p(), C.c_int64()
+            check(lib().vq_scan_multi_host_list(self.shards[0].handle, which, C.byref(rp), C.byref(sp), C.byref(n)),
+                  "vq_scan_multi_host_list")
+            if n.value == 0:
+                return np.empty(0, np.int64), np.empty(0, np.float32)
+            r = np.ctypeslib.as_array(C.cast(rp, C.POINTER(C.c_int64)), shape=(n.value,))
+            s_ = np.ctypeslib.as_array(C.cast(sp, C.POINTER(C.c_float)), shape=(n.value,))
+            if copy:
+                return r.copy(), s_.copy()
+            r.flags.writeable = False
+            s_.flags.writeable = False
+            return r, s_
         rows, scores = [], []
         copy = copy or not (self._lists_on_host or which == 2)      # after a lists=False scan only the tie band is mirrored
         for sh, c in zip(self.shards, self._last_counts):
