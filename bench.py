@@ -287,8 +287,18 @@ def main():
         k1_mine = float(np.mean(k1[:cnt.value])) if cnt.value else float("nan")
         phases = {"k1_ms": max_over_ranks(k1_mine), "k1_ms_rank0": k1_mine,
                   "select_ms": max_over_ranks(float(np.mean(sel[:cnt.value])) if cnt.value else float("nan")),
-                  "exchange_ms": max_over_ranks(float(np.mean(xt))) if len(xt) else 0.0,
+                  "exchange_ms_overlapped": max_over_ranks(float(np.mean(xt))) if len(xt) else 0.0,
                   "launches_timed": int(cnt.value)}
+        if world > 1 and rs._x is not None:
+            # the exchange kernel by itself on an otherwise idle GPU (in the timed region it runs beside the next step's
+            # scan, where every one of its dependent memory round trips queues behind a saturated HBM)
+            fn = lib.vq_scan_exchange_enqueue_lagged if args.exchange == "p2p-lagged" else lib.vq_scan_exchange_enqueue
+            for _ in range(24):
+                _ffi.check(fn(handle_, rs._x, sptr), "vq_scan_exchange_enqueue")
+            rs.flush(stream.cuda_stream)
+            barrier()
+            xi = rs.exchange_times()
+            phases["exchange_ms_alone"] = max_over_ranks(float(np.mean(xi[4:]))) if len(xi) > 4 else None
         return ms_total / steps, phases, rs
 
     sampler = ClockSampler(local_rank)               # NVML init happens here, outside every timed region
@@ -530,7 +540,9 @@ def main():
                          "frac_of_nominal_8TBs": achieved / 8000.0,
                          "algorithmic_bytes_per_launch": n * ROW_BYTES},
             "kernel_times": dict(phases, what="CUDA events inside the timed region, mean per launch, max over ranks: K1 scan, "
-                                 "K2a-c selection, exchange kernel (on its own stream: overlaps the next step's K1)"),
+                                 "K2a-c selection; exchange kernel timed by itself on the global timer — `overlapped`: inside the timed "
+                                 "region, on its own stream beside the next step's K1 (off the scan stream's critical path); "
+                                 "`alone`: the same kernel back to back on an idle GPU"),
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "what": e2e_what},
             "e2e_select": {"value": e2e_select_value, "unit": "clips/s", "h2d_bytes_per_step": int(h2d + 19 * 8),
