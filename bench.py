@@ -401,8 +401,7 @@ def main():
         if rstore is not None:
             rstore.gather_many([("matches", pos_m), ("near_misses", pos_n)])
         else:
-            st.gather("matches", pos_m)
-            st.gather("near_misses", pos_n)
+            st.gather_many([("matches", pos_m), ("near_misses", pos_n)])
 
     sel_s, _ = timed(select_step, e2e_steps)
     e2e_select_value = world * n * e2e_steps / sel_s
@@ -462,8 +461,8 @@ def main():
                 def sp_select():
                     r2 = big.scan(tdict, WEIGHTS, THRESHOLD, lower, EPS, topk=TOPK, lists=False)
                     big.topk(); big.ties(copy=False); big.near_best()
-                    big.gather("matches", _random.sample(range(r2.n_match), 10))
-                    big.gather("near_misses", _random.sample(range(r2.n_near - 1), 9))
+                    big.gather_many([("matches", _random.sample(range(r2.n_match), 10)),
+                                     ("near_misses", _random.sample(range(r2.n_near - 1), 9))])
                 for _ in range(3):
                     sp_select()
                 t1 = time.perf_counter()

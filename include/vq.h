@@ -116,6 +116,10 @@ int vq_gather_list(vq_store *s, int32_t which, int64_t n_idx, const int64_t *pos
 int vq_scan_multi(vq_store *const *shards, int32_t n_shards, const float *target, const vq_scan_params *p,
                   int32_t lists, vq_scan_counts *counts_out, int64_t *near_best_out, int32_t topk_cap,
                   int64_t *topk_rows_out, float *topk_scores_out, int32_t *n_topk_out);
+/* Entries of the search set's lists after a vq_scan_multi: which[e] names the list (0 matches, 1 near misses, 2 ties),
+ * positions[e] the position in it; gather kernels on all owning shards first, then one wait per shard.                */
+int vq_gather_list_multi(vq_store *const *shards, int32_t n_shards, int64_t n_idx, const int32_t *which,
+                         const int64_t *positions, int64_t *rows_out, float *scores_out);
 int vq_scan_multi_host_list(vq_store *first_shard, int32_t which, const int64_t **rows, const float **scores, int64_t *n);
 /* Same work, enqueued only: target already on the device, nothing copied back, no sync.
  * Used for device-side timing and for multi-GPU merges that read the results in place.      */

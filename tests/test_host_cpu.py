@@ -467,6 +467,9 @@ class _ArrayStore:
         pos = np.asarray(positions, np.int64)
         return self._l[which][pos].astype(np.int64), self._s[self._l[which][pos]]
 
+    def gather_many(self, requests):
+        return [self.gather(w, p) for w, p in requests]
+
     def near_best(self):
         n = self._l["near_misses"]
         if not len(n):

@@ -111,6 +111,9 @@ def make_oracle_store_class():
             pos = np.asarray(positions, np.int64)
             return rows[pos], scores[pos]
 
+        def gather_many(self, requests):
+            return [self.gather(w, p) for w, p in requests]
+
         def near_best(self):
             rows, scores = self._list("near_misses")
             if not len(rows):

@@ -61,6 +61,7 @@ PROTOTYPES = {
     "vq_scan_select": (C.c_int, [_vp, _vp, _P(ScanParams), _P(ScanCounts), _i64p, _i64p, _f32p]),
     "vq_gather_list": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _vp]),
     "vq_scan_multi": (C.c_int, [_vp, _i32, _vp, _P(ScanParams), _i32, _vp, _vp, _i32, _vp, _vp, _P(_i32)]),
+    "vq_gather_list_multi": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _vp, _vp]),
     "vq_scan_multi_host_list": (C.c_int, [_vp, _i32, _P(_vp), _P(_vp), _i64p]),
     "vq_fetch_scores_at": (C.c_int, [_vp, _i64, _vp, _vp]),
     "vq_scan_phase_times": (C.c_int, [_vp, _i32, _vp, _vp, _P(_i32)]),

@@ -983,6 +983,77 @@ extern "C" int vq_gather_list(vq_store *s, int32_t which, int64_t n_idx, const i
     return 0;
 }
 
+// The same for a store of several shards, both lists, one call: positions index the search set's lists (the shards' lists in
+// shard order); each entry names its list (0 matches, 1 near misses, 2 ties).  The gather kernels are enqueued on every
+// shard's stream before any stream is waited for — one round trip for a review round's 20 sampled clips whatever the
+// number of shards (ticket.py:333,341).
+extern "C" int vq_gather_list_multi(vq_store *const *shards, int32_t n_shards, int64_t n_idx, const int32_t *which,
+                                    const int64_t *positions, int64_t *rows_out, float *scores_out) {
+    VQ_REQUIRE(shards && n_shards >= 1 && (n_idx == 0 || (which && positions && rows_out && scores_out)),
+               "vq_gather_list_multi: null argument");
+    VQ_REQUIRE(n_idx >= 0 && n_idx < (1ll << 24), "vq_gather_list_multi: %lld positions", (long long)n_idx);
+    for (int i = 0; i < n_shards; ++i) VQ_REQUIRE(shards[i], "vq_gather_list_multi: shard %d is null", i);
+    if (n_idx == 0) return 0;
+    // per shard and list: the entries it owns, in request order
+    std::vector<std::vector<int64_t>> at((size_t)n_shards * 3);
+    for (int64_t e = 0; e < n_idx; ++e) {
+        const int w = which[e];
+        VQ_REQUIRE(w >= 0 && w <= 2, "vq_gather_list_multi: list %d outside 0..2", w);
+        int64_t p = positions[e];
+        int owner = -1;
+        for (int i = 0; i < n_shards && p >= 0; ++i) {
+            if (p < shards[i]->counts_host[w]) { owner = i; break; }
+            p -= shards[i]->counts_host[w];
+        }
+        VQ_REQUIRE(owner >= 0, "vq_gather_list_multi: position %lld outside list %d of the search set", (long long)positions[e], w);
+        at[(size_t)owner * 3 + w].push_back(e);
+    }
+    struct Job { int shard, w; int64_t off, n; };
+    std::vector<Job> jobs;
+    for (int i = 0; i < n_shards; ++i) {
+        vq_store *s = shards[i];
+        int64_t need = 0;
+        for (int w = 0; w < 3; ++w) need += (int64_t)at[(size_t)i * 3 + w].size();
+        if (!need) continue;
+        VQ_CUDA(cudaSetDevice(s->device));
+        if (int r = grow_gather(s, need)) return r;
+        long long *h_pos = (long long *)s->h_gather, *h_rows = h_pos + s->h_gather_cap;
+        float *h_sc = (float *)(h_rows + s->h_gather_cap);
+        int64_t base[3] = {0, 0, 0};
+        for (int j = 0; j < i; ++j)
+            for (int w = 0; w < 3; ++w) base[w] += shards[j]->counts_host[w];
+        int64_t off = 0;
+        for (int w = 0; w < 3; ++w) {
+            const std::vector<int64_t> &v = at[(size_t)i * 3 + w];
+            if (v.empty()) continue;
+            for (size_t q = 0; q < v.size(); ++q) h_pos[off + (int64_t)q] = positions[v[q]] - base[w];
+            gather_list<<<(unsigned int)((v.size() + 255) / 256), 256, 0, s->stream>>>(
+                s->list_rows[w], s->list_scores[w], s->counts_host[w], h_pos + off, (int)v.size(), s->first_global_row,
+                h_rows + off, h_sc + off);
+            VQ_CUDA(cudaGetLastError());
+            jobs.push_back({i, w, off, (int64_t)v.size()});
+            off += (int64_t)v.size();
+        }
+    }
+    int last = -1;
+    for (const Job &j : jobs) {
+        vq_store *s = shards[j.shard];
+        if (j.shard != last) {
+            VQ_CUDA(cudaSetDevice(s->device));
+            VQ_CUDA(cudaStreamSynchronize(s->stream));
+            last = j.shard;
+        }
+        const long long *h_rows = (long long *)s->h_gather + s->h_gather_cap;
+        const float *h_sc = (const float *)(h_rows + s->h_gather_cap);
+        const std::vector<int64_t> &v = at[(size_t)j.shard * 3 + j.w];
+        for (int64_t q = 0; q < j.n; ++q) {
+            rows_out[v[(size_t)q]] = h_rows[j.off + q];
+            scores_out[v[(size_t)q]] = h_sc[j.off + q];
+        }
+    }
+    return 0;
+}
+
 namespace {
 __global__ void gather_scores(const float *__restrict__ scores, long long n_rows, const long long *__restrict__ rows, int n,
                               float *out) {

@@ -614,9 +614,30 @@ class FeatureStore:
             base += c.n_near
         return best
 
+    def gather_many(self, requests):
+        """[(which, positions)] -> [(global rows, fp32 scores)] with ONE library call for all requests and all shards
+        (a review round fetches its sampled matches and near misses together, ticket.py:333,341)."""
+        names = {"matches": 0, "near_misses": 1, "ties": 2}
+        pos = [np.asarray(p, dtype=np.int64).reshape(-1) for _, p in requests]
+        n = sum(len(p) for p in pos)
+        rows, scores = np.empty(n, np.int64), np.empty(n, np.float32)
+        if n:
+            which = np.concatenate([np.full(len(p), names[w], np.int32) for (w, _), p in zip(requests, pos)])
+            allp = np.ascontiguousarray(np.concatenate(pos))
+            handles = (C.c_void_p * len(self.shards))(*[sh.handle for sh in self.shards])
+            check(lib().vq_gather_list_multi(handles, len(self.shards), n, ptr(which), ptr(allp), ptr(rows), ptr(scores)),
+                  "vq_gather_list_multi")
+        out, o = [], 0
+        for p in pos:
+            out.append((rows[o:o + len(p)], scores[o:o + len(p)]))
+            o += len(p)
+        return out
+
     def gather(self, which, positions):
         """Entries of the ordered match / near-miss / tie list of the last scan at the given list positions:
         (global rows, fp32 scores).  One small round trip instead of the whole list."""
+        if len(self.shards) > 1:
+            return self.gather_many([(which, positions)])[0]
         idx = {"matches": 0, "near_misses": 1, "ties": 2}[which]
         attr = ("n_match", "n_near", "n_tie")[idx]
         pos = np.asarray(positions, dtype=np.int64).reshape(-1)

@@ -376,9 +376,7 @@ class Ticket:
         # random.sample(population, k) draws depend only on (len(population), k): sampling the index
         # range consumes the generator exactly like sampling the reference's dict items (:333).
         picked = sample_range(random, res.n_match, mscores)
-        if sampled:
-            m_rows, m_sc = st.gather("matches", picked)
-        else:
+        if not sampled:
             all_rows, all_sc = st.matches(copy=False)     # views of the scan's host mirror: consumed before the next scan
             m_rows, m_sc = all_rows[picked], all_sc[picked]
         jbest, best_row, best_sc = None, None, None
@@ -395,8 +393,8 @@ class Ticket:
         picked_n = sample_range(random, n_left, m_near_scores)
         # positions in the list with the best near miss deleted (:340) -> positions in the full list
         pos = picked_n if jbest is None else picked_n + (picked_n >= jbest)
-        if sampled:
-            n_rows_p, n_sc_p = st.gather("near_misses", pos)
+        if sampled:                                        # one round trip for both lists' sampled entries
+            (m_rows, m_sc), (n_rows_p, n_sc_p) = st.gather_many([("matches", picked), ("near_misses", pos)])
         else:
             nm_rows, nm_sc = st.near_misses(copy=False)
             n_rows_p, n_sc_p = nm_rows[pos], nm_sc[pos]
