@@ -8,6 +8,7 @@
 // ticket.py:266).  The kernel itself is in vq_batch_bf16.cuh; this file holds the per-chunk top-k compaction
 // kernels, the tensor maps and the launch loop.
 #include <cuda.h>
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -43,6 +44,9 @@ struct BatchArgs {
     // tie band: closed fp32 intervals holding exactly the floats s with |(double)s - th| < eps (0) and |(double)s - lo| < eps (1)
     float tie_lo0, tie_hi0, tie_lo1, tie_hi1;
     long long tie_cap;
+    // fp16 + fp8 operand split (vq_batch_bf16.cuh): per stream, sx = bx * 2^6 scales the clip rows into fp16 range and
+    // descale = 1 / (4096 bx bt) undoes both operand scales on the stream's sum (powers of two: exact)
+    float sx[VQ_MAX_STREAMS], descale[VQ_MAX_STREAMS];
 };
 
 #include "vq_batch_bf16.cuh"
@@ -136,6 +140,39 @@ void tie_interval(double c, double eps, float *lo, float *hi) {
     }
 }
 
+// max |x| per stream over the shard (bit pattern of a non-negative float orders like the float); NaNs are skipped
+__global__ void absmax_kernel(const float4 *__restrict__ rows, long long n_vec, int vec_per_row, int vec_per_stream, unsigned int *out) {
+    __shared__ unsigned int red[VQ_MAX_STREAMS];
+    if (threadIdx.x < VQ_MAX_STREAMS) red[threadIdx.x] = 0u;
+    __syncthreads();
+    float m[VQ_MAX_STREAMS] = {0.f, 0.f, 0.f, 0.f};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_vec; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = rows[i];
+        const int s = (int)(i % vec_per_row) / vec_per_stream;
+        float a = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));      // fmaxf drops NaNs
+        if (!(a < INFINITY)) a = 0.f;
+#pragma unroll
+        for (int q = 0; q < VQ_MAX_STREAMS; ++q) m[q] = (q == s) ? fmaxf(m[q], a) : m[q];
+    }
+#pragma unroll
+    for (int q = 0; q < VQ_MAX_STREAMS; ++q) {
+        float v = m[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if ((threadIdx.x & 31) == 0 && v > 0.f) atomicMax(&red[q], __float_as_uint(v));
+    }
+    __syncthreads();
+    if (threadIdx.x < VQ_MAX_STREAMS && red[threadIdx.x]) atomicMax(&out[threadIdx.x], red[threadIdx.x]);
+}
+
+// largest power of two b with mx * b <= top (1 when mx is 0 or not finite)
+float pow2_scale(float mx, float top) {
+    if (!(mx > 0.f) || !(mx < INFINITY)) return 1.f;
+    int e;
+    frexpf(top / mx, &e);                       // top / mx = f * 2^e, 0.5 <= f < 1  ->  2^(e-1) <= top / mx
+    return ldexpf(1.f, e - 1);
+}
+
 constexpr long long kTieCap = 4096;      // tie-band entries kept per query (the band is 2 * COMPUTE_EPS wide: ~1e-5 of the rows)
 
 struct Dev {
@@ -147,7 +184,7 @@ struct Dev {
 
 // Scratch of the batched path, owned by the store: allocated on the first batched scan, reused by every later one.
 struct BatchScratch {
-    Dev t, t1, t2, cut, counts, cnt, keys, rows, sc, park, tie_cnt, tie_keys;
+    Dev t, t1, t2, cut, counts, cnt, keys, rows, sc, park, tie_cnt, tie_keys, amax;
     void *pinned_t = nullptr;            // pinned staging for one pass of targets
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     ~BatchScratch() {
@@ -171,6 +208,7 @@ int alloc_batch_scratch(const vq_store *s, size_t K, long long cap, BatchScratch
     VQ_CUDA(b->sc.alloc((size_t)QN * VQ_MAX_TOPK * 4));
     VQ_CUDA(b->park.alloc((size_t)s->sm_count * QN * bf::BM * 4));
     VQ_CUDA(b->tie_cnt.alloc(QN * 4));
+    VQ_CUDA(b->amax.alloc(VQ_MAX_STREAMS * 4));
     VQ_CUDA(b->tie_keys.alloc((size_t)QN * kTieCap * 8));
     VQ_CUDA(cudaMallocHost(&b->pinned_t, (size_t)QN * K * 4));
     VQ_CUDA(cudaEventCreate(&b->e0));
@@ -200,6 +238,7 @@ int run_batch_bf16(vq_store *s, const float *targets, int n_queries, const vq_sc
     VQ_REQUIRE(s && targets && p, "vq_scan_batch: null argument");
     VQ_REQUIRE(n_queries >= 1, "vq_scan_batch: need at least one query");
     VQ_REQUIRE(s->stream_len % bf::BK == 0, "vq_scan_batch: stream length %d is not a multiple of %d", s->stream_len, bf::BK);
+    VQ_REQUIRE(s->stream_len % 16 == 0, "vq_scan_batch: stream length %d is not a multiple of 16", s->stream_len);
     VQ_REQUIRE(p->topk >= 0 && p->topk <= VQ_MAX_TOPK, "vq_scan_batch: topk %d outside 0..%d", p->topk, VQ_MAX_TOPK);
     VQ_REQUIRE(s->n_rows < (1ll << 31), "vq_scan_batch: shard too large for 32-bit TMA coordinates");
     double den = 0.0;
@@ -238,6 +277,21 @@ int run_batch_bf16(vq_store *s, const float *targets, int n_queries, const vq_sc
     }
     memset(wd_host, 0, 256 * 16 * 2 * 8);
 #endif
+#ifndef VQ_BATCH_BF16X3
+    // clip-row scale per stream: max |x| of the shard, taken once per content version (upload / append / fill reset it)
+    if (!s->batch_absmax_valid && s->n_rows > 0) {
+        VQ_CUDA(cudaMemsetAsync(bs->amax.p, 0, VQ_MAX_STREAMS * 4, st));
+        const long long n_vec = (long long)s->n_rows * (long long)(K / 4);
+        absmax_kernel<<<s->sm_count * 8, 256, 0, st>>>(reinterpret_cast<const float4 *>(s->rows), n_vec, (int)(K / 4),
+                                                      s->stream_len / 4, bs->amax.as<unsigned int>());
+        VQ_CUDA(cudaGetLastError());
+        unsigned int bits[VQ_MAX_STREAMS];
+        VQ_CUDA(cudaMemcpyAsync(bits, bs->amax.p, sizeof(bits), cudaMemcpyDeviceToHost, st));
+        VQ_CUDA(cudaStreamSynchronize(st));
+        for (int i = 0; i < VQ_MAX_STREAMS; ++i) memcpy(&s->batch_absmax[i], &bits[i], 4);
+        s->batch_absmax_valid = true;
+    }
+#endif
     float total_ms = 0.f;
     int rc = 0;
     for (int q0 = 0; q0 < n_queries && rc == 0; q0 += QN) {
@@ -245,8 +299,31 @@ int run_batch_bf16(vq_store *s, const float *targets, int n_queries, const vq_sc
         if (nq < QN) VQ_CUDA(cudaMemsetAsync(d_t.p, 0, (size_t)QN * K * 4, st));
         memcpy(bs->pinned_t, targets + (size_t)q0 * K, (size_t)nq * K * 4);       // caller memory may be pageable
         VQ_CUDA(cudaMemcpyAsync(d_t.p, bs->pinned_t, (size_t)nq * K * 4, cudaMemcpyHostToDevice, st));
+        float sx[VQ_MAX_STREAMS] = {1.f, 1.f, 1.f, 1.f}, stq[VQ_MAX_STREAMS] = {1.f, 1.f, 1.f, 1.f}, descale[VQ_MAX_STREAMS] = {1.f, 1.f, 1.f, 1.f};
+#ifdef VQ_BATCH_BF16X3
         bf::split_targets_bf16<<<(unsigned)(((size_t)QN * K + 255) / 256), 256, 0, st>>>(
             d_t.as<float>(), d_t1.as<unsigned short>(), d_t2.as<unsigned short>(), (long long)QN * K);
+#else
+        for (int si = 0; si < s->n_streams; ++si) {          // query scale per stream: max |t| over this pass's targets
+            float mx = 0.f;
+            for (int q = 0; q < nq; ++q) {
+                const float *tp = targets + (size_t)(q0 + q) * K + (size_t)si * s->stream_len;
+                for (int d = 0; d < s->stream_len; ++d) {
+                    const float v = fabsf(tp[d]);
+                    if (v > mx && v < INFINITY) mx = v;
+                }
+            }
+            const float bx = pow2_scale(s->batch_absmax[si], 128.f), bt = pow2_scale(mx, 128.f);
+            sx[si] = bx * 64.f;
+            stq[si] = bt * 64.f;
+            descale[si] = 1.f / (4096.f * bx * bt);
+            VQ_REQUIRE(descale[si] > 0.f && descale[si] < INFINITY && sx[si] < INFINITY && stq[si] < INFINITY,
+                       "vq_scan_batch: operand scales out of range (stream %d: max |x| %g, max |t| %g)", si, (double)s->batch_absmax[si], (double)mx);
+        }
+        bf::split_targets_f16f8<<<(unsigned)(((size_t)QN * K / 16 + 255) / 256), 256, 0, st>>>(
+            d_t.as<float>(), d_t1.as<unsigned short>(), d_t2.as<unsigned char>(), (long long)QN * (long long)K / 16, s->stream_len,
+            s->n_streams, stq[0], stq[1], stq[2], stq[3]);
+#endif
         fill_f32<<<1, QN, 0, st>>>(d_cut.as<float>(), topk > 0 ? -INFINITY : INFINITY, QN);   // no top-k: nothing is a candidate
         VQ_CUDA(cudaMemsetAsync(d_counts.p, 0, QN * 2 * 8, st));
         VQ_CUDA(cudaMemsetAsync(d_cnt.p, 0, QN * 4, st));
@@ -272,6 +349,7 @@ int run_batch_bf16(vq_store *s, const float *targets, int n_queries, const vq_sc
         a.n_streams = s->n_streams;
         a.n_rows_total = s->n_rows;
         a.cand_cap = cap;
+        for (int i = 0; i < VQ_MAX_STREAMS; ++i) { a.sx[i] = sx[i]; a.descale[i] = descale[i]; }
         tie_interval(p->threshold, want_ties ? p->eps : 0.0, &a.tie_lo0, &a.tie_hi0);
         tie_interval(p->lower_limit, want_ties ? p->eps : 0.0, &a.tie_lo1, &a.tie_hi1);
         a.tie_cap = kTieCap;

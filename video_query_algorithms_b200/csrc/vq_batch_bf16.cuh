@@ -28,6 +28,18 @@
 //                  converted and stored
 //     warps 8-15   epilogue: drains, running sums, scores, per-query counts (bit-mask transpose), top-k candidates
 // Development history and the measurements behind these choices: profiles/r1_k3_batched_notes.md.
+//
+// Round 2: fp16 + fp8 operand split (default; -DVQ_BATCH_BF16X3 keeps the three-bf16-MMA arithmetic above).
+//     x' = x * bx * 2^6,  t' = t * bt * 2^6          bx (per store and stream), bt (per pass and stream): powers of two with
+//                                                    max |x| bx <= 128, max |t| bt <= 128
+//     x1 = fp16(x'), rx = x' - x1 (exact, |rx| <= 2^-11 |x'| <= 4);      t1, rt likewise
+//     x*t * (bx bt 2^12) ~= x1*t1  +  e4m3(rx 2^6) * e4m3(t bt)  +  e4m3(x bx) * e4m3(rt 2^6)
+// i.e. ONE kind::f16 MMA (K = 16) plus ONE kind::f8f6f4 MMA over a doubled K (32 e4m3 per 16 dims: [rx 2^6 | x bx] against
+// [t bt | rt 2^6]) per 16 dims: two thirds of the tensor-pipe cycles of the bf16x3 split.  All three products carry the same
+// power of two, so they share one accumulator and the epilogue multiplies the stream's sum by 1 / (4096 bx bt) (exact).
+// The residual operand tiles have the byte layout of the old x2 / t2 tiles (64 B per row and K block, 64B swizzle, +32 B per
+// K step), and the instruction descriptor is numerically the same for both kinds (format code 0 = F16 / E4M3).
+// CPU model of the arithmetic (tests/probes/k3_split_schemes.py): score error max 2.2e-6, rms 4.3e-7 (bf16x3: 8.3e-7 / 1.8e-7).
 #pragma once
 
 namespace bf {
@@ -64,6 +76,13 @@ struct Ring {
 // shared-memory descriptor high word: SBO = 512 B (8 rows of 64 B), descriptor version 1, SWIZZLE_64B
 constexpr uint32_t DESC_HI64 = (512u >> 4) | (1u << 14) | (4u << 29);
 
+template <bool kAcc>
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
+    asm volatile(
+        "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %4, 0;\nmov.b64 da, {%1, %5};\nmov.b64 db, {%2, %5};\n"
+        "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], da, db, %3, p;\n}" ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(idesc),
+        "n"(kAcc ? 1 : 0), "r"(DESC_HI64) : "memory");
+}
 template <bool kAcc>
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t idesc) {
     asm volatile(
@@ -114,6 +133,41 @@ __device__ __forceinline__ void split8(const float4 &u, const float4 &v, uint4 &
     VQ_SPLIT2(v.x, v.y, p.z, q.z)
     VQ_SPLIT2(v.z, v.w, p.w, q.w)
 #undef VQ_SPLIT2
+}
+
+// fp16 + fp8 split of 8 scaled floats (x' = x * sx, sx = bx * 2^6): p = 8 fp16 leading parts (16 B), rq = 8 e4m3 of the
+// residuals (x' - x1) * 2^6 (8 B), xq = 8 e4m3 of x * bx = x' * 2^-6 (8 B).  Element order inside each word: lower dims in
+// the lower bits (little endian), like the bf16 split above.
+__device__ __forceinline__ uint32_t pack_f16x2(float hi, float lo) {
+    uint32_t d;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+__device__ __forceinline__ uint32_t pack_e4m3x4(float f0, float f1, float f2, float f3) {
+    uint16_t lo, hi;
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(lo) : "f"(f1), "f"(f0));
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(hi) : "f"(f3), "f"(f2));
+    return (uint32_t)lo | ((uint32_t)hi << 16);
+}
+__device__ __forceinline__ void split8_f16f8(const float4 &u, const float4 &v, const float sx, uint4 &p, uint2 &rq, uint2 &xq) {
+    const float f[8] = {u.x * sx, u.y * sx, u.z * sx, u.w * sx, v.x * sx, v.y * sx, v.z * sx, v.w * sx};
+    float r[8];
+    uint32_t pw[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        pw[i] = pack_f16x2(f[2 * i + 1], f[2 * i]);
+        float h0, h1;
+        asm("{\n.reg .b16 lo, hi;\nmov.b32 {lo, hi}, %2;\ncvt.f32.f16 %0, lo;\ncvt.f32.f16 %1, hi;\n}" : "=f"(h0), "=f"(h1) : "r"(pw[i]));
+        r[2 * i] = (f[2 * i] - h0) * 64.0f;
+        r[2 * i + 1] = (f[2 * i + 1] - h1) * 64.0f;
+    }
+    p = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+    rq = make_uint2(pack_e4m3x4(r[0], r[1], r[2], r[3]), pack_e4m3x4(r[4], r[5], r[6], r[7]));
+    constexpr float k = 1.0f / 64.0f;
+    xq = make_uint2(pack_e4m3x4(f[0] * k, f[1] * k, f[2] * k, f[3] * k), pack_e4m3x4(f[4] * k, f[5] * k, f[6] * k, f[7] * k));
+}
+__device__ __forceinline__ void sts64(uint32_t addr, const uint2 &v) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
 }
 
 __device__ __forceinline__ float4 lds128(uint32_t addr) {
@@ -197,6 +251,39 @@ __global__ void split_targets_bf16(const float *__restrict__ t, unsigned short *
     t2[i] = (unsigned short)(q & 0xFFFFu);
 }
 
+// targets fp32 [rows][K] (K = S * stream_len) -> t1 = fp16(t * st) and, per 16 dims, 32 bytes of t2:
+// [e4m3(t * bt) x 16 | e4m3((t * st - t1) * 2^6) x 16]   (st = bt * 2^6, per stream); one thread per 16 dims.
+__global__ void split_targets_f16f8(const float *__restrict__ t, unsigned short *t1, unsigned char *t2, long long n16, int stream_len,
+                                    int n_streams, float st0, float st1, float st2, float st3) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n16) return;
+    const long long e0 = g * 16;
+    const int s = (int)((e0 / stream_len) % n_streams);
+    const float st = s == 0 ? st0 : (s == 1 ? st1 : (s == 2 ? st2 : st3));
+    uint32_t tq[4], rq[4];
+    for (int i = 0; i < 4; ++i) {
+        float f[4], r[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) f[j] = t[e0 + 4 * i + j] * st;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const uint32_t pw = pack_f16x2(f[2 * j + 1], f[2 * j]);
+            float h0, h1;
+            asm("{\n.reg .b16 lo, hi;\nmov.b32 {lo, hi}, %2;\ncvt.f32.f16 %0, lo;\ncvt.f32.f16 %1, hi;\n}" : "=f"(h0), "=f"(h1) : "r"(pw));
+            t1[e0 + 4 * i + 2 * j] = (unsigned short)(pw & 0xFFFFu);
+            t1[e0 + 4 * i + 2 * j + 1] = (unsigned short)(pw >> 16);
+            r[2 * j] = (f[2 * j] - h0) * 64.0f;
+            r[2 * j + 1] = (f[2 * j + 1] - h1) * 64.0f;
+        }
+        constexpr float k = 1.0f / 64.0f;
+        tq[i] = pack_e4m3x4(f[0] * k, f[1] * k, f[2] * k, f[3] * k);
+        rq[i] = pack_e4m3x4(r[0], r[1], r[2], r[3]);
+    }
+    uint4 *out = reinterpret_cast<uint4 *>(t2 + g * 32);
+    out[0] = make_uint4(tq[0], tq[1], tq[2], tq[3]);
+    out[1] = make_uint4(rq[0], rq[1], rq[2], rq[3]);
+}
+
 // Converter role: fp32 clip tile -> x1, x2 bf16 tiles, for a group of 32 * ITEMS ... threads.
 // Work item = (row r, 8 consecutive dims c8): two 16 B chunks of the fp32 row -> one 16 B chunk of x1 and of x2.
 // 8 consecutive threads take rows (2p, 2p+1) x c8 = 0..3, which makes every quarter-warp phase of the 128-bit loads
@@ -207,7 +294,8 @@ __global__ void split_targets_bf16(const float *__restrict__ t, unsigned short *
 template <int ITEMS, int QT>
 __device__ __forceinline__ void convert_blocks(const int t, const int lane, const int n_it, const uint32_t smem_base,
                                                const uint32_t bar_afull, const uint32_t bar_aempty, const uint32_t bar_xfull,
-                                               const uint32_t bar_xempty, long long &c_wait, long long &c_wait2) {
+                                               const uint32_t bar_xempty, long long &c_wait, long long &c_wait2,
+                                               const BatchArgs &a) {
     constexpr int ROWS_PER_PASS = BM / ITEMS;                        // 32 or 64
     constexpr int NA = Ring<QT>::NA, NXR = Ring<QT>::NXR;
     constexpr uint32_t RING_X = Ring<QT>::RING_X;
@@ -216,6 +304,14 @@ __device__ __forceinline__ void convert_blocks(const int t, const int lane, cons
     const uint32_t src_off0 = (uint32_t)rsub * 128u + (uint32_t)(((2 * c8) ^ (rsub & 7)) * 16);
     const uint32_t src_off1 = (uint32_t)rsub * 128u + (uint32_t)(((2 * c8 + 1) ^ (rsub & 7)) * 16);
     const uint32_t dst_off = (uint32_t)rsub * 64u + (uint32_t)((c8 ^ ((rsub >> 1) & 3)) * 16);
+#ifndef VQ_BATCH_BF16X3
+    // residual tile: per 16 dims [rx x 16 | x x 16] = chunks (2g, 2g + 1) of the 64 B row, g = c8 >> 1; this item's 8 dims
+    // fill bytes 8 (c8 & 1) .. +8 of both chunks
+    const uint32_t swz = (uint32_t)((rsub >> 1) & 3);
+    const uint32_t dst_r = (uint32_t)rsub * 64u + ((((uint32_t)(c8 >> 1) * 2u) ^ swz) * 16u) + (uint32_t)(c8 & 1) * 8u;
+    const uint32_t dst_x = (uint32_t)rsub * 64u + ((((uint32_t)(c8 >> 1) * 2u + 1u) ^ swz) * 16u) + (uint32_t)(c8 & 1) * 8u;
+    const int kb_total_c = a.kb_per_stream * a.n_streams;
+#endif
     float4 u[ITEMS], v[ITEMS];
     auto load_block = [&](int it) {
         const int sa = it % NA;
@@ -232,9 +328,18 @@ __device__ __forceinline__ void convert_blocks(const int t, const int lane, cons
     if (n_it > 0) load_block(0);
     for (int it = 0; it < n_it; ++it) {
         const int sa = it % NA, sx = it % NXR;
+#ifdef VQ_BATCH_BF16X3
         uint4 p[ITEMS], q[ITEMS];
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) split8(u[j], v[j], p[j], q[j]);
+#else
+        uint4 p[ITEMS];
+        uint2 rq[ITEMS], xq[ITEMS];
+        const int stream_i = (it % kb_total_c) / a.kb_per_stream;
+        const float scale = stream_i == 0 ? a.sx[0] : (stream_i == 1 ? a.sx[1] : (stream_i == 2 ? a.sx[2] : a.sx[3]));
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) split8_f16f8(u[j], v[j], scale, p[j], rq[j], xq[j]);
+#endif
         // the fp32 stage is free as soon as its values sit in registers (the loads above have returned: split8 used them)
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_aempty + 8 * sa);
@@ -243,11 +348,21 @@ __device__ __forceinline__ void convert_blocks(const int t, const int lane, cons
         mbar_wait(bar_xempty + 8 * sx, ((it / NXR) & 1) ^ 1);
         c_wait2 += VQ_CLOCK() - t1;
         const uint32_t dst = smem_base + RING_X + (uint32_t)sx * 2 * X_BYTES + dst_off;
+#ifdef VQ_BATCH_BF16X3
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) {
             sts128(dst + (uint32_t)(j * ROWS_PER_PASS * 64), p[j]);
             sts128(dst + X_BYTES + (uint32_t)(j * ROWS_PER_PASS * 64), q[j]);
         }
+#else
+        const uint32_t res = smem_base + RING_X + (uint32_t)sx * 2 * X_BYTES + X_BYTES;
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {        // ROWS_PER_PASS is a multiple of 8: the swizzle term of a row is the same in every pass
+            sts128(dst + (uint32_t)(j * ROWS_PER_PASS * 64), p[j]);
+            sts64(res + dst_r + (uint32_t)(j * ROWS_PER_PASS * 64), rq[j]);
+            sts64(res + dst_x + (uint32_t)(j * ROWS_PER_PASS * 64), xq[j]);
+        }
+#endif
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (UMMA)
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_xfull + 8 * sx);
@@ -357,8 +472,13 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             // ------------------------------------------------------------------ MMA issuer
             uint32_t elected;
             asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(elected));
+#ifdef VQ_BATCH_BF16X3
             // instruction descriptor: D = f32, A = B = bf16, both K-major, N = n_mma, M = 128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+#else
+            // instruction descriptor: D = f32, A / B format code 0 (= F16 for kind::f16, = E4M3 for kind::f8f6f4), both K-major
+            const uint32_t idesc = (1u << 4) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+#endif
             int it = 0, gcount = 0;
             long long w_acc = 0, w_data = 0, w_conv = 0;
             const long long m_t0 = VQ_CLOCK();
@@ -391,6 +511,7 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                             const uint32_t x1 = desc_lo(xbase), x2 = desc_lo(xbase + X_BYTES), t1d = desc_lo(tbase), t2d = desc_lo(tbase + T_BYTES);
                             if (group_first) umma_bf16<false>(d, x1, t1d, idesc);
                             else umma_bf16<true>(d, x1, t1d, idesc);
+#ifdef VQ_BATCH_BF16X3
                             umma_bf16<true>(d, x2, t1d, idesc);
                             umma_bf16<true>(d, x1, t2d, idesc);
 #pragma unroll
@@ -399,6 +520,14 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                                 umma_bf16<true>(d, x2 + 2 * k, t1d + 2 * k, idesc);
                                 umma_bf16<true>(d, x1 + 2 * k, t2d + 2 * k, idesc);
                             }
+#else
+                            umma_f8<true>(d, x2, t2d, idesc);                    // [rx | x] . [t | rt] over 32 e4m3 = both residual terms
+#pragma unroll
+                            for (int k = 1; k < BK / UK; ++k) {                  // +32 B per K step inside the 64 B row (both kinds)
+                                umma_bf16<true>(d, x1 + 2 * k, t1d + 2 * k, idesc);
+                                umma_f8<true>(d, x2 + 2 * k, t2d + 2 * k, idesc);
+                            }
+#endif
                             umma_commit(bar_xempty + 8 * sx);                     // both operand stages are reusable once these MMAs retire
                             umma_commit(bar_tempty + 8 * stg);
                             if (group_last) umma_commit(bar_part_full + 8 * (gcount % NPART));
@@ -421,8 +550,8 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         // ---------------------------------------------------------------------- converter (warps 4-7, one per SM sub-partition)
         long long c_wait = 0, c_wait2 = 0;
         const int t = threadIdx.x - 128;                             // 0..127
-        if (conv_warps == 2 * CONV_WARPS) convert_blocks<2, QT>(t, lane, n_it, smem_base, bar_afull, bar_aempty, bar_xfull, bar_xempty, c_wait, c_wait2);
-        else convert_blocks<4, QT>(t, lane, n_it, smem_base, bar_afull, bar_aempty, bar_xfull, bar_xempty, c_wait, c_wait2);
+        if (conv_warps == 2 * CONV_WARPS) convert_blocks<2, QT>(t, lane, n_it, smem_base, bar_afull, bar_aempty, bar_xfull, bar_xempty, c_wait, c_wait2, a);
+        else convert_blocks<4, QT>(t, lane, n_it, smem_base, bar_afull, bar_aempty, bar_xfull, bar_xempty, c_wait, c_wait2, a);
         if (prof && t == 0) { prof[blockIdx.x * 16 + 7] = c_wait; prof[blockIdx.x * 16 + 4] = c_wait2; }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
@@ -430,7 +559,7 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         if (warp >= 12 && conv_warps == 2 * CONV_WARPS) {
             // no queries in the upper half: these four warps are converter threads 128..255
             long long cw = 0, cw2 = 0;
-            convert_blocks<2, QT>(threadIdx.x - 384 + 128, lane, n_it, smem_base, bar_afull, bar_aempty, bar_xfull, bar_xempty, cw, cw2);
+            convert_blocks<2, QT>(threadIdx.x - 384 + 128, lane, n_it, smem_base, bar_afull, bar_aempty, bar_xfull, bar_xempty, cw, cw2, a);
         }
         const int ew = warp - 8;                  // 0..7
         const int quarter = warp & 3;             // TMEM lanes 32*quarter .. +31 (hardware rule: warp id % 4)
@@ -482,7 +611,12 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 // this stream's contribution (w (1 - sim))^2; earlier streams' terms come back from the park
                 {
                     const long long t1 = VQ_CLOCK();
+#ifdef VQ_BATCH_BF16X3
                     const float ic = (inv_counts && row_ok) ? inv_counts[row * a.n_streams + st] : a.inv_splits;
+#else
+                    const float ds = st == 0 ? a.descale[0] : (st == 1 ? a.descale[1] : (st == 2 ? a.descale[2] : a.descale[3]));
+                    const float ic = ((inv_counts && row_ok) ? inv_counts[row * a.n_streams + st] : a.inv_splits) * ds;   // ds: a power of two
+#endif
                     const float w = st == 0 ? a.w[0] : (st == 1 ? a.w[1] : (st == 2 ? a.w[2] : a.w[3]));   // no dynamic indexing: keeps `a` in the constant bank
                     const bool first = st == 0, last = st + 1 == a.n_streams;
                     if (first) {

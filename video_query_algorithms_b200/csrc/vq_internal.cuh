@@ -108,6 +108,8 @@ struct vq_store {
     char *lab_host = nullptr;
     size_t lab_host_cap = 0;
     // scratch of the batched path (vq_batch.cu), allocated on its first call and kept: a batched scan allocates nothing
+    float batch_absmax[VQ_MAX_STREAMS] = {0.f, 0.f, 0.f, 0.f};   // max |x| per stream (operand scale of the batched path), valid flag below
+    bool batch_absmax_valid = false;                              // reset by every write to the rows
     void *batch_scratch = nullptr;
     void (*batch_scratch_free)(void *) = nullptr;
 };

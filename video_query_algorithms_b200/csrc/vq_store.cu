@@ -279,6 +279,7 @@ static int check_range(const vq_store *s, int64_t first, int64_t n, const char *
 extern "C" int vq_store_upload(vq_store *s, int64_t first_row, int64_t n_rows, const float *rows) {
     if (int r = check_range(s, first_row, n_rows, "vq_store_upload")) return r;
     VQ_REQUIRE(rows || n_rows == 0, "vq_store_upload: null rows");
+    s->batch_absmax_valid = false;
     VQ_CUDA(cudaSetDevice(s->device));
     // Chunked so that pageable sources are staged in bounded pieces; pinned sources go at PCIe rate.
     const size_t row_bytes = s->row_floats * sizeof(float);
@@ -299,6 +300,7 @@ extern "C" int vq_store_upload_async(vq_store *s, int64_t first_row, int64_t n_r
     if (int r = check_range(s, first_row, n_rows, "vq_store_upload_async")) return r;
     VQ_REQUIRE(rows_pinned || n_rows == 0, "vq_store_upload_async: null rows");
     if (n_rows == 0) return 0;
+    s->batch_absmax_valid = false;
     VQ_CUDA(cudaSetDevice(s->device));
     VQ_CUDA(cudaMemcpyAsync(s->rows + (size_t)first_row * s->row_floats, rows_pinned, (size_t)n_rows * s->row_floats * sizeof(float),
                             cudaMemcpyHostToDevice, s->stream));
@@ -414,6 +416,7 @@ __global__ void synth_fill_kernel(float4 *rows, const float *__restrict__ base, 
 
 extern "C" int vq_store_fill_synthetic(vq_store *s, uint64_t seed, const float *stream_means) {
     VQ_REQUIRE(s, "vq_store_fill_synthetic: null store");
+    s->batch_absmax_valid = false;
     static const float kDefaultMeans[VQ_MAX_STREAMS] = {2.5f, 0.9f, 1.7f, 1.3f};
     VQ_CUDA(cudaSetDevice(s->device));
     float means3[VQ_MAX_STREAMS];
