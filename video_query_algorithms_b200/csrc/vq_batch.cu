@@ -44,9 +44,12 @@ struct BatchArgs {
     // tie band: closed fp32 intervals holding exactly the floats s with |(double)s - th| < eps (0) and |(double)s - lo| < eps (1)
     float tie_lo0, tie_hi0, tie_lo1, tie_hi1;
     long long tie_cap;
+#ifdef VQ_BATCH_F16F8
     // fp16 + fp8 operand split (vq_batch_bf16.cuh): per stream, sx = bx * 2^6 scales the clip rows into fp16 range and
-    // descale = 1 / (4096 bx bt) undoes both operand scales on the stream's sum (powers of two: exact)
+    // descale = 1 / (4096 bx bt) undoes both operand scales on the stream's sum (powers of two: exact).
+    // (Only in that build: 32 more bytes of kernel parameters cost the default kernel 40 bytes of extra spills.)
     float sx[VQ_MAX_STREAMS], descale[VQ_MAX_STREAMS];
+#endif
 };
 
 #include "vq_batch_bf16.cuh"
@@ -277,7 +280,7 @@ int run_batch_bf16(vq_store *s, const float *targets, int n_queries, const vq_sc
     }
     memset(wd_host, 0, 256 * 16 * 2 * 8);
 #endif
-#ifndef VQ_BATCH_BF16X3
+#ifdef VQ_BATCH_F16F8
     // clip-row scale per stream: max |x| of the shard, taken once per content version (upload / append / fill reset it)
     if (!s->batch_absmax_valid && s->n_rows > 0) {
         VQ_CUDA(cudaMemsetAsync(bs->amax.p, 0, VQ_MAX_STREAMS * 4, st));
@@ -299,8 +302,10 @@ int run_batch_bf16(vq_store *s, const float *targets, int n_queries, const vq_sc
         if (nq < QN) VQ_CUDA(cudaMemsetAsync(d_t.p, 0, (size_t)QN * K * 4, st));
         memcpy(bs->pinned_t, targets + (size_t)q0 * K, (size_t)nq * K * 4);       // caller memory may be pageable
         VQ_CUDA(cudaMemcpyAsync(d_t.p, bs->pinned_t, (size_t)nq * K * 4, cudaMemcpyHostToDevice, st));
+#ifdef VQ_BATCH_F16F8
         float sx[VQ_MAX_STREAMS] = {1.f, 1.f, 1.f, 1.f}, stq[VQ_MAX_STREAMS] = {1.f, 1.f, 1.f, 1.f}, descale[VQ_MAX_STREAMS] = {1.f, 1.f, 1.f, 1.f};
-#ifdef VQ_BATCH_BF16X3
+#endif
+#ifndef VQ_BATCH_F16F8
         bf::split_targets_bf16<<<(unsigned)(((size_t)QN * K + 255) / 256), 256, 0, st>>>(
             d_t.as<float>(), d_t1.as<unsigned short>(), d_t2.as<unsigned short>(), (long long)QN * K);
 #else
@@ -349,7 +354,9 @@ int run_batch_bf16(vq_store *s, const float *targets, int n_queries, const vq_sc
         a.n_streams = s->n_streams;
         a.n_rows_total = s->n_rows;
         a.cand_cap = cap;
+#ifdef VQ_BATCH_F16F8
         for (int i = 0; i < VQ_MAX_STREAMS; ++i) { a.sx[i] = sx[i]; a.descale[i] = descale[i]; }
+#endif
         tie_interval(p->threshold, want_ties ? p->eps : 0.0, &a.tie_lo0, &a.tie_hi0);
         tie_interval(p->lower_limit, want_ties ? p->eps : 0.0, &a.tie_lo1, &a.tie_hi1);
         a.tie_cap = kTieCap;

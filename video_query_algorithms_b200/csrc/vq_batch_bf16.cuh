@@ -29,7 +29,7 @@
 //     warps 8-15   epilogue: drains, running sums, scores, per-query counts (bit-mask transpose), top-k candidates
 // Development history and the measurements behind these choices: profiles/r1_k3_batched_notes.md.
 //
-// Round 2: fp16 + fp8 operand split (default; -DVQ_BATCH_BF16X3 keeps the three-bf16-MMA arithmetic above).
+// Round 2 experiment, NOT the default (build with -DVQ_BATCH_F16F8): fp16 + fp8 operand split.
 //     x' = x * bx * 2^6,  t' = t * bt * 2^6          bx (per store and stream), bt (per pass and stream): powers of two with
 //                                                    max |x| bx <= 128, max |t| bt <= 128
 //     x1 = fp16(x'), rx = x' - x1 (exact, |rx| <= 2^-11 |x'| <= 4);      t1, rt likewise
@@ -40,6 +40,10 @@
 // The residual operand tiles have the byte layout of the old x2 / t2 tiles (64 B per row and K block, 64B swizzle, +32 B per
 // K step), and the instruction descriptor is numerically the same for both kinds (format code 0 = F16 / E4M3).
 // CPU model of the arithmetic (tests/probes/k3_split_schemes.py): score error max 2.2e-6, rms 4.3e-7 (bf16x3: 8.3e-7 / 1.8e-7).
+// Measured on B200 (profiles/r2_k3_f16f8_notes.md): parity-green on VQSYN-1 (mean -5.1e-7, max 1.5e-6 at 1M x 256) but NOT faster
+// — 3.52 ms vs 3.50 ms at 1M x 256, 34.3 ms (1537 MHz) vs 33.0 ms (1380 MHz) at 10M x 256: the converter warps now execute 48
+// F2FP + 32 HADD2.F32 per thread and K block instead of 32 F2FP (the conversion pipe becomes the limiter as the tensor
+// pipe stops being one), and on uniform random rows the error reaches 1.3e-5.  Kept for the record; bf16x3 stays.
 #pragma once
 
 namespace bf {
@@ -284,6 +288,11 @@ __global__ void split_targets_f16f8(const float *__restrict__ t, unsigned short 
     out[1] = make_uint4(rq[0], rq[1], rq[2], rq[3]);
 }
 
+struct ConvScale {                      // what the converter needs of BatchArgs, by value (a reference would force a stack copy of the parameters)
+    float sx0, sx1, sx2, sx3;
+    int kbps, n_streams;
+};
+
 // Converter role: fp32 clip tile -> x1, x2 bf16 tiles, for a group of 32 * ITEMS ... threads.
 // Work item = (row r, 8 consecutive dims c8): two 16 B chunks of the fp32 row -> one 16 B chunk of x1 and of x2.
 // 8 consecutive threads take rows (2p, 2p+1) x c8 = 0..3, which makes every quarter-warp phase of the 128-bit loads
@@ -295,7 +304,7 @@ template <int ITEMS, int QT>
 __device__ __forceinline__ void convert_blocks(const int t, const int lane, const int n_it, const uint32_t smem_base,
                                                const uint32_t bar_afull, const uint32_t bar_aempty, const uint32_t bar_xfull,
                                                const uint32_t bar_xempty, long long &c_wait, long long &c_wait2,
-                                               const BatchArgs &a) {
+                                               const ConvScale cs) {
     constexpr int ROWS_PER_PASS = BM / ITEMS;                        // 32 or 64
     constexpr int NA = Ring<QT>::NA, NXR = Ring<QT>::NXR;
     constexpr uint32_t RING_X = Ring<QT>::RING_X;
@@ -304,13 +313,13 @@ __device__ __forceinline__ void convert_blocks(const int t, const int lane, cons
     const uint32_t src_off0 = (uint32_t)rsub * 128u + (uint32_t)(((2 * c8) ^ (rsub & 7)) * 16);
     const uint32_t src_off1 = (uint32_t)rsub * 128u + (uint32_t)(((2 * c8 + 1) ^ (rsub & 7)) * 16);
     const uint32_t dst_off = (uint32_t)rsub * 64u + (uint32_t)((c8 ^ ((rsub >> 1) & 3)) * 16);
-#ifndef VQ_BATCH_BF16X3
+#ifdef VQ_BATCH_F16F8
     // residual tile: per 16 dims [rx x 16 | x x 16] = chunks (2g, 2g + 1) of the 64 B row, g = c8 >> 1; this item's 8 dims
     // fill bytes 8 (c8 & 1) .. +8 of both chunks
     const uint32_t swz = (uint32_t)((rsub >> 1) & 3);
     const uint32_t dst_r = (uint32_t)rsub * 64u + ((((uint32_t)(c8 >> 1) * 2u) ^ swz) * 16u) + (uint32_t)(c8 & 1) * 8u;
     const uint32_t dst_x = (uint32_t)rsub * 64u + ((((uint32_t)(c8 >> 1) * 2u + 1u) ^ swz) * 16u) + (uint32_t)(c8 & 1) * 8u;
-    const int kb_total_c = a.kb_per_stream * a.n_streams;
+    const int kb_total_c = cs.kbps * cs.n_streams;
 #endif
     float4 u[ITEMS], v[ITEMS];
     auto load_block = [&](int it) {
@@ -328,15 +337,15 @@ __device__ __forceinline__ void convert_blocks(const int t, const int lane, cons
     if (n_it > 0) load_block(0);
     for (int it = 0; it < n_it; ++it) {
         const int sa = it % NA, sx = it % NXR;
-#ifdef VQ_BATCH_BF16X3
+#ifndef VQ_BATCH_F16F8
         uint4 p[ITEMS], q[ITEMS];
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) split8(u[j], v[j], p[j], q[j]);
 #else
         uint4 p[ITEMS];
         uint2 rq[ITEMS], xq[ITEMS];
-        const int stream_i = (it % kb_total_c) / a.kb_per_stream;
-        const float scale = stream_i == 0 ? a.sx[0] : (stream_i == 1 ? a.sx[1] : (stream_i == 2 ? a.sx[2] : a.sx[3]));
+        const int stream_i = (it % kb_total_c) / cs.kbps;
+        const float scale = stream_i == 0 ? cs.sx0 : (stream_i == 1 ? cs.sx1 : (stream_i == 2 ? cs.sx2 : cs.sx3));
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) split8_f16f8(u[j], v[j], scale, p[j], rq[j], xq[j]);
 #endif
@@ -348,7 +357,7 @@ __device__ __forceinline__ void convert_blocks(const int t, const int lane, cons
         mbar_wait(bar_xempty + 8 * sx, ((it / NXR) & 1) ^ 1);
         c_wait2 += VQ_CLOCK() - t1;
         const uint32_t dst = smem_base + RING_X + (uint32_t)sx * 2 * X_BYTES + dst_off;
-#ifdef VQ_BATCH_BF16X3
+#ifndef VQ_BATCH_F16F8
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) {
             sts128(dst + (uint32_t)(j * ROWS_PER_PASS * 64), p[j]);
@@ -424,6 +433,11 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+#ifdef VQ_BATCH_F16F8
+    const ConvScale cs = {a.sx[0], a.sx[1], a.sx[2], a.sx[3], a.kb_per_stream, a.n_streams};
+#else
+    const ConvScale cs = {1.f, 1.f, 1.f, 1.f, 0, 0};
+#endif
     const int kbps = a.kb_per_stream;
     const int kb_total = kbps * a.n_streams;
     const int n_mma = a.n_mma;                      // queries rounded up to 16: the N of every MMA
@@ -472,7 +486,7 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
             // ------------------------------------------------------------------ MMA issuer
             uint32_t elected;
             asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(elected));
-#ifdef VQ_BATCH_BF16X3
+#ifndef VQ_BATCH_F16F8
             // instruction descriptor: D = f32, A = B = bf16, both K-major, N = n_mma, M = 128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n_mma >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 #else
@@ -511,7 +525,7 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                             const uint32_t x1 = desc_lo(xbase), x2 = desc_lo(xbase + X_BYTES), t1d = desc_lo(tbase), t2d = desc_lo(tbase + T_BYTES);
                             if (group_first) umma_bf16<false>(d, x1, t1d, idesc);
                             else umma_bf16<true>(d, x1, t1d, idesc);
-#ifdef VQ_BATCH_BF16X3
+#ifndef VQ_BATCH_F16F8
                             umma_bf16<true>(d, x2, t1d, idesc);
                             umma_bf16<true>(d, x1, t2d, idesc);
 #pragma unroll
@@ -550,8 +564,8 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         // ---------------------------------------------------------------------- converter (warps 4-7, one per SM sub-partition)
         long long c_wait = 0, c_wait2 = 0;
         const int t = threadIdx.x - 128;                             // 0..127
-        if (conv_warps == 2 * CONV_WARPS) convert_blocks<2, QT>(t, lane, n_it, smem_base, bar_afull, bar_aempty, bar_xfull, bar_xempty, c_wait, c_wait2, a);
-        else convert_blocks<4, QT>(t, lane, n_it, smem_base, bar_afull, bar_aempty, bar_xfull, bar_xempty, c_wait, c_wait2, a);
+        if (conv_warps == 2 * CONV_WARPS) convert_blocks<2, QT>(t, lane, n_it, smem_base, bar_afull, bar_aempty, bar_xfull, bar_xempty, c_wait, c_wait2, cs);
+        else convert_blocks<4, QT>(t, lane, n_it, smem_base, bar_afull, bar_aempty, bar_xfull, bar_xempty, c_wait, c_wait2, cs);
         if (prof && t == 0) { prof[blockIdx.x * 16 + 7] = c_wait; prof[blockIdx.x * 16 + 4] = c_wait2; }
     } else {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 192;");
@@ -559,7 +573,7 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
         if (warp >= 12 && conv_warps == 2 * CONV_WARPS) {
             // no queries in the upper half: these four warps are converter threads 128..255
             long long cw = 0, cw2 = 0;
-            convert_blocks<2, QT>(threadIdx.x - 384 + 128, lane, n_it, smem_base, bar_afull, bar_aempty, bar_xfull, bar_xempty, cw, cw2, a);
+            convert_blocks<2, QT>(threadIdx.x - 384 + 128, lane, n_it, smem_base, bar_afull, bar_aempty, bar_xfull, bar_xempty, cw, cw2, cs);
         }
         const int ew = warp - 8;                  // 0..7
         const int quarter = warp & 3;             // TMEM lanes 32*quarter .. +31 (hardware rule: warp id % 4)
@@ -611,7 +625,7 @@ batch_scan_bf16(const __grid_constant__ CUtensorMap map_a, const __grid_constant
                 // this stream's contribution (w (1 - sim))^2; earlier streams' terms come back from the park
                 {
                     const long long t1 = VQ_CLOCK();
-#ifdef VQ_BATCH_BF16X3
+#ifndef VQ_BATCH_F16F8
                     const float ic = (inv_counts && row_ok) ? inv_counts[row * a.n_streams + st] : a.inv_splits;
 #else
                     const float ds = st == 0 ? a.descale[0] : (st == 1 ? a.descale[1] : (st == 2 ? a.descale[2] : a.descale[3]));
