@@ -442,7 +442,7 @@ class _ArrayStore:
     def row_of(self, c):
         return self._row[int(c)]
 
-    def scan(self, target, weights, threshold, lower_limit, eps, topk=0, want_sims=False, lists=True):
+    def scan(self, target, weights, threshold, lower_limit, eps, topk=0, want_sims=False, lists=True, packed=None):
         s = self._s
         self._l = {"matches": np.flatnonzero(s >= threshold), "near_misses": np.flatnonzero((s >= lower_limit) & (s < threshold)),
                    "ties": np.flatnonzero((np.abs(s - threshold) < eps) | (np.abs(s - lower_limit) < eps))}

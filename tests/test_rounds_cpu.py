@@ -76,7 +76,7 @@ def make_oracle_store_class():
             pass
 
         # ---- the scan and its results (conventions of vq_scan: fp32 scores, comparisons on (double)score)
-        def scan(self, target_features, weights, threshold, lower_limit, eps, topk=0, want_sims=False, lists=True):
+        def scan(self, target_features, weights, threshold, lower_limit, eps, topk=0, want_sims=False, lists=True, packed=None):
             T, have = self.pack_target(target_features, np.float32)
             present = np.ones((self.n_rows,) + self.row_shape[:2], bool) if self.present is None else self.present
             sims, _ = sc.similarities(self.X, T.astype(np.float64), present & have[None])

@@ -21,6 +21,13 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "vq_internal.cuh"
@@ -827,28 +834,124 @@ extern "C" int vq_scan_select(vq_store *s, const float *target, const vq_scan_pa
 }
 
 // The broker's arrangement (reference src/broker.py:62-92: ONE process, one job at a time): a search set sharded over the
-// GPUs of the box is scanned by one call from one thread — the target copy, K1, K2 and the publish kernel are enqueued on
-// every shard's own stream first, then each stream is waited for once.  The per-shard top-k lists (ranked, in the pinned
-// mirrors) are merged here into the search set's top-k; counts and the best near miss come back per shard because list
-// positions are per shard (the shards' lists, in shard order, ARE the search set's lists in database order).
+// GPUs of the box is scanned by ONE call.  Enqueueing a shard's work costs ~25 us of host time (a copy, four kernels, a
+// publish kernel, three events); done from one thread for eight shards, the last GPU would start 0.2 ms after the first.
+// The call therefore hands shards 1..n-1 to a small pool of library threads (created on first use, one per shard, spinning
+// for ~2 ms after a job so that a stream of queries finds them awake, then sleeping on a condition variable) and runs
+// shard 0 itself; every worker enqueues AND waits for its own shard.  The per-shard top-k lists (ranked, in the pinned
+// mirrors) are merged by the caller's thread; counts and the best near miss come back per shard because list positions
+// are per shard (the shards' lists, in shard order, ARE the search set's lists in database order).
+namespace {
+
+class ShardPool {
+public:
+    // runs fn(0..n-1): fn(0) on the calling thread, the rest on the pool; returns the first non-zero status and leaves its
+    // message in the caller's vq_last_error()
+    int run(int n, const std::function<int(int)> &fn) {
+        if (n <= 1) return n == 1 ? fn(0) : 0;
+        std::lock_guard<std::mutex> call(call_mutex_);              // one multi-shard call at a time (the contract anyway)
+        grow(n - 1);
+        fn_ = &fn;
+        n_jobs_ = n;
+        remaining_.store(n - 1, std::memory_order_relaxed);
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            gen_.fetch_add(1, std::memory_order_release);
+        }
+        cv_.notify_all();
+        int rc = fn(0);
+        while (remaining_.load(std::memory_order_acquire) != 0) cpu_relax();
+        for (int i = 1; i < n && rc == 0; ++i)
+            if (rc_[(size_t)i]) {
+                rc = rc_[(size_t)i];
+                vq::set_error("%s", err_[(size_t)i].c_str());
+            }
+        return rc;
+    }
+
+private:
+    static void cpu_relax() {
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#else
+        std::this_thread::yield();
+#endif
+    }
+    void grow(int workers) {
+        while ((int)threads_.size() < workers) {
+            const int id = (int)threads_.size() + 1;
+            rc_.resize((size_t)id + 1, 0);
+            err_.resize((size_t)id + 1);
+            const unsigned long long start = gen_.load(std::memory_order_acquire);   // the job of THIS run() is start + 1
+            threads_.emplace_back([this, id, start] { loop(id, start); });
+            threads_.back().detach();                                // they live as long as the process
+        }
+    }
+    void loop(int id, unsigned long long seen) {
+        for (;;) {
+            // spin ~2 ms for the next job, then sleep
+            const auto t0 = std::chrono::steady_clock::now();
+            while (gen_.load(std::memory_order_acquire) == seen) {
+                cpu_relax();
+                if (std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(2)) {
+                    std::unique_lock<std::mutex> lk(m_);
+                    cv_.wait(lk, [&] { return gen_.load(std::memory_order_acquire) != seen; });
+                }
+            }
+            seen = gen_.load(std::memory_order_acquire);
+            if (id < n_jobs_) {
+                rc_[(size_t)id] = (*fn_)(id);
+                if (rc_[(size_t)id]) err_[(size_t)id] = vq_last_error();
+                remaining_.fetch_sub(1, std::memory_order_release);
+            }
+        }
+    }
+    std::mutex call_mutex_, m_;
+    std::condition_variable cv_;
+    std::atomic<unsigned long long> gen_{0};
+    std::atomic<int> remaining_{0};
+    const std::function<int(int)> *fn_ = nullptr;
+    int n_jobs_ = 0;
+    std::vector<std::thread> threads_;
+    std::vector<int> rc_;
+    std::vector<std::string> err_;
+};
+
+ShardPool &shard_pool() {
+    static ShardPool *pool = new ShardPool();                        // never destroyed: its threads outlive static destruction
+    return *pool;
+}
+
+}  // namespace
+
 extern "C" int vq_scan_multi(vq_store *const *shards, int32_t n_shards, const float *target, const vq_scan_params *p,
                              int32_t lists, vq_scan_counts *counts_out, int64_t *near_best_out, int32_t topk_cap,
                              int64_t *topk_rows_out, float *topk_scores_out, int32_t *n_topk_out) {
     VQ_REQUIRE(shards && n_shards >= 1 && target && p && counts_out, "vq_scan_multi: null argument");
     for (int i = 0; i < n_shards; ++i) VQ_REQUIRE(shards[i], "vq_scan_multi: shard %d is null", i);
-    // phase 1: everything but the two long lists — scan, selection, counts / top-k / tie band / best near miss published
-    for (int i = 0; i < n_shards; ++i)
-        if (int r = scan_host_begin(shards[i], target, p, 0, "vq_scan_multi")) {
-            for (int j = 0; j < i; ++j) {                    // leave no stream busy behind an error
-                cudaSetDevice(shards[j]->device);
-                cudaStreamSynchronize(shards[j]->stream);
-            }
-            return r;
-        }
+    // phase 1, all shards in parallel: everything but the two long lists — scan, selection, counts / top-k / tie band /
+    // best near miss published — enqueued and waited for per shard
+    const bool serial = getenv("VQ_SCAN_MULTI_SERIAL") != nullptr;       // development: everything from the calling thread
+    std::function<int(int)> phase1 = [&](int i) -> int {
+        if (int r = scan_host_begin(shards[i], target, p, 0, "vq_scan_multi")) return r;
+        return scan_host_finish(shards[i], &counts_out[i], 0);
+    };
     int rc = 0;
-    for (int i = 0; i < n_shards; ++i)
-        if (int r = scan_host_finish(shards[i], &counts_out[i], 0)) rc = rc ? rc : r;
-    if (rc) return rc;
+    if (serial) {
+        for (int i = 0; i < n_shards; ++i)
+            if (int r = scan_host_begin(shards[i], target, p, 0, "vq_scan_multi")) rc = rc ? rc : r;
+        for (int i = 0; i < n_shards && rc == 0; ++i)
+            if (int r = scan_host_finish(shards[i], &counts_out[i], 0)) rc = r;
+    } else {
+        rc = shard_pool().run(n_shards, phase1);
+    }
+    if (rc) {
+        for (int j = 0; j < n_shards; ++j) {                 // leave no stream busy behind an error
+            cudaSetDevice(shards[j]->device);
+            cudaStreamSynchronize(shards[j]->stream);
+        }
+        return rc;
+    }
     vq_store *s0 = shards[0];
     s0->group_n[0] = s0->group_n[1] = -1;
     if (lists) {
@@ -867,24 +970,29 @@ extern "C" int vq_scan_multi(vq_store *const *shards, int32_t n_shards, const fl
                 s0->n_rows = keep_rows;
                 if (r) return r;
             }
-        int64_t off[2] = {0, 0};
-        for (int i = 0; i < n_shards; ++i) {
+        std::vector<int64_t> off((size_t)n_shards * 2, 0);
+        for (int i = 1; i < n_shards; ++i) {
+            off[(size_t)i * 2] = off[(size_t)(i - 1) * 2] + shards[i - 1]->counts_host[0];
+            off[(size_t)i * 2 + 1] = off[(size_t)(i - 1) * 2 + 1] + shards[i - 1]->counts_host[1];
+        }
+        std::function<int(int)> phase2 = [&](int i) -> int {
             vq_store *s = shards[i];
             const int64_t nm = s->counts_host[0], nn = s->counts_host[1];
-            if (nm + nn > 0) {
-                VQ_CUDA(cudaSetDevice(s->device));
-                publish_lists_at<<<s->sm_count, 256, 0, s->stream>>>(
-                    s->list_rows[0], s->list_scores[0], nm, s->list_rows[1], s->list_scores[1], nn, s->first_global_row,
-                    (long long *)s0->h_rows[0] + off[0], s0->h_scores[0] + off[0], (long long *)s0->h_rows[1] + off[1],
-                    s0->h_scores[1] + off[1]);
-                VQ_CUDA(cudaGetLastError());
-            }
-            off[0] += nm;
-            off[1] += nn;
-        }
-        for (int i = 0; i < n_shards; ++i) {
-            VQ_CUDA(cudaSetDevice(shards[i]->device));
-            VQ_CUDA(cudaStreamSynchronize(shards[i]->stream));
+            if (nm + nn == 0) return 0;
+            VQ_CUDA(cudaSetDevice(s->device));
+            publish_lists_at<<<s->sm_count, 256, 0, s->stream>>>(
+                s->list_rows[0], s->list_scores[0], nm, s->list_rows[1], s->list_scores[1], nn, s->first_global_row,
+                (long long *)s0->h_rows[0] + off[(size_t)i * 2], s0->h_scores[0] + off[(size_t)i * 2],
+                (long long *)s0->h_rows[1] + off[(size_t)i * 2 + 1], s0->h_scores[1] + off[(size_t)i * 2 + 1]);
+            VQ_CUDA(cudaGetLastError());
+            VQ_CUDA(cudaStreamSynchronize(s->stream));
+            return 0;
+        };
+        if (serial) {
+            for (int i = 0; i < n_shards; ++i)
+                if (int r = phase2(i)) return r;
+        } else if (int r = shard_pool().run(n_shards, phase2)) {
+            return r;
         }
         s0->group_n[0] = tot[0];
         s0->group_n[1] = tot[1];

@@ -300,7 +300,8 @@ class Ticket:
         """Bind target and store; similarities materialise on first read (ticket.py:120-163)."""
         self._hp = hyperparameters
         st = self._get_candidate_features(self.target.splits, hyperparameters)
-        _, self._target_have = st.pack_target(self.target.target_features)
+        T, self._target_have = st.pack_target(self.target.target_features, np.float32)
+        self._packed_target = (np.ascontiguousarray(T), self._target_have)     # the job's target does not change from here on
         self._scanned = self._have_sims = False
         self.similarities = _SimilarityView(self)
 
@@ -319,7 +320,8 @@ class Ticket:
             self._hp.weights or self._hp.default_weights)
         want_sims = want_sims or self._have_sims
         self.last_scan = st.scan(self.target.target_features, [weights[s] for s in st.streams],
-                                 threshold, lower_limit, self._eps(), topk=self.topk, want_sims=want_sims, lists=lists)
+                                 threshold, lower_limit, self._eps(), topk=self.topk, want_sims=want_sims, lists=lists,
+                                 packed=getattr(self, "_packed_target", None))
         self._scanned, self._have_sims = True, want_sims
         if isinstance(self.scores, _ScoreView):
             self.scores._arr = None
