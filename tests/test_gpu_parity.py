@@ -812,7 +812,7 @@ def test_partial_update_target_on_the_gpu_matches_reference(vq):
     st.close()
 
 
-def _ragged_api(vq, rng, n_clips=400, splits=(1, 2, 3), dim=256):
+def _ragged_api(vq, rng, n_clips=400, splits=(1, 2, 3), dim=256, ref_split_order=None):
     """A fake API whose search set is ragged: every clip has split 1 of both streams... except some that lack it in the
     first stream (they must move behind the others, ticket.py:146-160), and many lack other slots."""
     from fake_api import FakeAPI
@@ -834,19 +834,25 @@ def _ragged_api(vq, rng, n_clips=400, splits=(1, 2, 3), dim=256):
         si, pi = divmod(rest, len(splits))
         if present[c, si, pi]:
             api.add_feature(cids[c], STREAMS[si], splits[pi], X[c, si, pi].tolist())
+    # the order the API lists the reference clip's own records in (= the order a new round's target walks the splits in)
+    rank = {p: i for i, p in enumerate(ref_split_order or splits)}
+    api.features_by_clip[cids[7]].sort(key=lambda r: (STREAMS.index(r["dnn_stream_id"]), rank[r["dnn_stream_split"]]))
     ss = api.add_search_set("ragged", cids)
     qid = api.add_query("qr", vid, cids[7], ss, max_matches=16, dynamic_target_adjustment=True)
     return api, qid, cids, X, present
 
 
-def test_compute_matches_on_a_ragged_search_set_follows_the_oracle(vq, tmp_path, monkeypatch):
+@pytest.mark.parametrize("ref_split_order", [None, (2, 3, 1)], ids=["ascending", "target-walks-2-3-1"])
+def test_compute_matches_on_a_ragged_search_set_follows_the_oracle(vq, tmp_path, monkeypatch, ref_split_order):
     """A ragged search set (missing (clip, stream, split) slots, clips lacking the first split of the first stream, records
     in arbitrary order) through compute_matches on the GPU — new, revise and finalize rounds — against the float64 oracle
     on the same records: row order (the reference's dict order, ticket.py:146-160), per-clip split means, scores, weights,
-    the selected clips in order."""
+    the selected clips in order.  Second case: the API lists the reference clip's records as split 2, 3, 1, so the new
+    round's target walks the splits in that order and the reference's `scores` dict — which its seeded sampling draws
+    from — is NOT in the store's row order (Ticket._place)."""
     from fake_api import FakeRepository
     rng = np.random.default_rng(77)
-    api, qid, cids, X, present = _ragged_api(vq, rng)
+    api, qid, cids, X, present = _ragged_api(vq, rng, ref_split_order=ref_split_order)
     (tmp_path / "work").mkdir()
     monkeypatch.chdir(tmp_path / "work")
     vq.invalidate()
@@ -896,9 +902,23 @@ def test_compute_matches_on_a_ragged_search_set_follows_the_oracle(vq, tmp_path,
             assert np.abs(T - want_T).max() <= 1e-6 * np.abs(want_T).max()
             th, near = hp.threshold, hp.near_miss_default
             m64, nm64 = sc.classify(s64, th, near)
+            # the reference's dict for THIS target: walk the target's splits in the target's order, first stream first
+            walk = list(t.target.target_features[STREAMS[0]])
+            assert walk == list(ref_split_order or (1, 2, 3))
+            dict_order, seen = [], set()
+            for s_ in STREAMS:
+                for p in t.target.target_features[s_]:
+                    for r_ in rows:
+                        c = r_["video_clip_id"]
+                        if r_["dnn_stream_id"] == s_ and r_["dnn_stream_split"] == p and c not in seen:
+                            seen.add(c)
+                            dict_order.append(c)
+            assert list(t.scores) == dict_order and (ref_split_order is None) == (t._place is None)
             if not t.tie_band:
-                picked = random.sample(range(len(m64)), int(min(16 / 2, len(m64))))
-                assert list(t.matches)[:len(picked)] == [want_order[m64[j]] for j in picked]
+                in_m = set(int(want_order[j]) for j in m64)
+                m_dict = [c for c in dict_order if c in in_m]
+                picked = random.sample(range(len(m_dict)), int(min(16 / 2, len(m_dict))))
+                assert list(t.matches)[:len(picked)] == [m_dict[j] for j in picked]
     assert api.calls.count(("search-sets", "features")) == 1 + 3      # built once; the test itself read it three times
     vq.invalidate()
 

@@ -62,7 +62,10 @@ def draw_job(rng):
     return {"X": X, "splits": splits, "lacks": lacks, "ragged": ragged, "hp": hp, "ref_row": int(np.argmax(alpha)),
             "max_matches": int(rng.choice([6, 9, 12, 20])), "dyn": bool(rng.random() < 0.7),
             "label_quantile": float(rng.choice([0.3, 0.5, 0.7])), "seed": str(int(rng.integers(1, 10 ** 9))),
-            "unlabelled": float(rng.choice([0.0, 0.0, 0.3])), "ref_outside": bool(rng.random() < 0.15)}
+            "unlabelled": float(rng.choice([0.0, 0.0, 0.3])), "ref_outside": bool(rng.random() < 0.15),
+            # the order in which the API lists the reference clip's own records = the target's split order = the order in
+            # which the reference walks the splits while it fills its `scores` dict (ticket.py:146-160)
+            "ref_split_order": [int(p) for p in (rng.permutation(splits) if rng.random() < 0.5 else splits)]}
 
 
 def build_api(job, tag=""):
@@ -76,6 +79,8 @@ def build_api(job, tag=""):
             for c in range(n):
                 if (c, s_i, p) not in job["lacks"] or c == job["ref_row"]:
                     api.add_feature(ids[c], s, p, [float(x) for x in job["X"][c, s_i, p_i]])
+    rank = {p: i for i, p in enumerate(job["ref_split_order"])}
+    api.features_by_clip[ids[job["ref_row"]]].sort(key=lambda r: rank[r["dnn_stream_split"]])       # stable: streams keep their order
     ss = api.add_search_set("s", [c for i, c in enumerate(ids) if not (job["ref_outside"] and i == job["ref_row"])])
     qid = api.add_query("q" + tag, vid, ids[job["ref_row"]], ss, max_matches=job["max_matches"], dynamic_target_adjustment=job["dyn"])
     return api, qid
@@ -114,6 +119,8 @@ def test_reference_and_product_agree_on_random_jobs(reference, cpu_product, tmp_
             if i > 0:                                          # the user labels what the reference showed; same labels for both
                 shown = {m["video_clip"]: m["score"] for m in api_r.matches.values()
                          if m["query_result"] == api_r._latest_result(q_r)["id"]}
+                if not shown:                                  # the previous round selected nothing (state 5): no next round
+                    break
                 cut = float(np.quantile(list(shown.values()), job["label_quantile"])) + 1e-4
                 labels = {c: bool(v >= cut) for c, v in shown.items()}
                 for c in sorted(labels):                       # the user skips some clips: label None -> is_match decides

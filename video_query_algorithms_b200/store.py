@@ -68,13 +68,26 @@ class RecordIndex:
     call, no vector touched yet): clip ids in row order, the split numbers, the feature length, which (row, stream,
     split) slots are present and — per slot — the record that fills it."""
 
-    def __init__(self, order, splits, dim, n_streams, rec, row, si, pi):
+    def __init__(self, order, splits, dim, n_streams, rec, row, si, pi, first=None):
         self.order, self.splits, self.dim, self.n_streams = order, splits, int(dim), int(n_streams)
         self.n_rows = len(order)
         self.rec, self.row, self.si, self.pi = rec, row, si, pi            # one entry per filled slot, sorted by row
         self.row_floats = self.n_streams * len(splits) * self.dim
         self.present = np.zeros((self.n_rows, self.n_streams, len(splits)), bool)
         self.present[row, si, pi] = True
+        # position of each slot's FIRST record in the response (a dict keeps a key where it was first inserted, whatever
+        # overwrites its value later): what the reference's per-job dict order is made of (FeatureStore.dict_order)
+        self.first = rec if first is None else first
+
+    def slot_positions(self):
+        """int64 [n_rows, S, P]: response position of each slot's first record (-1: absent), or None when the order of
+        the rows is the same whatever split a job's target starts with — every slot present and every (stream, split)
+        listing the clips in row order — which is the case for everything load_db.py writes in one go."""
+        pos = np.full(self.present.shape, -1, np.int64)
+        pos[self.row, self.si, self.pi] = self.first
+        if self.present.all() and (self.n_rows < 2 or bool(np.all(pos[1:] > pos[:-1]))):
+            return None
+        return pos
 
     def fill(self, feature_rows, r0, r1, out, threads=0):
         """float32(feature vectors) of rows [r0, r1) into `out` (float32 [>= (r1 - r0) * row_floats], C-contiguous); slots
@@ -153,12 +166,16 @@ def index_feature_rows(feature_rows, streams, feature_name, held=None):
     pi = np.searchsorted(np.asarray(splits, np.int64), sp) if len(sp) else sp
     # one record per slot — the last one in response order — sorted by row
     slot = (row * len(streams) + si) * max(len(splits), 1) + pi
+    first = rec
     if len(slot):
-        _, last_rev = np.unique(slot[::-1], return_index=True)
-        keep = np.sort(len(slot) - 1 - last_rev)
-        o = keep[np.argsort(row[keep], kind="stable")]
-        rec, row, si, pi = rec[o], row[o], si[o], pi[o]
-    return RecordIndex(order, splits, dim, len(streams), rec, row, si, pi), feature_rows
+        uniq, first_idx = np.unique(slot, return_index=True)          # first record of each slot: its place in the reference's dicts
+        _, last_rev = np.unique(slot[::-1], return_index=True)       # last record of each slot: its value
+        keep = len(slot) - 1 - last_rev                               # (both in ascending slot order)
+        o = np.argsort(row[keep], kind="stable")
+        first = rec[first_idx][o]
+        keep = keep[o]
+        rec, row, si, pi = rec[keep], row[keep], si[keep], pi[keep]
+    return RecordIndex(order, splits, dim, len(streams), rec, row, si, pi, first), feature_rows
 
 
 def pack_feature_rows(feature_rows, streams, feature_name, held=None):
@@ -201,6 +218,7 @@ class FeatureStore:
         self._row_of = None
         self._row_memo = {}
         self.present = None          # bool [N, S, P] when some clip lacks some split, else None
+        self.slot_pos = None         # int64 [N, S, P] response positions when the dict order depends on the target (dict_order)
         if clip_ids is not None:
             self.set_clip_ids(clip_ids)
         self.last = None
@@ -375,7 +393,18 @@ class FeatureStore:
             pw = np.zeros((idx.n_rows,) + self.row_shape[:2], bool)
             Xw[:, :, at], pw[:, :, at] = X, present
             X, present = Xw, pw
+        old_pos, n_old = getattr(self, "slot_pos", None), self.n_rows
         self.append(X, clip_ids=idx.order, present=present)
+        new_pos = idx.slot_positions()
+        if old_pos is not None or new_pos is not None:
+            # appended clips come after everything held, in every (stream, split) listing
+            if old_pos is None:
+                old_pos = np.tile(np.arange(n_old, dtype=np.int64)[:, None, None], (1,) + self.row_shape[:2])
+            if new_pos is None:
+                new_pos = np.tile(np.arange(idx.n_rows, dtype=np.int64)[:, None, None], (1, len(self.streams), len(idx.splits)))
+            wide = np.full((idx.n_rows,) + self.row_shape[:2], -1, np.int64)
+            wide[:, :, [self.splits.index(p) for p in idx.splits]] = np.where(new_pos >= 0, new_pos + int(old_pos.max()) + 1, -1)
+            self.slot_pos = np.concatenate([old_pos, wide])
         return idx.n_rows
 
     def sync_feature_rows(self, feature_rows, feature_name):
@@ -420,6 +449,7 @@ class FeatureStore:
         st = cls(idx.n_rows, streams, idx.splits, idx.dim, devices=devices, clip_ids=idx.order)
         st._ingest(idx, feature_rows)
         st.set_present(idx.present)
+        st.slot_pos = idx.slot_positions()
         return st
 
     def _ingest(self, idx, feature_rows):
@@ -509,6 +539,34 @@ class FeatureStore:
                     T[si, pi] = np.asarray(v, dtype=np.float64)
                     have[si, pi] = True
         return T, have
+
+    def dict_order(self, target_features):
+        """Position of every row in the reference's `scores` dict for a job with this target, or None when that is the row
+        order itself.  The reference fills the dict while it walks the target's streams and, per stream, the target's splits
+        IN THE TARGET'S ORDER, listing each split's clips in response order (ticket.py:146-160): a clip enters at the first
+        such listing that has it.  The store's rows follow the ascending-split walk, which is what every bootstrapped target
+        and every reference clip whose records arrive in split order produce; on a ragged search set a reference clip whose
+        `video-clips/features` response lists, say, split 2 before split 1 seats the clips differently, and the seeded
+        sampling (ticket.py:333,341) walks THAT order."""
+        pos = getattr(self, "slot_pos", None)
+        if pos is None or not self.n_rows:
+            return None
+        n = self.n_rows
+        key_stream = np.full(n, len(self.streams), np.int64)
+        key_split = np.zeros(n, np.int64)
+        key_pos = np.arange(n, dtype=np.int64)
+        for si in reversed(range(len(self.streams))):
+            by_split = target_features.get(self.streams[si], {})
+            walk = [self.splits.index(p) for p in by_split if p in self.splits]          # the target's own split order
+            for j in reversed(range(len(walk))):
+                has = pos[:, si, walk[j]] >= 0
+                key_stream[has], key_split[has], key_pos[has] = si, j, pos[has, si, walk[j]]
+        order = np.lexsort((key_pos, key_split, key_stream))
+        if np.array_equal(order, np.arange(n)):
+            return None
+        place = np.empty(n, np.int64)
+        place[order] = np.arange(n)
+        return place
 
     def _sync_split_weights_for_target(self, have):
         """The reference averages over splits that BOTH the target and the clip have (ticket.py:146-160), so the per-row

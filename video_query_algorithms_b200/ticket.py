@@ -74,7 +74,7 @@ class _ScoreView(Mapping):
         return self._t.feature_store().has_clip(clip)
 
     def __iter__(self):
-        return (int(c) for c in self._t.feature_store().clip_ids)
+        return (int(c) for c in self._t._ids_in_dict_order())
 
     def __len__(self):
         return self._t.feature_store().n_rows
@@ -109,7 +109,7 @@ class _SimilarityView(Mapping):
         return out
 
     def __iter__(self):
-        return (int(c) for c in self._t.feature_store().clip_ids)
+        return (int(c) for c in self._t._ids_in_dict_order())
 
     def __len__(self):
         return self._t.feature_store().n_rows
@@ -302,6 +302,10 @@ class Ticket:
         st = self._get_candidate_features(self.target.splits, hyperparameters)
         T, self._target_have = st.pack_target(self.target.target_features, np.float32)
         self._packed_target = (np.ascontiguousarray(T), self._target_have)     # the job's target does not change from here on
+        # place of every row in the reference's `scores` dict when that is not the store's row order (a ragged search set
+        # and a target whose splits do not come in ascending order, FeatureStore.dict_order): the seeded sampling, the
+        # "first maximum" and the "last confirmed clip" of this job then walk that order
+        self._place = st.dict_order(self.target.target_features)
         self._scanned = self._have_sims = False
         self.similarities = _SimilarityView(self)
 
@@ -310,6 +314,10 @@ class Ticket:
         self._weights = dict(weights)
         self._scanned = self._have_sims = False
         self.scores = _ScoreView(self)
+
+    def _ids_in_dict_order(self):
+        ids, place = self.feature_store().clip_ids, getattr(self, "_place", None)
+        return ids if place is None else ids[np.argsort(place)]
 
     def _eps(self):
         return float(os.environ["COMPUTE_EPS"])
@@ -345,7 +353,8 @@ class Ticket:
         clips = [int(c) for c, v in self.user_matches.items() if v is True and st.has_clip(int(c))]
         if not clips:
             return 1, None
-        clips.sort(key=st.row_of)
+        place = getattr(self, "_place", None)
+        clips.sort(key=st.row_of if place is None else (lambda c: int(place[st.row_of(c)])))
         sims = st.labelled_sims(self.target.target_features, st.rows_of(clips))
         weights = self._weights if self._weights is not None else self._hp.weights
         ssum, denom = np.zeros(len(clips)), 0.0
@@ -365,7 +374,8 @@ class Ticket:
         # A review round samples a few dozen clips: the lists stay on the device and only the sampled entries are
         # fetched.  The finalize round (max = inf) returns every clip above the criterion: whole lists come back, and
         # everything below is array work — no per-clip Python objects until the final dict.
-        sampled = max_number_matches != float("inf")
+        place = getattr(self, "_place", None)                  # not None: the reference's dict order differs from the row order
+        sampled = max_number_matches != float("inf") and place is None
         res = self._scan(threshold, lower_limit, lists=not sampled)
         ids, first = st.clip_ids, st.first_global_row
         t_rows, _ = st.ties(copy=False)
@@ -378,8 +388,14 @@ class Ticket:
         # random.sample(population, k) draws depend only on (len(population), k): sampling the index
         # range consumes the generator exactly like sampling the reference's dict items (:333).
         picked = sample_range(random, res.n_match, mscores)
+        order_m = order_n = None
         if not sampled:
             all_rows, all_sc = st.matches(copy=False)     # views of the scan's host mirror: consumed before the next scan
+            nm_rows, nm_sc = st.near_misses(copy=False)
+            if place is not None:                          # the lists in the reference's dict order
+                order_m = np.argsort(place[all_rows - first], kind="stable")
+                order_n = np.argsort(place[nm_rows - first], kind="stable")
+                all_rows, all_sc, nm_rows, nm_sc = all_rows[order_m], all_sc[order_m], nm_rows[order_n], nm_sc[order_n]
             m_rows, m_sc = all_rows[picked], all_sc[picked]
         jbest, best_row, best_sc = None, None, None
         n_left = res.n_near
@@ -389,7 +405,6 @@ class Ticket:
             if sampled:
                 jbest, best_row, best_sc = st.near_best()  # first maximum in database order (:338), found on the device
             else:
-                nm_rows, nm_sc = st.near_misses(copy=False)
                 jbest = int(np.argmax(nm_sc))
                 best_row, best_sc = int(nm_rows[jbest]), float(nm_sc[jbest])
         picked_n = sample_range(random, n_left, m_near_scores)
@@ -398,7 +413,6 @@ class Ticket:
         if sampled:                                        # one round trip for both lists' sampled entries
             (m_rows, m_sc), (n_rows_p, n_sc_p) = st.gather_many([("matches", picked), ("near_misses", pos)])
         else:
-            nm_rows, nm_sc = st.near_misses(copy=False)
             n_rows_p, n_sc_p = nm_rows[pos], nm_sc[pos]
         sel_rows = np.concatenate([m_rows, n_rows_p] + ([[best_row]] if best_row is not None else [])).astype(np.int64)
         sel_sc = np.concatenate([m_sc, n_sc_p] + ([[best_sc]] if best_row is not None else []))
@@ -413,8 +427,13 @@ class Ticket:
             f_sc = st.scores_at(st.rows_of(forced))        # one round trip for all forced clips (:346-356)
             self.matches.update(zip(forced, f_sc.tolist()))
         # what the final report needs to rank on the device (ranked_selection): the lists' entries in selection order
-        self._selection = None if sampled else {
-            "n_match": res.n_match, "n_near": res.n_near, "picked": picked, "pos": pos, "jbest": jbest, "n_listed": len(sel_ids)}
+        # (as indices into the device's row-ordered lists; a review round on the whole-list path keeps nothing)
+        self._selection = None
+        if max_number_matches == float("inf"):
+            row_idx = lambda order, j: j if order is None else order[j]
+            self._selection = {"n_match": res.n_match, "n_near": res.n_near, "picked": row_idx(order_m, picked),
+                               "pos": row_idx(order_n, pos), "jbest": None if jbest is None else int(row_idx(order_n, jbest)),
+                               "n_listed": len(sel_ids)}
 
     def ranked_selection(self):
         """[(clip id, score)] of the last finalize selection in REPORT order: score descending, ties in the order the
