@@ -139,15 +139,29 @@ __global__ void gram_kernel(const float *__restrict__ rows, const long long *__r
 // A zero (or non-finite) pivot — a duplicated labelled clip, more independent rows than dimensions — sets *singular:
 // numpy.linalg.inv raises LinAlgError for such a matrix (target_clip.py:194,248), the caller here turns the flag into an error.
 __device__ void lu_solve(double *A, double *B, int n, int nrhs, int *piv_s, int *singular) {
+    __shared__ double red_v[32];
+    __shared__ int red_i[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     for (int k = 0; k < n; ++k) {
+        // pivot: largest |A[i][k]|, i >= k, lowest i among equals (what a serial scan finds) — block-wide arg-max
+        double best = -1.0;
+        int bi = k;
+        for (int i = k + threadIdx.x; i < n; i += blockDim.x) {
+            const double v = fabs(A[(size_t)i * n + k]);
+            if (v > best) { best = v; bi = i; }                      // a thread's candidates come in ascending i
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        }
+        if (lane == 0) { red_v[wid] = best; red_i[wid] = bi; }
+        __syncthreads();
         if (threadIdx.x == 0) {
-            int p = k;
-            double best = fabs(A[(size_t)k * n + k]);
-            for (int i = k + 1; i < n; ++i) {
-                const double v = fabs(A[(size_t)i * n + k]);
-                if (v > best) { best = v; p = i; }
-            }
-            *piv_s = p;
+            for (int w = 1; w < n_warps; ++w)
+                if (red_v[w] > best || (red_v[w] == best && red_i[w] < bi)) { best = red_v[w]; bi = red_i[w]; }
+            *piv_s = bi;
         }
         __syncthreads();
         const int p = *piv_s;
@@ -168,13 +182,17 @@ __device__ void lu_solve(double *A, double *B, int n, int nrhs, int *piv_s, int 
         if (threadIdx.x == 0 && !(fabs(pivot) > 0.0 && fabs(pivot) < 1.0e300)) *singular = 1;
         for (int i = k + 1 + threadIdx.x; i < n; i += blockDim.x) A[(size_t)i * n + k] /= pivot;
         __syncthreads();
+        // trailing update, one warp per row: lanes walk the row's columns (A's, then B's) — coalesced, no division
         const int rem = n - k - 1;
-        for (long long e = threadIdx.x; e < (long long)rem * (rem + nrhs); e += blockDim.x) {
-            const int i = k + 1 + (int)(e / (rem + nrhs));
-            const int c = (int)(e % (rem + nrhs));
+        for (int r = wid; r < rem; r += n_warps) {
+            const int i = k + 1 + r;
             const double l = A[(size_t)i * n + k];
-            if (c < rem) A[(size_t)i * n + (k + 1 + c)] -= l * A[(size_t)k * n + (k + 1 + c)];
-            else B[(size_t)i * nrhs + (c - rem)] -= l * B[(size_t)k * nrhs + (c - rem)];
+            double *Ai = A + (size_t)i * n + (k + 1);
+            const double *Ak = A + (size_t)k * n + (k + 1);
+            for (int c = lane; c < rem; c += 32) Ai[c] -= l * Ak[c];
+            double *Bi = B + (size_t)i * nrhs;
+            const double *Bk = B + (size_t)k * nrhs;
+            for (int c = lane; c < nrhs; c += 32) Bi[c] -= l * Bk[c];
         }
         __syncthreads();
     }
@@ -198,7 +216,7 @@ __device__ void lu_solve(double *A, double *B, int n, int nrhs, int *piv_s, int 
 //     a = beta - c delta;   b = c gamma + c K Gyx delta - K Gyx beta.
 // With m = 0 (or mu = 0 => c = 0, K = 0) this is a = Gxx^-1 1, the valid-only rule (:194-198).
 // Scratch per slot (doubles): Bm[n*n] | R[n*2] | Ky[m*m] | Z[m*(n+1)] | tmp[n+m]
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 bootstrap_solve_kernel(const double *__restrict__ G, int n, int m, double mu, double *scratch,
                        size_t scratch_per_slot, double *coef, int *singular, const unsigned char *__restrict__ slot_mask) {
     __shared__ int piv_s;
@@ -475,7 +493,7 @@ extern "C" int vq_bootstrap_target(vq_store *s, const int64_t *valid_rows, int32
     const long long warps = (long long)nz * nz * n_slots;
     gram_kernel<<<(unsigned int)((warps * 32 + 255) / 256), 256, 0, s->stream>>>(s->rows, d_ids, nz, n_slots, s->dim,
                                                                                s->row_floats, d_G);
-    bootstrap_solve_kernel<<<n_slots, 256, 0, s->stream>>>(d_G, n, m, mu, d_scr, per_slot, d_coef, d_flag, d_mask);
+    bootstrap_solve_kernel<<<n_slots, 1024, 0, s->stream>>>(d_G, n, m, mu, d_scr, per_slot, d_coef, d_flag, d_mask);
     combine_kernel<<<(n_slots * s->dim + 255) / 256, 256, 0, s->stream>>>(s->rows, d_ids, nz, n_slots, s->dim, s->row_floats,
                                                                          d_coef, d_out);
     VQ_CUDA(cudaGetLastError());

@@ -19,12 +19,14 @@
 // Summation order is fixed by the launch geometry, so results are deterministic run to run.
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <functional>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -850,7 +852,18 @@ public:
     int run(int n, const std::function<int(int)> &fn) {
         if (n <= 1) return n == 1 ? fn(0) : 0;
         std::lock_guard<std::mutex> call(call_mutex_);              // one multi-shard call at a time (the contract anyway)
-        grow(n - 1);
+        if (pid_ != getpid()) {                                     // a forked child inherits the object, not the threads
+            for (auto &t : threads_) t.release();                   // (never joined or destroyed: they do not exist here)
+            threads_.clear();
+            pid_ = getpid();
+        }
+        try {
+            grow(n - 1);
+        } catch (const std::exception &e) {                         // no exception crosses the C ABI: run the shards from this thread
+            int rc = 0;
+            for (int i = 0; i < n && rc == 0; ++i) rc = fn(i);
+            return rc;
+        }
         fn_ = &fn;
         n_jobs_ = n;
         remaining_.store(n - 1, std::memory_order_relaxed);
@@ -883,8 +896,9 @@ private:
             rc_.resize((size_t)id + 1, 0);
             err_.resize((size_t)id + 1);
             const unsigned long long start = gen_.load(std::memory_order_acquire);   // the job of THIS run() is start + 1
-            threads_.emplace_back([this, id, start] { loop(id, start); });
-            threads_.back().detach();                                // they live as long as the process
+            std::thread t([this, id, start] { loop(id, start); });
+            t.detach();                                              // they live as long as the process
+            threads_.emplace_back(new int(id));
         }
     }
     void loop(int id, unsigned long long seen) {
@@ -912,7 +926,8 @@ private:
     std::atomic<int> remaining_{0};
     const std::function<int(int)> *fn_ = nullptr;
     int n_jobs_ = 0;
-    std::vector<std::thread> threads_;
+    std::vector<std::unique_ptr<int>> threads_;                      // one entry per live worker (the threads themselves are detached)
+    pid_t pid_ = getpid();
     std::vector<int> rc_;
     std::vector<std::string> err_;
 };
