@@ -926,3 +926,79 @@ def test_row_order_on_ragged_search_sets_is_the_reference_scores_order():
             assert [int(present[r, si].sum()) for si in range(2)] == [t.similarities[c][s][1] for s in streams]
             assert [float(X[r, si, :, 0].sum() / present[r, si].sum()) for si in range(2)] == \
                 pytest.approx([t.similarities[c][s][0] for s in streams], rel=1e-6)
+
+
+# ---------------------------------------------------------------------------- round 2: native host pieces
+def test_native_sample_equals_random_sample_and_leaves_the_same_state(built_lib):
+    """vq_mt_sample_range (csrc/vq_rng.cu) against CPython's own random.sample(range(n), k) on the same generator state:
+    same picks, same state afterwards (so every later draw of the tick is unchanged) — across the pool / taken-set
+    switch of sample() (n <= 21 + 4**ceil(log4(3k))), bit lengths of n around powers of two (rejection loop of
+    randbelow), wide populations (two 32-bit outputs per draw) and the finalize round's full permutation."""
+    from video_query_algorithms_b200 import _rng
+    cases = [(100, 100), (64, 64), (1000, 64), (50_000, 50_000), (90_000, 70), (5000, 1000), (70, 65), (2 ** 33, 100),
+             (200_000, 199_999), (341, 64), (85, 64), (86, 64), (2 ** 20, 77), (2 ** 20 + 1, 77), (2 ** 32, 65), (2 ** 32 + 5, 65),
+             (277, 64), (278, 64), (1045, 256), (1046, 256)]
+    for n, k in cases:
+        random.seed("73459912436")
+        random.random()
+        want = random.sample(range(n), k)
+        state, nxt = random.getstate(), random.random()
+        random.seed("73459912436")
+        random.random()
+        got = _rng.sample_range(random, n, k)
+        assert got.tolist() == want, (n, k)
+        assert random.getstate() == state and random.random() == nxt, (n, k)
+    # small draws take Python's own path; a generator that is not CPython's MT19937 too
+    random.seed(5)
+    a = random.sample(range(1000), 10)
+    random.seed(5)
+    assert _rng.sample_range(random, 1000, 10).tolist() == a
+    with pytest.raises(ValueError):
+        _rng.sample_range(random, 10, 100)
+
+
+def test_dict_order_follows_the_reference_for_any_target_split_order(built_lib):
+    """FeatureStore.dict_order against a literal emulation of the reference's dict filling (ticket.py:142-160,374-381) on
+    random ragged responses — shuffled records, duplicate slots, targets that walk the splits in any order and lack some:
+    the order of the clips in the reference's `scores` dict, which its seeded sampling draws from."""
+    from video_query_algorithms_b200 import store as ps
+    rng = np.random.default_rng(1)
+    S = ("a", "b")
+    n_checked = n_moved = 0
+    for trial in range(300):
+        n, splits = int(rng.integers(3, 12)), [1, 2, 3][:int(rng.integers(1, 4))]
+        recs = [{"dnn_stream_id": s, "dnn_stream_split": p, "name": "g", "video_clip_id": 100 + c, "feature_vector": [float(c), 1.0, 2.0, 3.0]}
+                for c in range(n) for s in S for p in splits if rng.random() < 0.7]
+        rng.shuffle(recs)
+        if recs and rng.random() < 0.3:
+            recs.append(dict(recs[0]))                          # a slot listed twice: the dict keeps its first place
+        idx, _ = ps.index_feature_rows(recs, S, "g")
+        if idx.n_rows == 0:
+            continue
+        st = ps.FeatureStore.__new__(ps.FeatureStore)
+        st.streams, st.splits, st.n_rows, st.slot_pos = S, idx.splits, idx.n_rows, idx.slot_positions()
+        t_splits = [int(p) for p in rng.permutation(idx.splits) if rng.random() < 0.8] or [int(idx.splits[0])]
+        tf = {s: {p: [0.0] for p in t_splits} for s in S}
+        cand = {s: {p: {} for p in t_splits} for s in S}
+        for r in recs:
+            if r["dnn_stream_split"] in cand[r["dnn_stream_id"]]:
+                cand[r["dnn_stream_id"]][r["dnn_stream_split"]][r["video_clip_id"]] = 1
+        want = {}
+        for s in S:
+            sims = {}
+            for p in tf[s]:
+                for c in cand[s][p]:
+                    sims[c] = 1
+            for c in sims:
+                want.setdefault(c, 1)
+        place = st.dict_order(tf)
+        ids = np.asarray(idx.order)
+        got = [int(c) for c in (ids if place is None else ids[np.argsort(place)]) if c in want]
+        assert got == list(want), (trial, t_splits)
+        n_checked += 1
+        n_moved += place is not None
+    assert n_checked > 250 and n_moved > 50
+    # complete data listed consistently: the row order serves every target, nothing is kept
+    recs = [{"dnn_stream_id": s, "dnn_stream_split": p, "name": "g", "video_clip_id": c, "feature_vector": [1.0, 2.0, 3.0, 4.0]}
+            for p in (1, 2) for s in S for c in range(20)]
+    assert ps.index_feature_rows(recs, S, "g")[0].slot_positions() is None
