@@ -297,8 +297,11 @@ def main():
                 _ffi.check(fn(handle_, rs._x, sptr), "vq_scan_exchange_enqueue")
             rs.flush(stream.cuda_stream)
             barrier()
-            xi = rs.exchange_times()
+            xi, xp = rs.exchange_times(parts=True)
             phases["exchange_ms_alone"] = max_over_ranks(float(np.mean(xi[4:]))) if len(xi) > 4 else None
+            if len(xi) > 4:                                  # ... split: NVLink pushes | waiting for the slowest peer | the merge itself
+                for j, name in enumerate(("push", "wait_for_peers", "merge")):
+                    phases["exchange_ms_alone_" + name] = max_over_ranks(float(np.mean(xp[4:, j])))
         return ms_total / steps, phases, rs
 
     sampler = ClockSampler(local_rank)               # NVML init happens here, outside every timed region

@@ -192,9 +192,11 @@ int vq_exchange_merged(vq_exchange *x, const int64_t **merged_dev /* [4 + 2*topk
  * behind the peer it may be waiting for); vq_exchange_flush_enqueue also makes `stream` wait for it, so call it before
  * reading the merged buffer on `stream`.  A peer that never delivers ends the kernel after VQ_EXCHANGE_TIMEOUT_S
  * (default 10 s) with negative counts in the merged buffer: vq_exchange_check (after a synchronisation) reports it.
- * vq_exchange_kernel_times: device time of each exchange kernel since the last call (ring of 256), in ms.           */
+ * vq_exchange_kernel_times: each exchange kernel's own time since the last call (ring of 256), in ms, taken by the kernel
+ * on the global timer, optionally split into its three phases.                                                       */
 int vq_exchange_check(vq_exchange *x);
-int vq_exchange_kernel_times(vq_exchange *x, int32_t cap, float *ms_out, int32_t *n_out);
+int vq_exchange_kernel_times(vq_exchange *x, int32_t cap, float *ms_out, float *parts_out /* [cap][3]: push, wait, merge; or NULL */,
+                             int32_t *n_out);
 
 /* Host mailbox: all-gather of small records (up to slot_bytes each) between the rank processes of ONE box through a
  * POSIX shared-memory segment — the host-side twin of the exchange above, for what the host needs from its peers per

@@ -66,7 +66,7 @@ PROTOTYPES = {
     "vq_fetch_scores_at": (C.c_int, [_vp, _i64, _vp, _vp]),
     "vq_scan_phase_times": (C.c_int, [_vp, _i32, _vp, _vp, _P(_i32)]),
     "vq_exchange_check": (C.c_int, [_vp]),
-    "vq_exchange_kernel_times": (C.c_int, [_vp, _i32, _vp, _P(_i32)]),
+    "vq_exchange_kernel_times": (C.c_int, [_vp, _i32, _vp, _vp, _P(_i32)]),
     "vq_rank_list": (C.c_int, [_vp, _i32, _i64, _vp, _vp, _vp]),
     "vq_mt_sample_range": (C.c_int, [_vp, _P(_i32), _i64, _i64, _vp]),
     "vq_scan_enqueue": (C.c_int, [_vp, _vp, _P(ScanParams), _vp]),

@@ -34,7 +34,7 @@ struct vq_exchange {
     // before the next select_compact overwrites the payload (vq_store::pack_reader_done).
     cudaStream_t side = nullptr;
     cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
-    unsigned long long *t_ring = nullptr;       // pinned, device-mapped [256][2]: start / end of each exchange kernel (global timer, ns)
+    unsigned long long *t_ring = nullptr;       // pinned, device-mapped [256][4]: start, pushes done, peers' flags seen, end of each exchange kernel (global timer, ns)
     int ev_head = 0, ev_count = 0;
     double timeout_s = 10.0;                    // a peer that never arrives ends the kernel with an error marker instead of a hang
 };
@@ -131,8 +131,9 @@ exchange_push_merge(const long long *__restrict__ payload, long long *const *__r
             st_release_sys(flag, push_seq);
         }
     }
+    const unsigned long long t_pushed = global_ns();
     if (!merge_seq) {
-        if (t_ns && threadIdx.x == 0) { t_ns[0] = t_begin; t_ns[1] = global_ns(); }
+        if (t_ns && threadIdx.x == 0) { t_ns[0] = t_begin; t_ns[1] = t_pushed; t_ns[2] = t_pushed; t_ns[3] = global_ns(); }
         return;
     }
     // 2. wait until every rank's payload for the sequence number to merge has landed in my inbox; a peer that has died
@@ -151,6 +152,7 @@ exchange_push_merge(const long long *__restrict__ payload, long long *const *__r
         }
     }
     __syncthreads();
+    const unsigned long long t_seen = global_ns();
     if (timed_out) {
         if (threadIdx.x < 4) merged[threadIdx.x] = -1;         // counts < 0: vq_exchange_check / the host reader raise
         return;
@@ -192,7 +194,7 @@ exchange_push_merge(const long long *__restrict__ payload, long long *const *__r
         long long tot = 0;
         for (int l = 0; l < world; ++l) tot += len_s[l];
         merged[3] = tot < k ? tot : k;
-        if (t_ns) { t_ns[0] = t_begin; t_ns[1] = global_ns(); }
+        if (t_ns) { t_ns[0] = t_begin; t_ns[1] = t_pushed; t_ns[2] = t_seen; t_ns[3] = global_ns(); }
     }
 }
 }  // namespace
@@ -223,8 +225,8 @@ extern "C" int vq_exchange_create(vq_exchange **out, int device, int world, int 
         VQ_CUDA(cudaEventCreateWithFlags(&x->ev_ready, cudaEventDisableTiming));
         VQ_CUDA(cudaEventCreateWithFlags(&x->ev_done, cudaEventDisableTiming));
     }
-    VQ_CUDA(cudaMallocHost((void **)&x->t_ring, kRing * 2 * sizeof(unsigned long long)));
-    memset(x->t_ring, 0, kRing * 2 * sizeof(unsigned long long));
+    VQ_CUDA(cudaMallocHost((void **)&x->t_ring, kRing * 4 * sizeof(unsigned long long)));
+    memset(x->t_ring, 0, kRing * 4 * sizeof(unsigned long long));
     if (const char *t = getenv("VQ_EXCHANGE_TIMEOUT_S")) x->timeout_s = atof(t) > 0 ? atof(t) : x->timeout_s;
     cudaFuncSetAttribute(exchange_push_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, kMergeShared * 12);
     *out = x;
@@ -294,7 +296,7 @@ static int launch_exchange(vq_exchange *x, vq_store *s, cudaStream_t scan_st, co
     if (x->ev_count < kRing) x->ev_count++;
     exchange_push_merge<<<1, kXThreads, merge_smem(x->world, x->topk), run>>>(
         payload, x->peer_table_dev, x->world, x->rank, x->topk, push_seq, merge_seq, x->merged, x->scratch,
-        (unsigned long long)(x->timeout_s * 1e9), x->t_ring + 2 * slot);
+        (unsigned long long)(x->timeout_s * 1e9), x->t_ring + 4 * slot);
     VQ_CUDA(cudaGetLastError());
     if (x->side && s) {                              // the next select_compact on this store waits for this kernel before it rewrites the payload
         if (!s->pack_reader_done) VQ_CUDA(cudaEventCreateWithFlags(&s->pack_reader_done, cudaEventDisableTiming));
@@ -353,17 +355,25 @@ extern "C" int vq_exchange_merged(vq_exchange *x, const int64_t **merged_dev) {
 }
 
 // Device times (ms) of the exchange kernels launched since the last call (ring of 256), taken by the kernels themselves on
-// the global timer (start of the block to its last store: pushes, the wait for the peers' flags and the merge); call after a
-// synchronisation.
-extern "C" int vq_exchange_kernel_times(vq_exchange *x, int32_t cap, float *ms_out, int32_t *n_out) {
+// the global timer (start of the block to its last store); parts_out splits each into pushes | wait for the peers' flags |
+// merge.  Call after a synchronisation.
+extern "C" int vq_exchange_kernel_times(vq_exchange *x, int32_t cap, float *ms_out, float *parts_out /* [cap][3] or NULL */, int32_t *n_out) {
     VQ_REQUIRE(x && n_out, "vq_exchange_kernel_times: null argument");
     VQ_CUDA(cudaSetDevice(x->device));
     const int n = x->ev_count < cap ? x->ev_count : cap;
     int got = 0;
     for (int i = 0; i < n; ++i) {
         const int slot = (x->ev_head + kRing - n + i) % kRing;
-        const unsigned long long t0 = x->t_ring[2 * slot], t1 = x->t_ring[2 * slot + 1];
-        if (t1 >= t0 && t0 != 0 && ms_out) ms_out[got++] = (float)((double)(t1 - t0) * 1e-6);
+        const unsigned long long *t = x->t_ring + 4 * slot;
+        if (t[3] >= t[0] && t[0] != 0 && ms_out) {
+            ms_out[got] = (float)((double)(t[3] - t[0]) * 1e-6);
+            if (parts_out) {                                 // push | wait for the peers | merge
+                parts_out[3 * got] = (float)((double)(t[1] - t[0]) * 1e-6);
+                parts_out[3 * got + 1] = (float)((double)(t[2] - t[1]) * 1e-6);
+                parts_out[3 * got + 2] = (float)((double)(t[3] - t[2]) * 1e-6);
+            }
+            ++got;
+        }
     }
     *n_out = got;
     x->ev_count = 0;

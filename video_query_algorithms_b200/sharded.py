@@ -140,13 +140,14 @@ class RankScan:
         t = self.merged if self.world > 1 else self._payload_view()
         return unpack_payload(t.cpu().numpy(), self.k)
 
-    def exchange_times(self):
-        """device times (ms) of the exchange kernels since the last call (after a synchronisation)"""
+    def exchange_times(self, parts=False):
+        """the exchange kernels' own times (ms) since the last call (after a synchronisation); parts=True: also
+        [n, 3] = pushes | wait for the peers' flags | merge"""
         if self._x is None:
-            return np.empty(0, np.float32)
-        out, n = np.empty(256, np.float32), C.c_int32()
-        check(lib().vq_exchange_kernel_times(self._x, 256, ptr(out), C.byref(n)), "vq_exchange_kernel_times")
-        return out[:n.value]
+            return (np.empty(0, np.float32), np.empty((0, 3), np.float32)) if parts else np.empty(0, np.float32)
+        out, split, n = np.empty(256, np.float32), np.empty((256, 3), np.float32), C.c_int32()
+        check(lib().vq_exchange_kernel_times(self._x, 256, ptr(out), ptr(split), C.byref(n)), "vq_exchange_kernel_times")
+        return (out[:n.value], split[:n.value]) if parts else out[:n.value]
 
 
 def exchange_host(payload, dist, torch, k):
