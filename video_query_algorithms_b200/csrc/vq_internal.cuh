@@ -81,9 +81,9 @@ struct vq_store {
     cudaEvent_t pack_reader_done = nullptr;
     bool pack_reader_pending = false;
 
-    cudaEvent_t ev_start[vq::kTimeRing], ev_stop[vq::kTimeRing];   // around K1
-    cudaEvent_t ev_sel_stop[vq::kTimeRing];                         // after K2c: ev_stop .. ev_sel_stop = the selection kernels
-    bool ev_made = false;
+    // timing ring, a slot's three events created on its first use (3 x 1024 cudaEventCreate per store cost ~5 ms up front)
+    cudaEvent_t ev_start[vq::kTimeRing] = {}, ev_stop[vq::kTimeRing] = {};   // around K1
+    cudaEvent_t ev_sel_stop[vq::kTimeRing] = {};                              // after K2c: ev_stop .. ev_sel_stop = the selection kernels
     int ev_head = 0, ev_count = 0;
     void *pinned_stage = nullptr;    // small pinned buffer for targets / params
     // pinned, device-mapped mirror of the last scan's lists + top-k: vq_scan's publish kernel writes it over PCIe,

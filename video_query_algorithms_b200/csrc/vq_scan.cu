@@ -665,6 +665,11 @@ extern "C" int vq_scan_enqueue(vq_store *s, const float *target_dev, const vq_sc
     const int slot = s->ev_head;
     s->ev_head = (s->ev_head + 1) % vq::kTimeRing;
     if (s->ev_count < vq::kTimeRing) s->ev_count++;
+    if (!s->ev_start[slot]) {
+        VQ_CUDA(cudaEventCreate(&s->ev_start[slot]));
+        VQ_CUDA(cudaEventCreate(&s->ev_stop[slot]));
+        VQ_CUDA(cudaEventCreate(&s->ev_sel_stop[slot]));
+    }
     VQ_CUDA(cudaEventRecord(s->ev_start[slot], st));
     const int grid = s->sm_count * 3;
     if (s->n_streams == 2 && s->stream_len == 1024 && !getenv("VQ_SCAN_GENERIC")) {

@@ -90,8 +90,8 @@ static void store_free(vq_store *s) {
     if (s->h_rank_scores) cudaFreeHost(s->h_rank_scores);
     if (s->h_topk_rows) cudaFreeHost(s->h_topk_rows);
     if (s->h_topk_scores) cudaFreeHost(s->h_topk_scores);
-    if (s->ev_made)
-        for (int i = 0; i < vq::kTimeRing; ++i) {
+    for (int i = 0; i < vq::kTimeRing; ++i)                  // created on first use of their ring slot (vq_scan_enqueue)
+        if (s->ev_start[i]) {
             cudaEventDestroy(s->ev_start[i]);
             cudaEventDestroy(s->ev_stop[i]);
             cudaEventDestroy(s->ev_sel_stop[i]);
@@ -188,12 +188,6 @@ extern "C" int vq_store_create(vq_store **out, int device, int64_t n_rows, int n
         store_free(s);
         return -3;
     }
-    for (int i = 0; i < vq::kTimeRing; ++i) {
-        cudaEventCreate(&s->ev_start[i]);
-        cudaEventCreate(&s->ev_stop[i]);
-        cudaEventCreate(&s->ev_sel_stop[i]);
-    }
-    s->ev_made = true;
     cudaMemsetAsync(s->counts, 0, 8 * sizeof(int64_t), s->stream);
     cudaMemsetAsync(s->hist, 0, (vq::kHistBins + 8) * sizeof(unsigned int), s->stream);
     cudaMemsetAsync(s->cand_count, 0, 4 * sizeof(unsigned int), s->stream);

@@ -494,18 +494,35 @@ class FeatureStore:
             for b in bufs:
                 self._free_staging(b)
 
-    # staging / asynchronous upload primitives (test doubles replace these four)
+    # staging / asynchronous upload primitives (test doubles replace these four).  Page-locking memory costs milliseconds
+    # per buffer, so the last two staging buffers are kept for the next build or append (at most 2 x CHUNK_BYTES).
+    _STAGING_POOL = []               # [(address, n_floats)] of idle pinned buffers, process-wide
+
     def _alloc_staging(self, n_floats):
-        p = C.c_void_p()
-        check(lib().vq_pinned_alloc(C.byref(p), int(n_floats) * 4), "vq_pinned_alloc")
-        a = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(int(n_floats),))
-        self.__dict__.setdefault("_staging_ptrs", {})[a.ctypes.data] = p
-        return a
+        n_floats = int(n_floats)
+        pool = FeatureStore._STAGING_POOL
+        for i, (addr, cap) in enumerate(pool):
+            if cap >= n_floats:
+                pool.pop(i)
+                break
+        else:
+            p = C.c_void_p()
+            check(lib().vq_pinned_alloc(C.byref(p), n_floats * 4), "vq_pinned_alloc")
+            addr, cap = p.value, n_floats
+        whole = np.ctypeslib.as_array(C.cast(C.c_void_p(addr), C.POINTER(C.c_float)), shape=(cap,))
+        self.__dict__.setdefault("_staging_caps", {})[addr] = cap
+        return whole[:n_floats]
 
     def _free_staging(self, a):
-        p = self.__dict__.get("_staging_ptrs", {}).pop(a.ctypes.data, None)
-        if p is not None:
-            lib().vq_pinned_free(p)
+        addr = a.ctypes.data
+        cap = self.__dict__.get("_staging_caps", {}).pop(addr, None)
+        if cap is None:
+            return
+        pool = FeatureStore._STAGING_POOL
+        pool.append((addr, cap))
+        pool.sort(key=lambda e: -e[1])
+        while len(pool) > 2:                                      # keep the two largest
+            lib().vq_pinned_free(C.c_void_p(pool.pop()[0]))
 
     def _upload_async(self, first_row, flat):
         n = len(flat) // int(np.prod(self.row_shape))
