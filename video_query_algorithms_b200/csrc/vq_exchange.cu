@@ -116,8 +116,10 @@ __device__ __forceinline__ void merge_ranked(RowPtr rows, ScorePtr scs, const in
     }
 }
 
-// (A one-warp k-way merge of the list heads — k sequential steps of a shuffle butterfly — was measured at 31 us for world 2,
-// k 100 against 4 us for the binary searches below: its dependent shuffle chain has no parallelism to hide latency behind.)
+// Two alternatives were measured and dropped (8 B200s, world 8, k 100, merge phase alone: 25.6 us for the version above):
+// a one-warp k-way merge of the list heads (k sequential steps of a shuffle butterfly; 31 us already at world 2 — a dependent
+// chain with nothing to hide its latency behind) and eight lists' searches in lockstep with a fixed step count (49.8 us — it
+// gives up the early exit above, which ends most entries after one or two lists because their rank already exceeds k).
 __global__ void __launch_bounds__(kXThreads, 10)
 exchange_push_merge(const long long *__restrict__ payload, long long *const *__restrict__ peers, const int world,
                     const int rank, const int k, const unsigned long long push_seq /* 0: nothing to push */,
