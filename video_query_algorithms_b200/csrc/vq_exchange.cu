@@ -78,36 +78,21 @@ template <class RowPtr, class ScorePtr>
 __device__ __forceinline__ void merge_ranked(RowPtr rows, ScorePtr scs, const int *len, const int world, const int k,
                                              const int stride, long long *merged) {
     const int n = world * k;
-    int iters = 0;
-    while ((1 << iters) <= k) ++iters;                          // halvings that exhaust any list of <= k entries
     for (int e = threadIdx.x; e < n; e += blockDim.x) {
         const int l = e / k, i = e - l * k;
         if (i >= len[l]) continue;
         const float sc = scs[l * stride + i];
         const long long row = rows[l * stride + i];
         int rank = i;
-        // eight lists' binary searches advance in lockstep (branch-free lower bound, fixed step count): the searches are
-        // independent, so their shared-memory round trips overlap instead of queueing behind one another
-        for (int l0 = 0; l0 < world; l0 += 8) {
-            int lo[8], cnt[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int l2 = l0 + u;
-                cnt[u] = (l2 < world && l2 != l) ? len[l2] : 0;
-                lo[u] = 0;
+        for (int l2 = 0; l2 < world && rank < k; ++l2) {
+            if (l2 == l) continue;
+            int lo = 0, hi = len[l2];
+            while (lo < hi) {                                   // first entry of list l2 that does NOT come before (sc, row)
+                const int mid = (lo + hi) >> 1;
+                if (before(scs[l2 * stride + mid], rows[l2 * stride + mid], sc, row)) lo = mid + 1;
+                else hi = mid;
             }
-            for (int s = 0; s < iters; ++s) {
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const int half = cnt[u] >> 1, mid = lo[u] + half;
-                    bool pred = false;                            // cnt == 0: decided; otherwise mid <= len - 1
-                    if (cnt[u] > 0) pred = before(scs[(l0 + u) * stride + mid], rows[(l0 + u) * stride + mid], sc, row);
-                    lo[u] = pred ? mid + 1 : lo[u];
-                    cnt[u] = pred ? cnt[u] - half - 1 : half;
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) rank += lo[u];          // entries of list l0 + u that come before (sc, row)
+            rank += lo;
         }
         if (rank < k) {
             merged[4 + rank] = row;
@@ -116,6 +101,11 @@ __device__ __forceinline__ void merge_ranked(RowPtr rows, ScorePtr scs, const in
     }
 }
 
+// One block of kXThreads = 128 threads at <= 48 registers: small enough to be co-resident with the scan kernel of the NEXT
+// step (K1 keeps 3 blocks of 128 threads x 150 registers on every SM, which leaves 7168 registers per SM), so that it runs
+// as soon as its inputs are ready instead of queueing behind a 1.1 ms scan.  t_ns (when not null) receives the kernel's
+// own start and end on the global timer: CUDA events around a kernel on a side stream would also count the time it
+// waits for an SM.
 // Two alternatives were measured and dropped (8 B200s, world 8, k 100, merge phase alone: 25.6 us for the version above):
 // a one-warp k-way merge of the list heads (k sequential steps of a shuffle butterfly; 31 us already at world 2 — a dependent
 // chain with nothing to hide its latency behind) and eight lists' searches in lockstep with a fixed step count (49.8 us — it
