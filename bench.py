@@ -673,6 +673,14 @@ def run_batched(args, rank, world, local_rank, steps=None):
         flops = 2.0 * pairs * 2 * DIM                        # algorithmic: 2 * Q * N * S * D
         pk = _peaks()
         peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops", 1590.0)))
+        tensor_pipe = None                                   # from ONE ncu --set full capture of a steady-state launch (profiles/)
+        try:
+            with open(os.path.join(ROOT, "profiles", "k3_tensor_pipe.json")) as f:
+                tj = json.load(f)
+            if int(tj["queries"]) == Q:
+                tensor_pipe = {"active_pct_of_elapsed": tj["tensor_pipe_active_pct_of_elapsed"], "source": tj["source"]}
+        except Exception:
+            pass
         achieved = flops / world / (ms_step * 1e-3) / 1e12   # per GPU, like the peak
         line = {
             "metric": "clip-query pairs scored/sec (batched queries)", "value": pairs / (ms_step * 1e-3), "unit": "pairs/s",
@@ -689,6 +697,7 @@ def run_batched(args, rank, world, local_rank, steps=None):
                          "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16, back to back)" if pk
                          else "fallback 1590", "algorithmic_flops_per_step_per_gpu": flops / world,
                          "executed_tflops_bf16x2": 3 * achieved, "frac_executed": 3 * achieved / peak,
+                         "tensor_pipe_ncu": tensor_pipe,
                          "note": "three bf16 MMAs per fp32 product (x1*t1 + x2*t1 + x1*t2): the tensor pipe executes 3x "
                                  "the algorithmic flops"},
             "e2e": {"value": pairs * steps / wall, "unit": "pairs/s", "h2d_bytes_per_step": int(Q * ROW_BYTES + 64),
