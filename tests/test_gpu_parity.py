@@ -979,14 +979,18 @@ def test_singular_labelled_set_is_an_error_not_a_nan_target(vq):
     st.close()
 
 
-def test_finalize_selection_of_a_large_search_set_is_array_work(vq, tmp_path, monkeypatch):
+@pytest.mark.parametrize("n", [1_000_000, 12_500_000], ids=["config2-1M", "config3-shard-12.5M"])
+def test_finalize_selection_of_a_large_search_set_is_array_work(vq, tmp_path, monkeypatch, n):
     """Finalize on a 1M-clip store with ~90k matches: select_clips_to_review (max = inf: a seeded permutation of every
     match and near miss, ticket.py:333,341) and the report order (stable descending sort of the selection, ticket.py:266,
     ranked on the device with vq_rank_list) against their plain-Python restatement on the device's scores, and the host
     time of both (the per-clip HTTP calls of persistence are the API's contract and are not part of this)."""
     import time
     import types
-    n, seed = 1_000_000, synth.DEFAULT_SEED
+    import torch
+    if n * 8192 * 1.05 > torch.cuda.get_device_properties(0).total_memory:
+        pytest.skip("device memory too small for %d clips" % n)
+    seed = synth.DEFAULT_SEED
     st = vq.FeatureStore(n, STREAMS, [1], 1024, devices=[0], clip_ids=np.arange(n) * 2 + 10)
     st.fill_synthetic(seed)
     T = sc.scale_target(synth.rows(seed, [18120]).astype(np.float64)[0][:, None, :])
@@ -1030,7 +1034,8 @@ def test_finalize_selection_of_a_large_search_set_is_array_work(vq, tmp_path, mo
     assert ranked == sorted(want.items(), key=lambda kv: kv[1], reverse=True)
     print("finalize on %d clips: %d selected; selection %.1f ms (scan included), report order %.1f ms"
           % (n, len(want), 1e3 * t_sel, 1e3 * t_rank))
-    assert t_sel + t_rank < 0.25, (t_sel, t_rank)      # the Python-object floor: two dicts of ~180k entries
+    if n == 1_000_000:
+        assert t_sel + t_rank < 0.25, (t_sel, t_rank)  # the Python-object floor: two dicts of ~150k entries
     st.close()
 
 
