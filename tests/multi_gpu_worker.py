@@ -133,6 +133,26 @@ def main():
         print("host mailbox and NCCL small exchanges agree: %s" % same)
     ok = ok and same
     rstore.close()
+    # a peer that never delivers must end the exchange kernel with an error, not wedge the GPU: the last rank skips a step
+    os.environ["VQ_EXCHANGE_TIMEOUT_S"] = "0.5"
+    rs_t = RankScan(st.shards[0].handle, k, local, dist, torch, exchange="p2p")
+    del os.environ["VQ_EXCHANGE_TIMEOUT_S"]
+    timed_out = None
+    if rank != world - 1:
+        rs_t.enqueue(target.data_ptr(), params, stream.cuda_stream)
+        rs_t.flush(stream.cuda_stream)
+        torch.cuda.synchronize()
+        try:
+            rs_t.result()
+            timed_out = False
+        except vq.VQError as e:
+            timed_out = "gave up" in str(e)
+    t_flag = torch.tensor([1 if timed_out in (True, None) else 0], device=dev)
+    dist.all_reduce(t_flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print("exchange deadline: a missing peer ends the kernel with an error: %s" % bool(t_flag.item()))
+    ok = ok and bool(t_flag.item())
+    rs_t.close()
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, src=0)
     st.close()

@@ -25,6 +25,7 @@ def test_sharded_scan_equals_single_gpu_scan():
     assert "rank store scan" in r.stdout and "rank store batched scan" in r.stdout and "rank store labelled sims" in r.stdout
     assert "rank store selection scan" in r.stdout and "host mailbox and NCCL small exchanges agree: True" in r.stdout
     assert "rank store sharded lists and root-only gather agree with the replicated lists: True" in r.stdout
+    assert "exchange deadline: a missing peer ends the kernel with an error: True" in r.stdout
 
 
 def _devices():
