@@ -7,7 +7,9 @@
 A step = one single-query pass of the hot path over every rank's resident shard of 1M synthetic
 clips (2 streams x 1024-d fp32 = 8192 B/clip, 8.19 GB per GPU > 126 MB L2, so no flush is needed):
 fused scan K1 (dots, fusion, score) + selection K2 (match / near-miss / tie lists in database
-order, exact top-100) and, for N > 1, one NCCL allgather of the per-rank payload + device merge.
+order, exact top-100) and, for N > 1, the peer-memory exchange kernel that merges the ranks' counts and top-k.
+`e2e` is the public call with host buffers: FeatureStore.scan (+ lists) — for N > 1 from ONE process that drives all
+N GPUs (the broker's arrangement, what compute_matches calls); the one-process-per-GPU arrangement is `e2e_ranks`.
 Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for every field.
 """
 from __future__ import annotations
@@ -530,6 +532,25 @@ def main():
                 traffic, traffic_src = int(tj["dram_bytes_per_launch"]), tj.get("source")
         except Exception:
             pass
+        # N = 1: the one call there is.  N > 1: the headline `e2e` is the broker's arrangement — ONE process drives all N GPUs
+        # through FeatureStore.scan -> vq_scan_multi, the call compute_matches makes, and ends with the WHOLE result (all
+        # lists) in one place like the N = 1 call; the one-process-per-GPU arrangement (RankStore; every rank keeps its
+        # segment of the lists) is reported beside it as e2e_ranks / e2e_ranks_select / e2e_root
+        ranks_e2e = {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                     "steps": e2e_steps, "what": e2e_what}
+        ranks_sel = {"value": e2e_select_value, "unit": "clips/s", "h2d_bytes_per_step": int(h2d + 19 * 8),
+                     "d2h_bytes_per_step": int(64 + TOPK * 12 + res.n_tie * 12 + 19 * 12), "steps": e2e_steps, "what": sel_what}
+        e2e_main, e2e_sel_main, e2e_ranks, e2e_ranks_sel = ranks_e2e, ranks_sel, None, None
+        if world > 1 and single is not None and single.get("value"):
+            e2e_main = {"value": single["value"], "unit": "clips/s", "h2d_bytes_per_step": int(h2d * world),
+                        "d2h_bytes_per_step": int(single["d2h_bytes_per_step"]), "steps": single["steps"],
+                        "ms_per_query": single["ms_per_query"], "what": single["what"]}
+            e2e_sel_main = {"value": single["select_value"], "unit": "clips/s", "h2d_bytes_per_step": int((h2d + 19 * 8) * world),
+                            "d2h_bytes_per_step": int((64 + TOPK * 12) * world + res.n_tie * 12 * world + 19 * 12), "steps": single["steps"],
+                            "ms_per_query": single["select_ms_per_query"],
+                            "what": "the review round in the same arrangement (one process, all GPUs): FeatureStore.scan(lists=False) + "
+                                    "topk + tie band + best near miss + ONE vq_gather_list_multi for the 19 sampled entries"}
+            e2e_ranks, e2e_ranks_sel = ranks_e2e, ranks_sel
         line = {
             "metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True,
@@ -545,11 +566,10 @@ def main():
                                  "K2a-c selection; exchange kernel timed by itself on the global timer — `overlapped`: inside the timed "
                                  "region, on its own stream beside the next step's K1 (off the scan stream's critical path); "
                                  "`alone`: the same kernel back to back on an idle GPU"),
-            "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": e2e_steps, "what": e2e_what},
-            "e2e_select": {"value": e2e_select_value, "unit": "clips/s", "h2d_bytes_per_step": int(h2d + 19 * 8),
-                           "d2h_bytes_per_step": int(64 + TOPK * 12 + res.n_tie * 12 + 19 * 12), "steps": e2e_steps,
-                           "what": sel_what},
+            "e2e": e2e_main,
+            "e2e_select": e2e_sel_main,
+            "e2e_ranks": e2e_ranks,
+            "e2e_ranks_select": e2e_ranks_sel,
             "e2e_root": e2e_root,
             "e2e_single_process": single,
             "e2e_cold": cold,
