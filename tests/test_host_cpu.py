@@ -528,6 +528,37 @@ def test_ticket_selection_reproduces_reference_rounds_on_recorded_scores(name):
             assert t.ranked_selection() == want
 
 
+def test_report_order_with_heavy_ties_and_forced_clips_outside_the_lists():
+    """Finalize selection + report order on scores with many exact ties (quantised) and with forced clips (the reference
+    clip, confirmed clips) below the near-miss band: Ticket.ranked_selection equals the reference's stable descending
+    sort of the selection dict (ticket.py:266) — equal scores keep the order in which the selection inserted them, an
+    extra clip comes after every listed clip of its score, extras of one score keep their own order."""
+    import types
+    from video_query_algorithms_b200 import Ticket
+    for seed in range(6):
+        rng = np.random.default_rng(seed)
+        n = 3000
+        scores = np.round(rng.uniform(0.4, 1.0, n), 2)              # ~60 distinct values: every score is shared by ~50 clips
+        ids = rng.permutation(n) + 100
+        low = np.flatnonzero(scores < 0.6)
+        confirmed = rng.choice(low, 25, replace=False)               # below the band (threshold .8, near .35 -> lower .73)
+        inband = rng.choice(np.flatnonzero(scores >= 0.75), 10, replace=False)
+        user = {str(int(ids[r])): True for r in np.concatenate([confirmed[:12], inband, confirmed[12:]])}
+        user.update({str(int(ids[r])): False for r in rng.choice(n, 20, replace=False) if str(int(ids[r])) not in user})
+        job = {"query_id": 1, "video_id": 1, "ref_clip": 0, "ref_clip_id": int(ids[low[0]]), "search_set": 1,
+               "number_of_matches_to_review": 20, "dynamic_target_adjustment": False, "user_matches": user}
+        t = Ticket(job, "http://fake/", client=object(), schema=object(), store=_ArrayStore(ids, scores))
+        t.target = types.SimpleNamespace(target_features={})
+        t._weights = {"rgb": 1.0, "warped_optical_flow": 1.5}
+        random.seed(a=seed)
+        t.select_clips_to_review(0.8, float("inf"), 0.35)
+        assert len(t.matches) > t._selection["n_listed"]             # some forced clips sit in neither list
+        want = sorted(t.matches.items(), key=lambda kv: kv[1], reverse=True)
+        assert t.ranked_selection() == want
+        r_ids, r_sc = t.ranked_selection_arrays()
+        assert list(zip(r_ids.tolist(), r_sc.tolist())) == want
+
+
 # ---------------------------------------------------------------------------- TargetClip (host logic)
 class _SolveStore:
     """Test double for the store calls TargetClip makes: rows by clip id, and `bootstrap_target` answered by the

@@ -14,6 +14,7 @@ API actions.  What changes is where the arithmetic runs:
 from __future__ import annotations
 
 import csv
+import itertools
 import json
 import logging
 import os
@@ -436,7 +437,13 @@ class Ticket:
                                "n_listed": len(sel_ids)}
 
     def ranked_selection(self):
-        """[(clip id, score)] of the last finalize selection in REPORT order: score descending, ties in the order the
+        """[(clip id, score)] of the last finalize selection in REPORT order (see ranked_selection_arrays); the list of
+        pairs costs one Python tuple per clip, so consumers that only walk the order take the arrays."""
+        r_ids, r_sc = self.ranked_selection_arrays()
+        return list(zip(r_ids.tolist(), r_sc.tolist()))
+
+    def ranked_selection_arrays(self):
+        """(clip ids, scores) of the last finalize selection in REPORT order: score descending, ties in the order the
         selection inserted the clips (the reference's stable sort of its dict's items, ticket.py:266).  The match and
         near-miss lists are ranked on the device (vq_rank_list, K7) with each entry's place in the selection order as the
         tie-break; forced clips that sit in neither list (a reference clip or a confirmed clip below the band) are few
@@ -465,14 +472,16 @@ class Ticket:
         r_sc = np.concatenate([sm, sn])
         listed = n_m + n_n
         if len(self.matches) > listed:                                         # forced clips outside both lists, in dict order
-            extra = list(self.matches.items())[listed:]
-            r_ids = np.concatenate([r_ids, np.array([c for c, _ in extra], dtype=r_ids.dtype)])
-            r_sc = np.concatenate([r_sc, np.array([v for _, v in extra], dtype=np.float32)])
-            # stable: an extra clip lands after every listed clip of equal score (it was inserted later); the listed part
-            # is already in order, so this is one merge pass
-            order = np.argsort(-r_sc.astype(np.float64), kind="stable")
-            r_ids, r_sc = r_ids[order], r_sc[order]
-        return list(zip(r_ids.tolist(), r_sc.tolist()))
+            extra = list(itertools.islice(self.matches.items(), listed, None))
+            x_ids = np.array([c for c, _ in extra], dtype=r_ids.dtype)
+            x_sc = np.array([v for _, v in extra], dtype=r_sc.dtype)
+            # an extra clip lands after every listed clip of equal score (it was inserted later) and extras of equal score
+            # keep their own order: a stable sort of the few extras, then one merge into the already ordered listed part
+            xo = np.argsort(-x_sc.astype(np.float64), kind="stable")
+            x_ids, x_sc = x_ids[xo], x_sc[xo]
+            at = np.searchsorted(-r_sc.astype(np.float64), -x_sc.astype(np.float64), side="right")
+            r_ids, r_sc = np.insert(r_ids, at, x_ids), np.insert(r_sc, at, x_sc)
+        return r_ids, r_sc
 
     def _score_of(self, clip):
         st = self.feature_store()
@@ -524,9 +533,10 @@ class Ticket:
         # report order = stable descending sort of the selection (ticket.py:266), ranked on the device for a finalize
         # selection; any other producer of self.matches gets the same order from the host sort below
         if getattr(self, "_selection", None) is not None and self._selection["n_listed"] <= len(self.matches):
-            ordered, presorted = self.ranked_selection(), True
+            r_ids, r_sc = self.ranked_selection_arrays()
+            ordered, presorted = zip(r_ids.tolist(), r_sc.tolist()), True
         else:
-            ordered, presorted = list(self.matches.items()), False
+            ordered, presorted = self.matches.items(), False
         rows = []
         for video_clip_id, score in ordered:
             label = self.user_matches.get(str(video_clip_id))
