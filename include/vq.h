@@ -180,6 +180,9 @@ typedef struct vq_exchange vq_exchange;
 int vq_exchange_create(vq_exchange **out, int device, int world, int rank);
 int vq_exchange_local_handle(vq_exchange *x, void *handle_out /* 64 bytes */);
 int vq_exchange_connect(vq_exchange *x, const void *all_handles /* [world][64] */);
+/* The same for exchanges that live in ONE process (all[r] = rank r's exchange; one per GPU with peer access between the
+ * devices, or several on one device): the inboxes are addressed directly, no IPC mapping.                      */
+int vq_exchange_connect_local(vq_exchange *const *all, int32_t world);
 int vq_exchange_destroy(vq_exchange *x);
 int vq_scan_exchange_enqueue(vq_store *s, vq_exchange *x, void *stream);
 /* A stream of queries: push this step's payload, merge the PREVIOUS step's (no rank waits for the slowest rank of the

@@ -452,6 +452,96 @@ def test_exchange_kernel_in_step_lagged_and_flush_on_one_rank(vq):
     st.close()
 
 
+@pytest.mark.parametrize("world,k", [(8, 100), (8, 1000), (3, 7), (16, 64), (20, 5)])
+def test_exchange_kernel_between_ranks_emulated_on_one_device(vq, world, k):
+    """The multi-block exchange kernel between `world` ranks that all live on device 0 (vq_exchange_connect_local: one
+    process, inboxes addressed directly), so that a single-GPU box runs what tests/test_gpu_multi.py runs over NVLink:
+    every rank pushes into every inbox, waits for every flag and merges; each rank's merged result must equal one scan
+    of the whole search set — counts summed, global top-k under (score desc, global row asc).  The search set has many
+    exact ties inside and across ranks (rows drawn with repetition), ranks shorter than k, a one-row and an empty rank;
+    k = 1000 at world 8 takes the merge that reads the inbox directly (candidates do not fit in shared memory); world 20
+    has more ranks than blocks.  In-step and lagged mode, six steps each (every inbox slot reused), then the flush."""
+    import ctypes as C
+    import torch
+    from video_query_algorithms_b200 import _ffi
+    from video_query_algorithms_b200.store import make_params
+    from video_query_algorithms_b200.sharded import _DevArray, unpack_payload
+    lib = _ffi.lib()
+    rng = np.random.default_rng(world * 1000 + k)
+    base = synth.rows(7, np.arange(1500))                                     # [1500, 2, 1024] fp32
+    sizes = [700, 1, 0, 300, 50, 700, 650, 12] + [int(v) for v in rng.integers(1, 400, 32)]
+    sizes = sizes[:world]
+    picks = [rng.integers(0, len(base), n_r) for n_r in sizes]
+    firsts = np.concatenate([[0], np.cumsum(sizes)])
+    total = int(firsts[-1])
+    full = vq.FeatureStore(total, STREAMS, [1], 1024, devices=[0])
+    full.upload(0, base[np.concatenate(picks)][:, :, None, :])
+    stores = []
+    for r in range(world):
+        st = vq.FeatureStore(sizes[r], STREAMS, [1], 1024, devices=[0], first_global_row=int(firsts[r]))
+        if sizes[r]:
+            st.upload(0, base[picks[r]][:, :, None, :])
+        stores.append(st)
+    T = sc.scale_target(base[3].astype(np.float64)[:, None, :])
+    target = torch.from_numpy(T.astype(np.float32).reshape(-1)).to("cuda:0")
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    xs = (C.c_void_p * world)()
+    for r in range(world):
+        x = C.c_void_p()
+        _ffi.check(lib.vq_exchange_create(C.byref(x), 0, world, r), "vq_exchange_create")
+        xs[r] = x
+    _ffi.check(lib.vq_exchange_connect_local(xs, world), "vq_exchange_connect_local")
+    views = []
+    for r in range(world):
+        mp = C.c_void_p()
+        _ffi.check(lib.vq_exchange_merged(xs[r], C.byref(mp)), "vq_exchange_merged")
+        views.append(torch.as_tensor(_DevArray(mp.value, 4 + 2 * k), device=torch.device("cuda", 0)))
+
+    def expected(th):
+        res = full.scan(tdict(T), (1.0, 1.5), th, 0.6, EPS, topk=k)
+        rows, scores = full.topk()
+        return (res.n_match, res.n_near, res.n_tie), rows.copy(), scores.copy()
+
+    ths = [0.70 + 0.02 * i for i in range(6)]
+    want = [expected(th) for th in ths]
+    assert len(np.unique(want[0][2])) < len(want[0][2])                      # the top-k holds exact ties
+
+    def check_all(j, what):
+        torch.cuda.synchronize()
+        for r in range(world):
+            _ffi.check(lib.vq_exchange_check(xs[r]), "vq_exchange_check")
+            counts, rows, scores = unpack_payload(views[r].cpu().numpy(), k)
+            assert tuple(int(c) for c in counts[:3]) == want[j][0], (what, r, counts)
+            assert np.array_equal(rows, want[j][1]) and np.array_equal(scores, want[j][2]), (what, r)
+
+    for lagged in (False, True):
+        fn = lib.vq_scan_exchange_enqueue_lagged if lagged else lib.vq_scan_exchange_enqueue
+        for i, th in enumerate(ths):
+            p = make_params((1.0, 1.5), th, 0.6, EPS, topk=k)
+            for r in range(world):                                            # nothing here waits on the host: all ranks' kernels are in flight together
+                sp = C.c_void_p(streams[r].cuda_stream)
+                _ffi.check(lib.vq_scan_enqueue(stores[r].shards[0].handle, C.c_void_p(target.data_ptr()), C.byref(p), sp), "enqueue")
+                _ffi.check(fn(stores[r].shards[0].handle, xs[r], sp), "exchange")
+            if not lagged:
+                check_all(i, "in-step %d" % i)
+            elif i in (2, 5):
+                check_all(i - 1, "lagged %d" % i)
+        for r in range(world):
+            _ffi.check(lib.vq_exchange_flush_enqueue(xs[r], C.c_void_p(streams[r].cuda_stream)), "flush")
+        check_all(len(ths) - 1, "flush")
+    times = np.empty(256, np.float32)
+    parts = np.empty((256, 3), np.float32)
+    n_t = C.c_int32()
+    _ffi.check(lib.vq_exchange_kernel_times(xs[0], 256, _ffi.ptr(times), _ffi.ptr(parts), C.byref(n_t)), "vq_exchange_kernel_times")
+    assert n_t.value >= 12 and (times[:n_t.value] > 0).all() and (parts[:n_t.value] >= 0).all()
+    print("exchange kernel, world %d on one device, k %d: median %.1f us" % (world, k, 1e3 * float(np.median(times[:n_t.value]))))
+    for r in range(world):
+        _ffi.check(lib.vq_exchange_destroy(xs[r]), "vq_exchange_destroy")
+    for st in stores:
+        st.close()
+    full.close()
+
+
 # ---------------------------------------------------------------------------- batched queries (tcgen05)
 @pytest.mark.parametrize("n,nq", [(5003, 70), (300, 3), (20000, 300)])
 def test_batched_tensor_core_scan_matches_oracle(vq, n, nq):

@@ -85,6 +85,7 @@ PROTOTYPES = {
     "vq_exchange_create": (C.c_int, [_P(_vp), C.c_int, C.c_int, C.c_int]),
     "vq_exchange_local_handle": (C.c_int, [_vp, _vp]),
     "vq_exchange_connect": (C.c_int, [_vp, _vp]),
+    "vq_exchange_connect_local": (C.c_int, [_vp, _i32]),
     "vq_exchange_destroy": (C.c_int, [_vp]),
     "vq_scan_exchange_enqueue": (C.c_int, [_vp, _vp, _vp]),
     "vq_scan_exchange_enqueue_lagged": (C.c_int, [_vp, _vp, _vp]),

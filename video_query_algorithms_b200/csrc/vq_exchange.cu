@@ -1,8 +1,8 @@
 // C1' — peer-memory exchange of the per-rank scan payload, fused with the merge (one process per GPU).
 //
 // The only cross-GPU step of the path is the merge of per-rank results (counts + top-k, 1.6 KB at
-// k = 100).  Instead of an NCCL allgather followed by a merge kernel, each rank runs ONE single-block
-// kernel right behind its selection kernels: it stores its payload straight into every peer's inbox over
+// k = 100).  Instead of an NCCL allgather followed by a merge kernel, each rank runs ONE small kernel (a block
+// per rank) right behind its selection kernels: it stores its payload straight into every peer's inbox over
 // NVLink (peer pointers obtained through CUDA IPC), publishes a sequence flag with system-scope release
 // semantics, waits for the flags of all peers in its own inbox and merges.
 // Two modes.  In-step: kernel i pushes payload i and merges step i (a rank cannot get two steps ahead, because
@@ -11,7 +11,8 @@
 // the current step, ranks may drift by one step, and a flush kernel merges the last step.  Four inbox slots
 // (sequence mod 4) make the lagged mode safe: push i overwrites the slot of step i-4, which a peer reads in its
 // kernel i-3; before kernel i starts, this rank's kernel i-1 has seen every peer's flag i-2, i.e. every peer has
-// entered its kernel i-2 and therefore finished its kernel i-3.
+// entered its kernel i-2 and therefore finished its kernel i-3 (in lagged mode a flag is raised at the END of the kernel,
+// after the merge, which only strengthens this).
 #include <stdlib.h>
 #include <string.h>
 
@@ -23,9 +24,10 @@ struct vq_exchange {
     long long *peer_inbox[64] = {nullptr};      // mapped inboxes of all ranks (own = inbox)
     long long **peer_table_dev = nullptr;       // device copy of peer_inbox
     long long *merged = nullptr;                // [kSlot]
-    long long *scratch = nullptr;               // [world][kSlot] private copy of the gathered payloads (merges too large for shared memory)
+    unsigned long long *sync = nullptr;         // [4 + 4 * kMaxBlocks]: the exchange kernel's completion ticket, error mark and per-block times
     unsigned long long seq = 0;
     bool connected = false;
+    bool ipc_mapped = false;                    // peer_inbox entries are IPC mappings to close (vq_exchange_connect)
     bool unmerged = false;                      // lagged mode: the last pushed step has not been merged yet
     int topk = 0;
     cudaStream_t stream = nullptr;              // the scan stream of the last enqueue
@@ -34,7 +36,8 @@ struct vq_exchange {
     // before the next select_compact overwrites the payload (vq_store::pack_reader_done).
     cudaStream_t side = nullptr;
     cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
-    unsigned long long *t_ring = nullptr;       // pinned, device-mapped [256][4]: start, pushes done, peers' flags seen, end of each exchange kernel (global timer, ns)
+    unsigned long long *t_ring = nullptr;       // pinned, device-mapped [256][kMaxBlocks][4]: start, pushes done, peers' flags seen, end of each block of each exchange kernel (global timer, ns)
+    int blocks = 1;                             // blocks per exchange kernel
     int ev_head = 0, ev_count = 0;
     double timeout_s = 10.0;                    // a peer that never arrives ends the kernel with an error marker instead of a hang
 };
@@ -44,6 +47,7 @@ constexpr int kSlot = 4 + 2 * VQ_MAX_TOPK;      // int64 per payload slot
 constexpr int kSlots = 4;                       // inbox slots (sequence number mod 4)
 constexpr int kRing = 256;
 constexpr int kXThreads = 128;                   // see exchange_push_merge
+constexpr int kMaxBlocks = 16;                   // blocks of one exchange kernel (one per rank up to here)
 constexpr int kMergeShared = 4096;              // candidates (world * k) merged out of shared memory
 __host__ __device__ inline size_t flags_offset(int world) { return (size_t)kSlots * world * kSlot; }
 
@@ -73,12 +77,12 @@ __device__ __forceinline__ bool before(float sa, long long ra, float sb, long lo
 
 // Merge of `world` ranked lists (each sorted under `before`, entries distinct): the rank of entry i of list l in the
 // merged order is i + sum over the other lists of the number of their entries that come before it — one binary search
-// per other list, O(world * log k) per entry instead of the O(world * k) comparisons of a rank count.
-template <class RowPtr, class ScorePtr>
-__device__ __forceinline__ void merge_ranked(RowPtr rows, ScorePtr scs, const int *len, const int world, const int k,
-                                             const int stride, long long *merged) {
-    const int n = world * k;
-    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+// per other list, O(world * log k) per entry instead of the O(world * k) comparisons of a rank count.  This block takes
+// the entries [e_begin, e_end) of the world * k candidates; the blocks of the grid share the work.
+template <class Rows, class Scores>
+__device__ __forceinline__ void merge_ranked(Rows rows, Scores scs, const int *len, const int world, const int k,
+                                             const int stride, const int e_begin, const int e_end, long long *merged) {
+    for (int e = e_begin + threadIdx.x; e < e_end; e += blockDim.x) {
         const int l = e / k, i = e - l * k;
         if (i >= len[l]) continue;
         const float sc = scs[l * stride + i];
@@ -101,121 +105,182 @@ __device__ __forceinline__ void merge_ranked(RowPtr rows, ScorePtr scs, const in
     }
 }
 
-// One block of kXThreads = 128 threads at <= 48 registers: small enough to be co-resident with the scan kernel of the NEXT
-// step (K1 keeps 3 blocks of 128 threads x 150 registers on every SM, which leaves 7168 registers per SM), so that it runs
-// as soon as its inputs are ready instead of queueing behind a 1.1 ms scan.  t_ns (when not null) receives the kernel's
-// own start and end on the global timer: CUDA events around a kernel on a side stream would also count the time it
-// waits for an SM.
-// Two alternatives were measured and dropped (8 B200s, world 8, k 100, merge phase alone: 25.6 us for the version above):
-// a one-warp k-way merge of the list heads (k sequential steps of a shuffle butterfly; 31 us already at world 2 — a dependent
-// chain with nothing to hide its latency behind) and eight lists' searches in lockstep with a fixed step count (49.8 us — it
-// gives up the early exit above, which ends most entries after one or two lists because their rank already exceeds k).
-__global__ void __launch_bounds__(kXThreads, 10)
+// candidates read straight from the inbox (merges too large for shared memory): every access is one volatile load
+struct InboxRows {
+    const long long *p;
+    __device__ __forceinline__ long long operator[](int i) const { return ld_volatile(p + i); }
+};
+struct InboxScores {
+    const long long *p;
+    __device__ __forceinline__ float operator[](int i) const { return __uint_as_float((unsigned int)ld_volatile(p + i)); }
+};
+
+// A few blocks (one per rank, at most kMaxBlocks) of kXThreads = 128 threads at <= 48 registers: each small enough to be
+// co-resident with the scan kernel of the NEXT step (K1 keeps 3 blocks of 128 threads x 150 registers on every SM, which
+// leaves 7168 registers per SM), so that the kernel runs as soon as its inputs are ready instead of queueing behind a
+// 1.1 ms scan.  Block b stores the payload into the inboxes of the ranks r with r mod grid = b, every block waits for the
+// peers' flags by itself and stages all lists in its own shared memory, then ranks its share of the world * k candidates
+// (one candidate per thread at world 8, k 100), pads its share of the tail and leaves its own times; block 0 also sums
+// the counts.  No block waits for another.  Round 2's single block took 32 us at world 8 (6.7 us for eight peers' stores and one fence,
+// 25.6 us for the merge: 6 candidates x 7 searches per thread, a dependent chain of shared-memory reads).
+// When the step to merge is not the step pushed (lagged mode) the payloads to merge arrived a scan ago: the stores to the
+// peers are issued first, the merge runs while they travel, and the fence + flag follow it.
+// t_ns (when not null) receives every block's own start, end of pushes, end of waiting and end on the global timer: CUDA
+// events around a kernel on a side stream would also count the time it waits for an SM.
+// Alternatives measured and dropped in round 2 (8 B200s, world 8, k 100, one block): a one-warp k-way merge of the list
+// heads (k sequential steps of a shuffle butterfly; 31 us already at world 2 — a dependent chain with nothing to hide its
+// latency behind) and eight lists' searches in lockstep with a fixed step count (49.8 us — it gives up the early exit
+// above, which ends most entries after one or two lists because their rank already exceeds k).
+__global__ void __launch_bounds__(kXThreads, 9)    // <= 56 registers: 128 x 56 = the 7168 registers K1 leaves free per SM
 exchange_push_merge(const long long *__restrict__ payload, long long *const *__restrict__ peers, const int world,
                     const int rank, const int k, const unsigned long long push_seq /* 0: nothing to push */,
-                    const unsigned long long merge_seq /* 0: nothing to merge */, long long *merged, long long *scratch,
+                    const unsigned long long merge_seq /* 0: nothing to merge */, long long *merged,
+                    unsigned long long *sync /* [1]: sticky mark left by a block that gave up waiting */,
                     const unsigned long long timeout_ns, unsigned long long *t_ns) {
     const unsigned long long t_begin = global_ns();
     extern __shared__ long long sm_rows[];          // [world * k] rows, then [world * k] fp32 scores (when they fit)
     __shared__ int len_s[64];
     __shared__ int timed_out;
     const int n_pay = 4 + 2 * k;
+    const int nb = (int)gridDim.x, b = (int)blockIdx.x;
+    const bool flag_late = push_seq && merge_seq && push_seq != merge_seq;
+    unsigned long long ns_push = 0, ns_wait = 0;
+
+    // 1. my payload into slot [push_seq mod 4][rank] of the inboxes this block serves (own included)
+    const int push_slot = (int)(push_seq % kSlots);
     if (push_seq) {
-        // 1. push my payload into slot [push_seq mod 4][rank] of every inbox (own included)
-        const int slot = (int)(push_seq % kSlots);
-        for (int i = threadIdx.x; i < n_pay * world; i += blockDim.x) {
-            const int r = i / n_pay, j = i - r * n_pay;
-            peers[r][((size_t)slot * world + rank) * kSlot + j] = payload[j];
-        }
+        for (int r = b; r < world; r += nb)
+            for (int j = threadIdx.x; j < n_pay; j += blockDim.x)
+                peers[r][((size_t)push_slot * world + rank) * kSlot + j] = payload[j];
+    }
+    auto raise_flags = [&]() {
         __threadfence_system();
         __syncthreads();
-        if (threadIdx.x < world) {
-            unsigned long long *flag =
-                reinterpret_cast<unsigned long long *>(peers[threadIdx.x] + flags_offset(world)) + (size_t)slot * world + rank;
+        if (threadIdx.x < world && (int)threadIdx.x % nb == b) {
+            unsigned long long *flag = reinterpret_cast<unsigned long long *>(peers[threadIdx.x] + flags_offset(world)) +
+                                       (size_t)push_slot * world + rank;
             st_release_sys(flag, push_seq);
         }
-    }
-    const unsigned long long t_pushed = global_ns();
-    if (!merge_seq) {
-        if (t_ns && threadIdx.x == 0) { t_ns[0] = t_begin; t_ns[1] = t_pushed; t_ns[2] = t_pushed; t_ns[3] = global_ns(); }
-        return;
-    }
-    // 2. wait until every rank's payload for the sequence number to merge has landed in my inbox; a peer that has died
-    //    or fallen out of step must not wedge the GPU: past the deadline the kernel leaves an error marker and ends
-    const int slot = (int)(merge_seq % kSlots);
-    long long *mine = peers[rank];
+    };
+    if (push_seq && !flag_late) raise_flags();
+    ns_push = global_ns() - t_begin;
+
     if (threadIdx.x == 0) timed_out = 0;
     __syncthreads();
-    if (threadIdx.x < world) {
-        const unsigned long long *flag =
-            reinterpret_cast<const unsigned long long *>(mine + flags_offset(world)) + (size_t)slot * world + threadIdx.x;
+    if (merge_seq) {
+        // 2. wait until every rank's payload for the sequence number to merge has landed in my inbox; a peer that has
+        //    died or fallen out of step must not wedge the GPU: past the deadline the kernel leaves an error mark and ends
+        const int slot = (int)(merge_seq % kSlots);
+        long long *mine = peers[rank];
         const unsigned long long t0 = global_ns();
-        while (ld_acquire_sys(flag) != merge_seq) {
-            __nanosleep(64);
-            if (global_ns() - t0 > timeout_ns) { timed_out = 1; break; }
-        }
-    }
-    __syncthreads();
-    const unsigned long long t_seen = global_ns();
-    if (timed_out) {
-        if (threadIdx.x < 4) merged[threadIdx.x] = -1;         // counts < 0: vq_exchange_check / the host reader raise
-        return;
-    }
-    // 3. counts summed; global top-k by merging the ranks' ranked lists (peer-written memory is read once, bypassing L1)
-    const long long *g = mine + (size_t)slot * world * kSlot;
-    if (threadIdx.x < world) len_s[threadIdx.x] = (int)ld_volatile(g + (size_t)threadIdx.x * kSlot + 3);
-    if (threadIdx.x < 3) {
-        long long t = 0;
-        for (int l = 0; l < world; ++l) t += ld_volatile(g + (size_t)l * kSlot + threadIdx.x);
-        merged[threadIdx.x] = t;
-    }
-    for (int i = threadIdx.x; i < k; i += blockDim.x) {
-        merged[4 + i] = -1;
-        merged[4 + k + i] = (long long)0xff800000u;
-    }
-    const int n = world * k;
-    if (n <= kMergeShared) {
-        float *sm_sc = reinterpret_cast<float *>(sm_rows + n);
-        // all of a thread's loads are issued before the first one is used (each is a full round trip to L2 / HBM)
-        constexpr int kBatch = 8;
-        for (int e0 = threadIdx.x; e0 < n; e0 += blockDim.x * kBatch) {
-            long long r[kBatch], sb[kBatch];
-#pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
-                const int e = e0 + u * blockDim.x;
-                if (e < n) {
-                    const int l = e / k, i = e - l * k;
-                    r[u] = ld_volatile(g + (size_t)l * kSlot + 4 + i);
-                    sb[u] = ld_volatile(g + (size_t)l * kSlot + 4 + k + i);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < kBatch; ++u) {
-                const int e = e0 + u * blockDim.x;
-                if (e < n) {
-                    sm_rows[e] = r[u];
-                    sm_sc[e] = __uint_as_float((unsigned int)sb[u]);
-                }
+        if (threadIdx.x < world) {
+            const unsigned long long *flag =
+                reinterpret_cast<const unsigned long long *>(mine + flags_offset(world)) + (size_t)slot * world + threadIdx.x;
+            while (ld_acquire_sys(flag) != merge_seq) {
+                __nanosleep(64);
+                if (global_ns() - t0 > timeout_ns) { timed_out = 1; break; }
             }
         }
         __syncthreads();
-        merge_ranked(sm_rows, sm_sc, len_s, world, k, k, merged);
-    } else {
-        float *g_sc = reinterpret_cast<float *>(scratch + n);
-        for (int e = threadIdx.x; e < n; e += blockDim.x) {
-            const int l = e / k, i = e - l * k;
-            scratch[e] = ld_volatile(g + (size_t)l * kSlot + 4 + i);
-            g_sc[e] = __uint_as_float((unsigned int)ld_volatile(g + (size_t)l * kSlot + 4 + k + i));
+        ns_wait = global_ns() - t0;
+        if (!timed_out) {
+            // 3. global top-k by merging the ranks' ranked lists (peer-written memory is read once, bypassing L1)
+            const long long *g = mine + (size_t)slot * world * kSlot;
+            // (the lists' lengths are requested first and stored after the staging loads have been issued: one round trip)
+            long long len_r = 0;
+            if (threadIdx.x < world) len_r = ld_volatile(g + (size_t)threadIdx.x * kSlot + 3);
+            const int n = world * k;
+            const int per = (n + nb - 1) / nb;
+            const int e_begin = b * per, e_end = e_begin + per < n ? e_begin + per : n;
+            if (n <= kMergeShared) {
+                float *sm_sc = reinterpret_cast<float *>(sm_rows + n);
+                // all of a thread's loads are issued before the first one is used (each is a full round trip to L2 / HBM)
+                constexpr int kBatch = 8;
+                for (int e0 = threadIdx.x; e0 < n; e0 += blockDim.x * kBatch) {
+                    long long r[kBatch], sb[kBatch];
+#pragma unroll
+                    for (int u = 0; u < kBatch; ++u) {
+                        const int e = e0 + u * blockDim.x;
+                        if (e < n) {
+                            const int l = e / k, i = e - l * k;
+                            r[u] = ld_volatile(g + (size_t)l * kSlot + 4 + i);
+                            sb[u] = ld_volatile(g + (size_t)l * kSlot + 4 + k + i);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < kBatch; ++u) {
+                        const int e = e0 + u * blockDim.x;
+                        if (e < n) {
+                            sm_rows[e] = r[u];
+                            sm_sc[e] = __uint_as_float((unsigned int)sb[u]);
+                        }
+                    }
+                }
+                if (threadIdx.x < world) len_s[threadIdx.x] = (int)len_r;
+                __syncthreads();
+                merge_ranked(sm_rows, sm_sc, len_s, world, k, k, e_begin, e_end, merged);
+            } else {
+                if (threadIdx.x < world) len_s[threadIdx.x] = (int)len_r;
+                __syncthreads();
+                merge_ranked(InboxRows{g + 4}, InboxScores{g + 4 + k}, len_s, world, k, kSlot, e_begin, e_end, merged);
+            }
         }
-        __syncthreads();
-        merge_ranked(scratch, g_sc, len_s, world, k, k, merged);
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        long long tot = 0;
-        for (int l = 0; l < world; ++l) tot += len_s[l];
-        merged[3] = tot < k ? tot : k;
-        if (t_ns) { t_ns[0] = t_begin; t_ns[1] = t_pushed; t_ns[2] = t_seen; t_ns[3] = global_ns(); }
+    if (flag_late) raise_flags();
+
+    // 4. close the step: block 0 sums the counts (one lane per rank, shuffle reduction), every block pads its share of the
+    //    tail; a block that gave up leaves the sticky error mark; every block leaves its own times
+    if (merge_seq) {
+        if (timed_out) {
+            if (threadIdx.x == 0) sync[1] = merge_seq;         // sticky: vq_exchange_check reports and clears it
+            if (threadIdx.x < 4) merged[threadIdx.x] = -1;
+        } else {
+            int tot = 0;
+            for (int l = 0; l < world; ++l) tot += len_s[l];
+            const int filled = tot < k ? tot : k;
+            for (int i = filled + b * (int)blockDim.x + (int)threadIdx.x; i < k; i += nb * (int)blockDim.x) {
+                merged[4 + i] = -1;
+                merged[4 + k + i] = (long long)0xff800000u;
+            }
+            if (b == 0 && threadIdx.x < 32) {
+                const long long *g = peers[rank] + (size_t)(merge_seq % kSlots) * world * kSlot;
+                const int l0 = (int)threadIdx.x, l1 = l0 + 32;
+                long long c0 = 0, c1 = 0, c2 = 0, d0 = 0, d1 = 0, d2 = 0;
+                if (l0 < world) {
+                    c0 = ld_volatile(g + (size_t)l0 * kSlot);
+                    c1 = ld_volatile(g + (size_t)l0 * kSlot + 1);
+                    c2 = ld_volatile(g + (size_t)l0 * kSlot + 2);
+                }
+                if (l1 < world) {
+                    d0 = ld_volatile(g + (size_t)l1 * kSlot);
+                    d1 = ld_volatile(g + (size_t)l1 * kSlot + 1);
+                    d2 = ld_volatile(g + (size_t)l1 * kSlot + 2);
+                }
+                c0 += d0; c1 += d1; c2 += d2;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    c0 += __shfl_xor_sync(0xffffffffu, c0, o);
+                    c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+                    c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+                }
+                if (threadIdx.x == 0) {
+                    merged[0] = c0;
+                    merged[1] = c1;
+                    merged[2] = c2;
+                    merged[3] = filled;
+                }
+            }
+        }
+    }
+    if (t_ns) {
+        __syncthreads();                                       // the block's last stores are issued
+        if (threadIdx.x == 0) {
+            unsigned long long *t = t_ns + 4 * b;
+            t[0] = t_begin;
+            t[1] = t_begin + ns_push;
+            t[2] = t_begin + ns_push + ns_wait;
+            t[3] = global_ns();
+        }
     }
 }
 }  // namespace
@@ -231,7 +296,7 @@ extern "C" int vq_exchange_create(vq_exchange **out, int device, int world, int 
     x->rank = rank;
     const size_t bytes = (flags_offset(world) + (size_t)kSlots * world) * sizeof(long long);
     if (cudaMalloc((void **)&x->inbox, bytes) != cudaSuccess || cudaMalloc((void **)&x->merged, kSlot * 8) != cudaSuccess ||
-        cudaMalloc((void **)&x->scratch, (size_t)world * kSlot * 8) != cudaSuccess ||
+        cudaMalloc((void **)&x->sync, (4 + 4 * kMaxBlocks) * sizeof(unsigned long long)) != cudaSuccess ||
         cudaMalloc((void **)&x->peer_table_dev, 64 * sizeof(long long *)) != cudaSuccess) {
         vq::set_error("vq_exchange_create: cudaMalloc failed");
         delete x;
@@ -239,6 +304,7 @@ extern "C" int vq_exchange_create(vq_exchange **out, int device, int world, int 
     }
     VQ_CUDA(cudaMemset(x->inbox, 0, bytes));
     VQ_CUDA(cudaMemset(x->merged, 0, kSlot * 8));
+    VQ_CUDA(cudaMemset(x->sync, 0, (4 + 4 * kMaxBlocks) * sizeof(unsigned long long)));
     x->peer_inbox[rank] = x->inbox;
     const char *ss = getenv("VQ_EXCHANGE_SIDE_STREAM");
     if (!ss || atoi(ss) != 0) {
@@ -246,8 +312,9 @@ extern "C" int vq_exchange_create(vq_exchange **out, int device, int world, int 
         VQ_CUDA(cudaEventCreateWithFlags(&x->ev_ready, cudaEventDisableTiming));
         VQ_CUDA(cudaEventCreateWithFlags(&x->ev_done, cudaEventDisableTiming));
     }
-    VQ_CUDA(cudaMallocHost((void **)&x->t_ring, kRing * 4 * sizeof(unsigned long long)));
-    memset(x->t_ring, 0, kRing * 4 * sizeof(unsigned long long));
+    VQ_CUDA(cudaMallocHost((void **)&x->t_ring, (size_t)kRing * kMaxBlocks * 4 * sizeof(unsigned long long)));
+    memset(x->t_ring, 0, (size_t)kRing * kMaxBlocks * 4 * sizeof(unsigned long long));
+    x->blocks = world < kMaxBlocks ? world : kMaxBlocks;
     if (const char *t = getenv("VQ_EXCHANGE_TIMEOUT_S")) x->timeout_s = atof(t) > 0 ? atof(t) : x->timeout_s;
     cudaFuncSetAttribute(exchange_push_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, kMergeShared * 12);
     *out = x;
@@ -277,6 +344,32 @@ extern "C" int vq_exchange_connect(vq_exchange *x, const void *all_handles /* [w
     }
     VQ_CUDA(cudaMemcpy(x->peer_table_dev, x->peer_inbox, 64 * sizeof(long long *), cudaMemcpyHostToDevice));
     x->connected = true;
+    x->ipc_mapped = true;
+    return 0;
+}
+
+extern "C" int vq_exchange_connect_local(vq_exchange *const *all, int32_t world) {
+    VQ_REQUIRE(all && world >= 1 && world <= 64, "vq_exchange_connect_local: null argument or world %d", world);
+    for (int r = 0; r < world; ++r)
+        VQ_REQUIRE(all[r] && all[r]->world == world && all[r]->rank == r && !all[r]->connected,
+                   "vq_exchange_connect_local: entry %d is not the unconnected exchange of rank %d of %d", r, r, world);
+    for (int r = 0; r < world; ++r) {
+        vq_exchange *x = all[r];
+        VQ_CUDA(cudaSetDevice(x->device));
+        for (int p = 0; p < world; ++p) {
+            if (all[p]->device != x->device) {
+                int can = 0;
+                VQ_CUDA(cudaDeviceCanAccessPeer(&can, x->device, all[p]->device));
+                VQ_REQUIRE(can, "vq_exchange_connect_local: device %d cannot address device %d", x->device, all[p]->device);
+                const cudaError_t e = cudaDeviceEnablePeerAccess(all[p]->device, 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                else VQ_CUDA(e);
+            }
+            x->peer_inbox[p] = all[p]->inbox;
+        }
+        VQ_CUDA(cudaMemcpy(x->peer_table_dev, x->peer_inbox, 64 * sizeof(long long *), cudaMemcpyHostToDevice));
+        x->connected = true;
+    }
     return 0;
 }
 
@@ -284,7 +377,7 @@ extern "C" int vq_exchange_destroy(vq_exchange *x) {
     if (!x) return 0;
     cudaSetDevice(x->device);
     cudaDeviceSynchronize();
-    for (int r = 0; r < x->world; ++r)
+    for (int r = 0; r < x->world && x->ipc_mapped; ++r)
         if (r != x->rank && x->peer_inbox[r]) cudaIpcCloseMemHandle(x->peer_inbox[r]);
     if (x->t_ring) cudaFreeHost(x->t_ring);
     if (x->ev_ready) cudaEventDestroy(x->ev_ready);
@@ -292,7 +385,7 @@ extern "C" int vq_exchange_destroy(vq_exchange *x) {
     if (x->side) cudaStreamDestroy(x->side);
     cudaFree(x->inbox);
     cudaFree(x->merged);
-    cudaFree(x->scratch);
+    cudaFree(x->sync);
     cudaFree(x->peer_table_dev);
     delete x;
     return 0;
@@ -315,9 +408,10 @@ static int launch_exchange(vq_exchange *x, vq_store *s, cudaStream_t scan_st, co
     const int slot = x->ev_head;
     x->ev_head = (x->ev_head + 1) % kRing;
     if (x->ev_count < kRing) x->ev_count++;
-    exchange_push_merge<<<1, kXThreads, merge_smem(x->world, x->topk), run>>>(
-        payload, x->peer_table_dev, x->world, x->rank, x->topk, push_seq, merge_seq, x->merged, x->scratch,
-        (unsigned long long)(x->timeout_s * 1e9), x->t_ring + 4 * slot);
+    memset(x->t_ring + (size_t)slot * kMaxBlocks * 4, 0, (size_t)kMaxBlocks * 4 * sizeof(unsigned long long));
+    exchange_push_merge<<<x->blocks, kXThreads, merge_smem(x->world, x->topk), run>>>(
+        payload, x->peer_table_dev, x->world, x->rank, x->topk, push_seq, merge_seq, x->merged, x->sync,
+        (unsigned long long)(x->timeout_s * 1e9), x->t_ring + (size_t)slot * kMaxBlocks * 4);
     VQ_CUDA(cudaGetLastError());
     if (x->side && s) {                              // the next select_compact on this store waits for this kernel before it rewrites the payload
         if (!s->pack_reader_done) VQ_CUDA(cudaEventCreateWithFlags(&s->pack_reader_done, cudaEventDisableTiming));
@@ -385,13 +479,26 @@ extern "C" int vq_exchange_kernel_times(vq_exchange *x, int32_t cap, float *ms_o
     int got = 0;
     for (int i = 0; i < n; ++i) {
         const int slot = (x->ev_head + kRing - n + i) % kRing;
-        const unsigned long long *t = x->t_ring + 4 * slot;
-        if (t[3] >= t[0] && t[0] != 0 && ms_out) {
-            ms_out[got] = (float)((double)(t[3] - t[0]) * 1e-6);
-            if (parts_out) {                                 // push | wait for the peers | merge
-                parts_out[3 * got] = (float)((double)(t[1] - t[0]) * 1e-6);
-                parts_out[3 * got + 1] = (float)((double)(t[2] - t[1]) * 1e-6);
-                parts_out[3 * got + 2] = (float)((double)(t[3] - t[2]) * 1e-6);
+        const unsigned long long *t = x->t_ring + (size_t)slot * kMaxBlocks * 4;
+        // the kernel = its blocks: first start to last end; pushes / waiting = the slowest block's
+        unsigned long long t0 = 0, t3 = 0, push = 0, wait = 0;
+        bool complete = true;
+        for (int b = 0; b < x->blocks; ++b) {
+            const unsigned long long *tb = t + 4 * b;
+            if (tb[0] == 0 || tb[3] < tb[0]) { complete = false; break; }
+            if (b == 0 || tb[0] < t0) t0 = tb[0];
+            if (tb[3] > t3) t3 = tb[3];
+            if (tb[1] - tb[0] > push) push = tb[1] - tb[0];
+            if (tb[2] - tb[1] > wait) wait = tb[2] - tb[1];
+        }
+        if (complete && ms_out) {
+            const double total = (double)(t3 - t0);
+            ms_out[got] = (float)(total * 1e-6);
+            if (parts_out) {                                 // push | wait for the peers | merge and the rest
+                parts_out[3 * got] = (float)((double)push * 1e-6);
+                parts_out[3 * got + 1] = (float)((double)wait * 1e-6);
+                const double rest = total - (double)push - (double)wait;
+                parts_out[3 * got + 2] = (float)((rest > 0 ? rest : 0) * 1e-6);
             }
             ++got;
         }
@@ -406,8 +513,11 @@ extern "C" int vq_exchange_check(vq_exchange *x) {
     VQ_REQUIRE(x, "vq_exchange_check: null exchange");
     VQ_CUDA(cudaSetDevice(x->device));
     long long c[4];
+    unsigned long long mark = 0;
     VQ_CUDA(cudaMemcpy(c, x->merged, sizeof(c), cudaMemcpyDeviceToHost));
-    VQ_REQUIRE(c[0] >= 0 && c[3] >= 0, "vq_exchange: rank %d gave up after %.1f s waiting for a peer's payload (step %llu): "
-               "a rank died, skipped a step or is out of sequence", x->rank, x->timeout_s, x->seq);
+    VQ_CUDA(cudaMemcpy(&mark, x->sync + 1, sizeof(mark), cudaMemcpyDeviceToHost));
+    if (mark) VQ_CUDA(cudaMemset(x->sync + 1, 0, sizeof(mark)));           // reported once
+    VQ_REQUIRE(mark == 0 && c[0] >= 0 && c[3] >= 0, "vq_exchange: rank %d gave up after %.1f s waiting for a peer's payload (step %llu): "
+               "a rank died, skipped a step or is out of sequence", x->rank, x->timeout_s, mark ? mark : x->seq);
     return 0;
 }
