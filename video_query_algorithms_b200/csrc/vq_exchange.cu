@@ -11,8 +11,7 @@
 // the current step, ranks may drift by one step, and a flush kernel merges the last step.  Four inbox slots
 // (sequence mod 4) make the lagged mode safe: push i overwrites the slot of step i-4, which a peer reads in its
 // kernel i-3; before kernel i starts, this rank's kernel i-1 has seen every peer's flag i-2, i.e. every peer has
-// entered its kernel i-2 and therefore finished its kernel i-3 (in lagged mode a flag is raised at the END of the kernel,
-// after the merge, which only strengthens this).
+// entered its kernel i-2 and therefore finished its kernel i-3.
 #include <stdlib.h>
 #include <string.h>
 
@@ -36,7 +35,7 @@ struct vq_exchange {
     // before the next select_compact overwrites the payload (vq_store::pack_reader_done).
     cudaStream_t side = nullptr;
     cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
-    unsigned long long *t_ring = nullptr;       // pinned, device-mapped [256][kMaxBlocks][4]: start, pushes done, peers' flags seen, end of each block of each exchange kernel (global timer, ns)
+    unsigned long long *t_ring = nullptr;       // pinned, device-mapped [256][kMaxBlocks][kStamps]: start, pushes done, peers' flags seen, merge end, flags raised of each block of each exchange kernel (global timer, ns)
     int blocks = 1;                             // blocks per exchange kernel
     int ev_head = 0, ev_count = 0;
     double timeout_s = 10.0;                    // a peer that never arrives ends the kernel with an error marker instead of a hang
@@ -47,6 +46,8 @@ constexpr int kSlot = 4 + 2 * VQ_MAX_TOPK;      // int64 per payload slot
 constexpr int kSlots = 4;                       // inbox slots (sequence number mod 4)
 constexpr int kRing = 256;
 constexpr int kXThreads = 128;                   // see exchange_push_merge
+constexpr int kMergeThreads = 96;                // warps 0-2 wait for the peers and merge; warp 3 raises the flags
+constexpr int kStamps = 8;                       // global-timer stamps per block: start, pushed, peers seen, merge end, flags raised
 constexpr int kMaxBlocks = 16;                   // blocks of one exchange kernel (one per rank up to here)
 constexpr int kMergeShared = 4096;              // candidates (world * k) merged out of shared memory
 __host__ __device__ inline size_t flags_offset(int world) { return (size_t)kSlots * world * kSlot; }
@@ -62,6 +63,11 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ long long ld_volatile(const long long *p) {
     long long v;
     asm volatile("ld.volatile.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned int ld_volatile_lo32(const long long *p) {     // low half of a little-endian int64
+    unsigned int v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -82,7 +88,7 @@ __device__ __forceinline__ bool before(float sa, long long ra, float sb, long lo
 template <class Rows, class Scores>
 __device__ __forceinline__ void merge_ranked(Rows rows, Scores scs, const int *len, const int world, const int k,
                                              const int stride, const int e_begin, const int e_end, long long *merged) {
-    for (int e = e_begin + threadIdx.x; e < e_end; e += blockDim.x) {
+    for (int e = e_begin + (int)threadIdx.x; e < e_end; e += kMergeThreads) {
         const int l = e / k, i = e - l * k;
         if (i >= len[l]) continue;
         const float sc = scs[l * stride + i];
@@ -120,11 +126,12 @@ struct InboxScores {
 // leaves 7168 registers per SM), so that the kernel runs as soon as its inputs are ready instead of queueing behind a
 // 1.1 ms scan.  Block b stores the payload into the inboxes of the ranks r with r mod grid = b, every block waits for the
 // peers' flags by itself and stages all lists in its own shared memory, then ranks its share of the world * k candidates
-// (one candidate per thread at world 8, k 100), pads its share of the tail and leaves its own times; block 0 also sums
-// the counts.  No block waits for another.  Round 2's single block took 32 us at world 8 (6.7 us for eight peers' stores and one fence,
+// (about one candidate per thread at world 8, k 100), pads its share of the tail and leaves its own times; block 0 also
+// sums the counts.  No block waits for another.  Round 2's single block took 32 us at world 8 (6.7 us for eight peers' stores and one fence,
 // 25.6 us for the merge: 6 candidates x 7 searches per thread, a dependent chain of shared-memory reads).
-// When the step to merge is not the step pushed (lagged mode) the payloads to merge arrived a scan ago: the stores to the
-// peers are issued first, the merge runs while they travel, and the fence + flag follow it.
+// The flags are raised by the block's fourth warp alone: a store-release at system scope has to wait until the payload
+// stores are acknowledged across NVLink (~2 us on B200 + NVSwitch), and warps 0-2 spend that time waiting for the peers and
+// merging (with the release at the end of one instruction stream: 8.6 us at world 2; with every thread fencing: 10 us).
 // t_ns (when not null) receives every block's own start, end of pushes, end of waiting and end on the global timer: CUDA
 // events around a kernel on a side stream would also count the time it waits for an SM.
 // Alternatives measured and dropped in round 2 (8 B200s, world 8, k 100, one block): a one-warp k-way merge of the list
@@ -143,127 +150,122 @@ exchange_push_merge(const long long *__restrict__ payload, long long *const *__r
     __shared__ int timed_out;
     const int n_pay = 4 + 2 * k;
     const int nb = (int)gridDim.x, b = (int)blockIdx.x;
-    const bool flag_late = push_seq && merge_seq && push_seq != merge_seq;
-    unsigned long long ns_push = 0, ns_wait = 0;
+    const int tid = (int)threadIdx.x;
 
-    // 1. my payload into slot [push_seq mod 4][rank] of the inboxes this block serves (own included)
+    // 1. my payload into slot [push_seq mod 4][rank] of the inboxes this block serves (own included): all four warps
     const int push_slot = (int)(push_seq % kSlots);
     if (push_seq) {
         for (int r = b; r < world; r += nb)
-            for (int j = threadIdx.x; j < n_pay; j += blockDim.x)
+            for (int j = tid; j < n_pay; j += kXThreads)
                 peers[r][((size_t)push_slot * world + rank) * kSlot + j] = payload[j];
     }
-    auto raise_flags = [&]() {
-        __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x < world && (int)threadIdx.x % nb == b) {
-            unsigned long long *flag = reinterpret_cast<unsigned long long *>(peers[threadIdx.x] + flags_offset(world)) +
-                                       (size_t)push_slot * world + rank;
-            st_release_sys(flag, push_seq);
+    if (tid >= kMergeThreads) {
+        // The flag warp: a store-release at system scope waits until the payload stores are acknowledged across NVLink
+        // (~2 us).  It waits here, in one warp, while the other three go on to merge.  The named barrier orders every
+        // thread's payload stores before the release, which is cumulative over them (the merge warps only arrive).
+        if (push_seq) {
+            asm volatile("bar.sync 2, %0;" ::"n"(kXThreads) : "memory");
+            for (int r = b + (tid - kMergeThreads) * nb; r < world; r += 32 * nb) {
+                unsigned long long *flag =
+                    reinterpret_cast<unsigned long long *>(peers[r] + flags_offset(world)) + (size_t)push_slot * world + rank;
+                st_release_sys(flag, push_seq);
+            }
         }
-    };
-    if (push_seq && !flag_late) raise_flags();
-    ns_push = global_ns() - t_begin;
+        if (t_ns && tid == kMergeThreads) t_ns[kStamps * b + 4] = global_ns();
+        return;
+    }
+    if (push_seq) asm volatile("bar.arrive 2, %0;" ::"n"(kXThreads) : "memory");
+    const unsigned long long ns_push = global_ns() - t_begin;
+    unsigned long long ns_wait = 0;
+    auto merge_barrier = []() { asm volatile("bar.sync 1, %0;" ::"n"(kMergeThreads) : "memory"); };
 
-    if (threadIdx.x == 0) timed_out = 0;
-    __syncthreads();
+    if (tid == 0) timed_out = 0;
+    merge_barrier();
     if (merge_seq) {
         // 2. wait until every rank's payload for the sequence number to merge has landed in my inbox; a peer that has
         //    died or fallen out of step must not wedge the GPU: past the deadline the kernel leaves an error mark and ends
         const int slot = (int)(merge_seq % kSlots);
         long long *mine = peers[rank];
         const unsigned long long t0 = global_ns();
-        if (threadIdx.x < world) {
+        if (tid < world) {
             const unsigned long long *flag =
-                reinterpret_cast<const unsigned long long *>(mine + flags_offset(world)) + (size_t)slot * world + threadIdx.x;
+                reinterpret_cast<const unsigned long long *>(mine + flags_offset(world)) + (size_t)slot * world + tid;
             while (ld_acquire_sys(flag) != merge_seq) {
                 __nanosleep(64);
                 if (global_ns() - t0 > timeout_ns) { timed_out = 1; break; }
             }
         }
-        __syncthreads();
+        merge_barrier();
         ns_wait = global_ns() - t0;
-        if (!timed_out) {
-            // 3. global top-k by merging the ranks' ranked lists (peer-written memory is read once, bypassing L1)
+        if (timed_out) {
+            if (tid == 0) sync[1] = merge_seq;                 // sticky: vq_exchange_check reports and clears it
+            if (tid < 4) merged[tid] = -1;
+        } else {
+            // 3. global top-k by merging the ranks' ranked lists (peer-written memory is read once, bypassing L1).  The
+            //    lists' lengths and (block 0) the counts are requested first and used after the staging loads have been
+            //    issued: one round trip for all of them
             const long long *g = mine + (size_t)slot * world * kSlot;
-            // (the lists' lengths are requested first and stored after the staging loads have been issued: one round trip)
-            long long len_r = 0;
-            if (threadIdx.x < world) len_r = ld_volatile(g + (size_t)threadIdx.x * kSlot + 3);
+            long long len_r = 0, c0 = 0, c1 = 0, c2 = 0;
+            if (tid < world) len_r = ld_volatile(g + (size_t)tid * kSlot + 3);
+            if (b == 0 && tid < 32) {
+                for (int l = tid; l < world; l += 32) {
+                    c0 += ld_volatile(g + (size_t)l * kSlot);
+                    c1 += ld_volatile(g + (size_t)l * kSlot + 1);
+                    c2 += ld_volatile(g + (size_t)l * kSlot + 2);
+                }
+            }
             const int n = world * k;
             const int per = (n + nb - 1) / nb;
             const int e_begin = b * per, e_end = e_begin + per < n ? e_begin + per : n;
             if (n <= kMergeShared) {
                 float *sm_sc = reinterpret_cast<float *>(sm_rows + n);
                 // all of a thread's loads are issued before the first one is used (each is a full round trip to L2 / HBM)
-                constexpr int kBatch = 8;
-                for (int e0 = threadIdx.x; e0 < n; e0 += blockDim.x * kBatch) {
-                    long long r[kBatch], sb[kBatch];
+                constexpr int kBatch = 9;                      // 2 rounds of 96 threads cover 8 lists of 100
+                for (int e0 = tid; e0 < n; e0 += kMergeThreads * kBatch) {
+                    long long r[kBatch];
+                    unsigned int sb[kBatch];
 #pragma unroll
                     for (int u = 0; u < kBatch; ++u) {
-                        const int e = e0 + u * blockDim.x;
+                        const int e = e0 + u * kMergeThreads;
                         if (e < n) {
                             const int l = e / k, i = e - l * k;
                             r[u] = ld_volatile(g + (size_t)l * kSlot + 4 + i);
-                            sb[u] = ld_volatile(g + (size_t)l * kSlot + 4 + k + i);
+                            sb[u] = ld_volatile_lo32(g + (size_t)l * kSlot + 4 + k + i);
                         }
                     }
 #pragma unroll
                     for (int u = 0; u < kBatch; ++u) {
-                        const int e = e0 + u * blockDim.x;
+                        const int e = e0 + u * kMergeThreads;
                         if (e < n) {
                             sm_rows[e] = r[u];
-                            sm_sc[e] = __uint_as_float((unsigned int)sb[u]);
+                            sm_sc[e] = __uint_as_float(sb[u]);
                         }
                     }
                 }
-                if (threadIdx.x < world) len_s[threadIdx.x] = (int)len_r;
-                __syncthreads();
+                if (tid < world) len_s[tid] = (int)len_r;
+                merge_barrier();
                 merge_ranked(sm_rows, sm_sc, len_s, world, k, k, e_begin, e_end, merged);
             } else {
-                if (threadIdx.x < world) len_s[threadIdx.x] = (int)len_r;
-                __syncthreads();
+                if (tid < world) len_s[tid] = (int)len_r;
+                merge_barrier();
                 merge_ranked(InboxRows{g + 4}, InboxScores{g + 4 + k}, len_s, world, k, kSlot, e_begin, e_end, merged);
             }
-        }
-    }
-    if (flag_late) raise_flags();
-
-    // 4. close the step: block 0 sums the counts (one lane per rank, shuffle reduction), every block pads its share of the
-    //    tail; a block that gave up leaves the sticky error mark; every block leaves its own times
-    if (merge_seq) {
-        if (timed_out) {
-            if (threadIdx.x == 0) sync[1] = merge_seq;         // sticky: vq_exchange_check reports and clears it
-            if (threadIdx.x < 4) merged[threadIdx.x] = -1;
-        } else {
+            // 4. close the step: every block pads its share of the tail, block 0 writes the summed counts
             int tot = 0;
             for (int l = 0; l < world; ++l) tot += len_s[l];
             const int filled = tot < k ? tot : k;
-            for (int i = filled + b * (int)blockDim.x + (int)threadIdx.x; i < k; i += nb * (int)blockDim.x) {
+            for (int i = filled + b * kMergeThreads + tid; i < k; i += nb * kMergeThreads) {
                 merged[4 + i] = -1;
                 merged[4 + k + i] = (long long)0xff800000u;
             }
-            if (b == 0 && threadIdx.x < 32) {
-                const long long *g = peers[rank] + (size_t)(merge_seq % kSlots) * world * kSlot;
-                const int l0 = (int)threadIdx.x, l1 = l0 + 32;
-                long long c0 = 0, c1 = 0, c2 = 0, d0 = 0, d1 = 0, d2 = 0;
-                if (l0 < world) {
-                    c0 = ld_volatile(g + (size_t)l0 * kSlot);
-                    c1 = ld_volatile(g + (size_t)l0 * kSlot + 1);
-                    c2 = ld_volatile(g + (size_t)l0 * kSlot + 2);
-                }
-                if (l1 < world) {
-                    d0 = ld_volatile(g + (size_t)l1 * kSlot);
-                    d1 = ld_volatile(g + (size_t)l1 * kSlot + 1);
-                    d2 = ld_volatile(g + (size_t)l1 * kSlot + 2);
-                }
-                c0 += d0; c1 += d1; c2 += d2;
+            if (b == 0 && tid < 32) {
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
                     c0 += __shfl_xor_sync(0xffffffffu, c0, o);
                     c1 += __shfl_xor_sync(0xffffffffu, c1, o);
                     c2 += __shfl_xor_sync(0xffffffffu, c2, o);
                 }
-                if (threadIdx.x == 0) {
+                if (tid == 0) {
                     merged[0] = c0;
                     merged[1] = c1;
                     merged[2] = c2;
@@ -272,10 +274,10 @@ exchange_push_merge(const long long *__restrict__ payload, long long *const *__r
             }
         }
     }
-    if (t_ns) {
-        __syncthreads();                                       // the block's last stores are issued
-        if (threadIdx.x == 0) {
-            unsigned long long *t = t_ns + 4 * b;
+    if (t_ns) {                                                // every block leaves its own times
+        merge_barrier();                                       // the merge warps' last stores are issued
+        if (tid == 0) {
+            unsigned long long *t = t_ns + kStamps * b;
             t[0] = t_begin;
             t[1] = t_begin + ns_push;
             t[2] = t_begin + ns_push + ns_wait;
@@ -312,8 +314,8 @@ extern "C" int vq_exchange_create(vq_exchange **out, int device, int world, int 
         VQ_CUDA(cudaEventCreateWithFlags(&x->ev_ready, cudaEventDisableTiming));
         VQ_CUDA(cudaEventCreateWithFlags(&x->ev_done, cudaEventDisableTiming));
     }
-    VQ_CUDA(cudaMallocHost((void **)&x->t_ring, (size_t)kRing * kMaxBlocks * 4 * sizeof(unsigned long long)));
-    memset(x->t_ring, 0, (size_t)kRing * kMaxBlocks * 4 * sizeof(unsigned long long));
+    VQ_CUDA(cudaMallocHost((void **)&x->t_ring, (size_t)kRing * kMaxBlocks * kStamps * sizeof(unsigned long long)));
+    memset(x->t_ring, 0, (size_t)kRing * kMaxBlocks * kStamps * sizeof(unsigned long long));
     x->blocks = world < kMaxBlocks ? world : kMaxBlocks;
     if (const char *t = getenv("VQ_EXCHANGE_TIMEOUT_S")) x->timeout_s = atof(t) > 0 ? atof(t) : x->timeout_s;
     cudaFuncSetAttribute(exchange_push_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, kMergeShared * 12);
@@ -408,10 +410,10 @@ static int launch_exchange(vq_exchange *x, vq_store *s, cudaStream_t scan_st, co
     const int slot = x->ev_head;
     x->ev_head = (x->ev_head + 1) % kRing;
     if (x->ev_count < kRing) x->ev_count++;
-    memset(x->t_ring + (size_t)slot * kMaxBlocks * 4, 0, (size_t)kMaxBlocks * 4 * sizeof(unsigned long long));
+    memset(x->t_ring + (size_t)slot * kMaxBlocks * kStamps, 0, (size_t)kMaxBlocks * kStamps * sizeof(unsigned long long));
     exchange_push_merge<<<x->blocks, kXThreads, merge_smem(x->world, x->topk), run>>>(
         payload, x->peer_table_dev, x->world, x->rank, x->topk, push_seq, merge_seq, x->merged, x->sync,
-        (unsigned long long)(x->timeout_s * 1e9), x->t_ring + (size_t)slot * kMaxBlocks * 4);
+        (unsigned long long)(x->timeout_s * 1e9), x->t_ring + (size_t)slot * kMaxBlocks * kStamps);
     VQ_CUDA(cudaGetLastError());
     if (x->side && s) {                              // the next select_compact on this store waits for this kernel before it rewrites the payload
         if (!s->pack_reader_done) VQ_CUDA(cudaEventCreateWithFlags(&s->pack_reader_done, cudaEventDisableTiming));
@@ -479,15 +481,16 @@ extern "C" int vq_exchange_kernel_times(vq_exchange *x, int32_t cap, float *ms_o
     int got = 0;
     for (int i = 0; i < n; ++i) {
         const int slot = (x->ev_head + kRing - n + i) % kRing;
-        const unsigned long long *t = x->t_ring + (size_t)slot * kMaxBlocks * 4;
+        const unsigned long long *t = x->t_ring + (size_t)slot * kMaxBlocks * kStamps;
         // the kernel = its blocks: first start to last end; pushes / waiting = the slowest block's
         unsigned long long t0 = 0, t3 = 0, push = 0, wait = 0;
         bool complete = true;
         for (int b = 0; b < x->blocks; ++b) {
-            const unsigned long long *tb = t + 4 * b;
-            if (tb[0] == 0 || tb[3] < tb[0]) { complete = false; break; }
+            const unsigned long long *tb = t + kStamps * b;
+            if (tb[0] == 0 || tb[3] < tb[0] || tb[4] == 0) { complete = false; break; }
             if (b == 0 || tb[0] < t0) t0 = tb[0];
             if (tb[3] > t3) t3 = tb[3];
+            if (tb[4] > t3) t3 = tb[4];                      // the flag warp ends by itself
             if (tb[1] - tb[0] > push) push = tb[1] - tb[0];
             if (tb[2] - tb[1] > wait) wait = tb[2] - tb[1];
         }
