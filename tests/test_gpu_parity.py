@@ -315,6 +315,50 @@ def test_generic_shapes_single_and_batched(vq, streams, splits, dim):
     st.close()
 
 
+@pytest.mark.parametrize("seed", range(int(os.environ.get("VQ_FUZZ_SEEDS", "8"))))
+def test_scan_on_randomly_drawn_shapes_matches_oracle(vq, seed):
+    """Randomly drawn store shapes — 1-4 streams, 1-3 splits, feature lengths that are any multiple of 4 (so every
+    partial-chunk path of the generic scan kernel: a stream shorter than one warp pass, a ragged last chunk), row counts
+    from 1 to a few thousand (fewer rows than a block, more than a selection chunk), random missing (clip, stream, split)
+    slots, random weights, threshold and top-k — against the float64 oracle: scores 1e-5, sets bit-exact outside the tie
+    band, top-k equal to the stable ranking of the device's scores, labelled fp64 similarities to 1e-12."""
+    rng = np.random.default_rng(4200 + seed)
+    S, P = int(rng.integers(1, 5)), int(rng.integers(1, 4))
+    dim = int(rng.choice([4, 12, 100, 132, 516, 1000, 1024, 1540, 2052]))
+    n = int(rng.choice([1, 3, 31, 33, 129, 1000, 4097, 6000]))
+    streams = tuple("s%d" % i for i in range(S))
+    splits = sorted(int(p_) for p_ in rng.choice(np.arange(1, 8), P, replace=False))
+    X = (rng.random((n, S, P, dim)) * (0.2 + rng.random((n, 1, 1, 1)) * 2)).astype(np.float32)
+    present = rng.random((n, S, P)) > (0.15 if P > 1 and seed % 2 else 0.0)
+    present[:, :, 0] = True                                    # never lose every split of a stream
+    X = X * present[..., None]
+    st = vq.FeatureStore(n, streams, splits, dim, devices=[0])
+    st.upload(0, X)
+    st.set_present(present)
+    X64 = X.astype(np.float64)
+    w = [float(v) for v in rng.uniform(0.5, 2.5, S)]
+    td = lambda t: {s: {p_: t[si, pi] for pi, p_ in enumerate(splits)} for si, s in enumerate(streams)}
+    for r in {0, n // 2, n - 1}:
+        T = sc.scale_target(np.where(present[r][..., None], X64[r], 1.0))      # a full target even when the clip lacks a split
+        sims64, _ = sc.similarities(X64, T, None if present.all() else present)
+        s64 = sc.scores(sims64, w)
+        th = float(np.quantile(s64, 0.8)) if n > 4 else float(s64.min())
+        lo = th - 0.2 * (1 - th)
+        k = int(rng.choice([0, 1, 17, 100, 1024]))
+        res = st.scan(td(T), w, th, lo, EPS, topk=k, want_sims=True)
+        got = st.scores()
+        assert_scores_close(got, s64)
+        assert_sets_match(st.matches()[0], np.flatnonzero(s64 >= th), s64, (th,))
+        assert_sets_match(st.near_misses()[0], np.flatnonzero((s64 >= lo) & (s64 < th)), s64, (th, lo))
+        g64 = got.astype(np.float64)
+        assert res.n_match == np.count_nonzero(g64 >= th) and res.n_near == np.count_nonzero((g64 >= lo) & (g64 < th))
+        assert np.array_equal(st.topk()[0], sc.topk_stable(got, min(k, n)))
+        rows = np.unique(rng.integers(0, n, 40))
+        lab = st.labelled_sims(td(T), rows)
+        assert np.abs(lab - sims64[rows]).max() <= 1e-12 * max(np.abs(sims64).max(), 1.0)
+    st.close()
+
+
 def test_two_shards_merge_like_one(vq):
     """Clip-range sharding inside one process (both shards on device 0 here)."""
     n = 9001
