@@ -661,6 +661,62 @@ def test_batched_scan_counts_only_and_ragged_tail(vq):
     st.close()
 
 
+@pytest.mark.parametrize("seed", range(int(os.environ.get("VQ_FUZZ_SEEDS", "6"))))
+def test_batched_scan_on_randomly_drawn_shapes_matches_oracle(vq, seed):
+    """K3 on randomly drawn shapes: 1-4 streams, 1-2 splits, stream lengths 32..2048 (multiples of the 32-wide K block),
+    1..300 queries (narrow MMAs, exactly 256, more than one pass), shard sizes around the 128-clip tile and the launch
+    boundaries, any top-k, missing slots — scores against float64 (1e-5 of max(|score|, |similarity|, 0.25): its error is
+    relative to the similarity), per-query counts equal to a double comparison of its own scores, top-k equal to the stable ranking
+    of its own scores, tie band equal to the rows of its own scores within eps."""
+    rng = np.random.default_rng(9100 + seed)
+    S, P = int(rng.integers(1, 5)), int(rng.integers(1, 3))
+    dim = int(rng.choice([32, 64, 256, 512, 1024]))
+    n = int(rng.choice([1, 100, 127, 128, 129, 5000, 148 * 128 + 5, 40000]))
+    Q = int(rng.choice([1, 5, 63, 64, 65, 128, 129, 255, 256, 257, 300]))
+    if n * Q > 6_000_000:
+        Q = max(1, 6_000_000 // n)
+    streams = tuple("s%d" % i for i in range(S))
+    splits = list(range(1, P + 1))
+    X = (rng.random((n, S, P, dim), dtype=np.float32) * (0.5 + rng.random((n, 1, 1, 1), dtype=np.float32))).astype(np.float32)
+    present = rng.random((n, S, P)) > (0.2 if P > 1 and seed % 2 else 0.0)
+    present[:, :, 0] = True
+    X = X * present[..., None]
+    st = vq.FeatureStore(n, streams, splits, dim, devices=[0])
+    st.upload(0, X)
+    st.set_present(present)
+    X64 = X.astype(np.float64)
+    w = [float(v) for v in rng.uniform(0.5, 2.5, S)]
+    refs = rng.integers(0, n, Q)
+    T32 = np.stack([sc.scale_target(np.where(present[r][..., None], X64[r], 1.0)) for r in refs]).astype(np.float32)
+    th = 0.6
+    lo = th - 0.25
+    k = int(rng.choice([0, 1, 20, 100]))
+    wide = 1e-3
+    got = st.scan_batch(T32, w, th, lo, debug_scores=True)
+    counts, rows, scores, _ = st.scan_batch(T32, w, th, lo, topk=k, eps=wide)
+    t_counts, t_lists = st.batch_ties
+    assert got.shape == (Q, n) and rows.shape == (Q, k)
+    kk = min(k, n)
+    for q in range(Q):
+        if q < 12 or q % 37 == 0:                                  # float64 check on a subset of the queries (host time)
+            sims64, _ = sc.similarities(X64, T32[q].astype(np.float64), None if present.all() else present)
+            s64 = sc.scores(sims64, w)
+            # the operand split's error is relative to the SIMILARITY (3 * 2^-18 per product, random signs), which in this
+            # data reaches 2-3 where the score passes through 0: measured against max(|score|, max |sim|, 0.25)
+            scale = np.maximum(np.maximum(np.abs(s64), np.abs(sims64).max(axis=1)), 0.25)
+            err = np.abs(got[q].astype(np.float64) - s64) / scale
+            assert err.max() <= 1e-5, "query %d: max err %.3e at row %d" % (q, err.max(), err.argmax())
+        g = got[q].astype(np.float64)
+        assert counts[q, 0] == np.count_nonzero(g >= th) and counts[q, 1] == np.count_nonzero((g >= lo) & (g < th))
+        assert np.array_equal(rows[q, :kk], sc.topk_stable(got[q], kk)) and np.array_equal(scores[q, :kk], got[q][rows[q, :kk]])
+        assert (rows[q, kk:] == -1).all()
+        band = np.flatnonzero((np.abs(g - th) < wide) | (np.abs(g - lo) < wide))
+        assert t_counts[q] == len(band)
+        if len(band) <= st.TIE_CAP:
+            assert np.array_equal(t_lists[q][0], band) and np.array_equal(t_lists[q][1], got[q][band])
+    st.close()
+
+
 # ---------------------------------------------------------------------------- labelled subset (fp64)
 def test_loss_grid_and_replicates_match_oracle(vq):
     rng = np.random.default_rng(1)
