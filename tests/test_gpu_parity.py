@@ -753,6 +753,59 @@ def test_bootstrap_target_matches_oracle(vq):
     st.close()
 
 
+@pytest.mark.parametrize("seed", range(int(os.environ.get("VQ_FUZZ_SEEDS", "6"))))
+def test_labelled_path_on_randomly_drawn_problems_matches_oracle(vq, seed):
+    """The fp64 kernels of the weight update and the target bootstrap on randomly drawn problems: K5's loss grid for any
+    number of labelled clips (1 .. 3000), label mixes incl. all-True / all-False, grid sizes other than 40 x 31, ballast,
+    scores sitting exactly on a threshold (H(0) = 1), replicate index sets with repeats and of different lengths (1e-13
+    against the oracle's loop); K6's solve for 1-4 streams, 1-3 splits, feature lengths 64-1024, 1 .. 60 valid and
+    0 .. 30 invalid rows, mu = 0 and > 0, duplicate-free rows drawn from well-conditioned data, slot masks (1e-8 of the
+    oracle's numpy solve, hyperparameter.py:56-65, target_clip.py:194-198,248-260)."""
+    rng = np.random.default_rng(5300 + seed)
+    # ---- K5
+    L = int(rng.choice([1, 2, 7, 100, 1000, 3000]))
+    sims = 0.4 + 0.8 * rng.random((L, 2))
+    mode = seed % 4
+    y = np.ones(L, bool) if mode == 1 else np.zeros(L, bool) if mode == 2 else rng.random(L) < rng.uniform(0.1, 0.9)
+    wg = sc.weight_grid() if seed % 2 else np.linspace(0.3, 3.0, int(rng.integers(1, 60)))
+    tg = sc.threshold_grid() if seed % 3 else np.linspace(0.2, 1.2, int(rng.integers(1, 50)))
+    if L > 2:                                                      # a clip whose score equals a grid threshold exactly
+        sims[0] = (1.0 - (1.0 - tg[len(tg) // 2]), 1.0 - (1.0 - tg[len(tg) // 2]))
+    ballast = float(rng.choice([0.0, 0.1, 0.75]))
+    got = vq.loss_grid(sims, y, wg, tg, ballast)[0]
+    want = sc.loss_grid(sims, y, wg, tg, ballast) if L <= 1000 else sc.loss_grid_fast(sims, y, wg, tg, ballast)
+    assert got.shape == want.shape and np.abs(got - want).max() < 1e-13 * max(1.0, np.abs(want).max())
+    reps = [rng.integers(0, L, int(rng.integers(1, L + 2))) for _ in range(int(rng.integers(1, 12)))]
+    got = vq.loss_grid(sims, y, wg, tg, ballast, replicates=reps)
+    for r, idx in enumerate(reps):
+        want = sc.loss_grid_fast(sims[idx], y[idx], wg, tg, ballast)
+        assert np.abs(got[r] - want).max() < 1e-13 * max(1.0, np.abs(want).max())
+    # ---- K6
+    S, P = int(rng.integers(1, 5)), int(rng.integers(1, 4))
+    dim = int(rng.choice([64, 256, 1024]))
+    n = 400
+    X = (rng.random((n, S, P, dim)) + 0.1).astype(np.float32)
+    st = vq.FeatureStore(n, tuple("s%d" % i for i in range(S)), list(range(1, P + 1)), dim, devices=[0])
+    st.upload(0, X)
+    X64 = X.astype(np.float64)
+    for _ in range(3):
+        nv, ni = int(rng.integers(1, min(60, dim // 2))), int(rng.integers(0, 30))
+        rows = rng.choice(n, nv + ni, replace=False)
+        valid, invalid = rows[:nv], rows[nv:]
+        mu = float(rng.choice([0.0, 0.25, 1.0]))
+        slots = None if seed % 2 else rng.random((S, P)) < 0.6
+        got = st.bootstrap_target(valid, invalid if ni else None, mu, slots)
+        for s_ in range(S):
+            for p_ in range(P):
+                if slots is not None and not slots[s_, p_]:
+                    assert not got[s_, p_].any()
+                    continue
+                want = (ob.solve_valid_invalid(X64[valid, s_, p_], X64[invalid, s_, p_], mu) if ni
+                        else ob.solve_valid(X64[valid, s_, p_]))
+                assert np.abs(got[s_, p_] - want).max() <= 1e-8 * np.abs(want).max(), (S, P, dim, nv, ni, mu)
+    st.close()
+
+
 # ---------------------------------------------------------------------------- end to end vs reference goldens
 @pytest.mark.parametrize("name", SCENARIOS)
 def test_compute_matches_reproduces_reference_rounds(vq, name, tmp_path, monkeypatch):

@@ -66,15 +66,18 @@ __global__ void score_table_kernel(const double *__restrict__ sims, long long L,
 constexpr int kLossThreads = 128;
 constexpr int kMaxTh = 32;
 
-// one block per (replicate, weight): 31 running sums per thread, block tree reduction
+// one block per (replicate, weight, group of up to 32 thresholds): one running sum per threshold and thread (31 for the
+// reference's grid, hyperparameter.py:21), block tree reduction; longer threshold grids take more groups (blockIdx.y)
 __global__ void __launch_bounds__(kLossThreads)
 loss_grid_kernel(const double *__restrict__ table, const unsigned char *__restrict__ labels, long long L,
-                 const double *__restrict__ thgrid, int n_th, int n_w, double ballast,
+                 const double *__restrict__ thgrid, int n_th_all, int n_w, double ballast,
                  const int *__restrict__ rep_offset, const int *__restrict__ rep_index, double *losses) {
     __shared__ double th_s[kMaxTh];
     __shared__ double red[kLossThreads / 32][kMaxTh];
     const int r = blockIdx.x / n_w, iw = blockIdx.x - r * n_w;
-    if (threadIdx.x < n_th) th_s[threadIdx.x] = thgrid[threadIdx.x];
+    const int th0 = blockIdx.y * kMaxTh;
+    const int n_th = n_th_all - th0 < kMaxTh ? n_th_all - th0 : kMaxTh;
+    if (threadIdx.x < n_th) th_s[threadIdx.x] = thgrid[th0 + threadIdx.x];
     __syncthreads();
     const int lo = rep_offset[r], hi = rep_offset[r + 1];
     double acc[kMaxTh];
@@ -106,7 +109,7 @@ loss_grid_kernel(const double *__restrict__ table, const unsigned char *__restri
         double v = 0.0;
         for (int w = 0; w < kLossThreads / 32; ++w) v += red[w][threadIdx.x];
         const double n = (double)(hi - lo);
-        losses[((size_t)r * n_w + iw) * n_th + threadIdx.x] = (0.5 * th_s[threadIdx.x] + v) / n;
+        losses[((size_t)r * n_w + iw) * n_th_all + th0 + threadIdx.x] = (0.5 * th_s[threadIdx.x] + v) / n;
     }
 }
 
@@ -389,8 +392,8 @@ extern "C" int vq_loss_grid(int device, const double *sims, const uint8_t *label
                             double *losses_out) {
     VQ_REQUIRE(sims && labels && weight_grid && threshold_grid && rep_offset && rep_index && losses_out,
                "vq_loss_grid: null argument");
-    VQ_REQUIRE(L > 0 && n_w > 0 && R > 0 && n_th > 0 && n_th <= kMaxTh,
-               "vq_loss_grid: need L, R, n_w > 0 and 0 < n_th <= %d", kMaxTh);
+    VQ_REQUIRE(L > 0 && n_w > 0 && R > 0 && n_th > 0 && n_th <= 65535 * kMaxTh, "vq_loss_grid: need L, R, n_w, n_th > 0");
+    VQ_REQUIRE((int64_t)R * n_w < (1ll << 31), "vq_loss_grid: %d replicates x %d weights exceed the launch grid", R, n_w);
     for (int r = 0; r < R; ++r)
         VQ_REQUIRE(rep_offset[r + 1] > rep_offset[r], "vq_loss_grid: replicate %d is empty", r);
     const int64_t n_idx = rep_offset[R];
@@ -443,7 +446,7 @@ extern "C" int vq_loss_grid(int device, const double *sims, const uint8_t *label
     VQ_CUDA(cudaMemcpyAsync(ar.p, ar.h, in_bytes, cudaMemcpyHostToDevice, ar.st));
     score_table_kernel<<<(unsigned int)((L * n_w + 255) / 256), 256, 0, ar.st>>>(d_sims.as<double>(), L, d_w.as<double>(),
                                                                                  n_w, d_tab.as<double>());
-    loss_grid_kernel<<<(unsigned int)(R * n_w), kLossThreads, 0, ar.st>>>(d_tab.as<double>(), d_lab.as<unsigned char>(), L,
+    loss_grid_kernel<<<dim3((unsigned int)(R * n_w), (unsigned int)((n_th + kMaxTh - 1) / kMaxTh)), kLossThreads, 0, ar.st>>>(d_tab.as<double>(), d_lab.as<unsigned char>(), L,
                                                                           d_th.as<double>(), n_th, n_w, ballast,
                                                                           d_off.as<int>(), d_idx.as<int>(), d_out.as<double>());
     VQ_CUDA(cudaGetLastError());
