@@ -79,7 +79,7 @@ def test_gpu_store_and_oracle_store_agree_on_random_jobs(tmp_path, monkeypatch):
                     try:
                         vq.compute_matches(FakeRepository(api), hp, ticket_factory=factory)
                     except Exception as e:                     # e.g. a singular labelled set: both sides must refuse it
-                        err = type(e).__name__
+                        err = "%s: %s" % (type(e).__name__, str(e)[:300])
                     out[name] = (err, snapshot(api, q, hp), random.getstate(), hp)
                 (err_g, a, state_g, hp_g), (err_c, b, state_c, hp_c) = out["gpu"], out["cpu"]
                 where = (trial, kind, job["hp"]["bootstrap_type"], job["ragged"], job["X"].shape)

@@ -70,7 +70,12 @@ def make_oracle_store_class():
             pass
 
         def _sync_split_weights_for_target(self, have):
-            pass
+            """no device table to load; the product's refusal of a job in which some clip shares no split with the target
+            for some stream (the reference raises KeyError there, ticket.py:177) is kept"""
+            present = np.ones((self.n_rows,) + self.row_shape[:2], bool) if self.present is None else self.present
+            if self.n_rows and ((present & have[None]).sum(axis=2) == 0).any():
+                raise ps.VQError("a clip has no feature row at all for one stream; the reference raises KeyError "
+                                 "for such a search set (ticket.py:177)")
 
         def close(self):
             pass
@@ -78,6 +83,7 @@ def make_oracle_store_class():
         # ---- the scan and its results (conventions of vq_scan: fp32 scores, comparisons on (double)score)
         def scan(self, target_features, weights, threshold, lower_limit, eps, topk=0, want_sims=False, lists=True, packed=None):
             T, have = self.pack_target(target_features, np.float32)
+            self._sync_split_weights_for_target(have)
             present = np.ones((self.n_rows,) + self.row_shape[:2], bool) if self.present is None else self.present
             sims, _ = sc.similarities(self.X, T.astype(np.float64), present & have[None])
             w = [weights[s] for s in self.streams] if isinstance(weights, dict) else list(weights)
@@ -147,6 +153,7 @@ def make_oracle_store_class():
         # ---- labelled subset (float64, like K4 / K6)
         def labelled_sims(self, target_features, global_rows):
             T, have = self.pack_target(target_features, np.float64)
+            self._sync_split_weights_for_target(have)
             rows = np.asarray(global_rows, np.int64) - self.first_global_row
             present = np.ones((len(rows),) + self.row_shape[:2], bool) if self.present is None else self.present[rows]
             return sc.similarities(self.X[rows], T, present & have[None])[0]
