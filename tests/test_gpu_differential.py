@@ -20,8 +20,14 @@ from test_rounds_cpu import close, make_oracle_store_class
 pytestmark = pytest.mark.gpu
 
 
-def test_gpu_store_and_oracle_store_agree_on_random_jobs(tmp_path, monkeypatch):
+@pytest.mark.parametrize("devices", [[0], [0, 0, 0]], ids=["one-shard", "three-shards"])
+def test_gpu_store_and_oracle_store_agree_on_random_jobs(tmp_path, monkeypatch, devices):
+    """devices = [0, 0, 0]: the search set sharded three ways (all shards on device 0, so that a single-GPU box runs it): the
+    one-call multi-shard scan, the multi-shard gathers, per-shard device sorts merged for the report, labelled rows
+    gathered across shards for the solve — under the same jobs.  VQ_DIFF_DEVICES=0,1 spreads the shards over real devices."""
     import video_query_algorithms_b200 as vq
+    if os.environ.get("VQ_DIFF_DEVICES") and len(devices) > 1:
+        devices = [int(d_) for d_ in os.environ["VQ_DIFF_DEVICES"].split(",")]
     from fake_api import FakeRepository
     from video_query_algorithms_b200 import store as ps
     real_store, real_loss_grid = ps.FeatureStore, ps.loss_grid
@@ -31,7 +37,7 @@ def test_gpu_store_and_oracle_store_agree_on_random_jobs(tmp_path, monkeypatch):
     for d in ("gpu/work", "cpu/work"):
         (tmp_path / d).mkdir(parents=True)
     monkeypatch.chdir(tmp_path)
-    rng = np.random.default_rng(int(os.environ.get("VQ_DIFF_SEED", "4711")))
+    rng = np.random.default_rng(int(os.environ.get("VQ_DIFF_SEED", "4711")) + len(devices))
     n_trials = int(os.environ.get("VQ_DIFF_TRIALS", "40"))
     compared = ties = plateaus = reports = errors = 0
     ps.invalidate()
@@ -75,7 +81,7 @@ def test_gpu_store_and_oracle_store_agree_on_random_jobs(tmp_path, monkeypatch):
                     random.seed(a=job["seed"])
                     err = None
                     factory = (lambda j, url, name=name, api=api:
-                               tickets[name].append(vq.Ticket(j, url, client=api.client(), devices=[0])) or tickets[name][-1])
+                               tickets[name].append(vq.Ticket(j, url, client=api.client(), devices=devices)) or tickets[name][-1])
                     try:
                         vq.compute_matches(FakeRepository(api), hp, ticket_factory=factory)
                     except Exception as e:                     # e.g. a singular labelled set: both sides must refuse it
