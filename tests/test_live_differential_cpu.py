@@ -36,13 +36,17 @@ def reference(monkeypatch):
     random.sample = real_sample
 
 
-def draw_job(rng):
-    """One random job description: search set, reference clip, hyperparameters, rounds."""
+def draw_job(rng, shape=None):
+    """One random job description: search set, reference clip, hyperparameters, rounds.  shape = (n, dim, n_splits) fixes the
+    search set's size (the GPU twin uses it for 1024-d single-split sets of a few thousand clips; the draws below are
+    consumed either way, so the stream of jobs is the same)."""
     # dim stays above the number of clips a user can confirm over three rounds: with more confirmed clips than
     # dimensions the bootstrap's Gram matrix is singular and the reference's inv() returns garbage (SURVEY.md §8 A10;
     # the library refuses such a solve), so there is nothing to compare
     n, dim = int(rng.integers(24, 70)), int(rng.choice([48, 64]))
     splits = [1, 2, 3][:int(rng.integers(1, 4))]
+    if shape is not None:
+        n, dim, splits = int(shape[0]), int(shape[1]), [1, 2, 3][:int(shape[2])]
     base = rng.random((2, len(splits), dim)) + 0.2
     alpha = rng.random(n) ** 0.5                               # scores spread over the band, like VQSYN-1
     X = alpha[:, None, None, None] * base[None] + (1 - alpha)[:, None, None, None] * np.abs(rng.normal(size=(n, 2, len(splits), dim)))
