@@ -48,6 +48,38 @@ def assert_sets_match(got_rows, want_rows, score64, boundaries, eps=EPS):
     return len(diff)
 
 
+# ---------------------------------------------------------------------------- the C ABI from C
+def test_plain_c_consumer_of_the_abi_gets_what_the_python_host_gets(vq, tmp_path):
+    """tests/c_abi/scan_consumer.c — C99, only include/vq.h and libvq_b200.so, no Python in the process — builds a synthetic
+    shard, derives the target from one of its rows, scans with host buffers and prints counts, top-k and list checksums;
+    the same query through the Python host (ctypes) must give the same numbers bit for bit.  This is the boundary a cgo /
+    JNI / N-API binding would sit on."""
+    import json
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "scan_consumer")
+    lib_dir = os.path.join(root, "video_query_algorithms_b200", "lib")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "tests", "c_abi", "scan_consumer.c"), "-L", lib_dir, "-lvq_b200",
+                    "-Wl,-rpath," + lib_dir, "-o", exe], check=True, capture_output=True, text=True)
+    n, seed, ref = 50000, 20261018, 18120
+    out = subprocess.run([exe, str(n), str(seed), str(ref)], check=True, capture_output=True, text=True, timeout=300).stdout
+    got = json.loads(out.strip().splitlines()[-1])
+    st = vq.FeatureStore(n, STREAMS, [1], 1024, devices=[0])
+    st.fill_synthetic(seed)
+    f = st.download(ref, 1)[0].astype(np.float64)
+    T = np.stack([vq.TargetClip._scale_feature(f[s, 0]) for s in range(2)])[:, None, :]
+    res = st.scan(tdict(T), (1.0, 1.5), 0.8, 0.8 - 0.35 * (1 - 0.8), EPS, topk=100)
+    (m_rows, m_sc), (n_rows, n_sc), (k_rows, k_sc) = st.matches(), st.near_misses(), st.topk()
+    assert (got["n_match"], got["n_near"], got["n_tie"], got["n_topk"]) == (res.n_match, res.n_near, res.n_tie, res.n_topk)
+    assert res.n_match > 100 and res.n_near > 100
+    assert got["match_rows_sum"] == int(m_rows.sum()) and got["near_rows_sum"] == int(n_rows.sum())
+    assert got["match_bits_sum"] == int(m_sc.view(np.uint32).astype(np.uint64).sum())
+    assert got["near_bits_sum"] == int(n_sc.view(np.uint32).astype(np.uint64).sum())
+    assert got["topk_rows"] == k_rows.tolist() and np.float32(got["top1_score"]) == k_sc[0]
+    st.close()
+
+
 # ---------------------------------------------------------------------------- generator
 def test_synthetic_generator_is_bit_identical_to_cpu_twin(vq):
     st = vq.FeatureStore(5000, STREAMS, [1], 1024, devices=[0], first_global_row=123456789)

@@ -57,6 +57,21 @@ def test_header_is_plain_c(tmp_path):
     assert r.returncode == 0, r.stderr
 
 
+def test_plain_c_consumer_compiles_and_fails_loudly_without_a_gpu(built_lib, tmp_path):
+    """tests/c_abi/scan_consumer.c (C99, -Wall -Wextra -Werror) links against the library with nothing but include/vq.h; in
+    this container (no GPU) it must end with a non-zero status and the library's error text, not a crash or a result."""
+    import torch
+    exe = str(tmp_path / "scan_consumer")
+    lib_dir = os.path.dirname(built_lib.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "c_abi", "scan_consumer.c"), "-L", lib_dir, "-lvq_b200",
+                    "-Wl,-rpath," + lib_dir, "-o", exe], check=True, capture_output=True, text=True)
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the run itself is tests/test_gpu_parity.py's")
+    r = subprocess.run([exe, "1000"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 1 and r.stdout == "" and ("failed" in r.stderr or "no CUDA device" in r.stderr), (r.returncode, r.stderr)
+
+
 def test_no_gpu_means_loud_failure_not_fallback(built_lib):
     import video_query_algorithms_b200 as vq
     n = ctypes.c_int()
