@@ -58,6 +58,11 @@ def test_gpu_store_and_oracle_store_agree_on_random_jobs(tmp_path, monkeypatch, 
     try:
         for trial in range(n_trials):
             job = draw_job(rng, (int(rng.integers(300, 2500)), 1024, 1)) if big else draw_job(rng)
+            if trial % 3 == 2:                                 # every third job: hyperparameters at the edges of their ranges
+                job["hp"].update(default_threshold=float(rng.choice([0.3, 0.5, 0.999, 1.0])), near_miss_default=float(rng.choice([0.0, 0.05, 1.0, 3.0])),
+                                 mu=float(rng.choice([0.0, 0.001, 5.0])), f_bootstrap=float(rng.choice([0.01, 0.3, 1])),
+                                 nbags=int(rng.integers(1, 7)), ballast=float(rng.choice([0.0, 2.0])))
+                job["max_matches"] = int(rng.choice([0, 1, 2, 3, 5, 20]))
             kinds = ["new", "revise", "finalize"][:int(rng.integers(2, 4))]
             api_g, q_g = build_api(job, str(trial))
             api_c, q_c = build_api(job, str(trial))
