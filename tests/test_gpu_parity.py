@@ -1316,6 +1316,37 @@ def test_finalize_selection_of_a_large_search_set_is_array_work(vq, tmp_path, mo
     st.close()
 
 
+def test_a_full_device_reports_out_of_memory_evicts_and_goes_on(vq):
+    """Two shards of 55 % of the device memory each do not fit together: creating the second one fails with the
+    library's "out of memory" error (no crash, no sticky CUDA error), `evict_least_recently_used` closes the resident
+    one, the retry succeeds and the new shard scans correctly — what Ticket._build_store does when a broker's search sets
+    outgrow the HBM (the CPU twin is tests/test_rounds_cpu.py)."""
+    import torch
+    from video_query_algorithms_b200 import store as ps
+    total = torch.cuda.get_device_properties(0).total_memory
+    n = int(0.55 * total / 8192)
+    ps.invalidate()
+    a = vq.FeatureStore(n, STREAMS, [1], 1024, devices=[0])
+    a.last_used = 1.0
+    ps.register_store(("test", "a"), a)
+    small = vq.FeatureStore(5000, STREAMS, [1], 1024, devices=[0])          # a bystander that must keep working
+    small.fill_synthetic(3)
+    small.last_used = 2.0
+    ps.register_store(("test", "small"), small)
+    with pytest.raises(vq.VQError, match="out of memory"):
+        vq.FeatureStore(n, STREAMS, [1], 1024, devices=[0])
+    T = sc.scale_target(synth.rows(3, [7]).astype(np.float64)[0][:, None, :])
+    before = small.scan(tdict(T), (1.0, 1.5), 0.8, 0.73, EPS, topk=10)      # the failed allocation left no error behind
+    assert ps.evict_least_recently_used(keep=("test", "b")) and ("test", "a") not in ps._REGISTRY
+    b = vq.FeatureStore(n, STREAMS, [1], 1024, devices=[0])
+    ps.register_store(("test", "b"), b)
+    after = small.scan(tdict(T), (1.0, 1.5), 0.8, 0.73, EPS, topk=10)
+    assert (before.n_match, before.n_near) == (after.n_match, after.n_near) and before.n_match >= 1
+    assert ps.evict_least_recently_used(keep=("test", "b")) and list(ps._REGISTRY) == [("test", "b")]
+    assert not ps.evict_least_recently_used(keep=("test", "b"))
+    ps.invalidate()
+
+
 def test_store_follows_a_growing_search_set_on_the_gpu(vq, tmp_path, monkeypatch):
     """load_db.py adds clips between ticks (reference load_db.py:10-28; the reference re-reads the search set per job): the
     resident store notices (the search-set record changed) and appends the new clips — results equal a store built fresh."""

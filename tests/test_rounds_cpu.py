@@ -354,3 +354,64 @@ def test_job_error_states_follow_the_reference_on_cpu(cpu_product, tmp_path, mon
     rows = api.client().action(None, ["search-sets", "features"], params={"id": ss})
     assert st.append_feature_rows(rows, both.hp()["feature_name"]) == len(all_ids) - 95
     assert sorted(st.clip_ids) == sorted(all_ids) and st.X.shape[0] == len(all_ids)
+
+
+def test_a_full_device_evicts_the_least_recently_used_store_and_retries(cpu_product, tmp_path, monkeypatch):
+    """A broker serving several search sets: building a store when the devices are full of other search sets' stores
+    (the library's allocation error says "out of memory") closes the least recently used of those and tries again; the
+    evicted search set is rebuilt from the API the next time a job names it.  An allocation failure with nothing left
+    to evict, and any other error, reach the caller (the broker logs it, broker.py:88-89)."""
+    vq = cpu_product
+    from fake_api import FakeRepository
+    from video_query_algorithms_b200 import store as ps
+    monkeypatch.chdir(tmp_path)
+    scn = Scenario("A_brooklyn_bagging")
+    apis = []
+    for i in range(3):                                        # three brokers' worth of search sets: distinct API urls -> distinct keys
+        api, qid = scn.build_api()
+        api.url = "http://api-%d/" % i
+        apis.append((api, qid))
+
+    def run(i):
+        api, qid = apis[i]
+        api.request(qid, "new")
+        random.seed(a=scn.seed)
+        made = []
+        fac = lambda job, url: made.append(vq.Ticket(job, "http://api-%d/" % i, client=api.client(), devices=[0])) or made[-1]
+        vq.compute_matches(FakeRepository(api), vq.Hyperparameter(**scn.hp()), ticket_factory=fac)
+        assert api.queries[qid]["process_state"] == 4
+        return made[-1].feature_store()
+
+    st0, st1 = run(0), run(1)
+    assert len(ps._REGISTRY) == 2
+    run(0)                                                    # search set 0 was used last: search set 1 is the LRU one
+    real = ps.FeatureStore.from_feature_rows.__func__
+    budget = {"fail": 1}
+
+    def flaky(cls, *a, **kw):
+        if budget["fail"] > 0:
+            budget["fail"] -= 1
+            raise ps.VQError("vq_store_create failed (-3): vq_store: cudaMalloc(8192000000 bytes) for s->rows -> out of memory")
+        return real(cls, *a, **kw)
+
+    monkeypatch.setattr(ps.FeatureStore, "from_feature_rows", classmethod(flaky))
+    closed = []
+    monkeypatch.setattr(type(st1), "close", lambda self: closed.append(self))
+    st2 = run(2)                                              # first attempt fails -> evict search set 1 -> retry succeeds
+    assert closed == [st1] and st2.n_rows == st0.n_rows
+    keys = {k[0] for k in ps._REGISTRY}
+    assert keys == {"http://api-0/", "http://api-2/"}
+    n_calls = apis[1][0].calls.count(("search-sets", "features"))
+    assert run(1) is not st1 and apis[1][0].calls.count(("search-sets", "features")) == n_calls + 1   # rebuilt on demand
+    # nothing left to evict: the error reaches the caller
+    ps.invalidate()
+    budget["fail"] = 1
+    with pytest.raises(ps.VQError, match="out of memory"):
+        run(0)
+    # another error is not an eviction matter
+    run(1)
+    monkeypatch.setattr(ps.FeatureStore, "from_feature_rows",
+                        classmethod(lambda cls, *a, **kw: (_ for _ in ()).throw(ps.VQError("vq_store_create: dim must be a multiple of 4"))))
+    with pytest.raises(ps.VQError, match="multiple of 4"):
+        run(2)
+    assert len(ps._REGISTRY) == 1

@@ -21,6 +21,7 @@ void set_error(const char *fmt, ...);
         if (e__ != cudaSuccess) {                                                       \
             vq::set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call,                  \
                           cudaGetErrorString(e__));                                     \
+            (void)cudaGetLastError(); /* a failed allocation must not fail the next launch check */ \
             return -2;                                                                  \
         }                                                                               \
     } while (0)

@@ -110,6 +110,7 @@ static int alloc_row_buffers(vq_store *s, int64_t capacity) {
     do {                                                                                  \
         cudaError_t e2 = cudaMalloc((void **)&(ptr), (bytes));                            \
         if (e2 != cudaSuccess) {                                                          \
+            (void)cudaGetLastError();                                                     \
             vq::set_error("vq_store: cudaMalloc(%zu bytes) for %s -> %s", (size_t)(bytes), #ptr, cudaGetErrorString(e2)); \
             return -3;                                                                    \
         }                                                                                 \
@@ -168,6 +169,7 @@ extern "C" int vq_store_create(vq_store **out, int device, int64_t n_rows, int n
     do {                                                                                  \
         cudaError_t e2 = cudaMalloc((void **)&(ptr), (bytes));                            \
         if (e2 != cudaSuccess) {                                                          \
+            (void)cudaGetLastError();                                                     \
             vq::set_error("vq_store_create: cudaMalloc(%zu bytes) for %s -> %s", (size_t)(bytes), #ptr, \
                           cudaGetErrorString(e2));                                        \
             store_free(s);                                                                \

@@ -1062,6 +1062,17 @@ def register_store(key, store):
     _REGISTRY[key] = store
 
 
+def evict_least_recently_used(keep=None):
+    """Close the resident store that has gone unused the longest (never `keep`); True if one was closed.  A broker that
+    serves many search sets fills HBM with their stores; when building another one runs out of device memory the caller
+    evicts and retries (Ticket._build_store) instead of failing every job of the new search set from then on."""
+    victims = [(getattr(st, "last_used", 0.0), k) for k, st in _REGISTRY.items() if k != keep]
+    if not victims:
+        return False
+    invalidate(min(victims, key=lambda v: v[0])[1])
+    return True
+
+
 def invalidate(key=None):
     """Drop a cached store (or all): call when load_db.py has added clips to the search set."""
     for k in [key] if key is not None else list(_REGISTRY):

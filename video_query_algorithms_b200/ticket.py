@@ -247,12 +247,25 @@ class Ticket:
                     logging.info("search set %s grew by %d clip(s): appended to the resident store", self.search_set, added)
                 st.freshness = self._freshness_probe()
                 st.built_at = time.monotonic()
+        st.last_used = time.monotonic()
         self._store = st
         return st
 
     def _build_store(self, key, hyperparameters, rows):
-        st = _store.FeatureStore.from_feature_rows(rows, hyperparameters.streams, hyperparameters.feature_name,
-                                                   devices=self.devices)
+        """Build the search set's store; when the devices are full of OTHER search sets' stores, the least recently used
+        of those make room (they are rebuilt from the API the next time a job names them)."""
+        if not isinstance(rows, list):
+            rows = list(rows)
+        while True:
+            try:
+                st = _store.FeatureStore.from_feature_rows(rows, hyperparameters.streams, hyperparameters.feature_name,
+                                                           devices=self.devices)
+                break
+            except VQError as e:
+                if "out of memory" not in str(e) or not _store.evict_least_recently_used(keep=key):
+                    raise
+                logging.warning("device memory is full: evicted the least recently used feature store to build search set %s",
+                                self.search_set)
         st.freshness = self._freshness_probe()
         st.built_at = time.monotonic()
         _store.register_store(key, st)
