@@ -28,31 +28,48 @@ def needs_build():
 def build_pyhost():
     import sysconfig
     cc = os.environ.get("CC", "gcc")
-    cmd = [cc, "-O3", "-fPIC", "-shared", "-pthread", "-I", sysconfig.get_paths()["include"], "-o", PYHOST,
+    tmp = PYHOST + ".tmp.%d" % os.getpid()
+    cmd = [cc, "-O3", "-fPIC", "-shared", "-pthread", "-I", sysconfig.get_paths()["include"], "-o", tmp,
            os.path.join(CSRC, "vq_pyhost.c")]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("building libvq_pyhost.so failed:\n" + r.stdout + r.stderr)
+    os.replace(tmp, PYHOST)
     return PYHOST
 
 
 def build(force=False, verbose=False):
+    """Compile when a source is newer than the libraries.  Several processes may get here at once (torchrun starts one
+    bench.py per GPU): one of them builds under a file lock, into temporary files that are renamed into place, and the
+    others find the work done when they get the lock."""
     if not force and not needs_build():
         return LIB
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    import fcntl
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    cmd = [nvcc, *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-shared", "-o", LIB,
-           *[os.path.join(CSRC, f) for f in SOURCES]]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    cmd[1:1] = os.environ.get("VQ_NVCC_EXTRA", "").split()
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
-    if verbose:
-        print(r.stderr)
-    build_pyhost()
-    return LIB
+    with open(os.path.join(os.path.dirname(LIB), ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():
+                return LIB
+            nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+            tmp = LIB + ".tmp.%d" % os.getpid()
+            cmd = [nvcc, *NVCC_FLAGS, "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-shared", "-o", tmp,
+                   *[os.path.join(CSRC, f) for f in SOURCES]]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            cmd[1:1] = os.environ.get("VQ_NVCC_EXTRA", "").split()
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+            if verbose:
+                print(r.stderr)
+            os.replace(tmp, LIB)
+            build_pyhost()
+            return LIB
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
 
 
 if __name__ == "__main__":
