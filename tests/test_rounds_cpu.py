@@ -4,8 +4,8 @@ TargetClip / Hyperparameter -> store, against the in-memory fake API, with the d
 conventions: fp32 scores, lists in database order, float64 labelled similarities).  It is test infrastructure: the
 product has no such path and fails without its CUDA library.  What it checks is everything around the kernels —
 store construction from API records, lazy score views, the weight update, target bootstrapping, selection, forced
-clips, persistence, the final report — for all seven scenarios, including the two recorded after the round's GPU
-budget was spent (F, G), whose GPU replay is still to come."""
+clips, persistence, the final report — for all seven scenarios (the GPU replays are tests/test_gpu_parity.py; the same
+double is the CPU side of tests/test_gpu_differential.py)."""
 import os
 import random
 import types
