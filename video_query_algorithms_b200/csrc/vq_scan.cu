@@ -639,8 +639,9 @@ void launch_generic_u(vq_store *s, const float *target_dev, const ScanArgs &a, i
 void launch_generic(vq_store *s, const float *target_dev, const ScanArgs &a, int grid, cudaStream_t st) {
     const int len4 = s->stream_len / 4;
     const char *force = getenv("VQ_SCAN_U");           // development override
-    // measured on 3 x 1024-float streams (B200): U = 8 / 12 / 16 -> 6.22 / 6.11 / 6.86 TB/s (a partial last chunk costs less
-    // than fewer loads in flight); short streams keep 8
+    // measured on B200, 8 GB shards (tools/scan_shapes_probe.py), streams of 1 / 2 / 3 x 1024 floats: U = 8 -> 7.02 / 6.21 / 6.23,
+    // U = 12 -> 6.79 / 6.06 / 6.13, U = 16 -> 7.05 / 6.87 / 7.19 TB/s (a partial last chunk costs less than fewer loads in
+    // flight); short streams keep 8
     const int u = force ? atoi(force) : (len4 >= 512 ? 16 : 8);
     if (u == 12) launch_generic_u<12>(s, target_dev, a, grid, st);
     else if (u == 16) launch_generic_u<16>(s, target_dev, a, grid, st);
